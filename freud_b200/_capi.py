@@ -1,0 +1,340 @@
+"""ctypes binding of ``libfreud_b200.so`` (the C ABI declared in ``include/freud_b200.h``).
+
+This is the only way Python reaches the GPU path; there is no fallback.  Importing the module never needs a
+GPU, loading the library needs the built ``.so`` (``python -c "import __graft_entry__ as g; g.build()"``), and
+creating a :class:`Context` needs a CUDA device -- each failure is raised, never papered over.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfreud_b200.so")
+
+FLAVOUR_WRAP, FLAVOUR_IMAGE = 0, 1
+UNIQUE_ID_BYTES = 128
+
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+_vpp = C.POINTER(C.c_void_p)
+
+# every symbol include/freud_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "fgpu_last_error": (C.c_char_p, []),
+    "fgpu_version": (C.c_char_p, []),
+    "fgpu_device_count": (C.c_int, []),
+    "fgpu_ctx_create": (C.c_int, [C.c_int, _vpp]),
+    "fgpu_ctx_destroy": (None, [_vp]),
+    "fgpu_ctx_synchronize": (C.c_int, [_vp]),
+    "fgpu_ctx_stream": (_vp, [_vp]),
+    "fgpu_ctx_launch_count": (C.c_uint64, [_vp]),
+    "fgpu_ctx_count_pair_evals": (C.c_int, [_vp, C.c_int]),
+    "fgpu_ctx_pair_evals": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
+    "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
+    "fgpu_points_destroy": (None, [_vp]),
+    "fgpu_points_build_cells": (C.c_int, [_vp, C.c_float, _up]),
+    "fgpu_points_read_cells": (C.c_int, [_vp, _up, _up]),
+    "fgpu_ball_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                  _vpp]),
+    "fgpu_ball_query_dev": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int,
+                                      C.c_int, _vpp]),
+    "fgpu_knn_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_int,
+                                 _vpp]),
+    "fgpu_nlist_num_bonds": (C.c_uint64, [_vp]),
+    "fgpu_nlist_num_query_points": (C.c_uint32, [_vp]),
+    "fgpu_nlist_num_points": (C.c_uint32, [_vp]),
+    "fgpu_nlist_copy": (C.c_int, [_vp, _up, _fp, _fp, _fp, _up, _up]),
+    "fgpu_nlist_from_host": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, _up, _fp, _fp, _fp, _vpp]),
+    "fgpu_nlist_destroy": (None, [_vp]),
+    "fgpu_rdf_create": (C.c_int, [_vp, C.c_uint32, C.c_float, C.c_float, _vpp]),
+    "fgpu_rdf_destroy": (None, [_vp]),
+    "fgpu_rdf_reset": (C.c_int, [_vp]),
+    "fgpu_rdf_accumulate": (C.c_int, [_vp, _vp, _fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int]),
+    "fgpu_rdf_accumulate_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float,
+                                          C.c_int]),
+    "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
+    "fgpu_rdf_read": (C.c_int, [_vp, _up]),
+    "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
+    "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp]),
+    "fgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "fgpu_comm_create": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, _vpp]),
+    "fgpu_comm_destroy": (None, [_vp]),
+    "fgpu_comm_rank": (C.c_int, [_vp]),
+    "fgpu_comm_size": (C.c_int, [_vp]),
+    "fgpu_comm_barrier": (C.c_int, [_vp]),
+    "fgpu_comm_allreduce_u32": (C.c_int, [_vp, _up, C.c_uint64]),
+    "fgpu_comm_allreduce_f64": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_uint64]),
+}
+
+_lib = None
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+_CODE_TO_EXC = {-1: ValueError, -2: ValueError, -3: RuntimeError, -4: GpuError, -5: GpuError, -6: MemoryError}
+
+
+def lib():
+    """Load libfreud_b200.so and bind every declared symbol; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpuError(f"{LIB_PATH} is missing: build it with `make -C freud_b200/csrc` "
+                           "(or __graft_entry__.build()); freud_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise _CODE_TO_EXC.get(rc, RuntimeError)(lib().fgpu_last_error().decode())
+
+
+def f32(a, last=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(-1, last) if last else a
+
+
+def ptr(a, t=_fp):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def box6_of(box):
+    if hasattr(box, "as_array6"):
+        return box.as_array6(), bool(box.is2D)
+    from .box import Box
+
+    b = Box.from_box(box)
+    return b.as_array6(), bool(b.is2D)
+
+
+class Context:
+    """One GPU + one stream + scratch memory (``fgpu_ctx``)."""
+
+    _default = {}
+
+    def __init__(self, device=0):
+        self._h = _vp()
+        check(lib().fgpu_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    @classmethod
+    def default(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) % max(1, lib().fgpu_device_count())
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def synchronize(self):
+        check(lib().fgpu_ctx_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return lib().fgpu_ctx_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().fgpu_ctx_launch_count(self._h))
+
+    def count_pair_evals(self, enable=True):
+        check(lib().fgpu_ctx_count_pair_evals(self._h, int(enable)))
+
+    def pair_evals(self, reset=True):
+        out = C.c_uint64()
+        check(lib().fgpu_ctx_pair_evals(self._h, C.byref(out), int(reset)))
+        return int(out.value)
+
+    def close(self):
+        if self._h:
+            lib().fgpu_ctx_destroy(self._h)
+            self._h = _vp()
+
+
+class DeviceNeighborList:
+    """Device-resident NeighborList (``fgpu_nlist``); arrays come to the host on demand."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._h = handle
+        L = lib()
+        self.num_bonds = int(L.fgpu_nlist_num_bonds(handle))
+        self.num_query_points = int(L.fgpu_nlist_num_query_points(handle))
+        self.num_points = int(L.fgpu_nlist_num_points(handle))
+
+    def to_host(self, into=None):
+        nb, nq = self.num_bonds, self.num_query_points
+        out = into or dict(neighbors=np.empty((nb, 2), np.uint32), distances=np.empty(nb, np.float32),
+                           weights=np.empty(nb, np.float32), vectors=np.empty((nb, 3), np.float32),
+                           segments=np.empty(nq, np.uint32), counts=np.empty(nq, np.uint32))
+        check(lib().fgpu_nlist_copy(self._h, ptr(out["neighbors"], _up), ptr(out["distances"]), ptr(out["weights"]),
+                                    ptr(out["vectors"]), ptr(out["segments"], _up), ptr(out["counts"], _up)))
+        return out
+
+    @classmethod
+    def from_host(cls, ctx, neighbors, distances, weights, vectors, n_query, n_points):
+        nbr = np.ascontiguousarray(neighbors, dtype=np.uint32).reshape(-1, 2)
+        d = f32(distances)
+        w = f32(weights) if weights is not None else None
+        v = f32(vectors, 3) if vectors is not None else None
+        h = _vp()
+        check(lib().fgpu_nlist_from_host(ctx._h, len(d), int(n_query), int(n_points), ptr(nbr, _up), ptr(d), ptr(w),
+                                         ptr(v), C.byref(h)))
+        return cls(ctx, h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().fgpu_nlist_destroy(self._h)
+            self._h = None
+
+
+class DevicePoints:
+    """Device-resident reference points + box + cell list (``fgpu_points``)."""
+
+    def __init__(self, ctx, box, points):
+        self.ctx = ctx
+        self.box6, self.is2d = box6_of(box)
+        pts = f32(points, 3)
+        self.n = len(pts)
+        self._h = _vp()
+        check(lib().fgpu_points_create(ctx._h, ptr(self.box6), int(self.is2d), ptr(pts), self.n, C.byref(self._h)))
+
+    def build_cells(self, r_search):
+        dims = np.zeros(3, np.uint32)
+        check(lib().fgpu_points_build_cells(self._h, float(r_search), ptr(dims, _up)))
+        return dims
+
+    def read_cells(self, dims):
+        n_cells = int(np.prod(dims))
+        cell_start = np.zeros(n_cells + 1, np.uint32)
+        order = np.zeros(self.n, np.uint32)
+        check(lib().fgpu_points_read_cells(self._h, ptr(cell_start, _up), ptr(order, _up)))
+        return cell_start, order
+
+    def ball_query(self, query_points, flavour, r_max, r_min=0.0, exclude_ii=False, sort_by_distance=False,
+                   q_index_offset=0):
+        q = None if query_points is None else f32(query_points, 3)
+        nq = self.n if q is None else len(q)
+        h = _vp()
+        check(lib().fgpu_ball_query(self._h, ptr(q), nq, int(q_index_offset), int(flavour), float(r_max), float(r_min),
+                                    int(bool(exclude_ii)), int(bool(sort_by_distance)), C.byref(h)))
+        return DeviceNeighborList(self.ctx, h)
+
+    def knn_query(self, query_points, num_neighbors, r_max=np.inf, r_min=0.0, exclude_ii=False,
+                  sort_by_distance=False, q_index_offset=0):
+        q = None if query_points is None else f32(query_points, 3)
+        nq = self.n if q is None else len(q)
+        h = _vp()
+        check(lib().fgpu_knn_query(self._h, ptr(q), nq, int(q_index_offset), int(num_neighbors), float(r_max),
+                                   float(r_min), int(bool(exclude_ii)), int(bool(sort_by_distance)), C.byref(h)))
+        return DeviceNeighborList(self.ctx, h)
+
+    def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0):
+        ls = np.atleast_1d(np.asarray(ls, dtype=np.uint32)).copy()
+        n = nlist.num_query_points
+        tot_m = int(sum(2 * int(l) + 1 for l in ls))
+        ql = np.empty((n, len(ls)), np.float32)
+        qlm = np.empty(n * tot_m * 2, np.float32) if want_qlm else None
+        sys_qlm = np.empty(tot_m * 2, np.float32)
+        order = np.empty(len(ls), np.float32)
+        check(lib().fgpu_steinhardt_compute(self._h, nlist._h, ptr(ls, _up), len(ls), int(bool(weighted)), int(n_total),
+                                            comm._h if comm is not None else None, ptr(ql), ptr(qlm), ptr(sys_qlm),
+                                            ptr(order)))
+        out_qlm, out_sys, off, soff = [], [], 0, 0
+        for l in ls:
+            nm = 2 * int(l) + 1
+            if want_qlm:
+                blk = qlm[off:off + n * nm * 2].reshape(n, nm, 2)
+                out_qlm.append(blk.view(np.complex64).reshape(n, nm))
+                off += n * nm * 2
+            out_sys.append(sys_qlm[soff:soff + 2 * nm].view(np.complex64))
+            soff += 2 * nm
+        return dict(ql=ql, qlm=out_qlm, sys_qlm=out_sys, order=order)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().fgpu_points_destroy(self._h)
+            self._h = None
+
+
+class DeviceRDF:
+    """Device-resident RDF histogram (``fgpu_rdf``)."""
+
+    def __init__(self, ctx, bins, r_max, r_min=0.0):
+        self.ctx = ctx
+        self.bins = int(bins)
+        self._h = _vp()
+        check(lib().fgpu_rdf_create(ctx._h, self.bins, float(r_max), float(r_min), C.byref(self._h)))
+
+    def reset(self):
+        check(lib().fgpu_rdf_reset(self._h))
+
+    def accumulate(self, points, query_points, flavour, r_max, r_min=0.0, exclude_ii=False, q_index_offset=0):
+        q = None if query_points is None else f32(query_points, 3)
+        nq = points.n if q is None else len(q)
+        check(lib().fgpu_rdf_accumulate(self._h, points._h, ptr(q), nq, int(q_index_offset), int(flavour),
+                                        float(r_max), float(r_min), int(bool(exclude_ii))))
+
+    def accumulate_nlist(self, nlist):
+        check(lib().fgpu_rdf_accumulate_nlist(self._h, nlist._h))
+
+    def read(self):
+        counts = np.empty(self.bins, np.uint32)
+        check(lib().fgpu_rdf_read(self._h, ptr(counts, _up)))
+        return counts
+
+    def allreduce(self, comm):
+        check(lib().fgpu_rdf_allreduce(self._h, comm._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().fgpu_rdf_destroy(self._h)
+            self._h = None
+
+
+class Communicator:
+    """NCCL communicator, one rank per process (``fgpu_comm``)."""
+
+    def __init__(self, ctx, unique_id, rank, size):
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert len(uid) == UNIQUE_ID_BYTES
+        self.ctx = ctx
+        self._h = _vp()
+        check(lib().fgpu_comm_create(ctx._h, uid.ctypes.data_as(C.POINTER(C.c_uint8)), int(rank), int(size),
+                                     C.byref(self._h)))
+        self.rank, self.size = int(rank), int(size)
+
+    @staticmethod
+    def unique_id():
+        uid = np.zeros(UNIQUE_ID_BYTES, np.uint8)
+        check(lib().fgpu_comm_unique_id(uid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return uid.tobytes()
+
+    def barrier(self):
+        check(lib().fgpu_comm_barrier(self._h))
+
+    def allreduce_u32(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.uint32)
+        check(lib().fgpu_comm_allreduce_u32(self._h, ptr(a, _up), a.size))
+        return a
+
+    def allreduce_f64(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        check(lib().fgpu_comm_allreduce_f64(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), a.size))
+        return a
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fgpu_comm_destroy(self._h)
+            self._h = None

@@ -1,0 +1,1191 @@
+// C ABI of libfreud_b200.so (declared in include/freud_b200.h): argument validation with the reference's
+// error behaviour, memory management, and the kernel sequences of each entry point.
+#include <dlfcn.h>
+#include <nccl.h> // types and enums only; the library is loaded with dlopen at run time
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+
+#include "internal.h"
+
+namespace fgpu {
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+void set_last_error(const std::string& msg)
+{
+    g_last_error = msg;
+}
+
+namespace {
+
+template<typename F> int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return FGPU_OK;
+    }
+    catch (const Error& e)
+    {
+        set_last_error(e.what());
+        return e.code;
+    }
+    catch (const std::bad_alloc&)
+    {
+        set_last_error("out of host memory");
+        return FGPU_ENOMEM;
+    }
+    catch (const std::exception& e)
+    {
+        set_last_error(e.what());
+        return FGPU_ERUNTIME;
+    }
+}
+
+void require(bool cond, int code, const char* msg)
+{
+    if (!cond)
+    {
+        throw Error(code, msg);
+    }
+}
+
+// host float arithmetic that must not be contracted (this file is compiled with -ffp-contract=off)
+BoxDev make_box(const float* b6, int is2d)
+{
+    BoxDev b;
+    b.is2d = is2d != 0 ? 1 : 0;
+    b.Lx = b6[0];
+    b.Ly = b6[1];
+    b.Lz = b.is2d ? 0.0f : b6[2]; // Box.h:102-106
+    b.xy = b6[3];
+    b.xz = b6[4];
+    b.yz = b6[5];
+    volatile float half = 1.0f / 2.0f; // m_hi = m_L / 2.0f multiplies by the reciprocal, VectorMath.h:208-212
+    volatile float hx = b.Lx * half, hy = b.Ly * half, hz = b.Lz * half;
+    b.lox = -hx;
+    b.loy = -hy;
+    b.loz = -hz;
+    volatile float t = b.yz * b.xy;
+    volatile float t_xz = b.xz - t; // Box.h:246
+    b.t_xz = t_xz;
+    // lattice vectors, Box.h:503-518
+    volatile float bx = b.Ly * b.xy, cx = b.Lz * b.xz, cy = b.Lz * b.yz;
+    b.ax = b.Lx;
+    b.bx = bx;
+    b.by = b.Ly;
+    b.cx = b.is2d ? 0.0f : cx;
+    b.cy = b.is2d ? 0.0f : cy;
+    b.cz = b.is2d ? 0.0f : b.Lz;
+    return b;
+}
+
+// Box::getNearestPlaneDistance, Box.h:489-497
+void plane_distances(const BoxDev& b, float out[3])
+{
+    volatile float t0 = b.xy * b.yz;
+    volatile float t = t0 - b.xz;
+    volatile float a0 = b.xy * b.xy;
+    volatile float a1 = 1.0f + a0;
+    volatile float a2 = t * t;
+    volatile float a3 = a1 + a2;
+    out[0] = b.Lx / std::sqrt((float) a3);
+    volatile float c0 = b.yz * b.yz;
+    volatile float c1 = 1.0f + c0;
+    out[1] = b.Ly / std::sqrt((float) c1);
+    out[2] = b.Lz;
+}
+
+float box_volume(const BoxDev& b)
+{
+    volatile float a = b.Lx * b.Ly;
+    if (b.is2d)
+    {
+        return a;
+    }
+    volatile float v = a * b.Lz;
+    return v;
+}
+
+void h2d(fgpu_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes != 0)
+    {
+        FGPU_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+}
+
+void d2h(fgpu_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes != 0)
+    {
+        FGPU_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+}
+
+void sync(fgpu_ctx* ctx)
+{
+    FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void bind_device(fgpu_ctx* ctx)
+{
+    FGPU_CUDA_CHECK(cudaSetDevice(ctx->device));
+}
+
+struct QueryView
+{
+    const float4* sorted; // cell-ordered, w = original index
+    const float* xyz;     // original order
+};
+
+// Stage the query points (if any) and produce their cell-ordered view on the grid of pts.
+QueryView prepare_queries(fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query)
+{
+    fgpu_ctx* ctx = pts->ctx;
+    QueryView v;
+    if (q_host == nullptr && q_dev == nullptr)
+    {
+        v.sorted = pts->grid.sorted.ptr;
+        v.xyz = pts->xyz.ptr;
+        return v;
+    }
+    if (q_host != nullptr)
+    {
+        ctx->q_stage.reserve((size_t) n_query * 3);
+        h2d(ctx, ctx->q_stage.ptr, q_host, (size_t) n_query * 3 * sizeof(float));
+        q_dev = ctx->q_stage.ptr;
+    }
+    sort_queries(pts, q_dev, n_query);
+    v.sorted = ctx->q_sorted.ptr;
+    v.xyz = q_dev;
+    return v;
+}
+
+void validate_ball(const fgpu_points* pts, int flavour, float r_max, float r_min)
+{
+    require(flavour == FGPU_FLAVOUR_WRAP || flavour == FGPU_FLAVOUR_IMAGE, FGPU_EINVALID, "unknown flavour");
+    // NeighborQueryPerPointIterator ctor, NeighborQuery.h:321-328
+    require(r_max > 0, FGPU_EINVALID, "NeighborQuery requires r_max to be positive.");
+    require(r_max > r_min, FGPU_EINVALID, "NeighborQuery requires that r_max must be greater than r_min.");
+    if (flavour == FGPU_FLAVOUR_IMAGE)
+    {
+        // updateImageVectors, NeighborQuery.h:503-510 (all axes periodic)
+        double const two_r = (double) r_max * 2.0;
+        bool const too_large = pts->plane_dist[0] <= two_r || pts->plane_dist[1] <= two_r
+            || (!pts->box.is2d && pts->plane_dist[2] <= two_r);
+        require(!too_large, FGPU_ERUNTIME, "The AABBQuery r_max is too large for this box.");
+    }
+}
+
+SearchArgs base_search_args(fgpu_points* pts, const QueryView& qv, uint32_t n_query, uint32_t q_index_offset,
+                            float r_max, float r_min, int exclude_ii)
+{
+    SearchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.box = pts->box;
+    a.grid = grid_dev(pts);
+    a.q_sorted = qv.sorted;
+    a.n_query = n_query;
+    a.q_index_offset = q_index_offset;
+    a.r_max = r_max;
+    a.r_min = r_min;
+    a.exclude_ii = exclude_ii != 0;
+    a.evals = pts->ctx->count_evals ? pts->ctx->d_evals : nullptr;
+    return a;
+}
+
+std::unique_ptr<fgpu_nlist> new_nlist(fgpu_ctx* ctx, uint32_t n_query, uint32_t n_points)
+{
+    std::unique_ptr<fgpu_nlist> nl(new fgpu_nlist());
+    nl->ctx = ctx;
+    nl->n_query = n_query;
+    nl->n_points = n_points;
+    nl->row_start.reserve((size_t) n_query + 1);
+    nl->counts.reserve((size_t) n_query + 1);
+    nl->segments.reserve((size_t) n_query + 1);
+    return nl;
+}
+
+void alloc_bonds(fgpu_nlist* nl, uint64_t n_bonds)
+{
+    require(n_bonds <= 0xffffffffULL, FGPU_ERUNTIME, "NeighborList would exceed 2^32 - 1 bonds");
+    nl->n_bonds = n_bonds;
+    nl->neighbors.reserve(n_bonds * 2 + 2);
+    nl->distances.reserve(n_bonds + 1);
+    nl->weights.reserve(n_bonds + 1);
+    nl->vectors.reserve(n_bonds * 3 + 3);
+}
+
+// counts (ctx scratch, indexed by original query) -> nl->counts, nl->row_start (exclusive scan); returns total
+uint64_t finish_counts(fgpu_ctx* ctx, fgpu_nlist* nl, const uint32_t* counts_dev, unsigned long long* d_total)
+{
+    uint32_t const nq = nl->n_query;
+    FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->counts.ptr, counts_dev, (size_t) nq * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->row_start.ptr, counts_dev, (size_t) nq * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + nq, 0, sizeof(uint32_t), ctx->stream));
+    exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) nq + 1);
+    d2h(ctx, ctx->h_scalars, d_total, sizeof(unsigned long long));
+    sync(ctx);
+    return ctx->h_scalars[0];
+}
+
+void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query,
+                     uint32_t q_index_offset, int flavour, float r_max, float r_min, int exclude_ii,
+                     int sort_by_distance, fgpu_nlist** out)
+{
+    require(pts != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+    fgpu_ctx* ctx = pts->ctx;
+    bind_device(ctx);
+    validate_ball(pts, flavour, r_max, r_min);
+    bool const self = q_host == nullptr && q_dev == nullptr;
+    require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+    auto nl = new_nlist(ctx, n_query, pts->n);
+    if (n_query == 0)
+    {
+        alloc_bonds(nl.get(), 0);
+        *out = nl.release();
+        return;
+    }
+    build_grid(pts, r_max);
+    QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
+
+    ctx->row_counts.reserve((size_t) n_query + 1);
+    SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, r_max, r_min, exclude_ii);
+    a.sort_by_distance = sort_by_distance != 0;
+    a.row_counts = ctx->row_counts.ptr;
+    a.total = ctx->d_scalars;
+    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(unsigned long long), ctx->stream));
+    launch_search(ctx, flavour, SEARCH_COUNT, a);
+    uint64_t const n_bonds = finish_counts(ctx, nl.get(), ctx->row_counts.ptr, ctx->d_scalars);
+    alloc_bonds(nl.get(), n_bonds);
+    if (n_bonds != 0)
+    {
+        ctx->bag.reserve(n_bonds);
+        a.row_start = nl->row_start.ptr;
+        a.bag = ctx->bag.ptr;
+        a.evals = nullptr; // the second pass repeats the same evaluations; count them once
+        launch_search(ctx, flavour, SEARCH_FILL, a);
+        EmitArgs e;
+        e.box = pts->box;
+        e.sorted = pts->grid.sorted.ptr;
+        e.q_xyz = qv.xyz;
+        e.bag = ctx->bag.ptr;
+        e.row_start = nl->row_start.ptr;
+        e.n_bonds = n_bonds;
+        e.r_max = r_max;
+        e.r_min = r_min;
+        e.neighbors = nl->neighbors.ptr;
+        e.distances = nl->distances.ptr;
+        e.weights = nl->weights.ptr;
+        e.vectors = nl->vectors.ptr;
+        launch_emit(ctx, flavour, e);
+    }
+    launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
+    sync(ctx); // q_stage / bag are context scratch: the list must be complete before they are reused
+    *out = nl.release();
+}
+
+void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query,
+                         uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii)
+{
+    require(rdf != nullptr && pts != nullptr, FGPU_EINVALID, "null argument");
+    require(rdf->ctx == pts->ctx, FGPU_EINVALID, "rdf and points belong to different contexts");
+    fgpu_ctx* ctx = pts->ctx;
+    bind_device(ctx);
+    validate_ball(pts, flavour, q_r_max, q_r_min);
+    bool const self = q_host == nullptr && q_dev == nullptr;
+    require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+    if (n_query == 0)
+    {
+        return;
+    }
+    build_grid(pts, q_r_max);
+    QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
+    SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, q_r_max, q_r_min, exclude_ii);
+    a.axis = rdf->axis;
+    a.hist = rdf->hist.ptr;
+    launch_search(ctx, flavour, SEARCH_RDF, a);
+    if (q_host != nullptr)
+    {
+        sync(ctx); // the caller may reuse its host buffer / the staging buffer is context scratch
+    }
+}
+
+// ---- NCCL, loaded lazily -----------------------------------------------------------------------------
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+        = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names)
+        {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle != nullptr)
+            {
+                break;
+            }
+        }
+        if (api.handle == nullptr)
+        {
+            api.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString)
+        {
+            api.why = "libnccl.so.2 lacks a required symbol";
+            api.handle = nullptr;
+        }
+    });
+    return api;
+}
+
+void nccl_check(ncclResult_t r, const char* what)
+{
+    if (r != ncclSuccess)
+    {
+        throw Error(FGPU_ENCCL, std::string(what) + ": " + nccl().GetErrorString(r));
+    }
+}
+
+NcclApi& nccl_or_throw()
+{
+    NcclApi& api = nccl();
+    if (api.handle == nullptr)
+    {
+        throw Error(FGPU_ENCCL, api.why);
+    }
+    return api;
+}
+
+} // namespace
+
+int nccl_available(std::string* why)
+{
+    NcclApi& api = nccl();
+    if (api.handle == nullptr && why != nullptr)
+    {
+        *why = api.why;
+    }
+    return api.handle != nullptr;
+}
+
+} // namespace fgpu
+
+using namespace fgpu;
+
+extern "C" {
+
+const char* fgpu_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+int fgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* fgpu_version(void)
+{
+    static std::string text;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        text = "freud_b200 0.1 (sm_100a)";
+        int n = 0;
+        if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0)
+        {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, 0) == cudaSuccess)
+            {
+                char buf[256];
+                std::snprintf(buf, sizeof(buf), " on %s, %d SMs, cc %d.%d", prop.name, prop.multiProcessorCount,
+                              prop.major, prop.minor);
+                text += buf;
+            }
+        }
+        else
+        {
+            cudaGetLastError();
+            text += " (no CUDA device visible)";
+        }
+    });
+    return text.c_str();
+}
+
+// ---- context ---------------------------------------------------------------------------------------
+int fgpu_ctx_create(int device, fgpu_ctx** out)
+{
+    return guarded([&] {
+        require(out != nullptr, FGPU_EINVALID, "null argument");
+        int n = 0;
+        cudaError_t const err = cudaGetDeviceCount(&n);
+        if (err != cudaSuccess || n == 0)
+        {
+            cudaGetLastError();
+            throw Error(FGPU_ECUDA, "no CUDA device available: freud_b200 has no CPU fallback");
+        }
+        require(device >= 0 && device < n, FGPU_EINVALID, "device index out of range");
+        FGPU_CUDA_CHECK(cudaSetDevice(device));
+        std::unique_ptr<fgpu_ctx> ctx(new fgpu_ctx());
+        ctx->device = device;
+        FGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        FGPU_CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+        FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_scalars), 8 * sizeof(unsigned long long)));
+        FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_evals), sizeof(unsigned long long)));
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_evals, 0, sizeof(unsigned long long), ctx->stream));
+        FGPU_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 8 * sizeof(unsigned long long)));
+        FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        *out = ctx.release();
+    });
+}
+
+void fgpu_ctx_destroy(fgpu_ctx* ctx)
+{
+    if (ctx == nullptr)
+    {
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_scalars);
+    cudaFree(ctx->d_evals);
+    cudaFreeHost(ctx->h_scalars);
+    if (ctx->pinned_stage != nullptr)
+    {
+        cudaFreeHost(ctx->pinned_stage);
+    }
+    cudaStream_t const s = ctx->stream;
+    delete ctx; // frees the scratch buffers
+    cudaStreamDestroy(s);
+}
+
+int fgpu_ctx_synchronize(fgpu_ctx* ctx)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(ctx);
+        sync(ctx);
+    });
+}
+
+void* fgpu_ctx_stream(fgpu_ctx* ctx)
+{
+    return ctx != nullptr ? static_cast<void*>(ctx->stream) : nullptr;
+}
+
+uint64_t fgpu_ctx_launch_count(fgpu_ctx* ctx)
+{
+    return ctx != nullptr ? ctx->launches : 0;
+}
+
+int fgpu_ctx_count_pair_evals(fgpu_ctx* ctx, int enable)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        ctx->count_evals = enable != 0;
+    });
+}
+
+int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(ctx);
+        d2h(ctx, ctx->h_scalars + 1, ctx->d_evals, sizeof(unsigned long long));
+        if (reset)
+        {
+            FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_evals, 0, sizeof(unsigned long long), ctx->stream));
+        }
+        sync(ctx);
+        *out = ctx->h_scalars[1];
+    });
+}
+
+// ---- points ----------------------------------------------------------------------------------------
+static void points_create_impl(fgpu_ctx* ctx, const float* box6, int is2d, const float* host, const float* dev,
+                               uint32_t n, fgpu_points** out)
+{
+    require(ctx != nullptr && box6 != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+    // NeighborQuery ctor, NeighborQuery.h:97-100
+    require(n != 0, FGPU_EINVALID, "Cannot create a NeighborQuery with 0 particles.");
+    require(host != nullptr || dev != nullptr, FGPU_EINVALID, "null points");
+    bind_device(ctx);
+    std::unique_ptr<fgpu_points> p(new fgpu_points());
+    p->ctx = ctx;
+    p->box = make_box(box6, is2d);
+    require(p->box.Lx > 0 && p->box.Ly > 0 && (p->box.is2d || p->box.Lz > 0), FGPU_EINVALID,
+            "box lengths must be positive");
+    plane_distances(p->box, p->plane_dist);
+    p->n = n;
+    if (host != nullptr && p->box.is2d)
+    {
+        // NeighborQuery.h:103-112
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            require(!(std::fabs(host[3 * (size_t) i + 2]) > 1e-6), FGPU_EINVALID,
+                    "A point with z != 0 was provided in a 2D box.");
+        }
+    }
+    p->xyz.reserve((size_t) n * 3);
+    if (host != nullptr)
+    {
+        h2d(ctx, p->xyz.ptr, host, (size_t) n * 3 * sizeof(float));
+        sync(ctx); // the reference copies at construction; the caller may free its buffer right away
+    }
+    else
+    {
+        FGPU_CUDA_CHECK(cudaMemcpyAsync(p->xyz.ptr, dev, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+    }
+    *out = p.release();
+}
+
+int fgpu_points_create(fgpu_ctx* ctx, const float* box6, int is2d, const float* points_host, uint32_t n,
+                       fgpu_points** out)
+{
+    return guarded([&] { points_create_impl(ctx, box6, is2d, points_host, nullptr, n, out); });
+}
+
+int fgpu_points_create_dev(fgpu_ctx* ctx, const float* box6, int is2d, const float* points_dev, uint32_t n,
+                           fgpu_points** out)
+{
+    return guarded([&] { points_create_impl(ctx, box6, is2d, nullptr, points_dev, n, out); });
+}
+
+void fgpu_points_destroy(fgpu_points* pts)
+{
+    if (pts != nullptr)
+    {
+        cudaSetDevice(pts->ctx->device);
+        cudaStreamSynchronize(pts->ctx->stream);
+        delete pts;
+    }
+}
+
+int fgpu_points_build_cells(fgpu_points* pts, float r_search, uint32_t* out_dims)
+{
+    return guarded([&] {
+        require(pts != nullptr, FGPU_EINVALID, "null argument");
+        require(r_search > 0, FGPU_EINVALID, "r_search must be positive");
+        bind_device(pts->ctx);
+        pts->grid.r_search = -1.0f; // force a rebuild: this entry point exists to time/test the build
+        build_grid(pts, r_search);
+        if (out_dims != nullptr)
+        {
+            for (int d = 0; d < 3; ++d)
+            {
+                out_dims[d] = (uint32_t) pts->grid.dim[d];
+            }
+        }
+    });
+}
+
+int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host)
+{
+    return guarded([&] {
+        require(pts != nullptr, FGPU_EINVALID, "null argument");
+        require(pts->grid.r_search >= 0, FGPU_ERUNTIME, "cell list not built yet");
+        fgpu_ctx* ctx = pts->ctx;
+        bind_device(ctx);
+        if (cell_start_host != nullptr)
+        {
+            d2h(ctx, cell_start_host, pts->grid.cell_start.ptr, ((size_t) pts->grid.n_cells + 1) * sizeof(uint32_t));
+        }
+        std::vector<float4> tmp;
+        if (order_host != nullptr)
+        {
+            tmp.resize(pts->n);
+            d2h(ctx, tmp.data(), pts->grid.sorted.ptr, (size_t) pts->n * sizeof(float4));
+        }
+        sync(ctx);
+        if (order_host != nullptr)
+        {
+            for (uint32_t i = 0; i < pts->n; ++i)
+            {
+                std::memcpy(&order_host[i], &tmp[i].w, sizeof(uint32_t));
+            }
+        }
+    });
+}
+
+// ---- ball query --------------------------------------------------------------------------------------
+int fgpu_ball_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                    int flavour, float r_max, float r_min, int exclude_ii, int sort_by_distance, fgpu_nlist** out)
+{
+    return guarded([&] {
+        ball_query_impl(pts, query_points_host, nullptr, n_query, q_index_offset, flavour, r_max, r_min, exclude_ii,
+                        sort_by_distance, out);
+    });
+}
+
+int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_t n_query, uint32_t q_index_offset,
+                        int flavour, float r_max, float r_min, int exclude_ii, int sort_by_distance,
+                        fgpu_nlist** out)
+{
+    return guarded([&] {
+        ball_query_impl(pts, nullptr, query_points_dev, n_query, q_index_offset, flavour, r_max, r_min, exclude_ii,
+                        sort_by_distance, out);
+    });
+}
+
+// ---- kNN ---------------------------------------------------------------------------------------------
+int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                   uint32_t num_neighbors, float r_max, float r_min, int exclude_ii, int sort_by_distance,
+                   fgpu_nlist** out)
+{
+    return guarded([&] {
+        require(pts != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        fgpu_ctx* ctx = pts->ctx;
+        bind_device(ctx);
+        require(r_max > 0, FGPU_EINVALID, "NeighborQuery requires r_max to be positive.");
+        require(r_max > r_min, FGPU_EINVALID, "NeighborQuery requires that r_max must be greater than r_min.");
+        require(num_neighbors != 0xffffffffU, FGPU_ERUNTIME,
+                "You must set num_neighbors in the query arguments when performing number of neighbor queries.");
+        bool const self = query_points_host == nullptr;
+        require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        auto nl = new_nlist(ctx, n_query, pts->n);
+        uint32_t const k = std::min<uint32_t>(num_neighbors, pts->n);
+        if (n_query == 0 || k == 0)
+        {
+            alloc_bonds(nl.get(), 0);
+            if (n_query != 0)
+            {
+                FGPU_CUDA_CHECK(cudaMemsetAsync(nl->counts.ptr, 0, (size_t) n_query * sizeof(uint32_t), ctx->stream));
+                FGPU_CUDA_CHECK(
+                    cudaMemsetAsync(nl->row_start.ptr, 0, ((size_t) n_query + 1) * sizeof(uint32_t), ctx->stream));
+                FGPU_CUDA_CHECK(cudaMemsetAsync(nl->segments.ptr, 0, (size_t) n_query * sizeof(uint32_t), ctx->stream));
+                sync(ctx);
+            }
+            *out = nl.release();
+            return;
+        }
+        ctx->knn_d.reserve((size_t) n_query * k);
+        ctx->knn_s.reserve((size_t) n_query * k);
+        ctx->row_counts.reserve((size_t) n_query + 1);
+
+        // initial radius: the sphere expected to hold ~2k points at the mean density
+        // (the reference's own r_guess is the k-point sphere, NeighborQuery.h:251-253)
+        double const volume = box_volume(pts->box);
+        double const density = (double) pts->n / volume;
+        double r_search = pts->box.is2d ? std::sqrt(2.0 * (k + 1) / (M_PI * density))
+                                        : std::cbrt(3.0 * 2.0 * (k + 1) / (4.0 * M_PI * density));
+        QueryView qv;
+        uint64_t total = 0;
+        for (int attempt = 0;; ++attempt)
+        {
+            require(attempt < 64, FGPU_ERUNTIME, "kNN search did not converge");
+            float const r_grid = (float) std::min(r_search, (double) r_max * 1.0001);
+            build_grid(pts, r_grid);
+            const fgpu_grid& g = pts->grid;
+            bool const cover_all = g.dim[0] < 3 && g.dim[1] < 3 && (pts->box.is2d || g.dim[2] < 3);
+            qv = prepare_queries(pts, query_points_host, nullptr, n_query);
+            KnnArgs a;
+            std::memset(&a, 0, sizeof(a));
+            a.box = pts->box;
+            a.grid = grid_dev(pts);
+            a.q_sorted = qv.sorted;
+            a.n_query = n_query;
+            a.q_index_offset = q_index_offset;
+            a.k = k;
+            a.r_max = r_max;
+            a.r_min = r_min;
+            a.r_safe = r_grid;
+            a.exclude_ii = exclude_ii != 0;
+            a.cover_all = cover_all ? 1 : 0;
+            a.knn_d = ctx->knn_d.ptr;
+            a.knn_s = ctx->knn_s.ptr;
+            a.row_counts = ctx->row_counts.ptr;
+            a.unresolved = ctx->d_scalars + 2;
+            a.total = ctx->d_scalars + 3;
+            a.evals = ctx->count_evals ? ctx->d_evals : nullptr;
+            FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 2, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            launch_knn(ctx, a);
+            d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 2 * sizeof(unsigned long long));
+            sync(ctx);
+            if (ctx->h_scalars[2] == 0 || cover_all)
+            {
+                total = ctx->h_scalars[3];
+                break;
+            }
+            r_search = (double) r_grid * 1.5;
+        }
+        FGPU_CUDA_CHECK(cudaMemcpyAsync(ctx->d_scalars, ctx->d_scalars + 3, sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+        uint64_t const n_bonds = finish_counts(ctx, nl.get(), ctx->row_counts.ptr, ctx->d_scalars);
+        (void) total;
+        alloc_bonds(nl.get(), n_bonds);
+        if (n_bonds != 0)
+        {
+            KnnEmitArgs e;
+            e.box = pts->box;
+            e.sorted = pts->grid.sorted.ptr;
+            e.q_xyz = qv.xyz;
+            e.knn_d = ctx->knn_d.ptr;
+            e.knn_s = ctx->knn_s.ptr;
+            e.row_start = nl->row_start.ptr;
+            e.row_counts = nl->counts.ptr;
+            e.n_query = n_query;
+            e.k = k;
+            e.sort_by_distance = sort_by_distance != 0;
+            e.neighbors = nl->neighbors.ptr;
+            e.distances = nl->distances.ptr;
+            e.weights = nl->weights.ptr;
+            e.vectors = nl->vectors.ptr;
+            launch_knn_emit(ctx, e);
+        }
+        launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
+        sync(ctx);
+        *out = nl.release();
+    });
+}
+
+// ---- NeighborList -------------------------------------------------------------------------------------
+uint64_t fgpu_nlist_num_bonds(const fgpu_nlist* nl)
+{
+    return nl != nullptr ? nl->n_bonds : 0;
+}
+
+uint32_t fgpu_nlist_num_query_points(const fgpu_nlist* nl)
+{
+    return nl != nullptr ? nl->n_query : 0;
+}
+
+uint32_t fgpu_nlist_num_points(const fgpu_nlist* nl)
+{
+    return nl != nullptr ? nl->n_points : 0;
+}
+
+int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
+                    float* vectors_host, uint32_t* segments_host, uint32_t* counts_host)
+{
+    return guarded([&] {
+        require(nl != nullptr, FGPU_EINVALID, "null argument");
+        fgpu_ctx* ctx = nl->ctx;
+        bind_device(ctx);
+        size_t const nb = nl->n_bonds;
+        if (neighbors_host != nullptr)
+        {
+            d2h(ctx, neighbors_host, nl->neighbors.ptr, nb * 2 * sizeof(uint32_t));
+        }
+        if (distances_host != nullptr)
+        {
+            d2h(ctx, distances_host, nl->distances.ptr, nb * sizeof(float));
+        }
+        if (weights_host != nullptr)
+        {
+            d2h(ctx, weights_host, nl->weights.ptr, nb * sizeof(float));
+        }
+        if (vectors_host != nullptr)
+        {
+            d2h(ctx, vectors_host, nl->vectors.ptr, nb * 3 * sizeof(float));
+        }
+        if (segments_host != nullptr)
+        {
+            d2h(ctx, segments_host, nl->segments.ptr, (size_t) nl->n_query * sizeof(uint32_t));
+        }
+        if (counts_host != nullptr)
+        {
+            d2h(ctx, counts_host, nl->counts.ptr, (size_t) nl->n_query * sizeof(uint32_t));
+        }
+        sync(ctx);
+    });
+}
+
+int fgpu_nlist_from_host(fgpu_ctx* ctx, uint64_t n_bonds, uint32_t n_query, uint32_t n_points,
+                         const uint32_t* neighbors_host, const float* distances_host, const float* weights_host,
+                         const float* vectors_host, fgpu_nlist** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        require(n_bonds == 0 || (neighbors_host != nullptr && distances_host != nullptr), FGPU_EINVALID,
+                "neighbors and distances are required");
+        bind_device(ctx);
+        auto nl = new_nlist(ctx, n_query, n_points);
+        alloc_bonds(nl.get(), n_bonds);
+        // row structure on the host (the list is sorted by query index, NeighborList::validate)
+        std::vector<uint32_t> counts((size_t) n_query + 1, 0), row_start((size_t) n_query + 1, 0),
+            segments((size_t) n_query + 1, 0);
+        uint32_t last = 0;
+        for (uint64_t b = 0; b < n_bonds; ++b)
+        {
+            uint32_t const i = neighbors_host[2 * b];
+            require(i < n_query && neighbors_host[2 * b + 1] < n_points, FGPU_EINVALID,
+                    "NeighborList index out of range");
+            require(i >= last, FGPU_EINVALID, "NeighborList must be sorted by query point index");
+            last = i;
+            counts[i] += 1;
+        }
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < n_query; ++i)
+        {
+            row_start[i] = acc;
+            segments[i] = counts[i] != 0 ? acc : 0;
+            acc += counts[i];
+        }
+        row_start[n_query] = acc;
+        std::vector<float> ones;
+        h2d(ctx, nl->neighbors.ptr, neighbors_host, n_bonds * 2 * sizeof(uint32_t));
+        h2d(ctx, nl->distances.ptr, distances_host, n_bonds * sizeof(float));
+        if (weights_host == nullptr)
+        {
+            ones.assign(n_bonds, 1.0f);
+            weights_host = ones.data();
+        }
+        h2d(ctx, nl->weights.ptr, weights_host, n_bonds * sizeof(float));
+        if (vectors_host != nullptr)
+        {
+            h2d(ctx, nl->vectors.ptr, vectors_host, n_bonds * 3 * sizeof(float));
+        }
+        else if (n_bonds != 0)
+        {
+            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->vectors.ptr, 0, n_bonds * 3 * sizeof(float), ctx->stream));
+        }
+        h2d(ctx, nl->counts.ptr, counts.data(), (size_t) n_query * sizeof(uint32_t));
+        h2d(ctx, nl->row_start.ptr, row_start.data(), ((size_t) n_query + 1) * sizeof(uint32_t));
+        h2d(ctx, nl->segments.ptr, segments.data(), (size_t) n_query * sizeof(uint32_t));
+        sync(ctx);
+        *out = nl.release();
+    });
+}
+
+void fgpu_nlist_destroy(fgpu_nlist* nl)
+{
+    if (nl != nullptr)
+    {
+        cudaSetDevice(nl->ctx->device);
+        cudaStreamSynchronize(nl->ctx->stream);
+        delete nl;
+    }
+}
+
+// ---- RDF ----------------------------------------------------------------------------------------------
+int fgpu_rdf_create(fgpu_ctx* ctx, uint32_t bins, float r_max, float r_min, fgpu_rdf** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        // RDF::RDF, RDF.cc:27-42
+        require(bins != 0, FGPU_EINVALID, "RDF requires a nonzero number of bins.");
+        require(r_max > 0, FGPU_EINVALID, "RDF requires r_max to be positive.");
+        require(r_min >= 0, FGPU_EINVALID, "RDF requires r_min to be non-negative.");
+        require(r_max > r_min, FGPU_EINVALID, "RDF requires that r_max must be greater than r_min.");
+        bind_device(ctx);
+        std::unique_ptr<fgpu_rdf> r(new fgpu_rdf());
+        r->ctx = ctx;
+        // RegularAxis ctor, Histogram.h:126-138
+        volatile float span = r_max - r_min;
+        volatile float width = span / (float) bins;
+        volatile float inv = 1.0f / width;
+        r->axis.r_min = r_min;
+        r->axis.r_max = r_max;
+        r->axis.inv_width = inv;
+        r->axis.bins = bins;
+        r->hist.reserve(bins);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(r->hist.ptr, 0, (size_t) bins * sizeof(uint32_t), ctx->stream));
+        sync(ctx);
+        *out = r.release();
+    });
+}
+
+void fgpu_rdf_destroy(fgpu_rdf* rdf)
+{
+    if (rdf != nullptr)
+    {
+        cudaSetDevice(rdf->ctx->device);
+        cudaStreamSynchronize(rdf->ctx->stream);
+        delete rdf;
+    }
+}
+
+int fgpu_rdf_reset(fgpu_rdf* rdf)
+{
+    return guarded([&] {
+        require(rdf != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(rdf->ctx);
+        FGPU_CUDA_CHECK(
+            cudaMemsetAsync(rdf->hist.ptr, 0, (size_t) rdf->axis.bins * sizeof(uint32_t), rdf->ctx->stream));
+    });
+}
+
+int fgpu_rdf_accumulate(fgpu_rdf* rdf, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                        uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii)
+{
+    return guarded([&] {
+        rdf_accumulate_impl(rdf, pts, query_points_host, nullptr, n_query, q_index_offset, flavour, q_r_max, q_r_min,
+                            exclude_ii);
+    });
+}
+
+int fgpu_rdf_accumulate_dev(fgpu_rdf* rdf, fgpu_points* pts, const float* query_points_dev, uint32_t n_query,
+                            uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii)
+{
+    return guarded([&] {
+        rdf_accumulate_impl(rdf, pts, nullptr, query_points_dev, n_query, q_index_offset, flavour, q_r_max, q_r_min,
+                            exclude_ii);
+    });
+}
+
+int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl)
+{
+    return guarded([&] {
+        require(rdf != nullptr && nl != nullptr, FGPU_EINVALID, "null argument");
+        require(rdf->ctx == nl->ctx, FGPU_EINVALID, "rdf and nlist belong to different contexts");
+        bind_device(rdf->ctx);
+        launch_rdf_from_distances(rdf->ctx, nl->distances.ptr, nl->n_bonds, rdf->axis, rdf->hist.ptr);
+    });
+}
+
+int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host)
+{
+    return guarded([&] {
+        require(rdf != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(rdf->ctx);
+        d2h(rdf->ctx, counts_host, rdf->hist.ptr, (size_t) rdf->axis.bins * sizeof(uint32_t));
+        sync(rdf->ctx);
+    });
+}
+
+int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
+{
+    return guarded([&] {
+        require(rdf != nullptr && comm != nullptr, FGPU_EINVALID, "null argument");
+        require(rdf->ctx == comm->ctx, FGPU_EINVALID, "rdf and comm belong to different contexts");
+        bind_device(rdf->ctx);
+        NcclApi& api = nccl_or_throw();
+        nccl_check(api.AllReduce(rdf->hist.ptr, rdf->hist.ptr, rdf->axis.bins, ncclUint32, ncclSum,
+                                 static_cast<ncclComm_t>(comm->nccl_comm), rdf->ctx->stream),
+                   "ncclAllReduce(u32 histogram)");
+    });
+}
+
+// ---- Steinhardt ------------------------------------------------------------------------------------------
+int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int weighted,
+                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* qlm_host, float* sys_qlm_host,
+                            float* order_host)
+{
+    return guarded([&] {
+        require(pts != nullptr && nl != nullptr && ls != nullptr && n_ls != 0, FGPU_EINVALID, "null argument");
+        require(pts->ctx == nl->ctx, FGPU_EINVALID, "points and nlist belong to different contexts");
+        require(nl->n_points == pts->n, FGPU_EINVALID, "NeighborList was built for a different number of points");
+        require(nl->n_query <= pts->n, FGPU_EINVALID, "NeighborList has more rows than there are points");
+        fgpu_ctx* ctx = pts->ctx;
+        bind_device(ctx);
+        std::vector<uint32_t> lv(ls, ls + n_ls);
+        size_t tot_m = 0;
+        for (uint32_t l : lv)
+        {
+            tot_m += 2 * (size_t) l + 1;
+        }
+        uint32_t const n = nl->n_query; // rows held by this rank (== pts->n on a single GPU)
+        if (n_total == 0)
+        {
+            n_total = n;
+        }
+        DevBuf<float> d_ql, d_qlm;
+        DevBuf<double> d_sys;
+        d_ql.reserve((size_t) n * n_ls + 1);
+        bool const want_qlm = qlm_host != nullptr;
+        if (want_qlm)
+        {
+            d_qlm.reserve((size_t) n * tot_m * 2 + 2);
+        }
+        d_sys.reserve(tot_m * 2);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(d_sys.ptr, 0, tot_m * 2 * sizeof(double), ctx->stream));
+        SteinhardtArgs a;
+        a.box = pts->box;
+        a.xyz = pts->xyz.ptr;
+        a.n = n;
+        a.neighbors = nl->neighbors.ptr;
+        a.distances = nl->distances.ptr;
+        a.weights = nl->weights.ptr;
+        a.row_start = nl->row_start.ptr;
+        a.weighted = weighted != 0;
+        a.n_total = n_total;
+        a.ql = d_ql.ptr;
+        a.qlm = want_qlm ? d_qlm.ptr : nullptr;
+        a.sys_qlm = d_sys.ptr;
+        launch_steinhardt(ctx, a, lv);
+        if (comm != nullptr && comm->size > 1)
+        {
+            NcclApi& api = nccl_or_throw();
+            nccl_check(api.AllReduce(d_sys.ptr, d_sys.ptr, tot_m * 2, ncclFloat64, ncclSum,
+                                     static_cast<ncclComm_t>(comm->nccl_comm), ctx->stream),
+                       "ncclAllReduce(f64 system q_lm)");
+        }
+        std::vector<double> sys(tot_m * 2);
+        d2h(ctx, sys.data(), d_sys.ptr, tot_m * 2 * sizeof(double));
+        if (ql_host != nullptr)
+        {
+            d2h(ctx, ql_host, d_ql.ptr, (size_t) n * n_ls * sizeof(float));
+        }
+        if (want_qlm)
+        {
+            d2h(ctx, qlm_host, d_qlm.ptr, (size_t) n * tot_m * 2 * sizeof(float));
+        }
+        sync(ctx);
+        // system q_lm = sum_i q_lm(i) / N ; derive m < 0 ; normalizeSystem (Steinhardt.cc:291-327)
+        size_t off = 0;
+        for (uint32_t r = 0; r < n_ls; ++r)
+        {
+            uint32_t const l = lv[r];
+            double norm = 0.0;
+            for (uint32_t m = 0; m <= l; ++m)
+            {
+                sys[2 * (off + m)] /= (double) n_total;
+                sys[2 * (off + m) + 1] /= (double) n_total;
+            }
+            for (uint32_t m = 1; m <= l; ++m)
+            {
+                double const phase = (m & 1U) ? -1.0 : 1.0;
+                sys[2 * (off + l + m)] = phase * sys[2 * (off + m)];
+                sys[2 * (off + l + m) + 1] = -phase * sys[2 * (off + m) + 1];
+            }
+            for (uint32_t k = 0; k < 2 * l + 1; ++k)
+            {
+                double const re = sys[2 * (off + k)], im = sys[2 * (off + k) + 1];
+                norm += re * re + im * im;
+                if (sys_qlm_host != nullptr)
+                {
+                    sys_qlm_host[2 * (off + k)] = (float) re;
+                    sys_qlm_host[2 * (off + k) + 1] = (float) im;
+                }
+            }
+            if (order_host != nullptr)
+            {
+                order_host[r] = (float) std::sqrt(norm * (4.0 * M_PI / (2 * l + 1)));
+            }
+            off += 2 * (size_t) l + 1;
+        }
+    });
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------------------
+int fgpu_comm_unique_id(uint8_t* unique_id_out)
+{
+    return guarded([&] {
+        require(unique_id_out != nullptr, FGPU_EINVALID, "null argument");
+        static_assert(sizeof(ncclUniqueId) == FGPU_UNIQUE_ID_BYTES, "ncclUniqueId size");
+        NcclApi& api = nccl_or_throw();
+        ncclUniqueId id;
+        nccl_check(api.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(unique_id_out, &id, sizeof(id));
+    });
+}
+
+int fgpu_comm_create(fgpu_ctx* ctx, const uint8_t* unique_id, int rank, int n_ranks, fgpu_comm** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && unique_id != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        require(n_ranks >= 1 && rank >= 0 && rank < n_ranks, FGPU_EINVALID, "bad rank / size");
+        bind_device(ctx);
+        NcclApi& api = nccl_or_throw();
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof(id));
+        ncclComm_t c = nullptr;
+        nccl_check(api.CommInitRank(&c, n_ranks, id, rank), "ncclCommInitRank");
+        std::unique_ptr<fgpu_comm> comm(new fgpu_comm());
+        comm->ctx = ctx;
+        comm->nccl_comm = c;
+        comm->rank = rank;
+        comm->size = n_ranks;
+        *out = comm.release();
+    });
+}
+
+void fgpu_comm_destroy(fgpu_comm* comm)
+{
+    if (comm != nullptr)
+    {
+        cudaSetDevice(comm->ctx->device);
+        cudaStreamSynchronize(comm->ctx->stream);
+        if (comm->nccl_comm != nullptr && nccl().handle != nullptr)
+        {
+            nccl().CommDestroy(static_cast<ncclComm_t>(comm->nccl_comm));
+        }
+        delete comm;
+    }
+}
+
+int fgpu_comm_rank(const fgpu_comm* comm)
+{
+    return comm != nullptr ? comm->rank : 0;
+}
+
+int fgpu_comm_size(const fgpu_comm* comm)
+{
+    return comm != nullptr ? comm->size : 1;
+}
+
+static void allreduce_host(fgpu_comm* comm, void* host, uint64_t count, size_t elem, ncclDataType_t type)
+{
+    require(comm != nullptr && (host != nullptr || count == 0), FGPU_EINVALID, "null argument");
+    if (count == 0)
+    {
+        return;
+    }
+    fgpu_ctx* ctx = comm->ctx;
+    bind_device(ctx);
+    NcclApi& api = nccl_or_throw();
+    comm->stage.reserve(count * elem);
+    h2d(ctx, comm->stage.ptr, host, count * elem);
+    nccl_check(api.AllReduce(comm->stage.ptr, comm->stage.ptr, count, type, ncclSum,
+                             static_cast<ncclComm_t>(comm->nccl_comm), ctx->stream),
+               "ncclAllReduce");
+    d2h(ctx, host, comm->stage.ptr, count * elem);
+    sync(ctx);
+}
+
+int fgpu_comm_allreduce_u32(fgpu_comm* comm, uint32_t* host_inout, uint64_t count)
+{
+    return guarded([&] { allreduce_host(comm, host_inout, count, sizeof(uint32_t), ncclUint32); });
+}
+
+int fgpu_comm_allreduce_f64(fgpu_comm* comm, double* host_inout, uint64_t count)
+{
+    return guarded([&] { allreduce_host(comm, host_inout, count, sizeof(double), ncclFloat64); });
+}
+
+int fgpu_comm_barrier(fgpu_comm* comm)
+{
+    return guarded([&] {
+        uint32_t token = 1;
+        allreduce_host(comm, &token, 1, sizeof(uint32_t), ncclUint32);
+    });
+}
+
+} // extern "C"

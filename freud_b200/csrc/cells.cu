@@ -1,0 +1,309 @@
+// Periodic cell list: cell index + count, exclusive scan, scatter to cell-ordered float4.
+//
+// Replaces (with a different, GPU-shaped data structure) LinkCell::computeCellList
+// freud/locality/LinkCell.cc:316-336 / getCellCoord :356-367 and AABBQuery::buildTree
+// freud/locality/AABBQuery.cc:53-69.  The reference's structures only generate candidates; results are
+// decided by the per-pair arithmetic, so the grid here is free to use its own cell
+// width: the smallest width that is provably conservative for the query radius.
+//
+// Layout in HBM: cell_start u32[n_cells+1]; sorted float4[n] = {x, y, z, bits(point index)} grouped by
+// cell (x fastest, then y, then z), so the 3 x-neighbour cells of a (y, z) row are one contiguous run.
+// Algorithmic bytes: 12 (read xyz) + 16 (write float4) = 28 B/point, + 4 B/cell counters.
+#include <algorithm>
+#include <cmath>
+
+#include "internal.h"
+
+namespace fgpu {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// Per-tile exclusive scan; tile totals go to block_sums (if not null).
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* data, size_t n, uint32_t* block_sums)
+{
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    size_t const base = (size_t) blockIdx.x * kScanTile + (size_t) threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+    {
+        v[k] = base + k < n ? data[base + k] : 0U;
+        sum += v[k];
+    }
+    // inclusive warp scan of per-thread sums
+    uint32_t incl = sum;
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t const t = __shfl_up_sync(0xffffffffU, incl, o);
+        if (lane >= o)
+        {
+            incl += t;
+        }
+    }
+    if (lane == 31)
+    {
+        warp_sums[warp] = incl;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0U;
+#pragma unroll
+        for (int o = 1; o < kScanThreads / 32; o <<= 1)
+        {
+            uint32_t const t = __shfl_up_sync(0xffffffffU, w, o);
+            if (lane >= o)
+            {
+                w += t;
+            }
+        }
+        if (lane < kScanThreads / 32)
+        {
+            warp_sums[lane] = w; // inclusive over warps
+        }
+    }
+    __syncthreads();
+    uint32_t excl = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0U);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+    {
+        if (base + k < n)
+        {
+            data[base + k] = excl;
+        }
+        excl += v[k];
+    }
+    if (block_sums != nullptr && threadIdx.x == kScanThreads - 1)
+    {
+        block_sums[blockIdx.x] = excl;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* data, size_t n, const uint32_t* block_offsets)
+{
+    uint32_t const off = block_offsets[blockIdx.x];
+    size_t const base = (size_t) blockIdx.x * kScanTile + (size_t) threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+    {
+        if (base + k < n)
+        {
+            data[base + k] += off;
+        }
+    }
+}
+
+void scan_level(fgpu_ctx* ctx, uint32_t* data, size_t n, uint32_t* tmp)
+{
+    size_t const tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles <= 1)
+    {
+        k_scan_tiles<<<1, kScanThreads, 0, ctx->stream>>>(data, n, nullptr);
+        ctx->launches += 1;
+        return;
+    }
+    k_scan_tiles<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
+    ctx->launches += 1;
+    scan_level(ctx, tmp, tiles, tmp + tiles);
+    k_scan_add<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
+    ctx->launches += 1;
+}
+
+// K1: cell index + arrival rank (one atomic per point) -- 12 B read, 8 B written per point
+__global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
+                                                     uint32_t n, uint32_t* __restrict__ cell_of,
+                                                     uint32_t* __restrict__ rank_in, uint32_t* __restrict__ cell_count,
+                                                     int* __restrict__ any_shift)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
+    int cx, cy, cz, nx, ny, nz;
+    cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+    uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
+    cell_of[i] = c;
+    rank_in[i] = atomicAdd(&cell_count[c], 1U);
+    if ((nx | ny | nz) != 0)
+    {
+        *any_shift = 1;
+    }
+}
+
+// K3: scatter to cell order -- 20 B read, 16 (+4) B written per point
+__global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
+                                                      uint32_t n, const uint32_t* __restrict__ cell_of,
+                                                      const uint32_t* __restrict__ rank_in,
+                                                      const uint32_t* __restrict__ cell_start,
+                                                      float4* __restrict__ sorted, int* __restrict__ shift)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
+    uint32_t const slot = cell_start[cell_of[i]] + rank_in[i];
+    sorted[slot] = make_float4(x, y, z, __uint_as_float(i));
+    if (shift != nullptr)
+    {
+        int cx, cy, cz, nx, ny, nz;
+        cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+        shift[slot] = pack_shift(nx, ny, nz);
+    }
+}
+
+void choose_dims(const fgpu_points* pts, float r_search, bool force_single_cell, int dim[3], int ambiguous[3])
+{
+    double const lmax = std::max({(double) pts->box.Lx, (double) pts->box.Ly, (double) pts->box.Lz});
+    // cell thickness must exceed r_search by more than the float32 rounding of coordinates of size ~L
+    double const w = (double) r_search * (1.0 + 1.0e-4) + 1.0e-5 * lmax;
+    for (int d = 0; d < 3; ++d)
+    {
+        double const q = std::isfinite(w) && w > 0 ? (double) pts->plane_dist[d] / w : 1.0;
+        dim[d] = (int) std::max(1.0, std::min(std::floor(q), 1024.0 * 1024.0));
+    }
+    if (pts->box.is2d)
+    {
+        dim[2] = 1;
+    }
+    double const cap = 4.0 * (double) pts->n + 64.0;
+    while ((double) dim[0] * dim[1] * dim[2] > cap)
+    {
+        for (int d = 0; d < 3; ++d)
+        {
+            if (dim[d] > 1)
+            {
+                dim[d] = (dim[d] + 1) / 2;
+            }
+        }
+    }
+    if (force_single_cell)
+    {
+        dim[0] = dim[1] = dim[2] = 1;
+    }
+    for (int d = 0; d < 3; ++d)
+    {
+        ambiguous[d] = dim[d] < 3 ? 1 : 0;
+    }
+    if (pts->box.is2d)
+    {
+        ambiguous[2] = 0; // no z images in 2-D (NeighborQuery.h:519-521)
+    }
+}
+
+} // namespace
+
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n)
+{
+    if (n == 0)
+    {
+        return;
+    }
+    size_t tmp_need = 0;
+    for (size_t t = (n + kScanTile - 1) / kScanTile; t > 1; t = (t + kScanTile - 1) / kScanTile)
+    {
+        tmp_need += t;
+    }
+    ctx->scan_tmp.reserve(tmp_need + 1);
+    scan_level(ctx, data, n, ctx->scan_tmp.ptr);
+}
+
+GridDev grid_dev(const fgpu_points* pts)
+{
+    const fgpu_grid& g = pts->grid;
+    GridDev d;
+    d.dx = g.dim[0];
+    d.dy = g.dim[1];
+    d.dz = g.dim[2];
+    d.amb_x = g.ambiguous[0];
+    d.amb_y = g.ambiguous[1];
+    d.amb_z = g.ambiguous[2];
+    d.any_shift = g.any_shift ? 1 : 0;
+    d.cell_start = g.cell_start.ptr;
+    d.sorted = g.sorted.ptr;
+    d.shift = g.any_shift ? g.shift.ptr : nullptr;
+    return d;
+}
+
+void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
+{
+    fgpu_ctx* ctx = pts->ctx;
+    fgpu_grid& g = pts->grid;
+    int dim[3], amb[3];
+    choose_dims(pts, r_search, force_single_cell, dim, amb);
+    if (g.r_search >= 0 && dim[0] == g.dim[0] && dim[1] == g.dim[1] && dim[2] == g.dim[2])
+    {
+        g.r_search = std::max(g.r_search, r_search); // same grid already resident
+        return;
+    }
+    uint32_t const n = pts->n;
+    uint32_t const n_cells = (uint32_t) dim[0] * dim[1] * dim[2];
+    g.cell_of.reserve(n);
+    g.rank_in.reserve(n);
+    g.cell_start.reserve((size_t) n_cells + 1);
+    g.sorted.reserve(n);
+    FGPU_CUDA_CHECK(cudaMemsetAsync(g.cell_start.ptr, 0, ((size_t) n_cells + 1) * sizeof(uint32_t), ctx->stream));
+    int* d_flag = reinterpret_cast<int*>(ctx->d_scalars + 7);
+    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned const blocks = (n + 255) / 256;
+    k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_of.ptr,
+                                                   g.rank_in.ptr, g.cell_start.ptr, d_flag);
+    ctx->launches += 1;
+    exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1);
+    // the out-of-box flag decides whether the shift array is needed at all (it almost never is)
+    FGPU_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars + 7, d_flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    g.any_shift = ctx->h_scalars[7] != 0;
+    if (g.any_shift)
+    {
+        g.shift.reserve(n);
+    }
+    k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_of.ptr,
+                                                    g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
+                                                    g.any_shift ? g.shift.ptr : nullptr);
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+    for (int d = 0; d < 3; ++d)
+    {
+        g.dim[d] = dim[d];
+        g.ambiguous[d] = amb[d];
+    }
+    g.n_cells = n_cells;
+    g.r_search = r_search;
+}
+
+void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
+{
+    fgpu_ctx* ctx = pts->ctx;
+    const fgpu_grid& g = pts->grid;
+    ctx->q_cell.reserve(n_query);
+    ctx->q_rank.reserve(n_query);
+    ctx->q_cell_start.reserve((size_t) g.n_cells + 1);
+    ctx->q_sorted.reserve(n_query);
+    FGPU_CUDA_CHECK(
+        cudaMemsetAsync(ctx->q_cell_start.ptr, 0, ((size_t) g.n_cells + 1) * sizeof(uint32_t), ctx->stream));
+    int* d_flag = reinterpret_cast<int*>(ctx->d_scalars + 6); // unused result
+    unsigned const blocks = (n_query + 255) / 256;
+    k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
+                                                   ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr, d_flag);
+    ctx->launches += 1;
+    exclusive_scan_u32(ctx, ctx->q_cell_start.ptr, (size_t) g.n_cells + 1);
+    k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
+                                                    ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
+                                                    ctx->q_sorted.ptr, nullptr);
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace fgpu

@@ -1,0 +1,283 @@
+// Internal declarations shared by the translation units of libfreud_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/freud_b200.h"
+#include "pair_math.cuh"
+
+namespace fgpu {
+
+// ---- error plumbing ------------------------------------------------------------------------------
+struct Error : std::runtime_error
+{
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define FGPU_CUDA_CHECK(expr)                                                                                    \
+    do                                                                                                           \
+    {                                                                                                            \
+        cudaError_t const err__ = (expr);                                                                        \
+        if (err__ != cudaSuccess)                                                                                \
+        {                                                                                                        \
+            throw ::fgpu::Error(FGPU_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));              \
+        }                                                                                                        \
+    } while (0)
+
+// ---- device buffer (grow-only, stream-ordered use on the context's single stream) -----------------
+template<typename T> struct DevBuf
+{
+    T* ptr = nullptr;
+    size_t cap = 0; // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf()
+    {
+        release();
+    }
+    void release()
+    {
+        if (ptr != nullptr)
+        {
+            cudaFree(ptr);
+        }
+        ptr = nullptr;
+        cap = 0;
+    }
+    // contents are NOT preserved on growth
+    void reserve(size_t n)
+    {
+        if (n <= cap)
+        {
+            return;
+        }
+        release();
+        size_t const want = n + n / 8 + 64;
+        FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+        cap = want;
+    }
+};
+
+} // namespace fgpu
+
+// ---- opaque handle definitions ----------------------------------------------------------------------
+struct fgpu_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    bool count_evals = false;
+    unsigned long long* d_evals = nullptr; // device counter of pair evaluations
+    // scratch
+    fgpu::DevBuf<uint32_t> scan_tmp;
+    fgpu::DevBuf<float> q_stage;          // staged query points (H2D)
+    fgpu::DevBuf<uint32_t> q_cell;        // per query: cell index
+    fgpu::DevBuf<uint32_t> q_rank;        // per query: arrival rank inside its cell
+    fgpu::DevBuf<uint32_t> q_cell_start;  // per cell: start of the cell-ordered queries
+    fgpu::DevBuf<float4> q_sorted;        // cell-ordered query points, w = original query index
+    fgpu::DevBuf<uint32_t> row_counts;    // per query: number of bonds
+    fgpu::DevBuf<uint32_t> row_start;     // exclusive scan of row_counts (n_query + 1)
+    fgpu::DevBuf<uint4> bag;              // unsorted hits {key_hi, key_lo, slot, query}
+    fgpu::DevBuf<float> knn_d;            // kNN scratch, [k][n_query]
+    fgpu::DevBuf<uint32_t> knn_s;         // kNN scratch, [k][n_query] (slot | image code)
+    unsigned long long* d_scalars = nullptr; // 8 x u64 device scalars (totals, flags)
+    unsigned long long* h_scalars = nullptr; // pinned mirror
+    void* pinned_stage = nullptr;            // pinned staging for pageable H2D/D2H
+    size_t pinned_bytes = 0;
+};
+
+struct fgpu_grid
+{
+    float r_search = -1.0f; // radius the grid is conservative for (< 0: not built)
+    int dim[3] = {0, 0, 0};
+    uint32_t n_cells = 0;
+    int ambiguous[3] = {0, 0, 0}; // dim < 3 on a periodic axis: several images may map to one cell
+    bool any_shift = false;       // some point lies outside the box (integer image offset != 0)
+    fgpu::DevBuf<uint32_t> cell_of;    // per point
+    fgpu::DevBuf<uint32_t> rank_in;    // per point: arrival rank inside its cell
+    fgpu::DevBuf<uint32_t> cell_start; // n_cells + 1
+    fgpu::DevBuf<float4> sorted;       // cell-ordered positions, w = bit pattern of the point index
+    fgpu::DevBuf<int> shift;           // cell-ordered packed integer image offsets (10 bits per axis, biased)
+};
+
+struct fgpu_points
+{
+    fgpu_ctx* ctx = nullptr;
+    fgpu::BoxDev box;
+    float plane_dist[3];
+    uint32_t n = 0;
+    fgpu::DevBuf<float> xyz; // original order, n x 3
+    fgpu_grid grid;
+};
+
+struct fgpu_nlist
+{
+    fgpu_ctx* ctx = nullptr;
+    uint64_t n_bonds = 0;
+    uint32_t n_query = 0;
+    uint32_t n_points = 0;
+    fgpu::DevBuf<uint32_t> neighbors; // n_bonds x 2
+    fgpu::DevBuf<float> distances;
+    fgpu::DevBuf<float> weights;
+    fgpu::DevBuf<float> vectors;     // n_bonds x 3
+    fgpu::DevBuf<uint32_t> row_start; // n_query + 1 (exclusive scan; internal)
+    fgpu::DevBuf<uint32_t> counts;    // n_query
+    fgpu::DevBuf<uint32_t> segments;  // n_query (0 for empty rows, as upstream)
+};
+
+struct fgpu_rdf
+{
+    fgpu_ctx* ctx = nullptr;
+    fgpu::AxisDev axis;
+    fgpu::DevBuf<uint32_t> hist;
+};
+
+struct fgpu_comm
+{
+    fgpu_ctx* ctx = nullptr;
+    void* nccl_comm = nullptr;
+    int rank = 0;
+    int size = 1;
+    fgpu::DevBuf<unsigned char> stage;
+};
+
+namespace fgpu {
+
+// ---- launchers (one per kernel family; all enqueue on ctx->stream) ---------------------------------
+enum SearchMode
+{
+    SEARCH_COUNT = 0,
+    SEARCH_FILL = 1,
+    SEARCH_RDF = 2
+};
+
+struct GridDev
+{
+    int dx, dy, dz;
+    int amb_x, amb_y, amb_z;
+    int any_shift;
+    const uint32_t* cell_start;
+    const float4* sorted;
+    const int* shift;
+};
+
+struct SearchArgs
+{
+    BoxDev box;
+    GridDev grid;
+    const float4* q_sorted; // cell-ordered queries (w = original index)
+    uint32_t n_query;
+    uint32_t q_index_offset;
+    float r_max, r_min;
+    int exclude_ii;
+    int sort_by_distance;
+    // COUNT
+    uint32_t* row_counts;
+    unsigned long long* total; // u64 bond total (overflow detection)
+    // FILL
+    const uint32_t* row_start;
+    uint4* bag;
+    // RDF
+    AxisDev axis;
+    uint32_t* hist;
+    // instrumentation
+    unsigned long long* evals; // may be nullptr
+};
+
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n); // in place, n elements
+void build_grid(fgpu_points* pts, float r_search, bool force_single_cell = false);
+GridDev grid_dev(const fgpu_points* pts);
+// cell-sorts arbitrary query points with the grid of pts; result in ctx->q_sorted
+void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query);
+void launch_search(fgpu_ctx* ctx, int flavour, SearchMode mode, const SearchArgs& args);
+
+struct EmitArgs
+{
+    BoxDev box;
+    const float4* sorted;
+    const float* q_xyz; // original order n_query x 3
+    const uint4* bag;
+    const uint32_t* row_start;
+    uint64_t n_bonds;
+    float r_max, r_min;
+    uint32_t* neighbors;
+    float* distances;
+    float* weights;
+    float* vectors;
+};
+void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& args);
+void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* counts, uint32_t* segments,
+                     uint32_t n_query);
+
+struct KnnArgs
+{
+    BoxDev box;
+    GridDev grid;
+    const float4* q_sorted;
+    uint32_t n_query;
+    uint32_t q_index_offset;
+    uint32_t k;
+    float r_max, r_min;
+    float r_safe; // every point closer than this is inside the visited cells
+    int exclude_ii;
+    int cover_all; // grid visits every point with every image: nothing can be unresolved
+    float* knn_d;
+    uint32_t* knn_s;
+    uint32_t* row_counts;
+    unsigned long long* unresolved;
+    unsigned long long* total;
+    unsigned long long* evals;
+};
+void launch_knn(fgpu_ctx* ctx, const KnnArgs& args);
+
+struct KnnEmitArgs
+{
+    BoxDev box;
+    const float4* sorted;
+    const float* q_xyz;
+    const float* knn_d;
+    const uint32_t* knn_s;
+    const uint32_t* row_start;
+    const uint32_t* row_counts;
+    uint32_t n_query;
+    uint32_t k;
+    int sort_by_distance;
+    uint32_t* neighbors;
+    float* distances;
+    float* weights;
+    float* vectors;
+};
+void launch_knn_emit(fgpu_ctx* ctx, const KnnEmitArgs& args);
+
+void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
+
+struct SteinhardtArgs
+{
+    BoxDev box;
+    const float* xyz; // original order
+    uint32_t n;
+    const uint32_t* neighbors;
+    const float* distances;
+    const float* weights;
+    const uint32_t* row_start;
+    int weighted;
+    uint32_t n_total;
+    float* ql;       // n x n_ls
+    float* qlm;      // concatenated per l
+    double* sys_qlm; // concatenated per l, fp64 accumulators (re, im)
+};
+void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& args, const std::vector<uint32_t>& ls);
+
+// NCCL (loaded with dlopen)
+int nccl_available(std::string* why);
+
+} // namespace fgpu

@@ -1,0 +1,208 @@
+// Exact float32 pair arithmetic of the reference, for device code.
+//
+// The reference's x86-64 build is un-fused IEEE float32, so every operation that
+// feeds a value compared against r_max^2, binned, or written to a NeighborList goes through the
+// round-to-nearest intrinsics (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn), which nvcc never
+// contracts into FMAs, in exactly the reference's operation order:
+//   Box::makeFractional  freud/box/Box.h:243-255
+//   Box::makeAbsolute    freud/box/Box.h:212-222
+//   Box::wrap            freud/box/Box.h:307-329 with util::modulusPositive freud/util/utils.h:29-32
+//   dot(vec3, vec3)      freud/util/VectorMath.h:270-273   ((x*x + y*y) + z*z)
+//   image vectors        freud/locality/NeighborQuery.h:496-564
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fgpu {
+
+struct BoxDev
+{
+    float Lx, Ly, Lz;    // Lz == 0 in 2-D (Box.h:102-106)
+    float xy, xz, yz;    // tilt factors
+    float lox, loy, loz; // -(L * 0.5f)   (Box.h:113-114)
+    float t_xz;          // xz - yz * xy, the constant sub-expression of makeFractional (Box.h:246)
+    // lattice vectors (Box.h:503-518); c == 0 in 2-D (NeighborQuery.h:533-537)
+    float ax, bx, by, cx, cy, cz;
+    int is2d;
+};
+
+// fmodf(a, 1.0f) is exactly a - trunc(a) for every finite a (the subtraction is exact); the sign of a
+// zero result differs from fmodf only for a == -0.0f / negative integers, and modulusPositive adds 1.0f
+// right after, which erases it.
+__device__ __forceinline__ float modulus_positive_one(float a)
+{
+    float const t = __fsub_rn(a, truncf(a));
+    float const u = __fadd_rn(t, 1.0f);
+    return __fsub_rn(u, truncf(u));
+}
+
+__device__ __forceinline__ float dot_exact(float x, float y, float z)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// r = Box::wrap(v), all axes periodic.
+__device__ __forceinline__ void wrap_exact(const BoxDev& b, float vx, float vy, float vz, float& rx, float& ry,
+                                           float& rz)
+{
+    // makeFractional
+    float dx = __fsub_rn(vx, b.lox);
+    float dy = __fsub_rn(vy, b.loy);
+    float const dz = __fsub_rn(vz, b.loz);
+    dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(b.t_xz, vz), __fmul_rn(b.xy, vy)));
+    dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
+    float fx = __fdiv_rn(dx, b.Lx);
+    float fy = __fdiv_rn(dy, b.Ly);
+    float fz = b.is2d ? 0.0f : __fdiv_rn(dz, b.Lz); // 2-D: 0/0 -> NaN upstream, then forced to 0
+    // modulusPositive(f, 1)
+    fx = modulus_positive_one(fx);
+    fy = modulus_positive_one(fy);
+    fz = modulus_positive_one(fz);
+    // makeAbsolute
+    float x = __fadd_rn(b.lox, __fmul_rn(fx, b.Lx));
+    float y = __fadd_rn(b.loy, __fmul_rn(fy, b.Ly));
+    float z = __fadd_rn(b.loz, __fmul_rn(fz, b.Lz));
+    x = __fadd_rn(x, __fadd_rn(__fmul_rn(b.xy, y), __fmul_rn(b.xz, z)));
+    y = __fadd_rn(y, __fmul_rn(b.yz, z));
+    if (b.is2d)
+    {
+        z = 0.0f;
+    }
+    rx = x;
+    ry = y;
+    rz = z;
+}
+
+// image vector float(i)*a + float(j)*b + float(k)*c, component-wise, left to right
+__device__ __forceinline__ void image_vector(const BoxDev& b, int i, int j, int k, float& ix, float& iy, float& iz)
+{
+    float const fi = (float) i, fj = (float) j, fk = (float) k;
+    ix = __fadd_rn(__fadd_rn(__fmul_rn(fi, b.ax), __fmul_rn(fj, b.bx)), __fmul_rn(fk, b.cx));
+    iy = __fadd_rn(__fadd_rn(__fmul_rn(fi, 0.0f), __fmul_rn(fj, b.by)), __fmul_rn(fk, b.cy));
+    iz = __fadd_rn(__fadd_rn(__fmul_rn(fi, 0.0f), __fmul_rn(fj, 0.0f)), __fmul_rn(fk, b.cz));
+}
+
+// Fractional coordinates for CELL ASSIGNMENT only (candidate generation is conservative);
+// any consistent arithmetic works, the cell width carries a margin for its rounding.
+__device__ __forceinline__ void fractional_for_cells(const BoxDev& b, float vx, float vy, float vz, float& fx,
+                                                     float& fy, float& fz)
+{
+    float dx = vx - b.lox;
+    float dy = vy - b.loy;
+    float const dz = vz - b.loz;
+    dx -= b.t_xz * vz + b.xy * vy;
+    dy -= b.yz * vz;
+    fx = dx / b.Lx;
+    fy = dy / b.Ly;
+    fz = b.is2d ? 0.0f : dz / b.Lz;
+}
+
+// Cell coordinate of a point: frac - floor(frac) scaled to the grid; integer image offset = floor(frac).
+__device__ __forceinline__ void cell_coords(const BoxDev& b, int dx, int dy, int dz, float x, float y, float z,
+                                            int& cx, int& cy, int& cz, int& nx, int& ny, int& nz)
+{
+    float fx, fy, fz;
+    fractional_for_cells(b, x, y, z, fx, fy, fz);
+    float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    // NaN / far-away guard: such points cannot be neighbours of anything in range
+    if (!(fabsf(flx) < 500.0f))
+    {
+        flx = 0.0f;
+    }
+    if (!(fabsf(fly) < 500.0f))
+    {
+        fly = 0.0f;
+    }
+    if (!(fabsf(flz) < 500.0f))
+    {
+        flz = 0.0f;
+    }
+    cx = min(max((int) ((fx - flx) * (float) dx), 0), dx - 1);
+    cy = min(max((int) ((fy - fly) * (float) dy), 0), dy - 1);
+    cz = min(max((int) ((fz - flz) * (float) dz), 0), dz - 1);
+    nx = (int) flx;
+    ny = (int) fly;
+    nz = (int) flz;
+}
+
+// integer image offsets of a point, 10 bits per axis, biased by 512
+__device__ __forceinline__ int pack_shift(int nx, int ny, int nz)
+{
+    return ((nx + 512) & 1023) | (((ny + 512) & 1023) << 10) | (((nz + 512) & 1023) << 20);
+}
+
+__device__ __forceinline__ void unpack_shift(int packed, int& nx, int& ny, int& nz)
+{
+    nx = (packed & 1023) - 512;
+    ny = ((packed >> 10) & 1023) - 512;
+    nz = ((packed >> 20) & 1023) - 512;
+}
+
+// Per axis: the cells a query in home cell c must visit and, for each, how many times the periodic
+// boundary was crossed to reach it (w in {-1, 0, 1}; 2 == ambiguous: the axis has fewer than 3 cells, so
+// every image has to be tried on it).
+struct AxisSlots
+{
+    int n;
+    int cell[3];
+    int w[3];
+};
+
+__device__ __forceinline__ void make_slots(int dim, int ambiguous, int c, AxisSlots& s)
+{
+    if (dim >= 3)
+    {
+        s.n = 3;
+#pragma unroll
+        for (int o = -1; o <= 1; ++o)
+        {
+            int t = c + o;
+            int w = 0;
+            if (t < 0)
+            {
+                t += dim;
+                w = -1;
+            }
+            else if (t >= dim)
+            {
+                t -= dim;
+                w = 1;
+            }
+            s.cell[o + 1] = t;
+            s.w[o + 1] = w;
+        }
+    }
+    else
+    {
+        s.n = dim;
+        for (int t = 0; t < 3; ++t)
+        {
+            s.cell[t] = t < dim ? t : 0;
+            s.w[t] = ambiguous ? 2 : 0;
+        }
+    }
+}
+
+// RegularAxis::bin, freud/util/Histogram.h:152-174.  Returns -1 for the overflow bin.
+struct AxisDev
+{
+    float r_min, r_max, inv_width;
+    uint32_t bins;
+};
+
+__device__ __forceinline__ int axis_bin(const AxisDev& a, float value)
+{
+    if (value < a.r_min || value >= a.r_max)
+    {
+        return -1;
+    }
+    float const val = __fmul_rn(__fsub_rn(value, a.r_min), a.inv_width);
+    int bin = __float2int_rz(val); // truncation == _mm_cvtt_ss2si
+    if ((uint32_t) bin == a.bins)
+    {
+        bin -= 1;
+    }
+    return bin;
+}
+
+} // namespace fgpu

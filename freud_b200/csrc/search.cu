@@ -1,0 +1,475 @@
+// 27-cell minimum-image pair search: count / fill (NeighborList) / fused RDF histogram, plus the
+// NeighborList emit kernel.
+//
+// Replaces LinkCellQueryBallIterator::next (freud/locality/LinkCell.cc:496-573, flavour WRAP),
+// AABBQueryBallIterator::next (freud/locality/AABBQuery.cc:77-150, flavour IMAGE),
+// NeighborQueryIterator::toNeighborList (freud/locality/NeighborQuery.h:434-481) and the on-the-fly branch
+// of loopOverNeighbors + RDF's binning lambda (freud/locality/NeighborComputeFunctional.h:195-217,
+// freud/density/RDF.cc:101-110).
+//
+// Version 1 mapping: one thread per query point, queries visited in cell order so that the threads of a
+// warp walk the same few cells (L1-resident float4 candidates).  NeighborList build is
+//   count (per row) -> exclusive scan -> fill (unsorted 16-byte hit records per row) -> emit
+// where emit runs one thread per bond in OUTPUT order: it ranks its hit inside the row by counting smaller
+// keys, recomputes the bond with the exact arithmetic and writes all five arrays coalesced.
+#include "internal.h"
+
+namespace fgpu {
+
+namespace {
+
+constexpr int kSearchThreads = 128;
+
+__device__ __forceinline__ bool in_window(float r_sq, float r_max_sq, float r_min_sq)
+{
+    return r_sq < r_max_sq && r_sq >= r_min_sq; // LinkCell.cc:525, AABBQuery.cc:129
+}
+
+// Calls on_hit(slot, j, r_sq, rx, ry, rz) for every bond of one query point; returns pair evaluations.
+template<int FLAVOUR, typename OnHit>
+__device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev& g, float qx, float qy, float qz,
+                                               uint32_t q_global, int exclude_ii, float r_max_sq, float r_min_sq,
+                                               OnHit&& on_hit)
+{
+    uint32_t evals = 0;
+    if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
+    {
+        qz = 0.0f; // AABBQuery.cc:84-87
+    }
+    int cx, cy, cz, nqx, nqy, nqz;
+    cell_coords(box, g.dx, g.dy, g.dz, qx, qy, qz, cx, cy, cz, nqx, nqy, nqz);
+    AxisSlots sx, sy, sz;
+    make_slots(g.dx, g.amb_x, cx, sx);
+    make_slots(g.dy, g.amb_y, cy, sy);
+    make_slots(g.dz, g.amb_z, cz, sz);
+    for (int iz = 0; iz < sz.n; ++iz)
+    {
+        for (int iy = 0; iy < sy.n; ++iy)
+        {
+            uint32_t const row = ((uint32_t) sz.cell[iz] * g.dy + sy.cell[iy]) * g.dx;
+            for (int ix = 0; ix < sx.n; ++ix)
+            {
+                uint32_t const cell = row + sx.cell[ix];
+                uint32_t const beg = __ldg(g.cell_start + cell), end = __ldg(g.cell_start + cell + 1);
+                if (beg == end)
+                {
+                    continue;
+                }
+                int const wx = sx.w[ix], wy = sy.w[iy], wz = sz.w[iz];
+                if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+                {
+                    for (uint32_t s = beg; s < end; ++s)
+                    {
+                        float4 const p = __ldg(g.sorted + s);
+                        uint32_t const j = __float_as_uint(p.w);
+                        if (exclude_ii && j == q_global)
+                        {
+                            continue; // LinkCell.cc:517-520
+                        }
+                        ++evals;
+                        float rx, ry, rz;
+                        wrap_exact(box, __fsub_rn(p.x, qx), __fsub_rn(p.y, qy), __fsub_rn(p.z, qz), rx, ry, rz);
+                        float const r_sq = dot_exact(rx, ry, rz);
+                        if (in_window(r_sq, r_max_sq, r_min_sq))
+                        {
+                            on_hit(s, j, r_sq, rx, ry, rz);
+                        }
+                    }
+                }
+                else
+                {
+                    bool const definite = wx != 2 && wy != 2 && wz != 2 && !g.any_shift;
+                    if (definite)
+                    {
+                        // all points are inside the box: the image is fixed by how the cell was reached
+                        int const kx = -nqx - wx, ky = -nqy - wy, kz = -nqz - wz;
+                        if (kx < -1 || kx > 1 || ky < -1 || ky > 1 || kz < -1 || kz > 1)
+                        {
+                            continue;
+                        }
+                        float ix_, iy_, iz_;
+                        image_vector(box, kx, ky, kz, ix_, iy_, iz_);
+                        float const qix = __fadd_rn(qx, ix_), qiy = __fadd_rn(qy, iy_), qiz = __fadd_rn(qz, iz_);
+                        for (uint32_t s = beg; s < end; ++s)
+                        {
+                            float4 const p = __ldg(g.sorted + s);
+                            uint32_t const j = __float_as_uint(p.w);
+                            if (exclude_ii && j == q_global)
+                            {
+                                continue; // AABBQuery.cc:111-115
+                            }
+                            ++evals;
+                            float const pz = box.is2d ? 0.0f : p.z; // AABBQuery.cc:118-122
+                            float const rx = __fsub_rn(p.x, qix), ry = __fsub_rn(p.y, qiy), rz = __fsub_rn(pz, qiz);
+                            float const r_sq = dot_exact(rx, ry, rz);
+                            if (in_window(r_sq, r_max_sq, r_min_sq))
+                            {
+                                on_hit(s, j, r_sq, rx, ry, rz);
+                            }
+                        }
+                    }
+                    else
+                    {
+                        // small boxes / points outside the box: try every admissible image per candidate
+                        for (uint32_t s = beg; s < end; ++s)
+                        {
+                            float4 const p = __ldg(g.sorted + s);
+                            uint32_t const j = __float_as_uint(p.w);
+                            if (exclude_ii && j == q_global)
+                            {
+                                continue;
+                            }
+                            int njx = 0, njy = 0, njz = 0;
+                            if (g.any_shift)
+                            {
+                                unpack_shift(__ldg(g.shift + s), njx, njy, njz);
+                            }
+                            int const kx0 = wx == 2 ? -1 : njx - nqx - wx, kx1 = wx == 2 ? 1 : kx0;
+                            int const ky0 = wy == 2 ? -1 : njy - nqy - wy, ky1 = wy == 2 ? 1 : ky0;
+                            int const kz0 = wz == 2 ? -1 : njz - nqz - wz, kz1 = wz == 2 ? 1 : kz0;
+                            float const pz = box.is2d ? 0.0f : p.z;
+                            for (int kx = max(kx0, -1); kx <= min(kx1, 1); ++kx)
+                            {
+                                for (int ky = max(ky0, -1); ky <= min(ky1, 1); ++ky)
+                                {
+                                    for (int kz = max(kz0, -1); kz <= min(kz1, 1); ++kz)
+                                    {
+                                        ++evals;
+                                        float ix_, iy_, iz_;
+                                        image_vector(box, kx, ky, kz, ix_, iy_, iz_);
+                                        float const rx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
+                                        float const ry = __fsub_rn(p.y, __fadd_rn(qy, iy_));
+                                        float const rz = __fsub_rn(pz, __fadd_rn(qz, iz_));
+                                        float const r_sq = dot_exact(rx, ry, rz);
+                                        if (in_window(r_sq, r_max_sq, r_min_sq))
+                                        {
+                                            on_hit(s, j, r_sq, rx, ry, rz);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return evals;
+}
+
+template<int FLAVOUR, int MODE> __global__ void __launch_bounds__(kSearchThreads) k_search(SearchArgs a)
+{
+    extern __shared__ uint32_t sh_hist[];
+    bool const hist_in_smem = MODE == SEARCH_RDF && a.axis.bins * sizeof(uint32_t) <= 48 * 1024;
+    if (MODE == SEARCH_RDF && hist_in_smem)
+    {
+        for (uint32_t b = threadIdx.x; b < a.axis.bins; b += blockDim.x)
+        {
+            sh_hist[b] = 0;
+        }
+        __syncthreads();
+    }
+    uint32_t* const hist = hist_in_smem ? sh_hist : a.hist;
+    float const r_max_sq = __fmul_rn(a.r_max, a.r_max); // LinkCell.cc:498, AABBQuery.cc:79
+    float const r_min_sq = __fmul_rn(a.r_min, a.r_min);
+    unsigned long long my_total = 0, my_evals = 0;
+
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_query; t += gridDim.x * blockDim.x)
+    {
+        float4 const q = a.q_sorted[t];
+        uint32_t const qi = __float_as_uint(q.w);
+        uint32_t const q_global = qi + a.q_index_offset;
+        uint32_t count = 0;
+        uint32_t const base = MODE == SEARCH_FILL ? a.row_start[qi] : 0;
+        uint32_t const ev = visit_hits<FLAVOUR>(
+            a.box, a.grid, q.x, q.y, q.z, q_global, a.exclude_ii, r_max_sq, r_min_sq,
+            [&](uint32_t s, uint32_t j, float r_sq, float, float, float) {
+                if (MODE == SEARCH_FILL)
+                {
+                    uint32_t const key_hi = a.sort_by_distance ? __float_as_uint(__fsqrt_rn(r_sq)) : 0U;
+                    a.bag[base + count] = make_uint4(key_hi, j, s, qi);
+                }
+                else if (MODE == SEARCH_RDF)
+                {
+                    int const bin = axis_bin(a.axis, __fsqrt_rn(r_sq)); // NeighborBond distance = sqrt(r_sq)
+                    if (bin >= 0)
+                    {
+                        atomicAdd(&hist[bin], 1U);
+                    }
+                }
+                ++count;
+            });
+        if (MODE == SEARCH_COUNT)
+        {
+            a.row_counts[qi] = count;
+            my_total += count;
+        }
+        my_evals += ev;
+    }
+
+    if (MODE == SEARCH_COUNT || a.evals != nullptr)
+    {
+        // block reduction of the two u64 totals: one atomic each per block
+        __shared__ unsigned long long red[2][kSearchThreads / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            my_total += __shfl_down_sync(0xffffffffU, my_total, o);
+            my_evals += __shfl_down_sync(0xffffffffU, my_evals, o);
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            red[0][threadIdx.x >> 5] = my_total;
+            red[1][threadIdx.x >> 5] = my_evals;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned long long t0 = 0, t1 = 0;
+            for (int w = 0; w < kSearchThreads / 32; ++w)
+            {
+                t0 += red[0][w];
+                t1 += red[1][w];
+            }
+            if (MODE == SEARCH_COUNT && t0 != 0)
+            {
+                atomicAdd(a.total, t0);
+            }
+            if (a.evals != nullptr && t1 != 0)
+            {
+                atomicAdd(a.evals, t1);
+            }
+        }
+    }
+    if (MODE == SEARCH_RDF && hist_in_smem)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < a.axis.bins; b += blockDim.x)
+        {
+            uint32_t const v = sh_hist[b];
+            if (v != 0)
+            {
+                atomicAdd(&a.hist[b], v); // u32 wraps like the reference's unsigned int counters
+            }
+        }
+    }
+}
+
+// ---- emit: one thread per output bond ----------------------------------------------------------------
+template<int FLAVOUR> __global__ void __launch_bounds__(256) k_emit(EmitArgs a)
+{
+    uint64_t const b = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n_bonds)
+    {
+        return;
+    }
+    uint4 const e = a.bag[b];
+    uint32_t const qi = e.w;
+    uint32_t const beg = a.row_start[qi], end = a.row_start[qi + 1];
+    // rank inside the row: NeighborBond::less_as_tuple / less_as_distance restricted to one row with
+    // weight == 1 (NeighborBond.h:80-112); (key_hi, key_lo) = (0, j) or (bits(d), j)
+    unsigned long long const my_key = ((unsigned long long) e.x << 32) | e.y;
+    uint32_t rank = 0;
+    for (uint32_t k = beg; k < end; ++k)
+    {
+        uint4 const o = a.bag[k];
+        unsigned long long const key = ((unsigned long long) o.x << 32) | o.y;
+        rank += (key < my_key || (key == my_key && k < b)) ? 1U : 0U;
+    }
+    uint64_t const out = (uint64_t) beg + rank;
+
+    float4 const p = __ldg(a.sorted + e.z);
+    float qx = a.q_xyz[3 * (size_t) qi], qy = a.q_xyz[3 * (size_t) qi + 1], qz = a.q_xyz[3 * (size_t) qi + 2];
+    float rx, ry, rz, r_sq;
+    if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+    {
+        wrap_exact(a.box, __fsub_rn(p.x, qx), __fsub_rn(p.y, qy), __fsub_rn(p.z, qz), rx, ry, rz);
+        r_sq = dot_exact(rx, ry, rz);
+    }
+    else
+    {
+        // the image that produced the hit is the only one inside the window (plane distance > 2 r_max is
+        // enforced, NeighborQuery.h:503-510); walk the images in the reference's order and take it
+        float const r_max_sq = __fmul_rn(a.r_max, a.r_max), r_min_sq = __fmul_rn(a.r_min, a.r_min);
+        float const pz = a.box.is2d ? 0.0f : p.z;
+        if (a.box.is2d)
+        {
+            qz = 0.0f;
+        }
+        rx = ry = rz = r_sq = 0.0f;
+        bool found = false;
+        for (int code = 0; code < 27 && !found; ++code)
+        {
+            // code 0 is the identity image; 1..26 enumerate (i, j, k) in the order of NeighborQuery.h:546-562
+            int i = 0, j = 0, k = 0;
+            if (code > 0)
+            {
+                int const c = code - 1 + (code - 1 >= 13 ? 1 : 0); // skip (0,0,0) at position 13
+                i = c / 9 - 1;
+                j = (c / 3) % 3 - 1;
+                k = c % 3 - 1;
+            }
+            if (a.box.is2d && k != 0)
+            {
+                continue;
+            }
+            float ix_, iy_, iz_;
+            image_vector(a.box, i, j, k, ix_, iy_, iz_);
+            float const tx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
+            float const ty = __fsub_rn(p.y, __fadd_rn(qy, iy_));
+            float const tz = __fsub_rn(pz, __fadd_rn(qz, iz_));
+            float const t_sq = dot_exact(tx, ty, tz);
+            if (in_window(t_sq, r_max_sq, r_min_sq))
+            {
+                rx = tx;
+                ry = ty;
+                rz = tz;
+                r_sq = t_sq;
+                found = true;
+            }
+        }
+    }
+    a.neighbors[2 * out] = qi;
+    a.neighbors[2 * out + 1] = __float_as_uint(p.w);
+    a.distances[out] = __fsqrt_rn(r_sq); // NeighborBond(i, j, w, v): distance = sqrt(dot(v, v)), NeighborBond.h:41-44
+    a.weights[out] = 1.0f;
+    a.vectors[3 * out] = rx;
+    a.vectors[3 * out + 1] = ry;
+    a.vectors[3 * out + 2] = rz;
+}
+
+__global__ void __launch_bounds__(256) k_segments(const uint32_t* __restrict__ row_start,
+                                                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ segments,
+                                                  uint32_t n_query)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_query)
+    {
+        segments[i] = counts[i] != 0 ? row_start[i] : 0U; // NeighborList.cc:199-232: untouched rows stay 0
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rdf_distances(const float* __restrict__ d, uint64_t n, AxisDev axis,
+                                                       uint32_t* __restrict__ hist)
+{
+    extern __shared__ uint32_t sh_hist[];
+    bool const in_smem = axis.bins * sizeof(uint32_t) <= 48 * 1024;
+    if (in_smem)
+    {
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            sh_hist[b] = 0;
+        }
+        __syncthreads();
+    }
+    uint32_t* const h = in_smem ? sh_hist : hist;
+    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t) gridDim.x * blockDim.x)
+    {
+        int const bin = axis_bin(axis, d[k]);
+        if (bin >= 0)
+        {
+            atomicAdd(&h[bin], 1U);
+        }
+    }
+    if (in_smem)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            if (sh_hist[b] != 0)
+            {
+                atomicAdd(&hist[b], sh_hist[b]);
+            }
+        }
+    }
+}
+
+template<int FLAVOUR> void launch_search_mode(fgpu_ctx* ctx, SearchMode mode, const SearchArgs& a)
+{
+    if (a.n_query == 0)
+    {
+        return;
+    }
+    unsigned blocks = (a.n_query + kSearchThreads - 1) / kSearchThreads;
+    size_t smem = 0;
+    if (mode == SEARCH_RDF)
+    {
+        // persistent blocks so that each merges its private histogram once
+        blocks = std::min<unsigned>(blocks, (unsigned) ctx->sm_count * 16U);
+        smem = a.axis.bins * sizeof(uint32_t) <= 48 * 1024 ? a.axis.bins * sizeof(uint32_t) : 0;
+    }
+    switch (mode)
+    {
+    case SEARCH_COUNT:
+        k_search<FLAVOUR, SEARCH_COUNT><<<blocks, kSearchThreads, 0, ctx->stream>>>(a);
+        break;
+    case SEARCH_FILL:
+        k_search<FLAVOUR, SEARCH_FILL><<<blocks, kSearchThreads, 0, ctx->stream>>>(a);
+        break;
+    case SEARCH_RDF:
+        k_search<FLAVOUR, SEARCH_RDF><<<blocks, kSearchThreads, smem, ctx->stream>>>(a);
+        break;
+    }
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace
+
+void launch_search(fgpu_ctx* ctx, int flavour, SearchMode mode, const SearchArgs& args)
+{
+    if (flavour == FGPU_FLAVOUR_WRAP)
+    {
+        launch_search_mode<FGPU_FLAVOUR_WRAP>(ctx, mode, args);
+    }
+    else
+    {
+        launch_search_mode<FGPU_FLAVOUR_IMAGE>(ctx, mode, args);
+    }
+}
+
+void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& a)
+{
+    if (a.n_bonds == 0)
+    {
+        return;
+    }
+    unsigned const blocks = (unsigned) ((a.n_bonds + 255) / 256);
+    if (flavour == FGPU_FLAVOUR_WRAP)
+    {
+        k_emit<FGPU_FLAVOUR_WRAP><<<blocks, 256, 0, ctx->stream>>>(a);
+    }
+    else
+    {
+        k_emit<FGPU_FLAVOUR_IMAGE><<<blocks, 256, 0, ctx->stream>>>(a);
+    }
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* counts, uint32_t* segments,
+                     uint32_t n_query)
+{
+    if (n_query == 0)
+    {
+        return;
+    }
+    k_segments<<<(n_query + 255) / 256, 256, 0, ctx->stream>>>(row_start, counts, segments, n_query);
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist)
+{
+    if (n == 0)
+    {
+        return;
+    }
+    unsigned const blocks = (unsigned) std::min<uint64_t>((n + 255) / 256, (uint64_t) ctx->sm_count * 16U);
+    size_t const smem = axis.bins * sizeof(uint32_t) <= 48 * 1024 ? axis.bins * sizeof(uint32_t) : 0;
+    k_rdf_distances<<<blocks, 256, smem, ctx->stream>>>(distances, n, axis, hist);
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace fgpu

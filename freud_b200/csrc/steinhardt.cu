@@ -1,0 +1,391 @@
+// Steinhardt q_l: per-particle accumulation of spherical harmonics over the neighbour list.
+//
+// Replaces Steinhardt::baseCompute + normalizeSystem (freud/order/Steinhardt.cc:120-222, 291-327) and the
+// fsph::PointSPHEvaluator<float> recurrence it calls (extern/fsph/src/spherical_harmonics.hpp:155-290,
+// value iterator :78-93, Condon-Shortley sign Steinhardt.cc:47-49).
+//
+// One thread per particle.  For every bond the thread recomputes delta = Box::wrap(p_j - p_i) (Steinhardt.cc:155;
+// always the WRAP arithmetic, whoever found the bond), takes theta = acos(clamp(z / d)) with the list's
+// distance d and phi = atan2(y, x), runs the Jacobi recurrence for m = 0..l and accumulates Y_lm for m >= 0
+// in registers.  Negative m needs no accumulator: Y_{l,-m} = conj(Y_{l,m}) * (-1)^m term by term, and both
+// conj and the sign commute exactly with float summation, so q_{l,-m} is derived at the end.
+// Tolerance vs the reference: 1e-5 (libm vs CUDA sinf/cosf/atan2f/acosf differ in the last ulp).
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+
+namespace fgpu {
+
+namespace {
+
+constexpr int kSphLmax = 32;
+constexpr int kThreads = 128;
+
+// recurrence prefactors for lmax, laid out as the reference does: [0, lmax*(lmax+1)) first kind,
+// [lmax*(lmax+1), 2*lmax*(lmax+1)) second kind; index lmax*m + (l-1)
+__constant__ float c_pref[2 * (kSphLmax + 1) * kSphLmax];
+__constant__ float c_jac0[kSphLmax + 1]; // jacobi[m][0] = 1/sqrt(2) * prod_{k<=m} sqrt(1 + 1/(2k))
+__constant__ int c_ls[kSphLmax + 1];     // requested l values
+__constant__ int c_l_slot[kSphLmax + 1]; // l -> index into the request list, or -1
+__constant__ int c_acc_off[kSphLmax + 1]; // request index -> offset of its (l+1) complex accumulators
+__constant__ int c_out_off[kSphLmax + 1]; // request index -> offset (in complex elements per particle sum) of qlm block
+
+struct Angles
+{
+    float sphi, cphi; // sin / cos of the polar angle ("phi" in fsph, theta in freud)
+    float az;         // azimuth
+};
+
+__device__ __forceinline__ Angles bond_angles(const BoxDev& box, const float* __restrict__ xyz, uint32_t i, uint32_t j,
+                                              float dist)
+{
+    float const rx0 = xyz[3 * (size_t) i], ry0 = xyz[3 * (size_t) i + 1], rz0 = xyz[3 * (size_t) i + 2];
+    float const px = xyz[3 * (size_t) j], py = xyz[3 * (size_t) j + 1], pz = xyz[3 * (size_t) j + 2];
+    float dx, dy, dz;
+    wrap_exact(box, __fsub_rn(px, rx0), __fsub_rn(py, ry0), __fsub_rn(pz, rz0), dx, dy, dz);
+    float const phi = atan2f(dy, dx);                                         // Steinhardt.cc:161
+    float theta = acosf(fmaxf(-1.0f, fminf(__fdiv_rn(dz, dist), 1.0f)));      // Steinhardt.cc:167
+    if (dist == 0.0f)
+    {
+        theta = 0.0f; // Steinhardt.cc:171-174
+    }
+    Angles a;
+    a.sphi = sinf(theta);
+    a.cphi = cosf(theta);
+    a.az = phi;
+    return a;
+}
+
+// ---- single l, everything unrolled into registers ---------------------------------------------------
+template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(SteinhardtArgs a)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    float re[L + 1], im[L + 1];
+#pragma unroll
+    for (int m = 0; m <= L; ++m)
+    {
+        re[m] = 0.0f;
+        im[m] = 0.0f;
+    }
+    float total_weight = 0.0f;
+    bool const active = i < a.n;
+    if (active)
+    {
+        uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+        for (uint32_t b = beg; b < end; ++b)
+        {
+            uint32_t const j = a.neighbors[2 * (size_t) b + 1];
+            float const dist = a.distances[b];
+            float const w = a.weighted ? a.weights[b] : 1.0f;
+            Angles const ang = bond_angles(a.box, a.xyz, i, j, dist);
+            float sinpow = 1.0f;
+#pragma unroll
+            for (int m = 0; m <= L; ++m)
+            {
+                // Jacobi recurrence in l' = l - m up to L - m (spherical_harmonics.hpp:246-270)
+                float j_prev = 0.0f, j_cur = c_jac0[m];
+#pragma unroll
+                for (int lp = 1; lp <= L - m; ++lp)
+                {
+                    float next = ang.cphi * c_pref[L * m + (lp - 1)] * j_cur;
+                    if (lp >= 2)
+                    {
+                        next += c_pref[L * (L + 1) + L * m + (lp - 1)] * j_prev;
+                    }
+                    j_prev = j_cur;
+                    j_cur = next;
+                }
+                float const legendre = sinpow * j_cur;                      // :272-281
+                float const amp = (float) ((double) legendre / 2.5066282746310002); // / sqrt(2 pi), :85-91
+                float s, c;
+                sincosf((float) m * ang.az, &s, &c); // exp(i m theta), :239-244
+                float const phase = (m & 1) ? -1.0f : 1.0f; // Steinhardt.cc:47-49
+                re[m] += w * (phase * (amp * c));
+                im[m] += w * (phase * (amp * s));
+                sinpow *= ang.sphi;
+            }
+            total_weight += w;
+        }
+    }
+    // normalise, q_l, outputs (Steinhardt.cc:195-220)
+    float const nf = (float) (4.0 * 3.14159265358979323846 / (2 * L + 1));
+    float sum = 0.0f;
+    double sys_re[L + 1], sys_im[L + 1];
+#pragma unroll
+    for (int m = 0; m <= L; ++m)
+    {
+        re[m] = re[m] / total_weight;
+        im[m] = im[m] / total_weight;
+        sys_re[m] = active ? (double) re[m] : 0.0;
+        sys_im[m] = active ? (double) im[m] : 0.0;
+    }
+    if (active)
+    {
+        // m = 0..L, then -1..-L, as upstream orders them
+#pragma unroll
+        for (int m = 0; m <= L; ++m)
+        {
+            sum += re[m] * re[m] + im[m] * im[m];
+        }
+#pragma unroll
+        for (int m = 1; m <= L; ++m)
+        {
+            sum += re[m] * re[m] + im[m] * im[m];
+        }
+        a.ql[i] = sqrtf(sum * nf);
+        if (a.qlm != nullptr)
+        {
+            float2* out = reinterpret_cast<float2*>(a.qlm) + (size_t) i * (2 * L + 1);
+#pragma unroll
+            for (int m = 0; m <= L; ++m)
+            {
+                out[m] = make_float2(re[m], im[m]);
+            }
+#pragma unroll
+            for (int m = 1; m <= L; ++m)
+            {
+                float const phase = (m & 1) ? -1.0f : 1.0f;
+                out[L + m] = make_float2(phase * re[m], -(phase * im[m])); // conj without the sign
+            }
+        }
+    }
+    // system q_lm partial sums in fp64: warp shuffle, then one atomic per warp and component
+    if (a.sys_qlm != nullptr)
+    {
+#pragma unroll
+        for (int m = 0; m <= L; ++m)
+        {
+            double vr = sys_re[m], vi = sys_im[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                vr += __shfl_down_sync(0xffffffffU, vr, o);
+                vi += __shfl_down_sync(0xffffffffU, vi, o);
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                atomicAdd(&a.sys_qlm[2 * m], vr);
+                atomicAdd(&a.sys_qlm[2 * m + 1], vi);
+            }
+        }
+    }
+}
+
+// ---- generic: any set of l values up to kSphLmax, accumulators in local memory ------------------------
+constexpr int kMaxAcc = 2 * 160; // floats; sum over requested l of (l + 1) complex numbers
+
+__global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs a, int lmax, int n_ls, int n_acc,
+                                                                 int tot_m)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+    {
+        return;
+    }
+    float acc[kMaxAcc];
+    for (int k = 0; k < 2 * n_acc; ++k)
+    {
+        acc[k] = 0.0f;
+    }
+    float total_weight = 0.0f;
+    uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+    for (uint32_t b = beg; b < end; ++b)
+    {
+        uint32_t const j = a.neighbors[2 * (size_t) b + 1];
+        float const dist = a.distances[b];
+        float const w = a.weighted ? a.weights[b] : 1.0f;
+        Angles const ang = bond_angles(a.box, a.xyz, i, j, dist);
+        float sinpow = 1.0f;
+        for (int m = 0; m <= lmax; ++m)
+        {
+            float s, c;
+            sincosf((float) m * ang.az, &s, &c);
+            float const phase = (m & 1) ? -1.0f : 1.0f;
+            float j_prev = 0.0f, j_cur = c_jac0[m];
+            for (int lp = 0; lp <= lmax - m; ++lp)
+            {
+                if (lp >= 1)
+                {
+                    float next = ang.cphi * c_pref[lmax * m + (lp - 1)] * j_cur;
+                    if (lp >= 2)
+                    {
+                        next += c_pref[lmax * (lmax + 1) + lmax * m + (lp - 1)] * j_prev;
+                    }
+                    j_prev = j_cur;
+                    j_cur = next;
+                }
+                int const slot = c_l_slot[lp + m];
+                if (slot >= 0)
+                {
+                    float const legendre = sinpow * j_cur;
+                    float const amp = (float) ((double) legendre / 2.5066282746310002);
+                    int const o = 2 * (c_acc_off[slot] + m);
+                    acc[o] += w * (phase * (amp * c));
+                    acc[o + 1] += w * (phase * (amp * s));
+                }
+            }
+            sinpow *= ang.sphi;
+        }
+        total_weight += w;
+    }
+    for (int r = 0; r < n_ls; ++r)
+    {
+        int const l = c_ls[r];
+        float const nf = (float) (4.0 * 3.14159265358979323846 / (2 * l + 1));
+        float* q = acc + 2 * c_acc_off[r];
+        float sum = 0.0f;
+        for (int m = 0; m <= l; ++m)
+        {
+            q[2 * m] = q[2 * m] / total_weight;
+            q[2 * m + 1] = q[2 * m + 1] / total_weight;
+            sum += q[2 * m] * q[2 * m] + q[2 * m + 1] * q[2 * m + 1];
+        }
+        for (int m = 1; m <= l; ++m)
+        {
+            sum += q[2 * m] * q[2 * m] + q[2 * m + 1] * q[2 * m + 1];
+        }
+        a.ql[(size_t) i * n_ls + r] = sqrtf(sum * nf);
+        if (a.qlm != nullptr)
+        {
+            // per-l blocks are concatenated: block r starts at n * c_out_off[r] complex elements
+            float2* out = reinterpret_cast<float2*>(a.qlm) + (size_t) a.n * c_out_off[r] + (size_t) i * (2 * l + 1);
+            for (int m = 0; m <= l; ++m)
+            {
+                out[m] = make_float2(q[2 * m], q[2 * m + 1]);
+            }
+            for (int m = 1; m <= l; ++m)
+            {
+                float const phase = (m & 1) ? -1.0f : 1.0f;
+                out[l + m] = make_float2(phase * q[2 * m], -(phase * q[2 * m + 1]));
+            }
+        }
+        if (a.sys_qlm != nullptr)
+        {
+            // sys_qlm holds (2l+1) complex per l at complex offset c_out_off[r]; only m >= 0 is accumulated,
+            // the host derives m < 0
+            for (int m = 0; m <= l; ++m)
+            {
+                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m)], (double) q[2 * m]);
+                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m) + 1], (double) q[2 * m + 1]);
+            }
+        }
+    }
+    (void) tot_m;
+}
+
+void upload_tables(fgpu_ctx* ctx, int lmax, const std::vector<uint32_t>& ls)
+{
+    // evaluatePrefactors, spherical_harmonics.hpp:216-237 (double expression, stored to float)
+    std::vector<float> pref(2 * (kSphLmax + 1) * kSphLmax, 0.0f);
+    unsigned const L = (unsigned) lmax;
+    unsigned const f1 = L * (L + 1);
+    for (unsigned m = 0; m < L + 1; ++m)
+    {
+        for (unsigned l = 1; l < L + 1; ++l)
+        {
+            pref[L * m + (l - 1)] = (float) (2 * std::sqrt(1 + (m - 0.5) / l) * std::sqrt(1 - (m - 0.5) / (l + 2 * m)));
+        }
+    }
+    for (unsigned m = 0; m < L + 1; ++m)
+    {
+        if (L > 0)
+        {
+            pref[f1 + L * m] = 0.0f;
+        }
+        for (unsigned l = 2; l < L + 1; ++l)
+        {
+            pref[f1 + L * m + (l - 1)] = (float) (-std::sqrt(1.0 + 4.0 / (2 * l + 2 * m - 3)) * std::sqrt(1 - 1.0 / l)
+                                                  * std::sqrt(1.0 - 1.0 / (l + 2 * m)));
+        }
+    }
+    // compute_jacobis first column, spherical_harmonics.hpp:250-256
+    float jac0[kSphLmax + 1];
+    jac0[0] = (float) (1 / std::sqrt(2.0));
+    for (unsigned m = 1; m < L + 1; ++m)
+    {
+        jac0[m] = (float) (jac0[m - 1] * std::sqrt(1 + 1.0 / 2 / m));
+    }
+    for (unsigned m = L + 1; m < kSphLmax + 1; ++m)
+    {
+        jac0[m] = 0.0f;
+    }
+    int h_ls[kSphLmax + 1] = {0}, h_slot[kSphLmax + 1], h_acc[kSphLmax + 1] = {0}, h_out[kSphLmax + 1] = {0};
+    for (int& s : h_slot)
+    {
+        s = -1;
+    }
+    int acc = 0, out = 0;
+    for (size_t r = 0; r < ls.size(); ++r)
+    {
+        h_ls[r] = (int) ls[r];
+        h_slot[ls[r]] = (int) r;
+        h_acc[r] = acc;
+        h_out[r] = out;
+        acc += (int) ls[r] + 1;
+        out += 2 * (int) ls[r] + 1;
+    }
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pref, pref.data(), pref.size() * sizeof(float), 0,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_jac0, jac0, sizeof(jac0), 0, cudaMemcpyHostToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_ls, h_ls, sizeof(h_ls), 0, cudaMemcpyHostToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_l_slot, h_slot, sizeof(h_slot), 0, cudaMemcpyHostToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_acc_off, h_acc, sizeof(h_acc), 0, cudaMemcpyHostToDevice, ctx->stream));
+    FGPU_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_out_off, h_out, sizeof(h_out), 0, cudaMemcpyHostToDevice, ctx->stream));
+    // the host arrays above die at return; the copies must have been consumed by then
+    FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a)
+{
+    k_steinhardt_single<L><<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a);
+}
+
+} // namespace
+
+void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector<uint32_t>& ls)
+{
+    int lmax = 0, n_acc = 0, tot_m = 0;
+    for (uint32_t l : ls)
+    {
+        if (l > (uint32_t) kSphLmax)
+        {
+            throw Error(FGPU_EINVALID, "Steinhardt: l larger than 32 is not supported by the device path");
+        }
+        lmax = std::max(lmax, (int) l);
+        n_acc += (int) l + 1;
+        tot_m += 2 * (int) l + 1;
+    }
+    if (ls.empty() || (int) ls.size() > kSphLmax || 2 * n_acc > kMaxAcc)
+    {
+        throw Error(FGPU_EINVALID, "Steinhardt: unsupported list of l values");
+    }
+    upload_tables(ctx, lmax, ls);
+    if (a.n == 0)
+    {
+        return;
+    }
+    bool single = ls.size() == 1;
+    if (single)
+    {
+        switch (ls[0])
+        {
+        case 2: launch_single<2>(ctx, a); break;
+        case 4: launch_single<4>(ctx, a); break;
+        case 6: launch_single<6>(ctx, a); break;
+        case 8: launch_single<8>(ctx, a); break;
+        case 10: launch_single<10>(ctx, a); break;
+        case 12: launch_single<12>(ctx, a); break;
+        default: single = false; break;
+        }
+    }
+    if (!single)
+    {
+        k_steinhardt_generic<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, lmax, (int) ls.size(),
+                                                                                             n_acc, tot_m);
+    }
+    ctx->launches += 1;
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace fgpu

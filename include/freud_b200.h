@@ -1,0 +1,194 @@
+/* freud_b200 -- C ABI of the B200-native neighbour-query + pair-accumulation path.
+ *
+ * The reference (glotzerlab/freud @ e4272dbe) has no C ABI or plugin interface for this path: the
+ * boundary is the set of C++ methods its nanobind modules bind.  This header is
+ * the thin C layer those methods are re-implemented on (freud_b200/host/ holds the C++ classes with the
+ * reference's signatures; INTEGRATION.md shows the binding a maintainer would add).  Each entry point
+ * cites the reference method it replaces.
+ *
+ * Conventions
+ *   - every function returns FGPU_OK (0) or a negative FGPU_E* code; fgpu_last_error() returns the
+ *     message of the last failure on the calling thread.  The C++ layer maps codes to the reference's
+ *     exception types (INVALID -> std::invalid_argument, DOMAIN -> std::domain_error,
+ *     RUNTIME/CUDA/NCCL -> std::runtime_error).
+ *   - plain pointers and sizes only; "host" pointers are ordinary (pageable or pinned) host memory,
+ *     "dev" pointers are device memory on the context's GPU.
+ *   - points are (n, 3) C-contiguous float32, exactly the layout freud's bindings accept
+ *     (freud/locality/export-NeighborQuery.cc:19-31).
+ *   - box6 = {Lx, Ly, Lz, xy, xz, yz}; is2d != 0 selects freud's 2-D box (Lz ignored, z forced to 0).
+ *   - all arithmetic on pair distances is un-fused IEEE float32 in the reference's operation order, so
+ *     neighbour lists and RDF bin counts are bit-identical to the reference's x86-64 build.
+ *   - there is no CPU fallback: without a CUDA device every call fails with FGPU_ECUDA.
+ */
+#ifndef FREUD_B200_H
+#define FREUD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGPU_OK 0
+#define FGPU_EINVALID (-1) /* std::invalid_argument upstream */
+#define FGPU_EDOMAIN (-2)  /* std::domain_error upstream    */
+#define FGPU_ERUNTIME (-3) /* std::runtime_error upstream   */
+#define FGPU_ECUDA (-4)    /* CUDA runtime failure / no device */
+#define FGPU_ENCCL (-5)    /* NCCL failure / library missing */
+#define FGPU_ENOMEM (-6)
+
+/* Pair-distance arithmetic ("flavour"), SURVEY.md fact 2 */
+#define FGPU_FLAVOUR_WRAP 0  /* LinkCell:  r = Box::wrap(p_j - q)        freud/locality/LinkCell.cc:522 */
+#define FGPU_FLAVOUR_IMAGE 1 /* AABBQuery: r = p_j - (q + image_k)       freud/locality/AABBQuery.cc:93,125 */
+
+typedef struct fgpu_ctx fgpu_ctx;       /* one GPU + one stream + scratch memory            */
+typedef struct fgpu_points fgpu_points; /* device-resident reference points + box + cell list */
+typedef struct fgpu_nlist fgpu_nlist;   /* device-resident NeighborList (SoA, CSR)            */
+typedef struct fgpu_rdf fgpu_rdf;       /* device-resident RDF histogram accumulator          */
+typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
+
+const char* fgpu_last_error(void);
+/* library + device description, e.g. "freud_b200 0.1 sm_100a NVIDIA B200 148 SMs"; safe without a GPU */
+const char* fgpu_version(void);
+int fgpu_device_count(void);
+
+/* ---- context -------------------------------------------------------------------------------------- */
+int fgpu_ctx_create(int device, fgpu_ctx** out);
+void fgpu_ctx_destroy(fgpu_ctx* ctx);
+int fgpu_ctx_synchronize(fgpu_ctx* ctx);
+/* the context's cudaStream_t, for callers that time with CUDA events on the launching stream */
+void* fgpu_ctx_stream(fgpu_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t fgpu_ctx_launch_count(fgpu_ctx* ctx);
+/* cumulative pair-distance evaluations ("pair evals") performed by search kernels launched since the last
+ * reset; counted on the device.  Enabled with fgpu_ctx_count_pair_evals(ctx, 1) (off by default: the
+ * counting variant costs one extra atomic per block). */
+int fgpu_ctx_count_pair_evals(fgpu_ctx* ctx, int enable);
+int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset);
+
+/* ---- points + periodic cell list -------------------------------------------------------------------
+ * Replaces the constructors LinkCell(box, points, n, cell_width) freud/locality/LinkCell.cc:222-260,
+ * AABBQuery(box, points, n) freud/locality/AABBQuery.cc:17-26 and RawPoints (RawPoints.h:35-37):
+ * copies the points to the GPU.  The cell list itself (cell index, counting sort, prefix scan, cell-ordered
+ * float4 positions; replaces LinkCell::computeCellList freud/locality/LinkCell.cc:316-336 and
+ * AABBQuery::buildTree :53-69) is built on the first query, because its cell width follows r_max; it is
+ * cached per (r_max) and rebuilt only when a query needs a different width.
+ * Errors: n == 0 -> FGPU_EINVALID (NeighborQuery.h:97-100); 2-D box with |z| > 1e-6 -> FGPU_EINVALID
+ * (NeighborQuery.h:103-112). */
+int fgpu_points_create(fgpu_ctx* ctx, const float* box6, int is2d, const float* points_host, uint32_t n,
+                       fgpu_points** out);
+/* same, points already resident on the device (n x 3 float32) */
+int fgpu_points_create_dev(fgpu_ctx* ctx, const float* box6, int is2d, const float* points_dev, uint32_t n,
+                           fgpu_points** out);
+void fgpu_points_destroy(fgpu_points* pts);
+/* Force the cell-list build for search radius r (what the first query would do); exposed so the build can
+ * be timed and tested on its own.  out_dims[3] receives the cell grid, may be NULL. */
+int fgpu_points_build_cells(fgpu_points* pts, float r_search, uint32_t* out_dims);
+/* Copies out the cell list for tests: cell_start[n_cells + 1] and the point index of every cell-ordered
+ * slot (order[n]).  Either pointer may be NULL. */
+int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host);
+
+/* ---- ball query -> NeighborList ---------------------------------------------------------------------
+ * Replaces NeighborQuery::query(...)->toNeighborList(sort_by_distance) for mode == ball:
+ * freud/locality/NeighborQuery.h:130-142, 434-481 with LinkCellQueryBallIterator::next
+ * (freud/locality/LinkCell.cc:496-573, flavour WRAP) or AABBQueryBallIterator::next
+ * (freud/locality/AABBQuery.cc:77-150, flavour IMAGE).
+ * query_points_host == NULL means "the query points are the reference points themselves".
+ * q_index_offset is added to the local query index when comparing against point indices for exclude_ii
+ * and is NOT added to the emitted query index (rows are local); it lets one rank query a contiguous
+ * shard of the points.
+ * Errors: r_max <= 0 or r_max <= r_min -> FGPU_EINVALID (NeighborQuery.h:321-328); IMAGE flavour with
+ * a plane distance <= 2 r_max -> FGPU_ERUNTIME (NeighborQuery.h:503-510); n_query == 0 yields an empty
+ * list (tests/test_locality_neighbor_list.py:253-256). */
+int fgpu_ball_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                    int flavour, float r_max, float r_min, int exclude_ii, int sort_by_distance, fgpu_nlist** out);
+/* same with query points resident on the device */
+int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_t n_query,
+                        uint32_t q_index_offset, int flavour, float r_max, float r_min, int exclude_ii,
+                        int sort_by_distance, fgpu_nlist** out);
+
+/* ---- k-nearest-neighbour query -> NeighborList ------------------------------------------------------
+ * Replaces query(mode == nearest)->toNeighborList(): AABBQueryIterator::next
+ * freud/locality/AABBQuery.cc:152-281 (E3 in SURVEY.md: the k smallest closest-image distances in the
+ * IMAGE arithmetic, d >= r_min, d <= r_max; r_guess/scale do not influence the result,
+ * tests/test_locality_neighbor_query.py:635-656).  r_max may be INFINITY. */
+int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                   uint32_t num_neighbors, float r_max, float r_min, int exclude_ii, int sort_by_distance,
+                   fgpu_nlist** out);
+
+/* ---- NeighborList -----------------------------------------------------------------------------------
+ * Layout = freud::locality::NeighborList (freud/locality/NeighborList.h:139-157): neighbors u32[nb][2],
+ * distances f32[nb], weights f32[nb], vectors f32[nb][3], segments/counts u32[n_query]; bonds sorted by
+ * (i, j) or (i, d, j) (NeighborBond.h:80-112); segments of empty rows are 0 (NeighborList.cc:199-232). */
+uint64_t fgpu_nlist_num_bonds(const fgpu_nlist* nl);
+uint32_t fgpu_nlist_num_query_points(const fgpu_nlist* nl);
+uint32_t fgpu_nlist_num_points(const fgpu_nlist* nl);
+/* device -> host copy of any subset (NULL pointers are skipped) */
+int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
+                    float* vectors_host, uint32_t* segments_host, uint32_t* counts_host);
+/* upload a host NeighborList (already sorted by query index) so RDF / Steinhardt can consume it:
+ * replaces passing a NeighborList* into accumulate/compute (NeighborComputeFunctional.h:180-193, 121-135) */
+int fgpu_nlist_from_host(fgpu_ctx* ctx, uint64_t n_bonds, uint32_t n_query, uint32_t n_points,
+                         const uint32_t* neighbors_host, const float* distances_host, const float* weights_host,
+                         const float* vectors_host, fgpu_nlist** out);
+void fgpu_nlist_destroy(fgpu_nlist* nl);
+
+/* ---- RDF ---------------------------------------------------------------------------------------------
+ * Device half of freud::density::RDF (freud/density/RDF.cc:25-110) + BondHistogramCompute
+ * (freud/locality/BondHistogramCompute.h:29-140): a resident u32[bins] histogram with
+ * RegularAxis::bin semantics (freud/util/Histogram.h:126-174).  Normalisation to g(r), n(r)
+ * (RDF::reduce, RDF.cc:73-99) is host arithmetic in freud_b200/host/RDF.cc. */
+int fgpu_rdf_create(fgpu_ctx* ctx, uint32_t bins, float r_max, float r_min, fgpu_rdf** out);
+void fgpu_rdf_destroy(fgpu_rdf* rdf);
+int fgpu_rdf_reset(fgpu_rdf* rdf); /* BondHistogramCompute::reset :39-49 */
+/* accumulate one frame by querying on the fly (no NeighborList is materialised):
+ * RDF::accumulate with nlist == nullptr, RDF.cc:101-110 -> NeighborComputeFunctional.h:195-217.
+ * The query window (q_r_max, q_r_min) and the histogram range (r_max, r_min of create) are independent,
+ * as upstream. */
+int fgpu_rdf_accumulate(fgpu_rdf* rdf, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                        uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii);
+int fgpu_rdf_accumulate_dev(fgpu_rdf* rdf, fgpu_points* pts, const float* query_points_dev, uint32_t n_query,
+                            uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii);
+/* accumulate from an existing NeighborList: one increment per stored distance
+ * (NeighborComputeFunctional.h:180-193) */
+int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl);
+/* device -> host copy of the raw bin counts (BondHistogramCompute::getBinCounts :74-77) */
+int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
+/* sum the histograms of all ranks in place: one ncclAllReduce(u32[bins], sum) */
+int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
+
+/* ---- Steinhardt --------------------------------------------------------------------------------------
+ * Replaces Steinhardt::compute for plain q_l (average = wl = false): baseCompute + normalizeSystem,
+ * freud/order/Steinhardt.cc:85-222, 291-327, with fsph::PointSPHEvaluator
+ * (extern/fsph/src/spherical_harmonics.hpp:155-290).  The neighbour list must have been built against
+ * pts (n_query == n_points == n).  Outputs (host pointers, any may be NULL):
+ *   ql      f32[n][n_ls]
+ *   qlm     per l, concatenated: complex64[n][2l+1] (re, im interleaved), m order 0..l, -1..-l
+ *   sys_qlm per l, concatenated: complex64[2l+1] = sum_i qlm_i / n   (accumulated in fp64 on the device,
+ *           rounded once: a documented deviation, the reference's float32 thread-order sum is not
+ *           reproducible, SURVEY.md section 7 "hard parts")
+ *   order   f32[n_ls] system-wide q_l
+ * comm != NULL: sys_qlm/order are reduced over all ranks (each rank holds a shard of the rows; n_total is
+ * the global particle count used in the 1/N normalisation). */
+int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls,
+                            int weighted, uint32_t n_total, fgpu_comm* comm, float* ql_host, float* qlm_host,
+                            float* sys_qlm_host, float* order_host);
+
+/* ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
+ * NCCL is loaded at run time (libnccl.so.2); unique_id is NCCL's 128-byte ncclUniqueId, produced on rank 0
+ * and distributed by the caller (bench.py uses torch.distributed / a file for that). */
+#define FGPU_UNIQUE_ID_BYTES 128
+int fgpu_comm_unique_id(uint8_t* unique_id_out);
+int fgpu_comm_create(fgpu_ctx* ctx, const uint8_t* unique_id, int rank, int n_ranks, fgpu_comm** out);
+void fgpu_comm_destroy(fgpu_comm* comm);
+int fgpu_comm_rank(const fgpu_comm* comm);
+int fgpu_comm_size(const fgpu_comm* comm);
+int fgpu_comm_barrier(fgpu_comm* comm);
+/* generic in-place sum over host buffers of u32 / f64 (staged through device memory, one ncclAllReduce) */
+int fgpu_comm_allreduce_u32(fgpu_comm* comm, uint32_t* host_inout, uint64_t count);
+int fgpu_comm_allreduce_f64(fgpu_comm* comm, double* host_inout, uint64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREUD_B200_H */

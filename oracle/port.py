@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end to ``oracle/libfreud_port.so`` (the plain-C restatement in
+``port.c``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this
+module; the product (``freud_b200``) never does.
+"""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfreud_port.so")
+WRAP, IMAGE = 0, 1
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "port.c")):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.fport_ball_nlist.restype = C.c_void_p
+        L.fport_ball_nlist.argtypes = [C.c_int, _fp, C.c_int, _fp, C.c_uint32, _fp, C.c_uint32, C.c_float, C.c_float,
+                                       C.c_int, C.c_int]
+        L.fport_knn_nlist.restype = C.c_void_p
+        L.fport_knn_nlist.argtypes = [_fp, C.c_int, _fp, C.c_uint32, _fp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                      C.c_int, C.c_int]
+        L.fport_nlist_size.restype = C.c_uint64
+        L.fport_nlist_size.argtypes = [C.c_void_p]
+        L.fport_nlist_copy.argtypes = [C.c_void_p, _up, _fp, _fp, _fp, _up, _up]
+        L.fport_nlist_free.argtypes = [C.c_void_p]
+        L.fport_rdf_accumulate.argtypes = [C.c_int, _fp, C.c_int, _fp, C.c_uint32, _fp, C.c_uint32, C.c_float,
+                                           C.c_float, C.c_int, C.c_uint32, C.c_float, C.c_float, _up]
+        L.fport_rdf_accumulate_distances.argtypes = [_fp, C.c_uint64, C.c_uint32, C.c_float, C.c_float, _up]
+        L.fport_rdf_reduce.argtypes = [_up, C.c_uint32, C.c_float, C.c_float, _fp, C.c_int, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_int, _fp, _fp, _fp, _fp]
+        L.fport_steinhardt.argtypes = [_fp, C.c_int, _fp, C.c_uint32, _up, _fp, _fp, _up, _up, _up, C.c_uint32,
+                                       C.c_int, _fp, _fp, _fp, _fp]
+        L.fport_box_apply.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_uint32, _fp]
+        L.fport_box_info.argtypes = [_fp, C.c_int, _fp, _fp]
+        L.fport_count_candidates.restype = C.c_uint64
+        L.fport_count_candidates.argtypes = [_fp, C.c_int, _fp, C.c_uint32, _fp, C.c_uint32, C.c_float]
+        _lib = L
+    return _lib
+
+
+def _f32(a, last=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(-1, last) if last else a
+
+
+def _p(a, t=_fp):
+    return a.ctypes.data_as(t)
+
+
+def box6(box):
+    if hasattr(box, "Lx"):
+        box = (box.Lx, box.Ly, box.Lz, box.xy, box.xz, box.yz)
+    return np.asarray(box, dtype=np.float32).copy()
+
+
+class NeighborList:
+    def __init__(self, handle, n_query):
+        L = lib()
+        if not handle:
+            raise MemoryError("oracle port: allocation failed")
+        nb = L.fport_nlist_size(handle)
+        self.neighbors = np.zeros((nb, 2), np.uint32)
+        self.distances = np.zeros(nb, np.float32)
+        self.weights = np.zeros(nb, np.float32)
+        self.vectors = np.zeros((nb, 3), np.float32)
+        self.segments = np.zeros(n_query, np.uint32)
+        self.counts = np.zeros(n_query, np.uint32)
+        L.fport_nlist_copy(handle, _p(self.neighbors, _up), _p(self.distances), _p(self.weights), _p(self.vectors),
+                           _p(self.segments, _up), _p(self.counts, _up))
+        L.fport_nlist_free(handle)
+
+    def __len__(self):
+        return len(self.distances)
+
+
+def ball_nlist(flavour, box, is2d, points, query_points, r_max, r_min=0.0, exclude_ii=False, sort_by_distance=False):
+    b, p, q = box6(box), _f32(points, 3), _f32(query_points, 3)
+    h = lib().fport_ball_nlist(flavour, _p(b), int(is2d), _p(p), len(p), _p(q), len(q), r_max, r_min, int(exclude_ii),
+                               int(sort_by_distance))
+    return NeighborList(h, len(q))
+
+
+def knn_nlist(box, is2d, points, query_points, k, r_max=np.inf, r_min=0.0, exclude_ii=False, sort_by_distance=False):
+    b, p, q = box6(box), _f32(points, 3), _f32(query_points, 3)
+    h = lib().fport_knn_nlist(_p(b), int(is2d), _p(p), len(p), _p(q), len(q), int(k), r_max, r_min, int(exclude_ii),
+                              int(sort_by_distance))
+    return NeighborList(h, len(q))
+
+
+def rdf_accumulate(flavour, box, is2d, points, query_points, bins, r_max, r_min=0.0, exclude_ii=False, counts=None,
+                   query_r_max=None, query_r_min=None):
+    b, p, q = box6(box), _f32(points, 3), _f32(query_points, 3)
+    if counts is None:
+        counts = np.zeros(bins, np.uint32)
+    qmax = r_max if query_r_max is None else query_r_max
+    qmin = 0.0 if query_r_min is None else query_r_min
+    rc = lib().fport_rdf_accumulate(flavour, _p(b), int(is2d), _p(p), len(p), _p(q), len(q), qmax, qmin,
+                                    int(exclude_ii), bins, r_min, r_max, _p(counts, _up))
+    if rc:
+        raise MemoryError("oracle port: allocation failed")
+    return counts
+
+
+def rdf_accumulate_distances(distances, bins, r_max, r_min=0.0, counts=None):
+    d = _f32(distances)
+    if counts is None:
+        counts = np.zeros(bins, np.uint32)
+    lib().fport_rdf_accumulate_distances(_p(d), len(d), bins, r_min, r_max, _p(counts, _up))
+    return counts
+
+
+def rdf_reduce(counts, r_max, r_min, box, is2d, n_points, n_query_points, frames=1, finite_size=False):
+    c = np.ascontiguousarray(counts, dtype=np.uint32)
+    bins = len(c)
+    b = box6(box)
+    g = np.zeros(bins, np.float32)
+    n = np.zeros(bins, np.float32)
+    e = np.zeros(bins + 1, np.float32)
+    ce = np.zeros(bins, np.float32)
+    lib().fport_rdf_reduce(_p(c, _up), bins, r_min, r_max, _p(b), int(is2d), n_points, n_query_points, frames,
+                           int(finite_size), _p(g), _p(n), _p(e), _p(ce))
+    return dict(bin_counts=c, rdf=g, n_r=n, bin_edges=e, bin_centers=ce)
+
+
+def steinhardt(box, is2d, points, nlist, ls, weighted=False):
+    b, p = box6(box), _f32(points, 3)
+    ls = np.atleast_1d(np.asarray(ls, dtype=np.uint32)).copy()
+    n = len(p)
+    j = np.ascontiguousarray(nlist.neighbors[:, 1], dtype=np.uint32)
+    d = _f32(nlist.distances)
+    w = _f32(nlist.weights)
+    seg = np.ascontiguousarray(nlist.segments, dtype=np.uint32)
+    cnt = np.ascontiguousarray(nlist.counts, dtype=np.uint32)
+    tot_m = int(sum(2 * int(l) + 1 for l in ls))
+    ql = np.zeros((n, len(ls)), np.float32)
+    qlm = np.zeros(n * tot_m * 2, np.float32)
+    sys_qlm = np.zeros(tot_m * 2, np.float32)
+    order = np.zeros(len(ls), np.float32)
+    rc = lib().fport_steinhardt(_p(b), int(is2d), _p(p), n, _p(j, _up), _p(d), _p(w), _p(seg, _up), _p(cnt, _up),
+                                _p(ls, _up), len(ls), int(weighted), _p(ql), _p(qlm), _p(sys_qlm), _p(order))
+    if rc:
+        raise ValueError("oracle port: l too large")
+    out, off = [], 0
+    for l in ls:
+        nm = 2 * int(l) + 1
+        blk = qlm[off:off + n * nm * 2].reshape(n, nm, 2)
+        out.append((blk[..., 0] + 1j * blk[..., 1]).astype(np.complex64))
+        off += n * nm * 2
+    return dict(ql=ql, qlm=out, order=order, particle_order=ql)
+
+
+def box_apply(box, is2d, op, vecs):
+    v = _f32(vecs, 3)
+    out = np.empty_like(v)
+    b = box6(box)
+    lib().fport_box_apply(_p(b), int(is2d), {"wrap": 0, "fractional": 1, "absolute": 2}[op], _p(v), len(v), _p(out))
+    return out
+
+
+def box_info(box, is2d):
+    b = box6(box)
+    vol = C.c_float()
+    pd = np.zeros(3, np.float32)
+    lib().fport_box_info(_p(b), int(is2d), C.byref(vol), _p(pd))
+    return vol.value, pd
+
+
+def count_candidates(box, is2d, points, query_points, r_max):
+    b, p, q = box6(box), _f32(points, 3), _f32(query_points, 3)
+    return int(lib().fport_count_candidates(_p(b), int(is2d), _p(p), len(p), _p(q), len(q), r_max))

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One fgpu context for the whole GPU session; fails loudly when the library or the device is missing."""
+    from freud_b200 import _capi
+
+    c = _capi.Context(0)
+    yield c
+    c.close()

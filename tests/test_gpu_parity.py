@@ -1,0 +1,278 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle.
+
+Bar: bit-exact for neighbour lists (all five arrays + segments/counts) and raw RDF bin counts, per
+arithmetic flavour; 1e-5 for q_l.  Oracles: ``oracle/_ref`` (the unmodified reference compiled here,
+travels as a prebuilt .so) where it exists, else ``oracle/port`` (plain-C restatement, itself pinned to
+``_ref`` by tests/test_oracle_port.py).
+"""
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from tests.util import BOXES, assert_nlist_equal, random_points
+
+pytestmark = pytest.mark.gpu
+
+WRAP, IMAGE = 0, 1
+
+
+def _capi():
+    from freud_b200 import _capi
+
+    return _capi
+
+
+def oracle_ball(flavour, box, pts, q, r_max, r_min=0.0, exclude_ii=False, sort_by_distance=False):
+    """The reference itself when its compiled library travelled with the repo, else the pinned port."""
+    if ref.available():
+        eng = "linkcell" if flavour == WRAP else "aabb"
+        query = ref.Query(eng, box, pts, is2d=box.is2D, cell_width=min(r_max, 0.4 * float(min(box.Lx, box.Ly))))
+        return query.nlist(q, r_max=r_max, r_min=r_min, exclude_ii=exclude_ii, sort_by_distance=sort_by_distance)
+    return port.ball_nlist(flavour, box, box.is2D, pts, q, r_max, r_min, exclude_ii, sort_by_distance)
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+@pytest.mark.parametrize("flavour", [WRAP, IMAGE])
+def test_ball_nlist_self_query(ctx, name, flavour):
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=11)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    for exclude_ii in (True, False):
+        got = dp.ball_query(None, flavour, r, 0.0, exclude_ii).to_host()
+        want = oracle_ball(flavour, box, pts, pts, r, 0.0, exclude_ii)
+        assert_nlist_equal(got, want, f"{name} flavour={flavour} exclude_ii={exclude_ii}")
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+@pytest.mark.parametrize("flavour", [WRAP, IMAGE])
+def test_ball_nlist_separate_queries_rmin_sort_by_distance(ctx, name, flavour):
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=12)
+    q = random_points(box, 700, seed=13)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    for sort_by_distance in (False, True):
+        got = dp.ball_query(q, flavour, r, 1.0, False, sort_by_distance).to_host()
+        want = oracle_ball(flavour, box, pts, q, r, 1.0, False, sort_by_distance)
+        assert_nlist_equal(got, want, f"{name} flavour={flavour} sort_by_distance={sort_by_distance}")
+
+
+@pytest.mark.parametrize("name", ["cubic", "tri1", "sq2d"])
+def test_ball_points_outside_box(ctx, name):
+    """Un-wrapped inputs.  AABB has no restriction (images +-1 only); LinkCell's own cell index is UB upstream
+    for such points, so the WRAP flavour is checked against the port, whose
+    definition is E1: brute force with Box::wrap."""
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=14, spill=0.2)
+    q = random_points(box, 500, seed=15, spill=0.2)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    got = dp.ball_query(q, IMAGE, r).to_host()
+    assert_nlist_equal(got, oracle_ball(IMAGE, box, pts, q, r), f"{name} image outside")
+    got = dp.ball_query(q, WRAP, r).to_host()
+    assert_nlist_equal(got, port.ball_nlist(WRAP, box, box.is2D, pts, q, r), f"{name} wrap outside")
+
+
+def test_ball_query_shard_offsets(ctx):
+    """Contiguous query shards with q_index_offset concatenate to the single-GPU list."""
+    box, n, r = BOXES["tri1"]
+    pts = random_points(box, n, seed=16)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    full = dp.ball_query(None, IMAGE, r, 0.0, True).to_host()
+    parts, off = [], 0
+    for lo, hi in ((0, 1000), (1000, 1001), (1001, n)):
+        part = dp.ball_query(pts[lo:hi], IMAGE, r, 0.0, True, q_index_offset=lo).to_host()
+        part["neighbors"][:, 0] += lo
+        parts.append(part)
+    for key in ("neighbors", "distances", "vectors"):
+        assert np.array_equal(np.concatenate([p[key] for p in parts]), full[key]), key
+    assert np.array_equal(np.concatenate([p["counts"] for p in parts]), full["counts"])
+
+
+def test_empty_and_error_behaviour(ctx):
+    capi = _capi()
+    box, n, r = BOXES["cubic"]
+    pts = random_points(box, 100, seed=17)
+    dp = capi.DevicePoints(ctx, box, pts)
+    # zero query points -> empty (0, 2) list, tests/test_locality_neighbor_list.py:253-256
+    nl = dp.ball_query(np.zeros((0, 3), np.float32), IMAGE, r)
+    assert nl.num_bonds == 0 and nl.to_host()["neighbors"].shape == (0, 2)
+    # r_max <= 0, r_max <= r_min -> ValueError (NeighborQuery.h:321-328)
+    with pytest.raises(ValueError):
+        dp.ball_query(None, IMAGE, -1.0)
+    with pytest.raises(ValueError):
+        dp.ball_query(None, WRAP, 1.0, 2.0)
+    # AABB flavour: r_max >= half the box -> RuntimeError (NeighborQuery.h:503-510)
+    with pytest.raises(RuntimeError):
+        dp.ball_query(None, IMAGE, 10.1)
+    # zero particles -> ValueError (NeighborQuery.h:97-100)
+    with pytest.raises(ValueError):
+        capi.DevicePoints(ctx, box, np.zeros((0, 3), np.float32))
+    # 2-D box with z != 0 -> ValueError (NeighborQuery.h:103-112)
+    from freud_b200.box import Box
+
+    with pytest.raises(ValueError):
+        capi.DevicePoints(ctx, Box.square(10), np.array([[0, 0, 0.1]], np.float32))
+    # RDF constructor validation (RDF.cc:27-42)
+    for args in ((0, 5.0, 0.0), (10, -1.0, 0.0), (10, 5.0, -0.5), (10, 2.0, 3.0)):
+        with pytest.raises(ValueError):
+            capi.DeviceRDF(ctx, *args)
+
+
+def test_cell_list_is_a_partition(ctx):
+    """K1-K3: every point appears exactly once, cells are contiguous and ascending."""
+    box, n, r = BOXES["tri1"]
+    pts = random_points(box, n, seed=18)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    dims = dp.build_cells(r)
+    cell_start, order = dp.read_cells(dims)
+    assert cell_start[0] == 0 and cell_start[-1] == n and np.all(np.diff(cell_start.astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    # cell thickness covers r along every axis
+    pd = box.nearest_plane_distance()
+    assert np.all(pd / dims > r)
+    # membership: fractional coordinate of every point lies inside its cell (up to float rounding)
+    frac = box.make_fractional(pts[order]).astype(np.float64)
+    cell_of_slot = np.searchsorted(cell_start, np.arange(n), side="right") - 1
+    cx = cell_of_slot % dims[0]
+    cy = (cell_of_slot // dims[0]) % dims[1]
+    cz = cell_of_slot // (dims[0] * dims[1])
+    for c, f, d in ((cx, frac[:, 0], dims[0]), (cy, frac[:, 1], dims[1]), (cz, frac[:, 2], dims[2])):
+        assert np.all(np.abs(f * d - (c + 0.5)) <= 0.5 + 1e-3)
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+@pytest.mark.parametrize("flavour", [WRAP, IMAGE])
+def test_rdf_bin_counts(ctx, name, flavour):
+    capi = _capi()
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=21)
+    dp = capi.DevicePoints(ctx, box, pts)
+    rdf = capi.DeviceRDF(ctx, 50, r, 0.5)
+    rdf.accumulate(dp, None, flavour, r, 0.0, True)
+    want = port.rdf_accumulate(flavour, box, box.is2D, pts, pts, 50, r, 0.5, True)
+    assert np.array_equal(rdf.read(), want)
+    if ref.available() and flavour == IMAGE:
+        R = ref.RDF(50, r, 0.5)
+        R.accumulate(ref.Query("raw", box, pts, is2d=box.is2D), pts, mode="ball", r_max=r, exclude_ii=True)
+        assert np.array_equal(rdf.read(), R.results()["bin_counts"])
+    # reset=False semantics: a second frame adds; separate query points; then reset
+    q = random_points(box, 500, seed=22)
+    rdf.accumulate(dp, q, flavour, r, 0.0, False)
+    want2 = port.rdf_accumulate(flavour, box, box.is2D, pts, q, 50, r, 0.5, False, counts=want.copy())
+    assert np.array_equal(rdf.read(), want2)
+    rdf.reset()
+    assert not rdf.read().any()
+    # from an existing neighbour list: one increment per stored distance
+    nl = dp.ball_query(None, flavour, r, 0.0, True)
+    rdf.accumulate_nlist(nl)
+    assert np.array_equal(rdf.read(), want)
+
+
+def test_rdf_many_bins_global_histogram(ctx):
+    capi = _capi()
+    box, n, r = BOXES["cubic"]
+    pts = random_points(box, n, seed=23)
+    dp = capi.DevicePoints(ctx, box, pts)
+    bins = 20000  # > 48 KB of counters: the kernel bins straight into global memory
+    rdf = capi.DeviceRDF(ctx, bins, r)
+    rdf.accumulate(dp, None, IMAGE, r, 0.0, True)
+    assert np.array_equal(rdf.read(), port.rdf_accumulate(IMAGE, box, False, pts, pts, bins, r, 0.0, True))
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+def test_knn(ctx, name):
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=31)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    q = pts[:400]
+    for k, sbd in ((12, False), (6, True), (1, False)):
+        got = dp.knn_query(q, k, exclude_ii=True, sort_by_distance=sbd).to_host()
+        if ref.available():
+            want = ref.Query("aabb", box, pts, is2d=box.is2D).nlist(q, num_neighbors=k, exclude_ii=True,
+                                                                     sort_by_distance=sbd)
+        else:
+            want = port.knn_nlist(box, box.is2D, pts, q, k, exclude_ii=True, sort_by_distance=sbd)
+        assert_nlist_equal(got, want, f"{name} knn k={k}")
+
+
+def test_knn_r_max_r_min(ctx):
+    box, n, r = BOXES["cubic"]
+    pts = random_points(box, n, seed=32)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    got = dp.knn_query(pts[:300], 12, r_max=1.6, r_min=0.7, exclude_ii=True).to_host()
+    want = ref.Query("aabb", box, pts).nlist(pts[:300], num_neighbors=12, r_max=1.6, r_min=0.7, exclude_ii=True) \
+        if ref.available() else port.knn_nlist(box, False, pts, pts[:300], 12, 1.6, 0.7, True)
+    assert_nlist_equal(got, want, "knn r_max r_min")
+
+
+def test_steinhardt_fcc_known_answer(ctx):
+    """PERFECT_FCC_Q6 = 0.57452416 (reference tests/test_order_steinhardt.py:17, :101-166), k = 12."""
+    from freud_b200 import data
+
+    capi = _capi()
+    box, pts = data.make_fcc_system(4)
+    dp = capi.DevicePoints(ctx, box, pts)
+    nl = dp.knn_query(None, 12, exclude_ii=True)
+    out = dp.steinhardt(nl, [6])
+    assert np.allclose(out["ql"], 0.57452416, atol=1e-5)
+    assert abs(out["order"][0] - 0.57452416) < 1e-5
+    # ball query r_max = 1.5 * nn distance gives the same shell
+    nl = dp.ball_query(None, IMAGE, 0.8, 0.0, True)
+    assert np.allclose(dp.steinhardt(nl, [6])["ql"], 0.57452416, atol=1e-5)
+
+
+@pytest.mark.parametrize("ls", [[6], [4], [4, 6], [2, 8, 12], [3], [0, 1, 5], [20]])
+def test_steinhardt_vs_oracle(ctx, ls):
+    from freud_b200 import data
+
+    capi = _capi()
+    box, pts = data.make_fcc_system(5, scale=1.3, sigma_noise=0.08, seed=3)
+    dp = capi.DevicePoints(ctx, box, pts)
+    nl = dp.knn_query(None, 12, exclude_ii=True)
+    got = dp.steinhardt(nl, ls)
+    h = nl.to_host()
+
+    class _NL:
+        neighbors, distances, weights, segments, counts = (h["neighbors"], h["distances"], h["weights"],
+                                                           h["segments"], h["counts"])
+
+    want = port.steinhardt(box, False, pts, _NL, ls)
+    assert np.allclose(got["ql"], want["ql"], rtol=1e-5, atol=1e-6)
+    for a, b in zip(got["qlm"], want["qlm"]):
+        assert np.allclose(a, b, atol=1e-5)
+    assert np.allclose(got["order"], want["order"], rtol=1e-4, atol=1e-6)
+
+
+def test_steinhardt_no_neighbours_is_nan(ctx):
+    """tests/test_order_steinhardt.py:361-369."""
+    capi = _capi()
+    from freud_b200.box import Box
+
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [0.5, 0, 0], [4, 4, 4]], np.float32)
+    dp = capi.DevicePoints(ctx, box, pts)
+    nl = dp.ball_query(None, IMAGE, 1.0, 0.0, True)
+    ql = dp.steinhardt(nl, [6])["ql"][:, 0]
+    assert np.isfinite(ql[0]) and np.isfinite(ql[1]) and np.isnan(ql[2])
+
+
+@pytest.mark.parametrize("flavour", [WRAP, IMAGE])
+def test_medium_system_properties(ctx, flavour):
+    """N = 200k: counts vs the port, reciprocity of the pair set, RDF == histogram of the list."""
+    from freud_b200 import data
+
+    capi = _capi()
+    box, pts = data.make_random_system(135.72, 200000, seed=5)
+    dp = capi.DevicePoints(ctx, box, pts)
+    nl = dp.ball_query(None, flavour, 3.0, 0.0, True)
+    got = nl.to_host()
+    want = port.ball_nlist(flavour, box, False, pts, pts, 3.0, 0.0, True)
+    assert_nlist_equal(got, want, "200k")
+    i, j = got["neighbors"][:, 0].astype(np.int64), got["neighbors"][:, 1].astype(np.int64)
+    fwd = np.sort(i * len(pts) + j)
+    bwd = np.sort(j * len(pts) + i)
+    # the pair set is symmetric up to bonds sitting on the r_max rounding edge: neither wrap(p_j - p_i) nor
+    # p_j - (p_i + image) is bitwise antisymmetric in float32 (the reference shows the same asymmetry)
+    assert len(np.setxor1d(fwd, bwd)) <= 1e-4 * len(fwd)
+    rdf = capi.DeviceRDF(ctx, 100, 3.0)
+    rdf.accumulate(dp, None, flavour, 3.0, 0.0, True)
+    assert np.array_equal(rdf.read(), port.rdf_accumulate_distances(got["distances"], 100, 3.0))
