@@ -1,0 +1,637 @@
+#!/usr/bin/env python
+"""Benchmark of the neighbour-query + pair-accumulation hot path (contract: see DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload nl|rdf|q6|rdf4m|traj2d]
+
+Default workload ("nl", BASELINE.json configs[1]): LinkCell neighbour-list query, r_max = 3, exclude_ii, on 1 M
+uniform random points in a cubic periodic box at density 0.08; one step = cell-list build + 27-cell pair search +
+sorted CSR NeighborList (all five arrays) for one frame.  Metric: neighbour pair evaluations per second, where a
+pair evaluation is one execution of the reference's distance arithmetic on a (query, candidate) pair of the
+27-cell scheme (the same count for the reference's own LinkCell at cell_width = r_max).
+N > 1 (torchrun, one rank per GPU): every rank processes its own frame (seed = rank), no data-path collective,
+"scaling": "weak".  The other workloads are the remaining BASELINE.json configs and print the same line shape.
+
+Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being timed beside the GPU path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO = 0.08
+WRAP, IMAGE = 0, 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = max(mx, float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def pinned_empty(shape, dtype):
+    """numpy view of pinned host memory (torch is plumbing here: it owns the page-locked allocation)."""
+    import torch
+
+    tdt = {np.float32: torch.float32, np.uint32: torch.int32}[dtype]
+    t = torch.empty(tuple(int(s) for s in np.atleast_1d(shape)), dtype=tdt, pin_memory=True)
+    return t.numpy().view(dtype), t  # the caller keeps t alive
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workloads: each returns dict(step_dev, step_e2e, units_per_step, unit, metric, config, h2d, d2h, algo_bytes)
+def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
+    from freud_b200 import _capi, data
+
+    L = (n / RHO) ** (1.0 / 3.0)
+    box, pts = data.make_random_system(L, n, seed=rank)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    # pair evaluations of one step, counted on the device in an untimed pass
+    ctx.count_pair_evals(True)
+    ctx.pair_evals(reset=True)
+    nl = dp.ball_query(None, flavour, r_max, 0.0, True)
+    evals = ctx.pair_evals(reset=True)
+    ctx.count_pair_evals(False)
+    n_bonds = nl.num_bonds
+    del nl
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+    out, keep = {}, [keep0]
+    for key, shape, dt in (("neighbors", (n_bonds, 2), np.uint32), ("distances", (n_bonds,), np.float32),
+                           ("weights", (n_bonds,), np.float32), ("vectors", (n_bonds, 3), np.float32),
+                           ("segments", (n,), np.uint32), ("counts", (n,), np.uint32)):
+        out[key], t = pinned_empty(shape, dt)
+        keep.append(t)
+
+    def step_dev():
+        dp.build_cells(r_max)  # forced rebuild: the cell list is part of every frame
+        return dp.ball_query(None, flavour, r_max, 0.0, True)
+
+    def step_e2e():
+        # the call sequence behind LinkCell(box, points).query(points, dict(r_max=3, exclude_ii=True)).toNeighborList()
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        lst = d.ball_query(None, flavour, r_max, 0.0, True)
+        lst.to_host(into=out)
+        return out["neighbors"][-1, 1]
+
+    n_cells = int(np.prod(dp.build_cells(r_max)))
+    algo = {
+        # per launch, bytes that must move (DESIGN.md "Kernels"): fp32 positions, 16 B float4 on device
+        "cell_assign": 12 * n + 8 * n + 4 * n_cells,
+        "cell_scatter": 20 * n + 16 * n,
+        "search_count": 16 * (n + n) + 4 * n_cells + 4 * n,
+        "search_fill": 16 * (n + n) + 4 * n_cells + 4 * n + 16 * n_bonds,
+        "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
+        "pipeline": 16 * (n + n) + 28 * n_bonds + 8 * n,  # SURVEY.md section 8d "NL emit"
+    }
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=evals, unit="pair_evals/s",
+                metric="neighbour_pair_evals_per_sec",
+                config={"workload": f"LinkCell NeighborList r_max={r_max:g} exclude_ii N={n} cubic L={L:.4f} rho=0.08 "
+                                    f"flavour={'wrap' if flavour == WRAP else 'image'}",
+                        "bonds_per_step": n_bonds, "pair_evals_per_step": evals, "n_cells": n_cells},
+                h2d=12 * n, d2h=28 * n_bonds + 8 * n, algo=algo, keep=keep, box=box, pts=pts, r_max=r_max,
+                secondary={"bonds": n_bonds})
+
+
+def workload_rdf(ctx, rank, n, bins=100, r_max=5.0, flavour=IMAGE, tilt=None, is2d=False, density=RHO):
+    from freud_b200 import _capi, data
+
+    L = (n / density) ** (0.5 if is2d else 1.0 / 3.0)
+    box, pts = data.make_random_system(L, n, is2D=is2d, seed=rank, tilt=tilt)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    rdf = _capi.DeviceRDF(ctx, bins, r_max)
+    ctx.count_pair_evals(True)
+    ctx.pair_evals(reset=True)
+    rdf.accumulate(dp, None, flavour, r_max, 0.0, True)
+    evals = ctx.pair_evals(reset=True)
+    ctx.count_pair_evals(False)
+    n_bonds = int(rdf.read().astype(np.uint64).sum())
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+
+    def step_dev():
+        dp.build_cells(r_max)
+        rdf.accumulate(dp, None, flavour, r_max, 0.0, True)
+
+    def step_e2e():
+        # RDF(bins, r_max).compute((box, points), reset=False) then .bin_counts
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        rdf.accumulate(d, None, flavour, r_max, 0.0, True)
+        return rdf.read()
+
+    n_cells = int(np.prod(dp.build_cells(r_max)))
+    algo = {"search_rdf": 16 * (n + n) + 4 * n_cells + 4 * bins, "pipeline": 16 * (n + n) + 4 * bins,
+            "cell_assign": 20 * n + 4 * n_cells, "cell_scatter": 36 * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=1, unit="frames/s", metric="rdf_frames_per_sec",
+                config={"workload": f"RDF bins={bins} r_max={r_max:g} N={n} L={L:.4f} "
+                                    f"{'2D ' if is2d else ''}{'triclinic ' if tilt else ''}"
+                                    f"flavour={'wrap' if flavour == WRAP else 'image'} fused (no NeighborList)",
+                        "bonds_per_step": n_bonds, "pair_evals_per_step": evals},
+                h2d=12 * n, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max, rdf=rdf, dp=dp,
+                secondary={"pair_evals_per_sec_factor": evals})
+
+
+def workload_q6(ctx, rank, n):
+    from freud_b200 import _capi, data
+
+    m = max(2, round((n / 4) ** (1.0 / 3.0)))
+    box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=rank)
+    n = len(pts)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+
+    def step_dev():
+        dp.build_cells(1.0)
+        nl = dp.knn_query(None, 12, exclude_ii=True)
+        return dp.steinhardt(nl, [6], want_qlm=False)
+
+    def step_e2e():
+        # Steinhardt(6).compute((box, points), neighbors=dict(num_neighbors=12)) then .particle_order
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        nl = d.knn_query(None, 12, exclude_ii=True)
+        return d.steinhardt(nl, [6], want_qlm=True)["ql"]
+
+    algo = {"steinhardt": 588 * n, "knn": 16 * (n + n) + 8 * 12 * n, "pipeline": 124 * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
+                config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
+                h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0], box=box, pts=pts, secondary={})
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_nl(box, pts, r_max, budget_s=12.0, threads=None):
+    """The reference's own LinkCell (oracle/_ref, all host threads) on a bounded sample of query points.
+
+    The unmodified LinkCell deep-copies the whole cell list per visited cell, so only a few
+    thousand query points fit the budget at N = 1e6; its AABBQuery engine is timed beside it as the practical
+    CPU comparator."""
+    from oracle import port, ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    out = {"cores": threads, "kind": "reference" if ref.available() else "port"}
+    if not ref.available():
+        t0 = time.perf_counter()
+        nl = port.ball_nlist(port.WRAP, box, box.is2D, pts, pts, r_max, 0.0, True)
+        dt = time.perf_counter() - t0
+        ev = port.count_candidates(box, box.is2D, pts, pts, r_max)
+        out.update(value=ev / dt, unit="pair_evals/s", sample=f"oracle port, all {len(pts)} query points, {dt:.2f} s",
+                   bonds_per_sec=len(nl) / dt)
+        return out
+    t0 = time.perf_counter()
+    q = ref.Query("linkcell", box, pts, cell_width=r_max)
+    build_s = time.perf_counter() - t0
+    m = min(len(pts), 8 * threads)
+    t0 = time.perf_counter()
+    q.nlist(pts[:m], r_max=r_max, exclude_ii=True)
+    probe = time.perf_counter() - t0
+    m2 = int(min(len(pts), max(m, m * budget_s / max(probe, 1e-6))))
+    t0 = time.perf_counter()
+    nl = q.nlist(pts[:m2], r_max=r_max, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    ev = port.count_candidates(box, box.is2D, pts, pts[:m2], r_max)
+    out.update(value=ev / dt, unit="pair_evals/s", bonds_per_sec=len(nl) / dt,
+               sample=f"reference LinkCell(cell_width={r_max:g}) N={len(pts)}: first {m2} query points in {dt:.2f} s "
+                      f"(+{build_s:.2f} s serial build, not counted)")
+    # practical engine: AABBQuery on a sample sized to the same budget
+    t0 = time.perf_counter()
+    qa = ref.Query("aabb", box, pts)
+    ma = min(len(pts), 20000)
+    qa.nlist(pts[:ma], r_max=r_max, exclude_ii=True)
+    probe = time.perf_counter() - t0
+    ma2 = int(min(len(pts), max(ma, ma * 0.5 * budget_s / max(probe, 1e-6))))
+    t0 = time.perf_counter()
+    nla = qa.nlist(pts[:ma2], r_max=r_max, exclude_ii=True)
+    dta = time.perf_counter() - t0
+    eva = port.count_candidates(box, box.is2D, pts, pts[:ma2], r_max)
+    out["aabb"] = {"value": eva / dta, "unit": "pair_evals/s (27-cell-equivalent)", "bonds_per_sec": len(nla) / dta,
+                   "sample": f"reference AABBQuery N={len(pts)}: first {ma2} query points in {dta:.2f} s"}
+    return out
+
+
+def cpu_reference_rdf(box, pts, bins, r_max, budget_s=12.0, threads=None):
+    from oracle import port, ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        t0 = time.perf_counter()
+        port.rdf_accumulate(port.IMAGE, box, box.is2D, pts, pts, bins, r_max, 0.0, True)
+        dt = time.perf_counter() - t0
+        return {"value": 1.0 / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+                "sample": f"oracle port full frame {dt:.2f} s"}
+    q = ref.Query("raw", box, pts, is2d=box.is2D)
+    m = min(len(pts), 20000)
+    R = ref.RDF(bins, r_max)
+    t0 = time.perf_counter()
+    R.accumulate(q, pts[:m], mode="ball", r_max=r_max, exclude_ii=True)
+    probe = time.perf_counter() - t0
+    m2 = int(min(len(pts), max(m, m * budget_s / max(probe, 1e-6))))
+    R = ref.RDF(bins, r_max)
+    t0 = time.perf_counter()
+    R.accumulate(q, pts[:m2], mode="ball", r_max=r_max, exclude_ii=True)
+    R.results()
+    dt = time.perf_counter() - t0
+    return {"value": (m2 / len(pts)) / dt, "unit": "frames/s", "cores": threads, "kind": "reference",
+            "sample": f"reference RDF.accumulate via RawPoints/AABBQuery: first {m2} of {len(pts)} query points in "
+                      f"{dt:.2f} s, scaled to a full frame"}
+
+
+def cpu_reference_q6(box, pts, budget_s=12.0, threads=None):
+    from oracle import ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        return {"value": None, "unit": "particles/s", "cores": threads, "kind": "port", "sample": "unavailable"}
+    q = ref.Query("raw", box, pts)
+    S = ref.Steinhardt(6)
+    t0 = time.perf_counter()
+    S.compute(q, num_neighbors=12, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    return {"value": len(pts) / dt, "unit": "particles/s", "cores": threads, "kind": "reference",
+            "sample": f"reference Steinhardt(6).compute k=12 on all {len(pts)} particles in {dt:.2f} s"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d"])
+    ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
+                 "rdf4m": 4_000_000, "traj2d": 1_000_000}[args.workload]
+    n = args.n or n_default
+
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world, n)
+
+    import torch
+    import torch.distributed as dist
+
+    from freud_b200 import _capi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    comm = None
+    if world > 1 and args.workload in ("rdf4m", "traj2d"):
+        uid = [_capi.Communicator.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = _capi.Communicator(ctx, uid[0], rank, world)
+
+    if args.workload in ("nl", "nl_image"):
+        w = workload_nl(ctx, rank, n, WRAP if args.workload == "nl" else IMAGE)
+        scaling = "weak"
+    elif args.workload in ("rdf", "rdf_wrap"):
+        w = workload_rdf(ctx, rank, n, flavour=IMAGE if args.workload == "rdf" else WRAP)
+        scaling = "weak"
+    elif args.workload == "q6":
+        w = workload_q6(ctx, rank, n)
+        scaling = "weak"
+    elif args.workload == "rdf4m":
+        w = workload_rdf4m(ctx, rank, world, n, comm)
+        scaling = "strong"
+    else:
+        w = workload_traj2d(ctx, rank, world, n, comm)
+        scaling = "weak"
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ("value") ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        w["step_dev"]()
+    barrier()
+    ctx.profile(True)
+    ctx.kernel_time(reset=True)
+    launches0 = ctx.launch_count
+    events = []
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()  # L2 flush between steps (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = w["step_dev"]()
+            e1.record(stream)
+            events.append((e0, e1))
+            del out
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    launches = ctx.launch_count - launches0
+    ctx.profile(False)
+    # dominant kernel over the timed region
+    per_kernel = {}
+    for name in ("cell_assign", "cell_scatter", "scan", "search_count", "search_fill", "search_rdf", "emit", "segments",
+                 "knn_emit", "knn", "rdf_distances", "steinhardt"):
+        ms, cnt = ctx.kernel_time(name)
+        if name == "knn":
+            ms2, cnt2 = ctx.kernel_time("knn_emit")
+            ms, cnt = ms - ms2, cnt - cnt2
+        if cnt:
+            per_kernel[name] = (ms, cnt)
+    ctx.kernel_time(reset=True)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    ms_per_step = dev_ms_max / args.steps
+    value = w["units"] * world * args.steps / (dev_ms_max / 1e3)
+
+    # ---- end-to-end leg ("e2e"): host buffers in, host result out, through the C ABI --------------------
+    for _ in range(2):
+        w["step_e2e"]()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        w["step_e2e"]()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = w["units"] * world * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    roofline = None
+    if per_kernel:
+        name = max(per_kernel, key=lambda k: per_kernel[k][0])
+        ms, cnt = per_kernel[name]
+        avg_ms = ms / cnt
+        algo = w["algo"].get(name)
+        if algo:
+            achieved = algo / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(achieved / peak, 4), "traffic": None, "avg_launch_ms": round(avg_ms, 4),
+                        "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
+                        "share_of_step": round(ms / dev_ms, 3),
+                        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in per_kernel.items()}}
+    pipe = w["algo"]["pipeline"] / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(w["config"], l2="256 MB memset between timed steps (outside the event pairs)",
+                       timing="CUDA events on the library's stream, max over ranks"),
+        "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(w["h2d"]),
+                "d2h_bytes_per_step": int(w["d2h"]), "ms_per_step": e2e_s * 1e3 / args.steps,
+                "host_buffers": "pinned"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "roofline_step": {"bound": "hbm", "achieved": round(pipe, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(pipe / peak, 4),
+                          "note": "whole step: SURVEY.md 8d algorithmic bytes / ms_per_step"},
+        "wall_s": t_wall,
+    }
+    if "bonds" in w["secondary"]:
+        line["bonds_per_sec"] = w["secondary"]["bonds"] * world * args.steps / (dev_ms_max / 1e3)
+    if "pair_evals_per_sec_factor" in w["secondary"]:
+        line["pair_evals_per_sec"] = w["secondary"]["pair_evals_per_sec_factor"] * world * args.steps / (dev_ms_max / 1e3)
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            if args.workload in ("nl", "nl_image"):
+                line["cpu_baseline"] = cpu_reference_nl(w["box"], w["pts"], w["r_max"])
+            elif args.workload in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
+                line["cpu_baseline"] = cpu_reference_rdf(w["box"], w["pts"], w["rdf"].bins, w["r_max"])
+            else:
+                line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
+        except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def workload_rdf4m(ctx, rank, world, n, comm):
+    """BASELINE.json configs[3]: one 4 M-point triclinic frame, query points sharded, one u32 allreduce."""
+    from freud_b200 import _capi, data
+
+    bins, r_max = 500, 5.0
+    L = (n / RHO) ** (1.0 / 3.0)
+    box, pts = data.make_random_system(L, n, seed=0, tilt=(0.3, 0.2, 0.1))
+    dp = _capi.DevicePoints(ctx, box, pts)
+    rdf = _capi.DeviceRDF(ctx, bins, r_max)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    shard = np.ascontiguousarray(pts[lo:hi])
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+    pin_q, keep1 = pinned_empty((hi - lo, 3), np.float32)
+    pin_q[:] = shard
+
+    def step_dev():
+        rdf.reset()
+        dp.build_cells(r_max)
+        if world == 1:
+            rdf.accumulate(dp, None, IMAGE, r_max, 0.0, True)
+        else:
+            rdf.accumulate(dp, pin_q, IMAGE, r_max, 0.0, True, q_index_offset=lo)
+            rdf.allreduce(comm)
+
+    def step_e2e():
+        rdf.reset()
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        if world == 1:
+            rdf.accumulate(d, None, IMAGE, r_max, 0.0, True)
+        else:
+            rdf.accumulate(d, pin_q, IMAGE, r_max, 0.0, True, q_index_offset=lo)
+            rdf.allreduce(comm)
+        return rdf.read()
+
+    step_dev()
+    n_bonds = int(rdf.read().astype(np.uint64).sum())
+    n_cells = int(np.prod(dp.build_cells(r_max)))
+    nq = hi - lo
+    algo = {"search_rdf": 16 * (n + nq) + 4 * n_cells + 4 * bins, "pipeline": 16 * (n + nq) + 4 * bins,
+            "cell_assign": 20 * n + 4 * n_cells, "cell_scatter": 36 * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=1.0 / world, unit="frames/s",
+                metric="rdf_frames_per_sec",
+                config={"workload": f"RDF bins=500 r_max=5 N={n} triclinic (xy=.3,xz=.2,yz=.1) L={L:.4f} query points "
+                                    f"sharded over {world} GPU(s), points replicated, ncclAllReduce(u32[500])",
+                        "bonds_per_step": n_bonds},
+                h2d=12 * n + 12 * nq, d2h=4 * bins, algo=algo, keep=[keep0, keep1], box=box, pts=pts, r_max=r_max,
+                rdf=rdf, dp=dp, secondary={})
+
+
+def workload_traj2d(ctx, rank, world, n, comm, frames_per_rank=8):
+    """BASELINE.json configs[4]: 2-D trajectory, reset=False accumulation, frames sharded across ranks."""
+    from freud_b200 import _capi, data
+
+    bins, r_max = 100, 5.0
+    L = (n / 0.5) ** 0.5
+    frames = [data.make_random_system(L, n, is2D=True, seed=rank * frames_per_rank + f) for f in range(frames_per_rank)]
+    box = frames[0][0]
+    pins, keep = [], []
+    for _, p in frames:
+        a, t = pinned_empty((n, 3), np.float32)
+        a[:] = p
+        pins.append(a)
+        keep.append(t)
+    rdf = _capi.DeviceRDF(ctx, bins, r_max)
+    dps = [_capi.DevicePoints(ctx, box, p) for _, p in frames]
+
+    def step_dev():
+        rdf.reset()
+        for d in dps:
+            d.build_cells(r_max)
+            rdf.accumulate(d, None, IMAGE, r_max, 0.0, True)
+        if comm is not None:
+            rdf.allreduce(comm)
+
+    def step_e2e():
+        rdf.reset()
+        for a in pins:
+            d = _capi.DevicePoints(ctx, box, a)
+            rdf.accumulate(d, None, IMAGE, r_max, 0.0, True)
+        if comm is not None:
+            rdf.allreduce(comm)
+        return rdf.read()
+
+    algo = {"search_rdf": 16 * 2 * n + 4 * bins, "pipeline": frames_per_rank * (16 * 2 * n + 4 * bins),
+            "cell_assign": 20 * n, "cell_scatter": 36 * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=frames_per_rank, unit="frames/s",
+                metric="rdf_frames_per_sec",
+                config={"workload": f"trajectory RDF bins=100 r_max=5 reset=False, {frames_per_rank} frames/GPU of N={n} "
+                                    f"2-D square L={L:.4f}, frames sharded over {world} GPU(s), one allreduce at the end"},
+                h2d=12 * n * frames_per_rank, d2h=4 * bins, algo=algo, keep=keep, box=box, pts=frames[0][1],
+                r_max=r_max, rdf=rdf, dp=dps[0], secondary={})
+
+
+def run_reference_arm(args, rank, world, n):
+    """--impl reference: the reference's own CPU implementation on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from freud_b200 import data
+
+    threads = os.cpu_count()
+    steps = max(1, min(args.steps, 3))
+    budget = 8.0
+    if args.workload in ("nl", "nl_image"):
+        L = (n / RHO) ** (1.0 / 3.0)
+        box, pts = data.make_random_system(L, n, seed=0)
+        runs = [cpu_reference_nl(box, pts, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        metric, unit = "neighbour_pair_evals_per_sec", "pair_evals/s"
+        config = {"workload": f"LinkCell NeighborList r_max=3 exclude_ii N={n} cubic L={L:.4f} rho=0.08 flavour=wrap"}
+    elif args.workload in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
+        is2d = args.workload == "traj2d"
+        L = (n / (0.5 if is2d else RHO)) ** (0.5 if is2d else 1.0 / 3.0)
+        tilt = (0.3, 0.2, 0.1) if args.workload == "rdf4m" else None
+        box, pts = data.make_random_system(L, n, is2D=is2d, seed=0, tilt=tilt)
+        bins = 500 if args.workload == "rdf4m" else 100
+        runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        metric, unit = "rdf_frames_per_sec", "frames/s"
+        config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"}
+    else:
+        m = max(2, round((n / 4) ** (1.0 / 3.0)))
+        box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=0)
+        runs = [cpu_reference_q6(box, pts, threads=threads) for _ in range(steps)]
+        metric, unit = "q6_particles_per_sec", "particles/s"
+        config = {"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={len(pts)} sigma=0.05"}
+    vals = [r["value"] for r in runs if r.get("value")]
+    value = float(np.median(vals)) if vals else None
+    base = dict(runs[-1], value=value)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps,
+            "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,8 @@ SIGNATURES = {
     "fgpu_ctx_launch_count": (C.c_uint64, [_vp]),
     "fgpu_ctx_count_pair_evals": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_pair_evals": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "fgpu_ctx_profile": (C.c_int, [_vp, C.c_int]),
+    "fgpu_ctx_kernel_time": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
     "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
     "fgpu_points_destroy": (None, [_vp]),
@@ -155,6 +157,15 @@ class Context:
         out = C.c_uint64()
         check(lib().fgpu_ctx_pair_evals(self._h, C.byref(out), int(reset)))
         return int(out.value)
+
+    def profile(self, enable=True):
+        check(lib().fgpu_ctx_profile(self._h, int(enable)))
+
+    def kernel_time(self, prefix="", reset=False):
+        """(summed ms, launches) of the profiled kernels whose name starts with prefix."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(lib().fgpu_ctx_kernel_time(self._h, prefix.encode(), C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, int(n.value)
 
     def close(self):
         if self._h:

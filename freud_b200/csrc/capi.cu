@@ -24,6 +24,12 @@ void set_last_error(const std::string& msg)
     g_last_error = msg;
 }
 
+cudaStream_t& current_stream()
+{
+    static thread_local cudaStream_t stream = nullptr;
+    return stream;
+}
+
 namespace {
 
 template<typename F> int guarded(F&& f)
@@ -139,6 +145,14 @@ void sync(fgpu_ctx* ctx)
 void bind_device(fgpu_ctx* ctx)
 {
     FGPU_CUDA_CHECK(cudaSetDevice(ctx->device));
+    current_stream() = ctx->stream;
+}
+
+// for the destroy paths, which must not throw
+void bind_quiet(fgpu_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    current_stream() = ctx->stream;
 }
 
 struct QueryView
@@ -292,7 +306,8 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         launch_emit(ctx, flavour, e);
     }
     launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
-    sync(ctx); // q_stage / bag are context scratch: the list must be complete before they are reused
+    // no final sync: every consumer of the list (copy, RDF, Steinhardt, destroy) is ordered on the same stream,
+    // and the host query buffer was consumed before the bond total was read back above
     *out = nl.release();
 }
 
@@ -464,6 +479,12 @@ int fgpu_ctx_create(int device, fgpu_ctx** out)
         std::unique_ptr<fgpu_ctx> ctx(new fgpu_ctx());
         ctx->device = device;
         FGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        current_stream() = ctx->stream;
+        // keep freed blocks in the stream-ordered pool instead of handing them back to the driver
+        cudaMemPool_t pool = nullptr;
+        FGPU_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t threshold = UINT64_MAX;
+        FGPU_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
         FGPU_CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
         FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_scalars), 8 * sizeof(unsigned long long)));
         FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_evals), sizeof(unsigned long long)));
@@ -481,8 +502,13 @@ void fgpu_ctx_destroy(fgpu_ctx* ctx)
     {
         return;
     }
-    cudaSetDevice(ctx->device);
+    bind_quiet(ctx);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->timers)
+    {
+        cudaEventDestroy(t.begin);
+        cudaEventDestroy(t.end);
+    }
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_evals);
     cudaFreeHost(ctx->h_scalars);
@@ -534,6 +560,53 @@ int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset)
         }
         sync(ctx);
         *out = ctx->h_scalars[1];
+    });
+}
+
+int fgpu_ctx_profile(fgpu_ctx* ctx, int enable)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        ctx->profile = enable != 0;
+    });
+}
+
+int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(ctx);
+        sync(ctx);
+        size_t const plen = prefix != nullptr ? std::strlen(prefix) : 0;
+        double ms = 0.0;
+        uint64_t launches = 0;
+        for (const auto& t : ctx->timers)
+        {
+            if (plen == 0 || std::strncmp(t.name, prefix, plen) == 0)
+            {
+                float e = 0.0f;
+                FGPU_CUDA_CHECK(cudaEventElapsedTime(&e, t.begin, t.end));
+                ms += e;
+                launches += 1;
+            }
+        }
+        if (ms_out != nullptr)
+        {
+            *ms_out = ms;
+        }
+        if (launches_out != nullptr)
+        {
+            *launches_out = launches;
+        }
+        if (reset)
+        {
+            for (auto& t : ctx->timers)
+            {
+                cudaEventDestroy(t.begin);
+                cudaEventDestroy(t.end);
+            }
+            ctx->timers.clear();
+        }
     });
 }
 
@@ -592,8 +665,7 @@ void fgpu_points_destroy(fgpu_points* pts)
 {
     if (pts != nullptr)
     {
-        cudaSetDevice(pts->ctx->device);
-        cudaStreamSynchronize(pts->ctx->stream);
+        bind_quiet(pts->ctx); // frees are stream-ordered behind any pending work
         delete pts;
     }
 }
@@ -888,8 +960,7 @@ void fgpu_nlist_destroy(fgpu_nlist* nl)
 {
     if (nl != nullptr)
     {
-        cudaSetDevice(nl->ctx->device);
-        cudaStreamSynchronize(nl->ctx->stream);
+        bind_quiet(nl->ctx);
         delete nl;
     }
 }
@@ -926,8 +997,7 @@ void fgpu_rdf_destroy(fgpu_rdf* rdf)
 {
     if (rdf != nullptr)
     {
-        cudaSetDevice(rdf->ctx->device);
-        cudaStreamSynchronize(rdf->ctx->stream);
+        bind_quiet(rdf->ctx);
         delete rdf;
     }
 }
@@ -1131,7 +1201,7 @@ void fgpu_comm_destroy(fgpu_comm* comm)
 {
     if (comm != nullptr)
     {
-        cudaSetDevice(comm->ctx->device);
+        bind_quiet(comm->ctx);
         cudaStreamSynchronize(comm->ctx->stream);
         if (comm->nccl_comm != nullptr && nccl().handle != nullptr)
         {

@@ -105,15 +105,17 @@ void scan_level(fgpu_ctx* ctx, uint32_t* data, size_t n, uint32_t* tmp)
     size_t const tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles <= 1)
     {
+        KernelScope ks(ctx, "scan");
         k_scan_tiles<<<1, kScanThreads, 0, ctx->stream>>>(data, n, nullptr);
-        ctx->launches += 1;
         return;
     }
-    k_scan_tiles<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "scan");
+        k_scan_tiles<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
+    }
     scan_level(ctx, tmp, tiles, tmp + tiles);
+    KernelScope ks(ctx, "scan");
     k_scan_add<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
-    ctx->launches += 1;
 }
 
 // K1: cell index + arrival rank (one atomic per point) -- 12 B read, 8 B written per point
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy
                                                       uint32_t n, const uint32_t* __restrict__ cell_of,
                                                       const uint32_t* __restrict__ rank_in,
                                                       const uint32_t* __restrict__ cell_start,
-                                                      float4* __restrict__ sorted, int* __restrict__ shift)
+                                                      float4* __restrict__ sorted, int* __restrict__ shift,
+                                                      const int* __restrict__ any_shift)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy
     float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
     uint32_t const slot = cell_start[cell_of[i]] + rank_in[i];
     sorted[slot] = make_float4(x, y, z, __uint_as_float(i));
-    if (shift != nullptr)
+    if (shift != nullptr && *any_shift != 0)
     {
         int cx, cy, cz, nx, ny, nz;
         cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
@@ -228,10 +231,10 @@ GridDev grid_dev(const fgpu_points* pts)
     d.amb_x = g.ambiguous[0];
     d.amb_y = g.ambiguous[1];
     d.amb_z = g.ambiguous[2];
-    d.any_shift = g.any_shift ? 1 : 0;
+    d.any_shift_flag = g.any_shift_flag.ptr;
     d.cell_start = g.cell_start.ptr;
     d.sorted = g.sorted.ptr;
-    d.shift = g.any_shift ? g.shift.ptr : nullptr;
+    d.shift = g.shift.ptr;
     return d;
 }
 
@@ -253,26 +256,25 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
     g.cell_start.reserve((size_t) n_cells + 1);
     g.sorted.reserve(n);
     FGPU_CUDA_CHECK(cudaMemsetAsync(g.cell_start.ptr, 0, ((size_t) n_cells + 1) * sizeof(uint32_t), ctx->stream));
-    int* d_flag = reinterpret_cast<int*>(ctx->d_scalars + 7);
-    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned long long), ctx->stream));
+    // out-of-box flag: set on the device by K1, read on the device by K3 and the search kernels, so the
+    // build needs no host round trip; the shift array is only ever written when the flag is set
+    g.shift.reserve(n);
+    g.any_shift_flag.reserve(1);
+    int* d_flag = g.any_shift_flag.ptr;
+    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
     unsigned const blocks = (n + 255) / 256;
-    k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_of.ptr,
-                                                   g.rank_in.ptr, g.cell_start.ptr, d_flag);
-    ctx->launches += 1;
-    exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1);
-    // the out-of-box flag decides whether the shift array is needed at all (it almost never is)
-    FGPU_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars + 7, d_flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                    ctx->stream));
-    FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    g.any_shift = ctx->h_scalars[7] != 0;
-    if (g.any_shift)
     {
-        g.shift.reserve(n);
+        KernelScope ks(ctx, "cell_assign");
+        k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
+                                                       g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag);
     }
-    k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_of.ptr,
-                                                    g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
-                                                    g.any_shift ? g.shift.ptr : nullptr);
-    ctx->launches += 1;
+    exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1);
+    {
+        KernelScope ks(ctx, "cell_scatter");
+        k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
+                                                        g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
+                                                        g.shift.ptr, d_flag);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
     for (int d = 0; d < 3; ++d)
     {
@@ -295,14 +297,19 @@ void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
         cudaMemsetAsync(ctx->q_cell_start.ptr, 0, ((size_t) g.n_cells + 1) * sizeof(uint32_t), ctx->stream));
     int* d_flag = reinterpret_cast<int*>(ctx->d_scalars + 6); // unused result
     unsigned const blocks = (n_query + 255) / 256;
-    k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
-                                                   ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr, d_flag);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "cell_assign");
+        k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
+                                                       ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
+                                                       d_flag);
+    }
     exclusive_scan_u32(ctx, ctx->q_cell_start.ptr, (size_t) g.n_cells + 1);
-    k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
-                                                    ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
-                                                    ctx->q_sorted.ptr, nullptr);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "cell_scatter");
+        k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
+                                                        ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
+                                                        ctx->q_sorted.ptr, nullptr, nullptr);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 

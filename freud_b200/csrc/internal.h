@@ -31,6 +31,11 @@ void set_last_error(const std::string& msg);
         }                                                                                                        \
     } while (0)
 
+// The stream every allocation / free of the calling thread is ordered on; set by bind_device(ctx) at the top
+// of each entry point.  Allocation goes through CUDA's stream-ordered pool (release threshold = never), so a
+// NeighborList per frame costs microseconds instead of the milliseconds cudaMalloc/cudaFree take.
+cudaStream_t& current_stream();
+
 // ---- device buffer (grow-only, stream-ordered use on the context's single stream) -----------------
 template<typename T> struct DevBuf
 {
@@ -47,7 +52,7 @@ template<typename T> struct DevBuf
     {
         if (ptr != nullptr)
         {
-            cudaFree(ptr);
+            cudaFreeAsync(ptr, current_stream());
         }
         ptr = nullptr;
         cap = 0;
@@ -61,7 +66,7 @@ template<typename T> struct DevBuf
         }
         release();
         size_t const want = n + n / 8 + 64;
-        FGPU_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+        FGPU_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ptr), want * sizeof(T), current_stream()));
         cap = want;
     }
 };
@@ -93,7 +98,43 @@ struct fgpu_ctx
     unsigned long long* h_scalars = nullptr; // pinned mirror
     void* pinned_stage = nullptr;            // pinned staging for pageable H2D/D2H
     size_t pinned_bytes = 0;
+    // per-kernel timing (fgpu_ctx_profile)
+    struct TimerRec
+    {
+        const char* name;
+        cudaEvent_t begin, end;
+    };
+    bool profile = false;
+    std::vector<TimerRec> timers;
 };
+
+namespace fgpu {
+// Brackets one kernel launch: counts it and, when profiling, records an event pair on the stream.
+struct KernelScope
+{
+    fgpu_ctx* ctx;
+    cudaEvent_t begin = nullptr, end = nullptr;
+    const char* name;
+    KernelScope(fgpu_ctx* c, const char* n) : ctx(c), name(n)
+    {
+        ctx->launches += 1;
+        if (ctx->profile)
+        {
+            cudaEventCreate(&begin);
+            cudaEventCreate(&end);
+            cudaEventRecord(begin, ctx->stream);
+        }
+    }
+    ~KernelScope()
+    {
+        if (begin != nullptr)
+        {
+            cudaEventRecord(end, ctx->stream);
+            ctx->timers.push_back({name, begin, end});
+        }
+    }
+};
+} // namespace fgpu
 
 struct fgpu_grid
 {
@@ -101,7 +142,7 @@ struct fgpu_grid
     int dim[3] = {0, 0, 0};
     uint32_t n_cells = 0;
     int ambiguous[3] = {0, 0, 0}; // dim < 3 on a periodic axis: several images may map to one cell
-    bool any_shift = false;       // some point lies outside the box (integer image offset != 0)
+    fgpu::DevBuf<int> any_shift_flag; // device flag: some point lies outside the box (image offset != 0)
     fgpu::DevBuf<uint32_t> cell_of;    // per point
     fgpu::DevBuf<uint32_t> rank_in;    // per point: arrival rank inside its cell
     fgpu::DevBuf<uint32_t> cell_start; // n_cells + 1
@@ -164,7 +205,7 @@ struct GridDev
 {
     int dx, dy, dz;
     int amb_x, amb_y, amb_z;
-    int any_shift;
+    const int* any_shift_flag; // device flag, see fgpu_grid
     const uint32_t* cell_start;
     const float4* sorted;
     const int* shift;

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(KnnArgs a)
     uint32_t* const best_s = a.knn_s + qi;
     uint32_t count = 0;
     unsigned long long evals = 0;
+    bool const any_shift = *g.any_shift_flag != 0;
 
     int cx, cy, cz, nqx, nqy, nqz;
     cell_coords(box, g.dx, g.dy, g.dz, qx, qy, qz, cx, cy, cz, nqx, nqy, nqz);
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(KnnArgs a)
                         continue;
                     }
                     int njx = 0, njy = 0, njz = 0;
-                    if (g.any_shift)
+                    if (any_shift)
                     {
                         unpack_shift(__ldg(g.shift + s), njx, njy, njz);
                     }
@@ -254,8 +255,10 @@ void launch_knn(fgpu_ctx* ctx, const KnnArgs& a)
     {
         return;
     }
-    k_knn<<<(a.n_query + kKnnThreads - 1) / kKnnThreads, kKnnThreads, 0, ctx->stream>>>(a);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "knn");
+        k_knn<<<(a.n_query + kKnnThreads - 1) / kKnnThreads, kKnnThreads, 0, ctx->stream>>>(a);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -266,8 +269,10 @@ void launch_knn_emit(fgpu_ctx* ctx, const KnnEmitArgs& a)
     {
         return;
     }
-    k_knn_emit<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(a);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "knn_emit");
+        k_knn_emit<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(a);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 

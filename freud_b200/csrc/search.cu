@@ -32,6 +32,7 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                                                OnHit&& on_hit)
 {
     uint32_t evals = 0;
+    bool const any_shift = FLAVOUR == FGPU_FLAVOUR_IMAGE && *g.any_shift_flag != 0;
     if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
     {
         qz = 0.0f; // AABBQuery.cc:84-87
@@ -78,7 +79,7 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                 }
                 else
                 {
-                    bool const definite = wx != 2 && wy != 2 && wz != 2 && !g.any_shift;
+                    bool const definite = wx != 2 && wy != 2 && wz != 2 && !any_shift;
                     if (definite)
                     {
                         // all points are inside the box: the image is fixed by how the cell was reached
@@ -120,7 +121,7 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                                 continue;
                             }
                             int njx = 0, njy = 0, njz = 0;
-                            if (g.any_shift)
+                            if (any_shift)
                             {
                                 unpack_shift(__ldg(g.shift + s), njx, njy, njz);
                             }
@@ -401,16 +402,24 @@ template<int FLAVOUR> void launch_search_mode(fgpu_ctx* ctx, SearchMode mode, co
     switch (mode)
     {
     case SEARCH_COUNT:
+    {
+        KernelScope ks(ctx, "search_count");
         k_search<FLAVOUR, SEARCH_COUNT><<<blocks, kSearchThreads, 0, ctx->stream>>>(a);
         break;
+    }
     case SEARCH_FILL:
+    {
+        KernelScope ks(ctx, "search_fill");
         k_search<FLAVOUR, SEARCH_FILL><<<blocks, kSearchThreads, 0, ctx->stream>>>(a);
         break;
+    }
     case SEARCH_RDF:
+    {
+        KernelScope ks(ctx, "search_rdf");
         k_search<FLAVOUR, SEARCH_RDF><<<blocks, kSearchThreads, smem, ctx->stream>>>(a);
         break;
     }
-    ctx->launches += 1;
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -435,15 +444,17 @@ void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& a)
         return;
     }
     unsigned const blocks = (unsigned) ((a.n_bonds + 255) / 256);
-    if (flavour == FGPU_FLAVOUR_WRAP)
     {
-        k_emit<FGPU_FLAVOUR_WRAP><<<blocks, 256, 0, ctx->stream>>>(a);
+        KernelScope ks(ctx, "emit");
+        if (flavour == FGPU_FLAVOUR_WRAP)
+        {
+            k_emit<FGPU_FLAVOUR_WRAP><<<blocks, 256, 0, ctx->stream>>>(a);
+        }
+        else
+        {
+            k_emit<FGPU_FLAVOUR_IMAGE><<<blocks, 256, 0, ctx->stream>>>(a);
+        }
     }
-    else
-    {
-        k_emit<FGPU_FLAVOUR_IMAGE><<<blocks, 256, 0, ctx->stream>>>(a);
-    }
-    ctx->launches += 1;
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -454,8 +465,10 @@ void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* c
     {
         return;
     }
-    k_segments<<<(n_query + 255) / 256, 256, 0, ctx->stream>>>(row_start, counts, segments, n_query);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "segments");
+        k_segments<<<(n_query + 255) / 256, 256, 0, ctx->stream>>>(row_start, counts, segments, n_query);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -467,8 +480,10 @@ void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n
     }
     unsigned const blocks = (unsigned) std::min<uint64_t>((n + 255) / 256, (uint64_t) ctx->sm_count * 16U);
     size_t const smem = axis.bins * sizeof(uint32_t) <= 48 * 1024 ? axis.bins * sizeof(uint32_t) : 0;
-    k_rdf_distances<<<blocks, 256, smem, ctx->stream>>>(distances, n, axis, hist);
-    ctx->launches += 1;
+    {
+        KernelScope ks(ctx, "rdf_distances");
+        k_rdf_distances<<<blocks, 256, smem, ctx->stream>>>(distances, n, axis, hist);
+    }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 

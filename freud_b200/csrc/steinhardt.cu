@@ -365,6 +365,7 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
     {
         return;
     }
+    KernelScope ks(ctx, "steinhardt");
     bool single = ls.size() == 1;
     if (single)
     {
@@ -384,7 +385,6 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
         k_steinhardt_generic<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, lmax, (int) ls.size(),
                                                                                              n_acc, tot_m);
     }
-    ctx->launches += 1;
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 

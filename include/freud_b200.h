@@ -66,6 +66,14 @@ uint64_t fgpu_ctx_launch_count(fgpu_ctx* ctx);
 int fgpu_ctx_count_pair_evals(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset);
 
+/* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).  While enabled,
+ * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
+ * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
+ * reset.  Names: cell_assign, cell_scatter, scan, search_count, search_fill, search_rdf, emit, segments,
+ * knn, knn_emit, rdf_distances, steinhardt. */
+int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
+int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
+
 /* ---- points + periodic cell list -------------------------------------------------------------------
  * Replaces the constructors LinkCell(box, points, n, cell_width) freud/locality/LinkCell.cc:222-260,
  * AABBQuery(box, points, n) freud/locality/AABBQuery.cc:17-26 and RawPoints (RawPoints.h:35-37):
