@@ -1,0 +1,92 @@
+"""Generates the golden vectors under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+The Python package of the reference cannot be imported in the build container (nanobind and oneTBB are absent),
+so the vectors come from ``oracle/_ref/libfreud_ref.so``: the unmodified reference C++ sources compiled where they
+lie under /root/reference (oracle/Makefile).  Run from the repo root where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Inputs are regenerated from seeds by the tests (freud_b200.data / tests.util), only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from freud_b200 import data  # noqa: E402
+from freud_b200.box import Box  # noqa: E402
+from oracle import ref  # noqa: E402
+from tests.util import random_points  # noqa: E402
+
+CASES = {
+    # name: (box, n_points, n_query (0 = self query), r_max, r_min, exclude_ii, seed)
+    "tri": (Box(14, 15, 16, 0.3, 0.2, 0.1), 400, 0, 3.0, 0.0, True, 101),
+    "tri_q": (Box(14, 15, 16, -0.4, 0.25, 0.15), 350, 120, 3.2, 0.8, False, 102),
+    "cubic": (Box.cube(12), 400, 0, 2.5, 0.0, True, 103),
+    "sq2d": (Box.square(30), 400, 0, 3.0, 0.0, True, 104),
+    "tilt2d": (Box(30, 26, 0, 0.35, 0, 0, is2D=True), 300, 90, 3.0, 0.5, False, 105),
+}
+
+
+def nl_dict(nl, prefix):
+    return {f"{prefix}_neighbors": nl.neighbors, f"{prefix}_distances": nl.distances, f"{prefix}_vectors": nl.vectors,
+            f"{prefix}_segments": nl.segments, f"{prefix}_counts": nl.counts}
+
+
+def main():
+    ref.set_num_threads(4)
+    for name, (box, n, nq, r_max, r_min, excl, seed) in CASES.items():
+        pts = random_points(box, n, seed)
+        q = pts if nq == 0 else random_points(box, nq, seed + 1000)
+        out = {}
+        lc = ref.Query("linkcell", box, pts, is2d=box.is2D, cell_width=min(r_max, 0.45 * min(box.Lx, box.Ly)))
+        aq = ref.Query("aabb", box, pts, is2d=box.is2D)
+        out.update(nl_dict(lc.nlist(q, r_max=r_max, r_min=r_min, exclude_ii=excl), "wrap"))
+        out.update(nl_dict(aq.nlist(q, r_max=r_max, r_min=r_min, exclude_ii=excl), "image"))
+        out.update(nl_dict(aq.nlist(q, r_max=r_max, r_min=r_min, exclude_ii=excl, sort_by_distance=True), "image_bydist"))
+        out.update(nl_dict(aq.nlist(q, num_neighbors=6, exclude_ii=excl), "knn6"))
+        for flavour, query in (("wrap", lc), ("image", aq)):
+            R = ref.RDF(40, r_max, r_min)
+            R.accumulate(query, q, mode="ball", r_max=r_max, exclude_ii=excl)
+            res = R.results()
+            out.update({f"rdf_{flavour}_{k}": v for k, v in res.items()})
+        np.savez_compressed(os.path.join(HERE, f"nl_{name}.npz"), **out)
+        print(name, {k: v.shape for k, v in out.items() if k.endswith("neighbors")})
+
+    # BASELINE.json configs[0]: RDF bins=100 r_max=5 on make_random_system(box_size=50, num_points=10000)
+    box, pts = data.make_random_system(50, 10000, seed=0)
+    R = ref.RDF(100, 5.0)
+    R.accumulate(ref.Query("raw", box, pts), pts, mode="ball", r_max=5.0, exclude_ii=True)
+    res = R.results()
+    R2 = ref.RDF(100, 5.0)  # accumulation over two frames, reset=False
+    for s in (0, 1):
+        b2, p2 = data.make_random_system(50, 10000, seed=s)
+        R2.accumulate(ref.Query("raw", b2, p2), p2, mode="ball", r_max=5.0, exclude_ii=True)
+    res2 = R2.results()
+    np.savez_compressed(os.path.join(HERE, "rdf_config0.npz"), **res, **{f"two_frames_{k}": v for k, v in res2.items()})
+    print("rdf_config0", int(res["bin_counts"].sum()), res["bin_counts"][-3:])
+
+    # Steinhardt: noisy FCC, k = 12 (RawPoints -> AABB kNN, per-point iteration in distance order), and ball
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    out = {}
+    for ls in ([6], [4, 6], [2, 8], [12]):
+        S = ref.Steinhardt(ls)
+        r = S.compute(ref.Query("raw", box, pts), num_neighbors=12, exclude_ii=True)
+        tag = "_".join(str(l) for l in ls)
+        out[f"knn12_ql_{tag}"] = r["ql"]
+        out[f"knn12_order_{tag}"] = r["order"]
+        for l, qlm in zip(ls, r["qlm"]):
+            out[f"knn12_qlm_{tag}_l{l}"] = qlm
+    S = ref.Steinhardt([6])
+    r = S.compute(ref.Query("raw", box, pts), mode="ball", r_max=1.05, exclude_ii=True)
+    out["ball_ql_6"] = r["ql"]
+    np.savez_compressed(os.path.join(HERE, "steinhardt_fcc.npz"), **out)
+    print("steinhardt", out["knn12_ql_6"][:3, 0])
+
+
+if __name__ == "__main__":
+    main()

@@ -5,11 +5,14 @@ arithmetic flavour; 1e-5 for q_l.  Oracles: ``oracle/_ref`` (the unmodified refe
 travels as a prebuilt .so) where it exists, else ``oracle/port`` (plain-C restatement, itself pinned to
 ``_ref`` by tests/test_oracle_port.py).
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import port, ref
-from tests.util import BOXES, assert_nlist_equal, random_points
+from tests.golden.make_golden import CASES as GOLDEN_CASES
+from tests.util import BOXES, assert_nlist_equal, bits, random_points
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +32,91 @@ def oracle_ball(flavour, box, pts, q, r_max, r_min=0.0, exclude_ii=False, sort_b
         query = ref.Query(eng, box, pts, is2d=box.is2D, cell_width=min(r_max, 0.4 * float(min(box.Lx, box.Ly))))
         return query.nlist(q, r_max=r_max, r_min=r_min, exclude_ii=exclude_ii, sort_by_distance=sort_by_distance)
     return port.ball_nlist(flavour, box, box.is2D, pts, q, r_max, r_min, exclude_ii, sort_by_distance)
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _assert_gold(got, gold, prefix):
+    for key in ("neighbors", "segments", "counts"):
+        assert np.array_equal(got[key], gold[f"{prefix}_{key}"]), f"{prefix} {key}"
+    for key in ("distances", "vectors"):
+        assert np.array_equal(bits(got[key]), bits(gold[f"{prefix}_{key}"])), f"{prefix} {key} differ bitwise"
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_golden_vectors_from_the_reference(ctx, name):
+    """The committed outputs of the reference itself (tests/golden/make_golden.py), both flavours + kNN + RDF."""
+    capi = _capi()
+    box, n, nq, r_max, r_min, excl, seed = GOLDEN_CASES[name]
+    gold = np.load(os.path.join(GOLD, f"nl_{name}.npz"))
+    pts = random_points(box, n, seed)
+    q = None if nq == 0 else random_points(box, nq, seed + 1000)
+    dp = capi.DevicePoints(ctx, box, pts)
+    _assert_gold(dp.ball_query(q, WRAP, r_max, r_min, excl).to_host(), gold, "wrap")
+    _assert_gold(dp.ball_query(q, IMAGE, r_max, r_min, excl).to_host(), gold, "image")
+    _assert_gold(dp.ball_query(q, IMAGE, r_max, r_min, excl, True).to_host(), gold, "image_bydist")
+    _assert_gold(dp.knn_query(q, 6, exclude_ii=excl).to_host(), gold, "knn6")
+    for flavour, tag in ((WRAP, "wrap"), (IMAGE, "image")):
+        rdf = capi.DeviceRDF(ctx, 40, r_max, r_min)
+        rdf.accumulate(dp, q, flavour, r_max, 0.0, excl)
+        assert np.array_equal(rdf.read(), gold[f"rdf_{tag}_bin_counts"])
+
+
+def test_golden_rdf_config0(ctx):
+    """BASELINE.json configs[0] through the C ABI: raw bin counts bit-exact, one frame and two (reset=False)."""
+    from freud_b200 import data
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "rdf_config0.npz"))
+    rdf = capi.DeviceRDF(ctx, 100, 5.0)
+    for seed, key in ((0, "bin_counts"), (1, "two_frames_bin_counts")):
+        box, pts = data.make_random_system(50, 10000, seed=seed)
+        rdf.accumulate(capi.DevicePoints(ctx, box, pts), None, IMAGE, 5.0, 0.0, True)
+        assert np.array_equal(rdf.read(), gold[key])
+
+
+def test_golden_steinhardt(ctx):
+    from freud_b200 import data
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "steinhardt_fcc.npz"))
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    dp = capi.DevicePoints(ctx, box, pts)
+    nl = dp.knn_query(None, 12, exclude_ii=True)
+    for ls in ([6], [4, 6], [2, 8], [12]):
+        tag = "_".join(str(l) for l in ls)
+        out = dp.steinhardt(nl, ls)
+        assert np.allclose(out["ql"], gold[f"knn12_ql_{tag}"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(out["order"], gold[f"knn12_order_{tag}"], rtol=1e-4, atol=1e-6)
+        for l, qlm in zip(ls, out["qlm"]):
+            assert np.allclose(qlm, gold[f"knn12_qlm_{tag}_l{l}"], atol=1e-5)
+    nlb = dp.ball_query(None, IMAGE, 1.05, 0.0, True)
+    assert np.allclose(dp.steinhardt(nlb, [6])["ql"], gold["ball_ql_6"], rtol=1e-5, atol=1e-6)
+
+
+def test_hand_built_queries_of_the_reference_tests(ctx):
+    """tests/test_locality_neighbor_query.py:94-155, :218-300 through the C ABI."""
+    capi = _capi()
+    from freud_b200.box import Box
+
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [1, 0, 0], [3, 0, 0], [2, 0, 0]], np.float32)
+    dp = capi.DevicePoints(ctx, box, pts)
+
+    def sets(nl):
+        h = nl.to_host()
+        return [set(int(j) for j in h["neighbors"][h["neighbors"][:, 0] == i, 1]) for i in range(4)]
+
+    for flavour in (WRAP, IMAGE):
+        assert list(dp.ball_query(None, flavour, 2.01).to_host()["counts"]) == [3, 4, 3, 4]
+        assert dp.ball_query(None, flavour, 2.01, 0.0, True).num_bonds == 10
+        assert sets(dp.ball_query(None, flavour, 2.9, 1.1, True)) == [{3}, {2}, {1}, {0}]
+    assert sets(dp.knn_query(None, 3)) == [{0, 1, 3}, {0, 1, 3}, {1, 2, 3}, {1, 2, 3}]
+    assert sets(dp.knn_query(None, 3, exclude_ii=True)) == [{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}]
+    assert sets(dp.knn_query(None, 5, exclude_ii=True)) == [{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}]
+    assert sets(dp.knn_query(None, 3, r_max=1.9, exclude_ii=True)) == [{1}, {0, 3}, {3}, {1, 2}]
+    assert sets(dp.knn_query(None, 3, r_min=1.1, exclude_ii=True)) == [{2, 3}, {2}, {0, 1}, {0}]
 
 
 @pytest.mark.parametrize("name", list(BOXES))

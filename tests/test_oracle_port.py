@@ -1,0 +1,214 @@
+"""Pins the oracle (CPU, no GPU needed).
+
+1. ``oracle/port.c`` (plain-C restatement) against the golden vectors produced by the reference itself
+   (tests/golden/*.npz, generator committed beside them) -- bit for bit.
+2. the same port against ``oracle/_ref`` (the unmodified reference compiled here) on more boxes, when that
+   library exists (it does wherever /root/reference was available at build time).
+3. the known answers the reference's own tests hold for this path (SURVEY.md section 8c list).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from freud_b200 import data
+from freud_b200.box import Box
+from oracle import port, ref
+from tests.golden.make_golden import CASES
+from tests.util import BOXES, bits, random_points
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def same_nl(got, gold, prefix):
+    assert np.array_equal(got.neighbors, gold[f"{prefix}_neighbors"])
+    assert np.array_equal(bits(got.distances), bits(gold[f"{prefix}_distances"]))
+    assert np.array_equal(bits(got.vectors), bits(gold[f"{prefix}_vectors"]))
+    assert np.array_equal(got.segments, gold[f"{prefix}_segments"])
+    assert np.array_equal(got.counts, gold[f"{prefix}_counts"])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_port_matches_golden_neighbor_lists(name):
+    box, n, nq, r_max, r_min, excl, seed = CASES[name]
+    gold = np.load(os.path.join(GOLD, f"nl_{name}.npz"))
+    pts = random_points(box, n, seed)
+    q = pts if nq == 0 else random_points(box, nq, seed + 1000)
+    same_nl(port.ball_nlist(port.WRAP, box, box.is2D, pts, q, r_max, r_min, excl), gold, "wrap")
+    same_nl(port.ball_nlist(port.IMAGE, box, box.is2D, pts, q, r_max, r_min, excl), gold, "image")
+    same_nl(port.ball_nlist(port.IMAGE, box, box.is2D, pts, q, r_max, r_min, excl, True), gold, "image_bydist")
+    same_nl(port.knn_nlist(box, box.is2D, pts, q, 6, exclude_ii=excl), gold, "knn6")
+    for flavour, tag in ((port.WRAP, "wrap"), (port.IMAGE, "image")):
+        counts = port.rdf_accumulate(flavour, box, box.is2D, pts, q, 40, r_max, r_min, excl)
+        assert np.array_equal(counts, gold[f"rdf_{tag}_bin_counts"])
+        red = port.rdf_reduce(counts, r_max, r_min, box, box.is2D, n, len(q))
+        for key in ("rdf", "n_r", "bin_edges", "bin_centers"):
+            assert np.array_equal(bits(red[key]), bits(gold[f"rdf_{tag}_{key}"])), key
+
+
+def test_port_matches_golden_rdf_config0():
+    """BASELINE.json configs[0]: RDF bins=100 r_max=5 on make_random_system(50, 10000), one and two frames."""
+    gold = np.load(os.path.join(GOLD, "rdf_config0.npz"))
+    box, pts = data.make_random_system(50, 10000, seed=0)
+    counts = port.rdf_accumulate(port.IMAGE, box, False, pts, pts, 100, 5.0, 0.0, True)
+    assert np.array_equal(counts, gold["bin_counts"])
+    red = port.rdf_reduce(counts, 5.0, 0.0, box, False, 10000, 10000)
+    assert np.array_equal(bits(red["rdf"]), bits(gold["rdf"])) and np.array_equal(bits(red["n_r"]), bits(gold["n_r"]))
+    b1, p1 = data.make_random_system(50, 10000, seed=1)
+    port.rdf_accumulate(port.IMAGE, b1, False, p1, p1, 100, 5.0, 0.0, True, counts=counts)
+    assert np.array_equal(counts, gold["two_frames_bin_counts"])
+    red = port.rdf_reduce(counts, 5.0, 0.0, box, False, 10000, 10000, frames=2)
+    assert np.array_equal(bits(red["rdf"]), bits(gold["two_frames_rdf"]))
+    # statistical sanity the reference tests use (tests/test_density_rdf.py:94-127): g(r) -> 1
+    assert abs(float(np.mean(red["rdf"][50:])) - 1.0) < 0.05
+
+
+def test_port_matches_golden_steinhardt():
+    gold = np.load(os.path.join(GOLD, "steinhardt_fcc.npz"))
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    nl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True, sort_by_distance=True)
+    for ls in ([6], [4, 6], [2, 8], [12]):
+        tag = "_".join(str(l) for l in ls)
+        out = port.steinhardt(box, False, pts, nl, ls)
+        assert np.allclose(out["ql"], gold[f"knn12_ql_{tag}"], rtol=1e-6, atol=1e-7)
+        assert np.allclose(out["order"], gold[f"knn12_order_{tag}"], rtol=1e-5)
+        for l, qlm in zip(ls, out["qlm"]):
+            assert np.allclose(qlm, gold[f"knn12_qlm_{tag}_l{l}"], atol=1e-6)
+    nlb = port.ball_nlist(port.IMAGE, box, False, pts, pts, 1.05, 0.0, True)
+    assert np.allclose(port.steinhardt(box, False, pts, nlb, [6])["ql"], gold["ball_ql_6"], rtol=1e-6, atol=1e-7)
+
+
+# ---- known answers held by the reference's own tests ---------------------------------------------------
+def test_known_answer_perfect_fcc_q6():
+    """PERFECT_FCC_Q6 = 0.57452416, tests/test_order_steinhardt.py:17, :101-166 (k = 12 and ball)."""
+    box, pts = data.make_fcc_system(4)
+    nl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True)
+    out = port.steinhardt(box, False, pts, nl, [6])
+    assert np.allclose(out["ql"], 0.57452416, atol=1e-5) and abs(out["order"][0] - 0.57452416) < 1e-5
+    box, pts = data.make_fcc_system(4, scale=2.0)
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, pts, 1.5, 0.0, True)
+    assert np.allclose(port.steinhardt(box, False, pts, nl, [6])["ql"], 0.57452416, atol=1e-5)
+
+
+def test_known_answer_axis_aligned_ql():
+    """q_l of one bond along z: Y_lm vanishes for m != 0, so q_l = 1 for every l; tests/test_order_steinhardt.py:79-99."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [0, 0, 1]], np.float32)
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, pts, 1.5, 0.0, True)
+    for l in range(0, 20):
+        ql = port.steinhardt(box, False, pts, nl, [l])["ql"][:, 0]
+        assert np.allclose(ql, 1.0, atol=1e-5), l
+
+
+def test_known_answer_box_wrap_and_round_trip():
+    """tests/test_box_box.py:118-121 (wrap in a tilted box), :316-353 (fractional/absolute round trips)."""
+    for impl in (port.box_apply, lambda b, d, op, v: getattr(Box.from_box(b), {"wrap": "wrap", "fractional":
+                 "make_fractional", "absolute": "make_absolute"}[op])(v)):
+        assert np.array_equal(impl(Box(2, 2, 2, 1, 0, 0), False, "wrap", [[10, -5, -5]]), [[-2, -1, -1]])
+    box = Box(2, 2, 2, 1, 0, 0)
+    assert np.allclose(port.box_apply(box, False, "absolute", [[0.5, 0.5, 0.5]]), [[0, 0, 0]])
+    f = np.array([[0.1, 0.9, 0.4], [0.6, 0.2, 0.7]], np.float32)
+    back = port.box_apply(box, False, "fractional", port.box_apply(box, False, "absolute", f))
+    assert np.allclose(back, f, atol=1e-6)
+    # the numpy Box (host utility) and the port agree bit for bit on random inputs in a triclinic box
+    tb = Box(7, 8, 9, 0.3, -0.2, 0.1)
+    v = (np.random.RandomState(0).random_sample((500, 3)) * 40 - 20).astype(np.float32)
+    for op, fn in (("wrap", tb.wrap), ("fractional", tb.make_fractional), ("absolute", tb.make_absolute)):
+        assert np.array_equal(bits(port.box_apply(tb, False, op, v)), bits(fn(v))), op
+
+
+def test_known_answer_hand_built_ball_queries():
+    """tests/test_locality_neighbor_query.py:94-155 (bond counts) and :218-251 (r_min)."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [1, 0, 0], [3, 0, 0], [2, 0, 0]], np.float32)
+    for flavour in (port.WRAP, port.IMAGE):
+        nl = port.ball_nlist(flavour, box, False, pts, pts, 2.01)
+        assert list(nl.counts) == [3, 4, 3, 4]
+        assert len(port.ball_nlist(flavour, box, False, pts, pts, 2.01, 0.0, True)) == 10
+        moved = pts.copy()
+        moved[0] = 5
+        assert list(port.ball_nlist(flavour, box, False, moved, moved, 2.01).counts) == [1, 3, 3, 3]
+        nl = port.ball_nlist(flavour, box, False, pts, pts, 2.9, 1.1, True)
+        assert [set(nl.neighbors[nl.neighbors[:, 0] == i, 1]) for i in range(4)] == [{3}, {2}, {1}, {0}]
+
+
+def test_known_answer_hand_built_nearest_queries():
+    """tests/test_locality_neighbor_query.py:253-300."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [1, 0, 0], [3, 0, 0], [2, 0, 0]], np.float32)
+
+    def sets(nl):
+        return [set(int(j) for j in nl.neighbors[nl.neighbors[:, 0] == i, 1]) for i in range(4)]
+
+    assert sets(port.knn_nlist(box, False, pts, pts, 3)) == [{0, 1, 3}, {0, 1, 3}, {1, 2, 3}, {1, 2, 3}]
+    assert sets(port.knn_nlist(box, False, pts, pts, 3, exclude_ii=True)) == [{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}]
+    assert sets(port.knn_nlist(box, False, pts, pts, 5, exclude_ii=True)) == [{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}]
+    assert sets(port.knn_nlist(box, False, pts, pts, 3, r_max=1.9, exclude_ii=True)) == [{1}, {0, 3}, {3}, {1, 2}]
+    assert sets(port.knn_nlist(box, False, pts, pts, 3, r_min=1.1, exclude_ii=True)) == [{2, 3}, {2}, {0, 1}, {0}]
+
+
+def test_known_answer_rdf_bin_edges_and_2d_ring():
+    """tests/test_density_rdf.py:242-251 (bin edges) and :188-224 (exact n(r) for a 2-D ring system)."""
+    red = port.rdf_reduce(np.zeros(10, np.uint32), 5.0, 0.0, Box.cube(20), False, 10, 10)
+    assert np.allclose(red["bin_edges"], np.linspace(0, 5, 11), atol=1e-6)
+    assert np.allclose(red["bin_centers"], np.linspace(0.25, 4.75, 10), atol=1e-6)
+    # one point in the middle, `num` points on a ring of radius r: n(r) jumps from 0 to num at the ring
+    num, radius = 20, 2.0
+    box = Box.square(10)
+    ang = np.linspace(0, 2 * np.pi, num, endpoint=False)
+    ring = np.stack([radius * np.cos(ang), radius * np.sin(ang), 0 * ang], 1).astype(np.float32)
+    centre = np.zeros((1, 3), np.float32)
+    for flavour in (port.WRAP, port.IMAGE):
+        counts = port.rdf_accumulate(flavour, box, True, ring, centre, 50, 3.0, 0.1, False)
+        red = port.rdf_reduce(counts, 3.0, 0.1, box, True, num, 1)
+        edges = red["bin_edges"]
+        want = np.where(edges[1:] > radius, num, 0).astype(np.float32)
+        assert np.allclose(red["n_r"], want, atol=1e-5)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(BOXES))
+def test_port_matches_compiled_reference(name):
+    box, n, r = BOXES[name]
+    n = min(n, 1500)
+    pts = random_points(box, n, seed=41)
+    q = random_points(box, 300, seed=42)
+    cw = min(r, 0.4 * float(min(box.Lx, box.Ly)))
+    lc = ref.Query("linkcell", box, pts, is2d=box.is2D, cell_width=cw)
+    aq = ref.Query("aabb", box, pts, is2d=box.is2D)
+    for excl in (True, False):
+        for flavour, query in ((port.WRAP, lc), (port.IMAGE, aq)):
+            a = query.nlist(pts, r_max=r, exclude_ii=excl)
+            b = port.ball_nlist(flavour, box, box.is2D, pts, pts, r, 0.0, excl)
+            assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.distances), bits(b.distances))
+            assert np.array_equal(bits(a.vectors), bits(b.vectors)) and np.array_equal(a.segments, b.segments)
+    a = aq.nlist(q, r_max=r, r_min=1.0, sort_by_distance=True)
+    b = port.ball_nlist(port.IMAGE, box, box.is2D, pts, q, r, 1.0, False, True)
+    assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.distances), bits(b.distances))
+    a = aq.nlist(q, num_neighbors=12, exclude_ii=False)
+    b = port.knn_nlist(box, box.is2D, pts, q, 12)
+    assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.distances), bits(b.distances))
+    R = ref.RDF(50, r, 0.5, finite_size=True)
+    R.accumulate(ref.Query("raw", box, pts, is2d=box.is2D), pts, mode="ball", r_max=r, exclude_ii=True)
+    want = R.results()
+    counts = port.rdf_accumulate(port.IMAGE, box, box.is2D, pts, pts, 50, r, 0.5, True)
+    got = port.rdf_reduce(counts, r, 0.5, box, box.is2D, n, n, finite_size=True)
+    for key in want:
+        assert np.array_equal(bits(want[key]), bits(got[key])), key
+    # Steinhardt from a neighbour list: identical libm on the same host -> identical bits
+    nl = aq.nlist(pts, num_neighbors=8, exclude_ii=True)
+    want = ref.Steinhardt([4, 6]).compute(aq, nlist=nl)
+    got = port.steinhardt(box, box.is2D, pts, port.knn_nlist(box, box.is2D, pts, pts, 8, exclude_ii=True), [4, 6])
+    assert np.array_equal(bits(want["ql"]), bits(got["ql"]))
+
+
+@needs_ref
+def test_reference_reproduces_its_own_constants():
+    """The compiled reference itself: Q6 = 0.57452416, W6 = -0.00262604 (tests/test_order_steinhardt.py:17-18)."""
+    box, pts = data.make_fcc_system(4)
+    q = ref.Query("raw", box, pts)
+    assert np.allclose(ref.Steinhardt(6).compute(q, num_neighbors=12, exclude_ii=True)["ql"], 0.57452416, atol=1e-5)
+    w6 = ref.Steinhardt(6, wl=True).compute(q, num_neighbors=12, exclude_ii=True)["particle_order"]
+    assert np.allclose(w6, -0.00262604, atol=1e-5)
+    assert np.array_equal(ref.box_apply((2, 2, 2, 1, 0, 0), False, "wrap", [[10, -5, -5]]), [[-2, -1, -1]])
