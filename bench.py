@@ -409,7 +409,7 @@ def main():
     ctx.profile(False)
     # dominant kernel over the timed region
     per_kernel = {}
-    for name in ("cell_assign", "cell_scatter", "scan", "search_count", "search_fill", "search_rdf", "emit", "segments",
+    for name in ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general", "search_rdf", "emit_general", "emit", "segments",
                  "knn_emit", "knn", "rdf_distances", "steinhardt"):
         ms, cnt = ctx.kernel_time(name)
         if name == "knn":

@@ -33,6 +33,7 @@ SIGNATURES = {
     "fgpu_ctx_launch_count": (C.c_uint64, [_vp]),
     "fgpu_ctx_count_pair_evals": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_pair_evals": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "fgpu_ctx_force_general_search": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_profile": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_kernel_time": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
@@ -157,6 +158,9 @@ class Context:
         out = C.c_uint64()
         check(lib().fgpu_ctx_pair_evals(self._h, C.byref(out), int(reset)))
         return int(out.value)
+
+    def force_general_search(self, enable=True):
+        check(lib().fgpu_ctx_force_general_search(self._h, int(enable)))
 
     def profile(self, enable=True):
         check(lib().fgpu_ctx_profile(self._h, int(enable)))

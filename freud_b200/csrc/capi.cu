@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -157,8 +158,10 @@ void bind_quiet(fgpu_ctx* ctx)
 
 struct QueryView
 {
-    const float4* sorted; // cell-ordered, w = original index
-    const float* xyz;     // original order
+    const float4* sorted;        // cell-ordered, w = original index
+    const float* xyz;            // original order
+    const uint32_t* cell_start;  // n_cells + 1 offsets into sorted
+    const int* outside_flag;     // device flag: some query lies outside the box
 };
 
 // Stage the query points (if any) and produce their cell-ordered view on the grid of pts.
@@ -170,6 +173,8 @@ QueryView prepare_queries(fgpu_points* pts, const float* q_host, const float* q_
     {
         v.sorted = pts->grid.sorted.ptr;
         v.xyz = pts->xyz.ptr;
+        v.cell_start = pts->grid.cell_start.ptr;
+        v.outside_flag = pts->grid.any_shift_flag.ptr;
         return v;
     }
     if (q_host != nullptr)
@@ -181,6 +186,8 @@ QueryView prepare_queries(fgpu_points* pts, const float* q_host, const float* q_
     sort_queries(pts, q_dev, n_query);
     v.sorted = ctx->q_sorted.ptr;
     v.xyz = q_dev;
+    v.cell_start = ctx->q_cell_start.ptr;
+    v.outside_flag = ctx->q_outside_flag.ptr;
     return v;
 }
 
@@ -214,6 +221,53 @@ SearchArgs base_search_args(fgpu_points* pts, const QueryView& qv, uint32_t n_qu
     a.r_min = r_min;
     a.exclude_ii = exclude_ii != 0;
     a.evals = pts->ctx->count_evals ? pts->ctx->d_evals : nullptr;
+    return a;
+}
+
+// RN(1 / L) for the Markstein division of search2.cu; long double keeps the double rounding harmless
+float rounded_reciprocal(float L)
+{
+    return L != 0.0f ? (float) (1.0L / (long double) L) : 0.0f;
+}
+
+Search2Args base_search2_args(fgpu_points* pts, const QueryView& qv, uint32_t q_index_offset, float r_max,
+                              float r_min, int exclude_ii)
+{
+    fgpu_ctx* ctx = pts->ctx;
+    const fgpu_grid& g = pts->grid;
+    Search2Args a;
+    std::memset(&a, 0, sizeof(a));
+    a.box = pts->box;
+    a.dx = g.dim[0];
+    a.dy = g.dim[1];
+    a.dz = g.dim[2];
+    a.n_cells = g.n_cells;
+    a.n_tickets = search2_tickets(g.n_cells);
+    a.cell_start = g.cell_start.ptr;
+    a.sorted = g.sorted.ptr;
+    a.q_cell_start = qv.cell_start;
+    a.q_sorted = qv.sorted;
+    a.flag_points_outside = g.any_shift_flag.ptr;
+    a.flag_queries_outside = qv.outside_flag;
+    a.q_index_offset = q_index_offset;
+    a.r_max = r_max;
+    a.r_min = r_min;
+    a.exclude_ii = exclude_ii != 0;
+    a.rcp_lx = rounded_reciprocal(pts->box.Lx);
+    a.rcp_ly = rounded_reciprocal(pts->box.Ly);
+    a.rcp_lz = rounded_reciprocal(pts->box.Lz);
+    // stage-1 acceptance radius: r_max + 4E, E bounding the rounding error of a displacement component in either
+    // arithmetic (coordinates of magnitude <= (Lx + Ly + Lz)(1 + |tilts|), a dozen roundings of 2^-24 each)
+    double const ext = ((double) pts->box.Lx + pts->box.Ly + pts->box.Lz)
+        * (1.0 + std::fabs((double) pts->box.xy) + std::fabs((double) pts->box.xz) + std::fabs((double) pts->box.yz));
+    double const E = 16.0 * 5.9604644775390625e-08 * ext;
+    double const r_hi = (double) r_max + 4.0 * E;
+    a.r_hi_sq = std::nextafter((float) (r_hi * r_hi * (1.0 + 1.0e-6)), INFINITY);
+    a.out_cap = search2_out_cap((pts->box.is2d ? 9.0 : 27.0) * (double) pts->n / (double) std::max(g.n_cells, 1U));
+    a.fail = reinterpret_cast<int*>(ctx->d_scalars + 4);
+    a.cursor = ctx->d_scalars + 5;
+    a.work_counter = reinterpret_cast<unsigned int*>(ctx->d_scalars + 6);
+    a.evals = ctx->count_evals ? ctx->d_evals : nullptr;
     return a;
 }
 
@@ -274,8 +328,89 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     build_grid(pts, r_max);
     QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
 
+    // ---- production path: warp-cooperative single-pass search into a bag, then ranked emit ----------------
+    bool fast_counted_evals = false;
+    Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_max, r_min, exclude_ii);
+    if (!ctx->force_general && search2_supported(s2, S2_NL))
+    {
+        // bag capacity: the previous query's bond count if there was one, else the ideal-gas expectation
+        double const vol = box_volume(pts->box);
+        double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max
+                                           : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
+        uint64_t cap = ctx->bag_hint != 0
+            ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
+            : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
+        ctx->tmp_start.reserve((size_t) n_query + 1);
+        bool done = false, general = false;
+        uint64_t n_bonds = 0;
+        launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+        bool const evals_counted = s2.evals != nullptr;
+        for (int attempt = 0; attempt < 3 && !done && !general; ++attempt)
+        {
+            cap = std::min<uint64_t>(cap, 0xffffffffULL);
+            ctx->tq.reserve(cap);
+            ctx->tj.reserve(cap);
+            ctx->tv.reserve(cap * 3);
+            s2.tq = ctx->tq.ptr;
+            s2.tj = ctx->tj.ptr;
+            s2.tv = ctx->tv.ptr;
+            s2.temp_cap = (uint32_t) cap;
+            s2.counts = nl->counts.ptr;
+            s2.tmp_start = ctx->tmp_start.ptr;
+            FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            launch_search2(ctx, flavour, S2_NL, s2);
+            d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
+            sync(ctx);
+            int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+            if (fail != 0)
+            {
+                general = true; // 1: points outside the box, 2: a row may be longer than the warp buffer
+                fast_counted_evals = evals_counted && fail != 1; // the count kernel skips case 1 itself
+            }
+            else if (ctx->h_scalars[5] <= cap)
+            {
+                n_bonds = ctx->h_scalars[5];
+                done = true;
+            }
+            else
+            {
+                cap = ctx->h_scalars[5]; // exact size, the search is deterministic
+            }
+        }
+        if (done)
+        {
+            ctx->bag_hint = n_bonds;
+            alloc_bonds(nl.get(), n_bonds);
+            FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->row_start.ptr, nl->counts.ptr, (size_t) n_query * sizeof(uint32_t),
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
+            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+            Emit2Args e;
+            e.tq = ctx->tq.ptr;
+            e.tj = ctx->tj.ptr;
+            e.tv = ctx->tv.ptr;
+            e.tmp_start = ctx->tmp_start.ptr;
+            e.counts = nl->counts.ptr;
+            e.row_start = nl->row_start.ptr;
+            e.n_bonds = n_bonds;
+            e.neighbors = nl->neighbors.ptr;
+            e.distances = nl->distances.ptr;
+            e.weights = nl->weights.ptr;
+            e.vectors = nl->vectors.ptr;
+            launch_emit2(ctx, sort_by_distance, e);
+            launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
+            *out = nl.release();
+            return;
+        }
+    }
+
+    // ---- general path (small grids, points outside the box, very long rows): two-pass thread-per-query ------
     ctx->row_counts.reserve((size_t) n_query + 1);
     SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, r_max, r_min, exclude_ii);
+    if (fast_counted_evals)
+    {
+        a.evals = nullptr;
+    }
     a.sort_by_distance = sort_by_distance != 0;
     a.row_counts = ctx->row_counts.ptr;
     a.total = ctx->d_scalars;
@@ -327,9 +462,24 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     }
     build_grid(pts, q_r_max);
     QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
+    Search2Args s2 = base_search2_args(pts, qv, q_index_offset, q_r_max, q_r_min, exclude_ii);
+    s2.axis = rdf->axis;
+    bool const fast = !ctx->force_general && search2_supported(s2, S2_RDF);
     SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, q_r_max, q_r_min, exclude_ii);
     a.axis = rdf->axis;
     a.hist = rdf->hist.ptr;
+    if (fast)
+    {
+        // The warp-cooperative kernel adds nothing and raises the fail flag when a point lies outside the box;
+        // the general kernel is enqueued behind it and returns at once unless that flag is set, so the choice
+        // is made on the device and the frame needs no host round trip.
+        s2.hist = rdf->hist.ptr;
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        launch_search2(ctx, flavour, S2_RDF, s2);
+        launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+        a.only_if = reinterpret_cast<const int*>(ctx->d_scalars + 4);
+        // a.evals stays: the general kernel only runs (and counts) when the fast one and its count bailed out
+    }
     launch_search(ctx, flavour, SEARCH_RDF, a);
     if (q_host != nullptr)
     {
@@ -492,6 +642,8 @@ int fgpu_ctx_create(int device, fgpu_ctx** out)
         FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_evals, 0, sizeof(unsigned long long), ctx->stream));
         FGPU_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 8 * sizeof(unsigned long long)));
         FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const char* env = std::getenv("FGPU_SEARCH");
+        ctx->force_general = env != nullptr && std::strcmp(env, "general") == 0;
         *out = ctx.release();
     });
 }
@@ -560,6 +712,14 @@ int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset)
         }
         sync(ctx);
         *out = ctx->h_scalars[1];
+    });
+}
+
+int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        ctx->force_general = enable != 0;
     });
 }
 

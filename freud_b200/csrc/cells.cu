@@ -295,7 +295,9 @@ void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
     ctx->q_sorted.reserve(n_query);
     FGPU_CUDA_CHECK(
         cudaMemsetAsync(ctx->q_cell_start.ptr, 0, ((size_t) g.n_cells + 1) * sizeof(uint32_t), ctx->stream));
-    int* d_flag = reinterpret_cast<int*>(ctx->d_scalars + 6); // unused result
+    ctx->q_outside_flag.reserve(1);
+    int* d_flag = ctx->q_outside_flag.ptr; // read on the device by the warp-cooperative search
+    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
     unsigned const blocks = (n_query + 255) / 256;
     {
         KernelScope ks(ctx, "cell_assign");

@@ -92,6 +92,12 @@ struct fgpu_ctx
     fgpu::DevBuf<uint32_t> row_counts;    // per query: number of bonds
     fgpu::DevBuf<uint32_t> row_start;     // exclusive scan of row_counts (n_query + 1)
     fgpu::DevBuf<uint4> bag;              // unsorted hits {key_hi, key_lo, slot, query}
+    fgpu::DevBuf<uint32_t> tq, tj;        // search2 bag: query index / point index per hit
+    fgpu::DevBuf<float> tv;               // search2 bag: bond vector per hit
+    fgpu::DevBuf<uint32_t> tmp_start;     // per query: offset of its row in the bag
+    fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
+    uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
+    int force_general = 0;                // FGPU_SEARCH=general: always run the search.cu kernels (testing)
     fgpu::DevBuf<float> knn_d;            // kNN scratch, [k][n_query]
     fgpu::DevBuf<uint32_t> knn_s;         // kNN scratch, [k][n_query] (slot | image code)
     unsigned long long* d_scalars = nullptr; // 8 x u64 device scalars (totals, flags)
@@ -232,6 +238,8 @@ struct SearchArgs
     uint32_t* hist;
     // instrumentation
     unsigned long long* evals; // may be nullptr
+    // run only if *only_if != 0 (nullptr: always): device-side fallback behind the warp-cooperative kernel
+    const int* only_if;
 };
 
 void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n); // in place, n elements
@@ -258,6 +266,71 @@ struct EmitArgs
 void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& args);
 void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* counts, uint32_t* segments,
                      uint32_t n_query);
+
+// ---- warp-cooperative search (search2.cu): the production path on regular grids -------------------------
+enum Search2Mode
+{
+    S2_NL = 0,
+    S2_RDF = 1
+};
+
+struct Search2Args
+{
+    BoxDev box;
+    int dx, dy, dz;
+    uint32_t n_cells;
+    uint32_t n_tickets;             // work items (runs of consecutive home cells)
+    const uint32_t* cell_start;     // candidates: cell list of the reference points
+    const float4* sorted;
+    const uint32_t* q_cell_start;   // queries, cell-sorted on the same grid
+    const float4* q_sorted;
+    const int* flag_points_outside;  // device flags: some point / query lies outside the box
+    const int* flag_queries_outside;
+    uint32_t q_index_offset;
+    float r_max, r_min;
+    int exclude_ii;
+    float rcp_lx, rcp_ly, rcp_lz;   // RN(1 / L), rounded on the host
+    float r_hi_sq;                  // stage-1 acceptance bound (WRAP)
+    // NeighborList mode
+    uint32_t* tq;                   // bag: query index, point index, vector of every hit (rows contiguous)
+    uint32_t* tj;
+    float* tv;
+    uint32_t temp_cap;
+    uint32_t out_cap;               // hit records a warp can buffer per batch (dynamic shared memory)
+    uint32_t* counts;               // per query (original order)
+    uint32_t* tmp_start;            // per query: offset of its row in the bag
+    unsigned long long* cursor;     // bag records reserved so far (== total bonds at the end)
+    int* fail;                      // != 0: the result cannot be represented by this path, run the general kernels
+    // RDF mode
+    AxisDev axis;
+    uint32_t* hist;
+    // scheduling / instrumentation
+    unsigned int* work_counter;
+    unsigned long long* evals;      // may be nullptr
+};
+uint32_t search2_tickets(uint32_t n_cells);
+bool search2_supported(const Search2Args& a, int mode);
+void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a);
+uint32_t search2_out_cap(double expected_candidates_per_query);
+// adds the pair evaluations of the query set to *a.evals (no-op when a.evals == nullptr)
+void launch_count_evals(fgpu_ctx* ctx, const Search2Args& a, uint32_t n_query, const uint32_t* cell_of_point,
+                        uint32_t n_points);
+
+struct Emit2Args
+{
+    const uint32_t* tq;
+    const uint32_t* tj;
+    const float* tv;
+    const uint32_t* tmp_start;
+    const uint32_t* counts;
+    const uint32_t* row_start;
+    uint64_t n_bonds;
+    uint32_t* neighbors;
+    float* distances;
+    float* weights;
+    float* vectors;
+};
+void launch_emit2(fgpu_ctx* ctx, int sort_by_distance, const Emit2Args& a);
 
 struct KnnArgs
 {

@@ -161,6 +161,10 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
 template<int FLAVOUR, int MODE> __global__ void __launch_bounds__(kSearchThreads) k_search(SearchArgs a)
 {
     extern __shared__ uint32_t sh_hist[];
+    if (a.only_if != nullptr && *a.only_if == 0)
+    {
+        return;
+    }
     bool const hist_in_smem = MODE == SEARCH_RDF && a.axis.bins * sizeof(uint32_t) <= 48 * 1024;
     if (MODE == SEARCH_RDF && hist_in_smem)
     {
@@ -415,7 +419,7 @@ template<int FLAVOUR> void launch_search_mode(fgpu_ctx* ctx, SearchMode mode, co
     }
     case SEARCH_RDF:
     {
-        KernelScope ks(ctx, "search_rdf");
+        KernelScope ks(ctx, "search_rdf_general");
         k_search<FLAVOUR, SEARCH_RDF><<<blocks, kSearchThreads, smem, ctx->stream>>>(a);
         break;
     }
@@ -445,7 +449,7 @@ void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& a)
     }
     unsigned const blocks = (unsigned) ((a.n_bonds + 255) / 256);
     {
-        KernelScope ks(ctx, "emit");
+        KernelScope ks(ctx, "emit_general");
         if (flavour == FGPU_FLAVOUR_WRAP)
         {
             k_emit<FGPU_FLAVOUR_WRAP><<<blocks, 256, 0, ctx->stream>>>(a);

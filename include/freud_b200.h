@@ -66,11 +66,17 @@ uint64_t fgpu_ctx_launch_count(fgpu_ctx* ctx);
 int fgpu_ctx_count_pair_evals(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset);
 
+/* Two kernel families implement the ball search: the warp-cooperative one (regular grids with >= 3 cells per
+ * periodic axis and all points inside the box -- the normal case) and a general thread-per-query one that
+ * also covers tiny boxes, points outside the box and rows longer than the warp buffer.  The choice is
+ * automatic; enable != 0 forces the general family (parity tests compare the two; also FGPU_SEARCH=general). */
+int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
+
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).  While enabled,
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
- * reset.  Names: cell_assign, cell_scatter, scan, search_count, search_fill, search_rdf, emit, segments,
- * knn, knn_emit, rdf_distances, steinhardt. */
+ * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
+ * rdf_distances, steinhardt (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 

@@ -12,11 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
-def ctx():
-    """One fgpu context for the whole GPU session; fails loudly when the library or the device is missing."""
+@pytest.fixture(scope="session", params=["auto", "general"])
+def ctx(request):
+    """One fgpu context per search-kernel family for the whole GPU session; fails loudly when the library or
+    the device is missing.  "auto" is the product's own choice (the warp-cooperative kernels wherever the grid
+    is regular), "general" forces the thread-per-query family that covers the remaining cases: both must agree
+    with the oracle bit for bit."""
     from freud_b200 import _capi
 
     c = _capi.Context(0)
+    c.force_general_search(request.param == "general")
     yield c
     c.close()
