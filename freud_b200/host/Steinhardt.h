@@ -1,0 +1,112 @@
+// freud::order::Steinhardt (plain q_l) on the GPU kernel of libfreud_b200.so.
+//
+// Signatures: Steinhardt(ls, average, wl, weighted, wl_normalize) (freud/order/Steinhardt.h:66-90),
+// compute(nlist /*nullable*/, points, qargs) (Steinhardt.h:153-155), getQl / getQlm / getParticleOrder /
+// getOrder / getL / is* (Steinhardt.h:96-150; bound in export-Steinhardt.cc:22-33).
+// compute() = reallocateArrays + baseCompute + normalizeSystem (Steinhardt.cc:54-118, 120-222, 291-327): per
+// particle q_lm(i) = sum_j w_ij Y_lm(wrap(p_j - p_i)) / sum_j w_ij and q_l(i) = sqrt(4 pi / (2l+1) sum_m |q_lm|^2).
+// The second-shell average and the w_l invariants (computeAve, aggregatewl) are the "next" rows of SURVEY.md
+// section 8f and throw until they are built: nothing is silently computed on the CPU.
+// Deviation, documented: the system-wide q_lm is accumulated in fp64 on the device (the reference's float32
+// thread-order sum is not reproducible run to run).
+#pragma once
+#include <complex>
+#include <memory>
+#include <vector>
+
+#include "Context.h"
+#include "ManagedArray.h"
+#include "NeighborList.h"
+#include "NeighborQuery.h"
+
+namespace freud { namespace order {
+
+class Steinhardt
+{
+public:
+    explicit Steinhardt(const std::vector<unsigned int>& ls, bool average = false, bool wl = false,
+                        bool weighted = false, bool wl_normalize = false)
+        : m_ls(ls), m_average(average), m_wl(wl), m_weighted(weighted), m_wl_normalize(wl_normalize),
+          m_qlmi(ls.size())
+    {
+        if (ls.empty())
+        {
+            throw std::invalid_argument("Steinhardt requires at least one l.");
+        }
+        if (average || wl || wl_normalize)
+        {
+            throw std::runtime_error("freud_b200: Steinhardt average / wl / wl_normalize are not built yet "
+                                     "(SURVEY.md section 8f); only plain and weighted q_l run on the GPU path.");
+        }
+    }
+    explicit Steinhardt(unsigned int l, bool average = false, bool wl = false, bool weighted = false,
+                        bool wl_normalize = false)
+        : Steinhardt(std::vector<unsigned int> {l}, average, wl, weighted, wl_normalize)
+    {}
+
+    unsigned int getNP() const { return m_Np; }
+    const std::shared_ptr<util::ManagedArray<float>>& getParticleOrder() const { return m_qli; }
+    const std::shared_ptr<util::ManagedArray<float>>& getQl() const { return m_qli; }
+    const std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>>& getQlm() const { return m_qlmi; }
+    std::vector<float> getOrder() const { return m_norm; }
+    bool isAverage() const { return m_average; }
+    bool isWl() const { return m_wl; }
+    bool isWeighted() const { return m_weighted; }
+    bool isWlNormalized() const { return m_wl_normalize; }
+    std::vector<unsigned int> getL() const { return m_ls; }
+
+    void compute(const std::shared_ptr<locality::NeighborList>& nlist,
+                 const std::shared_ptr<locality::NeighborQuery>& points, const locality::QueryArgs& qargs)
+    {
+        unsigned int const Np = points->getNPoints();
+        // neighbours: the list handed in, or the default query over the points themselves
+        // (loopOverNeighborsIterator, NeighborComputeFunctional.h:112-150)
+        std::shared_ptr<locality::NeighborList> list = nlist;
+        if (!list)
+        {
+            list = points->query(points->getPoints(), Np, qargs)->toNeighborList();
+        }
+        else
+        {
+            list->validate(Np, Np);
+        }
+        // fresh outputs every call (Steinhardt.cc:54-83)
+        m_Np = Np;
+        size_t tot_m = 0;
+        for (unsigned int l : m_ls)
+        {
+            tot_m += 2 * (size_t) l + 1;
+        }
+        auto qli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()});
+        std::vector<float> qlm_flat((size_t) Np * tot_m * 2), sys(tot_m * 2);
+        std::vector<float> order(m_ls.size());
+        gpu::check(fgpu_steinhardt_compute(points->device(), list->device(gpu::context()), m_ls.data(),
+                                           (uint32_t) m_ls.size(), m_weighted ? 1 : 0, Np, nullptr, qli->data(),
+                                           qlm_flat.data(), sys.data(), order.data()));
+        size_t off = 0;
+        for (size_t r = 0; r < m_ls.size(); ++r)
+        {
+            size_t const nm = 2 * (size_t) m_ls[r] + 1;
+            auto arr = std::make_shared<util::ManagedArray<std::complex<float>>>(std::vector<size_t> {Np, nm});
+            const float* src = qlm_flat.data() + off;
+            for (size_t k = 0; k < (size_t) Np * nm; ++k)
+            {
+                (*arr)[k] = std::complex<float>(src[2 * k], src[2 * k + 1]);
+            }
+            m_qlmi[r] = arr;
+            off += (size_t) Np * nm * 2;
+        }
+        m_qli = qli;
+        m_norm = order;
+    }
+
+private:
+    unsigned int m_Np {0};
+    std::vector<unsigned int> m_ls;
+    bool m_average, m_wl, m_weighted, m_wl_normalize;
+    std::shared_ptr<util::ManagedArray<float>> m_qli;
+    std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>> m_qlmi;
+    std::vector<float> m_norm;
+};
+
+}} // namespace freud::order

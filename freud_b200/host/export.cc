@@ -1,0 +1,257 @@
+// Python bindings of the C++ host classes (module freud_b200._freud_b200).
+//
+// The reference binds the same methods with nanobind (freud/locality/export-NeighborQuery.cc,
+// export-NeighborList.cc, export-BondHistogramCompute.cc, freud/density/export-RDF.cc,
+// freud/order/export-Steinhardt.cc, freud/util/export-ManagedArray.h); nanobind is not installed in this
+// image, so the binding layer is written against pybind11 with the same conventions: inputs are C-contiguous
+// float32 (N, 3) arrays reinterpreted as vec3<float>*, outputs are zero-copy read-only numpy views whose
+// base object keeps the owning ManagedArray alive, C++ exceptions surface as ValueError / RuntimeError /
+// IndexError.  Submodules are named after the reference's extension modules (_box, _locality, _density,
+// _order) so that freud's Python layer maps onto them one to one.
+#include <pybind11/complex.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "Box.h"
+#include "NeighborList.h"
+#include "NeighborQuery.h"
+#include "RDF.h"
+#include "Steinhardt.h"
+
+namespace py = pybind11;
+using namespace freud;
+
+namespace {
+
+using points_array = py::array_t<float, py::array::c_style | py::array::forcecast>;
+
+const vec3<float>* as_vec3(const points_array& a, unsigned int& n)
+{
+    if (a.ndim() != 2 || a.shape(1) != 3)
+    {
+        throw std::invalid_argument("points must have shape (N, 3)");
+    }
+    n = (unsigned int) a.shape(0);
+    return reinterpret_cast<const vec3<float>*>(a.data());
+}
+
+// zero-copy, read-only view; the capsule owns a shared_ptr copy (export-ManagedArray.h:22-52)
+template<typename T> py::array to_numpy(const std::shared_ptr<const util::ManagedArray<T>>& arr)
+{
+    if (!arr)
+    {
+        return py::array_t<T>(0);
+    }
+    auto* holder = new std::shared_ptr<const util::ManagedArray<T>>(arr);
+    py::capsule owner(holder, [](void* p) { delete static_cast<std::shared_ptr<const util::ManagedArray<T>>*>(p); });
+    std::vector<py::ssize_t> shape(arr->shape().begin(), arr->shape().end());
+    py::array_t<T> out(shape, arr->data(), owner);
+    py::detail::array_proxy(out.ptr())->flags &= ~py::detail::npy_api::NPY_ARRAY_WRITEABLE_;
+    return std::move(out);
+}
+template<typename T> py::array to_numpy(const std::shared_ptr<util::ManagedArray<T>>& arr)
+{
+    return to_numpy<T>(std::shared_ptr<const util::ManagedArray<T>>(arr));
+}
+
+} // namespace
+
+PYBIND11_MODULE(_freud_b200, m)
+{
+    m.doc() = "C++ host classes of freud_b200 (reference-compatible signatures on the sm_100a C ABI)";
+    m.def("version", [] { return std::string(fgpu_version()); });
+    m.def("device_count", [] { return fgpu_device_count(); });
+
+    // ---- _box ------------------------------------------------------------------------------------------
+    auto mbox = m.def_submodule("_box");
+    py::class_<box::Box>(mbox, "Box")
+        .def(py::init<float, float, float, float, float, float, bool>(), py::arg("Lx"), py::arg("Ly"), py::arg("Lz"),
+             py::arg("xy") = 0.0F, py::arg("xz") = 0.0F, py::arg("yz") = 0.0F, py::arg("is2D") = false)
+        .def("getLx", &box::Box::getLx)
+        .def("getLy", &box::Box::getLy)
+        .def("getLz", &box::Box::getLz)
+        .def("getTiltFactorXY", &box::Box::getTiltFactorXY)
+        .def("getTiltFactorXZ", &box::Box::getTiltFactorXZ)
+        .def("getTiltFactorYZ", &box::Box::getTiltFactorYZ)
+        .def("is2D", &box::Box::is2D)
+        .def("getVolume", &box::Box::getVolume)
+        .def("setPeriodic", &box::Box::setPeriodic)
+        .def("getPeriodic",
+             [](const box::Box& b) {
+                 auto p = b.getPeriodic();
+                 return py::make_tuple(p.x, p.y, p.z);
+             })
+        .def("getNearestPlaneDistance", [](const box::Box& b) {
+            auto d = b.getNearestPlaneDistance();
+            return py::make_tuple(d.x, d.y, d.z);
+        });
+
+    // ---- _locality -------------------------------------------------------------------------------------
+    auto mloc = m.def_submodule("_locality");
+    py::enum_<locality::QueryType>(mloc, "QueryType")
+        .value("none", locality::QueryType::none)
+        .value("ball", locality::QueryType::ball)
+        .value("nearest", locality::QueryType::nearest);
+    py::class_<locality::QueryArgs>(mloc, "QueryArgs")
+        .def(py::init<>())
+        .def_readwrite("mode", &locality::QueryArgs::mode)
+        .def_readwrite("num_neighbors", &locality::QueryArgs::num_neighbors)
+        .def_readwrite("r_max", &locality::QueryArgs::r_max)
+        .def_readwrite("r_min", &locality::QueryArgs::r_min)
+        .def_readwrite("r_guess", &locality::QueryArgs::r_guess)
+        .def_readwrite("scale", &locality::QueryArgs::scale)
+        .def_readwrite("exclude_ii", &locality::QueryArgs::exclude_ii);
+    mloc.def("get_iterator_terminator", [] {
+        auto t = locality::iterator_terminator();
+        return py::make_tuple(t.query_point_idx, t.point_idx, t.distance, t.weight);
+    });
+
+    py::class_<locality::NeighborList, std::shared_ptr<locality::NeighborList>>(mloc, "NeighborList")
+        .def(py::init<>())
+        .def(py::init([](py::array_t<unsigned int, py::array::c_style | py::array::forcecast> qidx, unsigned int nq,
+                         py::array_t<unsigned int, py::array::c_style | py::array::forcecast> pidx, unsigned int np,
+                         points_array vectors, py::object weights) {
+                 unsigned int nv = 0;
+                 const vec3<float>* v = as_vec3(vectors, nv);
+                 if (qidx.size() != pidx.size() || (py::ssize_t) nv != qidx.size())
+                 {
+                     throw std::invalid_argument("NeighborList arrays must have the same length.");
+                 }
+                 py::array_t<float, py::array::c_style | py::array::forcecast> w;
+                 const float* wp = nullptr;
+                 if (!weights.is_none())
+                 {
+                     w = weights.cast<py::array_t<float, py::array::c_style | py::array::forcecast>>();
+                     if (w.size() != qidx.size())
+                     {
+                         throw std::invalid_argument("NeighborList arrays must have the same length.");
+                     }
+                     wp = w.data();
+                 }
+                 return std::make_shared<locality::NeighborList>((unsigned int) qidx.size(), qidx.data(), nq, pidx.data(),
+                                                                 np, v, wp);
+             }),
+             py::arg("query_point_indices"), py::arg("num_query_points"), py::arg("point_indices"),
+             py::arg("num_points"), py::arg("vectors"), py::arg("weights") = py::none())
+        .def("getNumBonds", &locality::NeighborList::getNumBonds)
+        .def("getNumQueryPoints", &locality::NeighborList::getNumQueryPoints)
+        .def("getNumPoints", &locality::NeighborList::getNumPoints)
+        .def("getNeighbors", [](const locality::NeighborList& nl) { return to_numpy<unsigned int>(nl.getNeighbors()); })
+        .def("getDistances", [](const locality::NeighborList& nl) { return to_numpy<float>(nl.getDistances()); })
+        .def("getWeights", [](const locality::NeighborList& nl) { return to_numpy<float>(nl.getWeights()); })
+        .def("getVectors", [](const locality::NeighborList& nl) { return to_numpy<float>(nl.getVectors()); })
+        .def("getCounts", [](const locality::NeighborList& nl) { return to_numpy<unsigned int>(nl.getCounts()); })
+        .def("getSegments", [](const locality::NeighborList& nl) { return to_numpy<unsigned int>(nl.getSegments()); })
+        .def("find_first_index", &locality::NeighborList::find_first_index)
+        .def("filter",
+             [](locality::NeighborList& nl, py::array_t<bool, py::array::c_style | py::array::forcecast> keep) {
+                 if (keep.size() != (py::ssize_t) nl.getNumBonds())
+                 {
+                     throw std::invalid_argument("filter mask must have one entry per bond");
+                 }
+                 return nl.filter(keep.data());
+             })
+        .def("filter_r", &locality::NeighborList::filter_r, py::arg("r_max"), py::arg("r_min") = 0.0F)
+        .def("sort", &locality::NeighborList::sort)
+        .def("copy", &locality::NeighborList::copy)
+        .def("validate", &locality::NeighborList::validate);
+
+    py::class_<locality::NeighborQueryIterator, std::shared_ptr<locality::NeighborQueryIterator>>(mloc,
+                                                                                                  "NeighborQueryIterator")
+        .def("next",
+             [](locality::NeighborQueryIterator& it) {
+                 auto b = it.next();
+                 return py::make_tuple(b.query_point_idx, b.point_idx, b.distance, b.weight);
+             })
+        .def("toNeighborList", &locality::NeighborQueryIterator::toNeighborList, py::arg("sort_by_distance") = false);
+
+    py::class_<locality::NeighborQuery, std::shared_ptr<locality::NeighborQuery>>(mloc, "NeighborQuery")
+        .def("query",
+             [](std::shared_ptr<locality::NeighborQuery> nq, points_array qp, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 return nq->query(q, n, qargs);
+             },
+             py::keep_alive<0, 1>(), py::keep_alive<0, 2>())
+        .def("getBox", &locality::NeighborQuery::getBox)
+        .def("getNPoints", &locality::NeighborQuery::getNPoints);
+    py::class_<locality::LinkCell, locality::NeighborQuery, std::shared_ptr<locality::LinkCell>>(mloc, "LinkCell")
+        .def(py::init([](const box::Box& b, points_array pts, float cell_width) {
+                 unsigned int n = 0;
+                 const vec3<float>* p = as_vec3(pts, n);
+                 return std::make_shared<locality::LinkCell>(b, p, n, cell_width);
+             }),
+             py::arg("box"), py::arg("points"), py::arg("cell_width") = 0.0F, py::keep_alive<1, 3>())
+        .def("getCellWidth", &locality::LinkCell::getCellWidth);
+    py::class_<locality::AABBQuery, locality::NeighborQuery, std::shared_ptr<locality::AABBQuery>>(mloc, "AABBQuery")
+        .def(py::init([](const box::Box& b, points_array pts) {
+                 unsigned int n = 0;
+                 const vec3<float>* p = as_vec3(pts, n);
+                 return std::make_shared<locality::AABBQuery>(b, p, n);
+             }),
+             py::arg("box"), py::arg("points"), py::keep_alive<1, 3>());
+    py::class_<locality::RawPoints, locality::NeighborQuery, std::shared_ptr<locality::RawPoints>>(mloc, "RawPoints")
+        .def(py::init([](const box::Box& b, points_array pts) {
+                 unsigned int n = 0;
+                 const vec3<float>* p = as_vec3(pts, n);
+                 return std::make_shared<locality::RawPoints>(b, p, n);
+             }),
+             py::arg("box"), py::arg("points"), py::keep_alive<1, 3>());
+
+    // ---- _density --------------------------------------------------------------------------------------
+    auto mden = m.def_submodule("_density");
+    py::enum_<density::NormalizationMode>(mden, "NormalizationMode")
+        .value("exact", density::NormalizationMode::exact)
+        .value("finite_size", density::NormalizationMode::finite_size);
+    py::class_<density::RDF, std::shared_ptr<density::RDF>>(mden, "RDF")
+        .def(py::init<unsigned int, float, float>(), py::arg("bins"), py::arg("r_max"), py::arg("r_min") = 0.0F)
+        .def("accumulateRDF",
+             [](density::RDF& rdf, std::shared_ptr<locality::NeighborQuery> nq, points_array qp,
+                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 rdf.accumulate(nq, q, n, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("query_points"), py::arg("nlist").none(true), py::arg("qargs"))
+        .def("getRDF", [](density::RDF& r) { return to_numpy<float>(r.getRDF()); })
+        .def("getNr", [](density::RDF& r) { return to_numpy<float>(r.getNr()); })
+        .def("getBinCounts", [](density::RDF& r) { return to_numpy<unsigned int>(r.getBinCounts()); })
+        .def("getBinEdges", &density::RDF::getBinEdges)
+        .def("getBinCenters", &density::RDF::getBinCenters)
+        .def("getBounds", &density::RDF::getBounds)
+        .def("getAxisSizes", &density::RDF::getAxisSizes)
+        .def("getBox", &density::RDF::getBox)
+        .def("reset", &density::RDF::reset)
+        .def_readwrite("mode", &density::RDF::mode);
+
+    // ---- _order ----------------------------------------------------------------------------------------
+    auto mord = m.def_submodule("_order");
+    py::class_<order::Steinhardt, std::shared_ptr<order::Steinhardt>>(mord, "Steinhardt")
+        .def(py::init<const std::vector<unsigned int>&, bool, bool, bool, bool>(), py::arg("ls"),
+             py::arg("average") = false, py::arg("wl") = false, py::arg("weighted") = false,
+             py::arg("wl_normalize") = false)
+        .def("compute",
+             [](order::Steinhardt& s, std::shared_ptr<locality::NeighborList> nlist,
+                std::shared_ptr<locality::NeighborQuery> nq,
+                const locality::QueryArgs& qargs) { s.compute(nlist, nq, qargs); },
+             py::arg("nlist").none(true), py::arg("points"), py::arg("qargs"))
+        .def("getQl", [](const order::Steinhardt& s) { return to_numpy<float>(s.getQl()); })
+        .def("getParticleOrder", [](const order::Steinhardt& s) { return to_numpy<float>(s.getParticleOrder()); })
+        .def("getQlm",
+             [](const order::Steinhardt& s) {
+                 py::list out;
+                 for (const auto& a : s.getQlm())
+                 {
+                     out.append(to_numpy<std::complex<float>>(a));
+                 }
+                 return out;
+             })
+        .def("getOrder", &order::Steinhardt::getOrder)
+        .def("getL", &order::Steinhardt::getL)
+        .def("getNP", &order::Steinhardt::getNP)
+        .def("isAverage", &order::Steinhardt::isAverage)
+        .def("isWl", &order::Steinhardt::isWl)
+        .def("isWeighted", &order::Steinhardt::isWeighted)
+        .def("isWlNormalized", &order::Steinhardt::isWlNormalized);
+}

@@ -1,0 +1,231 @@
+"""``freud.locality`` surface of the neighbour-query path, on the C++ host classes (``_freud_b200._locality``).
+
+Mirrors the reference's Python layer for this path only: ``NeighborQuery.from_system`` / ``query`` /
+``NeighborQueryResult.toNeighborList`` (``freud/locality.py:201-229, 268-414``), ``AABBQuery`` / ``LinkCell``
+/ ``_RawPoints`` (``:839-921``), ``NeighborList`` (``:417-836``), query-argument dictionaries (``:39-175``) and
+the ``_PairCompute`` argument resolution (``:924-1016``).  The objects held in ``_cpp_obj`` expose the same
+C++ methods the reference's nanobind modules do, so this file reads like upstream's; everything numerical
+happens in ``libfreud_b200.so`` on the GPU -- there is no CPU fallback.
+"""
+
+import numpy as np
+
+from .box import Box
+
+_VALID_QUERY_KEYS = ("mode", "r_min", "r_max", "r_guess", "num_neighbors", "exclude_ii", "scale")
+
+
+def _ext():
+    try:
+        from . import _freud_b200
+    except ImportError as exc:  # loud, never a fallback
+        raise ImportError("freud_b200._freud_b200 is not built: run `python -c \"import __graft_entry__ as g; "
+                          "g.build()\"` (make -C freud_b200/csrc && make -C freud_b200/host)") from exc
+    return _freud_b200
+
+
+def _cpp_box(box):
+    b = Box.from_box(box)
+    return _ext()._box.Box(b.Lx, b.Ly, b.Lz, b.xy, b.xz, b.yz, b.is2D)
+
+
+def _points(a, name="points"):
+    """freud.util._convert_array(shape=(None, 3), dtype=float32) semantics (freud/util.py:74-137)."""
+    a = np.asarray(a)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError(f"{name} must have shape (N, 3), got {a.shape}")
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _query_args(d):
+    """dict -> C++ QueryArgs (freud/locality.py:39-175: unknown keys are an error, mode is a string)."""
+    L = _ext()._locality
+    qa = L.QueryArgs()
+    for key, val in dict(d).items():
+        if key not in _VALID_QUERY_KEYS:
+            raise ValueError(f"You have passed an invalid query argument: {key}")
+        if key == "mode":
+            if val is None or val == "none":
+                qa.mode = L.QueryType.none
+            elif val == "ball":
+                qa.mode = L.QueryType.ball
+            elif val == "nearest":
+                qa.mode = L.QueryType.nearest
+            else:
+                raise ValueError("You have passed an invalid mode.")
+        elif key == "num_neighbors":
+            qa.num_neighbors = int(val)
+        elif key == "exclude_ii":
+            qa.exclude_ii = bool(val)
+        else:
+            setattr(qa, key, float(val))
+    return qa
+
+
+class NeighborQueryResult:
+    """Lazy result of ``NeighborQuery.query`` (freud/locality.py:178-229)."""
+
+    def __init__(self, nq, query_points, query_args):
+        self._nq = nq
+        self._query_points = query_points
+        self._query_args = query_args
+
+    def _iterator(self):
+        return self._nq._cpp_obj.query(self._query_points, self._query_args)
+
+    def __iter__(self):
+        it = self._iterator()
+        term = _ext()._locality.get_iterator_terminator()
+        while True:
+            bond = it.next()
+            if bond[:2] == term[:2]:
+                return
+            yield (bond[0], bond[1], bond[2])
+
+    def toNeighborList(self, sort_by_distance=False):
+        return NeighborList._from_cpp(self._iterator().toNeighborList(bool(sort_by_distance)))
+
+
+class NeighborQuery:
+    """Base of the query engines (freud/locality.py:232-414)."""
+
+    def __init__(self):
+        raise RuntimeError("The NeighborQuery class is abstract, and should not be instantiated directly.")
+
+    @classmethod
+    def from_system(cls, system, dimensions=None):
+        if isinstance(system, NeighborQuery):
+            return system
+        if hasattr(system, "box") and hasattr(system, "points"):
+            return _RawPoints(system.box, system.points)
+        box, points = system
+        return _RawPoints(Box.from_box(box, dimensions), points)
+
+    @property
+    def box(self):
+        return self._box
+
+    @property
+    def points(self):
+        return self._points
+
+    def query(self, query_points, query_args):
+        return NeighborQueryResult(self, _points(query_points, "query_points"), _query_args(query_args))
+
+
+class AABBQuery(NeighborQuery):
+    """freud/locality.py:852-869."""
+
+    def __init__(self, box, points):
+        self._box = Box.from_box(box)
+        self._points = _points(points).copy()  # private copy, as upstream (:867-868)
+        self._cpp_obj = _ext()._locality.AABBQuery(_cpp_box(self._box), self._points)
+
+
+class LinkCell(NeighborQuery):
+    """freud/locality.py:872-921."""
+
+    def __init__(self, box, points, cell_width=0):
+        self._box = Box.from_box(box)
+        self._points = _points(points).copy()
+        self._cpp_obj = _ext()._locality.LinkCell(_cpp_box(self._box), self._points, float(cell_width))
+
+    @property
+    def cell_width(self):
+        return self._cpp_obj.getCellWidth()
+
+
+class _RawPoints(NeighborQuery):
+    """freud/locality.py:839-849: what a ``(box, points)`` tuple becomes."""
+
+    def __init__(self, box, points):
+        self._box = Box.from_box(box)
+        self._points = _points(points).copy()
+        self._cpp_obj = _ext()._locality.RawPoints(_cpp_box(self._box), self._points)
+
+
+class NeighborList:
+    """freud/locality.py:417-836 (container surface)."""
+
+    def __init__(self):
+        self._cpp_obj = _ext()._locality.NeighborList()
+
+    @classmethod
+    def _from_cpp(cls, obj):
+        self = cls.__new__(cls)
+        self._cpp_obj = obj
+        return self
+
+    @classmethod
+    def from_arrays(cls, num_query_points, num_points, query_point_indices, point_indices, vectors, weights=None):
+        qi = np.ascontiguousarray(query_point_indices, dtype=np.uint32)
+        pi = np.ascontiguousarray(point_indices, dtype=np.uint32)
+        v = _points(vectors, "vectors")
+        if not (len(qi) == len(pi) == len(v)):
+            raise ValueError("query_point_indices, point_indices and vectors must have the same length.")
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        return cls._from_cpp(_ext()._locality.NeighborList(qi, int(num_query_points), pi, int(num_points), v, w))
+
+    def __len__(self):
+        return self._cpp_obj.getNumBonds()
+
+    def __getitem__(self, key):
+        return self._cpp_obj.getNeighbors()[key]
+
+    query_point_indices = property(lambda self: self._cpp_obj.getNeighbors()[:, 0])
+    point_indices = property(lambda self: self._cpp_obj.getNeighbors()[:, 1])
+    weights = property(lambda self: self._cpp_obj.getWeights())
+    distances = property(lambda self: self._cpp_obj.getDistances())
+    vectors = property(lambda self: self._cpp_obj.getVectors())
+    segments = property(lambda self: self._cpp_obj.getSegments())
+    neighbor_counts = property(lambda self: self._cpp_obj.getCounts())
+    num_query_points = property(lambda self: self._cpp_obj.getNumQueryPoints())
+    num_points = property(lambda self: self._cpp_obj.getNumPoints())
+
+    def copy(self, other=None):
+        if other is not None:
+            self._cpp_obj.copy(other._cpp_obj)
+            return self
+        new = NeighborList()
+        new._cpp_obj.copy(self._cpp_obj)
+        return new
+
+    def find_first_index(self, i):
+        return self._cpp_obj.find_first_index(int(i))
+
+    def filter(self, filt):
+        self._cpp_obj.filter(np.ascontiguousarray(filt, dtype=bool))
+        return self
+
+    def filter_r(self, r_max, r_min=0):
+        self._cpp_obj.filter_r(float(r_max), float(r_min))
+        return self
+
+    def sort(self, by_distance=False):
+        self._cpp_obj.sort(bool(by_distance))
+        return self
+
+
+class _PairCompute:
+    """Argument resolution shared by the computes (freud/locality.py:924-1016)."""
+
+    def _preprocess_arguments(self, system, query_points=None, neighbors=None):
+        nq = NeighborQuery.from_system(system)
+        if query_points is None:
+            query_points = nq.points
+        else:
+            query_points = _points(query_points, "query_points")
+        nlist, qargs = self._resolve_neighbors(neighbors, query_points is nq.points)
+        return nq, nlist, qargs, query_points
+
+    def _resolve_neighbors(self, neighbors, self_query):
+        if isinstance(neighbors, NeighborList):
+            return neighbors._cpp_obj, _ext()._locality.QueryArgs()
+        args = dict(self.default_query_args if neighbors is None else neighbors)
+        args.setdefault("exclude_ii", self_query)  # freud/locality.py:982
+        return None, _query_args(args)
+
+    @property
+    def default_query_args(self):
+        raise NotImplementedError(f"The {type(self).__name__} class does not provide default query arguments. "
+                                  "You must either provide query arguments or a neighbor list to this compute method.")

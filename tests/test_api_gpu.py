@@ -1,0 +1,199 @@
+"""The reference-facing API (freud_b200.locality / density / order -> C++ host classes -> C ABI -> CUDA) against the
+oracle.  Cases follow the reference's own suite: tests/test_locality_neighbor_query.py, test_density_rdf.py,
+test_order_steinhardt.py, test_managedarray.py (lines cited per test)."""
+import numpy as np
+import pytest
+
+from freud_b200 import data, density, locality, order
+from freud_b200.box import Box
+from oracle import port, ref
+from tests.util import BOXES, bits, random_points
+
+pytestmark = pytest.mark.gpu
+
+# upstream builds LinkCell with cell_width = r_max (tests/test_locality_neighbor_query.py:662-666); the default width
+# (10 particles per cell) is rejected for tiny systems exactly as in the reference (LinkCell.cc:241-246)
+ENGINES = {"aabb": locality.AABBQuery, "linkcell": lambda box, pts: locality.LinkCell(box, pts, cell_width=2.0),
+           "raw": lambda box, pts: (box, pts)}
+
+
+def make_nq(engine, box, pts):
+    obj = ENGINES[engine](box, pts)
+    return locality.NeighborQuery.from_system(obj)
+
+
+def assert_matches_oracle(nl, want, what):
+    assert len(nl) == len(want), what
+    assert np.array_equal(nl[:], want.neighbors), what
+    assert np.array_equal(bits(nl.distances), bits(want.distances)), f"{what}: distances differ bitwise"
+    assert np.array_equal(bits(nl.vectors), bits(want.vectors)), f"{what}: vectors differ bitwise"
+    assert np.array_equal(nl.segments, want.segments) and np.array_equal(nl.neighbor_counts, want.counts), what
+
+
+@pytest.mark.parametrize("engine", list(ENGINES))
+def test_query_ball_hand_built(engine):
+    """tests/test_locality_neighbor_query.py:94-155, :218-251 upstream."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [1, 0, 0], [3, 0, 0], [2, 0, 0]], np.float32)
+    nq = make_nq(engine, box, pts)
+    nl = nq.query(pts, dict(r_max=2.01)).toNeighborList()
+    assert list(nl.neighbor_counts) == [3, 4, 3, 4]
+    nl = nq.query(pts, dict(r_max=2.01, exclude_ii=True)).toNeighborList()
+    assert len(nl) == 10
+    bonds = {(int(i), int(j)) for i, j, d in nq.query(pts, dict(r_max=2.9, r_min=1.1, exclude_ii=True))}
+    assert bonds == {(0, 3), (1, 2), (2, 1), (3, 0)}
+    # zero query points -> empty (0, 2) list (tests/test_locality_neighbor_list.py:253-256)
+    nl = nq.query(np.zeros((0, 3), np.float32), dict(r_max=2.0)).toNeighborList()
+    assert len(nl) == 0 and nl[:].shape == (0, 2)
+
+
+@pytest.mark.parametrize("engine", ["aabb", "linkcell"])
+def test_query_nearest_hand_built(engine):
+    """tests/test_locality_neighbor_query.py:253-300 upstream."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [1, 0, 0], [3, 0, 0], [2, 0, 0]], np.float32)
+    nq = make_nq(engine, box, pts)
+    nl = nq.query(pts, dict(num_neighbors=3, exclude_ii=True)).toNeighborList()
+    rows = [set(int(j) for j in nl.point_indices[nl.query_point_indices == i]) for i in range(4)]
+    assert rows == [{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}]
+    nl = nq.query(pts, dict(num_neighbors=3, r_max=1.9, exclude_ii=True)).toNeighborList()
+    rows = [set(int(j) for j in nl.point_indices[nl.query_point_indices == i]) for i in range(4)]
+    assert rows == [{1}, {0, 3}, {3}, {1, 2}]
+
+
+@pytest.mark.parametrize("engine", ["aabb", "linkcell"])
+@pytest.mark.parametrize("seed", range(4))
+def test_exhaustive_search_vs_box_wrap(engine, seed):
+    """tests/test_locality_neighbor_query.py:395-448 upstream: the pair SET equals brute force with box.wrap."""
+    box, n, r = Box.cube(11), 400, 2.1
+    pts = random_points(box, n, seed)
+    q = random_points(box, 150, seed + 100)
+    nq = make_nq(engine, box, pts)
+    nl = nq.query(q, dict(r_max=r)).toNeighborList()
+    d = box.wrap((pts[None, :, :] - q[:, None, :]).reshape(-1, 3)).reshape(len(q), n, 3)
+    dist = np.sqrt((d.astype(np.float64) ** 2).sum(-1))
+    want = {(i, j) for i, j in zip(*np.nonzero(dist < r - 1e-4))}
+    maybe = {(i, j) for i, j in zip(*np.nonzero(dist < r + 1e-4))}
+    got = {(int(i), int(j)) for i, j in nl[:]}
+    assert want <= got <= maybe
+
+
+@pytest.mark.parametrize("name", ["cubic", "tri1", "sq2d"])
+@pytest.mark.parametrize("engine", ["aabb", "linkcell", "raw"])
+def test_engines_match_the_reference_bit_for_bit(name, engine):
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=41)
+    q = random_points(box, 300, seed=42)
+    nq = make_nq(engine, box, pts)
+    flavour = port.WRAP if engine == "linkcell" else port.IMAGE
+    for sbd in (False, True):
+        nl = nq.query(q, dict(r_max=r, r_min=0.5)).toNeighborList(sort_by_distance=sbd)
+        want = port.ball_nlist(flavour, box, box.is2D, pts, q, r, 0.5, False, sbd)
+        assert_matches_oracle(nl, want, f"{name} {engine} sbd={sbd}")
+    nl = nq.query(pts, dict(r_max=r, exclude_ii=True)).toNeighborList()
+    assert_matches_oracle(nl, port.ball_nlist(flavour, box, box.is2D, pts, pts, r, 0.0, True), f"{name} {engine} self")
+    # arrays are read-only (tests/test_locality_neighbor_list.py:26-39)
+    with pytest.raises(ValueError):
+        nl.distances[0] = 0
+
+
+@pytest.mark.parametrize("system_kind", ["tuple", "aabb", "linkcell"])
+def test_rdf_matches_the_reference(system_kind):
+    """density.RDF.compute on BASELINE.json configs[0]-shaped input: counts bit-exact, g(r) / n(r) within 1e-5."""
+    box, pts = data.make_random_system(30, 4000, seed=3)
+    system = {"tuple": (box, pts), "aabb": locality.AABBQuery(box, pts), "linkcell": locality.LinkCell(box, pts, 5.0)}[
+        system_kind]
+    flavour = port.WRAP if system_kind == "linkcell" else port.IMAGE
+    rdf = density.RDF(bins=100, r_max=5.0)
+    rdf.compute(system)
+    counts = port.rdf_accumulate(flavour, box, False, pts, pts, 100, 5.0, 0.0, True)
+    want = port.rdf_reduce(counts, 5.0, 0.0, box, False, len(pts), len(pts))
+    assert np.array_equal(rdf.bin_counts, counts)
+    np.testing.assert_allclose(rdf.rdf, want["rdf"], rtol=1e-5, atol=0)
+    np.testing.assert_allclose(rdf.n_r, want["n_r"], rtol=1e-5, atol=0)
+    assert np.array_equal(rdf.bin_edges, want["bin_edges"]) and np.array_equal(rdf.bin_centers, want["bin_centers"])
+    if ref.available() and system_kind != "linkcell":
+        R = ref.RDF(100, 5.0)
+        R.accumulate(ref.Query("raw", box, pts), pts, mode="ball", r_max=5.0, exclude_ii=True)
+        res = R.results()
+        assert np.array_equal(rdf.bin_counts, res["bin_counts"])
+        np.testing.assert_allclose(rdf.rdf, res["rdf"], rtol=1e-5, atol=0)
+        np.testing.assert_allclose(rdf.n_r, res["n_r"], rtol=1e-5, atol=0)
+    # statistical sanity of the reference suite (tests/test_density_rdf.py:94-127): g(r) ~ 1 for an ideal gas
+    assert abs(float(np.mean(rdf.rdf[20:])) - 1.0) < 0.02 and np.all(np.abs(rdf.rdf[40:] - 1.0) < 0.1)
+
+
+def test_rdf_accumulate_reset_false_query_points_and_nlist():
+    """tests/test_density_rdf.py:129-165 upstream (+ separate query points, a precomputed NeighborList, 2-D)."""
+    box, pts = data.make_random_system(40, 3000, is2D=True, seed=5)
+    _, pts2 = data.make_random_system(40, 3000, is2D=True, seed=6)
+    q = random_points(box, 500, seed=7)
+    rdf = density.RDF(50, 4.0, 0.5, normalization_mode="finite_size")
+    rdf.compute((box, pts), reset=False)
+    first = rdf.bin_counts  # a view handed out BEFORE the second frame
+    first_copy = first.copy()
+    rdf.compute((box, pts2), query_points=q, reset=False)
+    c = port.rdf_accumulate(port.IMAGE, box, True, pts, pts, 50, 4.0, 0.5, True)
+    assert np.array_equal(first_copy, c)
+    c2 = port.rdf_accumulate(port.IMAGE, box, True, pts2, q, 50, 4.0, 0.5, False, counts=c.copy())
+    assert np.array_equal(rdf.bin_counts, c2)
+    want = port.rdf_reduce(c2, 4.0, 0.5, box, True, len(pts2), len(q), frames=2, finite_size=True)
+    np.testing.assert_allclose(rdf.rdf, want["rdf"], rtol=1e-5)
+    np.testing.assert_allclose(rdf.n_r, want["n_r"], rtol=1e-5)
+    # reset=True starts over; a NeighborList as `neighbors` is binned bond by bond
+    nl = locality.AABBQuery(box, pts).query(pts, dict(r_max=4.0, exclude_ii=True)).toNeighborList()
+    rdf.compute((box, pts), neighbors=nl)
+    assert np.array_equal(rdf.bin_counts, c)
+    # output-lifetime contract (tests/test_managedarray.py:25-53): reset() hands out new arrays
+    old = rdf.rdf
+    old_copy = old.copy()
+    rdf.compute((box, pts2))
+    assert np.array_equal(old, old_copy) and not np.array_equal(rdf.rdf, old_copy)
+
+
+def test_rdf_empty_histogram():
+    """tests/test_density_rdf.py:226-237 upstream: far-apart points give zeros, no NaN in n(r)."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [4, 4, 4]], np.float32)
+    rdf = density.RDF(10, 1.0).compute((box, pts))
+    assert not rdf.bin_counts.any() and not rdf.rdf.any() and not rdf.n_r.any()
+
+
+def test_steinhardt_fcc_known_answers():
+    """PERFECT_FCC_Q6 = 0.57452416 (tests/test_order_steinhardt.py:17, :101-166 upstream) for k = 12 and a ball
+    query, through every system kind."""
+    box, pts = data.make_fcc_system(4)
+    for system in ((box, pts), locality.AABBQuery(box, pts), locality.LinkCell(box, pts, 1.0)):
+        st = order.Steinhardt(6).compute(system, neighbors=dict(num_neighbors=12))
+        np.testing.assert_allclose(st.particle_order, 0.57452416, atol=1e-5)
+        assert abs(st.order - 0.57452416) < 1e-5
+        st = order.Steinhardt(6).compute(system, neighbors=dict(r_max=0.8))
+        np.testing.assert_allclose(st.ql, 0.57452416, atol=1e-5)
+    # a NeighborList as neighbours, several l at once, harmonics shape
+    nl = locality.AABBQuery(box, pts).query(pts, dict(num_neighbors=12, exclude_ii=True)).toNeighborList()
+    st = order.Steinhardt([4, 6]).compute((box, pts), neighbors=nl)
+    assert st.particle_order.shape == (len(pts), 2) and [h.shape[1] for h in st.particle_harmonics] == [9, 13]
+    np.testing.assert_allclose(st.particle_order[:, 1], 0.57452416, atol=1e-5)
+
+
+def test_steinhardt_vs_reference_noisy_fcc():
+    box, pts = data.make_fcc_system(5, scale=1.2, sigma_noise=0.07, seed=9)
+    st = order.Steinhardt([4, 6]).compute((box, pts), neighbors=dict(num_neighbors=12))
+    if ref.available():
+        want = ref.Steinhardt([4, 6]).compute(ref.Query("raw", box, pts), num_neighbors=12, exclude_ii=True)
+        np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
+        for a, b in zip(st.particle_harmonics, want["qlm"]):
+            np.testing.assert_allclose(a, b, atol=1e-5)
+        np.testing.assert_allclose(st.order, want["order"], rtol=1e-4)
+    else:
+        pnl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True)
+        want = port.steinhardt(box, False, pts, pnl, [4, 6])
+        np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
+
+
+def test_steinhardt_nan_without_neighbours():
+    """tests/test_order_steinhardt.py:361-369 upstream."""
+    box = Box.cube(10)
+    pts = np.array([[0, 0, 0], [0.5, 0, 0], [4, 4, 4]], np.float32)
+    ql = order.Steinhardt(6).compute((box, pts), neighbors=dict(r_max=1.0)).ql
+    assert np.isfinite(ql[0]) and np.isfinite(ql[1]) and np.isnan(ql[2])
