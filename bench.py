@@ -355,9 +355,9 @@ def main():
 
     comm = None
     if world > 1 and args.workload in ("rdf4m", "traj2d"):
-        uid = [_capi.Communicator.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        comm = _capi.Communicator(ctx, uid[0], rank, world)
+        from freud_b200 import parallel
+
+        comm = parallel.make_communicator(ctx)  # NCCL on the library's stream; id travels over torch.distributed
 
     if args.workload in ("nl", "nl_image"):
         w = workload_nl(ctx, rank, n, WRAP if args.workload == "nl" else IMAGE)
@@ -505,33 +505,32 @@ def workload_rdf4m(ctx, rank, world, n, comm):
     bins, r_max = 500, 5.0
     L = (n / RHO) ** (1.0 / 3.0)
     box, pts = data.make_random_system(L, n, seed=0, tilt=(0.3, 0.2, 0.1))
+    from freud_b200 import parallel
+
     dp = _capi.DevicePoints(ctx, box, pts)
-    rdf = _capi.DeviceRDF(ctx, bins, r_max)
-    lo, hi = rank * n // world, (rank + 1) * n // world
+    srdf = parallel.ShardedRDF(ctx, bins, r_max, comm=comm, rank=rank, world=world)
+    rdf = srdf.rdf
+    lo, hi = parallel.shard_bounds(n, rank, world)
     shard = np.ascontiguousarray(pts[lo:hi])
     pin_pts, keep0 = pinned_empty((n, 3), np.float32)
     pin_pts[:] = pts
     pin_q, keep1 = pinned_empty((hi - lo, 3), np.float32)
     pin_q[:] = shard
 
+    shard_arg = None if world == 1 else (pin_q, lo)
+
     def step_dev():
-        rdf.reset()
+        srdf.reset()
         dp.build_cells(r_max)
-        if world == 1:
-            rdf.accumulate(dp, None, IMAGE, r_max, 0.0, True)
-        else:
-            rdf.accumulate(dp, pin_q, IMAGE, r_max, 0.0, True, q_index_offset=lo)
+        srdf.accumulate_frame(dp, IMAGE, r_max, 0.0, True, query_shard=shard_arg)
+        if comm is not None:
             rdf.allreduce(comm)
 
     def step_e2e():
-        rdf.reset()
+        srdf.reset()
         d = _capi.DevicePoints(ctx, box, pin_pts)
-        if world == 1:
-            rdf.accumulate(d, None, IMAGE, r_max, 0.0, True)
-        else:
-            rdf.accumulate(d, pin_q, IMAGE, r_max, 0.0, True, q_index_offset=lo)
-            rdf.allreduce(comm)
-        return rdf.read()
+        srdf.accumulate_frame(d, IMAGE, r_max, 0.0, True, query_shard=shard_arg)
+        return srdf.bin_counts()  # one ncclAllReduce(u32[500]) + D2H
 
     step_dev()
     n_bonds = int(rdf.read().astype(np.uint64).sum())
