@@ -145,6 +145,7 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
         # per launch, bytes that must move (DESIGN.md "Kernels"): fp32 positions, 16 B float4 on device
         "cell_assign": 12 * n + 8 * n + 4 * n_cells,
         "cell_scatter": 20 * n + 16 * n,
+        "search_nl": 16 * (n + n) + 4 * n_cells + 20 * n_bonds + 8 * n,  # single pass: positions in, 20 B/hit bag out
         "search_count": 16 * (n + n) + 4 * n_cells + 4 * n,
         "search_fill": 16 * (n + n) + 4 * n_cells + 4 * n + 16 * n_bonds,
         "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
