@@ -242,7 +242,6 @@ Search2Args base_search2_args(fgpu_points* pts, const QueryView& qv, uint32_t q_
     a.dy = g.dim[1];
     a.dz = g.dim[2];
     a.n_cells = g.n_cells;
-    a.n_tickets = search2_tickets(g.n_cells);
     a.cell_start = g.cell_start.ptr;
     a.sorted = g.sorted.ptr;
     a.q_cell_start = qv.cell_start;
@@ -263,7 +262,9 @@ Search2Args base_search2_args(fgpu_points* pts, const QueryView& qv, uint32_t q_
     double const E = 16.0 * 5.9604644775390625e-08 * ext;
     double const r_hi = (double) r_max + 4.0 * E;
     a.r_hi_sq = std::nextafter((float) (r_hi * r_hi * (1.0 + 1.0e-6)), INFINITY);
-    a.out_cap = search2_out_cap((pts->box.is2d ? 9.0 : 27.0) * (double) pts->n / (double) std::max(g.n_cells, 1U));
+    search2_plan(a, pts->n);
+    a.out_cap = search2_out_cap((pts->box.is2d ? 3.0 : 9.0) * (a.span + 2) * (double) pts->n
+                                / (double) std::max(g.n_cells, 1U));
     a.fail = reinterpret_cast<int*>(ctx->d_scalars + 4);
     a.cursor = ctx->d_scalars + 5;
     a.work_counter = reinterpret_cast<unsigned int*>(ctx->d_scalars + 6);
@@ -348,12 +349,8 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         for (int attempt = 0; attempt < 3 && !done && !general; ++attempt)
         {
             cap = std::min<uint64_t>(cap, 0xffffffffULL);
-            ctx->tq.reserve(cap);
-            ctx->tj.reserve(cap);
-            ctx->tv.reserve(cap * 3);
-            s2.tq = ctx->tq.ptr;
-            s2.tj = ctx->tj.ptr;
-            s2.tv = ctx->tv.ptr;
+            ctx->bag4.reserve(cap);
+            s2.bag = ctx->bag4.ptr;
             s2.temp_cap = (uint32_t) cap;
             s2.counts = nl->counts.ptr;
             s2.tmp_start = ctx->tmp_start.ptr;
@@ -386,12 +383,10 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
             FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
             exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
             Emit2Args e;
-            e.tq = ctx->tq.ptr;
-            e.tj = ctx->tj.ptr;
-            e.tv = ctx->tv.ptr;
+            e.bag = ctx->bag4.ptr;
             e.tmp_start = ctx->tmp_start.ptr;
-            e.counts = nl->counts.ptr;
             e.row_start = nl->row_start.ptr;
+            e.n_query = n_query;
             e.n_bonds = n_bonds;
             e.neighbors = nl->neighbors.ptr;
             e.distances = nl->distances.ptr;

@@ -92,8 +92,7 @@ struct fgpu_ctx
     fgpu::DevBuf<uint32_t> row_counts;    // per query: number of bonds
     fgpu::DevBuf<uint32_t> row_start;     // exclusive scan of row_counts (n_query + 1)
     fgpu::DevBuf<uint4> bag;              // unsorted hits {key_hi, key_lo, slot, query}
-    fgpu::DevBuf<uint32_t> tq, tj;        // search2 bag: query index / point index per hit
-    fgpu::DevBuf<float> tv;               // search2 bag: bond vector per hit
+    fgpu::DevBuf<float4> bag4;            // search2 bag: {bond vector, bits(point index)} per hit
     fgpu::DevBuf<uint32_t> tmp_start;     // per query: offset of its row in the bag
     fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
     uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
@@ -279,7 +278,9 @@ struct Search2Args
     BoxDev box;
     int dx, dy, dz;
     uint32_t n_cells;
-    uint32_t n_tickets;             // work items (runs of consecutive home cells)
+    int span;                       // cells per home tile along x (search2_plan)
+    uint32_t spans_per_row;
+    uint32_t n_tickets;             // work items: one home tile each
     const uint32_t* cell_start;     // candidates: cell list of the reference points
     const float4* sorted;
     const uint32_t* q_cell_start;   // queries, cell-sorted on the same grid
@@ -292,9 +293,7 @@ struct Search2Args
     float rcp_lx, rcp_ly, rcp_lz;   // RN(1 / L), rounded on the host
     float r_hi_sq;                  // stage-1 acceptance bound (WRAP)
     // NeighborList mode
-    uint32_t* tq;                   // bag: query index, point index, vector of every hit (rows contiguous)
-    uint32_t* tj;
-    float* tv;
+    float4* bag;                    // bag: {vector, bits(point index)} of every hit, rows contiguous
     uint32_t temp_cap;
     uint32_t out_cap;               // hit records a warp can buffer per batch (dynamic shared memory)
     uint32_t* counts;               // per query (original order)
@@ -308,7 +307,7 @@ struct Search2Args
     unsigned int* work_counter;
     unsigned long long* evals;      // may be nullptr
 };
-uint32_t search2_tickets(uint32_t n_cells);
+void search2_plan(Search2Args& a, uint32_t n_points); // sets span, spans_per_row, n_tickets
 bool search2_supported(const Search2Args& a, int mode);
 void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a);
 uint32_t search2_out_cap(double expected_candidates_per_query);
@@ -318,12 +317,10 @@ void launch_count_evals(fgpu_ctx* ctx, const Search2Args& a, uint32_t n_query, c
 
 struct Emit2Args
 {
-    const uint32_t* tq;
-    const uint32_t* tj;
-    const float* tv;
+    const float4* bag;
     const uint32_t* tmp_start;
-    const uint32_t* counts;
-    const uint32_t* row_start;
+    const uint32_t* row_start; // n_query + 1
+    uint32_t n_query;
     uint64_t n_bonds;
     uint32_t* neighbors;
     float* distances;

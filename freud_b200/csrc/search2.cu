@@ -6,13 +6,12 @@
 // loopOverNeighbors with RDF's binning lambda (freud/locality/NeighborComputeFunctional.h:195-217,
 // freud/density/RDF.cc:101-110).
 //
-// Mapping.  One warp owns one home cell at a time (work items are runs of kCellChunk consecutive cells, handed
-// out by an atomic ticket).  The 27 neighbour cells are <= 18 contiguous runs of the cell-ordered float4
-// array (3 x-adjacent cells of a (y, z) row are one run; the periodic x boundary splits a run in two); the
-// runs are flattened with a ballot/prefix scheme so that the 32 lanes load 32 consecutive CANDIDATES
-// (coalesced 16-byte loads, two rounds held in registers) while the queries of the home cell are broadcast
-// from shared memory one after the other.  Every warp instruction therefore decides 32 (query, candidate)
-// pairs.
+// Mapping.  One warp owns one home TILE at a time: a span of consecutive cells of one grid row (tile_walk.cuh;
+// the span is chosen so that a tile's candidates fill about four warp rounds), handed out by an atomic ticket.
+// The candidate cells of the tile are <= 27 contiguous runs of the cell-ordered float4 array; the runs are
+// flattened with a ballot/prefix scheme so that the 32 lanes load 32 consecutive CANDIDATES (coalesced 16-byte
+// loads, two rounds held in registers) while the queries of the tile are broadcast from shared memory one
+// after the other.  Every warp instruction therefore decides 32 (query, candidate) pairs.
 //
 // WRAP flavour, two stages: stage 1 is a conservative filter (fused arithmetic on pre-shifted candidates,
 // acceptance radius r_max + 4E, E = bound on the rounding of both arithmetics) that rejects ~80 % of the
@@ -24,23 +23,26 @@
 // vector of a candidate follows from how its cell was reached (all points inside the box, checked on the
 // device; otherwise the general kernel in search.cu runs instead).
 //
-// NeighborList mode writes each batch of complete rows (hits grouped by row, 20 B per hit) to a temporary
-// bag at a position reserved with one atomicAdd per batch, together with the row's count and bag offset;
-// k_emit2 then ranks every hit inside its row and writes the five output arrays.  RDF mode bins into one
+// NeighborList mode writes each batch of complete rows (hits grouped by row, one 16-byte record per hit) to a
+// temporary bag at a position reserved with one atomicAdd per batch, together with the row's count and bag
+// offset; k_emit2 then walks the OUTPUT rows, ranks every hit inside its row and writes the five arrays.  RDF mode bins into one
 // block-shared histogram with plain shared-memory atomics (measured 0.9 T increments/s, 5.7x faster than
 // match_any aggregation: profiles/microbench_r1_hist_div.txt) and merges once per block.
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "internal.h"
+#include "tile_walk.cuh"
 
 namespace fgpu {
 
 namespace {
 
-constexpr unsigned FULL = 0xffffffffU;
+using tile::Cand;
+using tile::FULL;
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCellChunk = 8;   // consecutive home cells per work ticket
 constexpr int kQueueCap = 96;   // stage-2 stack: < 32 left over + two pushes of <= 32
 
 __device__ __forceinline__ bool in_window2(float r_sq, float r_max_sq, float r_min_sq)
@@ -111,7 +113,7 @@ __device__ __forceinline__ void wrap_fast(const BoxDev& b, float ylx, float yly,
 // pairs reach stage 2 is irrelevant, rows are regrouped when a batch is flushed.
 struct WarpMemBase
 {
-    uint32_t r_excl[32], r_delta[32], r_code[32]; // non-empty candidate runs of the current home cell
+    tile::RunScratch runs;                        // non-empty candidate runs of the current home tile
     float4 query[32];                             // current query batch: x, y, z, bits(index to exclude)
     uint32_t qa[kQueueCap], qb[kQueueCap];        // stage-2 stack (WRAP: candidate slot, query slot; IMAGE+RDF: r_sq)
 };
@@ -136,14 +138,6 @@ __host__ __device__ inline size_t warp_mem_bytes(int mode, uint32_t out_cap)
 {
     return mode == S2_NL ? sizeof(WarpMemNL) + (size_t) out_cap * 5 * sizeof(uint32_t) : sizeof(WarpMemBase);
 }
-
-struct Cand
-{
-    float x, y, z;    // WRAP: p + lattice shift (approximate); IMAGE: p (z forced to 0 in 2-D)
-    float ix, iy, iz; // IMAGE: exact image vector to add to the query
-    uint32_t j;       // point index
-    uint32_t slot;    // position in the cell-ordered array
-};
 
 template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
 {
@@ -309,11 +303,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                 uint32_t const k = o_k[i];
                 uint32_t const rel = atomicAdd(&w.row_pos[k], 1U);
                 uint32_t const dst = (uint32_t) base + rel;
-                a.tq[dst] = w.qid[k];
-                a.tj[dst] = o_j[i];
-                a.tv[3 * (size_t) dst] = o_x[i];
-                a.tv[3 * (size_t) dst + 1] = o_y[i];
-                a.tv[3 * (size_t) dst + 2] = o_z[i];
+                a.bag[dst] = make_float4(o_x[i], o_y[i], o_z[i], __uint_as_float(o_j[i]));
             }
         }
         o_len = 0;
@@ -392,7 +382,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         }
     };
 
-    // ---- work loop ------------------------------------------------------------------------------------
+    // ---- work loop: one home tile (a span of a.span cells of one grid row) per ticket ---------------------
     for (;;)
     {
         uint32_t ticket = 0;
@@ -405,235 +395,101 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         {
             break;
         }
-        uint32_t const cell0 = ticket * kCellChunk;
-        uint32_t const cell1 = min(cell0 + (uint32_t) kCellChunk, a.n_cells);
-        int cz = (int) (cell0 / ((uint32_t) dx * dy));
-        uint32_t const rem = cell0 - (uint32_t) cz * dx * dy;
-        int cy = (int) (rem / (uint32_t) dx);
-        int cx = (int) (rem - (uint32_t) cy * dx);
-
-        for (uint32_t cell = cell0; cell < cell1; ++cell)
+        int cx0, cx1, cy, cz;
+        tile::ticket_tile(ticket, a.spans_per_row, a.span, dx, dy, cx0, cx1, cy, cz);
+        uint32_t const rowbase = ((uint32_t) cz * dy + cy) * dx;
+        uint32_t const qs0 = __ldg(a.q_cell_start + rowbase + cx0), qs1 = __ldg(a.q_cell_start + rowbase + cx1 + 1);
+        if (qs0 == qs1)
         {
-            uint32_t const qs0 = __ldg(a.q_cell_start + cell), qs1 = __ldg(a.q_cell_start + cell + 1);
-            if (qs0 != qs1)
+            continue;
+        }
+        tile::Runs const runs = tile::setup_runs(dx, dy, dz, a.cell_start, cx0, cx1, cy, cz, lane, wm.runs);
+        uint32_t const T = runs.T;
+        bool const any_wrap = runs.any_wrap;
+
+        // ---- batches of queries ------------------------------------------------------------------------
+        // NL: the hits of a batch are buffered until its rows are complete.  The batch size is optimistic
+        // (a third of a query's own 27 cells may hit; an ideal gas gives 15.5 %); a batch that overflows the
+        // buffer is discarded and redone at half the size, down to one query (whose hits fit if T does).
+        uint32_t q_per_batch = 32;
+        if (MODE == S2_NL)
+        {
+            if (T > a.out_cap)
             {
-                // ---- candidate runs: lane k < 18 describes run (row = k / 2, segment = k % 2) -------------
-                uint32_t len = 0, start = 0, code = 21U;
+                if (lane == 0)
                 {
-                    int const row = lane >> 1, seg = lane & 1;
-                    int const oz = row / 3 - 1, oy = row - 3 * (row / 3) - 1;
-                    bool valid = lane < 18 && !(dz == 1 && oz != 0);
-                    int y = cy + oy, z = cz + oz, wy = 0, wz = 0, wx = 0, x0, x1;
-                    if (y < 0)
-                    {
-                        y += dy;
-                        wy = -1;
-                    }
-                    else if (y >= dy)
-                    {
-                        y -= dy;
-                        wy = 1;
-                    }
-                    if (z < 0)
-                    {
-                        z += dz;
-                        wz = -1;
-                    }
-                    else if (z >= dz)
-                    {
-                        z -= dz;
-                        wz = 1;
-                    }
-                    if (seg == 0)
-                    {
-                        x0 = max(cx - 1, 0);
-                        x1 = min(cx + 1, dx - 1);
-                    }
-                    else
-                    {
-                        x0 = x1 = cx == 0 ? dx - 1 : 0;
-                        wx = cx == 0 ? -1 : 1;
-                        valid = valid && (cx == 0 || cx == dx - 1);
-                    }
-                    if (valid)
-                    {
-                        uint32_t const rowbase = ((uint32_t) z * dy + y) * dx;
-                        start = __ldg(a.cell_start + rowbase + x0);
-                        len = __ldg(a.cell_start + rowbase + x1 + 1) - start;
-                        code = (uint32_t) (wx + 1) | ((uint32_t) (wy + 1) << 2) | ((uint32_t) (wz + 1) << 4);
-                    }
+                    *a.fail = 2; // a single row may exceed the buffer: the general kernel takes over
                 }
-                uint32_t incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    uint32_t const t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o)
-                    {
-                        incl += t;
-                    }
-                }
-                uint32_t const T = __shfl_sync(FULL, incl, 31);
-                unsigned const m_ne = __ballot_sync(FULL, len != 0);
-                int const R = __popc(m_ne);
-                __syncwarp();
-                if (len != 0)
-                {
-                    int const ck = __popc(m_ne & lt_mask);
-                    wm.r_excl[ck] = incl - len;
-                    wm.r_delta[ck] = start - (incl - len);
-                    wm.r_code[ck] = code;
-                }
-                __syncwarp();
-                uint32_t const my_excl = lane < R ? wm.r_excl[lane] : 0xffffffffU;
-                uint32_t const my_delta = lane < R ? wm.r_delta[lane] : 0U;
-                uint32_t const my_code = lane < R ? wm.r_code[lane] : 21U;
-                bool const any_wrap = __any_sync(FULL, my_code != 21U);
-
-                // loads one round of candidates: flattened index f = B + lane
-                auto load_round = [&](uint32_t B, Cand& c) {
-                    uint32_t const f = B + lane;
-                    bool const in = f < T;
-                    uint32_t const rel = my_excl - B; // wraps for runs that start before B
-                    unsigned const M = __reduce_or_sync(FULL, rel < 32U ? 1U << rel : 0U);
-                    int const before = __popc(__ballot_sync(FULL, my_excl < B));
-                    int const r = in ? before + __popc(M & le_mask) - 1 : 0;
-                    uint32_t const delta = __shfl_sync(FULL, my_delta, r);
-                    c.slot = f + delta;
-                    c.ix = c.iy = c.iz = 0.0f;
-                    if (in)
-                    {
-                        float4 const p = __ldg(a.sorted + c.slot);
-                        c.x = p.x;
-                        c.y = p.y;
-                        c.z = p.z;
-                        c.j = __float_as_uint(p.w);
-                    }
-                    else
-                    {
-                        c.x = c.y = c.z = __int_as_float(0x7f800000); // +inf: fails every window test
-                        c.j = 0xffffffffU;
-                    }
-                    if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
-                    {
-                        c.z = in ? 0.0f : c.z; // AABBQuery.cc:118-122
-                    }
-                    if (any_wrap)
-                    {
-                        uint32_t const cd = __shfl_sync(FULL, my_code, r);
-                        int const wx = (int) (cd & 3U) - 1, wy = (int) ((cd >> 2) & 3U) - 1,
-                                  wz = (int) ((cd >> 4) & 3U) - 1;
-                        if (FLAVOUR == FGPU_FLAVOUR_WRAP)
-                        {
-                            // nearest image of the candidate (approximate: stage 1 only)
-                            float const fx = (float) wx, fy = (float) wy, fz = (float) wz;
-                            c.x += fx * box.ax + fy * box.bx + fz * box.cx;
-                            c.y += fy * box.by + fz * box.cy;
-                            c.z += fz * box.cz;
-                        }
-                        else
-                        {
-                            // the candidate's cell was reached by crossing w boundaries: the query image that
-                            // sees it is k = -w (all points inside the box), NeighborQuery.h:546-562
-                            image_vector(box, -wx, -wy, -wz, c.ix, c.iy, c.iz);
-                        }
-                    }
-                };
-
-                // ---- batches of queries --------------------------------------------------------------------
-                // NL: the hits of a batch are buffered until its rows are complete.  The batch size is optimistic
-                // (a third of the candidates may hit; an ideal gas gives 15.5 %); a batch that overflows the
-                // buffer is discarded and redone at half the size, down to one query (whose hits fit if T does).
-                uint32_t q_per_batch = 32;
+                q_per_batch = 0;
+            }
+            else
+            {
+                q_per_batch = min(32U, max(1U, (uint32_t) (cx1 - cx0 + 3) * a.out_cap / max(T, 1U)));
+            }
+        }
+        for (uint32_t qb0 = qs0; q_per_batch != 0 && qb0 < qs1;)
+        {
+            uint32_t const nqc = min(q_per_batch, qs1 - qb0);
+            __syncwarp();
+            if ((uint32_t) lane < nqc)
+            {
+                float4 q = __ldg(a.q_sorted + qb0 + lane);
+                uint32_t const qi = __float_as_uint(q.w);
                 if (MODE == S2_NL)
                 {
-                    if (T > a.out_cap)
-                    {
-                        if (lane == 0)
-                        {
-                            *a.fail = 2; // a single row may exceed the buffer: the general kernel takes over
-                        }
-                        q_per_batch = 0;
-                    }
-                    else
-                    {
-                        q_per_batch = min(32U, max(1U, 3U * a.out_cap / max(T, 1U)));
-                    }
+                    reinterpret_cast<WarpMemNL&>(wm).qid[lane] = qi;
                 }
-                for (uint32_t qb0 = qs0; q_per_batch != 0 && qb0 < qs1;)
+                if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
                 {
-                    uint32_t const nqc = min(q_per_batch, qs1 - qb0);
-                    __syncwarp();
-                    if ((uint32_t) lane < nqc)
-                    {
-                        float4 q = __ldg(a.q_sorted + qb0 + lane);
-                        uint32_t const qi = __float_as_uint(q.w);
-                        if (MODE == S2_NL)
-                        {
-                            reinterpret_cast<WarpMemNL&>(wm).qid[lane] = qi;
-                        }
-                        if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
-                        {
-                            q.z = 0.0f; // AABBQuery.cc:84-87
-                        }
-                        q.w = __uint_as_float(a.exclude_ii ? qi + a.q_index_offset : 0xffffffffU);
-                        sq[lane] = q;
-                    }
-                    __syncwarp();
-                    batch_base = qb0;
-                    batch_n = nqc;
-                    for (uint32_t B = 0; B < T; B += 64)
-                    {
-                        Cand c0, c1;
-                        load_round(B, c0);
-                        bool const two = B + 32 < T;
-                        if (two)
-                        {
-                            load_round(B + 32, c1);
-                        }
-                        else
-                        {
-                            c1 = c0;
-                        }
-                        if (any_wrap)
-                        {
-                            pair_loop(std::true_type {}, c0, c1, two, nqc);
-                        }
-                        else
-                        {
-                            pair_loop(std::false_type {}, c0, c1, two, nqc);
-                        }
-                    }
-                    if (MODE == S2_NL)
-                    {
-                        if (FLAVOUR == FGPU_FLAVOUR_WRAP && q_len != 0)
-                        {
-                            stage2_round(q_len); // rows of the batch must be complete before they are published
-                        }
-                        if (overflow)
-                        {
-                            __syncwarp();
-                            reinterpret_cast<WarpMemNL&>(wm).row_cnt[lane] = 0;
-                            o_len = 0;
-                            q_len = 0;
-                            overflow = false;
-                            q_per_batch = max(1U, nqc / 2);
-                            continue; // same qb0, smaller batch
-                        }
-                        flush_batch();
-                    }
-                    qb0 += nqc;
+                    q.z = 0.0f; // AABBQuery.cc:84-87
                 }
+                q.w = __uint_as_float(a.exclude_ii ? qi + a.q_index_offset : 0xffffffffU);
+                sq[lane] = q;
             }
-            if (++cx == dx)
+            __syncwarp();
+            batch_base = qb0;
+            batch_n = nqc;
+            for (uint32_t B = 0; B < T; B += 64)
             {
-                cx = 0;
-                if (++cy == dy)
+                Cand c0, c1;
+                tile::load_round<FLAVOUR>(runs, box, a.sorted, B, lane, c0);
+                bool const two = B + 32 < T;
+                if (two)
                 {
-                    cy = 0;
-                    ++cz;
+                    tile::load_round<FLAVOUR>(runs, box, a.sorted, B + 32, lane, c1);
+                }
+                else
+                {
+                    c1 = c0;
+                }
+                if (any_wrap)
+                {
+                    pair_loop(std::true_type {}, c0, c1, two, nqc);
+                }
+                else
+                {
+                    pair_loop(std::false_type {}, c0, c1, two, nqc);
                 }
             }
+            if (MODE == S2_NL)
+            {
+                if (FLAVOUR == FGPU_FLAVOUR_WRAP && q_len != 0)
+                {
+                    stage2_round(q_len); // rows of the batch must be complete before they are published
+                }
+                if (overflow)
+                {
+                    __syncwarp();
+                    reinterpret_cast<WarpMemNL&>(wm).row_cnt[lane] = 0;
+                    o_len = 0;
+                    q_len = 0;
+                    overflow = false;
+                    q_per_batch = max(1U, nqc / 2);
+                    continue; // same qb0, smaller batch
+                }
+                flush_batch();
+            }
+            qb0 += nqc;
         }
     }
     if (MODE == S2_RDF)
@@ -712,46 +568,77 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
     }
 }
 
-// ---- emit: one thread per bagged hit ------------------------------------------------------------------
-// Ranks the hit inside its row (NeighborBond::less_as_tuple / less_as_distance restricted to one row with
+// ---- emit: blocks over output rows, threads over the bonds of those rows ------------------------------------
+// Ranks every hit inside its row (NeighborBond::less_as_tuple / less_as_distance restricted to one row with
 // weight == 1, freud/locality/NeighborBond.h:80-112) and writes the five NeighborList arrays
-// (NeighborQuery.h:470-478).  The bag rows are contiguous, so the rank loop reads L1-resident words.
+// (NeighborQuery.h:470-478).  A block owns kEmitRows consecutive OUTPUT rows, so its stores cover one contiguous
+// window of every output array (full sectors); the bag rows it gathers are contiguous 16-byte records, and the
+// rank loop re-reads them from L1.
+constexpr int kEmitRows = 256;
+
 template<bool BY_DISTANCE> __global__ void __launch_bounds__(256) k_emit2(Emit2Args a)
 {
-    uint64_t const t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_bonds)
+    __shared__ uint32_t s_start[kEmitRows + 1];
+    __shared__ uint32_t s_tmp[kEmitRows];
+    uint32_t const r0 = blockIdx.x * kEmitRows;
+    uint32_t const n_rows = min((uint32_t) kEmitRows, a.n_query - r0);
+    for (uint32_t i = threadIdx.x; i <= n_rows; i += blockDim.x)
     {
-        return;
-    }
-    uint32_t const qi = a.tq[t], j = a.tj[t];
-    uint32_t const beg = a.tmp_start[qi], n = a.counts[qi];
-    float const rx = a.tv[3 * t], ry = a.tv[3 * t + 1], rz = a.tv[3 * t + 2];
-    float const d = __fsqrt_rn(dot_exact(rx, ry, rz)); // NeighborBond.h:41-44
-    uint32_t rank = 0;
-    if (!BY_DISTANCE)
-    {
-        for (uint32_t k = beg; k < beg + n; ++k)
+        s_start[i] = a.row_start[r0 + i];
+        if (i < n_rows)
         {
-            rank += a.tj[k] < j ? 1U : 0U;
+            s_tmp[i] = a.tmp_start[r0 + i];
         }
     }
-    else
+    __syncthreads();
+    uint32_t const out_end = s_start[n_rows];
+    for (uint32_t o = s_start[0] + threadIdx.x; o < out_end; o += blockDim.x)
     {
-        for (uint32_t k = beg; k < beg + n; ++k)
+        // row of output slot o: s_start[row] <= o < s_start[row + 1] (empty rows are skipped by construction)
+        uint32_t lo = 0, hi = n_rows;
+        while (hi - lo > 1)
         {
-            float const ox = a.tv[3 * (size_t) k], oy = a.tv[3 * (size_t) k + 1], oz = a.tv[3 * (size_t) k + 2];
-            float const od = __fsqrt_rn(dot_exact(ox, oy, oz));
-            uint32_t const oj = a.tj[k];
-            rank += (od < d || (od == d && oj < j)) ? 1U : 0U;
+            uint32_t const mid = (lo + hi) >> 1;
+            if (s_start[mid] <= o)
+            {
+                lo = mid;
+            }
+            else
+            {
+                hi = mid;
+            }
         }
+        uint32_t const first = s_start[lo], n = s_start[lo + 1] - first;
+        const float4* __restrict__ const row = a.bag + s_tmp[lo];
+        float4 const h = row[o - first];
+        uint32_t const j = __float_as_uint(h.w);
+        float const d = __fsqrt_rn(dot_exact(h.x, h.y, h.z)); // NeighborBond.h:41-44
+        uint32_t rank = 0;
+        if (!BY_DISTANCE)
+        {
+            for (uint32_t k = 0; k < n; ++k)
+            {
+                rank += __float_as_uint(row[k].w) < j ? 1U : 0U;
+            }
+        }
+        else
+        {
+            for (uint32_t k = 0; k < n; ++k)
+            {
+                float4 const t = row[k];
+                float const od = __fsqrt_rn(dot_exact(t.x, t.y, t.z));
+                uint32_t const oj = __float_as_uint(t.w);
+                rank += (od < d || (od == d && oj < j)) ? 1U : 0U;
+            }
+        }
+        uint64_t const out = (uint64_t) first + rank;
+        reinterpret_cast<uint2*>(a.neighbors)[out] = make_uint2(r0 + lo, j);
+        a.distances[out] = d;
+        a.weights[out] = 1.0f;
+        a.vectors[3 * out] = h.x;
+        a.vectors[3 * out + 1] = h.y;
+        a.vectors[3 * out + 2] = h.z;
     }
-    uint64_t const out = (uint64_t) a.row_start[qi] + rank;
-    reinterpret_cast<uint2*>(a.neighbors)[out] = make_uint2(qi, j);
-    a.distances[out] = d;
-    a.weights[out] = 1.0f;
-    a.vectors[3 * out] = rx;
-    a.vectors[3 * out + 1] = ry;
-    a.vectors[3 * out + 2] = rz;
 }
 
 template<int FLAVOUR, int MODE, bool TRI> void launch_one(fgpu_ctx* ctx, const Search2Args& a, const char* name)
@@ -779,9 +666,30 @@ template<int FLAVOUR, int MODE, bool TRI> void launch_one(fgpu_ctx* ctx, const S
 
 } // namespace
 
-uint32_t search2_tickets(uint32_t n_cells)
+void search2_plan(Search2Args& a, uint32_t n_points)
 {
-    return (n_cells + kCellChunk - 1) / kCellChunk;
+    // Span of the home tile along x: as many cells as keep the tile's candidates (9 or 3 rows of span + 2 cells)
+    // near four warp rounds.  Sparse cells (cell width ~ r_max at liquid densities holds ~2 points) would
+    // otherwise spend most of their instructions on per-tile setup rather than on pairs.
+    double const per_cell = (double) n_points / (double) std::max(a.n_cells, 1U);
+    double const rows = a.dz == 1 ? 3.0 : 9.0;
+    int span = 1;
+    static const char* env = std::getenv("FGPU_SPAN");
+    if (env != nullptr && std::atoi(env) > 0)
+    {
+        span = std::atoi(env);
+    }
+    else
+    {
+        while (span < 8 && rows * (span + 3) * per_cell <= 136.0)
+        {
+            ++span;
+        }
+    }
+    span = std::max(1, std::min(span, a.dx));
+    a.span = span;
+    a.spans_per_row = (uint32_t) ((a.dx + span - 1) / span);
+    a.n_tickets = a.spans_per_row * (uint32_t) a.dy * (uint32_t) a.dz;
 }
 
 bool search2_supported(const Search2Args& a, int mode)
@@ -853,7 +761,7 @@ void launch_emit2(fgpu_ctx* ctx, int sort_by_distance, const Emit2Args& a)
     {
         return;
     }
-    unsigned const blocks = (unsigned) ((a.n_bonds + 255) / 256);
+    unsigned const blocks = (a.n_query + kEmitRows - 1) / kEmitRows;
     {
         KernelScope ks(ctx, "emit");
         if (sort_by_distance)
