@@ -208,8 +208,12 @@ def workload_q6(ctx, rank, n):
     pin_pts, keep0 = pinned_empty((n, 3), np.float32)
     pin_pts[:] = pts
 
+    # the window radius fgpu_knn_query starts from (sphere expected to hold 2(k + 1) points), so that the forced
+    # rebuild below produces the grid the query uses and the step holds exactly one cell-list build
+    r_window = float(np.cbrt(3.0 * 2.0 * 13.0 / (4.0 * np.pi * (n / float(box.volume)))))
+
     def step_dev():
-        dp.build_cells(1.0)
+        dp.build_cells(r_window)
         nl = dp.knn_query(None, 12, exclude_ii=True)
         return dp.steinhardt(nl, [6], want_qlm=False)
 
@@ -219,7 +223,8 @@ def workload_q6(ctx, rank, n):
         nl = d.knn_query(None, 12, exclude_ii=True)
         return d.steinhardt(nl, [6], want_qlm=True)["ql"]
 
-    algo = {"steinhardt": 588 * n, "knn": 16 * (n + n) + 8 * 12 * n, "pipeline": 124 * n}
+    algo = {"steinhardt": 588 * n, "knn": 16 * (n + n) + 8 * 12 * n, "search_nl": 16 * (n + n) + 16 * 26 * n + 8 * n,
+            "knn_select": (16 * 26 + 12 + 28 * 12) * n, "pipeline": 124 * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
                 config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
                 h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0], box=box, pts=pts, secondary={})
@@ -410,12 +415,15 @@ def main():
     ctx.profile(False)
     # dominant kernel over the timed region
     per_kernel = {}
-    for name in ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general", "search_rdf", "emit_general", "emit", "segments",
-                 "knn_emit", "knn", "rdf_distances", "steinhardt"):
-        ms, cnt = ctx.kernel_time(name)
-        if name == "knn":
-            ms2, cnt2 = ctx.kernel_time("knn_emit")
-            ms, cnt = ms - ms2, cnt - cnt2
+    names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
+             "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
+             "rdf_distances", "steinhardt")
+    raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
+    for name in names:
+        ms, cnt = raw[name]
+        for other in names:
+            if other != name and other.startswith(name):
+                ms, cnt = ms - raw[other][0], cnt - raw[other][1]
         if cnt:
             per_kernel[name] = (ms, cnt)
     ctx.kernel_time(reset=True)

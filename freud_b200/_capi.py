@@ -7,6 +7,7 @@ creating a :class:`Context` needs a CUDA device -- each failure is raised, never
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -131,6 +132,7 @@ class Context:
         self._h = _vp()
         check(lib().fgpu_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
+        self._children = weakref.WeakSet()  # device objects that must die before the context does
 
     @classmethod
     def default(cls, device=None):
@@ -173,15 +175,37 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child._release()
             lib().fgpu_ctx_destroy(self._h)
             self._h = _vp()
 
 
-class DeviceNeighborList:
+class _DeviceObject:
+    """Handle owner: destroyed by its own finaliser or, earlier, by ``Context.close()``."""
+
+    _destroy = None  # name of the C destructor
+
+    def _adopt(self, ctx):
+        self.ctx = ctx
+        ctx._children.add(self)
+
+    def _release(self):
+        if getattr(self, "_h", None):
+            getattr(lib(), self._destroy)(self._h)
+        self._h = None
+
+    def __del__(self):
+        self._release()
+
+
+class DeviceNeighborList(_DeviceObject):
     """Device-resident NeighborList (``fgpu_nlist``); arrays come to the host on demand."""
 
+    _destroy = "fgpu_nlist_destroy"
+
     def __init__(self, ctx, handle):
-        self.ctx = ctx
+        self._adopt(ctx)
         self._h = handle
         L = lib()
         self.num_bonds = int(L.fgpu_nlist_num_bonds(handle))
@@ -208,17 +232,14 @@ class DeviceNeighborList:
                                          ptr(v), C.byref(h)))
         return cls(ctx, h)
 
-    def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fgpu_nlist_destroy(self._h)
-            self._h = None
 
-
-class DevicePoints:
+class DevicePoints(_DeviceObject):
     """Device-resident reference points + box + cell list (``fgpu_points``)."""
 
+    _destroy = "fgpu_points_destroy"
+
     def __init__(self, ctx, box, points):
-        self.ctx = ctx
+        self._adopt(ctx)
         self.box6, self.is2d = box6_of(box)
         pts = f32(points, 3)
         self.n = len(pts)
@@ -277,17 +298,14 @@ class DevicePoints:
             soff += 2 * nm
         return dict(ql=ql, qlm=out_qlm, sys_qlm=out_sys, order=order)
 
-    def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fgpu_points_destroy(self._h)
-            self._h = None
 
-
-class DeviceRDF:
+class DeviceRDF(_DeviceObject):
     """Device-resident RDF histogram (``fgpu_rdf``)."""
 
+    _destroy = "fgpu_rdf_destroy"
+
     def __init__(self, ctx, bins, r_max, r_min=0.0):
-        self.ctx = ctx
+        self._adopt(ctx)
         self.bins = int(bins)
         self._h = _vp()
         check(lib().fgpu_rdf_create(ctx._h, self.bins, float(r_max), float(r_min), C.byref(self._h)))
@@ -312,19 +330,16 @@ class DeviceRDF:
     def allreduce(self, comm):
         check(lib().fgpu_rdf_allreduce(self._h, comm._h))
 
-    def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fgpu_rdf_destroy(self._h)
-            self._h = None
 
-
-class Communicator:
+class Communicator(_DeviceObject):
     """NCCL communicator, one rank per process (``fgpu_comm``)."""
+
+    _destroy = "fgpu_comm_destroy"
 
     def __init__(self, ctx, unique_id, rank, size):
         uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
         assert len(uid) == UNIQUE_ID_BYTES
-        self.ctx = ctx
+        self._adopt(ctx)
         self._h = _vp()
         check(lib().fgpu_comm_create(ctx._h, uid.ctypes.data_as(C.POINTER(C.c_uint8)), int(rank), int(size),
                                      C.byref(self._h)))
@@ -350,6 +365,4 @@ class Communicator:
         return a
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().fgpu_comm_destroy(self._h)
-            self._h = None
+        self._release()

@@ -934,6 +934,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                                         : std::cbrt(3.0 * 2.0 * (k + 1) / (4.0 * M_PI * density));
         QueryView qv;
         uint64_t total = 0;
+        bool evals_counted = false; // by the count kernel of the warp-cooperative path
         for (int attempt = 0;; ++attempt)
         {
             require(attempt < 64, FGPU_ERUNTIME, "kNN search did not converge");
@@ -942,6 +943,97 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             const fgpu_grid& g = pts->grid;
             bool const cover_all = g.dim[0] < 3 && g.dim[1] < 3 && (pts->box.is2d || g.dim[2] < 3);
             qv = prepare_queries(pts, query_points_host, nullptr, n_query);
+
+            // ---- production path: warp-cooperative ball search at the window radius, selection per row -----
+            // (regular grids with every point inside the box; the thread-per-query kernel below handles the rest)
+            float const r_win = r_grid < r_max ? r_grid : r_max;
+            Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, 0.0f, exclude_ii);
+            s2.knn_r_min = r_min > 0.0f ? r_min : 0.0f;
+            if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL))
+            {
+                bool const final_window = !(r_win < r_max);
+                double const shell = pts->box.is2d ? M_PI * (double) r_win * r_win
+                                                   : 4.0 / 3.0 * M_PI * (double) r_win * r_win * r_win;
+                uint64_t cap = (uint64_t) (1.25 * (double) n_query * density * shell) + 4096;
+                ctx->tmp_start.reserve((size_t) n_query + 1);
+                ctx->knn_hits.reserve((size_t) n_query + 1);
+                if (attempt == 0)
+                {
+                    launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+                }
+                bool done = false, general = false;
+                for (int pass = 0; pass < 3 && !done && !general; ++pass)
+                {
+                    cap = std::min<uint64_t>(cap, 0xffffffffULL);
+                    ctx->bag4.reserve(cap);
+                    s2.bag = ctx->bag4.ptr;
+                    s2.temp_cap = (uint32_t) cap;
+                    s2.counts = ctx->knn_hits.ptr;
+                    s2.tmp_start = ctx->tmp_start.ptr;
+                    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
+                    launch_search2(ctx, FGPU_FLAVOUR_IMAGE, S2_NL, s2);
+                    // optimistically enqueue the row bookkeeping behind the search: one host round trip per attempt
+                    KnnRowsArgs ra;
+                    ra.hits = ctx->knn_hits.ptr;
+                    ra.n_query = n_query;
+                    ra.k = k;
+                    ra.final = final_window ? 1 : 0;
+                    ra.counts = nl->counts.ptr;
+                    ra.row_start = nl->row_start.ptr;
+                    ra.unresolved = ctx->d_scalars + 2;
+                    ra.total = ctx->d_scalars + 3;
+                    launch_knn_rows(ctx, ra);
+                    FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
+                    exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+                    d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(unsigned long long));
+                    sync(ctx);
+                    int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+                    if (fail != 0)
+                    {
+                        general = true; // 1: points outside the box, 2: a row may be longer than the warp buffer
+                        evals_counted = evals_counted || (s2.evals != nullptr && attempt == 0 && fail != 1);
+                    }
+                    else if (ctx->h_scalars[5] <= cap)
+                    {
+                        done = true;
+                        evals_counted = evals_counted || s2.evals != nullptr;
+                    }
+                    else
+                    {
+                        cap = ctx->h_scalars[5]; // exact size, the search is deterministic
+                    }
+                }
+                if (done)
+                {
+                    if (ctx->h_scalars[2] != 0)
+                    {
+                        r_search = (double) r_grid * 1.5; // some row holds fewer than k points: widen the window
+                        continue;
+                    }
+                    uint64_t const n_bonds = ctx->h_scalars[3];
+                    alloc_bonds(nl.get(), n_bonds);
+                    if (n_bonds != 0)
+                    {
+                        KnnSelectArgs sa;
+                        sa.bag = ctx->bag4.ptr;
+                        sa.tmp_start = ctx->tmp_start.ptr;
+                        sa.hits = ctx->knn_hits.ptr;
+                        sa.row_start = nl->row_start.ptr;
+                        sa.n_query = n_query;
+                        sa.k = k;
+                        sa.neighbors = nl->neighbors.ptr;
+                        sa.distances = nl->distances.ptr;
+                        sa.weights = nl->weights.ptr;
+                        sa.vectors = nl->vectors.ptr;
+                        launch_knn_select(ctx, sort_by_distance, sa);
+                    }
+                    launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
+                    // no final sync: consumers are ordered on the same stream; the host query buffer was
+                    // consumed before the totals were read back above
+                    *out = nl.release();
+                    return;
+                }
+            }
             KnnArgs a;
             std::memset(&a, 0, sizeof(a));
             a.box = pts->box;
@@ -960,7 +1052,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             a.row_counts = ctx->row_counts.ptr;
             a.unresolved = ctx->d_scalars + 2;
             a.total = ctx->d_scalars + 3;
-            a.evals = ctx->count_evals ? ctx->d_evals : nullptr;
+            a.evals = ctx->count_evals && !evals_counted ? ctx->d_evals : nullptr;
             FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 2, 0, 2 * sizeof(unsigned long long), ctx->stream));
             launch_knn(ctx, a);
             d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 2 * sizeof(unsigned long long));

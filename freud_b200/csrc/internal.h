@@ -94,6 +94,7 @@ struct fgpu_ctx
     fgpu::DevBuf<uint4> bag;              // unsorted hits {key_hi, key_lo, slot, query}
     fgpu::DevBuf<float4> bag4;            // search2 bag: {bond vector, bits(point index)} per hit
     fgpu::DevBuf<uint32_t> tmp_start;     // per query: offset of its row in the bag
+    fgpu::DevBuf<uint32_t> knn_hits;      // kNN: per query, hits inside the search window
     fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
     uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
     int force_general = 0;                // FGPU_SEARCH=general: always run the search.cu kernels (testing)
@@ -292,6 +293,7 @@ struct Search2Args
     int exclude_ii;
     float rcp_lx, rcp_ly, rcp_lz;   // RN(1 / L), rounded on the host
     float r_hi_sq;                  // stage-1 acceptance bound (WRAP)
+    float knn_r_min;                // > 0 (IMAGE + NL, kNN only): also reject sqrt(r_sq) < knn_r_min (AABBQuery.cc:213)
     // NeighborList mode
     float4* bag;                    // bag: {vector, bits(point index)} of every hit, rows contiguous
     uint32_t temp_cap;
@@ -368,6 +370,35 @@ struct KnnEmitArgs
     float* vectors;
 };
 void launch_knn_emit(fgpu_ctx* ctx, const KnnEmitArgs& args);
+
+// ---- kNN on the warp-cooperative search (knn2.cu): ball search into the bag, then per-row selection ---------
+struct KnnRowsArgs
+{
+    const uint32_t* hits;        // per query: hits inside the window (bag row length)
+    uint32_t n_query;
+    uint32_t k;
+    int final;                   // the window already is r_max: short rows are complete
+    uint32_t* counts;            // per query: min(hits, k)
+    uint32_t* row_start;         // same values, scanned in place by the caller
+    unsigned long long* unresolved;
+    unsigned long long* total;
+};
+void launch_knn_rows(fgpu_ctx* ctx, const KnnRowsArgs& a);
+
+struct KnnSelectArgs
+{
+    const float4* bag;
+    const uint32_t* tmp_start;   // per query: offset of its row in the bag
+    const uint32_t* hits;        // per query: bag row length
+    const uint32_t* row_start;   // n_query + 1, output offsets
+    uint32_t n_query;
+    uint32_t k;
+    uint32_t* neighbors;
+    float* distances;
+    float* weights;
+    float* vectors;
+};
+void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs& a);
 
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
 

@@ -352,7 +352,11 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                     }
                     float const rx = __fsub_rn(c.x, tx), ry = __fsub_rn(c.y, ty), rz = __fsub_rn(c.z, tz);
                     float const r_sq = dot_exact(rx, ry, rz);
-                    bool const hit = in_window2(r_sq, r_max_sq, r_min_sq) && c.j != q_excl; // AABBQuery.cc:111-115
+                    bool hit = in_window2(r_sq, r_max_sq, r_min_sq) && c.j != q_excl; // AABBQuery.cc:111-115
+                    if (MODE == S2_NL && a.knn_r_min > 0.0f)
+                    {
+                        hit = hit && !(__fsqrt_rn(r_sq) < a.knn_r_min); // kNN filters on the distance, AABBQuery.cc:213
+                    }
                     if (MODE == S2_NL)
                     {
                         buffer_hits(hit, k, c.j, rx, ry, rz);
