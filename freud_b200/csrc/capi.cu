@@ -949,7 +949,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             float const r_win = r_grid < r_max ? r_grid : r_max;
             Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, 0.0f, exclude_ii);
             s2.knn_r_min = r_min > 0.0f ? r_min : 0.0f;
-            if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL))
+            if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL) && pts->n < 0x7fffffffU)
             {
                 bool const final_window = !(r_win < r_max);
                 double const shell = pts->box.is2d ? M_PI * (double) r_win * r_win

@@ -22,22 +22,53 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-// Per-tile exclusive scan; tile totals go to block_sums (if not null).
-__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* data, size_t n, uint32_t* block_sums)
+// Single-pass exclusive scan (chained scan with decoupled look-back): a block takes the next tile from an
+// atomic ticket (so every predecessor tile is already running), scans it in registers, publishes its
+// aggregate, and the first warp walks back over the predecessors' {flag, value} words -- 32 at a time --
+// until it meets an inclusive prefix.  One launch and 8 B/element of traffic instead of three launches per
+// level; u32 sums wrap like the counters they come from.
+enum : unsigned long long
+{
+    kFlagAggregate = 1ULL << 32,
+    kFlagPrefix = 2ULL << 32
+};
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restrict__ data, size_t n,
+                                                               volatile unsigned long long* state,
+                                                               unsigned int* ticket)
 {
     __shared__ uint32_t warp_sums[kScanThreads / 32];
-    size_t const base = (size_t) blockIdx.x * kScanTile + (size_t) threadIdx.x * kScanItems;
+    __shared__ uint32_t s_tile, s_prefix;
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+    {
+        s_tile = atomicAdd(ticket, 1U);
+    }
+    __syncthreads();
+    uint32_t const tile = s_tile;
+    size_t const base = (size_t) tile * kScanTile + (size_t) threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
+    if (base + kScanItems <= n)
+    {
+        uint4 const a = *reinterpret_cast<const uint4*>(data + base);
+        uint4 const b = *reinterpret_cast<const uint4*>(data + base + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+        {
+            v[k] = base + k < n ? data[base + k] : 0U;
+        }
+    }
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
     {
-        v[k] = base + k < n ? data[base + k] : 0U;
         sum += v[k];
     }
-    // inclusive warp scan of per-thread sums
     uint32_t incl = sum;
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
@@ -64,58 +95,83 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* data, siz
                 w += t;
             }
         }
+        uint32_t const total = __shfl_sync(0xffffffffU, w, kScanThreads / 32 - 1);
         if (lane < kScanThreads / 32)
         {
             warp_sums[lane] = w; // inclusive over warps
         }
+        // publish the aggregate, then look back for the exclusive prefix of this tile
+        uint32_t prefix = 0;
+        if (tile == 0)
+        {
+            if (lane == 0)
+            {
+                state[0] = kFlagPrefix | total;
+            }
+        }
+        else
+        {
+            if (lane == 0)
+            {
+                state[tile] = kFlagAggregate | total;
+            }
+            for (long long first = (long long) tile - 1;; first -= 32)
+            {
+                long long const idx = first - lane;
+                unsigned long long st;
+                do
+                {
+                    st = idx >= 0 ? state[idx] : kFlagPrefix; // tiles before the first: prefix 0
+                } while (__any_sync(0xffffffffU, (st >> 32) == 0));
+                unsigned const m = __ballot_sync(0xffffffffU, (st >> 32) == 2);
+                int const stop = m != 0 ? __ffs(m) - 1 : 31; // nearest predecessor holding an inclusive prefix
+                uint32_t part = lane <= stop ? (uint32_t) st : 0U;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    part += __shfl_xor_sync(0xffffffffU, part, o);
+                }
+                prefix += part;
+                if (m != 0)
+                {
+                    break;
+                }
+            }
+            if (lane == 0)
+            {
+                state[tile] = kFlagPrefix | (uint32_t) (prefix + total);
+            }
+        }
+        if (lane == 0)
+        {
+            s_prefix = prefix;
+        }
     }
     __syncthreads();
-    uint32_t excl = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0U);
+    uint32_t excl = s_prefix + incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0U);
+    uint32_t o[kScanItems];
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
     {
-        if (base + k < n)
-        {
-            data[base + k] = excl;
-        }
+        o[k] = excl;
         excl += v[k];
     }
-    if (block_sums != nullptr && threadIdx.x == kScanThreads - 1)
+    if (base + kScanItems <= n)
     {
-        block_sums[blockIdx.x] = excl;
+        *reinterpret_cast<uint4*>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
     }
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* data, size_t n, const uint32_t* block_offsets)
-{
-    uint32_t const off = block_offsets[blockIdx.x];
-    size_t const base = (size_t) blockIdx.x * kScanTile + (size_t) threadIdx.x * kScanItems;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
+    else
     {
-        if (base + k < n)
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
         {
-            data[base + k] += off;
+            if (base + k < n)
+            {
+                data[base + k] = o[k];
+            }
         }
     }
-}
-
-void scan_level(fgpu_ctx* ctx, uint32_t* data, size_t n, uint32_t* tmp)
-{
-    size_t const tiles = (n + kScanTile - 1) / kScanTile;
-    if (tiles <= 1)
-    {
-        KernelScope ks(ctx, "scan");
-        k_scan_tiles<<<1, kScanThreads, 0, ctx->stream>>>(data, n, nullptr);
-        return;
-    }
-    {
-        KernelScope ks(ctx, "scan");
-        k_scan_tiles<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
-    }
-    scan_level(ctx, tmp, tiles, tmp + tiles);
-    KernelScope ks(ctx, "scan");
-    k_scan_add<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, tmp);
 }
 
 // K1: cell index + arrival rank (one atomic per point) -- 12 B read, 8 B written per point
@@ -212,13 +268,21 @@ void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n)
     {
         return;
     }
-    size_t tmp_need = 0;
-    for (size_t t = (n + kScanTile - 1) / kScanTile; t > 1; t = (t + kScanTile - 1) / kScanTile)
+    if ((reinterpret_cast<uintptr_t>(data) & 15U) != 0)
     {
-        tmp_need += t;
+        throw Error(FGPU_ERUNTIME, "exclusive_scan_u32 needs a 16-byte aligned array");
     }
-    ctx->scan_tmp.reserve(tmp_need + 1);
-    scan_level(ctx, data, n, ctx->scan_tmp.ptr);
+    size_t const tiles = (n + kScanTile - 1) / kScanTile;
+    // scratch: one {flag, value} word per tile + the tile ticket
+    ctx->scan_tmp.reserve(2 * tiles + 2);
+    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->scan_tmp.ptr, 0, (2 * tiles + 2) * sizeof(uint32_t), ctx->stream));
+    auto* state = reinterpret_cast<unsigned long long*>(ctx->scan_tmp.ptr);
+    auto* ticket = reinterpret_cast<unsigned int*>(ctx->scan_tmp.ptr + 2 * tiles);
+    {
+        KernelScope ks(ctx, "scan");
+        k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
 GridDev grid_dev(const fgpu_points* pts)

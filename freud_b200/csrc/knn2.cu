@@ -14,8 +14,9 @@
 //                 order in which the reference's std::sort of NeighborBonds resolves the k-th place up to its
 //                 unspecified ties -- keep ranks < k, rank the kept hits by point index (or by (d, point
 //                 index) for sort_by_distance, NeighborBond.h:80-112) and write the five NeighborList arrays
-//                 (NeighborQuery.h:470-478).  Keys are staged in shared memory so that a rank is a loop of
-//                 broadcast loads; rows longer than the staging area re-read the bag (L1 hits).
+//                 (NeighborQuery.h:470-478).  r_sq and point indices are staged in shared memory so that a
+//                 rank is a loop of broadcast 16-byte loads and float compares (ties at the k-th place take
+//                 a slower exact path); rows longer than the staging area re-read the bag (L1 hits).
 #include "internal.h"
 
 namespace fgpu {
@@ -65,14 +66,72 @@ __device__ __forceinline__ uint64_t make_key(float f, uint32_t j)
     return ((uint64_t) __float_as_uint(f) << 32) | (uint64_t) j;
 }
 
+__device__ __forceinline__ uint64_t select_key(const float4& r)
+{
+    return make_key(dot_exact(r.x, r.y, r.z), __float_as_uint(r.w));
+}
+
+template<bool BY_DISTANCE> __device__ __forceinline__ uint64_t order_key(const float4& r)
+{
+    uint32_t const j = __float_as_uint(r.w);
+    return BY_DISTANCE ? make_key(__fsqrt_rn(dot_exact(r.x, r.y, r.z)), j) : (uint64_t) j;
+}
+
+__device__ __forceinline__ void write_bond(const KnnSelectArgs& a, uint64_t out, uint32_t row, const float4& r)
+{
+    reinterpret_cast<uint2*>(a.neighbors)[out] = make_uint2(row, __float_as_uint(r.w));
+    a.distances[out] = __fsqrt_rn(dot_exact(r.x, r.y, r.z)); // NeighborBond.h:41-44
+    a.weights[out] = 1.0f;
+    a.vectors[3 * out] = r.x;
+    a.vectors[3 * out + 1] = r.y;
+    a.vectors[3 * out + 2] = r.z;
+}
+
+// Rows longer than the staging area (very dense spots or a very large k): every rank re-reads the bag.
+template<bool BY_DISTANCE>
+__device__ __noinline__ void select_long_row(const KnnSelectArgs& a, const float4* __restrict__ bag, uint32_t n,
+                                             uint32_t kept, uint32_t row, uint64_t out0, int lane)
+{
+    auto rank_of = [&](uint64_t key) {
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            rank += select_key(bag[i]) < key ? 1U : 0U;
+        }
+        return rank;
+    };
+    for (uint32_t h = lane; h < n; h += 32)
+    {
+        float4 const r = bag[h];
+        if (rank_of(select_key(r)) >= kept)
+        {
+            continue;
+        }
+        uint64_t const ord = order_key<BY_DISTANCE>(r);
+        uint32_t pos = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            float4 const u = bag[i];
+            pos += (rank_of(select_key(u)) < kept && order_key<BY_DISTANCE>(u) < ord) ? 1U : 0U;
+        }
+        write_bond(a, out0 + pos, row, r);
+    }
+}
+
 template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_knn_select(KnnSelectArgs a)
 {
-    __shared__ uint64_t s_key[kSelWarps][kStage];  // selection keys (r_sq, j) of the row
-    __shared__ uint64_t s_ord[kSelWarps][kStage];  // ordering keys of the kept hits
+    // per warp: r_sq and point index of every hit of the row, then the ordering keys of the kept hits
+    __shared__ __align__(16) float s_rsq[kSelWarps][kStage];
+    __shared__ __align__(16) uint32_t s_j[kSelWarps][kStage];
+    __shared__ __align__(16) uint32_t s_oj[kSelWarps][kStage];
+    __shared__ __align__(16) float s_od[kSelWarps][kStage];
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t const lt_mask = (1U << lane) - 1U;
-    uint64_t* const sk = s_key[warp];
-    uint64_t* const so = s_ord[warp];
+    float* const rsq = s_rsq[warp];
+    uint32_t* const js = s_j[warp];
+    uint32_t* const oj = s_oj[warp];
+    float* const od = s_od[warp];
+    float const inf = __int_as_float(0x7f800000);
     uint32_t const n_warps = gridDim.x * kSelWarps;
     for (uint32_t row = blockIdx.x * kSelWarps + warp; row < a.n_query; row += n_warps)
     {
@@ -84,110 +143,117 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_k
         uint32_t const kept = min(n, a.k);
         const float4* __restrict__ const bag = a.bag + a.tmp_start[row];
         uint64_t const out0 = a.row_start[row];
-        bool const staged = n <= kStage; // then kept <= kStage as well
-        auto key_of = [](const float4& r) { return make_key(dot_exact(r.x, r.y, r.z), __float_as_uint(r.w)); };
-        auto ord_of = [](const float4& r) {
-            uint32_t const j = __float_as_uint(r.w);
-            return BY_DISTANCE ? make_key(__fsqrt_rn(dot_exact(r.x, r.y, r.z)), j) : (uint64_t) j;
-        };
-        // hits of the row that sort before `key` in the selection order
-        auto rank_of = [&](uint64_t key) {
-            uint32_t rank = 0;
-            if (staged)
-            {
-#pragma unroll 4
-                for (uint32_t i = 0; i < n; ++i)
-                {
-                    rank += sk[i] < key ? 1U : 0U;
-                }
-            }
-            else
-            {
-                for (uint32_t i = 0; i < n; ++i)
-                {
-                    rank += key_of(bag[i]) < key ? 1U : 0U;
-                }
-            }
-            return rank;
-        };
-        __syncwarp();
-        if (staged)
+        if (n > kStage)
         {
-            for (uint32_t h = lane; h < n; h += 32)
-            {
-                sk[h] = key_of(bag[h]);
-            }
+            select_long_row<BY_DISTANCE>(a, bag, n, kept, row, out0, lane);
+            continue;
+        }
+        uint32_t const n4 = (n + 3U) & ~3U, rounds = (n + 31U) >> 5;
+        __syncwarp();
+        for (uint32_t h = lane; h < n4; h += 32)
+        {
+            float4 const r = h < n ? bag[h] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0xffffffffU));
+            rsq[h] = h < n ? dot_exact(r.x, r.y, r.z) : inf; // padding never sorts before anything
+            js[h] = __float_as_uint(r.w);
         }
         __syncwarp();
-        // pass 1: selection rank of every hit (lane l owns hits l, l + 32, ...); kept hits publish their
-        // ordering key.  keep_bits remembers the verdicts of the (at most four) rounds of a staged row.
-        uint32_t keep_bits = 0, n_seen = 0;
-        for (uint32_t h0 = 0, t = 0; h0 < n; h0 += 32, ++t)
+        // pass 1: hits closer than this one (lane l owns hits l, l + 32, ...).  Hits whose count is below
+        // `kept` are the answer unless a group of equal r_sq straddles the k-th place.
+        uint32_t keep_bits = 0, n_keep = 0;
+        for (uint32_t t = 0; t < rounds; ++t)
         {
-            uint32_t const h = h0 + lane;
-            bool keep = false;
-            float4 r = make_float4(0, 0, 0, 0);
-            if (h < n)
+            uint32_t const h = t * 32 + lane;
+            // r_sq >= +0, so bit patterns order like values and (a - b) >> 31 is [a < b] in two instructions
+            uint32_t const mine = __float_as_uint(h < n ? rsq[h] : inf);
+            uint32_t closer = 0;
+            for (uint32_t i = 0; i < n4; i += 4)
             {
-                r = bag[h];
-                keep = rank_of(key_of(r)) < kept;
+                uint4 const v = *reinterpret_cast<const uint4*>(rsq + i);
+                closer += (v.x - mine) >> 31;
+                closer += (v.y - mine) >> 31;
+                closer += (v.z - mine) >> 31;
+                closer += (v.w - mine) >> 31;
             }
-            unsigned const mk = __ballot_sync(FULL, keep);
-            if (staged)
+            bool const keep = h < n && closer < kept;
+            keep_bits |= keep ? 1U << t : 0U;
+            n_keep += __popc(__ballot_sync(FULL, keep));
+        }
+        if (n_keep != kept)
+        {
+            // ties at the k-th place: resolve by point index, the order the general kernel and the oracle use
+            keep_bits = 0;
+            for (uint32_t t = 0; t < rounds; ++t)
             {
-                if (keep)
+                uint32_t const h = t * 32 + lane;
+                float const mine = h < n ? rsq[h] : inf;
+                uint32_t const my_j = h < n ? js[h] : 0xffffffffU;
+                uint32_t before = 0;
+                for (uint32_t i = 0; i < n; ++i)
                 {
-                    so[n_seen + __popc(mk & lt_mask)] = ord_of(r);
-                    keep_bits |= 1U << t;
+                    float const v = rsq[i];
+                    before += (v < mine || (v == mine && js[i] < my_j)) ? 1U : 0U;
                 }
-                n_seen += __popc(mk);
+                keep_bits |= (h < n && before < kept) ? 1U << t : 0U;
             }
+        }
+        // the kept hits publish their ordering keys (padded to a multiple of four)
+        uint32_t n_seen = 0;
+        for (uint32_t t = 0; t < rounds; ++t)
+        {
+            uint32_t const h = t * 32 + lane;
+            bool const keep = ((keep_bits >> t) & 1U) != 0;
+            unsigned const mk = __ballot_sync(FULL, keep);
+            if (keep)
+            {
+                uint32_t const pos = n_seen + __popc(mk & lt_mask);
+                oj[pos] = js[h];
+                if (BY_DISTANCE)
+                {
+                    od[pos] = __fsqrt_rn(rsq[h]);
+                }
+            }
+            n_seen += __popc(mk);
+        }
+        uint32_t const kept4 = (kept + 3U) & ~3U;
+        if (lane < kept4 - kept)
+        {
+            oj[kept + lane] = 0x7fffffffU; // sorts after every point index
+            od[kept + lane] = inf;
         }
         __syncwarp();
         // pass 2: position of every kept hit among the kept ones, then the five arrays
-        for (uint32_t h0 = 0, t = 0; h0 < n; h0 += 32, ++t)
+        for (uint32_t t = 0; t < rounds; ++t)
         {
-            uint32_t const h = h0 + lane;
-            bool keep = false;
-            float4 r = make_float4(0, 0, 0, 0);
-            if (h < n)
-            {
-                r = bag[h];
-                keep = staged ? ((keep_bits >> t) & 1U) != 0 : rank_of(key_of(r)) < kept;
-            }
-            if (__ballot_sync(FULL, keep) == 0)
+            if (((keep_bits >> t) & 1U) == 0)
             {
                 continue;
             }
-            uint64_t const ord = ord_of(r);
+            uint32_t const h = t * 32 + lane;
+            float4 const r = bag[h];
+            uint32_t const my_j = __float_as_uint(r.w);
             uint32_t pos = 0;
-            if (staged)
+            if (!BY_DISTANCE)
             {
-#pragma unroll 4
-                for (uint32_t i = 0; i < kept; ++i)
+                // point indices are below 2^31 on this path (checked by the host): same two-instruction compare
+                for (uint32_t i = 0; i < kept4; i += 4)
                 {
-                    pos += so[i] < ord ? 1U : 0U;
+                    uint4 const v = *reinterpret_cast<const uint4*>(oj + i);
+                    pos += (v.x - my_j) >> 31;
+                    pos += (v.y - my_j) >> 31;
+                    pos += (v.z - my_j) >> 31;
+                    pos += (v.w - my_j) >> 31;
                 }
             }
             else
             {
-                // rows longer than the staging area: order against every kept hit of the bag
-                for (uint32_t i = 0; i < n; ++i)
+                float const my_d = __fsqrt_rn(dot_exact(r.x, r.y, r.z));
+                for (uint32_t i = 0; i < kept; ++i)
                 {
-                    float4 const u = bag[i];
-                    pos += (rank_of(key_of(u)) < kept && ord_of(u) < ord) ? 1U : 0U;
+                    float const d = od[i];
+                    pos += (d < my_d || (d == my_d && oj[i] < my_j)) ? 1U : 0U; // NeighborBond.h:96-112
                 }
             }
-            if (keep)
-            {
-                uint64_t const out = out0 + pos;
-                reinterpret_cast<uint2*>(a.neighbors)[out] = make_uint2(row, __float_as_uint(r.w));
-                a.distances[out] = __fsqrt_rn(dot_exact(r.x, r.y, r.z));
-                a.weights[out] = 1.0f;
-                a.vectors[3 * out] = r.x;
-                a.vectors[3 * out + 1] = r.y;
-                a.vectors[3 * out + 2] = r.z;
-            }
+            write_bond(a, out0 + pos, row, r);
         }
     }
 }

@@ -13,15 +13,17 @@
 // loads, two rounds held in registers) while the queries of the tile are broadcast from shared memory one
 // after the other.  Every warp instruction therefore decides 32 (query, candidate) pairs.
 //
-// WRAP flavour, two stages: stage 1 is a conservative filter (fused arithmetic on pre-shifted candidates,
-// acceptance radius r_max + 4E, E = bound on the rounding of both arithmetics) that rejects ~80 % of the
-// pairs in 7 instructions; survivors are ballot-compacted into a per-warp queue and stage 2 runs the
-// reference's exact, un-fused arithmetic on 32 queued pairs at a time (dense lanes).  Stage 2 may assume
-// what stage 1 established -- |fractional displacement| <= 1/3 + eps on every axis -- which makes two exact
-// shortcuts legal (wrap_fast below).
-// IMAGE flavour: the exact test r = p - (q + image) is only 10 instructions, so there is no filter; the image
-// vector of a candidate follows from how its cell was reached (all points inside the box, checked on the
-// device; otherwise the general kernel in search.cu runs instead).
+// Two stages wherever a decision costs more than a filter (WRAP flavour in both modes, IMAGE flavour in
+// NeighborList mode): stage 1 is a conservative filter (fused arithmetic on candidates pre-shifted to the image
+// nearest to the home tile, acceptance radius r_max + 4E, E = bound on the rounding of both arithmetics) that
+// rejects ~80 % of the pairs in 7 instructions; survivors are ballot-compacted into a per-warp stack of
+// {candidate slot, query, boundary crossings} and stage 2 runs the reference's exact, un-fused arithmetic on 32
+// stacked pairs at a time (dense lanes), then buffers or bins the hits.  For WRAP, stage 2 may assume what
+// stage 1 established -- |fractional displacement| <= 1/3 + eps on every axis -- which makes two exact
+// shortcuts legal (wrap_fast below).  For IMAGE the exact test is r = p - (q + image): the image vector of a
+// candidate follows from how its cell was reached (all points inside the box, checked on the device; otherwise
+// the general kernel in search.cu runs instead).  The fused RDF of the IMAGE flavour has no filter: its exact
+// test is 10 instructions, so it decides inline and only stacks r_sq of the hits for the dense sqrt + bin.
 //
 // NeighborList mode writes each batch of complete rows (hits grouped by row, one 16-byte record per hit) to a
 // temporary bag at a position reserved with one atomicAdd per batch, together with the row's count and bag
@@ -29,6 +31,7 @@
 // block-shared histogram with plain shared-memory atomics (measured 0.9 T increments/s, 5.7x faster than
 // match_any aggregation: profiles/microbench_r1_hist_div.txt) and merges once per block.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
@@ -115,7 +118,7 @@ struct WarpMemBase
 {
     tile::RunScratch runs;                        // non-empty candidate runs of the current home tile
     float4 query[32];                             // current query batch: x, y, z, bits(index to exclude)
-    uint32_t qa[kQueueCap], qb[kQueueCap];        // stage-2 stack (WRAP: candidate slot, query slot; IMAGE+RDF: r_sq)
+    uint2 queue[kQueueCap];                       // stage-2 stack: {candidate slot, query k | crossing code << 8}; IMAGE+RDF: {r_sq, -}
 };
 
 struct WarpMemNL : WarpMemBase
@@ -150,8 +153,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
     unsigned char* const wbase = smem_raw + hist_bytes + (size_t) warp * warp_mem_bytes(MODE, a.out_cap);
     WarpMem& wm = *reinterpret_cast<WarpMem*>(wbase);
     float4* __restrict__ const sq = wm.query;
-    uint32_t* __restrict__ const qa = wm.qa;
-    uint32_t* __restrict__ const qb = wm.qb;
+    uint2* __restrict__ const queue = wm.queue;
     // NL only (pointers are never dereferenced otherwise)
     uint32_t* __restrict__ const o_k = reinterpret_cast<uint32_t*>(wbase + sizeof(WarpMemNL));
     uint32_t* __restrict__ const o_j = o_k + a.out_cap;
@@ -186,10 +188,14 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
     float const r_max_sq = __fmul_rn(a.r_max, a.r_max); // LinkCell.cc:498, AABBQuery.cc:79
     float const r_min_sq = __fmul_rn(a.r_min, a.r_min);
     float const r_hi_sq = a.r_hi_sq;
+    float const knn_r_min = a.knn_r_min;
+    // NeighborList mode always filters first and decides on dense lanes (stage 2); the fused RDF of the IMAGE
+    // flavour decides inline, its exact test being as cheap as the filter
+    constexpr bool FILTERED = FLAVOUR == FGPU_FLAVOUR_WRAP || MODE == S2_NL;
     int const dx = a.dx, dy = a.dy, dz = a.dz;
     uint32_t q_len = 0;     // stage-2 stack height
     uint32_t o_len = 0;     // NL: buffered hits of the current batch
-    uint32_t batch_base = 0, batch_n = 0; // NL: query slots [batch_base, batch_base + batch_n) form the batch
+    uint32_t batch_n = 0;   // NL: queries of the current batch (their hits are buffered until the rows are complete)
 
     // ---- consumers ------------------------------------------------------------------------------------
     // NL: append the hits of one round (local row k) to the batch buffer
@@ -231,26 +237,44 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         bool const act = (uint32_t) lane < n;
         uint32_t const e = q_len - n + lane;
         q_len -= n;
-        if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+        if (FILTERED)
         {
+            // the stack holds pairs that passed the conservative filter: run the reference's exact arithmetic
             bool hit = false;
             float rx = 0, ry = 0, rz = 0, r_sq = 0;
-            uint32_t j = 0, qs = 0;
+            uint32_t j = 0, k = 0;
             if (act)
             {
-                uint32_t const cs = qa[e];
-                qs = qb[e];
-                float4 const p = __ldg(a.sorted + cs);
-                float4 const q = __ldg(a.q_sorted + qs);
+                uint2 const ent = queue[e];
+                k = ent.y & 0xffU;
+                float4 const p = __ldg(a.sorted + ent.x);
+                float4 const q = sq[k];
                 j = __float_as_uint(p.w);
-                wrap_fast<TRI>(box, a.rcp_lx, a.rcp_ly, a.rcp_lz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y),
-                               __fsub_rn(p.z, q.z), rx, ry, rz);
+                if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+                {
+                    wrap_fast<TRI>(box, a.rcp_lx, a.rcp_ly, a.rcp_lz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y),
+                                   __fsub_rn(p.z, q.z), rx, ry, rz); // LinkCell.cc:522
+                }
+                else
+                {
+                    // r = p - (q + image), AABBQuery.cc:93,125; image 0 is +0 and is added like any other
+                    float ix, iy, iz;
+                    tile::code_image(box, ent.y >> 8, ix, iy, iz);
+                    float const pz = box.is2d ? 0.0f : p.z; // AABBQuery.cc:118-122 (q.z was zeroed on load)
+                    rx = __fsub_rn(p.x, __fadd_rn(q.x, ix));
+                    ry = __fsub_rn(p.y, __fadd_rn(q.y, iy));
+                    rz = __fsub_rn(pz, __fadd_rn(q.z, iz));
+                }
                 r_sq = dot_exact(rx, ry, rz);
-                hit = in_window2(r_sq, r_max_sq, r_min_sq);
+                hit = in_window2(r_sq, r_max_sq, r_min_sq) && j != __float_as_uint(q.w);
+                if (FLAVOUR == FGPU_FLAVOUR_IMAGE && knn_r_min > 0.0f)
+                {
+                    hit = hit && !(__fsqrt_rn(r_sq) < knn_r_min); // kNN filters on the distance, AABBQuery.cc:213
+                }
             }
             if (MODE == S2_NL)
             {
-                buffer_hits(hit, qs - batch_base, j, rx, ry, rz);
+                buffer_hits(hit, k, j, rx, ry, rz);
             }
             else
             {
@@ -260,7 +284,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         else
         {
             // IMAGE + RDF: the stack holds r_sq of accepted bonds
-            bin_hit(act, act ? __uint_as_float(qa[e]) : 0.0f);
+            bin_hit(act, act ? __uint_as_float(queue[e].x) : 0.0f);
         }
         __syncwarp();
     };
@@ -311,33 +335,28 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
     };
 
     // ---- the pair loop: every query of the batch against the (up to) 64 candidates held in registers --------
-    // WRAPPED: some candidate run of this home cell crosses a periodic boundary (uniform per cell)
-    auto pair_loop = [&](auto wrapped_tag, const Cand& c0, const Cand& c1, bool two, uint32_t nqc) {
+    // WRAPPED: some candidate run of this home tile crosses a periodic boundary; TWO: c1 holds a second round
+    auto pair_loop = [&](auto wrapped_tag, auto two_tag, const Cand& c0, const Cand& c1, uint32_t nqc) {
         constexpr bool WRAPPED = decltype(wrapped_tag)::value;
+        constexpr bool TWO = decltype(two_tag)::value;
         for (uint32_t k = 0; k < nqc; ++k)
         {
             float4 const q = sq[k];
             uint32_t const q_excl = __float_as_uint(q.w);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < (TWO ? 2 : 1); ++h)
             {
                 const Cand& c = h == 0 ? c0 : c1;
-                if (h == 1 && !two)
-                {
-                    break;
-                }
-                if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+                if (FILTERED)
                 {
                     // stage 1: conservative filter on the pre-shifted candidate (fused arithmetic is fine here)
                     float const ddx = c.x - q.x, ddy = c.y - q.y, ddz = c.z - q.z;
                     float const r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-                    bool const ok = r2 <= r_hi_sq && c.j != q_excl; // LinkCell.cc:517-520
+                    bool const ok = r2 <= r_hi_sq && c.j != q_excl; // LinkCell.cc:517-520, AABBQuery.cc:111-115
                     unsigned const m = __ballot_sync(FULL, ok);
                     if (ok)
                     {
-                        uint32_t const e = q_len + __popc(m & lt_mask);
-                        qa[e] = c.slot;
-                        qb[e] = batch_base + k;
+                        queue[q_len + __popc(m & lt_mask)] = make_uint2(c.slot, WRAPPED ? k | (c.code << 8) : k | (tile::kNoWrap << 8));
                     }
                     q_len += __popc(m);
                 }
@@ -352,35 +371,21 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                     }
                     float const rx = __fsub_rn(c.x, tx), ry = __fsub_rn(c.y, ty), rz = __fsub_rn(c.z, tz);
                     float const r_sq = dot_exact(rx, ry, rz);
-                    bool hit = in_window2(r_sq, r_max_sq, r_min_sq) && c.j != q_excl; // AABBQuery.cc:111-115
-                    if (MODE == S2_NL && a.knn_r_min > 0.0f)
+                    bool const hit = in_window2(r_sq, r_max_sq, r_min_sq) && c.j != q_excl; // AABBQuery.cc:111-115
+                    unsigned const m = __ballot_sync(FULL, hit);
+                    if (hit)
                     {
-                        hit = hit && !(__fsqrt_rn(r_sq) < a.knn_r_min); // kNN filters on the distance, AABBQuery.cc:213
+                        queue[q_len + __popc(m & lt_mask)].x = __float_as_uint(r_sq);
                     }
-                    if (MODE == S2_NL)
-                    {
-                        buffer_hits(hit, k, c.j, rx, ry, rz);
-                    }
-                    else
-                    {
-                        unsigned const m = __ballot_sync(FULL, hit);
-                        if (hit)
-                        {
-                            qa[q_len + __popc(m & lt_mask)] = __float_as_uint(r_sq);
-                        }
-                        q_len += __popc(m);
-                    }
+                    q_len += __popc(m);
                 }
             }
-            if (FLAVOUR == FGPU_FLAVOUR_WRAP || MODE == S2_RDF)
+            if (q_len >= 32)
             {
-                if (q_len >= 32)
+                stage2_round(32);
+                if (TWO && q_len >= 32)
                 {
                     stage2_round(32);
-                    if (q_len >= 32)
-                    {
-                        stage2_round(32);
-                    }
                 }
             }
         }
@@ -451,36 +456,41 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                 sq[lane] = q;
             }
             __syncwarp();
-            batch_base = qb0;
             batch_n = nqc;
             for (uint32_t B = 0; B < T; B += 64)
             {
                 Cand c0, c1;
-                tile::load_round<FLAVOUR>(runs, box, a.sorted, B, lane, c0);
-                bool const two = B + 32 < T;
-                if (two)
+                constexpr bool ZERO_Z = FLAVOUR == FGPU_FLAVOUR_IMAGE;
+                tile::load_round<FILTERED, ZERO_Z>(runs, box, a.sorted, B, lane, c0);
+                if (B + 32 < T)
                 {
-                    tile::load_round<FLAVOUR>(runs, box, a.sorted, B + 32, lane, c1);
+                    tile::load_round<FILTERED, ZERO_Z>(runs, box, a.sorted, B + 32, lane, c1);
+                    if (any_wrap)
+                    {
+                        pair_loop(std::true_type {}, std::true_type {}, c0, c1, nqc);
+                    }
+                    else
+                    {
+                        pair_loop(std::false_type {}, std::true_type {}, c0, c1, nqc);
+                    }
+                }
+                else if (any_wrap)
+                {
+                    pair_loop(std::true_type {}, std::false_type {}, c0, c0, nqc);
                 }
                 else
                 {
-                    c1 = c0;
+                    pair_loop(std::false_type {}, std::false_type {}, c0, c0, nqc);
                 }
-                if (any_wrap)
-                {
-                    pair_loop(std::true_type {}, c0, c1, two, nqc);
-                }
-                else
-                {
-                    pair_loop(std::false_type {}, c0, c1, two, nqc);
-                }
+            }
+            if (FILTERED && q_len != 0)
+            {
+                // stacked pairs name their query by its slot in this batch (and NeighborList rows must be
+                // complete before they are published): drain before the batch changes
+                stage2_round(q_len);
             }
             if (MODE == S2_NL)
             {
-                if (FLAVOUR == FGPU_FLAVOUR_WRAP && q_len != 0)
-                {
-                    stage2_round(q_len); // rows of the batch must be complete before they are published
-                }
                 if (overflow)
                 {
                     __syncwarp();
@@ -703,16 +713,16 @@ bool search2_supported(const Search2Args& a, int mode)
     return grid_ok && hist_ok;
 }
 
-uint32_t search2_out_cap(double expected_candidates_per_query)
+uint32_t search2_out_cap(double expected_candidates_per_tile)
 {
-    // room for 1.5x the expected candidate count of one query (so that a single row always fits, however
-    // dense), 20 B per record, four warps per block
-    uint32_t cap = 256;
-    while (cap < 2048 && (double) cap < 1.5 * expected_candidates_per_query)
-    {
-        cap *= 2;
-    }
-    return cap;
+    // A warp buffers the hits of a batch of rows; a single row always fits a buffer that holds every candidate
+    // of the tile, and a tile with more candidates than that sends the frame to the general kernel.  Room for
+    // the mean + 7 sigma of a Poisson tile (uniform systems never trip it), 20 B per record; the buffer is
+    // what limits the resident warps, so it is not rounded up to a power of two.
+    double const mu = std::max(expected_candidates_per_tile, 1.0);
+    double const want = mu + 7.0 * std::sqrt(mu) + 16.0;
+    uint32_t const cap = ((uint32_t) std::min(want, 2048.0) + 31U) & ~31U;
+    return std::max(cap, 128U);
 }
 
 void launch_count_evals(fgpu_ctx* ctx, const Search2Args& a, uint32_t n_query, const uint32_t* cell_of_point,

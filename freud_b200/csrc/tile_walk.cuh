@@ -38,10 +38,11 @@ struct Runs
 
 struct Cand
 {
-    float x, y, z;    // WRAP: p + lattice shift (approximate); IMAGE: p (z forced to 0 in 2-D)
-    float ix, iy, iz; // IMAGE: exact image vector to add to the query
+    float x, y, z;    // SHIFTED: p + lattice shift (approximate, filter only); else p (z forced to 0 if ZERO_Z)
+    float ix, iy, iz; // !SHIFTED: exact image vector to add to the query
     uint32_t j;       // point index
     uint32_t slot;    // position in the cell-ordered array
+    uint32_t code;    // boundary crossings of the candidate's run (kNoWrap: none)
 };
 
 __device__ __forceinline__ Runs setup_runs(int dx, int dy, int dz, const uint32_t* __restrict__ cell_start, int cx0,
@@ -129,9 +130,19 @@ __device__ __forceinline__ Runs setup_runs(int dx, int dy, int dz, const uint32_
     return r;
 }
 
+// The candidate's cell was reached by crossing w boundaries: the query image that sees it is k = -w (all
+// points inside the box), NeighborQuery.h:546-562.
+__device__ __forceinline__ void code_image(const BoxDev& box, uint32_t cd, float& ix, float& iy, float& iz)
+{
+    int const wx = (int) (cd & 3U) - 1, wy = (int) ((cd >> 2) & 3U) - 1, wz = (int) ((cd >> 4) & 3U) - 1;
+    image_vector(box, -wx, -wy, -wz, ix, iy, iz);
+}
+
 // One round of candidates: lane l gets flattened candidate B + l (a candidate that fails every window test if
-// B + l >= T).
-template<int FLAVOUR>
+// B + l >= T).  SHIFTED: the coordinates are moved to the image nearest to the home tile with fused arithmetic
+// -- good for a conservative filter only; otherwise they stay exact and (ix, iy, iz) is the image vector the
+// reference adds to the query.  ZERO_Z: AABBQuery.cc:118-122 (2-D boxes, IMAGE flavour).
+template<bool SHIFTED, bool ZERO_Z>
 __device__ __forceinline__ void load_round(const Runs& r, const BoxDev& box, const float4* __restrict__ sorted,
                                            uint32_t B, int lane, Cand& c)
 {
@@ -145,6 +156,7 @@ __device__ __forceinline__ void load_round(const Runs& r, const BoxDev& box, con
     uint32_t const delta = __shfl_sync(FULL, r.delta, run);
     c.slot = f + delta;
     c.ix = c.iy = c.iz = 0.0f;
+    c.code = kNoWrap;
     if (in)
     {
         float4 const p = __ldg(sorted + c.slot);
@@ -158,17 +170,17 @@ __device__ __forceinline__ void load_round(const Runs& r, const BoxDev& box, con
         c.x = c.y = c.z = __int_as_float(0x7f800000); // +inf: fails every window test
         c.j = 0xffffffffU;
     }
-    if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
+    if (ZERO_Z && box.is2d)
     {
-        c.z = in ? 0.0f : c.z; // AABBQuery.cc:118-122
+        c.z = in ? 0.0f : c.z;
     }
     if (r.any_wrap)
     {
         uint32_t const cd = __shfl_sync(FULL, r.code, run);
+        c.code = cd;
         int const wx = (int) (cd & 3U) - 1, wy = (int) ((cd >> 2) & 3U) - 1, wz = (int) ((cd >> 4) & 3U) - 1;
-        if (FLAVOUR == FGPU_FLAVOUR_WRAP)
+        if (SHIFTED)
         {
-            // nearest image of the candidate (approximate: stage-1 filter only)
             float const fx = (float) wx, fy = (float) wy, fz = (float) wz;
             c.x += fx * box.ax + fy * box.bx + fz * box.cx;
             c.y += fy * box.by + fz * box.cy;
@@ -176,9 +188,7 @@ __device__ __forceinline__ void load_round(const Runs& r, const BoxDev& box, con
         }
         else
         {
-            // the candidate's cell was reached by crossing w boundaries: the query image that sees it is
-            // k = -w (all points inside the box), NeighborQuery.h:546-562
-            image_vector(box, -wx, -wy, -wz, c.ix, c.iy, c.iz);
+            code_image(box, cd, c.ix, c.iy, c.iz);
         }
     }
 }
