@@ -145,7 +145,7 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
         # per launch, bytes that must move (DESIGN.md "Kernels"): fp32 positions, 16 B float4 on device
         "cell_assign": 12 * n + 8 * n + 4 * n_cells,
         "cell_scatter": 20 * n + 16 * n,
-        "search_nl": 16 * (n + n) + 4 * n_cells + 20 * n_bonds + 8 * n,  # single pass: positions in, 20 B/hit bag out
+        "search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,  # single pass: positions in, 16 B/hit bag out
         "search_count": 16 * (n + n) + 4 * n_cells + 4 * n,
         "search_fill": 16 * (n + n) + 4 * n_cells + 4 * n + 16 * n_bonds,
         "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
@@ -217,17 +217,21 @@ def workload_q6(ctx, rank, n):
         nl = dp.knn_query(None, 12, exclude_ii=True)
         return dp.steinhardt(nl, [6], want_qlm=False)
 
+    pin_ql, keep1 = pinned_empty((n, 1), np.float32)
+    pin_qlm, keep2 = pinned_empty((n * 13 * 2,), np.float32)
+
     def step_e2e():
-        # Steinhardt(6).compute((box, points), neighbors=dict(num_neighbors=12)) then .particle_order
+        # Steinhardt(6).compute((box, points), neighbors=dict(num_neighbors=12)) then .particle_order; the
+        # per-particle q_lm come back too, as the reference's compute() materialises them on the host
         d = _capi.DevicePoints(ctx, box, pin_pts)
         nl = d.knn_query(None, 12, exclude_ii=True)
-        return d.steinhardt(nl, [6], want_qlm=True)["ql"]
+        return d.steinhardt(nl, [6], want_qlm=True, out={"ql": pin_ql, "qlm": pin_qlm})["ql"]
 
     algo = {"steinhardt": 588 * n, "knn": 16 * (n + n) + 8 * 12 * n, "search_nl": 16 * (n + n) + 16 * 26 * n + 8 * n,
             "knn_select": (16 * 26 + 12 + 28 * 12) * n, "pipeline": 124 * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
                 config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
-                h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0], box=box, pts=pts, secondary={})
+                h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={})
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreud_b200.so")
 
 FLAVOUR_WRAP, FLAVOUR_IMAGE = 0, 1
+ST_WEIGHTED, ST_AVERAGE, ST_WL, ST_WL_NORMALIZE = 1, 2, 4, 8
 UNIQUE_ID_BYTES = 128
 
 _fp = C.POINTER(C.c_float)
@@ -63,7 +64,8 @@ SIGNATURES = {
     "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
     "fgpu_rdf_read": (C.c_int, [_vp, _up]),
     "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
-    "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp]),
+    "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp,
+                                         _fp]),
     "fgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "fgpu_comm_create": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, _vpp]),
     "fgpu_comm_destroy": (None, [_vp]),
@@ -81,7 +83,8 @@ class GpuError(RuntimeError):
     pass
 
 
-_CODE_TO_EXC = {-1: ValueError, -2: ValueError, -3: RuntimeError, -4: GpuError, -5: GpuError, -6: MemoryError}
+_CODE_TO_EXC = {-1: ValueError, -2: ValueError, -3: RuntimeError, -4: GpuError, -5: GpuError, -6: MemoryError,
+                -7: IndexError}
 
 
 def lib():
@@ -276,17 +279,27 @@ class DevicePoints(_DeviceObject):
                                    float(r_min), int(bool(exclude_ii)), int(bool(sort_by_distance)), C.byref(h)))
         return DeviceNeighborList(self.ctx, h)
 
-    def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0):
+    def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0, out=None, average=False,
+                   wl=False, wl_normalize=False):
+        """``out``: optional dict of preallocated (e.g. page-locked) float32 arrays ``ql`` (n, len(ls)) and
+        ``qlm`` (n * sum(2l+1) * 2,) to receive the per-particle results.  Returns ``ql`` (the averaged q_l when
+        ``average``), ``wl`` (when ``wl``), ``qlm`` (always un-averaged), ``sys_qlm`` and ``order``."""
         ls = np.atleast_1d(np.asarray(ls, dtype=np.uint32)).copy()
         n = nlist.num_query_points
         tot_m = int(sum(2 * int(l) + 1 for l in ls))
-        ql = np.empty((n, len(ls)), np.float32)
-        qlm = np.empty(n * tot_m * 2, np.float32) if want_qlm else None
+        out = out or {}
+        ql = out["ql"] if "ql" in out else np.empty((n, len(ls)), np.float32)
+        qlm = (out["qlm"] if "qlm" in out else np.empty(n * tot_m * 2, np.float32)) if want_qlm else None
+        assert ql.dtype == np.float32 and ql.size == n * len(ls) and ql.flags.c_contiguous
+        assert qlm is None or (qlm.dtype == np.float32 and qlm.size == n * tot_m * 2 and qlm.flags.c_contiguous)
+        wl_arr = np.empty((n, len(ls)), np.float32) if wl else None
         sys_qlm = np.empty(tot_m * 2, np.float32)
         order = np.empty(len(ls), np.float32)
-        check(lib().fgpu_steinhardt_compute(self._h, nlist._h, ptr(ls, _up), len(ls), int(bool(weighted)), int(n_total),
-                                            comm._h if comm is not None else None, ptr(ql), ptr(qlm), ptr(sys_qlm),
-                                            ptr(order)))
+        flags = (ST_WEIGHTED if weighted else 0) | (ST_AVERAGE if average else 0) | (ST_WL if wl else 0) \
+            | (ST_WL_NORMALIZE if wl_normalize else 0)
+        check(lib().fgpu_steinhardt_compute(self._h, nlist._h, ptr(ls, _up), len(ls), flags, int(n_total),
+                                            comm._h if comm is not None else None, ptr(ql), ptr(wl_arr), ptr(qlm),
+                                            ptr(sys_qlm), ptr(order)))
         out_qlm, out_sys, off, soff = [], [], 0, 0
         for l in ls:
             nm = 2 * int(l) + 1
@@ -296,7 +309,7 @@ class DevicePoints(_DeviceObject):
                 off += n * nm * 2
             out_sys.append(sys_qlm[soff:soff + 2 * nm].view(np.complex64))
             soff += 2 * nm
-        return dict(ql=ql, qlm=out_qlm, sys_qlm=out_sys, order=order)
+        return dict(ql=ql, wl=wl_arr, qlm=out_qlm, sys_qlm=out_sys, order=order)
 
 
 class DeviceRDF(_DeviceObject):

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <complex>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -1311,15 +1312,17 @@ int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
 }
 
 // ---- Steinhardt ------------------------------------------------------------------------------------------
-int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int weighted,
-                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* qlm_host, float* sys_qlm_host,
-                            float* order_host)
+int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
+                            float* sys_qlm_host, float* order_host)
 {
     return guarded([&] {
         require(pts != nullptr && nl != nullptr && ls != nullptr && n_ls != 0, FGPU_EINVALID, "null argument");
         require(pts->ctx == nl->ctx, FGPU_EINVALID, "points and nlist belong to different contexts");
         require(nl->n_points == pts->n, FGPU_EINVALID, "NeighborList was built for a different number of points");
         require(nl->n_query <= pts->n, FGPU_EINVALID, "NeighborList has more rows than there are points");
+        bool const weighted = (flags & FGPU_ST_WEIGHTED) != 0, average = (flags & FGPU_ST_AVERAGE) != 0;
+        bool const wl = (flags & FGPU_ST_WL) != 0, wl_normalize = wl && (flags & FGPU_ST_WL_NORMALIZE) != 0;
         fgpu_ctx* ctx = pts->ctx;
         bind_device(ctx);
         std::vector<uint32_t> lv(ls, ls + n_ls);
@@ -1327,17 +1330,22 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         for (uint32_t l : lv)
         {
             tot_m += 2 * (size_t) l + 1;
+            // getWigner3j, freud/order/Wigner3j.cc: std::out_of_range beyond the tabulated range
+            require(!wl || l <= 20, FGPU_ERANGE, "Wigner 3j coefficients are implemented for l <= 20.");
         }
         uint32_t const n = nl->n_query; // rows held by this rank (== pts->n on a single GPU)
+        require(!average || n == pts->n, FGPU_ERUNTIME,
+                "Steinhardt average needs the q_lm of every neighbour: all rows must be on this rank");
         if (n_total == 0)
         {
             n_total = n;
         }
-        DevBuf<float> d_ql, d_qlm;
+        DevBuf<float> d_ql, d_qlm, d_ql_ave, d_qlm_ave, d_wl, d_w3j;
+        DevBuf<uint32_t> d_w3j_off;
         DevBuf<double> d_sys;
         d_ql.reserve((size_t) n * n_ls + 1);
-        bool const want_qlm = qlm_host != nullptr;
-        if (want_qlm)
+        bool const need_qlm = qlm_host != nullptr || average || wl;
+        if (need_qlm)
         {
             d_qlm.reserve((size_t) n * tot_m * 2 + 2);
         }
@@ -1351,12 +1359,53 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         a.distances = nl->distances.ptr;
         a.weights = nl->weights.ptr;
         a.row_start = nl->row_start.ptr;
-        a.weighted = weighted != 0;
+        a.weighted = weighted;
         a.n_total = n_total;
         a.ql = d_ql.ptr;
-        a.qlm = want_qlm ? d_qlm.ptr : nullptr;
-        a.sys_qlm = d_sys.ptr;
+        a.qlm = need_qlm ? d_qlm.ptr : nullptr;
+        a.sys_qlm = average ? nullptr : d_sys.ptr; // the system sums come from the averaged q_lm then
         launch_steinhardt(ctx, a, lv);
+        if (average)
+        {
+            d_ql_ave.reserve((size_t) n * n_ls + 1);
+            d_qlm_ave.reserve((size_t) n * tot_m * 2 + 2);
+            SteinhardtAveArgs av;
+            av.n = n;
+            av.neighbors = nl->neighbors.ptr;
+            av.row_start = nl->row_start.ptr;
+            av.qlm = d_qlm.ptr;
+            av.qlm_ave = d_qlm_ave.ptr;
+            av.ql_ave = d_ql_ave.ptr;
+            av.sys_qlm = d_sys.ptr;
+            launch_steinhardt_average(ctx, av, (int) n_ls);
+        }
+        std::vector<std::vector<float>> w3j(n_ls);
+        if (wl)
+        {
+            std::vector<float> flat;
+            std::vector<uint32_t> off(n_ls);
+            for (uint32_t r = 0; r < n_ls; ++r)
+            {
+                w3j[r] = wigner3j_table(lv[r]);
+                off[r] = (uint32_t) flat.size();
+                flat.insert(flat.end(), w3j[r].begin(), w3j[r].end());
+            }
+            d_w3j.reserve(flat.size());
+            d_w3j_off.reserve(n_ls);
+            d_wl.reserve((size_t) n * n_ls + 1);
+            h2d(ctx, d_w3j.ptr, flat.data(), flat.size() * sizeof(float));
+            h2d(ctx, d_w3j_off.ptr, off.data(), n_ls * sizeof(uint32_t));
+            SteinhardtWlArgs wa;
+            wa.n = n;
+            wa.qlm = average ? d_qlm_ave.ptr : d_qlm.ptr;
+            wa.ql = average ? d_ql_ave.ptr : d_ql.ptr;
+            wa.w3j = d_w3j.ptr;
+            wa.w3j_off = d_w3j_off.ptr;
+            wa.normalize = wl_normalize ? 1 : 0;
+            wa.wl = d_wl.ptr;
+            launch_steinhardt_wl(ctx, wa, (int) n_ls);
+            sync(ctx); // the pageable host tables above were consumed
+        }
         if (comm != nullptr && comm->size > 1)
         {
             NcclApi& api = nccl_or_throw();
@@ -1368,9 +1417,13 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         d2h(ctx, sys.data(), d_sys.ptr, tot_m * 2 * sizeof(double));
         if (ql_host != nullptr)
         {
-            d2h(ctx, ql_host, d_ql.ptr, (size_t) n * n_ls * sizeof(float));
+            d2h(ctx, ql_host, average ? d_ql_ave.ptr : d_ql.ptr, (size_t) n * n_ls * sizeof(float));
         }
-        if (want_qlm)
+        if (wl_host != nullptr && wl)
+        {
+            d2h(ctx, wl_host, d_wl.ptr, (size_t) n * n_ls * sizeof(float));
+        }
+        if (qlm_host != nullptr)
         {
             d2h(ctx, qlm_host, d_qlm.ptr, (size_t) n * tot_m * 2 * sizeof(float));
         }
@@ -1402,9 +1455,38 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
                     sys_qlm_host[2 * (off + k) + 1] = (float) im;
                 }
             }
+            double const nf = 4.0 * M_PI / (2 * l + 1);
+            double order = std::sqrt(norm * nf);
+            if (wl)
+            {
+                // reduceWigner3j over the system q_lm (Wigner3j.cc:43-55), then the optional normalisation
+                double const ql_system = order;
+                double acc = 0.0;
+                size_t counter = 0;
+                int const li = (int) l;
+                auto at = [&](int m) { return off + (size_t) (m < 0 ? li - m : m); };
+                for (int m1 = -li; m1 <= li; ++m1)
+                {
+                    for (int m2 = std::max(-li - m1, -li); m2 <= std::min(li - m1, li); ++m2)
+                    {
+                        int const m3 = -m1 - m2;
+                        std::complex<double> const s1(sys[2 * at(m1)], sys[2 * at(m1) + 1]);
+                        std::complex<double> const s2(sys[2 * at(m2)], sys[2 * at(m2) + 1]);
+                        std::complex<double> const s3(sys[2 * at(m3)], sys[2 * at(m3) + 1]);
+                        acc += ((double) w3j[r][counter] * s1 * s2 * s3).real();
+                        ++counter;
+                    }
+                }
+                if (wl_normalize)
+                {
+                    double const nrm = std::sqrt(nf) / ql_system;
+                    acc *= nrm * nrm * nrm;
+                }
+                order = acc;
+            }
             if (order_host != nullptr)
             {
-                order_host[r] = (float) std::sqrt(norm * (4.0 * M_PI / (2 * l + 1)));
+                order_host[r] = (float) order;
             }
             off += 2 * (size_t) l + 1;
         }

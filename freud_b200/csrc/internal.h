@@ -419,6 +419,32 @@ struct SteinhardtArgs
 };
 void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& args, const std::vector<uint32_t>& ls);
 
+// follow-up kernels over the per-particle q_lm array (the l tables of launch_steinhardt must be resident)
+struct SteinhardtAveArgs
+{
+    uint32_t n;
+    const uint32_t* neighbors;
+    const uint32_t* row_start;
+    const float* qlm;     // per l blocks, complex64[n][2l+1]
+    float* qlm_ave;       // same layout
+    float* ql_ave;        // n x n_ls
+    double* sys_qlm;      // fp64 accumulators of the averaged q_lm (m >= 0), may be nullptr
+};
+void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls);
+
+struct SteinhardtWlArgs
+{
+    uint32_t n;
+    const float* qlm;        // source: q_lm or the averaged q_lm
+    const float* ql;         // normalisation source: q_l or the averaged q_l (n x n_ls)
+    const float* w3j;        // concatenated Wigner 3j tables
+    const uint32_t* w3j_off; // n_ls offsets into w3j (device)
+    int normalize;
+    float* wl;               // n x n_ls
+};
+void launch_steinhardt_wl(fgpu_ctx* ctx, const SteinhardtWlArgs& a, int n_ls);
+std::vector<float> wigner3j_table(uint32_t l);
+
 // NCCL (loaded with dlopen)
 int nccl_available(std::string* why);
 

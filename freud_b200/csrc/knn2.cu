@@ -150,6 +150,88 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_k
         }
         uint32_t const n4 = (n + 3U) & ~3U, rounds = (n + 31U) >> 5;
         __syncwarp();
+        if (n <= 32)
+        {
+            // the common case, straight-line: one hit per lane
+            bool const act = (uint32_t) lane < n;
+            float4 const r = act ? bag[lane] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0x7fffffffU));
+            uint32_t const my_j = __float_as_uint(r.w);
+            float const my_rsq = act ? dot_exact(r.x, r.y, r.z) : inf;
+            uint32_t const mine = __float_as_uint(my_rsq);
+            rsq[lane] = my_rsq;
+            js[lane] = my_j;
+            __syncwarp();
+            uint32_t closer = 0;
+            for (uint32_t i = 0; i < n4; i += 4)
+            {
+                uint4 const v = *reinterpret_cast<const uint4*>(rsq + i);
+                closer += (v.x - mine) >> 31;
+                closer += (v.y - mine) >> 31;
+                closer += (v.z - mine) >> 31;
+                closer += (v.w - mine) >> 31;
+            }
+            bool keep = act && closer < kept;
+            unsigned mk = __ballot_sync(FULL, keep);
+            if ((uint32_t) __popc(mk) != kept)
+            {
+                // ties at the k-th place: resolve by point index, the order the general kernel and the oracle use
+                uint32_t before = 0;
+                for (uint32_t i = 0; i < n; ++i)
+                {
+                    float const v = rsq[i];
+                    before += (v < my_rsq || (v == my_rsq && js[i] < my_j)) ? 1U : 0U;
+                }
+                keep = act && before < kept;
+                mk = __ballot_sync(FULL, keep);
+            }
+            float const my_d = __fsqrt_rn(my_rsq);
+            if (keep)
+            {
+                uint32_t const slot = __popc(mk & lt_mask);
+                oj[slot] = my_j;
+                if (BY_DISTANCE)
+                {
+                    od[slot] = my_d;
+                }
+            }
+            if (lane < 4)
+            {
+                oj[kept + lane] = 0x7fffffffU; // padding sorts after every point index (kept + 3 < kStage)
+                od[kept + lane] = inf;
+            }
+            __syncwarp();
+            if (keep)
+            {
+                uint32_t pos = 0;
+                if (!BY_DISTANCE)
+                {
+                    for (uint32_t i = 0; i < kept; i += 4)
+                    {
+                        uint4 const v = *reinterpret_cast<const uint4*>(oj + i);
+                        pos += (v.x - my_j) >> 31;
+                        pos += (v.y - my_j) >> 31;
+                        pos += (v.z - my_j) >> 31;
+                        pos += (v.w - my_j) >> 31;
+                    }
+                }
+                else
+                {
+                    for (uint32_t i = 0; i < kept; ++i)
+                    {
+                        float const d = od[i];
+                        pos += (d < my_d || (d == my_d && oj[i] < my_j)) ? 1U : 0U; // NeighborBond.h:96-112
+                    }
+                }
+                uint64_t const out = out0 + pos;
+                reinterpret_cast<uint2*>(a.neighbors)[out] = make_uint2(row, my_j);
+                a.distances[out] = my_d; // NeighborBond.h:41-44
+                a.weights[out] = 1.0f;
+                a.vectors[3 * out] = r.x;
+                a.vectors[3 * out + 1] = r.y;
+                a.vectors[3 * out + 2] = r.z;
+            }
+            continue;
+        }
         for (uint32_t h = lane; h < n4; h += 32)
         {
             float4 const r = h < n ? bag[h] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0xffffffffU));

@@ -10,6 +10,15 @@
 // in registers.  Negative m needs no accumulator: Y_{l,-m} = conj(Y_{l,m}) * (-1)^m term by term, and both
 // conj and the sign commute exactly with float summation, so q_{l,-m} is derived at the end.
 // Tolerance vs the reference: 1e-5 (libm vs CUDA sinf/cosf/atan2f/acosf differ in the last ulp).
+//
+// Options (Steinhardt.cc:224-289, 329-359; Wigner3j.cc:22-57) run as follow-up kernels over the per-particle
+// q_lm array left in device memory by the base kernel:
+//   k_steinhardt_average  second-shell average: q_lm(i) summed over the neighbours of i in bond order, plus
+//                         i itself, divided by (bonds + 1); averaged q_l; system sums of the averaged q_lm.
+//   k_steinhardt_wl       third-order invariant: sum over the Wigner 3j table of q_{l m1} q_{l m2} q_{l m3}
+//                         (real part), optionally scaled by (sqrt(4 pi / (2l+1)) / q_l)^3.
+// The 3j coefficients are computed on the host (Racah's formula with an exact integer sum) in the reference's
+// table order -- m1 = -l..l, m2 = max(-l-m1, -l)..min(l-m1, l) -- and used as float, like upstream.
 #include <cmath>
 #include <cstring>
 
@@ -274,6 +283,115 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
     (void) tot_m;
 }
 
+// ---- second-shell average (Steinhardt::computeAve, Steinhardt.cc:224-289) ----------------------------------
+// One thread per particle.  Only m >= 0 is accumulated: q_{l,-m} = (-1)^m conj(q_{l,m}) holds term by term and
+// both conj and the sign commute exactly with float summation and division.
+__global__ void __launch_bounds__(kThreads) k_steinhardt_average(SteinhardtAveArgs a, int n_ls)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+    {
+        return;
+    }
+    uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+    float const count = (float) (end - beg + 1U); // neighborcount starts at 1, Steinhardt.cc:244
+    for (int r = 0; r < n_ls; ++r)
+    {
+        int const l = c_ls[r];
+        int const nm = 2 * l + 1;
+        const float2* __restrict__ const block = reinterpret_cast<const float2*>(a.qlm) + (size_t) a.n * c_out_off[r];
+        float re[kSphLmax + 1], im[kSphLmax + 1];
+        for (int m = 0; m <= l; ++m)
+        {
+            re[m] = 0.0f;
+            im[m] = 0.0f;
+        }
+        for (uint32_t b = beg; b < end; ++b)
+        {
+            uint32_t const j = a.neighbors[2 * (size_t) b + 1];
+            const float2* __restrict__ const src = block + (size_t) j * nm;
+            for (int m = 0; m <= l; ++m)
+            {
+                float2 const v = src[m];
+                re[m] += v.x;
+                im[m] += v.y;
+            }
+        }
+        const float2* __restrict__ const own = block + (size_t) i * nm;
+        float2* const out = reinterpret_cast<float2*>(a.qlm_ave) + (size_t) a.n * c_out_off[r] + (size_t) i * nm;
+        float sum = 0.0f;
+        for (int m = 0; m <= l; ++m)
+        {
+            float2 const v = own[m];
+            re[m] = (re[m] + v.x) / count;
+            im[m] = (im[m] + v.y) / count;
+            out[m] = make_float2(re[m], im[m]);
+            sum += re[m] * re[m] + im[m] * im[m];
+            if (a.sys_qlm != nullptr)
+            {
+                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m)], (double) re[m]);
+                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m) + 1], (double) im[m]);
+            }
+        }
+        for (int m = 1; m <= l; ++m)
+        {
+            float const phase = (m & 1) ? -1.0f : 1.0f;
+            out[l + m] = make_float2(phase * re[m], -(phase * im[m]));
+            sum += re[m] * re[m] + im[m] * im[m];
+        }
+        float const nf = (float) (4.0 * 3.14159265358979323846 / nm);
+        a.ql_ave[(size_t) i * n_ls + r] = sqrtf(sum * nf);
+    }
+}
+
+// ---- third-order invariant (Steinhardt::aggregatewl + reduceWigner3j, Steinhardt.cc:329-359, Wigner3j.cc:22-57)
+__global__ void __launch_bounds__(kThreads) k_steinhardt_wl(SteinhardtWlArgs a, int n_ls)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+    {
+        return;
+    }
+    for (int r = 0; r < n_ls; ++r)
+    {
+        int const l = c_ls[r];
+        int const nm = 2 * l + 1;
+        const float2* __restrict__ const src
+            = reinterpret_cast<const float2*>(a.qlm) + (size_t) a.n * c_out_off[r] + (size_t) i * nm;
+        float2 q[2 * kSphLmax + 1];
+        for (int k = 0; k < nm; ++k)
+        {
+            q[k] = src[k];
+        }
+        const float* __restrict__ const w3j = a.w3j + a.w3j_off[r];
+        float result = 0.0f;
+        int counter = 0;
+        for (int m1 = -l; m1 <= l; ++m1)
+        {
+            float2 const s1 = q[m1 < 0 ? l - m1 : m1];
+            int const lo = max(-l - m1, -l), hi = min(l - m1, l);
+            for (int m2 = lo; m2 <= hi; ++m2)
+            {
+                int const m3 = -m1 - m2;
+                float2 const s2 = q[m2 < 0 ? l - m2 : m2], s3 = q[m3 < 0 ? l - m3 : m3];
+                float const w = __ldg(w3j + counter);
+                // (w * s1) * s2 * s3, left to right, real part
+                float const ar = w * s1.x, ai = w * s1.y;
+                float const br = ar * s2.x - ai * s2.y, bi = ar * s2.y + ai * s2.x;
+                result += br * s3.x - bi * s3.y;
+                ++counter;
+            }
+        }
+        if (a.normalize)
+        {
+            float const nf = (float) (4.0 * 3.14159265358979323846 / nm);
+            float const nrm = sqrtf(nf) / a.ql[(size_t) i * n_ls + r];
+            result *= nrm * nrm * nrm;
+        }
+        a.wl[(size_t) i * n_ls + r] = result;
+    }
+}
+
 void upload_tables(fgpu_ctx* ctx, int lmax, const std::vector<uint32_t>& ls)
 {
     // evaluatePrefactors, spherical_harmonics.hpp:216-237 (double expression, stored to float)
@@ -386,6 +504,77 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
                                                                                              n_acc, tot_m);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls)
+{
+    if (a.n == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "steinhardt_average");
+        k_steinhardt_average<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, n_ls);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_steinhardt_wl(fgpu_ctx* ctx, const SteinhardtWlArgs& a, int n_ls)
+{
+    if (a.n == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "steinhardt_wl");
+        k_steinhardt_wl<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, n_ls);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+// Wigner 3j symbols (l l l; m1 m2 m3) in the order reduceWigner3j walks its table (Wigner3j.cc:43-55).
+// Racah's formula with the alternating sum written as a sum of products of three binomial coefficients,
+//   (l l l; m1 m2 m3) = (-1)^m3 sqrt( prod (l +- m_i)! / ((3l+1)! (l!)^3) ) sum_k (-1)^k C(l,k) C(l,l-m1-k) C(l,l+m2-k),
+// which is exact in 128-bit integers for l <= 32; the prefactor is evaluated in long double.
+std::vector<float> wigner3j_table(uint32_t l_)
+{
+    int const l = (int) l_;
+    std::vector<long double> fact(3 * l + 2);
+    fact[0] = 1.0L;
+    for (int k = 1; k < 3 * l + 2; ++k)
+    {
+        fact[k] = fact[k - 1] * (long double) k;
+    }
+    std::vector<std::vector<__int128>> binom(l + 1, std::vector<__int128>(l + 1, 0));
+    for (int n = 0; n <= l; ++n)
+    {
+        binom[n][0] = 1;
+        for (int k = 1; k <= n; ++k)
+        {
+            binom[n][k] = binom[n - 1][k - 1] + (k <= n - 1 ? binom[n - 1][k] : 0);
+        }
+    }
+    auto C = [&](int n, int k) -> __int128 { return (k < 0 || k > n) ? (__int128) 0 : binom[n][k]; };
+    std::vector<float> table;
+    for (int m1 = -l; m1 <= l; ++m1)
+    {
+        for (int m2 = std::max(-l - m1, -l); m2 <= std::min(l - m1, l); ++m2)
+        {
+            int const m3 = -m1 - m2;
+            __int128 sum = 0;
+            for (int k = 0; k <= l; ++k)
+            {
+                __int128 const term = C(l, k) * C(l, l - m1 - k) * C(l, l + m2 - k);
+                sum += (k & 1) ? -term : term;
+            }
+            long double const pref = std::sqrt(fact[l + m1] * fact[l - m1] * fact[l + m2] * fact[l - m2] * fact[l + m3]
+                                               * fact[l - m3] / (fact[3 * l + 1] * fact[l] * fact[l] * fact[l]));
+            long double const sign = (m3 & 1) ? -1.0L : 1.0L;
+            double const value = (double) (sign * pref * (long double) sum);
+            table.push_back((float) value); // upstream stores doubles and uses float(w), Wigner3j.cc:52
+        }
+    }
+    return table;
 }
 
 } // namespace fgpu

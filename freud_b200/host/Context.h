@@ -13,7 +13,8 @@
 namespace freud { namespace gpu {
 
 // Maps a C-ABI status to the exception type the reference throws (and nanobind/pybind11 translate):
-// EINVALID/EDOMAIN -> ValueError, ERUNTIME/ECUDA/ENCCL -> RuntimeError, ENOMEM -> MemoryError.
+// EINVALID/EDOMAIN -> ValueError, ERUNTIME/ECUDA/ENCCL -> RuntimeError, ENOMEM -> MemoryError,
+// ERANGE -> IndexError.
 inline void check(int rc)
 {
     if (rc == FGPU_OK)
@@ -29,6 +30,8 @@ inline void check(int rc)
         throw std::domain_error(msg);
     case FGPU_ENOMEM:
         throw std::bad_alloc();
+    case FGPU_ERANGE:
+        throw std::out_of_range(msg);
     default:
         throw std::runtime_error(msg);
     }

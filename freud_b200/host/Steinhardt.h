@@ -1,12 +1,14 @@
-// freud::order::Steinhardt (plain q_l) on the GPU kernel of libfreud_b200.so.
+// freud::order::Steinhardt on the GPU kernels of libfreud_b200.so.
 //
 // Signatures: Steinhardt(ls, average, wl, weighted, wl_normalize) (freud/order/Steinhardt.h:66-90),
 // compute(nlist /*nullable*/, points, qargs) (Steinhardt.h:153-155), getQl / getQlm / getParticleOrder /
 // getOrder / getL / is* (Steinhardt.h:96-150; bound in export-Steinhardt.cc:22-33).
-// compute() = reallocateArrays + baseCompute + normalizeSystem (Steinhardt.cc:54-118, 120-222, 291-327): per
-// particle q_lm(i) = sum_j w_ij Y_lm(wrap(p_j - p_i)) / sum_j w_ij and q_l(i) = sqrt(4 pi / (2l+1) sum_m |q_lm|^2).
-// The second-shell average and the w_l invariants (computeAve, aggregatewl) are the "next" rows of SURVEY.md
-// section 8f and throw until they are built: nothing is silently computed on the CPU.
+// compute() = reallocateArrays + baseCompute [+ computeAve] [+ aggregatewl] + normalizeSystem
+// (Steinhardt.cc:54-118, 120-222, 224-289, 329-359, 291-327): per particle
+// q_lm(i) = sum_j w_ij Y_lm(wrap(p_j - p_i)) / sum_j w_ij and q_l(i) = sqrt(4 pi / (2l+1) sum_m |q_lm|^2);
+// average: q_lm averaged over i and its neighbours; wl: the Wigner-3j contraction of q_lm (or of the averaged
+// q_lm), optionally normalised.  Getters follow upstream: getQl() is the averaged q_l when average is set,
+// getParticleOrder() is w_l when wl is set, getQlm() is always the un-averaged q_lm(i).
 // Deviation, documented: the system-wide q_lm is accumulated in fp64 on the device (the reference's float32
 // thread-order sum is not reproducible run to run).
 #pragma once
@@ -33,11 +35,6 @@ public:
         {
             throw std::invalid_argument("Steinhardt requires at least one l.");
         }
-        if (average || wl || wl_normalize)
-        {
-            throw std::runtime_error("freud_b200: Steinhardt average / wl / wl_normalize are not built yet "
-                                     "(SURVEY.md section 8f); only plain and weighted q_l run on the GPU path.");
-        }
     }
     explicit Steinhardt(unsigned int l, bool average = false, bool wl = false, bool weighted = false,
                         bool wl_normalize = false)
@@ -45,7 +42,7 @@ public:
     {}
 
     unsigned int getNP() const { return m_Np; }
-    const std::shared_ptr<util::ManagedArray<float>>& getParticleOrder() const { return m_qli; }
+    const std::shared_ptr<util::ManagedArray<float>>& getParticleOrder() const { return m_wl ? m_wli : m_qli; }
     const std::shared_ptr<util::ManagedArray<float>>& getQl() const { return m_qli; }
     const std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>>& getQlm() const { return m_qlmi; }
     std::vector<float> getOrder() const { return m_norm; }
@@ -78,11 +75,18 @@ public:
             tot_m += 2 * (size_t) l + 1;
         }
         auto qli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()});
+        std::shared_ptr<util::ManagedArray<float>> wli;
+        if (m_wl)
+        {
+            wli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()});
+        }
         std::vector<float> qlm_flat((size_t) Np * tot_m * 2), sys(tot_m * 2);
         std::vector<float> order(m_ls.size());
+        int const flags = (m_weighted ? FGPU_ST_WEIGHTED : 0) | (m_average ? FGPU_ST_AVERAGE : 0)
+            | (m_wl ? FGPU_ST_WL : 0) | (m_wl_normalize ? FGPU_ST_WL_NORMALIZE : 0);
         gpu::check(fgpu_steinhardt_compute(points->device(), list->device(gpu::context()), m_ls.data(),
-                                           (uint32_t) m_ls.size(), m_weighted ? 1 : 0, Np, nullptr, qli->data(),
-                                           qlm_flat.data(), sys.data(), order.data()));
+                                           (uint32_t) m_ls.size(), flags, Np, nullptr, qli->data(),
+                                           wli ? wli->data() : nullptr, qlm_flat.data(), sys.data(), order.data()));
         size_t off = 0;
         for (size_t r = 0; r < m_ls.size(); ++r)
         {
@@ -97,6 +101,7 @@ public:
             off += (size_t) Np * nm * 2;
         }
         m_qli = qli;
+        m_wli = wli;
         m_norm = order;
     }
 
@@ -104,7 +109,8 @@ private:
     unsigned int m_Np {0};
     std::vector<unsigned int> m_ls;
     bool m_average, m_wl, m_weighted, m_wl_normalize;
-    std::shared_ptr<util::ManagedArray<float>> m_qli;
+    std::shared_ptr<util::ManagedArray<float>> m_qli; // q_l, or the averaged q_l (what getQl() returns upstream)
+    std::shared_ptr<util::ManagedArray<float>> m_wli; // w_l when wl is set
     std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>> m_qlmi;
     std::vector<float> m_norm;
 };

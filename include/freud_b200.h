@@ -36,6 +36,7 @@ extern "C" {
 #define FGPU_ECUDA (-4)    /* CUDA runtime failure / no device */
 #define FGPU_ENCCL (-5)    /* NCCL failure / library missing */
 #define FGPU_ENOMEM (-6)
+#define FGPU_ERANGE (-7)   /* std::out_of_range upstream    */
 
 /* Pair-distance arithmetic ("flavour"), SURVEY.md fact 2 */
 #define FGPU_FLAVOUR_WRAP 0  /* LinkCell:  r = Box::wrap(p_j - q)        freud/locality/LinkCell.cc:522 */
@@ -76,7 +77,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, steinhardt (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -172,20 +173,29 @@ int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
 
 /* ---- Steinhardt --------------------------------------------------------------------------------------
- * Replaces Steinhardt::compute for plain q_l (average = wl = false): baseCompute + normalizeSystem,
- * freud/order/Steinhardt.cc:85-222, 291-327, with fsph::PointSPHEvaluator
- * (extern/fsph/src/spherical_harmonics.hpp:155-290).  The neighbour list must have been built against
- * pts (n_query == n_points == n).  Outputs (host pointers, any may be NULL):
- *   ql      f32[n][n_ls]
- *   qlm     per l, concatenated: complex64[n][2l+1] (re, im interleaved), m order 0..l, -1..-l
- *   sys_qlm per l, concatenated: complex64[2l+1] = sum_i qlm_i / n   (accumulated in fp64 on the device,
- *           rounded once: a documented deviation, the reference's float32 thread-order sum is not
- *           reproducible, SURVEY.md section 7 "hard parts")
- *   order   f32[n_ls] system-wide q_l
+ * Replaces Steinhardt::compute (freud/order/Steinhardt.cc:85-118): baseCompute :120-222 with
+ * fsph::PointSPHEvaluator (extern/fsph/src/spherical_harmonics.hpp:155-290), computeAve :224-289, aggregatewl
+ * :329-359 with reduceWigner3j (freud/order/Wigner3j.cc:22-57) and normalizeSystem :291-327.  `flags` are the
+ * constructor's booleans (Steinhardt.h:66-76).  The neighbour list must have been built against pts
+ * (n_query == n_points == n).  Outputs (host pointers, any may be NULL):
+ *   ql      f32[n][n_ls]   what getQl() returns: q_l, or the second-shell averaged q_l with FGPU_ST_AVERAGE
+ *   wl      f32[n][n_ls]   w_l (FGPU_ST_WL only): from q_lm, or from the averaged q_lm with FGPU_ST_AVERAGE;
+ *                          scaled by (sqrt(4 pi / (2l+1)) / q_l)^3 with FGPU_ST_WL_NORMALIZE
+ *   qlm     per l, concatenated: complex64[n][2l+1] (re, im interleaved), m order 0..l, -1..-l; always the
+ *           un-averaged q_lm(i), as getQlm()
+ *   sys_qlm per l, concatenated: complex64[2l+1] = sum_i qlm_i / n (of the averaged q_lm with
+ *           FGPU_ST_AVERAGE), accumulated in fp64 on the device and rounded once: a documented deviation, the
+ *           reference's float32 thread-order sum is not reproducible, SURVEY.md section 7 "hard parts"
+ *   order   f32[n_ls] getOrder(): system-wide q_l, or system-wide w_l with FGPU_ST_WL
+ * Errors: FGPU_ST_WL with an l > 20 -> FGPU_ERANGE (Wigner3j.cc, "implemented for l <= 20").
  * comm != NULL: sys_qlm/order are reduced over all ranks (each rank holds a shard of the rows; n_total is
- * the global particle count used in the 1/N normalisation). */
-int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls,
-                            int weighted, uint32_t n_total, fgpu_comm* comm, float* ql_host, float* qlm_host,
+ * the global particle count used in the 1/N normalisation); FGPU_ST_AVERAGE needs every row on the rank. */
+#define FGPU_ST_WEIGHTED 1
+#define FGPU_ST_AVERAGE 2
+#define FGPU_ST_WL 4
+#define FGPU_ST_WL_NORMALIZE 8
+int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
                             float* sys_qlm_host, float* order_host);
 
 /* ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------

@@ -86,6 +86,32 @@ def main():
     out["ball_ql_6"] = r["ql"]
     np.savez_compressed(os.path.join(HERE, "steinhardt_fcc.npz"), **out)
     print("steinhardt", out["knn12_ql_6"][:3, 0])
+    steinhardt_options()
+
+
+STEINHARDT_OPTIONS = {
+    # tag: constructor flags (freud/order/Steinhardt.h:66-76)
+    "ave": dict(average=True),
+    "wl": dict(wl=True),
+    "wln": dict(wl=True, wl_normalize=True),
+    "ave_wl": dict(average=True, wl=True),
+    "ave_wln": dict(average=True, wl=True, wl_normalize=True),
+}
+
+
+def steinhardt_options():
+    """Second-shell average and w_l (Steinhardt.cc:224-289, 329-359) on the noisy FCC system, k = 12."""
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    out = {}
+    for tag, flags in STEINHARDT_OPTIONS.items():
+        for ls in ([6], [4, 6], [3, 10]):
+            r = ref.Steinhardt(ls, **flags).compute(ref.Query("raw", box, pts), num_neighbors=12, exclude_ii=True)
+            key = tag + "_" + "_".join(str(l) for l in ls)
+            out[f"{key}_particle_order"] = r["particle_order"]
+            out[f"{key}_ql"] = r["ql"]
+            out[f"{key}_order"] = r["order"]
+    np.savez_compressed(os.path.join(HERE, "steinhardt_options.npz"), **out)
+    print("steinhardt options", out["ave_wln_6_particle_order"][:3, 0], out["ave_wln_6_order"])
 
 
 if __name__ == "__main__":

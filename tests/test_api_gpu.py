@@ -1,6 +1,8 @@
 """The reference-facing API (freud_b200.locality / density / order -> C++ host classes -> C ABI -> CUDA) against the
 oracle.  Cases follow the reference's own suite: tests/test_locality_neighbor_query.py, test_density_rdf.py,
 test_order_steinhardt.py, test_managedarray.py (lines cited per test)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -189,6 +191,47 @@ def test_steinhardt_vs_reference_noisy_fcc():
         pnl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True)
         want = port.steinhardt(box, False, pts, pnl, [4, 6])
         np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
+
+
+def test_steinhardt_w6_known_answers():
+    """PERFECT_FCC_W6 = -0.00262604 with wl (and wl + average) on the perfect FCC crystal, k = 12 and a ball query
+    (tests/test_order_steinhardt.py:18, :168-214 upstream)."""
+    box, pts = data.make_fcc_system(4)
+    for neighbors in (dict(num_neighbors=12), dict(r_max=0.8)):
+        for kw in (dict(wl=True), dict(wl=True, average=True)):
+            st = order.Steinhardt(6, **kw).compute((box, pts), neighbors=neighbors)
+            np.testing.assert_allclose(np.average(st.particle_order), -0.00262604, atol=1e-5)
+            np.testing.assert_allclose(st.particle_order, st.particle_order[0], atol=1e-5)
+            assert abs(st.order - (-0.00262604)) < 1e-5
+    # the averaged q_6 of a perfect crystal is q_6 itself; `ql` follows `average` (Steinhardt.h:107-114)
+    st = order.Steinhardt(6, average=True).compute((box, pts), neighbors=dict(num_neighbors=12))
+    np.testing.assert_allclose(st.particle_order, 0.57452416, atol=1e-5)
+    np.testing.assert_allclose(st.ql, 0.57452416, atol=1e-5)
+    with pytest.raises(IndexError):  # Wigner3j.cc: "implemented for l <= 20"
+        order.Steinhardt(21, wl=True).compute((box, pts), neighbors=dict(num_neighbors=12))
+
+
+@pytest.mark.parametrize("tag", ["ave", "wl", "wln", "ave_wl", "ave_wln"])
+def test_steinhardt_options_golden(tag):
+    """Second-shell average, w_l and its normalisation against outputs of the reference itself
+    (tests/golden/steinhardt_options.npz, made by tests/golden/make_golden.py)."""
+    from tests.golden.make_golden import STEINHARDT_OPTIONS
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "steinhardt_options.npz"))
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    for ls in ([6], [4, 6], [3, 10]):
+        key = tag + "_" + "_".join(str(l) for l in ls)
+        st = order.Steinhardt(ls, **STEINHARDT_OPTIONS[tag]).compute((box, pts), neighbors=dict(num_neighbors=12))
+        po, ql, want_po = st.particle_order, st.ql, gold[f"{key}_particle_order"]
+        # w_l is a sum of O(l^2) signed terms: the tolerance is relative to the scale of the row, not the element
+        scale = np.abs(want_po).max(axis=0)
+        np.testing.assert_allclose(po, want_po, rtol=1e-5, atol=2e-5 * float(scale.max()))
+        np.testing.assert_allclose(ql, gold[f"{key}_ql"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(st.order, gold[f"{key}_order"], rtol=1e-4, atol=1e-7)
+        if ref.available():
+            want = ref.Steinhardt(ls, **STEINHARDT_OPTIONS[tag]).compute(ref.Query("raw", box, pts), num_neighbors=12,
+                                                                         exclude_ii=True)
+            np.testing.assert_allclose(po, want["particle_order"], rtol=1e-5, atol=2e-5 * float(scale.max()))
 
 
 def test_steinhardt_nan_without_neighbours():

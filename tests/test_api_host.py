@@ -95,11 +95,13 @@ def test_neighborlist_from_arrays_and_container():
     assert len(nl) == 5  # the copies did not touch the original
 
 
-def test_steinhardt_options_not_built_fail_loudly():
+def test_steinhardt_constructor():
+    """Constructor flags are kept as given (freud/order.py:489-520); nothing touches the GPU before compute()."""
     assert order.Steinhardt(6).l == 6 and order.Steinhardt([4, 6]).l == [4, 6]
-    for kw in (dict(average=True), dict(wl=True), dict(wl_normalize=True)):
-        with pytest.raises(RuntimeError):
-            order.Steinhardt(6, **kw)
+    st = order.Steinhardt(6, average=True, wl=True, weighted=True, wl_normalize=True)
+    assert st.average and st.wl and st.weighted and st.wl_normalize
+    st = order.Steinhardt(6)
+    assert not (st.average or st.wl or st.weighted or st.wl_normalize)
     with pytest.raises(ValueError):
         order.Steinhardt(-1)
     with pytest.raises(NotImplementedError):  # no default query arguments, as upstream
