@@ -523,14 +523,14 @@ def workload_rdf4m(ctx, rank, world, n, comm):
     dp = _capi.DevicePoints(ctx, box, pts)
     srdf = parallel.ShardedRDF(ctx, bins, r_max, comm=comm, rank=rank, world=world)
     rdf = srdf.rdf
-    lo, hi = parallel.shard_bounds(n, rank, world)
-    shard = np.ascontiguousarray(pts[lo:hi])
     pin_pts, keep0 = pinned_empty((n, 3), np.float32)
     pin_pts[:] = pts
-    pin_q, keep1 = pinned_empty((hi - lo, 3), np.float32)
-    pin_q[:] = shard
 
-    shard_arg = None if world == 1 else (pin_q, lo)
+    # the home tiles of the self query are dealt to the ranks; each rank builds the slab of the cell list its
+    # tiles see (fgpu_points_set_shard), so neither the search nor the build is replicated work
+    shard_arg = None if world == 1 else "tiles"
+    if world > 1:
+        dp.set_shard(rank, world)
 
     def step_dev():
         srdf.reset()
@@ -546,17 +546,18 @@ def workload_rdf4m(ctx, rank, world, n, comm):
         return srdf.bin_counts()  # one ncclAllReduce(u32[500]) + D2H
 
     step_dev()
-    n_bonds = int(rdf.read().astype(np.uint64).sum())
+    n_bonds = int(rdf.read().astype(np.uint64).sum())  # after the allreduce: the whole frame
     n_cells = int(np.prod(dp.build_cells(r_max)))
-    nq = hi - lo
+    nq = n // world
     algo = {"search_rdf": 16 * (n + nq) + 4 * n_cells + 4 * bins, "pipeline": 16 * (n + nq) + 4 * bins,
             "cell_assign": 20 * n + 4 * n_cells, "cell_scatter": 36 * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=1.0 / world, unit="frames/s",
                 metric="rdf_frames_per_sec",
                 config={"workload": f"RDF bins=500 r_max=5 N={n} triclinic (xy=.3,xz=.2,yz=.1) L={L:.4f} query points "
-                                    f"sharded over {world} GPU(s), points replicated, ncclAllReduce(u32[500])",
+                                    f"(home tiles) sharded over {world} GPU(s), points replicated, cell list built "
+                                    f"per slab, ncclAllReduce(u32[500])",
                         "bonds_per_step": n_bonds},
-                h2d=12 * n + 12 * nq, d2h=4 * bins, algo=algo, keep=[keep0, keep1], box=box, pts=pts, r_max=r_max,
+                h2d=12 * n, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max,
                 rdf=rdf, dp=dp, secondary={})
 
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
     "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
     "fgpu_points_destroy": (None, [_vp]),
+    "fgpu_points_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "fgpu_points_build_cells": (C.c_int, [_vp, C.c_float, _up]),
     "fgpu_points_read_cells": (C.c_int, [_vp, _up, _up]),
     "fgpu_ball_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
@@ -253,6 +254,10 @@ class DevicePoints(_DeviceObject):
         dims = np.zeros(3, np.uint32)
         check(lib().fgpu_points_build_cells(self._h, float(r_search), ptr(dims, _up)))
         return dims
+
+    def set_shard(self, shard, n_shards):
+        """Deal the home tiles of self-query RDF accumulation to ``n_shards`` ranks; this object is rank ``shard``."""
+        check(lib().fgpu_points_set_shard(self._h, int(shard), int(n_shards)))
 
     def read_cells(self, dims):
         n_cells = int(np.prod(dims))

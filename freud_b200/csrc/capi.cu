@@ -327,6 +327,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         *out = nl.release();
         return;
     }
+    require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
     build_grid(pts, r_max);
     QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
 
@@ -456,11 +457,38 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     {
         return;
     }
+    bool const sharded = pts->n_shards > 1;
+    require(!sharded || self, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
     build_grid(pts, q_r_max);
     QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
     Search2Args s2 = base_search2_args(pts, qv, q_index_offset, q_r_max, q_r_min, exclude_ii);
     s2.axis = rdf->axis;
     bool const fast = !ctx->force_general && search2_supported(s2, S2_RDF);
+    if (sharded)
+    {
+        // This rank bins the pairs of its share of the home tiles; the cell list holds the slab they can see.
+        // There is no general-kernel fallback here: it would need the whole list.
+        // (FGPU_SEARCH=general does not apply: the sharded path has one kernel family)
+        require(search2_supported(s2, S2_RDF), FGPU_ERUNTIME,
+                "sharded RDF accumulation needs a grid of at least 3 cells per periodic axis");
+        ShardPlan const sp = shard_plan(pts->grid.dim, pts->n, pts->shard, pts->n_shards);
+        s2.ticket_begin = sp.ticket_begin;
+        s2.ticket_end = sp.ticket_end;
+        s2.cell_begin = sp.cell_begin;
+        s2.cell_end = sp.cell_end;
+        s2.hist = rdf->hist.ptr;
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        if (s2.ticket_end > s2.ticket_begin)
+        {
+            launch_search2(ctx, flavour, S2_RDF, s2);
+            launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+        }
+        d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, sizeof(unsigned long long));
+        sync(ctx);
+        require((ctx->h_scalars[4] & 0xffffffffULL) == 0, FGPU_ERUNTIME,
+                "sharded RDF accumulation needs every point inside the box (wrap the points first)");
+        return;
+    }
     SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, q_r_max, q_r_min, exclude_ii);
     a.axis = rdf->axis;
     a.hist = rdf->hist.ptr;
@@ -844,6 +872,16 @@ int fgpu_points_build_cells(fgpu_points* pts, float r_search, uint32_t* out_dims
     });
 }
 
+int fgpu_points_set_shard(fgpu_points* pts, int shard, int n_shards)
+{
+    return guarded([&] {
+        require(pts != nullptr, FGPU_EINVALID, "null argument");
+        require(n_shards >= 1 && shard >= 0 && shard < n_shards, FGPU_EINVALID, "shard index out of range");
+        pts->shard = shard;
+        pts->n_shards = n_shards; // the next build_grid sees the change and rebuilds
+    });
+}
+
 int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host)
 {
     return guarded([&] {
@@ -907,6 +945,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                 "You must set num_neighbors in the query arguments when performing number of neighbor queries.");
         bool const self = query_points_host == nullptr;
         require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
         auto nl = new_nlist(ctx, n_query, pts->n);
         uint32_t const k = std::min<uint32_t>(num_neighbors, pts->n);
         if (n_query == 0 || k == 0)
@@ -936,6 +975,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
         QueryView qv;
         uint64_t total = 0;
         bool evals_counted = false; // by the count kernel of the warp-cooperative path
+        float r_grid_done = 0.0f;   // grid radius the last warp-cooperative search ran at
         for (int attempt = 0;; ++attempt)
         {
             require(attempt < 64, FGPU_ERUNTIME, "kNN search did not converge");
@@ -952,63 +992,111 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             s2.knn_r_min = r_min > 0.0f ? r_min : 0.0f;
             if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL) && pts->n < 0x7fffffffU)
             {
-                bool const final_window = !(r_win < r_max);
-                double const shell = pts->box.is2d ? M_PI * (double) r_win * r_win
-                                                   : 4.0 / 3.0 * M_PI * (double) r_win * r_win * r_win;
-                uint64_t cap = (uint64_t) (1.25 * (double) n_query * density * shell) + 4096;
                 ctx->tmp_start.reserve((size_t) n_query + 1);
                 ctx->knn_hits.reserve((size_t) n_query + 1);
+                ctx->knn_unresolved.reserve(2 * (size_t) n_query + 2);
                 if (attempt == 0)
                 {
                     launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
                 }
-                bool done = false, general = false;
-                for (int pass = 0; pass < 3 && !done && !general; ++pass)
+                enum WindowResult
                 {
-                    cap = std::min<uint64_t>(cap, 0xffffffffULL);
-                    ctx->bag4.reserve(cap);
-                    s2.bag = ctx->bag4.ptr;
-                    s2.temp_cap = (uint32_t) cap;
-                    s2.counts = ctx->knn_hits.ptr;
-                    s2.tmp_start = ctx->tmp_start.ptr;
-                    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
-                    launch_search2(ctx, FGPU_FLAVOUR_IMAGE, S2_NL, s2);
-                    // optimistically enqueue the row bookkeeping behind the search: one host round trip per attempt
-                    KnnRowsArgs ra;
-                    ra.hits = ctx->knn_hits.ptr;
-                    ra.n_query = n_query;
-                    ra.k = k;
-                    ra.final = final_window ? 1 : 0;
-                    ra.counts = nl->counts.ptr;
-                    ra.row_start = nl->row_start.ptr;
-                    ra.unresolved = ctx->d_scalars + 2;
-                    ra.total = ctx->d_scalars + 3;
-                    launch_knn_rows(ctx, ra);
-                    FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
-                    exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
-                    d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(unsigned long long));
-                    sync(ctx);
-                    int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
-                    if (fail != 0)
+                    WINDOW_DONE,
+                    WINDOW_GENERAL
+                };
+                // One search of `rows` query points at the window of `args` into `bag`, then the row bookkeeping
+                // over all n_query rows, enqueued behind it: one host round trip per search.
+                auto run_window = [&](Search2Args& args, DevBuf<float4>& bag, uint64_t rows, float window,
+                                      uint32_t* unresolved_rows) {
+                    bool const final_window = !(window < r_max);
+                    double const shell = pts->box.is2d ? M_PI * (double) window * window
+                                                       : 4.0 / 3.0 * M_PI * (double) window * window * window;
+                    uint64_t cap = (uint64_t) (1.25 * (double) rows * density * shell) + 4096;
+                    for (int pass = 0; pass < 3; ++pass)
                     {
-                        general = true; // 1: points outside the box, 2: a row may be longer than the warp buffer
-                        evals_counted = evals_counted || (s2.evals != nullptr && attempt == 0 && fail != 1);
-                    }
-                    else if (ctx->h_scalars[5] <= cap)
-                    {
-                        done = true;
-                        evals_counted = evals_counted || s2.evals != nullptr;
-                    }
-                    else
-                    {
+                        cap = std::min<uint64_t>(cap, 0x7fffffffULL); // the top bit of a bag offset names the bag
+                        bag.reserve(cap);
+                        args.bag = bag.ptr;
+                        args.temp_cap = (uint32_t) cap;
+                        args.counts = ctx->knn_hits.ptr;
+                        args.tmp_start = ctx->tmp_start.ptr;
+                        FGPU_CUDA_CHECK(
+                            cudaMemsetAsync(ctx->d_scalars + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
+                        launch_search2(ctx, FGPU_FLAVOUR_IMAGE, S2_NL, args);
+                        KnnRowsArgs ra;
+                        ra.hits = ctx->knn_hits.ptr;
+                        ra.n_query = n_query;
+                        ra.k = k;
+                        ra.final = final_window ? 1 : 0;
+                        ra.counts = nl->counts.ptr;
+                        ra.row_start = nl->row_start.ptr;
+                        ra.unresolved = ctx->d_scalars + 2;
+                        ra.total = ctx->d_scalars + 3;
+                        ra.unresolved_rows = unresolved_rows;
+                        launch_knn_rows(ctx, ra);
+                        FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
+                        exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+                        d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(unsigned long long));
+                        sync(ctx);
+                        if ((ctx->h_scalars[4] & 0xffffffffULL) != 0)
+                        {
+                            return WINDOW_GENERAL; // 1: points outside the box, 2: a row may be longer than the warp buffer
+                        }
+                        if (ctx->h_scalars[5] <= cap)
+                        {
+                            return WINDOW_DONE;
+                        }
                         cap = ctx->h_scalars[5]; // exact size, the search is deterministic
                     }
-                }
-                if (done)
+                    return WINDOW_GENERAL;
+                };
+                WindowResult res = run_window(s2, ctx->bag4, n_query, r_win, ctx->knn_unresolved.ptr);
+                int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+                evals_counted = evals_counted
+                    || (s2.evals != nullptr && attempt == 0 && (res == WINDOW_DONE || fail != 1));
+                uint64_t n_short = res == WINDOW_DONE ? ctx->h_scalars[2] : 0;
+                bool second_bag = false;
+                if (res == WINDOW_DONE && n_short != 0 && n_short <= (uint64_t) n_query / 16 + 1)
                 {
-                    if (ctx->h_scalars[2] != 0)
+                    // A few rows hold fewer than k points: search those again -- only those -- with a window 1.5x
+                    // wider on a coarser grid, into a second bag.  The first bag stays valid: its records carry
+                    // the bond vectors, not references into the old grid.
+                    float const r_grid2 = (float) std::min((double) r_grid * 1.5, (double) r_max * 1.0001);
+                    build_grid(pts, r_grid2);
+                    const fgpu_grid& g2 = pts->grid;
+                    bool const cover_all2 = g2.dim[0] < 3 && g2.dim[1] < 3 && (pts->box.is2d || g2.dim[2] < 3);
+                    ctx->knn_subset.reserve(3 * (size_t) n_short);
+                    launch_gather_points(ctx, qv.xyz, ctx->knn_unresolved.ptr, (uint32_t) n_short,
+                                         ctx->knn_subset.ptr);
+                    sort_queries(pts, ctx->knn_subset.ptr, (uint32_t) n_short);
+                    QueryView sub;
+                    sub.sorted = ctx->q_sorted.ptr;
+                    sub.xyz = ctx->knn_subset.ptr;
+                    sub.cell_start = ctx->q_cell_start.ptr;
+                    sub.outside_flag = ctx->q_outside_flag.ptr;
+                    float const r_win2 = r_grid2 < r_max ? r_grid2 : r_max;
+                    Search2Args s2b = base_search2_args(pts, sub, q_index_offset, r_win2, 0.0f, exclude_ii);
+                    s2b.knn_r_min = s2.knn_r_min;
+                    s2b.q_remap = ctx->knn_unresolved.ptr;
+                    s2b.tmp_flag = kSecondBag;
+                    if (!cover_all2 && search2_supported(s2b, S2_NL)
+                        && run_window(s2b, ctx->bag4b, n_short, r_win2, ctx->knn_unresolved.ptr + n_query)
+                            == WINDOW_DONE)
                     {
-                        r_search = (double) r_grid * 1.5; // some row holds fewer than k points: widen the window
+                        second_bag = true;
+                        n_short = ctx->h_scalars[2];
+                    }
+                    r_grid_done = r_grid2;
+                }
+                else
+                {
+                    r_grid_done = r_grid;
+                }
+                if (res == WINDOW_DONE)
+                {
+                    if (n_short != 0)
+                    {
+                        r_search = (double) r_grid_done * 1.5; // many short rows: widen the window of the whole frame
                         continue;
                     }
                     uint64_t const n_bonds = ctx->h_scalars[3];
@@ -1017,6 +1105,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                     {
                         KnnSelectArgs sa;
                         sa.bag = ctx->bag4.ptr;
+                        sa.bag2 = second_bag ? ctx->bag4b.ptr : nullptr;
                         sa.tmp_start = ctx->tmp_start.ptr;
                         sa.hits = ctx->knn_hits.ptr;
                         sa.row_start = nl->row_start.ptr;

@@ -11,6 +11,7 @@
 // Algorithmic bytes: 12 (read xyz) + 16 (write float4) = 28 B/point, + 4 B/cell counters.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "internal.h"
 
@@ -175,10 +176,19 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restr
 }
 
 // K1: cell index + arrival rank (one atomic per point) -- 12 B read, 8 B written per point
+// A slab restricts the list to the cell layers [lo, lo + len) (cyclic) of one axis: a rank that only searches
+// its share of the home tiles needs nothing else (the build must not stay serial).
+struct SlabDev
+{
+    int axis; // 1: y layers (2-D grids), 2: z layers
+    int lo;
+    int len;  // < 0: no restriction
+};
+
 __global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
                                                      uint32_t n, uint32_t* __restrict__ cell_of,
                                                      uint32_t* __restrict__ rank_in, uint32_t* __restrict__ cell_count,
-                                                     int* __restrict__ any_shift)
+                                                     int* __restrict__ any_shift, SlabDev slab)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -188,13 +198,24 @@ __global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy,
     float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
     int cx, cy, cz, nx, ny, nz;
     cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
-    uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
-    cell_of[i] = c;
-    rank_in[i] = atomicAdd(&cell_count[c], 1U);
     if ((nx | ny | nz) != 0)
     {
         *any_shift = 1;
     }
+    if (slab.len >= 0)
+    {
+        int const d = slab.axis == 2 ? dz : dy, c = slab.axis == 2 ? cz : cy;
+        int rel = c - slab.lo;
+        rel += rel < 0 ? d : 0;
+        if (rel >= slab.len)
+        {
+            cell_of[i] = 0xffffffffU; // not in this rank's slab: left out of the list
+            return;
+        }
+    }
+    uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
+    cell_of[i] = c;
+    rank_in[i] = atomicAdd(&cell_count[c], 1U);
 }
 
 // K3: scatter to cell order -- 20 B read, 16 (+4) B written per point
@@ -210,8 +231,13 @@ __global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy
     {
         return;
     }
+    uint32_t const cell = cell_of[i];
+    if (cell == 0xffffffffU)
+    {
+        return; // outside the slab of this rank
+    }
     float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
-    uint32_t const slot = cell_start[cell_of[i]] + rank_in[i];
+    uint32_t const slot = cell_start[cell] + rank_in[i];
     sorted[slot] = make_float4(x, y, z, __uint_as_float(i));
     if (shift != nullptr && *any_shift != 0)
     {
@@ -302,16 +328,63 @@ GridDev grid_dev(const fgpu_points* pts)
     return d;
 }
 
+ShardPlan shard_plan(const int dim[3], uint32_t n_points, int shard, int n_shards)
+{
+    // the home tiles of search2_plan, dealt to the shards in contiguous runs of tickets (rows of the grid, z
+    // slowest): shard s owns [s T / S, (s + 1) T / S)
+    Search2Args a;
+    std::memset(&a, 0, sizeof(a));
+    a.dx = dim[0];
+    a.dy = dim[1];
+    a.dz = dim[2];
+    a.n_cells = (uint32_t) dim[0] * dim[1] * dim[2];
+    search2_plan(a, n_points);
+    ShardPlan p;
+    p.ticket_begin = (uint32_t) ((uint64_t) a.n_tickets * (uint64_t) shard / (uint64_t) n_shards);
+    p.ticket_end = (uint32_t) ((uint64_t) a.n_tickets * (uint64_t) (shard + 1) / (uint64_t) n_shards);
+    p.slab_axis = dim[2] > 1 ? 2 : 1;
+    int const layers = p.slab_axis == 2 ? dim[2] : dim[1];
+    p.slab_lo = 0;
+    p.slab_len = -1;
+    if (n_shards > 1 && p.ticket_end > p.ticket_begin)
+    {
+        uint32_t const row0 = p.ticket_begin / a.spans_per_row, row1 = (p.ticket_end - 1) / a.spans_per_row;
+        int const l0 = p.slab_axis == 2 ? (int) (row0 / (uint32_t) dim[1]) : (int) row0;
+        int const l1 = p.slab_axis == 2 ? (int) (row1 / (uint32_t) dim[1]) : (int) row1;
+        int const len = l1 - l0 + 3; // one halo layer on each side
+        if (len < layers)
+        {
+            p.slab_lo = (l0 - 1 + layers) % layers;
+            p.slab_len = len;
+        }
+    }
+    uint32_t const cells_per_row = (uint32_t) dim[0];
+    p.cell_begin = (p.ticket_begin / a.spans_per_row) * cells_per_row
+        + std::min((p.ticket_begin % a.spans_per_row) * (uint32_t) a.span, cells_per_row);
+    p.cell_end = p.ticket_end == a.n_tickets
+        ? a.n_cells
+        : (p.ticket_end / a.spans_per_row) * cells_per_row
+            + std::min((p.ticket_end % a.spans_per_row) * (uint32_t) a.span, cells_per_row);
+    return p;
+}
+
 void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
 {
     fgpu_ctx* ctx = pts->ctx;
     fgpu_grid& g = pts->grid;
     int dim[3], amb[3];
     choose_dims(pts, r_search, force_single_cell, dim, amb);
-    if (g.r_search >= 0 && dim[0] == g.dim[0] && dim[1] == g.dim[1] && dim[2] == g.dim[2])
+    if (g.r_search >= 0 && dim[0] == g.dim[0] && dim[1] == g.dim[1] && dim[2] == g.dim[2]
+        && g.shard == pts->shard && g.n_shards == pts->n_shards)
     {
         g.r_search = std::max(g.r_search, r_search); // same grid already resident
         return;
+    }
+    SlabDev slab {2, 0, -1};
+    if (pts->n_shards > 1)
+    {
+        ShardPlan const sp = shard_plan(dim, pts->n, pts->shard, pts->n_shards);
+        slab = SlabDev {sp.slab_axis, sp.slab_lo, sp.slab_len};
     }
     uint32_t const n = pts->n;
     uint32_t const n_cells = (uint32_t) dim[0] * dim[1] * dim[2];
@@ -330,7 +403,7 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
     {
         KernelScope ks(ctx, "cell_assign");
         k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
-                                                       g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag);
+                                                       g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag, slab);
     }
     exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1);
     {
@@ -347,6 +420,8 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
     }
     g.n_cells = n_cells;
     g.r_search = r_search;
+    g.shard = pts->shard;
+    g.n_shards = pts->n_shards;
 }
 
 void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
@@ -367,7 +442,7 @@ void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
         KernelScope ks(ctx, "cell_assign");
         k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
                                                        ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
-                                                       d_flag);
+                                                       d_flag, SlabDev {2, 0, -1});
     }
     exclusive_scan_u32(ctx, ctx->q_cell_start.ptr, (size_t) g.n_cells + 1);
     {

@@ -95,6 +95,9 @@ struct fgpu_ctx
     fgpu::DevBuf<float4> bag4;            // search2 bag: {bond vector, bits(point index)} per hit
     fgpu::DevBuf<uint32_t> tmp_start;     // per query: offset of its row in the bag
     fgpu::DevBuf<uint32_t> knn_hits;      // kNN: per query, hits inside the search window
+    fgpu::DevBuf<uint32_t> knn_unresolved; // kNN: rows with fewer than k hits (searched again, wider)
+    fgpu::DevBuf<float> knn_subset;       // kNN: positions of those rows' query points
+    fgpu::DevBuf<float4> bag4b;           // kNN: bag of the second, wider search
     fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
     uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
     int force_general = 0;                // FGPU_SEARCH=general: always run the search.cu kernels (testing)
@@ -154,6 +157,7 @@ struct fgpu_grid
     fgpu::DevBuf<uint32_t> cell_start; // n_cells + 1
     fgpu::DevBuf<float4> sorted;       // cell-ordered positions, w = bit pattern of the point index
     fgpu::DevBuf<int> shift;           // cell-ordered packed integer image offsets (10 bits per axis, biased)
+    int shard = 0, n_shards = 1;       // the slab this list was built for (fgpu_points_set_shard)
 };
 
 struct fgpu_points
@@ -164,6 +168,7 @@ struct fgpu_points
     uint32_t n = 0;
     fgpu::DevBuf<float> xyz; // original order, n x 3
     fgpu_grid grid;
+    int shard = 0, n_shards = 1; // > 1: this rank searches one share of the home tiles (self-query RDF only)
 };
 
 struct fgpu_nlist
@@ -282,6 +287,9 @@ struct Search2Args
     int span;                       // cells per home tile along x (search2_plan)
     uint32_t spans_per_row;
     uint32_t n_tickets;             // work items: one home tile each
+    uint32_t ticket_begin;          // this launch handles tickets [ticket_begin, ticket_end) (ticket_end == 0: all)
+    uint32_t ticket_end;
+    uint32_t cell_begin, cell_end;  // the cells those tickets cover (count_evals)
     const uint32_t* cell_start;     // candidates: cell list of the reference points
     const float4* sorted;
     const uint32_t* q_cell_start;   // queries, cell-sorted on the same grid
@@ -289,6 +297,8 @@ struct Search2Args
     const int* flag_points_outside;  // device flags: some point / query lies outside the box
     const int* flag_queries_outside;
     uint32_t q_index_offset;
+    const uint32_t* q_remap;        // not null: the queries are a subset, q_remap[i] is the row of subset query i
+    uint32_t tmp_flag;              // or-ed into tmp_start (kSecondBag when the bag is the second one)
     float r_max, r_min;
     int exclude_ii;
     float rcp_lx, rcp_ly, rcp_lz;   // RN(1 / L), rounded on the host
@@ -310,6 +320,16 @@ struct Search2Args
     unsigned long long* evals;      // may be nullptr
 };
 void search2_plan(Search2Args& a, uint32_t n_points); // sets span, spans_per_row, n_tickets
+
+// Share of one rank when the home tiles of a self query are dealt to n_shards ranks: a contiguous run of tickets,
+// the cells they cover, and the slab of cell layers (with one halo layer on each side) their candidates live in.
+struct ShardPlan
+{
+    uint32_t ticket_begin, ticket_end;
+    uint32_t cell_begin, cell_end;
+    int slab_axis, slab_lo, slab_len; // slab_len < 0: every layer
+};
+ShardPlan shard_plan(const int dim[3], uint32_t n_points, int shard, int n_shards);
 bool search2_supported(const Search2Args& a, int mode);
 void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a);
 uint32_t search2_out_cap(double expected_candidates_per_query);
@@ -382,12 +402,16 @@ struct KnnRowsArgs
     uint32_t* row_start;         // same values, scanned in place by the caller
     unsigned long long* unresolved;
     unsigned long long* total;
+    uint32_t* unresolved_rows;   // n_query slots: the rows counted in *unresolved, in any order
 };
 void launch_knn_rows(fgpu_ctx* ctx, const KnnRowsArgs& a);
+void launch_gather_points(fgpu_ctx* ctx, const float* xyz, const uint32_t* rows, uint32_t n_rows, float* out);
+constexpr uint32_t kSecondBag = 0x80000000U; // flag in tmp_start: the row lives in the second bag
 
 struct KnnSelectArgs
 {
     const float4* bag;
+    const float4* bag2;          // rows whose tmp_start carries kSecondBag
     const uint32_t* tmp_start;   // per query: offset of its row in the bag
     const uint32_t* hits;        // per query: bag row length
     const uint32_t* row_start;   // n_query + 1, output offsets

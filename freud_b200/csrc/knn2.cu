@@ -9,7 +9,9 @@
 // followed by a selection inside every bag row:
 //
 //   k_knn_rows    counts[q] = min(hits[q], k); a row with fewer than k hits is unresolved unless the window
-//                 already is r_max (the host then widens the window for the whole frame and repeats).
+//                 already is r_max.  The host searches the unresolved rows again -- only those, into a second
+//                 bag -- with a window 1.5x wider; if many rows are short (or some still are after that) it
+//                 widens the window for the whole frame and repeats.
 //   k_knn_select  one warp per row, lanes over the row's hits: rank every hit by (r_sq, point index) -- the
 //                 order in which the reference's std::sort of NeighborBonds resolves the k-th place up to its
 //                 unspecified ties -- keep ranks < k, rank the kept hits by point index (or by (d, point
@@ -30,6 +32,7 @@ constexpr uint32_t kStage = 128; // staged keys per warp
 __global__ void __launch_bounds__(256) k_knn_rows(KnnRowsArgs a)
 {
     uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    int const lane = threadIdx.x & 31;
     uint32_t kept = 0;
     bool unresolved = false;
     if (q < a.n_query)
@@ -47,16 +50,36 @@ __global__ void __launch_bounds__(256) k_knn_rows(KnnRowsArgs a)
     {
         sum += __shfl_down_sync(FULL, sum, o);
     }
-    if ((threadIdx.x & 31) == 0)
+    unsigned long long base = 0;
+    if (lane == 0)
     {
         if (mu != 0)
         {
-            atomicAdd(a.unresolved, (unsigned long long) __popc(mu));
+            base = atomicAdd(a.unresolved, (unsigned long long) __popc(mu));
         }
         if (sum != 0)
         {
             atomicAdd(a.total, sum);
         }
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (unresolved)
+    {
+        a.unresolved_rows[base + __popc(mu & ((1U << lane) - 1U))] = q; // order is irrelevant
+    }
+}
+
+// positions of a subset of the query points (the rows a wider window has to search again)
+__global__ void __launch_bounds__(256) k_gather_points(const float* __restrict__ xyz, const uint32_t* __restrict__ rows,
+                                                       uint32_t n_rows, float* __restrict__ out)
+{
+    uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_rows)
+    {
+        size_t const r = rows[s];
+        out[3 * (size_t) s] = xyz[3 * r];
+        out[3 * (size_t) s + 1] = xyz[3 * r + 1];
+        out[3 * (size_t) s + 2] = xyz[3 * r + 2];
     }
 }
 
@@ -141,7 +164,10 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_k
             continue;
         }
         uint32_t const kept = min(n, a.k);
-        const float4* __restrict__ const bag = a.bag + a.tmp_start[row];
+        uint32_t const ts = a.tmp_start[row];
+        // rows searched again with a wider window live in the second bag (flagged in the top bit)
+        const float4* __restrict__ const bag
+            = (ts & kSecondBag) != 0 ? a.bag2 + (ts & ~kSecondBag) : a.bag + ts;
         uint64_t const out0 = a.row_start[row];
         if (n > kStage)
         {
@@ -351,6 +377,19 @@ void launch_knn_rows(fgpu_ctx* ctx, const KnnRowsArgs& a)
     {
         KernelScope ks(ctx, "knn_rows");
         k_knn_rows<<<(a.n_query + 255) / 256, 256, 0, ctx->stream>>>(a);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gather_points(fgpu_ctx* ctx, const float* xyz, const uint32_t* rows, uint32_t n_rows, float* out)
+{
+    if (n_rows == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "knn_gather");
+        k_gather_points<<<(n_rows + 255) / 256, 256, 0, ctx->stream>>>(xyz, rows, n_rows, out);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }

@@ -315,7 +315,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         {
             uint32_t const qi = w.qid[lane];
             a.counts[qi] = cnt;
-            a.tmp_start[qi] = (uint32_t) base + (incl - cnt);
+            a.tmp_start[qi] = ((uint32_t) base + (incl - cnt)) | a.tmp_flag;
             w.row_pos[lane] = incl - cnt;
             w.row_cnt[lane] = 0; // ready for the next batch
         }
@@ -399,8 +399,8 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         {
             ticket = atomicAdd(a.work_counter, 1U);
         }
-        ticket = __shfl_sync(FULL, ticket, 0);
-        if (ticket >= a.n_tickets)
+        ticket = __shfl_sync(FULL, ticket, 0) + a.ticket_begin;
+        if (ticket >= a.ticket_end)
         {
             break;
         }
@@ -443,7 +443,11 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
             if ((uint32_t) lane < nqc)
             {
                 float4 q = __ldg(a.q_sorted + qb0 + lane);
-                uint32_t const qi = __float_as_uint(q.w);
+                uint32_t qi = __float_as_uint(q.w);
+                if (MODE == S2_NL && a.q_remap != nullptr)
+                {
+                    qi = __ldg(a.q_remap + qi); // a subset of the rows is searched again (kNN, knn2.cu)
+                }
                 if (MODE == S2_NL)
                 {
                     reinterpret_cast<WarpMemNL&>(wm).qid[lane] = qi;
@@ -533,9 +537,11 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
     {
         return;
     }
-    uint32_t const t = blockIdx.x * blockDim.x + threadIdx.x;
+    // the cell-ordered queries of the cells this launch covers (all of them unless the tickets are sharded)
+    uint32_t const slot0 = a.q_cell_start[a.cell_begin], slot1 = a.q_cell_start[a.cell_end];
+    uint32_t const t = blockIdx.x * blockDim.x + threadIdx.x + slot0;
     unsigned long long evals = 0;
-    if (t < n_query)
+    if (t < slot1 && t - slot0 < n_query)
     {
         float4 const q = a.q_sorted[t];
         int cx, cy, cz, nx, ny, nz;
@@ -559,14 +565,17 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
             if (j < n_points)
             {
                 uint32_t const c = cell_of_point[j];
-                int const jx = c % a.dx, jy = (c / a.dx) % a.dy, jz = c / (a.dx * a.dy);
-                auto adjacent = [](int u, int v, int d) {
-                    int const diff = (u - v + d) % d;
-                    return diff == 0 || diff == 1 || diff == d - 1;
-                };
-                if (adjacent(jx, cx, a.dx) && adjacent(jy, cy, a.dy) && adjacent(jz, cz, a.dz))
+                if (c != 0xffffffffU) // else the point is outside this rank's slab: in none of the visited cells
                 {
-                    evals -= 1;
+                    int const jx = c % a.dx, jy = (c / a.dx) % a.dy, jz = c / (a.dx * a.dy);
+                    auto adjacent = [](int u, int v, int d) {
+                        int const diff = (u - v + d) % d;
+                        return diff == 0 || diff == 1 || diff == d - 1;
+                    };
+                    if (adjacent(jx, cx, a.dx) && adjacent(jy, cy, a.dy) && adjacent(jz, cz, a.dz))
+                    {
+                        evals -= 1;
+                    }
                 }
             }
         }
@@ -673,7 +682,8 @@ template<int FLAVOUR, int MODE, bool TRI> void launch_one(fgpu_ctx* ctx, const S
         throw Error(FGPU_ERUNTIME, "search kernel does not fit the shared memory of this device");
     }
     unsigned const blocks
-        = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, ((uint64_t) a.n_tickets + kWarps - 1) / kWarps);
+        = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm,
+                                        ((uint64_t) (a.ticket_end - a.ticket_begin) + kWarps - 1) / kWarps);
     KernelScope ks(ctx, name);
     kern<<<std::max(blocks, 1U), kThreads, smem, ctx->stream>>>(a);
 }
@@ -704,6 +714,10 @@ void search2_plan(Search2Args& a, uint32_t n_points)
     a.span = span;
     a.spans_per_row = (uint32_t) ((a.dx + span - 1) / span);
     a.n_tickets = a.spans_per_row * (uint32_t) a.dy * (uint32_t) a.dz;
+    a.ticket_begin = 0;
+    a.ticket_end = a.n_tickets;
+    a.cell_begin = 0;
+    a.cell_end = a.n_cells;
 }
 
 bool search2_supported(const Search2Args& a, int mode)

@@ -98,9 +98,16 @@ class ShardedRDF:
         self._reduced = True
 
     def accumulate_frame(self, points, flavour, r_max, r_min=0.0, exclude_ii=True, query_shard=None):
-        """points: DevicePoints (replicated).  query_shard: (host array of this rank's query points, first index) or
-        None for "all points of the frame" (frame sharding)."""
+        """points: DevicePoints (replicated).  query_shard:
+
+        * ``None``: all points of the frame are queries (frame sharding, or a single GPU);
+        * ``"tiles"``: self query whose home tiles are dealt to the ranks (``fgpu_points_set_shard``): this rank
+          searches its share and builds only the slab of the cell list that share can see -- config 4's path;
+        * ``(host array, first index)``: an explicit block of query points with ``q_index_offset``."""
         if query_shard is None:
+            self.rdf.accumulate(points, None, flavour, r_max, r_min, exclude_ii)
+        elif isinstance(query_shard, str) and query_shard == "tiles":
+            points.set_shard(self.rank, self.world)
             self.rdf.accumulate(points, None, flavour, r_max, r_min, exclude_ii)
         else:
             q, lo = query_shard

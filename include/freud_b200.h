@@ -99,6 +99,15 @@ void fgpu_points_destroy(fgpu_points* pts);
 /* Force the cell-list build for search radius r (what the first query would do); exposed so the build can
  * be timed and tested on its own.  out_dims[3] receives the cell grid, may be NULL. */
 int fgpu_points_build_cells(fgpu_points* pts, float r_search, uint32_t* out_dims);
+/* Multi-GPU self-query RDF (BASELINE.json configs[3]): the points are replicated on every
+ * rank, the HOME TILES of the search -- hence the query points -- are dealt to the ranks in contiguous runs, and
+ * rank `shard` of `n_shards` builds only the slab of the cell list its tiles can see (their cell layers plus one
+ * halo layer on each side), so neither the search nor the build stays serial.  fgpu_rdf_accumulate with
+ * query_points == NULL then bins the pairs of this rank's tiles; fgpu_rdf_allreduce sums the ranks.  Counts are
+ * integers, so the total is bit-identical to the single-GPU histogram.  Sharded points serve that call only
+ * (everything else returns FGPU_ERUNTIME), need a grid of >= 3 cells per periodic axis and every point inside
+ * the box; n_shards == 1 restores the normal behaviour. */
+int fgpu_points_set_shard(fgpu_points* pts, int shard, int n_shards);
 /* Copies out the cell list for tests: cell_start[n_cells + 1] and the point index of every cell-ordered
  * slot (order[n]).  Either pointer may be NULL. */
 int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host);

@@ -282,6 +282,50 @@ def test_knn(ctx, name):
         assert_nlist_equal(got, want, f"{name} knn k={k}")
 
 
+@pytest.mark.parametrize("k", [4, 12])
+def test_knn_short_rows_are_searched_again(ctx, k):
+    """Uniform random points: the first window (2(k+1) expected points) leaves a few rows with fewer than k hits;
+    those rows -- only those -- are searched again with a wider window into a second bag (knn2.cu).  Self query and
+    a separate query set, both orders."""
+    box = __import__("freud_b200.box", fromlist=["Box"]).Box(26, 24, 22, 0.2, -0.1, 0.15)
+    pts = random_points(box, 5000, seed=77)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    for q, excl in ((None, True), (random_points(box, 1500, seed=78), False)):
+        for sbd in (False, True):
+            got = dp.knn_query(q, k, exclude_ii=excl, sort_by_distance=sbd).to_host()
+            qq = pts if q is None else q
+            want = port.knn_nlist(box, False, pts, qq, k, exclude_ii=excl, sort_by_distance=sbd)
+            assert_nlist_equal(got, want, f"knn k={k} self={q is None} sbd={sbd}")
+            assert (got["counts"] == k).all()
+
+
+@pytest.mark.parametrize("name", ["cubic", "tri2", "sq2d", "tilt2d"])
+@pytest.mark.parametrize("flavour", [WRAP, IMAGE])
+def test_rdf_home_tiles_sharded(ctx, name, flavour):
+    """fgpu_points_set_shard: the home tiles of a self-query RDF dealt to S ranks, each with a cell list built for
+    its slab only.  One process plays the ranks in turn; the summed counts are the single-GPU counts bit for bit."""
+    capi = _capi()
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=91)
+    want = port.rdf_accumulate(flavour, box, box.is2D, pts, pts, 64, r, 0.0, True)
+    for shards in (2, 3, 5):
+        rdf = capi.DeviceRDF(ctx, 64, r)
+        for s in range(shards):
+            dp = capi.DevicePoints(ctx, box, pts)
+            dp.set_shard(s, shards)
+            rdf.accumulate(dp, None, flavour, r, 0.0, True)
+        assert np.array_equal(rdf.read(), want), f"{name} flavour={flavour} shards={shards}"
+    # sharded points serve that call only
+    dp = capi.DevicePoints(ctx, box, pts)
+    dp.set_shard(1, 2)
+    with pytest.raises(RuntimeError):
+        dp.ball_query(None, flavour, r, 0.0, True)
+    with pytest.raises(RuntimeError):
+        capi.DeviceRDF(ctx, 64, r).accumulate(dp, pts[:10], flavour, r, 0.0, False)
+    dp.set_shard(0, 1)
+    assert dp.ball_query(None, flavour, r, 0.0, True).num_bonds == int(want.sum())
+
+
 def test_knn_r_max_r_min(ctx):
     box, n, r = BOXES["cubic"]
     pts = random_points(box, n, seed=32)
