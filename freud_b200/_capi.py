@@ -48,8 +48,8 @@ SIGNATURES = {
                                   _vpp]),
     "fgpu_ball_query_dev": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int,
                                       C.c_int, _vpp]),
-    "fgpu_knn_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_int,
-                                 _vpp]),
+    "fgpu_knn_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_int,
+                                 C.c_int, _vpp]),
     "fgpu_nlist_num_bonds": (C.c_uint64, [_vp]),
     "fgpu_nlist_num_query_points": (C.c_uint32, [_vp]),
     "fgpu_nlist_num_points": (C.c_uint32, [_vp]),
@@ -276,12 +276,13 @@ class DevicePoints(_DeviceObject):
         return DeviceNeighborList(self.ctx, h)
 
     def knn_query(self, query_points, num_neighbors, r_max=np.inf, r_min=0.0, exclude_ii=False,
-                  sort_by_distance=False, q_index_offset=0):
+                  sort_by_distance=False, q_index_offset=0, flavour=FLAVOUR_IMAGE):
         q = None if query_points is None else f32(query_points, 3)
         nq = self.n if q is None else len(q)
         h = _vp()
-        check(lib().fgpu_knn_query(self._h, ptr(q), nq, int(q_index_offset), int(num_neighbors), float(r_max),
-                                   float(r_min), int(bool(exclude_ii)), int(bool(sort_by_distance)), C.byref(h)))
+        check(lib().fgpu_knn_query(self._h, ptr(q), nq, int(q_index_offset), int(flavour), int(num_neighbors),
+                                   float(r_max), float(r_min), int(bool(exclude_ii)), int(bool(sort_by_distance)),
+                                   C.byref(h)))
         return DeviceNeighborList(self.ctx, h)
 
     def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0, out=None, average=False,

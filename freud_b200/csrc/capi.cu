@@ -477,16 +477,15 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
         s2.cell_begin = sp.cell_begin;
         s2.cell_end = sp.cell_end;
         s2.hist = rdf->hist.ptr;
-        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        // a point outside the box makes the kernel give up; the flag is sticky in the word behind the counters
+        // and fgpu_rdf_read reports it, so the frame needs no host round trip
+        s2.fail = reinterpret_cast<int*>(rdf->hist.ptr + rdf->axis.bins);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 5, 0, 2 * sizeof(unsigned long long), ctx->stream));
         if (s2.ticket_end > s2.ticket_begin)
         {
             launch_search2(ctx, flavour, S2_RDF, s2);
             launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
         }
-        d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, sizeof(unsigned long long));
-        sync(ctx);
-        require((ctx->h_scalars[4] & 0xffffffffULL) == 0, FGPU_ERUNTIME,
-                "sharded RDF accumulation needs every point inside the box (wrap the points first)");
         return;
     }
     SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, q_r_max, q_r_min, exclude_ii);
@@ -932,11 +931,13 @@ int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_
 
 // ---- kNN ---------------------------------------------------------------------------------------------
 int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
-                   uint32_t num_neighbors, float r_max, float r_min, int exclude_ii, int sort_by_distance,
-                   fgpu_nlist** out)
+                   int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                   int sort_by_distance, fgpu_nlist** out)
 {
     return guarded([&] {
         require(pts != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        require(flavour == FGPU_FLAVOUR_WRAP || flavour == FGPU_FLAVOUR_IMAGE, FGPU_EINVALID, "unknown flavour");
+        bool const wrap = flavour == FGPU_FLAVOUR_WRAP;
         fgpu_ctx* ctx = pts->ctx;
         bind_device(ctx);
         require(r_max > 0, FGPU_EINVALID, "NeighborQuery requires r_max to be positive.");
@@ -988,8 +989,9 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             // ---- production path: warp-cooperative ball search at the window radius, selection per row -----
             // (regular grids with every point inside the box; the thread-per-query kernel below handles the rest)
             float const r_win = r_grid < r_max ? r_grid : r_max;
-            Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, 0.0f, exclude_ii);
-            s2.knn_r_min = r_min > 0.0f ? r_min : 0.0f;
+            // r_min: LinkCell compares squares (LinkCell.cc:619), AABBQuery the distance itself (AABBQuery.cc:213)
+            Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, wrap ? r_min : 0.0f, exclude_ii);
+            s2.knn_r_min = !wrap && r_min > 0.0f ? r_min : 0.0f;
             if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL) && pts->n < 0x7fffffffU)
             {
                 ctx->tmp_start.reserve((size_t) n_query + 1);
@@ -1022,7 +1024,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                         args.tmp_start = ctx->tmp_start.ptr;
                         FGPU_CUDA_CHECK(
                             cudaMemsetAsync(ctx->d_scalars + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
-                        launch_search2(ctx, FGPU_FLAVOUR_IMAGE, S2_NL, args);
+                        launch_search2(ctx, flavour, S2_NL, args);
                         KnnRowsArgs ra;
                         ra.hits = ctx->knn_hits.ptr;
                         ra.n_query = n_query;
@@ -1075,7 +1077,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                     sub.cell_start = ctx->q_cell_start.ptr;
                     sub.outside_flag = ctx->q_outside_flag.ptr;
                     float const r_win2 = r_grid2 < r_max ? r_grid2 : r_max;
-                    Search2Args s2b = base_search2_args(pts, sub, q_index_offset, r_win2, 0.0f, exclude_ii);
+                    Search2Args s2b = base_search2_args(pts, sub, q_index_offset, r_win2, wrap ? r_min : 0.0f, exclude_ii);
                     s2b.knn_r_min = s2.knn_r_min;
                     s2b.q_remap = ctx->knn_unresolved.ptr;
                     s2b.tmp_flag = kSecondBag;
@@ -1128,6 +1130,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             std::memset(&a, 0, sizeof(a));
             a.box = pts->box;
             a.grid = grid_dev(pts);
+            a.flavour = flavour;
             a.q_sorted = qv.sorted;
             a.n_query = n_query;
             a.q_index_offset = q_index_offset;
@@ -1163,6 +1166,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
         {
             KnnEmitArgs e;
             e.box = pts->box;
+            e.flavour = flavour;
             e.sorted = pts->grid.sorted.ptr;
             e.q_xyz = qv.xyz;
             e.knn_d = ctx->knn_d.ptr;
@@ -1323,8 +1327,9 @@ int fgpu_rdf_create(fgpu_ctx* ctx, uint32_t bins, float r_max, float r_min, fgpu
         r->axis.r_max = r_max;
         r->axis.inv_width = inv;
         r->axis.bins = bins;
-        r->hist.reserve(bins);
-        FGPU_CUDA_CHECK(cudaMemsetAsync(r->hist.ptr, 0, (size_t) bins * sizeof(uint32_t), ctx->stream));
+        // one word behind the counters: sticky "a sharded accumulation could not run" flag, checked by read()
+        r->hist.reserve((size_t) bins + 1);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(r->hist.ptr, 0, ((size_t) bins + 1) * sizeof(uint32_t), ctx->stream));
         sync(ctx);
         *out = r.release();
     });
@@ -1345,7 +1350,7 @@ int fgpu_rdf_reset(fgpu_rdf* rdf)
         require(rdf != nullptr, FGPU_EINVALID, "null argument");
         bind_device(rdf->ctx);
         FGPU_CUDA_CHECK(
-            cudaMemsetAsync(rdf->hist.ptr, 0, (size_t) rdf->axis.bins * sizeof(uint32_t), rdf->ctx->stream));
+            cudaMemsetAsync(rdf->hist.ptr, 0, ((size_t) rdf->axis.bins + 1) * sizeof(uint32_t), rdf->ctx->stream));
     });
 }
 
@@ -1382,8 +1387,14 @@ int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host)
     return guarded([&] {
         require(rdf != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
         bind_device(rdf->ctx);
-        d2h(rdf->ctx, counts_host, rdf->hist.ptr, (size_t) rdf->axis.bins * sizeof(uint32_t));
-        sync(rdf->ctx);
+        fgpu_ctx* ctx = rdf->ctx;
+        d2h(ctx, counts_host, rdf->hist.ptr, (size_t) rdf->axis.bins * sizeof(uint32_t));
+        d2h(ctx, ctx->h_scalars + 7, rdf->hist.ptr + rdf->axis.bins, sizeof(uint32_t));
+        sync(ctx);
+        // raised on the device by a sharded accumulation (fgpu_points_set_shard), which has no general-kernel
+        // fallback and no host round trip of its own
+        require((ctx->h_scalars[7] & 0xffffffffULL) == 0, FGPU_ERUNTIME,
+                "sharded RDF accumulation needs every point inside the box (wrap the points first)");
     });
 }
 

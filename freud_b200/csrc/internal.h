@@ -355,6 +355,7 @@ struct KnnArgs
 {
     BoxDev box;
     GridDev grid;
+    int flavour;
     const float4* q_sorted;
     uint32_t n_query;
     uint32_t q_index_offset;
@@ -375,6 +376,7 @@ void launch_knn(fgpu_ctx* ctx, const KnnArgs& args);
 struct KnnEmitArgs
 {
     BoxDev box;
+    int flavour;
     const float4* sorted;
     const float* q_xyz;
     const float* knn_d;

@@ -4,6 +4,9 @@
 // iterator returns the k smallest closest-image distances in the IMAGE arithmetic r = p_j - (q + image_k),
 // restricted to r_min <= d and r_sq < r_max^2, independent of r_guess/scale; ties at the k-th place are
 // resolved by an unstable std::sort upstream (unspecified) and by (r_sq, point index) here.
+// WRAP flavour = LinkCellQueryIterator::next (freud/locality/LinkCell.cc:575-679): the k smallest wrapped
+// distances r = Box::wrap(p_j - q) with r_min^2 <= r_sq < r_max^2; its shell-by-shell early exit only stops once
+// the k-th distance is inside the searched shells, so the answer does not depend on the cell width.
 //
 // One thread per query point keeps its k best candidates in a [k][n_query] scratch array (slot-major, so
 // the threads of a warp touch consecutive words).  A query is resolved when its k-th distance is inside the
@@ -42,6 +45,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(KnnArgs a)
     uint32_t const q_global = qi + a.q_index_offset;
     float const qx = q.x, qy = q.y, qz = box.is2d ? 0.0f : q.z; // AABBQuery.cc:84-87
     float const r_max_sq = __fmul_rn(a.r_max, a.r_max);
+    float const r_min_sq = __fmul_rn(a.r_min, a.r_min); // WRAP flavour: LinkCell.cc:577-578
     float const r_safe_sq = a.r_safe * a.r_safe;
     uint32_t const nq = a.n_query, k = a.k;
     float* const best_d = a.knn_d + qi;
@@ -73,44 +77,59 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(KnnArgs a)
                     {
                         continue;
                     }
-                    int njx = 0, njy = 0, njz = 0;
-                    if (any_shift)
-                    {
-                        unpack_shift(__ldg(g.shift + s), njx, njy, njz);
-                    }
-                    int const kx0 = wx == 2 ? -1 : njx - nqx - wx, kx1 = wx == 2 ? 1 : kx0;
-                    int const ky0 = wy == 2 ? -1 : njy - nqy - wy, ky1 = wy == 2 ? 1 : ky0;
-                    int const kz0 = wz == 2 ? -1 : njz - nqz - wz, kz1 = wz == 2 ? 1 : kz0;
-                    float const pz = box.is2d ? 0.0f : p.z; // AABBQuery.cc:118-122
-                    // closest admissible image (AABBQuery.cc:197-211 keeps the closest image per point)
                     float best = INFINITY;
-                    for (int kx = max(kx0, -1); kx <= min(kx1, 1); ++kx)
+                    if (a.flavour == FGPU_FLAVOUR_WRAP)
                     {
-                        for (int ky = max(ky0, -1); ky <= min(ky1, 1); ++ky)
+                        // LinkCellQueryIterator::next: one wrapped displacement per point, LinkCell.cc:617-622
+                        ++evals;
+                        float rx, ry, rz;
+                        wrap_exact(box, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z), rx, ry, rz);
+                        best = dot_exact(rx, ry, rz);
+                        if (!(best < r_max_sq) || best < r_min_sq)
                         {
-                            for (int kz = max(kz0, -1); kz <= min(kz1, 1); ++kz)
-                            {
-                                ++evals;
-                                float ix_, iy_, iz_;
-                                image_vector(box, kx, ky, kz, ix_, iy_, iz_);
-                                float const rx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
-                                float const ry = __fsub_rn(p.y, __fadd_rn(qy, iy_));
-                                float const rz = __fsub_rn(pz, __fadd_rn(qz, iz_));
-                                best = fminf(best, dot_exact(rx, ry, rz));
-                            }
+                            continue;
                         }
                     }
-                    if (!(best < r_max_sq))
+                    else
                     {
-                        continue; // the ball query inside the iterator keeps r_sq < min(r_cur, r_max)^2
+                        int njx = 0, njy = 0, njz = 0;
+                        if (any_shift)
+                        {
+                            unpack_shift(__ldg(g.shift + s), njx, njy, njz);
+                        }
+                        int const kx0 = wx == 2 ? -1 : njx - nqx - wx, kx1 = wx == 2 ? 1 : kx0;
+                        int const ky0 = wy == 2 ? -1 : njy - nqy - wy, ky1 = wy == 2 ? 1 : ky0;
+                        int const kz0 = wz == 2 ? -1 : njz - nqz - wz, kz1 = wz == 2 ? 1 : kz0;
+                        float const pz = box.is2d ? 0.0f : p.z; // AABBQuery.cc:118-122
+                        // closest admissible image (AABBQuery.cc:197-211 keeps the closest image per point)
+                        for (int kx = max(kx0, -1); kx <= min(kx1, 1); ++kx)
+                        {
+                            for (int ky = max(ky0, -1); ky <= min(ky1, 1); ++ky)
+                            {
+                                for (int kz = max(kz0, -1); kz <= min(kz1, 1); ++kz)
+                                {
+                                    ++evals;
+                                    float ix_, iy_, iz_;
+                                    image_vector(box, kx, ky, kz, ix_, iy_, iz_);
+                                    float const rx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
+                                    float const ry = __fsub_rn(p.y, __fadd_rn(qy, iy_));
+                                    float const rz = __fsub_rn(pz, __fadd_rn(qz, iz_));
+                                    best = fminf(best, dot_exact(rx, ry, rz));
+                                }
+                            }
+                        }
+                        if (!(best < r_max_sq))
+                        {
+                            continue; // the ball query inside the iterator keeps r_sq < min(r_cur, r_max)^2
+                        }
+                        if (__fsqrt_rn(best) < a.r_min)
+                        {
+                            continue; // AABBQuery.cc:213-216
+                        }
                     }
                     if (!a.cover_all && best > r_safe_sq)
                     {
                         continue; // cannot be part of a resolved answer
-                    }
-                    if (__fsqrt_rn(best) < a.r_min)
-                    {
-                        continue; // AABBQuery.cc:213-216
                     }
                     // insert into the sorted top-k
                     uint32_t pos;
@@ -187,7 +206,13 @@ __global__ void __launch_bounds__(256) k_knn_emit(KnnEmitArgs a)
     float const qz = a.box.is2d ? 0.0f : a.q_xyz[3 * (size_t) qi + 2];
     float const pz = a.box.is2d ? 0.0f : p.z;
     float rx = 0, ry = 0, rz = 0, r_sq = INFINITY;
-    for (int code = 0; code < 27; ++code)
+    if (a.flavour == FGPU_FLAVOUR_WRAP)
+    {
+        wrap_exact(a.box, __fsub_rn(p.x, qx), __fsub_rn(p.y, qy), __fsub_rn(p.z, a.q_xyz[3 * (size_t) qi + 2]), rx, ry,
+                   rz);
+        r_sq = dot_exact(rx, ry, rz);
+    }
+    for (int code = 0; a.flavour != FGPU_FLAVOUR_WRAP && code < 27; ++code)
     {
         int i = 0, jj = 0, k = 0;
         if (code > 0)

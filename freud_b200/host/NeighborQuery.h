@@ -253,8 +253,9 @@ public:
         }
         else
         {
-            gpu::check(fgpu_knn_query(pts, q, m_n_query_points, 0, m_qargs.num_neighbors, m_qargs.r_max, m_qargs.r_min,
-                                      m_qargs.exclude_ii ? 1 : 0, sort_by_distance ? 1 : 0, &out));
+            gpu::check(fgpu_knn_query(pts, q, m_n_query_points, 0, m_nq->getFlavour(), m_qargs.num_neighbors,
+                                      m_qargs.r_max, m_qargs.r_min, m_qargs.exclude_ii ? 1 : 0,
+                                      sort_by_distance ? 1 : 0, &out));
         }
         return std::make_shared<NeighborList>(out, gpu::context());
     }
@@ -285,8 +286,8 @@ inline std::shared_ptr<NeighborQueryIterator> NeighborQuery::query(const vec3<fl
 
 // LinkCell (freud/locality/LinkCell.h:188, LinkCell.cc:222-260).  cell_width is validated like upstream and
 // otherwise ignored: by SURVEY.md E1 it never influences the result, and the GPU grid follows r_max.
-// Nearest-neighbour queries run the closest-image search of AABBQuery (same neighbour sets; distances in the
-// image arithmetic) -- upstream's LinkCell kNN iterator (LinkCell.cc:575-679) is listed under "next".
+// Nearest-neighbour queries are LinkCellQueryIterator::next (LinkCell.cc:575-679): the k smallest wrapped
+// distances, in the same WRAP arithmetic as the ball query.
 class LinkCell : public NeighborQuery
 {
 public:

@@ -132,13 +132,18 @@ int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_
                         int sort_by_distance, fgpu_nlist** out);
 
 /* ---- k-nearest-neighbour query -> NeighborList ------------------------------------------------------
- * Replaces query(mode == nearest)->toNeighborList(): AABBQueryIterator::next
- * freud/locality/AABBQuery.cc:152-281 (E3 in SURVEY.md: the k smallest closest-image distances in the
- * IMAGE arithmetic, d >= r_min, d <= r_max; r_guess/scale do not influence the result,
- * tests/test_locality_neighbor_query.py:635-656).  r_max may be INFINITY. */
+ * Replaces query(mode == nearest)->toNeighborList().
+ *   FGPU_FLAVOUR_IMAGE: AABBQueryIterator::next, freud/locality/AABBQuery.cc:152-281 (E3 in SURVEY.md: the k
+ *     smallest closest-image distances in the IMAGE arithmetic, d >= r_min, r_sq < r_max^2; r_guess/scale do
+ *     not influence the result, tests/test_locality_neighbor_query.py:635-656).
+ *   FGPU_FLAVOUR_WRAP: LinkCellQueryIterator::next, freud/locality/LinkCell.cc:575-679: the k smallest wrapped
+ *     distances r = Box::wrap(p_j - q) with r_min^2 <= r_sq < r_max^2 (the cell width only steers its early
+ *     exit, never the answer).
+ * Ties at the k-th place are unspecified upstream (unstable std::sort on the distance) and resolved by
+ * (r_sq, point index) here.  r_max may be INFINITY. */
 int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
-                   uint32_t num_neighbors, float r_max, float r_min, int exclude_ii, int sort_by_distance,
-                   fgpu_nlist** out);
+                   int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                   int sort_by_distance, fgpu_nlist** out);
 
 /* ---- NeighborList -----------------------------------------------------------------------------------
  * Layout = freud::locality::NeighborList (freud/locality/NeighborList.h:139-157): neighbors u32[nb][2],

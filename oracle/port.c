@@ -847,6 +847,53 @@ port_nlist_t* fport_knn_nlist(const float* box6, int is2d, const float* pts, uin
     return assemble(rows, nq);
 }
 
+/* ---- kNN, wrap flavour ------------------------------------------------------------------------- */
+/* LinkCellQueryIterator::next (LinkCell.cc:575-679): every point once with r = Box::wrap(p_j - q), kept if
+ * r_min^2 <= r.r < r_max^2 (:577-578, :617-622), sorted by distance, the first num_neighbors returned (:663-672).
+ * The shell-by-shell early exit (:654-661) only stops once the k-th distance is inside the searched shells, so the
+ * cell structure does not influence the answer.  Brute force over the points. */
+port_nlist_t* fport_knn_nlist_wrap(const float* box6, int is2d, const float* pts, uint32_t n, const float* qpts,
+                                   uint32_t nq, uint32_t k, float r_max, float r_min, int exclude_ii,
+                                   int sort_by_distance)
+{
+    box_t b = box_make(box6, is2d);
+    volatile float r_max_sq_v = r_max * r_max, r_min_sq_v = r_min * r_min;
+    float r_max_sq = r_max_sq_v, r_min_sq = r_min_sq_v;
+    hitvec_t* rows = (hitvec_t*) calloc(nq ? nq : 1, sizeof(hitvec_t));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < (int64_t) nq; ++i)
+    {
+        hitvec_t all = {0, 0, 0};
+        for (uint32_t j = 0; j < n; ++j)
+        {
+            if (exclude_ii && j == (uint32_t) i)
+            {
+                continue;
+            }
+            float dlt[3] = {pts[3 * (size_t) j] - qpts[3 * i], pts[3 * (size_t) j + 1] - qpts[3 * i + 1],
+                            pts[3 * (size_t) j + 2] - qpts[3 * i + 2]};
+            float r[3];
+            box_wrap(&b, dlt, r);
+            float r_sq = dot3(r);
+            if (r_sq < r_max_sq && r_sq >= r_min_sq)
+            {
+                hit_push(&all, j, sqrtf(r_sq), r);
+            }
+        }
+        qsort(all.data, all.size, sizeof(hit_t), cmp_hit_d);
+        if (all.size > k)
+        {
+            all.size = k;
+        }
+        if (!sort_by_distance)
+        {
+            qsort(all.data, all.size, sizeof(hit_t), cmp_hit_j);
+        }
+        rows[i] = all;
+    }
+    return assemble(rows, nq);
+}
+
 /* ---- Steinhardt ------------------------------------------------------------------------------- */
 /* fsph::PointSPHEvaluator<float> (extern/fsph/src/spherical_harmonics.hpp:155-290), lmax <= 32 */
 #define SPH_LMAX 32

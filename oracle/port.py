@@ -33,6 +33,8 @@ def lib():
         L.fport_knn_nlist.restype = C.c_void_p
         L.fport_knn_nlist.argtypes = [_fp, C.c_int, _fp, C.c_uint32, _fp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                       C.c_int, C.c_int]
+        L.fport_knn_nlist_wrap.restype = C.c_void_p
+        L.fport_knn_nlist_wrap.argtypes = L.fport_knn_nlist.argtypes
         L.fport_nlist_size.restype = C.c_uint64
         L.fport_nlist_size.argtypes = [C.c_void_p]
         L.fport_nlist_copy.argtypes = [C.c_void_p, _up, _fp, _fp, _fp, _up, _up]
@@ -94,10 +96,13 @@ def ball_nlist(flavour, box, is2d, points, query_points, r_max, r_min=0.0, exclu
     return NeighborList(h, len(q))
 
 
-def knn_nlist(box, is2d, points, query_points, k, r_max=np.inf, r_min=0.0, exclude_ii=False, sort_by_distance=False):
+def knn_nlist(box, is2d, points, query_points, k, r_max=np.inf, r_min=0.0, exclude_ii=False, sort_by_distance=False,
+              flavour=IMAGE):
+    """flavour IMAGE: AABBQueryIterator (AABBQuery.cc:152-281); WRAP: LinkCellQueryIterator (LinkCell.cc:575-679)."""
     b, p, q = box6(box), _f32(points, 3), _f32(query_points, 3)
-    h = lib().fport_knn_nlist(_p(b), int(is2d), _p(p), len(p), _p(q), len(q), int(k), r_max, r_min, int(exclude_ii),
-                              int(sort_by_distance))
+    fn = lib().fport_knn_nlist if flavour == IMAGE else lib().fport_knn_nlist_wrap
+    h = fn(_p(b), int(is2d), _p(p), len(p), _p(q), len(q), int(k), r_max, r_min, int(exclude_ii),
+           int(sort_by_distance))
     return NeighborList(h, len(q))
 
 

@@ -282,6 +282,21 @@ def test_knn(ctx, name):
         assert_nlist_equal(got, want, f"{name} knn k={k}")
 
 
+@pytest.mark.parametrize("name", list(BOXES))
+def test_knn_wrap_flavour(ctx, name):
+    """LinkCell's nearest-neighbour iterator (LinkCell.cc:575-679): the k smallest WRAPPED distances."""
+    box, n, r = BOXES[name]
+    pts = random_points(box, n, seed=33)
+    dp = _capi().DevicePoints(ctx, box, pts)
+    for q, excl in ((None, True), (random_points(box, 300, seed=34), False)):
+        qq = pts if q is None else q
+        for k, sbd, kw in ((12, False, {}), (5, True, {}), (7, False, dict(r_max=2.2, r_min=0.7))):
+            got = dp.knn_query(q, k, exclude_ii=excl, sort_by_distance=sbd, flavour=WRAP, **kw).to_host()
+            want = port.knn_nlist(box, box.is2D, pts, qq, k, kw.get("r_max", np.inf), kw.get("r_min", 0.0), excl, sbd,
+                                  flavour=port.WRAP)
+            assert_nlist_equal(got, want, f"{name} wrap knn k={k} self={q is None}")
+
+
 @pytest.mark.parametrize("k", [4, 12])
 def test_knn_short_rows_are_searched_again(ctx, k):
     """Uniform random points: the first window (2(k+1) expected points) leaves a few rows with fewer than k hits;
@@ -324,6 +339,13 @@ def test_rdf_home_tiles_sharded(ctx, name, flavour):
         capi.DeviceRDF(ctx, 64, r).accumulate(dp, pts[:10], flavour, r, 0.0, False)
     dp.set_shard(0, 1)
     assert dp.ball_query(None, flavour, r, 0.0, True).num_bonds == int(want.sum())
+    # un-wrapped input: the sharded path has no general-kernel fallback and says so when the counts are read
+    dq = capi.DevicePoints(ctx, box, random_points(box, n, seed=92, spill=0.05))
+    dq.set_shard(0, 2)
+    bad = capi.DeviceRDF(ctx, 64, r)
+    bad.accumulate(dq, None, flavour, r, 0.0, True)
+    with pytest.raises(RuntimeError):
+        bad.read()
 
 
 def test_knn_r_max_r_min(ctx):

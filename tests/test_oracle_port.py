@@ -47,6 +47,23 @@ def test_port_matches_golden_neighbor_lists(name):
             assert np.array_equal(bits(red[key]), bits(gold[f"rdf_{tag}_{key}"])), key
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref is built only where /root/reference exists")
+@pytest.mark.parametrize("name", list(BOXES))
+def test_port_knn_wrap_matches_the_reference_linkcell(name):
+    """fport_knn_nlist_wrap against the reference's own LinkCellQueryIterator (LinkCell.cc:575-679), bit for bit."""
+    box, n, _ = BOXES[name]
+    pts, q = random_points(box, min(n, 800), 5), random_points(box, 150, 6)
+    width = min(2.0, 0.4 * float(min(box.Lx, box.Ly)))
+    for k, sbd, kw in ((6, False, {}), (12, True, {}), (5, False, dict(r_max=2.0, r_min=0.6))):
+        want = ref.Query("linkcell", box, pts, is2d=box.is2D, cell_width=width).nlist(q, num_neighbors=k,
+                                                                                      sort_by_distance=sbd, **kw)
+        got = port.knn_nlist(box, box.is2D, pts, q, k, kw.get("r_max", np.inf), kw.get("r_min", 0.0), False, sbd,
+                             flavour=port.WRAP)
+        assert np.array_equal(got.neighbors, want.neighbors), (name, k)
+        assert np.array_equal(bits(got.distances), bits(want.distances)), (name, k)
+        assert np.array_equal(bits(got.vectors), bits(want.vectors)), (name, k)
+
+
 def test_port_matches_golden_rdf_config0():
     """BASELINE.json configs[0]: RDF bins=100 r_max=5 on make_random_system(50, 10000), one and two frames."""
     gold = np.load(os.path.join(GOLD, "rdf_config0.npz"))
