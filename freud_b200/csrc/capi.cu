@@ -336,7 +336,10 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_max, r_min, exclude_ii);
     if (!ctx->force_general && search2_supported(s2, S2_NL))
     {
-        // bag capacity: the previous query's bond count if there was one, else the ideal-gas expectation
+        // Capacities of the bag and of the output arrays: the previous query's bond count if there was one, else
+        // the ideal-gas expectation.  Search, offsets scan and emit are enqueued back to back -- the emit kernel
+        // checks on the device that the search succeeded and that everything fits -- so the frame has one host
+        // round trip, at the end, and the GPU never waits for the host in between.
         double const vol = box_volume(pts->box);
         double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max
                                            : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
@@ -352,12 +355,33 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         {
             cap = std::min<uint64_t>(cap, 0xffffffffULL);
             ctx->bag4.reserve(cap);
+            alloc_bonds(nl.get(), cap); // n_bonds is corrected below
             s2.bag = ctx->bag4.ptr;
             s2.temp_cap = (uint32_t) cap;
             s2.counts = nl->counts.ptr;
             s2.tmp_start = ctx->tmp_start.ptr;
             FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
             launch_search2(ctx, flavour, S2_NL, s2);
+            FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->row_start.ptr, nl->counts.ptr, (size_t) n_query * sizeof(uint32_t),
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
+            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+            Emit2Args e;
+            e.bag = ctx->bag4.ptr;
+            e.tmp_start = ctx->tmp_start.ptr;
+            e.row_start = nl->row_start.ptr;
+            e.counts = nl->counts.ptr;
+            e.segments = nl->segments.ptr;
+            e.n_query = n_query;
+            e.fail = s2.fail;
+            e.cursor = s2.cursor;
+            e.bag_cap = cap;
+            e.out_cap = cap;
+            e.neighbors = nl->neighbors.ptr;
+            e.distances = nl->distances.ptr;
+            e.weights = nl->weights.ptr;
+            e.vectors = nl->vectors.ptr;
+            launch_emit2(ctx, sort_by_distance, e);
             d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
             sync(ctx);
             int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
@@ -379,23 +403,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         if (done)
         {
             ctx->bag_hint = n_bonds;
-            alloc_bonds(nl.get(), n_bonds);
-            FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->row_start.ptr, nl->counts.ptr, (size_t) n_query * sizeof(uint32_t),
-                                            cudaMemcpyDeviceToDevice, ctx->stream));
-            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
-            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
-            Emit2Args e;
-            e.bag = ctx->bag4.ptr;
-            e.tmp_start = ctx->tmp_start.ptr;
-            e.row_start = nl->row_start.ptr;
-            e.n_query = n_query;
-            e.n_bonds = n_bonds;
-            e.neighbors = nl->neighbors.ptr;
-            e.distances = nl->distances.ptr;
-            e.weights = nl->weights.ptr;
-            e.vectors = nl->vectors.ptr;
-            launch_emit2(ctx, sort_by_distance, e);
-            launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
+            nl->n_bonds = n_bonds;
             *out = nl.release();
             return;
         }

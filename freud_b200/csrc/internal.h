@@ -342,8 +342,14 @@ struct Emit2Args
     const float4* bag;
     const uint32_t* tmp_start;
     const uint32_t* row_start; // n_query + 1
+    const uint32_t* counts;    // n_query
+    uint32_t* segments;        // n_query: counts ? row_start : 0 (NeighborList.cc:199-232), written here too
     uint32_t n_query;
-    uint64_t n_bonds;
+    // launched before the host knows how the search went: the kernel returns at once if the search gave up
+    // (*fail), if its bag overflowed (*cursor > bag_cap) or if the output arrays are too small (> out_cap)
+    const int* fail;
+    const unsigned long long* cursor;
+    uint64_t bag_cap, out_cap;
     uint32_t* neighbors;
     float* distances;
     float* weights;

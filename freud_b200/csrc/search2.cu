@@ -603,6 +603,13 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(256) k_emit2(Emit2A
 {
     __shared__ uint32_t s_start[kEmitRows + 1];
     __shared__ uint32_t s_tmp[kEmitRows];
+    {
+        unsigned long long const total = *a.cursor;
+        if (*a.fail != 0 || total > a.bag_cap || total > a.out_cap)
+        {
+            return; // the host repeats the step it has to repeat
+        }
+    }
     uint32_t const r0 = blockIdx.x * kEmitRows;
     uint32_t const n_rows = min((uint32_t) kEmitRows, a.n_query - r0);
     for (uint32_t i = threadIdx.x; i <= n_rows; i += blockDim.x)
@@ -611,6 +618,7 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(256) k_emit2(Emit2A
         if (i < n_rows)
         {
             s_tmp[i] = a.tmp_start[r0 + i];
+            a.segments[r0 + i] = a.counts[r0 + i] != 0 ? s_start[i] : 0U; // untouched rows stay 0 upstream
         }
     }
     __syncthreads();
@@ -785,7 +793,7 @@ void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a)
 
 void launch_emit2(fgpu_ctx* ctx, int sort_by_distance, const Emit2Args& a)
 {
-    if (a.n_bonds == 0)
+    if (a.n_query == 0)
     {
         return;
     }
