@@ -471,6 +471,10 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     QueryView const qv = prepare_queries(pts, q_host, q_dev, n_query);
     Search2Args s2 = base_search2_args(pts, qv, q_index_offset, q_r_max, q_r_min, exclude_ii);
     s2.axis = rdf->axis;
+    // Queries are the points themselves and no image vector is involved in most pairs: r_ij and r_ji are exact
+    // negatives there, so one test stands for both bonds (IMAGE arithmetic only: Box::wrap is not odd in floating
+    // point).  The self pair (i, i) lies in the tile's own row, which is always walked in full.
+    s2.symmetric = self && q_index_offset == 0 && flavour == FGPU_FLAVOUR_IMAGE && std::getenv("FGPU_NO_SYMMETRY") == nullptr;
     bool const fast = !ctx->force_general && search2_supported(s2, S2_RDF);
     if (sharded)
     {

@@ -303,6 +303,8 @@ struct Search2Args
     int exclude_ii;
     float rcp_lx, rcp_ly, rcp_lz;   // RN(1 / L), rounded on the host
     float r_hi_sq;                  // stage-1 acceptance bound (WRAP)
+    int symmetric;                  // IMAGE + RDF, queries == points: walk every boundary-free pair of rows once
+                                    // and count its hits twice (tile_walk.cuh)
     float knn_r_min;                // > 0 (IMAGE + NL, kNN only): also reject sqrt(r_sq) < knn_r_min (AABBQuery.cc:213)
     // NeighborList mode
     float4* bag;                    // bag: {vector, bits(point index)} of every hit, rows contiguous

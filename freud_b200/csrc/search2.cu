@@ -142,8 +142,10 @@ __host__ __device__ inline size_t warp_mem_bytes(int mode, uint32_t out_cap)
     return mode == S2_NL ? sizeof(WarpMemNL) + (size_t) out_cap * 5 * sizeof(uint32_t) : sizeof(WarpMemBase);
 }
 
-template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
+template<int FLAVOUR, int MODE, bool TRI, bool SYM = false>
+__global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
 {
+    static_assert(!SYM || (FLAVOUR == FGPU_FLAVOUR_IMAGE && MODE == S2_RDF), "symmetric walk: fused IMAGE RDF only");
     using WarpMem = typename WarpMemOf<MODE>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,13 +222,14 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         }
         o_len += __popc(mh);
     };
-    auto bin_hit = [&](bool hit, float r_sq) {
+    // weight: 1, or 2 for a bond found by the symmetric walk (it stands for (i, j) and (j, i), tile_walk.cuh)
+    auto bin_hit = [&](bool hit, float r_sq, uint32_t weight = 1U) {
         if (hit)
         {
             int const bin = axis_bin(a.axis, __fsqrt_rn(r_sq)); // NeighborBond distance = sqrt(dot(v, v))
             if (bin >= 0)
             {
-                atomicAdd(&sh_hist[bin], 1U);
+                atomicAdd(&sh_hist[bin], weight);
             }
         }
     };
@@ -283,8 +286,9 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         }
         else
         {
-            // IMAGE + RDF: the stack holds r_sq of accepted bonds
-            bin_hit(act, act ? __uint_as_float(queue[e].x) : 0.0f);
+            // IMAGE + RDF: the stack holds r_sq of accepted bonds (sign bit = counts twice, SYM only)
+            uint32_t const bits = act ? queue[e].x : 0U;
+            bin_hit(act, __uint_as_float(bits & 0x7fffffffU), SYM ? 1U + (bits >> 31) : 1U);
         }
         __syncwarp();
     };
@@ -356,7 +360,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                     unsigned const m = __ballot_sync(FULL, ok);
                     if (ok)
                     {
-                        queue[q_len + __popc(m & lt_mask)] = make_uint2(c.slot, WRAPPED ? k | (c.code << 8) : k | (tile::kNoWrap << 8));
+                        queue[q_len + __popc(m & lt_mask)] = make_uint2(c.slot, WRAPPED ? k | ((c.code & tile::kCodeMask) << 8) : k | (tile::kNoWrap << 8));
                     }
                     q_len += __popc(m);
                 }
@@ -375,7 +379,8 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
                     unsigned const m = __ballot_sync(FULL, hit);
                     if (hit)
                     {
-                        queue[q_len + __popc(m & lt_mask)].x = __float_as_uint(r_sq);
+                        queue[q_len + __popc(m & lt_mask)].x
+                            = SYM ? __float_as_uint(r_sq) | (c.code & tile::kTwice) : __float_as_uint(r_sq);
                     }
                     q_len += __popc(m);
                 }
@@ -412,7 +417,7 @@ template<int FLAVOUR, int MODE, bool TRI> __global__ void __launch_bounds__(kThr
         {
             continue;
         }
-        tile::Runs const runs = tile::setup_runs(dx, dy, dz, a.cell_start, cx0, cx1, cy, cz, lane, wm.runs);
+        tile::Runs const runs = tile::setup_runs<SYM>(dx, dy, dz, a.cell_start, cx0, cx1, cy, cz, lane, wm.runs);
         uint32_t const T = runs.T;
         bool const any_wrap = runs.any_wrap;
 
@@ -672,11 +677,12 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(256) k_emit2(Emit2A
     }
 }
 
-template<int FLAVOUR, int MODE, bool TRI> void launch_one(fgpu_ctx* ctx, const Search2Args& a, const char* name)
+template<int FLAVOUR, int MODE, bool TRI, bool SYM = false>
+void launch_one(fgpu_ctx* ctx, const Search2Args& a, const char* name)
 {
     size_t const hist_bytes = MODE == S2_RDF ? ((a.axis.bins * sizeof(uint32_t) + 15) / 16) * 16 : 0;
     size_t const smem = hist_bytes + (size_t) kWarps * warp_mem_bytes(MODE, a.out_cap);
-    auto kern = k_search2<FLAVOUR, MODE, TRI>;
+    auto kern = k_search2<FLAVOUR, MODE, TRI, SYM>;
     static bool configured = false; // per instantiation
     if (!configured)
     {
@@ -784,8 +790,10 @@ void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a)
     {
         if (mode == S2_NL)
             FGPU_S2(FGPU_FLAVOUR_IMAGE, S2_NL);
+        else if (a.symmetric)
+            launch_one<FGPU_FLAVOUR_IMAGE, S2_RDF, false, true>(ctx, a, name); // TRI only matters to wrap_fast
         else
-            FGPU_S2(FGPU_FLAVOUR_IMAGE, S2_RDF);
+            launch_one<FGPU_FLAVOUR_IMAGE, S2_RDF, false, false>(ctx, a, name);
     }
 #undef FGPU_S2
     FGPU_CUDA_CHECK(cudaGetLastError());

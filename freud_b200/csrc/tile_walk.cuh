@@ -20,20 +20,27 @@ namespace tile {
 
 constexpr unsigned FULL = 0xffffffffU;
 constexpr uint32_t kNoWrap = 21U; // code of (wx, wy, wz) = (0, 0, 0): (0+1) | (0+1) << 2 | (0+1) << 4
+constexpr uint32_t kCodeMask = 63U;
+// Symmetric self queries (IMAGE flavour, fused RDF): a run that crosses no boundary is only walked from the
+// tile that sees it in a "forward" row (oz > 0, or oz == 0 and oy > 0) and its hits count twice -- without an
+// image vector r_ij = p_j - p_i and r_ji = p_i - p_j are exact negatives, so both bonds have the same r_sq
+// bit for bit.  Runs that do cross a boundary, and the tile's own row, are walked from both sides as before.
+constexpr uint32_t kTwice = 0x80000000U;
 
 struct RunScratch
 {
-    uint32_t excl[32], delta[32], code[32];
+    uint32_t excl[32], delta[32], code[32]; // code: boundary crossings | kTwice
 };
 
 struct Runs
 {
     uint32_t excl;  // lane r < R: flattened index of the first candidate of run r (0xffffffff otherwise)
     uint32_t delta; // lane r < R: slot of a candidate = flattened index + delta
-    uint32_t code;  // lane r < R: boundary crossings of run r
+    uint32_t code;  // lane r < R: boundary crossings of run r (| kTwice: its hits count twice)
     uint32_t T;     // candidates of the tile
     int R;          // non-empty runs
     bool any_wrap;  // some run crosses a periodic boundary
+    bool any_twice; // some run counts twice
 };
 
 struct Cand
@@ -45,6 +52,7 @@ struct Cand
     uint32_t code;    // boundary crossings of the candidate's run (kNoWrap: none)
 };
 
+template<bool SYMMETRIC = false>
 __device__ __forceinline__ Runs setup_runs(int dx, int dy, int dz, const uint32_t* __restrict__ cell_start, int cx0,
                                            int cx1, int cy, int cz, int lane, RunScratch& s)
 {
@@ -94,10 +102,19 @@ __device__ __forceinline__ Runs setup_runs(int dx, int dy, int dz, const uint32_
         }
         if (valid)
         {
+            code = (uint32_t) (wx + 1) | ((uint32_t) (wy + 1) << 2) | ((uint32_t) (wz + 1) << 4);
+            if (SYMMETRIC && code == kNoWrap && (oz != 0 || oy != 0))
+            {
+                bool const forward = oz > 0 || (oz == 0 && oy > 0);
+                valid = forward; // the tile on the other side walks this pair of rows
+                code |= kTwice;
+            }
+        }
+        if (valid)
+        {
             uint32_t const rowbase = ((uint32_t) z * dy + y) * dx;
             start = __ldg(cell_start + rowbase + x0);
             len = __ldg(cell_start + rowbase + x1 + 1) - start;
-            code = (uint32_t) (wx + 1) | ((uint32_t) (wy + 1) << 2) | ((uint32_t) (wz + 1) << 4);
         }
     }
     uint32_t incl = len;
@@ -126,7 +143,8 @@ __device__ __forceinline__ Runs setup_runs(int dx, int dy, int dz, const uint32_
     r.excl = lane < r.R ? s.excl[lane] : 0xffffffffU;
     r.delta = lane < r.R ? s.delta[lane] : 0U;
     r.code = lane < r.R ? s.code[lane] : kNoWrap;
-    r.any_wrap = __any_sync(FULL, r.code != kNoWrap);
+    r.any_wrap = __any_sync(FULL, (r.code & kCodeMask) != kNoWrap);
+    r.any_twice = SYMMETRIC && __any_sync(FULL, (r.code & kTwice) != 0);
     return r;
 }
 
@@ -174,10 +192,14 @@ __device__ __forceinline__ void load_round(const Runs& r, const BoxDev& box, con
     {
         c.z = in ? 0.0f : c.z;
     }
-    if (r.any_wrap)
+    if (r.any_wrap || r.any_twice)
     {
         uint32_t const cd = __shfl_sync(FULL, r.code, run);
         c.code = cd;
+    }
+    if (r.any_wrap)
+    {
+        uint32_t const cd = c.code & kCodeMask;
         int const wx = (int) (cd & 3U) - 1, wy = (int) ((cd >> 2) & 3U) - 1, wz = (int) ((cd >> 4) & 3U) - 1;
         if (SHIFTED)
         {
