@@ -208,9 +208,9 @@ def workload_q6(ctx, rank, n):
     pin_pts, keep0 = pinned_empty((n, 3), np.float32)
     pin_pts[:] = pts
 
-    # the window radius fgpu_knn_query starts from (sphere expected to hold 2(k + 1) points), so that the forced
+    # the window radius fgpu_knn_query starts from (sphere expected to hold 1.5 (k + 1) points), so that the forced
     # rebuild below produces the grid the query uses and the step holds exactly one cell-list build
-    r_window = float(np.cbrt(3.0 * 2.0 * 13.0 / (4.0 * np.pi * (n / float(box.volume)))))
+    r_window = float(np.cbrt(3.0 * 1.5 * 13.0 / (4.0 * np.pi * (n / float(box.volume)))))
 
     def step_dev():
         dp.build_cells(r_window)

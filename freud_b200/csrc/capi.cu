@@ -942,6 +942,8 @@ int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_
 }
 
 // ---- kNN ---------------------------------------------------------------------------------------------
+static constexpr double kKnnWindowFill = 1.5;
+
 int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
                    int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
                    int sort_by_distance, fgpu_nlist** out)
@@ -979,12 +981,13 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
         ctx->knn_s.reserve((size_t) n_query * k);
         ctx->row_counts.reserve((size_t) n_query + 1);
 
-        // initial radius: the sphere expected to hold ~2k points at the mean density
-        // (the reference's own r_guess is the k-point sphere, NeighborQuery.h:251-253)
+        // initial radius: the sphere expected to hold 1.5 (k + 1) points at the mean density (the reference's own
+        // r_guess is the k-point sphere, NeighborQuery.h:251-253).  In an ideal gas ~3 % of the rows then hold
+        // fewer than k points; they are searched again alone, which is cheaper than a wider window for everybody.
         double const volume = box_volume(pts->box);
         double const density = (double) pts->n / volume;
-        double r_search = pts->box.is2d ? std::sqrt(2.0 * (k + 1) / (M_PI * density))
-                                        : std::cbrt(3.0 * 2.0 * (k + 1) / (4.0 * M_PI * density));
+        double r_search = pts->box.is2d ? std::sqrt(kKnnWindowFill * (k + 1) / (M_PI * density))
+                                        : std::cbrt(3.0 * kKnnWindowFill * (k + 1) / (4.0 * M_PI * density));
         QueryView qv;
         uint64_t total = 0;
         bool evals_counted = false; // by the count kernel of the warp-cooperative path

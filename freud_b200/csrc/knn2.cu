@@ -156,19 +156,42 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_k
     float* const od = s_od[warp];
     float const inf = __int_as_float(0x7f800000);
     uint32_t const n_warps = gridDim.x * kSelWarps;
-    for (uint32_t row = blockIdx.x * kSelWarps + warp; row < a.n_query; row += n_warps)
+    // What a row needs from memory, fetched one row ahead: the chain length -> bag offset -> record is three
+    // dependent loads, and a warp walks its rows one after the other.
+    struct RowIn
     {
-        uint32_t const n = a.hits[row];
+        uint32_t n;
+        const float4* bag;
+        uint64_t out0;
+        float4 rec; // lane l: hit l of the row (padding beyond the row)
+    };
+    auto fetch = [&](uint32_t row) {
+        RowIn in;
+        in.n = a.hits[row];
+        uint32_t const ts = a.tmp_start[row];
+        // rows searched again with a wider window live in the second bag (flagged in the top bit)
+        in.bag = (ts & kSecondBag) != 0 ? a.bag2 + (ts & ~kSecondBag) : a.bag + ts;
+        in.out0 = a.row_start[row];
+        in.rec = (uint32_t) lane < in.n ? in.bag[lane] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0x7fffffffU));
+        return in;
+    };
+    uint32_t const first_row = blockIdx.x * kSelWarps + warp;
+    RowIn ahead = first_row < a.n_query ? fetch(first_row) : RowIn {0, nullptr, 0, make_float4(0, 0, 0, 0)};
+    for (uint32_t row = first_row; row < a.n_query; row += n_warps)
+    {
+        RowIn const cur = ahead;
+        if (row + n_warps < a.n_query && row + n_warps > row)
+        {
+            ahead = fetch(row + n_warps);
+        }
+        uint32_t const n = cur.n;
         if (n == 0)
         {
             continue;
         }
         uint32_t const kept = min(n, a.k);
-        uint32_t const ts = a.tmp_start[row];
-        // rows searched again with a wider window live in the second bag (flagged in the top bit)
-        const float4* __restrict__ const bag
-            = (ts & kSecondBag) != 0 ? a.bag2 + (ts & ~kSecondBag) : a.bag + ts;
-        uint64_t const out0 = a.row_start[row];
+        const float4* __restrict__ const bag = cur.bag;
+        uint64_t const out0 = cur.out0;
         if (n > kStage)
         {
             select_long_row<BY_DISTANCE>(a, bag, n, kept, row, out0, lane);
@@ -180,7 +203,7 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(kSelWarps * 32) k_k
         {
             // the common case, straight-line: one hit per lane
             bool const act = (uint32_t) lane < n;
-            float4 const r = act ? bag[lane] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0x7fffffffU));
+            float4 const r = cur.rec;
             uint32_t const my_j = __float_as_uint(r.w);
             float const my_rsq = act ? dot_exact(r.x, r.y, r.z) : inf;
             uint32_t const mine = __float_as_uint(my_rsq);

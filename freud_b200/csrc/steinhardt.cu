@@ -5,11 +5,12 @@
 // value iterator :78-93, Condon-Shortley sign Steinhardt.cc:47-49).
 //
 // One thread per particle.  For every bond the thread recomputes delta = Box::wrap(p_j - p_i) (Steinhardt.cc:155;
-// always the WRAP arithmetic, whoever found the bond), takes theta = acos(clamp(z / d)) with the list's
-// distance d and phi = atan2(y, x), runs the Jacobi recurrence for m = 0..l and accumulates Y_lm for m >= 0
-// in registers.  Negative m needs no accumulator: Y_{l,-m} = conj(Y_{l,m}) * (-1)^m term by term, and both
+// always the WRAP arithmetic, whoever found the bond), takes cos(theta) = clamp(z / d) with the list's
+// distance d and (cos, sin)(phi) from (x, y), runs the Jacobi recurrence for m = 0..l, rotates exp(i m phi)
+// from m to m + 1 and accumulates Y_lm for m >= 0 in registers.  Negative m needs no accumulator: Y_{l,-m} = conj(Y_{l,m}) * (-1)^m term by term, and both
 // conj and the sign commute exactly with float summation, so q_{l,-m} is derived at the end.
-// Tolerance vs the reference: 1e-5 (libm vs CUDA sinf/cosf/atan2f/acosf differ in the last ulp).
+// Tolerance vs the reference: 1e-5 (the reference goes through libm's atan2f/acosf/sinf/cosf/exp, this kernel
+// through algebraically identical component formulas; both are a few ulp from the exact value).
 //
 // Options (Steinhardt.cc:224-289, 329-359; Wigner3j.cc:22-57) run as follow-up kernels over the per-particle
 // q_lm array left in device memory by the base kernel:
@@ -21,6 +22,8 @@
 // table order -- m1 = -l..l, m2 = max(-l-m1, -l)..min(l-m1, l) -- and used as float, like upstream.
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "internal.h"
 
@@ -29,6 +32,10 @@ namespace fgpu {
 namespace {
 
 constexpr int kSphLmax = 32;
+// Y = P / sqrt(2 pi) is a double division rounded to float upstream (spherical_harmonics.hpp:85-91); the product
+// with the double reciprocal rounds to the same float except when the quotient sits within 2^-53 of a float
+// rounding boundary.
+constexpr double kInvSqrt2Pi = 1.0 / 2.5066282746310002;
 constexpr int kThreads = 128;
 
 // recurrence prefactors for lmax, laid out as the reference does: [0, lmax*(lmax+1)) first kind,
@@ -43,26 +50,50 @@ __constant__ int c_out_off[kSphLmax + 1]; // request index -> offset (in complex
 struct Angles
 {
     float sphi, cphi; // sin / cos of the polar angle ("phi" in fsph, theta in freud)
-    float az;         // azimuth
+    float caz, saz;   // cos / sin of the azimuth
 };
 
-__device__ __forceinline__ Angles bond_angles(const BoxDev& box, const float* __restrict__ xyz, uint32_t i, uint32_t j,
-                                              float dist)
+// One bond as it comes out of memory: the neighbour's position, the list's distance and weight.  Loading the next
+// bond before the current one is evaluated keeps two dependent gathers (index -> position) in flight per thread.
+struct BondIn
 {
-    float const rx0 = xyz[3 * (size_t) i], ry0 = xyz[3 * (size_t) i + 1], rz0 = xyz[3 * (size_t) i + 2];
-    float const px = xyz[3 * (size_t) j], py = xyz[3 * (size_t) j + 1], pz = xyz[3 * (size_t) j + 2];
+    float px, py, pz, dist, w;
+};
+
+__device__ __forceinline__ BondIn load_bond(const SteinhardtArgs& a, uint32_t b)
+{
+    uint32_t const j = a.neighbors[2 * (size_t) b + 1];
+    BondIn in;
+    in.px = __ldg(a.xyz + 3 * (size_t) j);
+    in.py = __ldg(a.xyz + 3 * (size_t) j + 1);
+    in.pz = __ldg(a.xyz + 3 * (size_t) j + 2);
+    in.dist = a.distances[b];
+    in.w = a.weighted ? a.weights[b] : 1.0f;
+    return in;
+}
+
+__device__ __forceinline__ Angles bond_angles(const BoxDev& box, float rx0, float ry0, float rz0, float px, float py,
+                                              float pz, float dist)
+{
     float dx, dy, dz;
     wrap_exact(box, __fsub_rn(px, rx0), __fsub_rn(py, ry0), __fsub_rn(pz, rz0), dx, dy, dz);
-    float const phi = atan2f(dy, dx);                                         // Steinhardt.cc:161
-    float theta = acosf(fmaxf(-1.0f, fminf(__fdiv_rn(dz, dist), 1.0f)));      // Steinhardt.cc:167
+    // The reference takes phi = atan2(y, x) and theta = acos(clamp(z / d)) (Steinhardt.cc:161-174) and the
+    // evaluator immediately goes back to sin/cos of both (spherical_harmonics.hpp:239-244, :272-281).  Here the
+    // sines and cosines come straight from the components -- cos(theta) = clamp(z / d), sin(theta) =
+    // sqrt(1 - cos^2), (cos, sin)(phi) = (x, y) / hypot(x, y) -- which agrees with the libm round trip to a few
+    // ulp (the documented tolerance is 1e-5) and costs no transcendental at all.
+    float ct = fmaxf(-1.0f, fminf(__fdiv_rn(dz, dist), 1.0f));
     if (dist == 0.0f)
     {
-        theta = 0.0f; // Steinhardt.cc:171-174
+        ct = 1.0f; // theta = 0, Steinhardt.cc:171-174
     }
+    float const rho_sq = dx * dx + dy * dy;
+    float const inv_rho = rho_sq > 0.0f ? rsqrtf(rho_sq) : 0.0f;
     Angles a;
-    a.sphi = sinf(theta);
-    a.cphi = cosf(theta);
-    a.az = phi;
+    a.cphi = ct;
+    a.sphi = sqrtf(fmaxf(0.0f, (1.0f - ct) * (1.0f + ct)));
+    a.caz = rho_sq > 0.0f ? dx * inv_rho : 1.0f; // atan2(0, 0) = 0
+    a.saz = rho_sq > 0.0f ? dy * inv_rho : 0.0f;
     return a;
 }
 
@@ -82,13 +113,19 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
     if (active)
     {
         uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+        float const rx0 = a.xyz[3 * (size_t) i], ry0 = a.xyz[3 * (size_t) i + 1], rz0 = a.xyz[3 * (size_t) i + 2];
+        BondIn next = beg < end ? load_bond(a, beg) : BondIn {0, 0, 0, 0, 0};
         for (uint32_t b = beg; b < end; ++b)
         {
-            uint32_t const j = a.neighbors[2 * (size_t) b + 1];
-            float const dist = a.distances[b];
-            float const w = a.weighted ? a.weights[b] : 1.0f;
-            Angles const ang = bond_angles(a.box, a.xyz, i, j, dist);
+            BondIn const cur = next;
+            if (b + 1 < end)
+            {
+                next = load_bond(a, b + 1);
+            }
+            float const w = cur.w;
+            Angles const ang = bond_angles(a.box, rx0, ry0, rz0, cur.px, cur.py, cur.pz, cur.dist);
             float sinpow = 1.0f;
+            float c = 1.0f, s = 0.0f; // exp(i m phi) by rotation, m = 0
 #pragma unroll
             for (int m = 0; m <= L; ++m)
             {
@@ -106,13 +143,14 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
                     j_cur = next;
                 }
                 float const legendre = sinpow * j_cur;                      // :272-281
-                float const amp = (float) ((double) legendre / 2.5066282746310002); // / sqrt(2 pi), :85-91
-                float s, c;
-                sincosf((float) m * ang.az, &s, &c); // exp(i m theta), :239-244
+                float const amp = (float) ((double) legendre * kInvSqrt2Pi); // / sqrt(2 pi), :85-91
                 float const phase = (m & 1) ? -1.0f : 1.0f; // Steinhardt.cc:47-49
-                re[m] += w * (phase * (amp * c));
+                re[m] += w * (phase * (amp * c));           // exp(i m theta), :239-244
                 im[m] += w * (phase * (amp * s));
                 sinpow *= ang.sphi;
+                float const cn = c * ang.caz - s * ang.saz;
+                s = s * ang.caz + c * ang.saz;
+                c = cn;
             }
             total_weight += w;
         }
@@ -199,17 +237,21 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
     }
     float total_weight = 0.0f;
     uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+    float const rx0 = a.xyz[3 * (size_t) i], ry0 = a.xyz[3 * (size_t) i + 1], rz0 = a.xyz[3 * (size_t) i + 2];
+    BondIn next = beg < end ? load_bond(a, beg) : BondIn {0, 0, 0, 0, 0};
     for (uint32_t b = beg; b < end; ++b)
     {
-        uint32_t const j = a.neighbors[2 * (size_t) b + 1];
-        float const dist = a.distances[b];
-        float const w = a.weighted ? a.weights[b] : 1.0f;
-        Angles const ang = bond_angles(a.box, a.xyz, i, j, dist);
+        BondIn const cur = next;
+        if (b + 1 < end)
+        {
+            next = load_bond(a, b + 1);
+        }
+        float const w = cur.w;
+        Angles const ang = bond_angles(a.box, rx0, ry0, rz0, cur.px, cur.py, cur.pz, cur.dist);
         float sinpow = 1.0f;
+        float c = 1.0f, s = 0.0f;
         for (int m = 0; m <= lmax; ++m)
         {
-            float s, c;
-            sincosf((float) m * ang.az, &s, &c);
             float const phase = (m & 1) ? -1.0f : 1.0f;
             float j_prev = 0.0f, j_cur = c_jac0[m];
             for (int lp = 0; lp <= lmax - m; ++lp)
@@ -228,13 +270,16 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
                 if (slot >= 0)
                 {
                     float const legendre = sinpow * j_cur;
-                    float const amp = (float) ((double) legendre / 2.5066282746310002);
+                    float const amp = (float) ((double) legendre * kInvSqrt2Pi);
                     int const o = 2 * (c_acc_off[slot] + m);
                     acc[o] += w * (phase * (amp * c));
                     acc[o + 1] += w * (phase * (amp * s));
                 }
             }
             sinpow *= ang.sphi;
+            float const cn = c * ang.caz - s * ang.saz;
+            s = s * ang.caz + c * ang.saz;
+            c = cn;
         }
         total_weight += w;
     }
@@ -478,7 +523,18 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
     {
         throw Error(FGPU_EINVALID, "Steinhardt: unsupported list of l values");
     }
-    upload_tables(ctx, lmax, ls);
+    {
+        // the tables live in __constant__ memory, one copy per device: upload only when the l list changes
+        static std::mutex mtx;
+        static std::map<int, std::vector<uint32_t>> resident;
+        std::lock_guard<std::mutex> lock(mtx);
+        auto it = resident.find(ctx->device);
+        if (it == resident.end() || it->second != ls)
+        {
+            upload_tables(ctx, lmax, ls);
+            resident[ctx->device] = ls;
+        }
+    }
     if (a.n == 0)
     {
         return;
