@@ -1468,7 +1468,17 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         FGPU_CUDA_CHECK(cudaMemsetAsync(d_sys.ptr, 0, tot_m * 2 * sizeof(double), ctx->stream));
         SteinhardtArgs a;
         a.box = pts->box;
+        a.rcp_lx = rounded_reciprocal(pts->box.Lx);
+        a.rcp_ly = rounded_reciprocal(pts->box.Ly);
+        a.rcp_lz = rounded_reciprocal(pts->box.Lz);
+        if (!pts->xyz4_ready)
+        {
+            pts->xyz4.reserve(pts->n);
+            launch_pad_positions(ctx, pts->xyz.ptr, pts->n, pts->xyz4.ptr);
+            pts->xyz4_ready = true;
+        }
         a.xyz = pts->xyz.ptr;
+        a.xyz4 = pts->xyz4.ptr;
         a.n = n;
         a.neighbors = nl->neighbors.ptr;
         a.distances = nl->distances.ptr;

@@ -167,6 +167,8 @@ struct fgpu_points
     float plane_dist[3];
     uint32_t n = 0;
     fgpu::DevBuf<float> xyz; // original order, n x 3
+    fgpu::DevBuf<float4> xyz4; // original order, padded; built on first use by Steinhardt (xyz4_ready)
+    bool xyz4_ready = false;
     fgpu_grid grid;
     int shard = 0, n_shards = 1; // > 1: this rank searches one share of the home tiles (self-query RDF only)
 };
@@ -439,7 +441,9 @@ void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n
 struct SteinhardtArgs
 {
     BoxDev box;
-    const float* xyz; // original order
+    float rcp_lx, rcp_ly, rcp_lz; // RN(1 / L), rounded on the host (wrap_quick)
+    const float* xyz;    // original order, n_points x 3
+    const float4* xyz4;  // the same, padded to 16 bytes (fgpu_points::xyz4)
     uint32_t n;
     const uint32_t* neighbors;
     const float* distances;
@@ -452,6 +456,7 @@ struct SteinhardtArgs
     double* sys_qlm; // concatenated per l, fp64 accumulators (re, im)
 };
 void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& args, const std::vector<uint32_t>& ls);
+void launch_pad_positions(fgpu_ctx* ctx, const float* xyz, uint32_t n, float4* out);
 
 // follow-up kernels over the per-particle q_lm array (the l tables of launch_steinhardt must be resident)
 struct SteinhardtAveArgs

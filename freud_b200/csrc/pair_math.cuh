@@ -41,6 +41,45 @@ __device__ __forceinline__ float dot_exact(float x, float y, float z)
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
+// a / L with y = RN(1 / L) rounded on the host: q0 = RN(a y), one fused correction makes the quotient faithful,
+// the second one makes it RN(a / L) (Markstein; the residuals a - L q are exact in an FMA) as long as nothing
+// underflows.  Five issue slots instead of the ~15 of __fdiv_rn.  Users state why their operands are in range.
+__device__ __forceinline__ float div_by_const(float a, float L, float y)
+{
+    float const q0 = __fmul_rn(a, y);
+    float const r0 = __fmaf_rn(-q0, L, a);
+    float const q1 = __fmaf_rn(r0, y, q0);
+    float const r1 = __fmaf_rn(-q1, L, a);
+    return __fmaf_rn(r1, y, q1);
+}
+
+// Box::wrap(v) with the three divisions done by div_by_const: the same result as wrap_exact except when a
+// fractional coordinate is so small that a residual underflows (|v - lo| below ~1e-30 L).  For consumers with a
+// tolerance (Steinhardt's 1e-5), not for bit-exact bond lists.
+__device__ __forceinline__ void wrap_quick(const BoxDev& b, float ylx, float yly, float ylz, float vx, float vy,
+                                           float vz, float& rx, float& ry, float& rz)
+{
+    float dx = __fsub_rn(vx, b.lox);
+    float dy = __fsub_rn(vy, b.loy);
+    float const dz = __fsub_rn(vz, b.loz);
+    dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(b.t_xz, vz), __fmul_rn(b.xy, vy)));
+    dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
+    float fx = div_by_const(dx, b.Lx, ylx);
+    float fy = div_by_const(dy, b.Ly, yly);
+    float fz = b.is2d ? 0.0f : div_by_const(dz, b.Lz, ylz);
+    fx = modulus_positive_one(fx);
+    fy = modulus_positive_one(fy);
+    fz = modulus_positive_one(fz);
+    float x = __fadd_rn(b.lox, __fmul_rn(fx, b.Lx));
+    float y = __fadd_rn(b.loy, __fmul_rn(fy, b.Ly));
+    float z = __fadd_rn(b.loz, __fmul_rn(fz, b.Lz));
+    x = __fadd_rn(x, __fadd_rn(__fmul_rn(b.xy, y), __fmul_rn(b.xz, z)));
+    y = __fadd_rn(y, __fmul_rn(b.yz, z));
+    rx = x;
+    ry = y;
+    rz = b.is2d ? 0.0f : z;
+}
+
 // r = Box::wrap(v), all axes periodic.
 __device__ __forceinline__ void wrap_exact(const BoxDev& b, float vx, float vy, float vz, float& rx, float& ry,
                                            float& rz)

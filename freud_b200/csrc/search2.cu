@@ -53,19 +53,8 @@ __device__ __forceinline__ bool in_window2(float r_sq, float r_max_sq, float r_m
     return r_sq < r_max_sq && r_sq >= r_min_sq; // LinkCell.cc:525, AABBQuery.cc:129
 }
 
-// Correctly rounded a / L for normal-range operands: q0 = RN(a * y) with y = RN(1 / L) (rounded on the host),
-// one fused correction makes the quotient faithful, the second one makes it RN(a / L) (Markstein's theorem;
-// the residuals a - L * q are exact in an FMA).  Replaces __fdiv_rn (x86 divss upstream, Box.h:248-250) at
-// 5 instead of ~15 issue slots.  Valid because stage 1 bounds |a| / L away from 0 (no underflow).
-__device__ __forceinline__ float div_by_const(float a, float L, float y)
-{
-    float const q0 = __fmul_rn(a, y);
-    float const r0 = __fmaf_rn(-q0, L, a);
-    float const q1 = __fmaf_rn(r0, y, q0);
-    float const r1 = __fmaf_rn(-q1, L, a);
-    return __fmaf_rn(r1, y, q1);
-}
-
+// Division by a box length: div_by_const (pair_math.cuh) replaces __fdiv_rn (x86 divss upstream, Box.h:248-250).
+// Exact here because stage 1 bounds |a| / L away from 0 (no underflow in the residuals).
 // util::modulusPositive(f, 1) = fmodf(fmodf(f, 1) + 1, 1) (freud/util/utils.h:29-32) for f in (-1, 2) whose
 // intermediate sum stays below 2: truncation is a compare (FSET), not an FRND.
 __device__ __forceinline__ float modulus_positive_one_small(float f)

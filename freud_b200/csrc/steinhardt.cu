@@ -37,6 +37,19 @@ constexpr int kSphLmax = 32;
 // rounding boundary.
 constexpr double kInvSqrt2Pi = 1.0 / 2.5066282746310002;
 constexpr int kThreads = 128;
+constexpr int kStageBonds = 1792; // bonds staged per pass by k_steinhardt_single: 5 floats each, 35 KB
+constexpr int kStageBatch = 7;    // gathers a thread keeps in flight while staging
+static_assert(kStageBonds % (kThreads * kStageBatch) == 0, "staging passes must tile the chunk");
+
+// positions padded to 16 bytes in the original order: one aligned load (one sector) per gathered neighbour
+__global__ void __launch_bounds__(256) k_pad_positions(const float* __restrict__ xyz, uint32_t n, float4* __restrict__ out)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        out[i] = make_float4(xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2], 0.0f);
+    }
+}
 
 // recurrence prefactors for lmax, laid out as the reference does: [0, lmax*(lmax+1)) first kind,
 // [lmax*(lmax+1), 2*lmax*(lmax+1)) second kind; index lmax*m + (l-1)
@@ -72,11 +85,12 @@ __device__ __forceinline__ BondIn load_bond(const SteinhardtArgs& a, uint32_t b)
     return in;
 }
 
-__device__ __forceinline__ Angles bond_angles(const BoxDev& box, float rx0, float ry0, float rz0, float px, float py,
-                                              float pz, float dist)
+__device__ __forceinline__ Angles bond_angles(const SteinhardtArgs& args, float rx0, float ry0, float rz0, float px,
+                                              float py, float pz, float dist)
 {
     float dx, dy, dz;
-    wrap_exact(box, __fsub_rn(px, rx0), __fsub_rn(py, ry0), __fsub_rn(pz, rz0), dx, dy, dz);
+    wrap_quick(args.box, args.rcp_lx, args.rcp_ly, args.rcp_lz, __fsub_rn(px, rx0), __fsub_rn(py, ry0), __fsub_rn(pz, rz0), dx, dy,
+               dz);
     // The reference takes phi = atan2(y, x) and theta = acos(clamp(z / d)) (Steinhardt.cc:161-174) and the
     // evaluator immediately goes back to sin/cos of both (spherical_harmonics.hpp:239-244, :272-281).  Here the
     // sines and cosines come straight from the components -- cos(theta) = clamp(z / d), sin(theta) =
@@ -110,20 +124,64 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
     }
     float total_weight = 0.0f;
     bool const active = i < a.n;
+    // The bonds of the block's particles are one contiguous range of the list.  The block stages them chunk by
+    // chunk in shared memory -- coalesced reads of the index and distance arrays, one independent gather of the
+    // neighbour's position per thread -- and only then walks its rows: the per-row loop is a chain of dependent
+    // loads otherwise (index -> position), twelve deep, with nothing to overlap it.
+    __shared__ float s_px[kStageBonds], s_py[kStageBonds], s_pz[kStageBonds], s_dist[kStageBonds], s_w[kStageBonds];
+    uint32_t const i0 = blockIdx.x * blockDim.x, i1 = min(i0 + blockDim.x, a.n);
+    uint32_t const block_beg = a.row_start[i0], block_end = a.row_start[i1];
+    uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
+    float rx0 = 0.0f, ry0 = 0.0f, rz0 = 0.0f;
     if (active)
     {
-        uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
-        float const rx0 = a.xyz[3 * (size_t) i], ry0 = a.xyz[3 * (size_t) i + 1], rz0 = a.xyz[3 * (size_t) i + 2];
-        BondIn next = beg < end ? load_bond(a, beg) : BondIn {0, 0, 0, 0, 0};
-        for (uint32_t b = beg; b < end; ++b)
+        rx0 = a.xyz[3 * (size_t) i];
+        ry0 = a.xyz[3 * (size_t) i + 1];
+        rz0 = a.xyz[3 * (size_t) i + 2];
+    }
+    for (uint32_t c0 = block_beg; c0 < block_end; c0 += kStageBonds)
+    {
+        uint32_t const c1 = min(c0 + (uint32_t) kStageBonds, block_end);
+        __syncthreads();
+        // seven bonds per thread at a time: all indices first, then all gathers (16-byte padded positions, one
+        // sector each), then the stores -- the hardware issues in order, so a gather that is consumed right
+        // away would leave one chain in flight per warp
+#pragma unroll
+        for (int h = 0; h < kStageBonds / kThreads / kStageBatch; ++h)
         {
-            BondIn const cur = next;
-            if (b + 1 < end)
+            uint32_t jj[kStageBatch];
+            float4 pp[kStageBatch];
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
             {
-                next = load_bond(a, b + 1);
+                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
+                jj[k] = b < c1 ? a.neighbors[2 * (size_t) b + 1] : 0U;
             }
-            float const w = cur.w;
-            Angles const ang = bond_angles(a.box, rx0, ry0, rz0, cur.px, cur.py, cur.pz, cur.dist);
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
+            {
+                pp[k] = __ldg(a.xyz4 + jj[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
+            {
+                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
+                if (b < c1)
+                {
+                    s_px[b - c0] = pp[k].x;
+                    s_py[b - c0] = pp[k].y;
+                    s_pz[b - c0] = pp[k].z;
+                    s_dist[b - c0] = a.distances[b];
+                    s_w[b - c0] = a.weighted ? a.weights[b] : 1.0f;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t const lo = max(beg, c0), hi = min(end, c1);
+        for (uint32_t b = lo; b < hi; ++b)
+        {
+            float const w = s_w[b - c0];
+            Angles const ang = bond_angles(a, rx0, ry0, rz0, s_px[b - c0], s_py[b - c0], s_pz[b - c0], s_dist[b - c0]);
             float sinpow = 1.0f;
             float c = 1.0f, s = 0.0f; // exp(i m phi) by rotation, m = 0
 #pragma unroll
@@ -247,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
             next = load_bond(a, b + 1);
         }
         float const w = cur.w;
-        Angles const ang = bond_angles(a.box, rx0, ry0, rz0, cur.px, cur.py, cur.pz, cur.dist);
+        Angles const ang = bond_angles(a, rx0, ry0, rz0, cur.px, cur.py, cur.pz, cur.dist);
         float sinpow = 1.0f;
         float c = 1.0f, s = 0.0f;
         for (int m = 0; m <= lmax; ++m)
@@ -558,6 +616,19 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
     {
         k_steinhardt_generic<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, lmax, (int) ls.size(),
                                                                                              n_acc, tot_m);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_pad_positions(fgpu_ctx* ctx, const float* xyz, uint32_t n, float4* out)
+{
+    if (n == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "pad_positions");
+        k_pad_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(xyz, n, out);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
