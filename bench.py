@@ -151,7 +151,9 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
         "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
         "pipeline": 16 * (n + n) + 28 * n_bonds + 8 * n,  # SURVEY.md section 8d "NL emit"
     }
-    return dict(step_dev=step_dev, step_e2e=step_e2e, units=evals, unit="pair_evals/s",
+    # measured DRAM bytes per launch (ncu, profiles/ncu_r1_v6_summary.md): only for the configuration it was taken on
+    traffic = {"search_nl": 22736384 + 99777536, "emit": 225808896 + 208339968} if n == 1_000_000 and r_max == 3.0 else {}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=evals, unit="pair_evals/s", traffic=traffic,
                 metric="neighbour_pair_evals_per_sec",
                 config={"workload": f"LinkCell NeighborList r_max={r_max:g} exclude_ii N={n} cubic L={L:.4f} rho=0.08 "
                                     f"flavour={'wrap' if flavour == WRAP else 'image'}",
@@ -469,7 +471,11 @@ def main():
         if algo:
             achieved = algo / (avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(achieved / peak, 4), "traffic": None, "avg_launch_ms": round(avg_ms, 4),
+                        "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(name),
+                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                          "capture of this workload (profiles/ncu_r1_v6_summary.md)"
+                        if w.get("traffic", {}).get(name) else None,
+                        "avg_launch_ms": round(avg_ms, 4),
                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
                         "share_of_step": round(ms / dev_ms, 3),
                         "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in per_kernel.items()}}
