@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreud_b200.so")
 
-FLAVOUR_WRAP, FLAVOUR_IMAGE = 0, 1
+FLAVOUR_WRAP, FLAVOUR_IMAGE, FLAVOUR_GHOST = 0, 1, 2
 ST_WEIGHTED, ST_AVERAGE, ST_WL, ST_WL_NORMALIZE = 1, 2, 4, 8
 UNIQUE_ID_BYTES = 128
 

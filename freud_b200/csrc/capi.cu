@@ -194,17 +194,21 @@ QueryView prepare_queries(fgpu_points* pts, const float* q_host, const float* q_
 
 void validate_ball(const fgpu_points* pts, int flavour, float r_max, float r_min)
 {
-    require(flavour == FGPU_FLAVOUR_WRAP || flavour == FGPU_FLAVOUR_IMAGE, FGPU_EINVALID, "unknown flavour");
+    require(flavour == FGPU_FLAVOUR_WRAP || flavour == FGPU_FLAVOUR_IMAGE || flavour == FGPU_FLAVOUR_GHOST,
+            FGPU_EINVALID, "unknown flavour");
     // NeighborQueryPerPointIterator ctor, NeighborQuery.h:321-328
     require(r_max > 0, FGPU_EINVALID, "NeighborQuery requires r_max to be positive.");
     require(r_max > r_min, FGPU_EINVALID, "NeighborQuery requires that r_max must be greater than r_min.");
-    if (flavour == FGPU_FLAVOUR_IMAGE)
+    if (flavour != FGPU_FLAVOUR_WRAP)
     {
-        // updateImageVectors, NeighborQuery.h:503-510 (all axes periodic)
+        // updateImageVectors, NeighborQuery.h:503-510 (all axes periodic); CellQuery::validateQueryArgs,
+        // CellQuery.h:186-192
         double const two_r = (double) r_max * 2.0;
         bool const too_large = pts->plane_dist[0] <= two_r || pts->plane_dist[1] <= two_r
             || (!pts->box.is2d && pts->plane_dist[2] <= two_r);
-        require(!too_large, FGPU_ERUNTIME, "The AABBQuery r_max is too large for this box.");
+        require(!too_large, FGPU_ERUNTIME,
+                flavour == FGPU_FLAVOUR_IMAGE ? "The AABBQuery r_max is too large for this box."
+                                              : "The CellQuery r_max is too large for this box.");
     }
 }
 
@@ -823,12 +827,17 @@ static void points_create_impl(fgpu_ctx* ctx, const float* box6, int is2d, const
     p->n = n;
     if (host != nullptr && p->box.is2d)
     {
-        // NeighborQuery.h:103-112
+        // NeighborQuery.h:103-112; a max-reduction first (vectorisable), the throw after the loop
+        float zmax = 0.0f;
+        bool nan_seen = false;
         for (uint32_t i = 0; i < n; ++i)
         {
-            require(!(std::fabs(host[3 * (size_t) i + 2]) > 1e-6), FGPU_EINVALID,
-                    "A point with z != 0 was provided in a 2D box.");
+            float const z = std::fabs(host[3 * (size_t) i + 2]);
+            zmax = z > zmax ? z : zmax;
+            nan_seen |= z != z;
         }
+        (void) nan_seen; // upstream's test is abs(z) > 1e-6, which a NaN passes
+        require(!(zmax > 1e-6), FGPU_EINVALID, "A point with z != 0 was provided in a 2D box.");
     }
     p->xyz.reserve((size_t) n * 3);
     if (host != nullptr)
@@ -950,6 +959,10 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
 {
     return guarded([&] {
         require(pts != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        // CellQuery::validateQueryArgs, CellQuery.h:180-184
+        require(flavour != FGPU_FLAVOUR_GHOST, FGPU_ERUNTIME,
+                "CellQuery only supports ball queries (r_max), not nearest queries (num_neighbors). Use AABBQuery "
+                "for nearest neighbor queries.");
         require(flavour == FGPU_FLAVOUR_WRAP || flavour == FGPU_FLAVOUR_IMAGE, FGPU_EINVALID, "unknown flavour");
         bool const wrap = flavour == FGPU_FLAVOUR_WRAP;
         fgpu_ctx* ctx = pts->ctx;

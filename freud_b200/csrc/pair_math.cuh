@@ -121,6 +121,61 @@ __device__ __forceinline__ void image_vector(const BoxDev& b, int i, int j, int 
     iz = __fadd_rn(__fadd_rn(__fmul_rn(fi, 0.0f), __fmul_rn(fj, 0.0f)), __fmul_rn(fk, b.cz));
 }
 
+// CellQuery's ghost displacement for a point seen across w = (wx, wy, wz) boundaries (CellQuery.h:246-262):
+// shift = 0, then += +-a, += +-b, += +-c for the non-zero components, with a = (Lx, 0, 0), b = (Ly xy, Ly, 0),
+// c = (Lz xz, Lz yz, Lz) (Box.h:503-518) and component-wise float adds.
+__device__ __forceinline__ void ghost_shift(const BoxDev& b, int wx, int wy, int wz, float& sx, float& sy, float& sz)
+{
+    sx = sy = sz = 0.0f;
+    if (wx != 0)
+    {
+        float const sg = wx > 0 ? 1.0f : -1.0f;
+        sx = __fadd_rn(sx, sg * b.ax);
+        sy = __fadd_rn(sy, sg * 0.0f);
+        sz = __fadd_rn(sz, sg * 0.0f);
+    }
+    if (wy != 0)
+    {
+        float const sg = wy > 0 ? 1.0f : -1.0f;
+        sx = __fadd_rn(sx, sg * b.bx);
+        sy = __fadd_rn(sy, sg * b.by);
+        sz = __fadd_rn(sz, sg * 0.0f);
+    }
+    if (wz != 0)
+    {
+        float const sg = wz > 0 ? 1.0f : -1.0f;
+        sx = __fadd_rn(sx, sg * b.cx);
+        sy = __fadd_rn(sy, sg * b.cy);
+        sz = __fadd_rn(sz, sg * b.cz);
+    }
+}
+
+// Bond vector of candidate p and query q when the QUERY is taken in image k (the candidate sits across w = -k
+// boundaries).  IMAGE: r = p - (q + image_k), AABBQuery.cc:93,125.  GHOST: r = (p + shift_w) - q,
+// CellQuery.cc:107 + CellIterator.h:167.  (WRAP never gets here: it wraps the difference.)
+template<int FLAVOUR>
+__device__ __forceinline__ void image_pair(const BoxDev& b, float px, float py, float pz, float qx, float qy, float qz,
+                                           int kx, int ky, int kz, float& rx, float& ry, float& rz)
+{
+    if (FLAVOUR == FGPU_FLAVOUR_GHOST)
+    {
+        float sx, sy, sz;
+        ghost_shift(b, -kx, -ky, -kz, sx, sy, sz);
+        bool const real = kx == 0 && ky == 0 && kz == 0; // a real point is stored as it is, CellQuery.cc:121
+        rx = __fsub_rn(real ? px : __fadd_rn(px, sx), qx);
+        ry = __fsub_rn(real ? py : __fadd_rn(py, sy), qy);
+        rz = __fsub_rn(real ? pz : __fadd_rn(pz, sz), qz);
+    }
+    else
+    {
+        float ix, iy, iz;
+        image_vector(b, kx, ky, kz, ix, iy, iz);
+        rx = __fsub_rn(px, __fadd_rn(qx, ix));
+        ry = __fsub_rn(py, __fadd_rn(qy, iy));
+        rz = __fsub_rn(pz, __fadd_rn(qz, iz));
+    }
+}
+
 // Fractional coordinates for CELL ASSIGNMENT only (candidate generation is conservative);
 // any consistent arithmetic works, the cell width carries a margin for its rounding.
 __device__ __forceinline__ void fractional_for_cells(const BoxDev& b, float vx, float vy, float vz, float& fx,

@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                                                OnHit&& on_hit)
 {
     uint32_t evals = 0;
-    bool const any_shift = FLAVOUR == FGPU_FLAVOUR_IMAGE && *g.any_shift_flag != 0;
+    bool const any_shift = FLAVOUR != FGPU_FLAVOUR_WRAP && *g.any_shift_flag != 0;
     if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
     {
         qz = 0.0f; // AABBQuery.cc:84-87
@@ -88,20 +88,19 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                         {
                             continue;
                         }
-                        float ix_, iy_, iz_;
-                        image_vector(box, kx, ky, kz, ix_, iy_, iz_);
-                        float const qix = __fadd_rn(qx, ix_), qiy = __fadd_rn(qy, iy_), qiz = __fadd_rn(qz, iz_);
                         for (uint32_t s = beg; s < end; ++s)
                         {
                             float4 const p = __ldg(g.sorted + s);
                             uint32_t const j = __float_as_uint(p.w);
                             if (exclude_ii && j == q_global)
                             {
-                                continue; // AABBQuery.cc:111-115
+                                continue; // AABBQuery.cc:111-115, CellIterator.h:160-163
                             }
                             ++evals;
-                            float const pz = box.is2d ? 0.0f : p.z; // AABBQuery.cc:118-122
-                            float const rx = __fsub_rn(p.x, qix), ry = __fsub_rn(p.y, qiy), rz = __fsub_rn(pz, qiz);
+                            // AABBQuery.cc:118-122 zeroes z in 2-D boxes, CellQuery does not
+                            float const pz = FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d ? 0.0f : p.z;
+                            float rx, ry, rz;
+                            image_pair<FLAVOUR>(box, p.x, p.y, pz, qx, qy, qz, kx, ky, kz, rx, ry, rz);
                             float const r_sq = dot_exact(rx, ry, rz);
                             if (in_window(r_sq, r_max_sq, r_min_sq))
                             {
@@ -128,7 +127,7 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                             int const kx0 = wx == 2 ? -1 : njx - nqx - wx, kx1 = wx == 2 ? 1 : kx0;
                             int const ky0 = wy == 2 ? -1 : njy - nqy - wy, ky1 = wy == 2 ? 1 : ky0;
                             int const kz0 = wz == 2 ? -1 : njz - nqz - wz, kz1 = wz == 2 ? 1 : kz0;
-                            float const pz = box.is2d ? 0.0f : p.z;
+                            float const pz = FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d ? 0.0f : p.z;
                             for (int kx = max(kx0, -1); kx <= min(kx1, 1); ++kx)
                             {
                                 for (int ky = max(ky0, -1); ky <= min(ky1, 1); ++ky)
@@ -136,11 +135,8 @@ __device__ __forceinline__ uint32_t visit_hits(const BoxDev& box, const GridDev&
                                     for (int kz = max(kz0, -1); kz <= min(kz1, 1); ++kz)
                                     {
                                         ++evals;
-                                        float ix_, iy_, iz_;
-                                        image_vector(box, kx, ky, kz, ix_, iy_, iz_);
-                                        float const rx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
-                                        float const ry = __fsub_rn(p.y, __fadd_rn(qy, iy_));
-                                        float const rz = __fsub_rn(pz, __fadd_rn(qz, iz_));
+                                        float rx, ry, rz;
+                                        image_pair<FLAVOUR>(box, p.x, p.y, pz, qx, qy, qz, kx, ky, kz, rx, ry, rz);
                                         float const r_sq = dot_exact(rx, ry, rz);
                                         if (in_window(r_sq, r_max_sq, r_min_sq))
                                         {
@@ -296,8 +292,8 @@ template<int FLAVOUR> __global__ void __launch_bounds__(256) k_emit(EmitArgs a)
         // the image that produced the hit is the only one inside the window (plane distance > 2 r_max is
         // enforced, NeighborQuery.h:503-510); walk the images in the reference's order and take it
         float const r_max_sq = __fmul_rn(a.r_max, a.r_max), r_min_sq = __fmul_rn(a.r_min, a.r_min);
-        float const pz = a.box.is2d ? 0.0f : p.z;
-        if (a.box.is2d)
+        float const pz = FLAVOUR == FGPU_FLAVOUR_IMAGE && a.box.is2d ? 0.0f : p.z;
+        if (FLAVOUR == FGPU_FLAVOUR_IMAGE && a.box.is2d)
         {
             qz = 0.0f;
         }
@@ -318,11 +314,8 @@ template<int FLAVOUR> __global__ void __launch_bounds__(256) k_emit(EmitArgs a)
             {
                 continue;
             }
-            float ix_, iy_, iz_;
-            image_vector(a.box, i, j, k, ix_, iy_, iz_);
-            float const tx = __fsub_rn(p.x, __fadd_rn(qx, ix_));
-            float const ty = __fsub_rn(p.y, __fadd_rn(qy, iy_));
-            float const tz = __fsub_rn(pz, __fadd_rn(qz, iz_));
+            float tx, ty, tz;
+            image_pair<FLAVOUR>(a.box, p.x, p.y, pz, qx, qy, qz, i, j, k, tx, ty, tz);
             float const t_sq = dot_exact(tx, ty, tz);
             if (in_window(t_sq, r_max_sq, r_min_sq))
             {
@@ -437,7 +430,14 @@ void launch_search(fgpu_ctx* ctx, int flavour, SearchMode mode, const SearchArgs
     }
     else
     {
-        launch_search_mode<FGPU_FLAVOUR_IMAGE>(ctx, mode, args);
+        if (flavour == FGPU_FLAVOUR_GHOST)
+        {
+            launch_search_mode<FGPU_FLAVOUR_GHOST>(ctx, mode, args);
+        }
+        else
+        {
+            launch_search_mode<FGPU_FLAVOUR_IMAGE>(ctx, mode, args);
+        }
     }
 }
 
@@ -456,7 +456,14 @@ void launch_emit(fgpu_ctx* ctx, int flavour, const EmitArgs& a)
         }
         else
         {
-            k_emit<FGPU_FLAVOUR_IMAGE><<<blocks, 256, 0, ctx->stream>>>(a);
+            if (flavour == FGPU_FLAVOUR_GHOST)
+            {
+                k_emit<FGPU_FLAVOUR_GHOST><<<blocks, 256, 0, ctx->stream>>>(a);
+            }
+            else
+            {
+                k_emit<FGPU_FLAVOUR_IMAGE><<<blocks, 256, 0, ctx->stream>>>(a);
+            }
         }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
     float const knn_r_min = a.knn_r_min;
     // NeighborList mode always filters first and decides on dense lanes (stage 2); the fused RDF of the IMAGE
     // flavour decides inline, its exact test being as cheap as the filter
-    constexpr bool FILTERED = FLAVOUR == FGPU_FLAVOUR_WRAP || MODE == S2_NL;
+    constexpr bool FILTERED = FLAVOUR != FGPU_FLAVOUR_IMAGE || MODE == S2_NL;
     int const dx = a.dx, dy = a.dy, dz = a.dz;
     uint32_t q_len = 0;     // stage-2 stack height
     uint32_t o_len = 0;     // NL: buffered hits of the current batch
@@ -246,6 +246,19 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
                 {
                     wrap_fast<TRI>(box, a.rcp_lx, a.rcp_ly, a.rcp_lz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y),
                                    __fsub_rn(p.z, q.z), rx, ry, rz); // LinkCell.cc:522
+                }
+                else if (FLAVOUR == FGPU_FLAVOUR_GHOST)
+                {
+                    // r = (p + shift) - q with the ghost displacement of the crossed boundaries (none: + 0),
+                    // CellQuery.cc:107, CellIterator.h:167
+                    uint32_t const cd = ent.y >> 8;
+                    float sx, sy, sz;
+                    ghost_shift(box, (int) (cd & 3U) - 1, (int) ((cd >> 2) & 3U) - 1, (int) ((cd >> 4) & 3U) - 1, sx, sy,
+                                sz);
+                    bool const real = cd == tile::kNoWrap; // a real point is stored as it is, CellQuery.cc:121
+                    rx = __fsub_rn(real ? p.x : __fadd_rn(p.x, sx), q.x);
+                    ry = __fsub_rn(real ? p.y : __fadd_rn(p.y, sy), q.y);
+                    rz = __fsub_rn(real ? p.z : __fadd_rn(p.z, sz), q.z);
                 }
                 else
                 {
@@ -774,6 +787,13 @@ void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a)
             FGPU_S2(FGPU_FLAVOUR_WRAP, S2_NL);
         else
             FGPU_S2(FGPU_FLAVOUR_WRAP, S2_RDF);
+    }
+    else if (flavour == FGPU_FLAVOUR_GHOST)
+    {
+        if (mode == S2_NL)
+            launch_one<FGPU_FLAVOUR_GHOST, S2_NL, false>(ctx, a, name);
+        else
+            launch_one<FGPU_FLAVOUR_GHOST, S2_RDF, false>(ctx, a, name);
     }
     else
     {

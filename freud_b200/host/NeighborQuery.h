@@ -321,6 +321,33 @@ public:
     {}
 };
 
+// CellQuery (freud/locality/CellQuery.h:29): ghost particles on a Cartesian grid upstream; by equivalence E5 its
+// ball query is the bond set r = (p_j + shift_w) - q over the lattice displacements, reproduced bit for bit by the
+// GHOST flavour.  Ball queries only (CellQuery.h:180-184).
+class CellQuery : public NeighborQuery
+{
+public:
+    CellQuery(const box::Box& box, const vec3<float>* points, unsigned int n_points)
+        : NeighborQuery(box, points, n_points, FGPU_FLAVOUR_GHOST)
+    {}
+
+    // CellQuery::validateQueryArgs, CellQuery.h:177-203: raised by query(), before anything runs
+    void validateQueryArgs(QueryArgs& args) const override
+    {
+        NeighborQuery::validateQueryArgs(args);
+        if (args.mode == QueryType::nearest)
+        {
+            throw std::runtime_error("CellQuery only supports ball queries (r_max), not nearest queries "
+                                     "(num_neighbors). Use AABBQuery for nearest neighbor queries.");
+        }
+        vec3<float> const pd = m_box.getNearestPlaneDistance();
+        if ((pd.x <= args.r_max * 2.0F) || (pd.y <= args.r_max * 2.0F) || (!m_box.is2D() && pd.z <= args.r_max * 2.0F))
+        {
+            throw std::runtime_error("The CellQuery r_max is too large for this box.");
+        }
+    }
+};
+
 // RawPoints (freud/locality/RawPoints.h:35-73): upstream builds an AABBQuery lazily on the first query.
 class RawPoints : public NeighborQuery
 {

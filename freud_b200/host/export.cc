@@ -191,6 +191,13 @@ PYBIND11_MODULE(_freud_b200, m)
                  return std::make_shared<locality::AABBQuery>(b, p, n);
              }),
              py::arg("box"), py::arg("points"), py::keep_alive<1, 3>());
+    py::class_<locality::CellQuery, locality::NeighborQuery, std::shared_ptr<locality::CellQuery>>(mloc, "CellQuery")
+        .def(py::init([](const box::Box& b, points_array pts) {
+                 unsigned int n = 0;
+                 const vec3<float>* p = as_vec3(pts, n);
+                 return std::make_shared<locality::CellQuery>(b, p, n);
+             }),
+             py::arg("box"), py::arg("points"), py::keep_alive<1, 3>());
     py::class_<locality::RawPoints, locality::NeighborQuery, std::shared_ptr<locality::RawPoints>>(mloc, "RawPoints")
         .def(py::init([](const box::Box& b, points_array pts) {
                  unsigned int n = 0;

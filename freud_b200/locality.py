@@ -122,6 +122,15 @@ class AABBQuery(NeighborQuery):
         self._cpp_obj = _ext()._locality.AABBQuery(_cpp_box(self._box), self._points)
 
 
+class CellQuery(NeighborQuery):
+    """freud/locality.py:900-921: ball queries only, in CellQuery's own (ghost-shift) float32 arithmetic."""
+
+    def __init__(self, box, points):
+        self._box = Box.from_box(box)
+        self._points = _points(points).copy()
+        self._cpp_obj = _ext()._locality.CellQuery(_cpp_box(self._box), self._points)
+
+
 class LinkCell(NeighborQuery):
     """freud/locality.py:872-921."""
 

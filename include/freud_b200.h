@@ -41,6 +41,8 @@ extern "C" {
 /* Pair-distance arithmetic ("flavour"), SURVEY.md fact 2 */
 #define FGPU_FLAVOUR_WRAP 0  /* LinkCell:  r = Box::wrap(p_j - q)        freud/locality/LinkCell.cc:522 */
 #define FGPU_FLAVOUR_IMAGE 1 /* AABBQuery: r = p_j - (q + image_k)       freud/locality/AABBQuery.cc:93,125 */
+#define FGPU_FLAVOUR_GHOST 2 /* CellQuery: r = (p_j + shift_k) - q       freud/locality/CellQuery.cc:107,
+                                freud/locality/CellIterator.h:167; ball queries only, every point inside the box */
 
 typedef struct fgpu_ctx fgpu_ctx;       /* one GPU + one stream + scratch memory            */
 typedef struct fgpu_points fgpu_points; /* device-resident reference points + box + cell list */

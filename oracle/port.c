@@ -16,6 +16,9 @@
  *   E1  LinkCell ball query   == { (i,j) : r = Box::wrap(p_j - q_i), r_min^2 <= r.r < r_max^2 }
  *   E2  AABBQuery ball query  == { (i,j,k) : r = p_j - (q_i + image_k), same window }, 27 (9) images
  *   E3  AABBQuery kNN         == k smallest closest-image distances in the E2 arithmetic
+ *   E5  CellQuery ball query  == { (i,j,w) : r = (p_j + shift_w) - q_i, same window }, shift_w the ghost
+ *       displacement of CellQuery.h:246-262 (points and queries inside the box, r_max <= the r_max the grid
+ *       was built for)
  * so candidate generation (the cell grid below) is free to differ from the reference's as long as it
  * is conservative.
  */
@@ -26,6 +29,7 @@
 
 #define FLAVOUR_WRAP 0  /* LinkCell:  freud/locality/LinkCell.cc:522 */
 #define FLAVOUR_IMAGE 1 /* AABBQuery: freud/locality/AABBQuery.cc:93,125 */
+#define FLAVOUR_GHOST 2 /* CellQuery: freud/locality/CellQuery.cc:107, CellIterator.h:167 */
 
 typedef struct
 {
@@ -150,6 +154,29 @@ static float dot3(const float r[3])
 }
 
 /* freud/locality/NeighborQuery.h:496-564: image k = i*a + j*b + k*c, image 0 first */
+/* CellQuery::generateGhosts' displacement for a point seen across w boundaries (CellQuery.h:246-262): shift = 0,
+ * then += +-a, += +-b, += +-c for the non-zero components (vec3 adds, component by component).  The query image
+ * k of box_images corresponds to w = -k. */
+static void ghost_shift(const box_t* b, const int w[3], float sh[3])
+{
+    float a[3] = {b->Lx, 0.0f, 0.0f};
+    float bb[3] = {b->Ly * b->xy, b->Ly, 0.0f};
+    float c[3] = {b->Lz * b->xz, b->Lz * b->yz, b->Lz};
+    const float* vec[3] = {a, bb, c};
+    sh[0] = sh[1] = sh[2] = 0.0f;
+    for (int d = 0; d < 3; ++d)
+    {
+        if (w[d] != 0)
+        {
+            for (int e = 0; e < 3; ++e)
+            {
+                float v = w[d] > 0 ? vec[d][e] : -vec[d][e];
+                sh[e] = sh[e] + v;
+            }
+        }
+    }
+}
+
 static int box_images(const box_t* b, float img[27][3], int ijk[27][3])
 {
     float a[3] = {b->Lx, 0.0f, 0.0f};
@@ -466,7 +493,8 @@ static int ball_hits(const box_t* b, const grid_t* g, int flavour, const float* 
                     }
                     else
                     {
-                        float p[3] = {pj[0], pj[1], b->is2d ? 0.0f : pj[2]}; /* AABBQuery.cc:118-122 */
+                        /* AABBQuery.cc:118-122 zeroes z in 2-D boxes; CellQuery takes the points as they are */
+                        float p[3] = {pj[0], pj[1], (flavour == FLAVOUR_IMAGE && b->is2d) ? 0.0f : pj[2]};
                         const int* nj = g->shift + 3 * (size_t) j;
                         int w[3] = {wx[ix], wy[iy], wz[iz]};
                         for (int k = 0; k < n_img; ++k)
@@ -483,8 +511,27 @@ static int ball_hits(const box_t* b, const grid_t* g, int flavour, const float* 
                             {
                                 continue;
                             }
-                            float qk[3] = {q[0] + img[k][0], q[1] + img[k][1], q[2] + img[k][2]};
-                            float r[3] = {p[0] - qk[0], p[1] - qk[1], p[2] - qk[2]};
+                            float r[3];
+                            if (flavour == FLAVOUR_GHOST)
+                            {
+                                /* ghost = point + shift (CellQuery.cc:107), a real point is stored as it is (:121);
+                                 * delta = ghost - query (CellIterator.h:167) */
+                                int wk[3] = {-ijk[k][0], -ijk[k][1], -ijk[k][2]};
+                                float sh[3];
+                                ghost_shift(b, wk, sh);
+                                for (int d = 0; d < 3; ++d)
+                                {
+                                    float gpos = k == 0 ? p[d] : p[d] + sh[d];
+                                    r[d] = gpos - q[d];
+                                }
+                            }
+                            else
+                            {
+                                float qk[3] = {q[0] + img[k][0], q[1] + img[k][1], q[2] + img[k][2]};
+                                r[0] = p[0] - qk[0];
+                                r[1] = p[1] - qk[1];
+                                r[2] = p[2] - qk[2];
+                            }
                             float r_sq = dot3(r);
                             if (r_sq < r_max_sq && r_sq >= r_min_sq)
                             {

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreud_port.so")
-WRAP, IMAGE = 0, 1
+WRAP, IMAGE, GHOST = 0, 1, 2
 _fp = C.POINTER(C.c_float)
 _up = C.POINTER(C.c_uint32)
 _lib = None

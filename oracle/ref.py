@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libfreud_ref.so")
 
-ENGINE_LINKCELL, ENGINE_AABB, ENGINE_RAW = 0, 1, 2
+ENGINE_LINKCELL, ENGINE_AABB, ENGINE_RAW, ENGINE_CELL = 0, 1, 2, 3
 MODE_NONE, MODE_BALL, MODE_NEAREST = 0, 1, 2
 DEFAULT_NUM_NEIGHBORS = 0xFFFFFFFF
 
@@ -147,13 +147,13 @@ def _qargs(mode=None, num_neighbors=None, r_max=None, r_min=0.0, r_guess=None, s
 
 
 class Query:
-    """LinkCell / AABBQuery / RawPoints of the reference."""
+    """LinkCell / AABBQuery / RawPoints / CellQuery of the reference."""
 
     def __init__(self, engine, box, points, is2d=False, cell_width=0.0):
         self.points = _f32(points, 3)
         self.box = box6(box)
         self.is2d = bool(is2d)
-        eng = {"linkcell": ENGINE_LINKCELL, "aabb": ENGINE_AABB, "raw": ENGINE_RAW}[engine]
+        eng = {"linkcell": ENGINE_LINKCELL, "aabb": ENGINE_AABB, "raw": ENGINE_RAW, "cell": ENGINE_CELL}[engine]
         self._h = lib().fref_nq_create(eng, _p(self.box), int(self.is2d), _p(self.points), len(self.points),
                                        float(cell_width))
         if not self._h:

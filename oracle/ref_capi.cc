@@ -7,6 +7,7 @@
 // Reference classes driven:
 //   freud::box::Box                                  freud/box/Box.h:44
 //   freud::locality::{LinkCell,AABBQuery,RawPoints}  freud/locality/LinkCell.h:188, AABBQuery.h:42, RawPoints.h:35
+//   freud::locality::CellQuery                       freud/locality/CellQuery.h:29
 //   NeighborQuery::query / toNeighborList            freud/locality/NeighborQuery.h:130,434
 //   freud::density::RDF                              freud/density/RDF.h:33
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
@@ -21,6 +22,7 @@
 
 #include "AABBQuery.h"
 #include "Box.h"
+#include "CellQuery.h"
 #include "LinkCell.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
@@ -149,7 +151,7 @@ int fref_box_info(const float* box6, int is2d, float* volume, float* plane_dist3
 }
 
 // ---- NeighborQuery --------------------------------------------------------------------------------
-// engine: 0 LinkCell, 1 AABBQuery, 2 RawPoints
+// engine: 0 LinkCell, 1 AABBQuery, 2 RawPoints, 3 CellQuery
 void* fref_nq_create(int engine, const float* box6, int is2d, const float* pts, unsigned n, float cell_width)
 {
     QueryHandle* h = nullptr;
@@ -165,6 +167,10 @@ void* fref_nq_create(int engine, const float* box6, int is2d, const float* pts, 
         else if (engine == 1)
         {
             handle->nq = std::make_shared<freud::locality::AABBQuery>(box, handle->points.data(), n);
+        }
+        else if (engine == 3)
+        {
+            handle->nq = std::make_shared<freud::locality::CellQuery>(box, handle->points.data(), n);
         }
         else
         {

@@ -193,6 +193,31 @@ def test_steinhardt_vs_reference_noisy_fcc():
         np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
 
 
+def test_cellquery_engine():
+    """freud.locality.CellQuery (tests/test_locality_neighbor_query.py:697-811 upstream): ball queries in its own
+    arithmetic, nearest-neighbour queries refused with the reference's message, r_max validated against the box."""
+    box, n, r = BOXES["tri1"]
+    pts, q = random_points(box, n, seed=61), random_points(box, 300, seed=62)
+    cq = locality.CellQuery(box, pts)
+    for sbd in (False, True):
+        nl = cq.query(q, dict(r_max=r, r_min=0.5)).toNeighborList(sort_by_distance=sbd)
+        assert_matches_oracle(nl, port.ball_nlist(port.GHOST, box, False, pts, q, r, 0.5, False, sbd), f"cellquery {sbd}")
+    nl = cq.query(pts, dict(r_max=r, exclude_ii=True)).toNeighborList()
+    assert_matches_oracle(nl, port.ball_nlist(port.GHOST, box, False, pts, pts, r, 0.0, True), "cellquery self")
+    if ref.available():
+        want = ref.Query("cell", box, pts).nlist(pts, r_max=r, exclude_ii=True)
+        assert_matches_oracle(nl, want, "cellquery vs the reference")
+    with pytest.raises(RuntimeError, match="CellQuery only supports"):  # raised when the lazy result is consumed
+        list(cq.query(q, dict(mode="nearest", num_neighbors=3)))
+    with pytest.raises(RuntimeError, match="CellQuery only supports"):
+        cq.query(q, dict(num_neighbors=4)).toNeighborList()
+    with pytest.raises(RuntimeError, match="too large"):
+        cq.query(q, dict(r_max=0.6 * float(box.Lx))).toNeighborList()
+    # an RDF over a CellQuery system uses the same arithmetic
+    rdf = density.RDF(bins=40, r_max=r).compute(cq)
+    assert np.array_equal(rdf.bin_counts, port.rdf_accumulate(port.GHOST, box, False, pts, pts, 40, r, 0.0, True))
+
+
 def test_steinhardt_w6_known_answers():
     """PERFECT_FCC_W6 = -0.00262604 with wl (and wl + average) on the perfect FCC crystal, k = 12 and a ball query
     (tests/test_order_steinhardt.py:18, :168-214 upstream)."""

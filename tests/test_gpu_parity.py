@@ -282,6 +282,32 @@ def test_knn(ctx, name):
         assert_nlist_equal(got, want, f"{name} knn k={k}")
 
 
+GHOST = 2
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+def test_ghost_flavour_ball_and_rdf(ctx, name):
+    """CellQuery's arithmetic r = (p_j + shift) - q (CellQuery.cc:107, CellIterator.h:167; E5 in oracle/port.c):
+    NeighborList in both orders and fused RDF, self query and a separate query set."""
+    capi = _capi()
+    box, n, r = BOXES[name]
+    r = min(r, 0.49 * float(min(box.Lx, box.Ly)))
+    pts = random_points(box, n, seed=51)
+    dp = capi.DevicePoints(ctx, box, pts)
+    for q, excl, r_min in ((None, True, 0.0), (random_points(box, 400, seed=52), False, 0.5)):
+        qq = pts if q is None else q
+        for sbd in (False, True):
+            got = dp.ball_query(q, GHOST, r, r_min, excl, sbd).to_host()
+            want = port.ball_nlist(port.GHOST, box, box.is2D, pts, qq, r, r_min, excl, sbd)
+            assert_nlist_equal(got, want, f"{name} ghost self={q is None} sbd={sbd}")
+        rdf = capi.DeviceRDF(ctx, 50, r)
+        rdf.accumulate(dp, q, GHOST, r, r_min, excl)
+        assert np.array_equal(rdf.read(), port.rdf_accumulate(port.GHOST, box, box.is2D, pts, qq, 50, r, 0.0, excl,
+                                                              query_r_min=r_min))
+    with pytest.raises(RuntimeError, match="CellQuery only supports"):
+        dp.knn_query(None, 4, flavour=GHOST)
+
+
 @pytest.mark.parametrize("name", list(BOXES))
 def test_knn_wrap_flavour(ctx, name):
     """LinkCell's nearest-neighbour iterator (LinkCell.cc:575-679): the k smallest WRAPPED distances."""

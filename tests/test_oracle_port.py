@@ -64,6 +64,23 @@ def test_port_knn_wrap_matches_the_reference_linkcell(name):
         assert np.array_equal(bits(got.vectors), bits(want.vectors)), (name, k)
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref is built only where /root/reference exists")
+@pytest.mark.parametrize("name", list(BOXES))
+def test_port_ghost_flavour_matches_the_reference_cellquery(name):
+    """E5: the port's GHOST flavour against the reference's own CellQuery (CellQuery.cc, CellIterator.h), bit for bit."""
+    box, n, r = BOXES[name]
+    r = min(r, 0.49 * float(min(box.Lx, box.Ly)))
+    pts, q = random_points(box, min(n, 1500), 5), random_points(box, 300, 6)
+    for qq, excl, r_min, sbd in ((q, False, 0.4, False), (pts, True, 0.0, True)):
+        want = ref.Query("cell", box, pts, is2d=box.is2D).nlist(qq, r_max=r, r_min=r_min, exclude_ii=excl,
+                                                                sort_by_distance=sbd)
+        got = port.ball_nlist(port.GHOST, box, box.is2D, pts, qq, r, r_min, excl, sbd)
+        assert np.array_equal(got.neighbors, want.neighbors), name
+        assert np.array_equal(bits(got.distances), bits(want.distances)), name
+        assert np.array_equal(bits(got.vectors), bits(want.vectors)), name
+        assert np.array_equal(got.segments, want.segments) and np.array_equal(got.counts, want.counts)
+
+
 def test_port_matches_golden_rdf_config0():
     """BASELINE.json configs[0]: RDF bins=100 r_max=5 on make_random_system(50, 10000), one and two frames."""
     gold = np.load(os.path.join(GOLD, "rdf_config0.npz"))
