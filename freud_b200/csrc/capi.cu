@@ -825,30 +825,30 @@ static void points_create_impl(fgpu_ctx* ctx, const float* box6, int is2d, const
             "box lengths must be positive");
     plane_distances(p->box, p->plane_dist);
     p->n = n;
-    if (host != nullptr && p->box.is2d)
-    {
-        // NeighborQuery.h:103-112; a max-reduction first (vectorisable), the throw after the loop
-        float zmax = 0.0f;
-        bool nan_seen = false;
-        for (uint32_t i = 0; i < n; ++i)
-        {
-            float const z = std::fabs(host[3 * (size_t) i + 2]);
-            zmax = z > zmax ? z : zmax;
-            nan_seen |= z != z;
-        }
-        (void) nan_seen; // upstream's test is abs(z) > 1e-6, which a NaN passes
-        require(!(zmax > 1e-6), FGPU_EINVALID, "A point with z != 0 was provided in a 2D box.");
-    }
     p->xyz.reserve((size_t) n * 3);
     if (host != nullptr)
     {
         h2d(ctx, p->xyz.ptr, host, (size_t) n * 3 * sizeof(float));
-        sync(ctx); // the reference copies at construction; the caller may free its buffer right away
     }
     else
     {
         FGPU_CUDA_CHECK(cudaMemcpyAsync(p->xyz.ptr, dev, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToDevice,
                                         ctx->stream));
+    }
+    if (p->box.is2d)
+    {
+        // NeighborQuery.h:103-112, on the device behind the upload
+        int* flag = reinterpret_cast<int*>(ctx->d_scalars + 7);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), ctx->stream));
+        launch_check_2d_z(ctx, p->xyz.ptr, n, flag);
+        d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
+        sync(ctx);
+        require((ctx->h_scalars[7] & 0xffffffffULL) == 0, FGPU_EINVALID,
+                "A point with z != 0 was provided in a 2D box.");
+    }
+    else if (host != nullptr)
+    {
+        sync(ctx); // the reference copies at construction; the caller may free its buffer right away
     }
     *out = p.release();
 }

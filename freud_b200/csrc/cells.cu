@@ -247,6 +247,17 @@ __global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy
     }
 }
 
+// NeighborQuery.h:103-112: a 2-D box takes no point with |z| > 1e-6.  Checked on the device after the upload (a host
+// pass over the array costs more than the whole RDF frame it precedes).
+__global__ void __launch_bounds__(256) k_check_2d_z(const float* __restrict__ xyz, uint32_t n, int* __restrict__ flag)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && fabsf(xyz[3 * (size_t) i + 2]) > 1e-6f)
+    {
+        *flag = 1;
+    }
+}
+
 void choose_dims(const fgpu_points* pts, float r_search, bool force_single_cell, int dim[3], int ambiguous[3])
 {
     double const lmax = std::max({(double) pts->box.Lx, (double) pts->box.Ly, (double) pts->box.Lz});
@@ -307,6 +318,19 @@ void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n)
     {
         KernelScope ks(ctx, "scan");
         k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_check_2d_z(fgpu_ctx* ctx, const float* xyz, uint32_t n, int* flag)
+{
+    if (n == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "check_2d_z");
+        k_check_2d_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(xyz, n, flag);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }

@@ -251,6 +251,7 @@ struct SearchArgs
 
 void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n); // in place, n elements
 void build_grid(fgpu_points* pts, float r_search, bool force_single_cell = false);
+void launch_check_2d_z(fgpu_ctx* ctx, const float* xyz, uint32_t n, int* flag); // *flag = 1 if some |z| > 1e-6
 GridDev grid_dev(const fgpu_points* pts);
 // cell-sorts arbitrary query points with the grid of pts; result in ctx->q_sorted
 void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query);
