@@ -1502,6 +1502,7 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         a.ql = d_ql.ptr;
         a.qlm = need_qlm ? d_qlm.ptr : nullptr;
         a.sys_qlm = average ? nullptr : d_sys.ptr; // the system sums come from the averaged q_lm then
+        a.sys_partials = nullptr;
         launch_steinhardt(ctx, a, lv);
         if (average)
         {
@@ -1515,7 +1516,8 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
             av.qlm_ave = d_qlm_ave.ptr;
             av.ql_ave = d_ql_ave.ptr;
             av.sys_qlm = d_sys.ptr;
-            launch_steinhardt_average(ctx, av, (int) n_ls);
+            av.sys_partials = nullptr;
+            launch_steinhardt_average(ctx, av, (int) n_ls, (uint32_t) tot_m);
         }
         std::vector<std::vector<float>> w3j(n_ls);
         if (wl)

@@ -101,6 +101,7 @@ struct fgpu_ctx
     fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
     uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
     int force_general = 0;                // FGPU_SEARCH=general: always run the search.cu kernels (testing)
+    fgpu::DevBuf<double> st_partials;     // Steinhardt: per-block partial sums of the system q_lm
     fgpu::DevBuf<float> knn_d;            // kNN scratch, [k][n_query]
     fgpu::DevBuf<uint32_t> knn_s;         // kNN scratch, [k][n_query] (slot | image code)
     unsigned long long* d_scalars = nullptr; // 8 x u64 device scalars (totals, flags)
@@ -455,6 +456,7 @@ struct SteinhardtArgs
     float* ql;       // n x n_ls
     float* qlm;      // concatenated per l
     double* sys_qlm; // concatenated per l, fp64 accumulators (re, im)
+    double* sys_partials; // set by the launcher: one row of block sums per block (single-l kernel)
 };
 void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& args, const std::vector<uint32_t>& ls);
 void launch_pad_positions(fgpu_ctx* ctx, const float* xyz, uint32_t n, float4* out);
@@ -469,8 +471,9 @@ struct SteinhardtAveArgs
     float* qlm_ave;       // same layout
     float* ql_ave;        // n x n_ls
     double* sys_qlm;      // fp64 accumulators of the averaged q_lm (m >= 0), may be nullptr
+    double* sys_partials; // set by the launcher: per-block partial sums
 };
-void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls);
+void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls, uint32_t tot_m);
 
 struct SteinhardtWlArgs
 {

@@ -50,17 +50,29 @@ __global__ void __launch_bounds__(256) k_knn_rows(KnnRowsArgs a)
     {
         sum += __shfl_down_sync(FULL, sum, o);
     }
-    unsigned long long base = 0;
+    // one atomic per block on the hot total (one per warp serialises in L2: 31 k adds on one address)
+    __shared__ unsigned long long s_sum[256 / 32];
     if (lane == 0)
     {
-        if (mu != 0)
+        s_sum[threadIdx.x >> 5] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long t = 0;
+        for (int w = 0; w < 256 / 32; ++w)
         {
-            base = atomicAdd(a.unresolved, (unsigned long long) __popc(mu));
+            t += s_sum[w];
         }
-        if (sum != 0)
+        if (t != 0)
         {
-            atomicAdd(a.total, sum);
+            atomicAdd(a.total, t);
         }
+    }
+    unsigned long long base = 0;
+    if (lane == 0 && mu != 0)
+    {
+        base = atomicAdd(a.unresolved, (unsigned long long) __popc(mu));
     }
     base = __shfl_sync(FULL, base, 0);
     if (unresolved)

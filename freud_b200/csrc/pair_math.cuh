@@ -36,6 +36,15 @@ __device__ __forceinline__ float modulus_positive_one(float a)
     return __fsub_rn(u, truncf(u));
 }
 
+// The same for f in (-1, 2) whose intermediate sum stays below 2: truncation is a compare (FSET), not an FRND on
+// the XU pipe.
+__device__ __forceinline__ float modulus_positive_one_small(float f)
+{
+    float const t = __fsub_rn(f, f >= 1.0f ? 1.0f : 0.0f);
+    float const u = __fadd_rn(t, 1.0f);
+    return __fsub_rn(u, u >= 1.0f ? 1.0f : 0.0f);
+}
+
 __device__ __forceinline__ float dot_exact(float x, float y, float z)
 {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
@@ -67,9 +76,20 @@ __device__ __forceinline__ void wrap_quick(const BoxDev& b, float ylx, float yly
     float fx = div_by_const(dx, b.Lx, ylx);
     float fy = div_by_const(dy, b.Ly, yly);
     float fz = b.is2d ? 0.0f : div_by_const(dz, b.Lz, ylz);
-    fx = modulus_positive_one(fx);
-    fy = modulus_positive_one(fy);
-    fz = modulus_positive_one(fz);
+    // two points of the box are less than one box apart: f in (-1, 2), where fmodf(fmodf(f, 1) + 1, 1) needs
+    // compares only (bit-identical to the truncating form there); anything else takes the general form
+    if (fabsf(fx - 0.5f) < 1.4f && fabsf(fy - 0.5f) < 1.4f && fabsf(fz - 0.5f) < 1.4f)
+    {
+        fx = modulus_positive_one_small(fx);
+        fy = modulus_positive_one_small(fy);
+        fz = modulus_positive_one_small(fz);
+    }
+    else
+    {
+        fx = modulus_positive_one(fx);
+        fy = modulus_positive_one(fy);
+        fz = modulus_positive_one(fz);
+    }
     float x = __fadd_rn(b.lox, __fmul_rn(fx, b.Lx));
     float y = __fadd_rn(b.loy, __fmul_rn(fy, b.Ly));
     float z = __fadd_rn(b.loz, __fmul_rn(fz, b.Lz));

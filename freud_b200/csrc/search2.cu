@@ -55,15 +55,7 @@ __device__ __forceinline__ bool in_window2(float r_sq, float r_max_sq, float r_m
 
 // Division by a box length: div_by_const (pair_math.cuh) replaces __fdiv_rn (x86 divss upstream, Box.h:248-250).
 // Exact here because stage 1 bounds |a| / L away from 0 (no underflow in the residuals).
-// util::modulusPositive(f, 1) = fmodf(fmodf(f, 1) + 1, 1) (freud/util/utils.h:29-32) for f in (-1, 2) whose
-// intermediate sum stays below 2: truncation is a compare (FSET), not an FRND.
-__device__ __forceinline__ float modulus_positive_one_small(float f)
-{
-    float const t = __fsub_rn(f, f >= 1.0f ? 1.0f : 0.0f);
-    float const u = __fadd_rn(t, 1.0f);
-    return __fsub_rn(u, u >= 1.0f ? 1.0f : 0.0f);
-}
-
+// modulus_positive_one_small (pair_math.cuh): util::modulusPositive(f, 1) (freud/util/utils.h:29-32) for f in (-1, 2).
 // Box::wrap(v) (freud/box/Box.h:307-329) for displacements whose fractional coordinates are within
 // (-1/2 - 0.35, 1/2 + 0.35) + {-1, 0, 1}; bit-identical to wrap_exact on that domain.
 template<bool TRI>

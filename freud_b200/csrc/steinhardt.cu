@@ -32,9 +32,10 @@ namespace fgpu {
 namespace {
 
 constexpr int kSphLmax = 32;
-// Y = P / sqrt(2 pi) is a double division rounded to float upstream (spherical_harmonics.hpp:85-91); the product
-// with the double reciprocal rounds to the same float except when the quotient sits within 2^-53 of a float
-// rounding boundary.
+// Y = P / sqrt(2 pi) upstream (a double division per value, spherical_harmonics.hpp:85-91).  The Jacobi recurrence is
+// linear in its first column, so the factor is folded into c_jac0 on the host (float(jac0 / sqrt(2 pi))): one
+// rounding in a different place, ~1e-7 relative, and no float<->double conversion per (bond, m) -- those conversions
+// and the wrap's truncations kept the XU pipe 52 % busy, the most loaded unit of the kernel (profiles, k19 capture).
 constexpr double kInvSqrt2Pi = 1.0 / 2.5066282746310002;
 constexpr int kThreads = 128;
 constexpr int kStageBonds = 1792; // bonds staged per pass by k_steinhardt_single: 5 floats each, 35 KB
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) k_pad_positions(const float* __restrict__
 // recurrence prefactors for lmax, laid out as the reference does: [0, lmax*(lmax+1)) first kind,
 // [lmax*(lmax+1), 2*lmax*(lmax+1)) second kind; index lmax*m + (l-1)
 __constant__ float c_pref[2 * (kSphLmax + 1) * kSphLmax];
-__constant__ float c_jac0[kSphLmax + 1]; // jacobi[m][0] = 1/sqrt(2) * prod_{k<=m} sqrt(1 + 1/(2k))
+__constant__ float c_jac0[kSphLmax + 1]; // jacobi[m][0] = 1/sqrt(2) * prod_{k<=m} sqrt(1 + 1/(2k)), times 1/sqrt(2 pi)
 __constant__ int c_ls[kSphLmax + 1];     // requested l values
 __constant__ int c_l_slot[kSphLmax + 1]; // l -> index into the request list, or -1
 __constant__ int c_acc_off[kSphLmax + 1]; // request index -> offset of its (l+1) complex accumulators
@@ -109,6 +110,33 @@ __device__ __forceinline__ Angles bond_angles(const SteinhardtArgs& args, float 
     a.caz = rho_sq > 0.0f ? dx * inv_rho : 1.0f; // atan2(0, 0) = 0
     a.saz = rho_sq > 0.0f ? dy * inv_rho : 0.0f;
     return a;
+}
+
+// Sum of v over the block, written to *dst by thread 0; every thread of the block must call it.
+__device__ __forceinline__ void block_sum_to(double v, double* dst)
+{
+    __shared__ double s_w[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        v += __shfl_down_sync(0xffffffffU, v, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        s_w[threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w)
+        {
+            t += s_w[w];
+        }
+        *dst = t;
+    }
+    __syncthreads();
 }
 
 // ---- single l, everything unrolled into registers ---------------------------------------------------
@@ -201,7 +229,7 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
                     j_cur = next;
                 }
                 float const legendre = sinpow * j_cur;                      // :272-281
-                float const amp = (float) ((double) legendre * kInvSqrt2Pi); // / sqrt(2 pi), :85-91
+                float const amp = legendre; // / sqrt(2 pi) is folded into c_jac0
                 float const phase = (m & 1) ? -1.0f : 1.0f; // Steinhardt.cc:47-49
                 re[m] += w * (phase * (amp * c));           // exp(i m theta), :239-244
                 im[m] += w * (phase * (amp * s));
@@ -255,9 +283,13 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
             }
         }
     }
-    // system q_lm partial sums in fp64: warp shuffle, then one atomic per warp and component
-    if (a.sys_qlm != nullptr)
+    // System q_lm partial sums in fp64: warp shuffle, block sum in shared memory, one row of partials per block.
+    // (One atomicAdd per warp and component on the 2(l+1) accumulators serialises in L2: 31 k warps x 14 hot
+    // addresses cost ~0.25 ms at C3, more than the rest of the kernel.  k_sum_partials adds the rows up, in a
+    // fixed order.)
+    if (a.sys_partials != nullptr)
     {
+        __shared__ double s_part[kThreads / 32][2 * (L + 1)];
 #pragma unroll
         for (int m = 0; m <= L; ++m)
         {
@@ -270,10 +302,48 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
             }
             if ((threadIdx.x & 31) == 0)
             {
-                atomicAdd(&a.sys_qlm[2 * m], vr);
-                atomicAdd(&a.sys_qlm[2 * m + 1], vi);
+                s_part[threadIdx.x >> 5][2 * m] = vr;
+                s_part[threadIdx.x >> 5][2 * m + 1] = vi;
             }
         }
+        __syncthreads();
+        if (threadIdx.x < 2 * (L + 1))
+        {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w)
+            {
+                v += s_part[w][threadIdx.x];
+            }
+            a.sys_partials[(size_t) blockIdx.x * (2 * (L + 1)) + threadIdx.x] = v;
+        }
+    }
+}
+
+// Column sums of the per-block partials: one block per column, fixed summation order (bitwise reproducible).
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, uint32_t n_rows, uint32_t width,
+                                                      double* __restrict__ out)
+{
+    __shared__ double s_sum[256];
+    uint32_t const col = blockIdx.x;
+    double v = 0.0;
+    for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x)
+    {
+        v += partials[(size_t) r * width + col];
+    }
+    s_sum[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int) threadIdx.x < o)
+        {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        out[col] += s_sum[0];
     }
 }
 
@@ -284,18 +354,16 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
                                                                  int tot_m)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n)
-    {
-        return;
-    }
+    bool const active = i < a.n; // idle threads stay for the block sums at the end
     float acc[kMaxAcc];
     for (int k = 0; k < 2 * n_acc; ++k)
     {
         acc[k] = 0.0f;
     }
     float total_weight = 0.0f;
-    uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
-    float const rx0 = a.xyz[3 * (size_t) i], ry0 = a.xyz[3 * (size_t) i + 1], rz0 = a.xyz[3 * (size_t) i + 2];
+    uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
+    size_t const ii = active ? i : 0;
+    float const rx0 = a.xyz[3 * ii], ry0 = a.xyz[3 * ii + 1], rz0 = a.xyz[3 * ii + 2];
     BondIn next = beg < end ? load_bond(a, beg) : BondIn {0, 0, 0, 0, 0};
     for (uint32_t b = beg; b < end; ++b)
     {
@@ -328,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
                 if (slot >= 0)
                 {
                     float const legendre = sinpow * j_cur;
-                    float const amp = (float) ((double) legendre * kInvSqrt2Pi);
+                    float const amp = legendre; // / sqrt(2 pi) is folded into c_jac0
                     int const o = 2 * (c_acc_off[slot] + m);
                     acc[o] += w * (phase * (amp * c));
                     acc[o + 1] += w * (phase * (amp * s));
@@ -357,8 +425,11 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
         {
             sum += q[2 * m] * q[2 * m] + q[2 * m + 1] * q[2 * m + 1];
         }
-        a.ql[(size_t) i * n_ls + r] = sqrtf(sum * nf);
-        if (a.qlm != nullptr)
+        if (active)
+        {
+            a.ql[(size_t) i * n_ls + r] = sqrtf(sum * nf);
+        }
+        if (active && a.qlm != nullptr)
         {
             // per-l blocks are concatenated: block r starts at n * c_out_off[r] complex elements
             float2* out = reinterpret_cast<float2*>(a.qlm) + (size_t) a.n * c_out_off[r] + (size_t) i * (2 * l + 1);
@@ -372,18 +443,18 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
                 out[l + m] = make_float2(phase * q[2 * m], -(phase * q[2 * m + 1]));
             }
         }
-        if (a.sys_qlm != nullptr)
+        if (a.sys_partials != nullptr)
         {
             // sys_qlm holds (2l+1) complex per l at complex offset c_out_off[r]; only m >= 0 is accumulated,
-            // the host derives m < 0
+            // the host derives m < 0.  Block sums, one row of 2 tot_m partials per block (see k_sum_partials).
+            double* const row = a.sys_partials + (size_t) blockIdx.x * (2 * tot_m);
             for (int m = 0; m <= l; ++m)
             {
-                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m)], (double) q[2 * m]);
-                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m) + 1], (double) q[2 * m + 1]);
+                block_sum_to(active ? (double) q[2 * m] : 0.0, row + 2 * (c_out_off[r] + m));
+                block_sum_to(active ? (double) q[2 * m + 1] : 0.0, row + 2 * (c_out_off[r] + m) + 1);
             }
         }
     }
-    (void) tot_m;
 }
 
 // ---- second-shell average (Steinhardt::computeAve, Steinhardt.cc:224-289) ----------------------------------
@@ -392,12 +463,10 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
 __global__ void __launch_bounds__(kThreads) k_steinhardt_average(SteinhardtAveArgs a, int n_ls)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n)
-    {
-        return;
-    }
-    uint32_t const beg = a.row_start[i], end = a.row_start[i + 1];
+    bool const active = i < a.n; // idle threads stay for the block sums
+    uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
     float const count = (float) (end - beg + 1U); // neighborcount starts at 1, Steinhardt.cc:244
+    int const tot_m = c_out_off[n_ls - 1] + 2 * c_ls[n_ls - 1] + 1;
     for (int r = 0; r < n_ls; ++r)
     {
         int const l = c_ls[r];
@@ -420,30 +489,39 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_average(SteinhardtAveAr
                 im[m] += v.y;
             }
         }
-        const float2* __restrict__ const own = block + (size_t) i * nm;
-        float2* const out = reinterpret_cast<float2*>(a.qlm_ave) + (size_t) a.n * c_out_off[r] + (size_t) i * nm;
+        size_t const ii = active ? i : 0;
+        const float2* __restrict__ const own = block + ii * nm;
+        float2* const out = reinterpret_cast<float2*>(a.qlm_ave) + (size_t) a.n * c_out_off[r] + ii * nm;
         float sum = 0.0f;
         for (int m = 0; m <= l; ++m)
         {
             float2 const v = own[m];
             re[m] = (re[m] + v.x) / count;
             im[m] = (im[m] + v.y) / count;
-            out[m] = make_float2(re[m], im[m]);
-            sum += re[m] * re[m] + im[m] * im[m];
-            if (a.sys_qlm != nullptr)
+            if (active)
             {
-                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m)], (double) re[m]);
-                atomicAdd(&a.sys_qlm[2 * (c_out_off[r] + m) + 1], (double) im[m]);
+                out[m] = make_float2(re[m], im[m]);
+            }
+            sum += re[m] * re[m] + im[m] * im[m];
+            if (a.sys_partials != nullptr)
+            {
+                // block sums instead of 2(l+1) hot atomics per particle (see k_steinhardt_single)
+                double* const row = a.sys_partials + (size_t) blockIdx.x * (2 * tot_m);
+                block_sum_to(active ? (double) re[m] : 0.0, row + 2 * (c_out_off[r] + m));
+                block_sum_to(active ? (double) im[m] : 0.0, row + 2 * (c_out_off[r] + m) + 1);
             }
         }
-        for (int m = 1; m <= l; ++m)
+        if (active)
         {
-            float const phase = (m & 1) ? -1.0f : 1.0f;
-            out[l + m] = make_float2(phase * re[m], -(phase * im[m]));
-            sum += re[m] * re[m] + im[m] * im[m];
+            for (int m = 1; m <= l; ++m)
+            {
+                float const phase = (m & 1) ? -1.0f : 1.0f;
+                out[l + m] = make_float2(phase * re[m], -(phase * im[m]));
+                sum += re[m] * re[m] + im[m] * im[m];
+            }
+            float const nf = (float) (4.0 * 3.14159265358979323846 / nm);
+            a.ql_ave[(size_t) i * n_ls + r] = sqrtf(sum * nf);
         }
-        float const nf = (float) (4.0 * 3.14159265358979323846 / nm);
-        a.ql_ave[(size_t) i * n_ls + r] = sqrtf(sum * nf);
     }
 }
 
@@ -521,7 +599,7 @@ void upload_tables(fgpu_ctx* ctx, int lmax, const std::vector<uint32_t>& ls)
         }
     }
     // compute_jacobis first column, spherical_harmonics.hpp:250-256
-    float jac0[kSphLmax + 1];
+    float jac0[kSphLmax + 1]; // first column of the recurrence as upstream stores it (float), scaled at the end
     jac0[0] = (float) (1 / std::sqrt(2.0));
     for (unsigned m = 1; m < L + 1; ++m)
     {
@@ -530,6 +608,10 @@ void upload_tables(fgpu_ctx* ctx, int lmax, const std::vector<uint32_t>& ls)
     for (unsigned m = L + 1; m < kSphLmax + 1; ++m)
     {
         jac0[m] = 0.0f;
+    }
+    for (unsigned m = 0; m < L + 1; ++m)
+    {
+        jac0[m] = (float) ((double) jac0[m] * kInvSqrt2Pi);
     }
     int h_ls[kSphLmax + 1] = {0}, h_slot[kSphLmax + 1], h_acc[kSphLmax + 1] = {0}, h_out[kSphLmax + 1] = {0};
     for (int& s : h_slot)
@@ -557,9 +639,21 @@ void upload_tables(fgpu_ctx* ctx, int lmax, const std::vector<uint32_t>& ls)
     FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
-template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a)
+template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a_in)
 {
-    k_steinhardt_single<L><<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a);
+    SteinhardtArgs a = a_in;
+    unsigned const blocks = (a.n + kThreads - 1) / kThreads;
+    uint32_t const width = 2 * (L + 1);
+    if (a.sys_qlm != nullptr)
+    {
+        ctx->st_partials.reserve((size_t) blocks * width);
+        a.sys_partials = ctx->st_partials.ptr;
+    }
+    k_steinhardt_single<L><<<blocks, kThreads, 0, ctx->stream>>>(a);
+    if (a.sys_qlm != nullptr)
+    {
+        k_sum_partials<<<width, 256, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
+    }
 }
 
 } // namespace
@@ -614,8 +708,20 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
     }
     if (!single)
     {
-        k_steinhardt_generic<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, lmax, (int) ls.size(),
-                                                                                             n_acc, tot_m);
+        SteinhardtArgs g = a;
+        unsigned const blocks = (a.n + kThreads - 1) / kThreads;
+        uint32_t const width = 2 * (uint32_t) tot_m;
+        if (a.sys_qlm != nullptr)
+        {
+            ctx->st_partials.reserve((size_t) blocks * width);
+            g.sys_partials = ctx->st_partials.ptr;
+            FGPU_CUDA_CHECK(cudaMemsetAsync(g.sys_partials, 0, (size_t) blocks * width * sizeof(double), ctx->stream));
+        }
+        k_steinhardt_generic<<<blocks, kThreads, 0, ctx->stream>>>(g, lmax, (int) ls.size(), n_acc, tot_m);
+        if (a.sys_qlm != nullptr)
+        {
+            k_sum_partials<<<width, 256, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
+        }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
@@ -633,7 +739,7 @@ void launch_pad_positions(fgpu_ctx* ctx, const float* xyz, uint32_t n, float4* o
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls)
+void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_ls, uint32_t tot_m)
 {
     if (a.n == 0)
     {
@@ -641,7 +747,20 @@ void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_
     }
     {
         KernelScope ks(ctx, "steinhardt_average");
-        k_steinhardt_average<<<(a.n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(a, n_ls);
+        SteinhardtAveArgs g = a;
+        unsigned const blocks = (a.n + kThreads - 1) / kThreads;
+        uint32_t const width = 2 * tot_m;
+        if (a.sys_qlm != nullptr)
+        {
+            ctx->st_partials.reserve((size_t) blocks * width);
+            g.sys_partials = ctx->st_partials.ptr;
+            FGPU_CUDA_CHECK(cudaMemsetAsync(g.sys_partials, 0, (size_t) blocks * width * sizeof(double), ctx->stream));
+        }
+        k_steinhardt_average<<<blocks, kThreads, 0, ctx->stream>>>(g, n_ls);
+        if (a.sys_qlm != nullptr)
+        {
+            k_sum_partials<<<width, 256, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
+        }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
