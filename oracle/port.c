@@ -1239,3 +1239,225 @@ uint64_t fport_count_candidates(const float* box6, int is2d, const float* pts, u
     grid_free(&g);
     return total;
 }
+
+/* ---- Steinhardt options: second-shell average and w_l ------------------------------------------------------
+ * Steinhardt::computeAve (Steinhardt.cc:224-289), aggregatewl (:329-359) with reduceWigner3j (Wigner3j.cc:22-57)
+ * and normalizeSystem (:291-327), applied to the q_lm(i) and q_l(i) that fport_steinhardt produced.
+ * Upstream tabulates the Wigner 3j symbols (l l l; m1 m2 m3) for l <= 20 (Wigner3j.cc:59-5832); the table is a
+ * third-party-style constant, so it is restated here by the published algorithm behind it -- Racah's formula,
+ *   (l l l; m1 m2 m3) = (-1)^m3 sqrt( prod (l +- m_i)! / ((3l+1)! (l!)^3) ) sum_k (-1)^k C(l,k) C(l,l-m1-k) C(l,l+m2-k)
+ * with the sum exact in 128-bit integers -- and checked against upstream's numbers (identical as float for every
+ * l <= 20, tests/test_oracle_port.py). */
+static void wigner3j_table(int l, float* out)
+{
+    long double fact[3 * 32 + 2];
+    fact[0] = 1.0L;
+    for (int k = 1; k < 3 * l + 2; ++k)
+    {
+        fact[k] = fact[k - 1] * (long double) k;
+    }
+    __int128 binom[33][33];
+    for (int a = 0; a <= l; ++a)
+    {
+        for (int k = 0; k <= l; ++k)
+        {
+            binom[a][k] = 0;
+        }
+        binom[a][0] = 1;
+        for (int k = 1; k <= a; ++k)
+        {
+            binom[a][k] = binom[a - 1][k - 1] + (k <= a - 1 ? binom[a - 1][k] : 0);
+        }
+    }
+    size_t counter = 0;
+    for (int m1 = -l; m1 <= l; ++m1)
+    {
+        int lo = -l - m1 > -l ? -l - m1 : -l, hi = l - m1 < l ? l - m1 : l;
+        for (int m2 = lo; m2 <= hi; ++m2)
+        {
+            int m3 = -m1 - m2;
+            __int128 sum = 0;
+            for (int k = 0; k <= l; ++k)
+            {
+                int k2 = l - m1 - k, k3 = l + m2 - k;
+                if (k2 < 0 || k2 > l || k3 < 0 || k3 > l)
+                {
+                    continue;
+                }
+                __int128 term = binom[l][k] * binom[l][k2] * binom[l][k3];
+                sum += (k & 1) ? -term : term;
+            }
+            long double pref = sqrtl(fact[l + m1] * fact[l - m1] * fact[l + m2] * fact[l - m2] * fact[l + m3]
+                                     * fact[l - m3] / (fact[3 * l + 1] * fact[l] * fact[l] * fact[l]));
+            long double v = ((m3 & 1) ? -1.0L : 1.0L) * pref * (long double) sum;
+            out[counter++] = (float) (double) v; /* upstream stores doubles and uses float(w), Wigner3j.cc:52 */
+        }
+    }
+}
+
+static size_t wigner3j_count(int l)
+{
+    return (size_t) (3 * l * l + 3 * l + 1);
+}
+
+/* reduceWigner3j, Wigner3j.cc:22-57: sum over the table of Re(float(w) * s[m1] * s[m2] * s[m3]), std::complex<float>
+ * products left to right; source is interleaved (re, im) in the order m = 0..l, -1..-l */
+static float reduce_wigner3j(const float* src, int l, const float* w3j)
+{
+    float result = 0;
+    size_t counter = 0;
+    for (int m1 = -l; m1 <= l; ++m1)
+    {
+        int i1 = m1 < 0 ? l - m1 : m1;
+        int lo = -l - m1 > -l ? -l - m1 : -l, hi = l - m1 < l ? l - m1 : l;
+        for (int m2 = lo; m2 <= hi; ++m2)
+        {
+            int i2 = m2 < 0 ? l - m2 : m2;
+            int m3 = -m1 - m2;
+            int i3 = m3 < 0 ? l - m3 : m3;
+            float w = w3j[counter++];
+            float ar = w * src[2 * i1], ai = w * src[2 * i1 + 1];
+            float t1 = ar * src[2 * i2], t2 = ai * src[2 * i2 + 1];
+            float t3 = ar * src[2 * i2 + 1], t4 = ai * src[2 * i2];
+            float br = t1 - t2, bi = t3 + t4;
+            float u1 = br * src[2 * i3], u2 = bi * src[2 * i3 + 1];
+            float cr = u1 - u2;
+            result = result + cr;
+        }
+    }
+    return result;
+}
+
+/* qlm: per l blocks as fport_steinhardt lays them out (n x (2l+1) complex each); ql: n x n_ls.
+ * ql_out: what getQl() returns (the averaged q_l with average); particle_order: getParticleOrder(); order: getOrder(). */
+int fport_steinhardt_options(uint32_t n, const uint32_t* nl_j, const uint32_t* segments, const uint32_t* counts,
+                             const uint32_t* ls, uint32_t n_ls, int average, int wl, int wl_normalize,
+                             const float* qlm, const float* ql, float* ql_out, float* particle_order, float* order)
+{
+    size_t total = 0;
+    for (uint32_t a = 0; a < n_ls; ++a)
+    {
+        if (ls[a] > SPH_LMAX || (wl && ls[a] > 20))
+        {
+            return -1; /* getWigner3j throws std::out_of_range beyond l = 20 */
+        }
+        total += (size_t) n * (2 * ls[a] + 1) * 2;
+    }
+    float* ave = average ? (float*) calloc(total ? total : 1, sizeof(float)) : NULL;
+    float* ql_ave = average ? (float*) calloc((size_t) n * n_ls + 1, sizeof(float)) : NULL;
+    size_t off = 0;
+    for (uint32_t a = 0; a < n_ls; ++a)
+    {
+        int l = (int) ls[a];
+        unsigned nm = 2 * ls[a] + 1;
+        float nf = (float) (4.0 * M_PI / nm);
+        const float* blk = qlm + off;
+        if (average)
+        {
+            float* ablk = ave + off;
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                float* dst = ablk + (size_t) i * nm * 2;
+                uint32_t beg = counts[i] ? segments[i] : 0;
+                unsigned neighborcount = 1; /* Steinhardt.cc:244 */
+                for (uint32_t kb = 0; kb < counts[i]; ++kb)
+                {
+                    const float* src = blk + (size_t) nl_j[beg + kb] * nm * 2;
+                    for (unsigned k = 0; k < 2 * nm; ++k)
+                    {
+                        dst[k] = dst[k] + src[k];
+                    }
+                    neighborcount++;
+                }
+                const float* own = blk + (size_t) i * nm * 2;
+                float sum = 0;
+                for (unsigned k = 0; k < nm; ++k)
+                {
+                    dst[2 * k] = dst[2 * k] + own[2 * k];
+                    dst[2 * k + 1] = dst[2 * k + 1] + own[2 * k + 1];
+                    dst[2 * k] = dst[2 * k] / (float) neighborcount;
+                    dst[2 * k + 1] = dst[2 * k + 1] / (float) neighborcount;
+                    float rr = dst[2 * k] * dst[2 * k], ii = dst[2 * k + 1] * dst[2 * k + 1];
+                    float nn = rr + ii;
+                    sum = sum + nn;
+                }
+                sum = sum * nf;
+                ql_ave[(size_t) i * n_ls + a] = sqrtf(sum);
+            }
+        }
+        const float* source = average ? ave + off : blk;
+        const float* norm_src = average ? ql_ave : ql;
+        float* w3j = NULL;
+        if (wl)
+        {
+            w3j = (float*) malloc(wigner3j_count(l) * sizeof(float));
+            wigner3j_table(l, w3j);
+        }
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            float q = norm_src[(size_t) i * n_ls + a];
+            ql_out[(size_t) i * n_ls + a] = q;
+            float po = q;
+            if (wl)
+            {
+                po = reduce_wigner3j(source + (size_t) i * nm * 2, l, w3j);
+                if (wl_normalize)
+                {
+                    float normalization = sqrtf(nf) / q;
+                    float n2 = normalization * normalization;
+                    float n3 = n2 * normalization;
+                    po = po * n3;
+                }
+            }
+            particle_order[(size_t) i * n_ls + a] = po;
+        }
+        /* system q_lm (index order here; scheduler order upstream) and normalizeSystem */
+        float sys[2 * (2 * SPH_LMAX + 1)];
+        float calc_norm = 0;
+        for (unsigned k = 0; k < nm; ++k)
+        {
+            float sr = 0, si = 0;
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                const float* src = source + (size_t) i * nm * 2;
+                sr = sr + src[2 * k] / (float) n;
+                si = si + src[2 * k + 1] / (float) n;
+            }
+            sys[2 * k] = sr;
+            sys[2 * k + 1] = si;
+            float nn = sr * sr + si * si;
+            calc_norm = calc_norm + nn;
+        }
+        float ql_system = sqrtf(calc_norm * nf);
+        if (wl)
+        {
+            float wl_system = reduce_wigner3j(sys, l, w3j);
+            if (wl_normalize)
+            {
+                float normalization = sqrtf(nf) / ql_system;
+                wl_system = wl_system * (normalization * normalization * normalization);
+            }
+            order[a] = wl_system;
+        }
+        else
+        {
+            order[a] = ql_system;
+        }
+        free(w3j);
+        off += (size_t) n * nm * 2;
+    }
+    free(ave);
+    free(ql_ave);
+    return 0;
+}
+
+/* the table alone, for the test that compares it with upstream's numbers */
+int fport_wigner3j(uint32_t l, float* out)
+{
+    if (l > 32)
+    {
+        return -1;
+    }
+    wigner3j_table((int) l, out);
+    return (int) wigner3j_count((int) l);
+}

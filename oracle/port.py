@@ -46,6 +46,9 @@ def lib():
                                        C.c_uint32, C.c_int, _fp, _fp, _fp, _fp]
         L.fport_steinhardt.argtypes = [_fp, C.c_int, _fp, C.c_uint32, _up, _fp, _fp, _up, _up, _up, C.c_uint32,
                                        C.c_int, _fp, _fp, _fp, _fp]
+        L.fport_steinhardt_options.argtypes = [C.c_uint32, _up, _up, _up, _up, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                               _fp, _fp, _fp, _fp, _fp]
+        L.fport_wigner3j.argtypes = [C.c_uint32, _fp]
         L.fport_box_apply.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_uint32, _fp]
         L.fport_box_info.argtypes = [_fp, C.c_int, _fp, _fp]
         L.fport_count_candidates.restype = C.c_uint64
@@ -141,7 +144,15 @@ def rdf_reduce(counts, r_max, r_min, box, is2d, n_points, n_query_points, frames
     return dict(bin_counts=c, rdf=g, n_r=n, bin_edges=e, bin_centers=ce)
 
 
-def steinhardt(box, is2d, points, nlist, ls, weighted=False):
+def wigner3j(l):
+    """(l l l; m1 m2 m3) in the order of reduceWigner3j's table (Wigner3j.cc:43-55), as float."""
+    out = np.zeros(3 * l * l + 3 * l + 1, np.float32)
+    if lib().fport_wigner3j(int(l), _p(out)) != len(out):
+        raise ValueError("oracle port: l too large")
+    return out
+
+
+def steinhardt(box, is2d, points, nlist, ls, weighted=False, average=False, wl=False, wl_normalize=False):
     b, p = box6(box), _f32(points, 3)
     ls = np.atleast_1d(np.asarray(ls, dtype=np.uint32)).copy()
     n = len(p)
@@ -165,6 +176,13 @@ def steinhardt(box, is2d, points, nlist, ls, weighted=False):
         blk = qlm[off:off + n * nm * 2].reshape(n, nm, 2)
         out.append((blk[..., 0] + 1j * blk[..., 1]).astype(np.complex64))
         off += n * nm * 2
+    if average or wl:
+        ql_out, po = np.zeros_like(ql), np.zeros_like(ql)
+        rc = lib().fport_steinhardt_options(n, _p(j, _up), _p(seg, _up), _p(cnt, _up), _p(ls, _up), len(ls), int(average),
+                                            int(wl), int(wl_normalize), _p(qlm), _p(ql), _p(ql_out), _p(po), _p(order))
+        if rc:
+            raise IndexError("Wigner 3j coefficients are implemented for l <= 20.")
+        return dict(ql=ql_out, qlm=out, order=order, particle_order=po)
     return dict(ql=ql, qlm=out, order=order, particle_order=ql)
 
 

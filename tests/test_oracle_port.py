@@ -113,6 +113,40 @@ def test_port_matches_golden_steinhardt():
     assert np.allclose(port.steinhardt(box, False, pts, nlb, [6])["ql"], gold["ball_ql_6"], rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("tag", ["ave", "wl", "wln", "ave_wl", "ave_wln"])
+def test_port_matches_golden_steinhardt_options(tag):
+    """computeAve / aggregatewl / normalizeSystem restated in oracle/port.c against outputs of the reference itself
+    (tests/golden/steinhardt_options.npz): per-particle values bit for bit, the system order to summation order."""
+    from tests.golden.make_golden import STEINHARDT_OPTIONS
+
+    gold = np.load(os.path.join(GOLD, "steinhardt_options.npz"))
+    box, pts = data.make_fcc_system(4, scale=1.2, sigma_noise=0.06, seed=7)
+    nl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True, sort_by_distance=True)
+    for ls in ([6], [4, 6], [3, 10]):
+        key = tag + "_" + "_".join(str(l) for l in ls)
+        out = port.steinhardt(box, False, pts, nl, ls, **STEINHARDT_OPTIONS[tag])
+        assert np.array_equal(bits(out["particle_order"]), bits(gold[f"{key}_particle_order"])), key
+        assert np.array_equal(bits(out["ql"]), bits(gold[f"{key}_ql"])), key
+        np.testing.assert_allclose(out["order"], gold[f"{key}_order"], rtol=1e-5, atol=1e-8)
+
+
+def test_port_wigner3j_known_values():
+    """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
+    the reference is present, every tabulated l <= 20 as float."""
+    assert np.array_equal(port.wigner3j(0), np.float32([1.0]))
+    s = np.float32(1.0 / np.sqrt(6.0))
+    assert np.array_equal(port.wigner3j(1), np.float32([s, -s, -s, 0.0, s, s, -s]))
+    path = "/root/reference/freud/order/Wigner3j.cc"
+    if os.path.exists(path):
+        import re
+
+        src = open(path).read()
+        for l in range(21):
+            body = re.search(r"case %d: \{\s*return \{(.*?)\};" % l, src, re.S).group(1)
+            table = np.array([float(x) for x in body.replace("\n", " ").split(",") if x.strip()])
+            assert np.array_equal(table.astype(np.float32), port.wigner3j(l)), l
+
+
 # ---- known answers held by the reference's own tests ---------------------------------------------------
 def test_known_answer_perfect_fcc_q6():
     """PERFECT_FCC_Q6 = 0.57452416, tests/test_order_steinhardt.py:17, :101-166 (k = 12 and ball)."""
