@@ -42,6 +42,7 @@ SIGNATURES = {
     "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
     "fgpu_points_destroy": (None, [_vp]),
     "fgpu_points_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "fgpu_shard_plan": (C.c_int, [_up, C.c_uint32, C.c_int, C.c_int, _up]),
     "fgpu_points_build_cells": (C.c_int, [_vp, C.c_float, _up]),
     "fgpu_points_read_cells": (C.c_int, [_vp, _up, _up]),
     "fgpu_ball_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
@@ -125,6 +126,17 @@ def box6_of(box):
 
     b = Box.from_box(box)
     return b.as_array6(), bool(b.is2D)
+
+
+def shard_plan(dims, n_points, shard, n_shards):
+    """Host-only arithmetic of ``fgpu_points_set_shard``: dict of the tickets, cells and slab of one shard."""
+    d = np.asarray(dims, dtype=np.uint32).copy()
+    out = np.zeros(8, np.uint32)
+    check(lib().fgpu_shard_plan(ptr(d, _up), int(n_points), int(shard), int(n_shards), ptr(out, _up)))
+    keys = ("ticket_begin", "ticket_end", "n_tickets", "cell_begin", "cell_end", "slab_axis", "slab_lo", "slab_len")
+    plan = {k: int(v) for k, v in zip(keys, out)}
+    plan["slab_len"] = None if plan["slab_len"] == 0xFFFFFFFF else plan["slab_len"]
+    return plan
 
 
 class Context:

@@ -902,6 +902,26 @@ int fgpu_points_set_shard(fgpu_points* pts, int shard, int n_shards)
     });
 }
 
+int fgpu_shard_plan(const uint32_t* dims, uint32_t n_points, int shard, int n_shards, uint32_t* out)
+{
+    return guarded([&] {
+        require(dims != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        require(n_shards >= 1 && shard >= 0 && shard < n_shards, FGPU_EINVALID, "shard index out of range");
+        require(dims[0] >= 1 && dims[1] >= 1 && dims[2] >= 1, FGPU_EINVALID, "empty grid");
+        int const d[3] = {(int) dims[0], (int) dims[1], (int) dims[2]};
+        ShardPlan const sp = shard_plan(d, n_points, shard, n_shards);
+        ShardPlan const last = shard_plan(d, n_points, n_shards - 1, n_shards);
+        out[0] = sp.ticket_begin;
+        out[1] = sp.ticket_end;
+        out[2] = last.ticket_end;
+        out[3] = sp.cell_begin;
+        out[4] = sp.cell_end;
+        out[5] = (uint32_t) sp.slab_axis;
+        out[6] = (uint32_t) sp.slab_lo;
+        out[7] = sp.slab_len < 0 ? 0xffffffffU : (uint32_t) sp.slab_len;
+    });
+}
+
 int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host)
 {
     return guarded([&] {

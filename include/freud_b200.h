@@ -110,6 +110,10 @@ int fgpu_points_build_cells(fgpu_points* pts, float r_search, uint32_t* out_dims
  * (everything else returns FGPU_ERUNTIME), need a grid of >= 3 cells per periodic axis and every point inside
  * the box; n_shards == 1 restores the normal behaviour. */
 int fgpu_points_set_shard(fgpu_points* pts, int shard, int n_shards);
+/* The arithmetic behind it, host only (no device needed; tests/test_multirank_gloo.py): for a grid of dims[3] cells
+ * holding n_points, out[8] = {ticket_begin, ticket_end, n_tickets, cell_begin, cell_end, slab_axis, slab_lo,
+ * slab_len (0xffffffff: every layer)} of shard `shard` of `n_shards`. */
+int fgpu_shard_plan(const uint32_t* dims, uint32_t n_points, int shard, int n_shards, uint32_t* out);
 /* Copies out the cell list for tests: cell_start[n_cells + 1] and the point index of every cell-ordered
  * slot (order[n]).  Either pointer may be NULL. */
 int fgpu_points_read_cells(fgpu_points* pts, uint32_t* cell_start_host, uint32_t* order_host);

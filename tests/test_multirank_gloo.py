@@ -102,3 +102,33 @@ def test_merge_nlist_shards_segments():
     assert np.array_equal(merged["neighbors"], full.neighbors)
     assert np.array_equal(merged["segments"], full.segments) and np.array_equal(merged["counts"], full.counts)
     assert (full.counts == 0).any()
+
+
+def test_home_tile_shards_tile_the_grid():
+    """fgpu_shard_plan (host arithmetic of fgpu_points_set_shard, no device): the shards' ticket and cell ranges tile
+    the grid in order, and every shard's slab holds the layers of its cells plus one halo layer on each side."""
+    from freud_b200 import _capi
+
+    for dims, n_points in (((73, 73, 73), 4_000_000), ((77, 77, 77), 1_000_000), ((282, 282, 1), 1_000_000),
+                           ((5, 4, 3), 500), ((9, 7, 1), 300)):
+        n_cells = dims[0] * dims[1] * dims[2]
+        for shards in (1, 2, 3, 8):
+            plans = [_capi.shard_plan(dims, n_points, s, shards) for s in range(shards)]
+            assert plans[0]["ticket_begin"] == 0 and plans[-1]["ticket_end"] == plans[0]["n_tickets"]
+            assert plans[0]["cell_begin"] == 0 and plans[-1]["cell_end"] == n_cells
+            for a, b in zip(plans, plans[1:]):
+                assert a["ticket_end"] == b["ticket_begin"] and a["cell_end"] == b["cell_begin"]
+            for p in plans:
+                if p["cell_end"] == p["cell_begin"]:
+                    continue
+                axis = p["slab_axis"]
+                assert axis == (2 if dims[2] > 1 else 1)
+                layers = dims[axis]
+                per_layer = dims[0] * dims[1] if axis == 2 else dims[0]
+                first = (p["cell_begin"] // per_layer) % layers if axis == 1 else p["cell_begin"] // per_layer
+                last = ((p["cell_end"] - 1) // per_layer) % layers if axis == 1 else (p["cell_end"] - 1) // per_layer
+                if p["slab_len"] is None or shards == 1:
+                    continue  # every layer is kept
+                need = {(first - 1) % layers, (last + 1) % layers} | {x % layers for x in range(first, last + 1)}
+                have = {(p["slab_lo"] + k) % layers for k in range(p["slab_len"])}
+                assert need <= have, (dims, shards, p)
