@@ -236,6 +236,67 @@ def workload_q6(ctx, rank, n):
                 h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={})
 
 
+def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
+    """SURVEY.md section 8f rank 3, first client: freud.density.LocalDensity(r_max, diameter).compute((box, points)) on
+    the C2 system -- ball query of r_max + diameter / 2 = 3 (IMAGE arithmetic), then the fractional count per row."""
+    from freud_b200 import _capi, data
+
+    L = (n / RHO) ** (1.0 / 3.0)
+    box, pts = data.make_random_system(L, n, seed=rank)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    rq = r_max + 0.5 * diameter
+    n_bonds = dp.ball_query(None, IMAGE, rq, 0.0, True).num_bonds
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+
+    pin_num, keep1 = pinned_empty((n,), np.float32)
+    pin_den, keep2 = pinned_empty((n,), np.float32)
+
+    def step_dev():
+        # the C ABI hands the two result arrays (8 MB) to the host: that copy is part of every call
+        dp.build_cells(rq)
+        return dp.ball_query(None, IMAGE, rq, 0.0, True).local_density(r_max, diameter, out=(pin_num, pin_den))
+
+    def step_e2e():
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        return d.ball_query(None, IMAGE, rq, 0.0, True).local_density(r_max, diameter, out=(pin_num, pin_den))[1]
+
+    n_cells = int(np.prod(dp.build_cells(rq)))
+    algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
+            "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
+            "local_density": 4 * n_bonds + 8 * n + 8 * n,
+            "pipeline": 16 * (n + n) + 8 * n}  # fused search + count would read the positions and write two floats
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s",
+                metric="local_density_particles_per_sec",
+                config={"workload": f"LocalDensity r_max={r_max:g} diameter={diameter:g} (ball query r={rq:g}, image "
+                                    f"flavour) N={n} cubic L={L:.4f} rho=0.08", "bonds_per_step": n_bonds},
+                h2d=12 * n, d2h=8 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, r_max=r_max,
+                diameter=diameter,
+                secondary={"bonds": n_bonds})
+
+
+def cpu_reference_local_density(box, pts, r_max, diameter, budget_s=12.0, threads=None):
+    """The reference's LocalDensity::compute (AABBQuery engine, all host threads) on a bounded sample of query points."""
+    from oracle import ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        return {"value": None, "unit": "particles/s", "cores": threads, "kind": "port", "sample": "unavailable"}
+    q = ref.Query("aabb", box, pts)
+    probe = 20000
+    t0 = time.perf_counter()
+    ref.local_density(q, pts[:probe], r_max, diameter, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    m = int(min(len(pts), max(probe, probe * budget_s / max(dt, 1e-6) * 0.8)))
+    t0 = time.perf_counter()
+    ref.local_density(q, pts[:m], r_max, diameter, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "particles/s", "cores": threads, "kind": "reference",
+            "sample": f"reference LocalDensity({r_max:g}, {diameter:g}).compute via AABBQuery: first {m} of {len(pts)} "
+                      f"query points in {dt:.2f} s"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_nl(box, pts, r_max, budget_s=12.0, threads=None):
     """The reference's own LinkCell (oracle/_ref, all host threads) on a bounded sample of query points.
@@ -338,7 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d"])
+    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density"])
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -348,7 +409,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
-                 "rdf4m": 4_000_000, "traj2d": 1_000_000}[args.workload]
+                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000}[args.workload]
     n = args.n or n_default
 
     if args.impl == "reference":
@@ -379,6 +440,9 @@ def main():
         scaling = "weak"
     elif args.workload == "q6":
         w = workload_q6(ctx, rank, n)
+        scaling = "weak"
+    elif args.workload == "local_density":
+        w = workload_local_density(ctx, rank, n)
         scaling = "weak"
     elif args.workload == "rdf4m":
         w = workload_rdf4m(ctx, rank, world, n, comm)
@@ -423,7 +487,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt")
+             "rdf_distances", "steinhardt", "local_density")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]
@@ -507,6 +571,8 @@ def main():
                 line["cpu_baseline"] = cpu_reference_nl(w["box"], w["pts"], w["r_max"])
             elif args.workload in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
                 line["cpu_baseline"] = cpu_reference_rdf(w["box"], w["pts"], w["rdf"].bins, w["r_max"])
+            elif args.workload == "local_density":
+                line["cpu_baseline"] = cpu_reference_local_density(w["box"], w["pts"], w["r_max"], w["diameter"])
             else:
                 line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
@@ -635,6 +701,12 @@ def run_reference_arm(args, rank, world, n):
         runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "rdf_frames_per_sec", "frames/s"
         config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"}
+    elif args.workload == "local_density":
+        L = (n / RHO) ** (1.0 / 3.0)
+        box, pts = data.make_random_system(L, n, seed=0)
+        runs = [cpu_reference_local_density(box, pts, 2.5, 1.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        metric, unit = "local_density_particles_per_sec", "particles/s"
+        config = {"workload": f"LocalDensity r_max=2.5 diameter=1 N={n} cubic L={L:.4f} rho=0.08"}
     else:
         m = max(2, round((n / 4) ** (1.0 / 3.0)))
         box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=0)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
     "fgpu_rdf_read": (C.c_int, [_vp, _up]),
     "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
+    "fgpu_local_density": (C.c_int, [_vp, C.c_float, C.c_float, C.c_int, _fp, _fp]),
     "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp,
                                          _fp]),
     "fgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
@@ -236,6 +237,15 @@ class DeviceNeighborList(_DeviceObject):
         check(lib().fgpu_nlist_copy(self._h, ptr(out["neighbors"], _up), ptr(out["distances"]), ptr(out["weights"]),
                                     ptr(out["vectors"]), ptr(out["segments"], _up), ptr(out["counts"], _up)))
         return out
+
+    def local_density(self, r_max, diameter, is2d=False, out=None):
+        """(num_neighbors, density) of ``fgpu_local_density`` over this list's rows; ``out``: optional pair of
+        preallocated (e.g. page-locked) float32 arrays of length num_query_points."""
+        num, den = out if out is not None else (np.empty(self.num_query_points, np.float32),
+                                                np.empty(self.num_query_points, np.float32))
+        assert num.dtype == np.float32 and den.dtype == np.float32 and num.size == den.size == self.num_query_points
+        check(lib().fgpu_local_density(self._h, float(r_max), float(diameter), int(bool(is2d)), ptr(num), ptr(den)))
+        return num, den
 
     @classmethod
     def from_host(cls, ctx, neighbors, distances, weights, vectors, n_query, n_points):

@@ -1460,6 +1460,39 @@ int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
 }
 
 // ---- Steinhardt ------------------------------------------------------------------------------------------
+int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is2d, float* num_neighbors_host,
+                       float* density_host)
+{
+    return guarded([&] {
+        require(nl != nullptr, FGPU_EINVALID, "null argument");
+        require(r_max > 0, FGPU_EINVALID, "LocalDensity requires r_max to be positive.");
+        require(!(diameter < 0), FGPU_EINVALID, "LocalDensity requires diameter to be non-negative.");
+        fgpu_ctx* ctx = nl->ctx;
+        bind_device(ctx);
+        uint32_t const n = nl->n_query;
+        // LocalDensity.cc:48-49: area = M_PI * r * r (double, rounded once); volume = float(4/3 pi) * r * r * r
+        volatile float vol = static_cast<float>(4.0 / 3.0 * M_PI);
+        vol = vol * r_max;
+        vol = vol * r_max;
+        vol = vol * r_max;
+        float const measure = is2d ? (float) (M_PI * (double) r_max * (double) r_max) : (float) vol;
+        DevBuf<float> d_num, d_den;
+        d_num.reserve((size_t) n + 1);
+        d_den.reserve((size_t) n + 1);
+        launch_local_density(ctx, nl->row_start.ptr, nl->distances.ptr, n, r_max, diameter, measure, d_num.ptr,
+                             d_den.ptr);
+        if (num_neighbors_host != nullptr)
+        {
+            d2h(ctx, num_neighbors_host, d_num.ptr, (size_t) n * sizeof(float));
+        }
+        if (density_host != nullptr)
+        {
+            d2h(ctx, density_host, d_den.ptr, (size_t) n * sizeof(float));
+        }
+        sync(ctx);
+    });
+}
+
 int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
                             uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
                             float* sys_qlm_host, float* order_host)

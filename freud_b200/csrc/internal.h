@@ -439,6 +439,8 @@ struct KnnSelectArgs
 void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs& a);
 
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
+void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,
+                          float diameter, float measure, float* num_neighbors, float* density);
 
 struct SteinhardtArgs
 {

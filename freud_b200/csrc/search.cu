@@ -483,6 +483,55 @@ void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* c
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
+// LocalDensity::compute (freud/density/LocalDensity.cc:38-84) over a NeighborList: one thread per query point walks
+// its row in list order and sums, in float and in that order, 1 for a point wholly inside r_max and
+// 1 + (r_max - (d + diameter/2)) / diameter for one that straddles it; density = count / area (2-D) or / volume.
+// Rows without bonds stay 0 (upstream only ever writes inside the bond loop).
+__global__ void __launch_bounds__(256) k_local_density(const uint32_t* __restrict__ row_start, const float* __restrict__ distances,
+                                                       uint32_t n_query, float r_max, float diameter, float measure,
+                                                       float* __restrict__ num_neighbors, float* __restrict__ density)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_query)
+    {
+        return;
+    }
+    uint32_t const beg = row_start[i], end = row_start[i + 1];
+    float const half = __fdiv_rn(diameter, 2.0f);
+    float const inner = __fsub_rn(r_max, half);
+    float num = 0.0f;
+    for (uint32_t b = beg; b < end; ++b)
+    {
+        float const d = distances[b];
+        if (d < inner)
+        {
+            num = __fadd_rn(num, 1.0f);
+        }
+        else
+        {
+            float const part = __fdiv_rn(__fsub_rn(r_max, __fadd_rn(d, half)), diameter);
+            num = __fadd_rn(num, __fadd_rn(1.0f, part));
+        }
+    }
+    num_neighbors[i] = num;
+    density[i] = beg == end ? 0.0f : __fdiv_rn(num, measure);
+}
+
+void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,
+                          float diameter, float measure, float* num_neighbors, float* density)
+{
+    if (n_query == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "local_density");
+        k_local_density<<<(n_query + 255) / 256, 256, 0, ctx->stream>>>(row_start, distances, n_query, r_max, diameter,
+                                                                        measure, num_neighbors, density);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist)
 {
     if (n == 0)

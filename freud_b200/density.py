@@ -1,5 +1,5 @@
-"""``freud.density.RDF`` on the GPU path (reference ``freud/density.py:535-696`` + the ``_SpatialHistogram1D``
-properties of ``freud/locality.py:1019-1098``)."""
+"""``freud.density.RDF`` (reference ``freud/density.py:535-696`` + the ``_SpatialHistogram1D`` properties of
+``freud/locality.py:1019-1098``) and ``freud.density.LocalDensity`` (``freud/density.py:418-533``) on the GPU path."""
 
 import numpy as np
 
@@ -50,3 +50,53 @@ class RDF(_PairCompute):
         b = self._cpp_obj.getBox()
         return Box(b.getLx(), b.getLy(), b.getLz(), b.getTiltFactorXY(), b.getTiltFactorXZ(), b.getTiltFactorYZ(),
                    b.is2D())
+
+
+def _box_of(cpp_box):
+    from .box import Box
+
+    return Box(cpp_box.getLx(), cpp_box.getLy(), cpp_box.getLz(), cpp_box.getTiltFactorXY(), cpp_box.getTiltFactorXZ(),
+               cpp_box.getTiltFactorYZ(), cpp_box.is2D())
+
+
+class LocalDensity(_PairCompute):
+    """``freud.density.LocalDensity``: fractional neighbour count inside ``r_max`` and the density it implies."""
+
+    def __init__(self, r_max, diameter):
+        self._cpp_obj = _ext()._density.LocalDensity(float(r_max), float(diameter))
+        self._computed = False
+
+    r_max = property(lambda self: self._cpp_obj.getRMax())
+    diameter = property(lambda self: self._cpp_obj.getDiameter())
+
+    @property
+    def default_query_args(self):
+        return dict(mode="ball", r_max=self.r_max + 0.5 * self.diameter)  # freud/density.py:510-514
+
+    def compute(self, system, query_points=None, neighbors=None):
+        nq, nlist, qargs, qp = self._preprocess_arguments(system, query_points, neighbors)
+        self._cpp_obj.compute(nq._cpp_obj, qp, nlist, qargs)
+        self._computed = True
+        return self
+
+    def _need(self):
+        if not self._computed:  # _Compute._computed_property, freud/util.py
+            raise AttributeError("Property not computed. Call compute first.")
+
+    @property
+    def box(self):
+        self._need()
+        return _box_of(self._cpp_obj.box)
+
+    @property
+    def density(self):
+        self._need()
+        return self._cpp_obj.density
+
+    @property
+    def num_neighbors(self):
+        self._need()
+        return self._cpp_obj.num_neighbors
+
+    def __repr__(self):
+        return f"freud.density.{type(self).__name__}(r_max={self.r_max}, diameter={self.diameter})"

@@ -16,6 +16,7 @@
 #include "Box.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
+#include "LocalDensity.h"
 #include "RDF.h"
 #include "Steinhardt.h"
 
@@ -231,6 +232,23 @@ PYBIND11_MODULE(_freud_b200, m)
         .def("getBox", &density::RDF::getBox)
         .def("reset", &density::RDF::reset)
         .def_readwrite("mode", &density::RDF::mode);
+    // freud/density/export-LocalDensity.cc:37-47
+    py::class_<density::LocalDensity, std::shared_ptr<density::LocalDensity>>(mden, "LocalDensity")
+        .def(py::init<float, float>(), py::arg("r_max"), py::arg("diameter"))
+        .def("compute",
+             [](density::LocalDensity& ld, std::shared_ptr<locality::NeighborQuery> nq, points_array qp,
+                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 ld.compute(nq, q, n, nlist, qargs);
+             },
+             py::arg("points"), py::arg("query_points"), py::arg("nlist").none(true), py::arg("qargs"))
+        .def("getRMax", &density::LocalDensity::getRMax)
+        .def("getDiameter", &density::LocalDensity::getDiameter)
+        .def_property_readonly("box", &density::LocalDensity::getBox)
+        .def_property_readonly("density", [](const density::LocalDensity& ld) { return to_numpy<float>(ld.getDensity()); })
+        .def_property_readonly("num_neighbors",
+                               [](const density::LocalDensity& ld) { return to_numpy<float>(ld.getNumNeighbors()); });
 
     // ---- _order ----------------------------------------------------------------------------------------
     auto mord = m.def_submodule("_order");

@@ -79,7 +79,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -191,6 +191,15 @@ int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl);
 int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
 /* sum the histograms of all ranks in place: one ncclAllReduce(u32[bins], sum) */
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
+
+/* ---- LocalDensity --------------------------------------------------------------------------------------
+ * Replaces LocalDensity::compute (freud/density/LocalDensity.cc:38-84) once the neighbours are a NeighborList (the
+ * host class runs the ball query of the reference's default arguments, r_max + diameter / 2, when none is given):
+ * per query point the fractional neighbour count -- summed in float in list order, so a list sorted like the one
+ * upstream was handed gives the same bits -- and count / (pi r_max^2) in 2-D boxes or / (4/3 pi r_max^3).
+ * Errors: r_max <= 0 or diameter < 0 -> FGPU_EINVALID (LocalDensity.cc:25-36).  Outputs: f32[n_query] each. */
+int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is2d, float* num_neighbors_host,
+                       float* density_host);
 
 /* ---- Steinhardt --------------------------------------------------------------------------------------
  * Replaces Steinhardt::compute (freud/order/Steinhardt.cc:85-118): baseCompute :120-222 with

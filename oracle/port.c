@@ -1461,3 +1461,44 @@ int fport_wigner3j(uint32_t l, float* out)
     wigner3j_table((int) l, out);
     return (int) wigner3j_count((int) l);
 }
+
+/* ---- LocalDensity ------------------------------------------------------------------------------------
+ * LocalDensity::compute (freud/density/LocalDensity.cc:38-84) over the rows of a NeighborList, in list order:
+ * a point wholly inside r_max counts 1, one straddling it 1 + (r_max - (d + diameter/2)) / diameter (:58-69);
+ * density = count / (M_PI r^2) in 2-D boxes (:48, double product rounded once) or / (float(4/3 pi) r r r) (:49).
+ * Rows without bonds keep 0 (the arrays are zero-initialised and only written inside the bond loop). */
+int fport_local_density(const float* nl_d, const uint32_t* segments, const uint32_t* counts, uint32_t n_query,
+                        float r_max, float diameter, int is2d, float* num_neighbors, float* density)
+{
+    float area = (float) (M_PI * r_max * r_max);
+    float volume = (float) (4.0 / 3.0 * M_PI);
+    volume = volume * r_max;
+    volume = volume * r_max;
+    volume = volume * r_max;
+    float half = diameter / 2.0f;
+    float inner = r_max - half;
+    for (uint32_t i = 0; i < n_query; ++i)
+    {
+        float num = 0;
+        uint32_t beg = counts[i] ? segments[i] : 0;
+        for (uint32_t kb = 0; kb < counts[i]; ++kb)
+        {
+            float d = nl_d[beg + kb];
+            if (d < inner)
+            {
+                num = num + 1.0f;
+            }
+            else
+            {
+                float t = d + half;
+                float u = r_max - t;
+                float part = u / diameter;
+                float inc = 1.0f + part;
+                num = num + inc;
+            }
+        }
+        num_neighbors[i] = num;
+        density[i] = counts[i] ? (is2d ? num / area : num / volume) : 0.0f;
+    }
+    return 0;
+}

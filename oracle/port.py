@@ -144,6 +144,19 @@ def rdf_reduce(counts, r_max, r_min, box, is2d, n_points, n_query_points, frames
     return dict(bin_counts=c, rdf=g, n_r=n, bin_edges=e, bin_centers=ce)
 
 
+def local_density(nlist, r_max, diameter, is2d=False):
+    """(num_neighbors, density) of LocalDensity::compute over the rows of an oracle NeighborList."""
+    d = _f32(nlist.distances)
+    seg = np.ascontiguousarray(nlist.segments, dtype=np.uint32)
+    cnt = np.ascontiguousarray(nlist.counts, dtype=np.uint32)
+    num, den = np.zeros(len(seg), np.float32), np.zeros(len(seg), np.float32)
+    L = lib()
+    L.fport_local_density.argtypes = [_fp, _up, _up, C.c_uint32, C.c_float, C.c_float, C.c_int, _fp, _fp]
+    L.fport_local_density(_p(d), _p(seg, _up), _p(cnt, _up), len(seg), float(r_max), float(diameter), int(bool(is2d)),
+                          _p(num), _p(den))
+    return num, den
+
+
 def wigner3j(l):
     """(l l l; m1 m2 m3) in the order of reduceWigner3j's table (Wigner3j.cc:43-55), as float."""
     out = np.zeros(3 * l * l + 3 * l + 1, np.float32)

@@ -207,6 +207,21 @@ class RDF:
             self._h = None
 
 
+def local_density(query, query_points, r_max, diameter, nlist=None, q_r_max=None, exclude_ii=False):
+    """LocalDensity(r_max, diameter).compute(...) of the reference: (num_neighbors, density).  Without a NeighborList
+    it queries a ball of q_r_max (default r_max + diameter / 2, freud/density.py:510-514) on the fly."""
+    q = _f32(query_points, 3)
+    num, den = np.zeros(len(q), np.float32), np.zeros(len(q), np.float32)
+    L = lib()
+    L.fref_local_density.argtypes = [C.c_void_p, _fp, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                     _fp, _fp]
+    qr = r_max + 0.5 * diameter if q_r_max is None else q_r_max
+    if L.fref_local_density(query._h, _p(q), len(q), nlist._h if nlist is not None else None, float(r_max),
+                            float(diameter), float(qr), int(bool(exclude_ii)), _p(num), _p(den)):
+        _raise()
+    return num, den
+
+
 class Steinhardt:
     def __init__(self, l, average=False, wl=False, weighted=False, wl_normalize=False):
         self.ls = np.atleast_1d(np.asarray(l, dtype=np.uint32)).copy()

@@ -10,6 +10,7 @@
 //   freud::locality::CellQuery                       freud/locality/CellQuery.h:29
 //   NeighborQuery::query / toNeighborList            freud/locality/NeighborQuery.h:130,434
 //   freud::density::RDF                              freud/density/RDF.h:33
+//   freud::density::LocalDensity                     freud/density/LocalDensity.h:29
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
 
@@ -24,6 +25,7 @@
 #include "Box.h"
 #include "CellQuery.h"
 #include "LinkCell.h"
+#include "LocalDensity.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
 #include "RDF.h"
@@ -297,6 +299,26 @@ int fref_rdf_get(void* rdf, unsigned* bin_counts, float* g_r, float* n_r, float*
             auto c = r->getBinCenters()[0];
             std::memcpy(bin_centers, c.data(), bins * sizeof(float));
         }
+    });
+}
+
+// ---- LocalDensity ---------------------------------------------------------------------------------
+// LocalDensity(r_max, diameter).compute(nq, query_points, n, nlist /*nullable*/, qargs); outputs n_query floats each
+int fref_local_density(void* nq, const float* qpts, unsigned n_query, void* nlist_or_null, float r_max, float diameter,
+                       float q_r_max, int exclude_ii, float* num_neighbors, float* density)
+{
+    return guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        std::shared_ptr<NeighborList> nl;
+        if (nlist_or_null != nullptr)
+        {
+            nl = *static_cast<std::shared_ptr<NeighborList>*>(nlist_or_null);
+        }
+        QueryArgs const args = makeArgs(/*ball*/ 1, 0xffffffffU, q_r_max, 0.0F, -1.0F, -1.0F, exclude_ii);
+        freud::density::LocalDensity ld(r_max, diameter);
+        ld.compute(h->nq, reinterpret_cast<const vec3<float>*>(qpts), n_query, nl, args);
+        std::memcpy(num_neighbors, ld.getNumNeighbors()->data(), n_query * sizeof(float));
+        std::memcpy(density, ld.getDensity()->data(), n_query * sizeof(float));
     });
 }
 

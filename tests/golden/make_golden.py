@@ -87,6 +87,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "steinhardt_fcc.npz"), **out)
     print("steinhardt", out["knn12_ql_6"][:3, 0])
     steinhardt_options()
+    local_density()
 
 
 STEINHARDT_OPTIONS = {
@@ -112,6 +113,24 @@ def steinhardt_options():
             out[f"{key}_order"] = r["order"]
     np.savez_compressed(os.path.join(HERE, "steinhardt_options.npz"), **out)
     print("steinhardt options", out["ave_wln_6_particle_order"][:3, 0], out["ave_wln_6_order"])
+
+
+def local_density():
+    """LocalDensity(r_max=3, diameter=1) and (2, 0.5) (LocalDensity.cc:38-84): with a NeighborList handed in (bonds summed
+    in list order: the bit-exact target) and with the default on-the-fly query (engine order: tolerance)."""
+    out = {}
+    for name, box, n in (("cube", Box.cube(10), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 123), random_points(box, 500, 124)
+        Q = ref.Query("aabb", box, pts, is2d=box.is2D)
+        for r_max, diameter in ((3.0, 1.0), (2.0, 0.5)):
+            key = f"{name}_{r_max:g}_{diameter:g}"
+            nl = Q.nlist(q, mode="ball", r_max=r_max + 0.5 * diameter)
+            out[f"{key}_nlist_num"], out[f"{key}_nlist_density"] = ref.local_density(Q, q, r_max, diameter, nlist=nl)
+            out[f"{key}_query_num"], out[f"{key}_query_density"] = ref.local_density(Q, q, r_max, diameter)
+            out[f"{key}_self_num"], out[f"{key}_self_density"] = ref.local_density(Q, pts, r_max, diameter,
+                                                                                   exclude_ii=True)
+    np.savez_compressed(os.path.join(HERE, "local_density.npz"), **out)
+    print("local density", out["cube_3_1_nlist_num"][:3], out["cube_3_1_nlist_density"][:3])
 
 
 if __name__ == "__main__":

@@ -193,6 +193,40 @@ def test_steinhardt_vs_reference_noisy_fcc():
         np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
 
 
+def test_local_density_api():
+    """freud.density.LocalDensity (tests/test_density_local_density.py:21-110 upstream): attribute access, the known
+    ranges of the reference's own test, default query arguments, an explicit NeighborList, query points != points."""
+    box, pts = data.make_random_system(10, 10000, seed=123)
+    ld = density.LocalDensity(3, 1)
+    assert ld.r_max == 3 and ld.diameter == 1 and ld.default_query_args == dict(mode="ball", r_max=3.5)
+    for attr in ("density", "num_neighbors", "box"):
+        with pytest.raises(AttributeError):
+            getattr(ld, attr)
+    ld.compute(locality.AABBQuery(box, pts), neighbors=dict(mode="ball", r_max=3.5, exclude_ii=True))
+    assert ld.box == Box.cube(10)
+    assert (np.fabs(ld.density - 10.0) < 1.5).all() and (np.fabs(ld.num_neighbors - 1130.973355292) < 200).all()
+    ld.compute((box, pts))  # default arguments, the points against themselves
+    assert (np.fabs(ld.density - 10.0) < 1.5).all()
+    # against the reference: committed outputs (on-the-fly query: summation order) and a handed-in list (bit for bit)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "local_density.npz"))
+    box, n = Box.cube(10), 3000
+    pts, q = random_points(box, n, 123), random_points(box, 500, 124)
+    ld = density.LocalDensity(3.0, 1.0).compute((box, pts), query_points=q)
+    np.testing.assert_allclose(ld.num_neighbors, gold["cube_3_1_query_num"], rtol=1e-5)
+    np.testing.assert_allclose(ld.density, gold["cube_3_1_query_density"], rtol=1e-5)
+    ld = density.LocalDensity(3.0, 1.0).compute((box, pts))
+    np.testing.assert_allclose(ld.num_neighbors, gold["cube_3_1_self_num"], rtol=1e-5)
+    nl = locality.AABBQuery(box, pts).query(q, dict(r_max=3.5)).toNeighborList()
+    ld = density.LocalDensity(3.0, 1.0).compute((box, pts), query_points=q, neighbors=nl)
+    assert np.array_equal(bits(ld.num_neighbors), bits(gold["cube_3_1_nlist_num"]))
+    assert np.array_equal(bits(ld.density), bits(gold["cube_3_1_nlist_density"]))
+    with pytest.raises(ValueError):
+        density.LocalDensity(0, 1)
+    with pytest.raises(ValueError):
+        density.LocalDensity(1, -1)
+    assert repr(ld) == "freud.density.LocalDensity(r_max=3.0, diameter=1.0)"
+
+
 def test_cellquery_engine():
     """freud.locality.CellQuery (tests/test_locality_neighbor_query.py:697-811 upstream): ball queries in its own
     arithmetic, nearest-neighbour queries refused with the reference's message, r_max validated against the box."""

@@ -285,6 +285,32 @@ def test_knn(ctx, name):
 GHOST = 2
 
 
+def test_local_density_over_a_neighbor_list(ctx):
+    """fgpu_local_density (LocalDensity.cc:38-84) over device NeighborLists: the same bits as the oracle over the same
+    list, in 3-D and 2-D, and the committed outputs of the reference."""
+    from freud_b200.box import Box
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "local_density.npz"))
+    for name, box, n in (("cube", Box.cube(10), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 123), random_points(box, 500, 124)
+        dp = capi.DevicePoints(ctx, box, pts)
+        for r_max, diameter in ((3.0, 1.0), (2.0, 0.5)):
+            key = f"{name}_{r_max:g}_{diameter:g}"
+            nl = dp.ball_query(q, IMAGE, r_max + 0.5 * diameter, 0.0, False)
+            num, den = nl.local_density(r_max, diameter, box.is2D)
+            assert np.array_equal(bits(num), bits(gold[f"{key}_nlist_num"])), key
+            assert np.array_equal(bits(den), bits(gold[f"{key}_nlist_density"])), key
+            want = port.local_density(port.ball_nlist(port.WRAP, box, box.is2D, pts, pts, r_max + 0.5 * diameter, 0.0, True),
+                                      r_max, diameter, box.is2D)
+            got = dp.ball_query(None, WRAP, r_max + 0.5 * diameter, 0.0, True).local_density(r_max, diameter, box.is2D)
+            assert np.array_equal(bits(got[0]), bits(want[0])) and np.array_equal(bits(got[1]), bits(want[1])), key
+    with pytest.raises(ValueError):
+        nl.local_density(-1.0, 1.0)
+    with pytest.raises(ValueError):
+        nl.local_density(1.0, -1.0)
+
+
 @pytest.mark.parametrize("name", list(BOXES))
 def test_ghost_flavour_ball_and_rdf(ctx, name):
     """CellQuery's arithmetic r = (p_j + shift) - q (CellQuery.cc:107, CellIterator.h:167; E5 in oracle/port.c):

@@ -130,6 +130,22 @@ def test_port_matches_golden_steinhardt_options(tag):
         np.testing.assert_allclose(out["order"], gold[f"{key}_order"], rtol=1e-5, atol=1e-8)
 
 
+def test_port_local_density_matches_golden():
+    """LocalDensity::compute restated in oracle/port.c against outputs of the reference (tests/golden/local_density.npz):
+    bit for bit when the bonds are summed in list order, to summation order against the on-the-fly query."""
+    gold = np.load(os.path.join(GOLD, "local_density.npz"))
+    for name, box, n in (("cube", Box.cube(10), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 123), random_points(box, 500, 124)
+        for r_max, diameter in ((3.0, 1.0), (2.0, 0.5)):
+            key = f"{name}_{r_max:g}_{diameter:g}"
+            nl = port.ball_nlist(port.IMAGE, box, box.is2D, pts, q, r_max + 0.5 * diameter, 0.0, False)
+            num, den = port.local_density(nl, r_max, diameter, box.is2D)
+            assert np.array_equal(bits(num), bits(gold[f"{key}_nlist_num"])), key
+            assert np.array_equal(bits(den), bits(gold[f"{key}_nlist_density"])), key
+            np.testing.assert_allclose(num, gold[f"{key}_query_num"], rtol=1e-5)
+            np.testing.assert_allclose(den, gold[f"{key}_query_density"], rtol=1e-5)
+
+
 def test_port_wigner3j_known_values():
     """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
     the reference is present, every tabulated l <= 20 as float."""
