@@ -99,7 +99,7 @@ def pinned_empty(shape, dtype):
     """numpy view of pinned host memory (torch is plumbing here: it owns the page-locked allocation)."""
     import torch
 
-    tdt = {np.float32: torch.float32, np.uint32: torch.int32}[dtype]
+    tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.complex128: torch.complex128}[dtype]
     t = torch.empty(tuple(int(s) for s in np.atleast_1d(shape)), dtype=tdt, pin_memory=True)
     return t.numpy().view(dtype), t  # the caller keeps t alive
 
@@ -275,6 +275,71 @@ def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
                 secondary={"bonds": n_bonds})
 
 
+def workload_correlation(ctx, rank, n, bins=100, r_max=3.0):
+    """SURVEY.md section 8f rank 3, second client: freud.density.CorrelationFunction(bins, r_max).compute((box, points),
+    values) on the C2 system with complex values -- ball query (IMAGE arithmetic), then counts and complex<double>
+    sums per distance bin."""
+    from freud_b200 import _capi, data
+
+    L = (n / RHO) ** (1.0 / 3.0)
+    box, pts = data.make_random_system(L, n, seed=rank)
+    rs = np.random.RandomState(rank + 17)
+    values, keep1 = pinned_empty((n,), np.complex128)
+    values[:] = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    cf = _capi.DeviceCorrelation(ctx, bins, r_max)
+    n_bonds = dp.ball_query(None, IMAGE, r_max, 0.0, True).num_bonds
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+
+    def step_dev():
+        # the values (16 MB of complex128, page-locked) cross PCIe in every call: the C ABI takes them from the host
+        cf.reset()
+        dp.build_cells(r_max)
+        cf.accumulate_nlist(dp.ball_query(None, IMAGE, r_max, 0.0, True), values, values)
+        return cf.read()
+
+    def step_e2e():
+        cf.reset()
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        cf.accumulate_nlist(d.ball_query(None, IMAGE, r_max, 0.0, True), values, values)
+        return cf.read()[1]
+
+    n_cells = int(np.prod(dp.build_cells(r_max)))
+    algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
+            "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
+            "correlation": 12 * n_bonds + 32 * n_bonds + 20 * bins,  # (i, j, d) per bond + two gathered complex128
+            "pipeline": 16 * (n + n) + 32 * n + 20 * bins}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s",
+                metric="correlation_function_particles_per_sec",
+                config={"workload": f"CorrelationFunction bins={bins} r_max={r_max:g} complex values (image flavour) "
+                                    f"N={n} cubic L={L:.4f} rho=0.08", "bonds_per_step": n_bonds},
+                h2d=12 * n + 16 * n, d2h=20 * bins, algo=algo, keep=[keep0, keep1], box=box, pts=pts, r_max=r_max,
+                bins=bins, values=values, secondary={"bonds": n_bonds})
+
+
+def cpu_reference_correlation(box, pts, values, bins, r_max, budget_s=12.0, threads=None):
+    """The reference's CorrelationFunction (AABBQuery engine, all host threads) on a bounded sample of query points."""
+    from oracle import ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        return {"value": None, "unit": "particles/s", "cores": threads, "kind": "port", "sample": "unavailable"}
+    q = ref.Query("aabb", box, pts)
+    probe = 20000
+    t0 = time.perf_counter()
+    ref.correlation_function(q, values, pts[:probe], values[:probe], bins, r_max, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    m = int(min(len(pts), max(probe, probe * budget_s / max(dt, 1e-6) * 0.8)))
+    t0 = time.perf_counter()
+    ref.correlation_function(q, values, pts[:m], values[:m], bins, r_max, exclude_ii=True)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "particles/s", "cores": threads, "kind": "reference",
+            "sample": f"reference CorrelationFunction({bins}, {r_max:g}).compute via AABBQuery: first {m} of {len(pts)} "
+                      f"query points in {dt:.2f} s"}
+
+
 def cpu_reference_local_density(box, pts, r_max, diameter, budget_s=12.0, threads=None):
     """The reference's LocalDensity::compute (AABBQuery engine, all host threads) on a bounded sample of query points."""
     from oracle import ref
@@ -399,7 +464,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density"])
+    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation"])
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -409,7 +474,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
-                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000}[args.workload]
+                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000}[args.workload]
     n = args.n or n_default
 
     if args.impl == "reference":
@@ -443,6 +508,9 @@ def main():
         scaling = "weak"
     elif args.workload == "local_density":
         w = workload_local_density(ctx, rank, n)
+        scaling = "weak"
+    elif args.workload == "correlation":
+        w = workload_correlation(ctx, rank, n)
         scaling = "weak"
     elif args.workload == "rdf4m":
         w = workload_rdf4m(ctx, rank, world, n, comm)
@@ -487,7 +555,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density")
+             "rdf_distances", "steinhardt", "local_density", "correlation")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]
@@ -573,6 +641,8 @@ def main():
                 line["cpu_baseline"] = cpu_reference_rdf(w["box"], w["pts"], w["rdf"].bins, w["r_max"])
             elif args.workload == "local_density":
                 line["cpu_baseline"] = cpu_reference_local_density(w["box"], w["pts"], w["r_max"], w["diameter"])
+            elif args.workload == "correlation":
+                line["cpu_baseline"] = cpu_reference_correlation(w["box"], w["pts"], w["values"], w["bins"], w["r_max"])
             else:
                 line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
@@ -701,6 +771,14 @@ def run_reference_arm(args, rank, world, n):
         runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "rdf_frames_per_sec", "frames/s"
         config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"}
+    elif args.workload == "correlation":
+        L = (n / RHO) ** (1.0 / 3.0)
+        box, pts = data.make_random_system(L, n, seed=0)
+        rs = np.random.RandomState(17)
+        values = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+        runs = [cpu_reference_correlation(box, pts, values, 100, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        metric, unit = "correlation_function_particles_per_sec", "particles/s"
+        config = {"workload": f"CorrelationFunction bins=100 r_max=3 complex values N={n} cubic L={L:.4f} rho=0.08"}
     elif args.workload == "local_density":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)

@@ -66,6 +66,11 @@ SIGNATURES = {
     "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
     "fgpu_rdf_read": (C.c_int, [_vp, _up]),
     "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
+    "fgpu_corr_create": (C.c_int, [_vp, C.c_uint32, C.c_float, _vpp]),
+    "fgpu_corr_destroy": (None, [_vp]),
+    "fgpu_corr_reset": (C.c_int, [_vp]),
+    "fgpu_corr_accumulate_nlist": (C.c_int, [_vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "fgpu_corr_read": (C.c_int, [_vp, _up, C.POINTER(C.c_double)]),
     "fgpu_local_density": (C.c_int, [_vp, C.c_float, C.c_float, C.c_int, _fp, _fp]),
     "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp,
                                          _fp]),
@@ -370,6 +375,34 @@ class DeviceRDF(_DeviceObject):
 
     def allreduce(self, comm):
         check(lib().fgpu_rdf_allreduce(self._h, comm._h))
+
+
+class DeviceCorrelation(_DeviceObject):
+    """Device-resident CorrelationFunction accumulators (``fgpu_corr``)."""
+
+    _destroy = "fgpu_corr_destroy"
+
+    def __init__(self, ctx, bins, r_max):
+        self._adopt(ctx)
+        self.bins = int(bins)
+        self._h = _vp()
+        check(lib().fgpu_corr_create(ctx._h, self.bins, float(r_max), C.byref(self._h)))
+
+    def reset(self):
+        check(lib().fgpu_corr_reset(self._h))
+
+    def accumulate_nlist(self, nlist, values, query_values):
+        v = np.ascontiguousarray(values, dtype=np.complex128).ravel()
+        q = v if query_values is values else np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
+        assert len(v) == nlist.num_points and len(q) == nlist.num_query_points
+        dp = C.POINTER(C.c_double)
+        check(lib().fgpu_corr_accumulate_nlist(self._h, nlist._h, v.ctypes.data_as(dp), q.ctypes.data_as(dp)))
+
+    def read(self):
+        counts = np.empty(self.bins, np.uint32)
+        sums = np.empty(self.bins, np.complex128)
+        check(lib().fgpu_corr_read(self._h, ptr(counts, _up), sums.ctypes.data_as(C.POINTER(C.c_double))))
+        return counts, sums
 
 
 class Communicator(_DeviceObject):

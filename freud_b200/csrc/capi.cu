@@ -1460,6 +1460,94 @@ int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
 }
 
 // ---- Steinhardt ------------------------------------------------------------------------------------------
+int fgpu_corr_create(fgpu_ctx* ctx, uint32_t bins, float r_max, fgpu_corr** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        // CorrelationFunction.cc:28-35
+        require(bins != 0, FGPU_EINVALID, "CorrelationFunction  requires a nonzero number of bins.");
+        require(r_max > 0, FGPU_EINVALID, "CorrelationFunction requires r_max to be positive.");
+        bind_device(ctx);
+        std::unique_ptr<fgpu_corr> c(new fgpu_corr());
+        c->ctx = ctx;
+        volatile float span = r_max - 0.0f; // RegularAxis ctor, Histogram.h:126-138
+        volatile float width = span / (float) bins;
+        volatile float inv = 1.0f / width;
+        c->axis.r_min = 0.0f;
+        c->axis.r_max = r_max;
+        c->axis.inv_width = inv;
+        c->axis.bins = bins;
+        c->counts.reserve(bins);
+        c->sums.reserve(2 * (size_t) bins);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(c->counts.ptr, 0, (size_t) bins * sizeof(uint32_t), ctx->stream));
+        FGPU_CUDA_CHECK(cudaMemsetAsync(c->sums.ptr, 0, 2 * (size_t) bins * sizeof(double), ctx->stream));
+        sync(ctx);
+        *out = c.release();
+    });
+}
+
+void fgpu_corr_destroy(fgpu_corr* corr)
+{
+    if (corr != nullptr)
+    {
+        bind_quiet(corr->ctx);
+        delete corr;
+    }
+}
+
+int fgpu_corr_reset(fgpu_corr* corr)
+{
+    return guarded([&] {
+        require(corr != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(corr->ctx);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(corr->counts.ptr, 0, (size_t) corr->axis.bins * sizeof(uint32_t), corr->ctx->stream));
+        FGPU_CUDA_CHECK(cudaMemsetAsync(corr->sums.ptr, 0, 2 * (size_t) corr->axis.bins * sizeof(double), corr->ctx->stream));
+    });
+}
+
+int fgpu_corr_accumulate_nlist(fgpu_corr* corr, const fgpu_nlist* nl, const double* values_host,
+                               const double* query_values_host)
+{
+    return guarded([&] {
+        require(corr != nullptr && nl != nullptr && values_host != nullptr && query_values_host != nullptr, FGPU_EINVALID,
+                "null argument");
+        require(corr->ctx == nl->ctx, FGPU_EINVALID, "corr and nlist belong to different contexts");
+        fgpu_ctx* ctx = corr->ctx;
+        bind_device(ctx);
+        corr->values.reserve(2 * (size_t) nl->n_points + 2);
+        h2d(ctx, corr->values.ptr, values_host, 2 * (size_t) nl->n_points * sizeof(double));
+        const double* d_query_values = corr->values.ptr;
+        if (query_values_host != values_host || nl->n_query != nl->n_points)
+        {
+            // (the points against themselves hand in one array for both: uploaded once)
+            corr->query_values.reserve(2 * (size_t) nl->n_query + 2);
+            h2d(ctx, corr->query_values.ptr, query_values_host, 2 * (size_t) nl->n_query * sizeof(double));
+            d_query_values = corr->query_values.ptr;
+        }
+        launch_correlation(ctx, nl->neighbors.ptr, nl->distances.ptr, nl->n_bonds, corr->values.ptr, d_query_values,
+                           corr->axis, corr->counts.ptr, corr->sums.ptr);
+        sync(ctx); // the caller's value arrays were consumed
+    });
+}
+
+int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host)
+{
+    return guarded([&] {
+        require(corr != nullptr, FGPU_EINVALID, "null argument");
+        fgpu_ctx* ctx = corr->ctx;
+        bind_device(ctx);
+        if (counts_host != nullptr)
+        {
+            d2h(ctx, counts_host, corr->counts.ptr, (size_t) corr->axis.bins * sizeof(uint32_t));
+        }
+        if (sums_host != nullptr)
+        {
+            d2h(ctx, sums_host, corr->sums.ptr, 2 * (size_t) corr->axis.bins * sizeof(double));
+        }
+        sync(ctx);
+    });
+}
+
 int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is2d, float* num_neighbors_host,
                        float* density_host)
 {

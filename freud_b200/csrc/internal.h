@@ -196,6 +196,15 @@ struct fgpu_rdf
     fgpu::DevBuf<uint32_t> hist;
 };
 
+struct fgpu_corr
+{
+    fgpu_ctx* ctx = nullptr;
+    fgpu::AxisDev axis;
+    fgpu::DevBuf<uint32_t> counts; // bins
+    fgpu::DevBuf<double> sums;     // bins x (re, im)
+    fgpu::DevBuf<double> values, query_values; // staged per call
+};
+
 struct fgpu_comm
 {
     fgpu_ctx* ctx = nullptr;
@@ -439,6 +448,8 @@ struct KnnSelectArgs
 void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs& a);
 
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
+void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
+                        const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums);
 void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,
                           float diameter, float measure, float* num_neighbors, float* density);
 

@@ -483,6 +483,90 @@ void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* c
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
+// CorrelationFunction::accumulate (freud/density/CorrelationFunction.cc:81-95) over a NeighborList: per bond the bin of
+// its distance (RegularAxis(bins, 0, r_max)), one count and conj(values[j]) * query_values[i] in complex<double>.
+// Block-shared accumulators (u32 + two doubles per bin) merged once per block; bins that do not fit shared memory
+// go straight to global atomics.  The order of the double sums is not fixed -- upstream's thread-local sums are not
+// either -- so results agree to double rounding, not bit for bit.
+__global__ void __launch_bounds__(256) k_correlation(const uint32_t* __restrict__ neighbors, const float* __restrict__ distances,
+                                                     uint64_t n_bonds, const double2* __restrict__ values,
+                                                     const double2* __restrict__ query_values, AxisDev axis,
+                                                     uint32_t* __restrict__ counts, double* __restrict__ sums,
+                                                     int use_shared)
+{
+    extern __shared__ __align__(16) unsigned char corr_smem[];
+    double* const s_sum = reinterpret_cast<double*>(corr_smem);                    // 2 * bins
+    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(s_sum + 2 * (size_t) axis.bins); // bins
+    if (use_shared)
+    {
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            s_sum[2 * b] = 0.0;
+            s_sum[2 * b + 1] = 0.0;
+            s_cnt[b] = 0;
+        }
+        __syncthreads();
+    }
+    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
+    {
+        int const bin = axis_bin(axis, distances[k]);
+        if (bin < 0)
+        {
+            continue;
+        }
+        uint2 const ij = reinterpret_cast<const uint2*>(neighbors)[k];
+        double2 const x = values[ij.y], y = query_values[ij.x];
+        // std::conj(x) * y, CorrelationFunction.cc:69-72
+        double const re = __dadd_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y));
+        double const im = __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x));
+        if (use_shared)
+        {
+            atomicAdd(&s_cnt[bin], 1U);
+            atomicAdd(&s_sum[2 * bin], re);
+            atomicAdd(&s_sum[2 * bin + 1], im);
+        }
+        else
+        {
+            atomicAdd(&counts[bin], 1U);
+            atomicAdd(&sums[2 * bin], re);
+            atomicAdd(&sums[2 * bin + 1], im);
+        }
+    }
+    if (use_shared)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            if (s_cnt[b] != 0)
+            {
+                atomicAdd(&counts[b], s_cnt[b]);
+                atomicAdd(&sums[2 * b], s_sum[2 * b]);
+                atomicAdd(&sums[2 * b + 1], s_sum[2 * b + 1]);
+            }
+        }
+    }
+}
+
+void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
+                        const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums)
+{
+    if (n_bonds == 0)
+    {
+        return;
+    }
+    size_t const smem = (size_t) axis.bins * (2 * sizeof(double) + sizeof(uint32_t));
+    int const use_shared = smem <= 40 * 1024 ? 1 : 0;
+    // few blocks: every block merges 3 words per occupied bin into the same global accumulators at the end
+    unsigned const blocks = (unsigned) std::min<uint64_t>((n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 4U);
+    {
+        KernelScope ks(ctx, "correlation");
+        k_correlation<<<blocks, 256, use_shared ? smem : 0, ctx->stream>>>(
+            neighbors, distances, n_bonds, reinterpret_cast<const double2*>(values),
+            reinterpret_cast<const double2*>(query_values), axis, counts, sums, use_shared);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
 // LocalDensity::compute (freud/density/LocalDensity.cc:38-84) over a NeighborList: one thread per query point walks
 // its row in list order and sums, in float and in that order, 1 for a point wholly inside r_max and
 // 1 + (r_max - (d + diameter/2)) / diameter for one that straddles it; density = count / area (2-D) or / volume.

@@ -1,5 +1,6 @@
 """``freud.density.RDF`` (reference ``freud/density.py:535-696`` + the ``_SpatialHistogram1D`` properties of
-``freud/locality.py:1019-1098``) and ``freud.density.LocalDensity`` (``freud/density.py:418-533``) on the GPU path."""
+``freud/locality.py:1019-1098``) ``freud.density.LocalDensity`` (``freud/density.py:418-533``) and ``freud.density.CorrelationFunction``
+(``freud/density.py:31-165``) on the GPU path."""
 
 import numpy as np
 
@@ -100,3 +101,42 @@ class LocalDensity(_PairCompute):
 
     def __repr__(self):
         return f"freud.density.{type(self).__name__}(r_max={self.r_max}, diameter={self.diameter})"
+
+
+class CorrelationFunction(_PairCompute):
+    """``freud.density.CorrelationFunction``: C(r) = <conj(values_j) query_values_i> over the bonds of each distance bin."""
+
+    def __init__(self, bins, r_max):
+        self._cpp_obj = _ext()._density.CorrelationFunction(int(bins), float(r_max))
+        self.r_max = float(r_max)
+        self.is_complex = False
+
+    @property
+    def default_query_args(self):
+        return dict(mode="ball", r_max=self.r_max)  # freud/locality.py:1013-1016
+
+    def compute(self, system, values, query_points=None, query_values=None, neighbors=None, reset=True):
+        if reset:
+            self.is_complex = False
+            self._cpp_obj.reset()
+        nq, nlist, qargs, qp = self._preprocess_arguments(system, query_points, neighbors)
+        # freud/density.py:109-113: complex inputs in any accumulated frame make the result complex
+        self.is_complex = bool(self.is_complex or np.any(np.iscomplex(values))
+                               or (query_values is not None and np.any(np.iscomplex(query_values))))
+        values = np.ascontiguousarray(values, dtype=np.complex128).ravel()
+        # freud/density.py:131-135: the points correlate with themselves unless query points (and values) are given
+        query_values = values if query_values is None else np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
+        self._cpp_obj.accumulateCF(nq._cpp_obj, values, qp, query_values, nlist, qargs)
+        return self
+
+    @property
+    def correlation(self):
+        c = self._cpp_obj.getCorrelation()
+        return c if self.is_complex else np.real(c)  # freud/density.py:139-144
+
+    bin_counts = property(lambda self: self._cpp_obj.getBinCounts())
+    bin_edges = property(lambda self: np.array(self._cpp_obj.getBinEdges()[0], dtype=np.float32))
+    bin_centers = property(lambda self: np.array(self._cpp_obj.getBinCenters()[0], dtype=np.float32))
+    bounds = property(lambda self: tuple(self._cpp_obj.getBounds()[0]))
+    nbins = property(lambda self: self._cpp_obj.getAxisSizes()[0])
+    box = property(lambda self: _box_of(self._cpp_obj.getBox()))

@@ -16,6 +16,7 @@
 #include "Box.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
+#include "CorrelationFunction.h"
 #include "LocalDensity.h"
 #include "RDF.h"
 #include "Steinhardt.h"
@@ -232,6 +233,33 @@ PYBIND11_MODULE(_freud_b200, m)
         .def("getBox", &density::RDF::getBox)
         .def("reset", &density::RDF::reset)
         .def_readwrite("mode", &density::RDF::mode);
+    // freud/density/export-CorrelationFunction.cc
+    py::class_<density::CorrelationFunction, std::shared_ptr<density::CorrelationFunction>>(mden, "CorrelationFunction")
+        .def(py::init<unsigned int, float>(), py::arg("bins"), py::arg("r_max"))
+        .def("accumulateCF",
+             [](density::CorrelationFunction& cf, std::shared_ptr<locality::NeighborQuery> nq,
+                py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> values, points_array qp,
+                py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> query_values,
+                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 if ((size_t) values.size() != nq->getNPoints() || (size_t) query_values.size() != n)
+                 {
+                     throw std::invalid_argument("values / query_values must hold one number per point / query point");
+                 }
+                 cf.accumulate(nq, values.data(), q, query_values.data(), n, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("values"), py::arg("query_points"), py::arg("query_values"),
+             py::arg("nlist").none(true), py::arg("qargs"))
+        .def("getCorrelation",
+             [](density::CorrelationFunction& c) { return to_numpy<std::complex<double>>(c.getCorrelation()); })
+        .def("getBinCounts", [](density::CorrelationFunction& c) { return to_numpy<unsigned int>(c.getBinCounts()); })
+        .def("getBinEdges", &density::CorrelationFunction::getBinEdges)
+        .def("getBinCenters", &density::CorrelationFunction::getBinCenters)
+        .def("getBounds", &density::CorrelationFunction::getBounds)
+        .def("getAxisSizes", &density::CorrelationFunction::getAxisSizes)
+        .def("getBox", &density::CorrelationFunction::getBox)
+        .def("reset", &density::CorrelationFunction::reset);
     // freud/density/export-LocalDensity.cc:37-47
     py::class_<density::LocalDensity, std::shared_ptr<density::LocalDensity>>(mden, "LocalDensity")
         .def(py::init<float, float>(), py::arg("r_max"), py::arg("diameter"))

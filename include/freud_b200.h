@@ -48,6 +48,7 @@ typedef struct fgpu_ctx fgpu_ctx;       /* one GPU + one stream + scratch memory
 typedef struct fgpu_points fgpu_points; /* device-resident reference points + box + cell list */
 typedef struct fgpu_nlist fgpu_nlist;   /* device-resident NeighborList (SoA, CSR)            */
 typedef struct fgpu_rdf fgpu_rdf;       /* device-resident RDF histogram accumulator          */
+typedef struct fgpu_corr fgpu_corr;     /* device-resident CorrelationFunction accumulators  */
 typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
 
 const char* fgpu_last_error(void);
@@ -79,7 +80,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -191,6 +192,20 @@ int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl);
 int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
 /* sum the histograms of all ranks in place: one ncclAllReduce(u32[bins], sum) */
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
+
+/* ---- CorrelationFunction ---------------------------------------------------------------------------------
+ * Device half of freud::density::CorrelationFunction (freud/density/CorrelationFunction.cc:26-95): per bin of
+ * RegularAxis(bins, 0, r_max) a u32 bond count and the complex<double> sum of conj(values[j]) * query_values[i]
+ * over the bonds of a NeighborList, resident across accumulate calls (compute(..., reset=False)).  The division by
+ * the counts (reduce, :49-59) is host arithmetic in freud_b200/host/CorrelationFunction.h.  Double sums are added in
+ * no fixed order, as upstream's thread-local histograms are: agreement is to double rounding.
+ * values_host: complex128[n_points]; query_values_host: complex128[n_query] (re, im interleaved). */
+int fgpu_corr_create(fgpu_ctx* ctx, uint32_t bins, float r_max, fgpu_corr** out);
+void fgpu_corr_destroy(fgpu_corr* corr);
+int fgpu_corr_reset(fgpu_corr* corr);
+int fgpu_corr_accumulate_nlist(fgpu_corr* corr, const fgpu_nlist* nl, const double* values_host,
+                               const double* query_values_host);
+int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host);
 
 /* ---- LocalDensity --------------------------------------------------------------------------------------
  * Replaces LocalDensity::compute (freud/density/LocalDensity.cc:38-84) once the neighbours are a NeighborList (the

@@ -1502,3 +1502,42 @@ int fport_local_density(const float* nl_d, const uint32_t* segments, const uint3
     }
     return 0;
 }
+
+/* ---- CorrelationFunction ---------------------------------------------------------------------------------
+ * CorrelationFunction::accumulate + reduce (freud/density/CorrelationFunction.cc:49-59, 69-95) over the bonds of a
+ * NeighborList: bin = RegularAxis(bins, 0, r_max).bin(distance) (overflow bonds are dropped, Histogram.h:313-320),
+ * count[bin]++, sum[bin] += conj(values[j]) * query_values[i] in complex<double>; then sum / count where count != 0.
+ * Bonds are added in list order here; upstream adds per-thread partial sums, so agreement is to double rounding. */
+int fport_correlation(const uint32_t* nl_ij, const float* nl_d, uint64_t n_bonds, const double* values,
+                      const double* query_values, uint32_t bins, float r_max, double* correlation, uint32_t* counts)
+{
+    volatile float width_v = r_max / (float) bins;
+    volatile float inv_v = 1.0f / width_v;
+    float inv = inv_v;
+    memset(correlation, 0, 2 * (size_t) bins * sizeof(double));
+    memset(counts, 0, (size_t) bins * sizeof(uint32_t));
+    for (uint64_t k = 0; k < n_bonds; ++k)
+    {
+        int64_t bin = axis_bin(nl_d[k], 0.0f, r_max, inv, bins);
+        if (bin < 0)
+        {
+            continue;
+        }
+        const double* x = values + 2 * (size_t) nl_ij[2 * k + 1];
+        const double* y = query_values + 2 * (size_t) nl_ij[2 * k];
+        double re = x[0] * y[0] + x[1] * y[1];
+        double im = x[0] * y[1] - x[1] * y[0];
+        counts[bin] += 1;
+        correlation[2 * bin] += re;
+        correlation[2 * bin + 1] += im;
+    }
+    for (uint32_t b = 0; b < bins; ++b)
+    {
+        if (counts[b] != 0)
+        {
+            correlation[2 * b] /= (double) counts[b];
+            correlation[2 * b + 1] /= (double) counts[b];
+        }
+    }
+    return 0;
+}

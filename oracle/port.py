@@ -144,6 +144,21 @@ def rdf_reduce(counts, r_max, r_min, box, is2d, n_points, n_query_points, frames
     return dict(bin_counts=c, rdf=g, n_r=n, bin_edges=e, bin_centers=ce)
 
 
+def correlation_function(nlist, values, query_values, bins, r_max):
+    """(correlation complex128[bins], bin_counts) of CorrelationFunction over the bonds of an oracle NeighborList."""
+    ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)
+    d = _f32(nlist.distances)
+    v = np.ascontiguousarray(values, dtype=np.complex128).ravel()
+    qv = np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
+    corr, counts = np.zeros(bins, np.complex128), np.zeros(bins, np.uint32)
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.fport_correlation.argtypes = [_up, _fp, C.c_uint64, dp, dp, C.c_uint32, C.c_float, dp, _up]
+    L.fport_correlation(_p(ij, _up), _p(d), len(d), v.ctypes.data_as(dp), qv.ctypes.data_as(dp), int(bins), float(r_max),
+                        corr.ctypes.data_as(dp), _p(counts, _up))
+    return corr, counts
+
+
 def local_density(nlist, r_max, diameter, is2d=False):
     """(num_neighbors, density) of LocalDensity::compute over the rows of an oracle NeighborList."""
     d = _f32(nlist.distances)

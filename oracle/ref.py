@@ -207,6 +207,22 @@ class RDF:
             self._h = None
 
 
+def correlation_function(query, values, query_points, query_values, bins, r_max, nlist=None, exclude_ii=False):
+    """CorrelationFunction(bins, r_max).compute(...) of the reference: (correlation complex128[bins], bin_counts)."""
+    q = _f32(query_points, 3)
+    v = np.ascontiguousarray(values, dtype=np.complex128).ravel()
+    qv = np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
+    corr, counts = np.zeros(bins, np.complex128), np.zeros(bins, np.uint32)
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.fref_correlation.argtypes = [C.c_void_p, dp, _fp, dp, C.c_uint, C.c_void_p, C.c_uint, C.c_float, C.c_int, dp, _up]
+    if L.fref_correlation(query._h, v.ctypes.data_as(dp), _p(q), qv.ctypes.data_as(dp), len(q),
+                          nlist._h if nlist is not None else None, int(bins), float(r_max), int(bool(exclude_ii)),
+                          corr.ctypes.data_as(dp), _p(counts, _up)):
+        _raise()
+    return corr, counts
+
+
 def local_density(query, query_points, r_max, diameter, nlist=None, q_r_max=None, exclude_ii=False):
     """LocalDensity(r_max, diameter).compute(...) of the reference: (num_neighbors, density).  Without a NeighborList
     it queries a ball of q_r_max (default r_max + diameter / 2, freud/density.py:510-514) on the fly."""

@@ -11,6 +11,7 @@
 //   NeighborQuery::query / toNeighborList            freud/locality/NeighborQuery.h:130,434
 //   freud::density::RDF                              freud/density/RDF.h:33
 //   freud::density::LocalDensity                     freud/density/LocalDensity.h:29
+//   freud::density::CorrelationFunction              freud/density/CorrelationFunction.h:52
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
 
@@ -24,6 +25,7 @@
 #include "AABBQuery.h"
 #include "Box.h"
 #include "CellQuery.h"
+#include "CorrelationFunction.h"
 #include "LinkCell.h"
 #include "LocalDensity.h"
 #include "NeighborList.h"
@@ -299,6 +301,30 @@ int fref_rdf_get(void* rdf, unsigned* bin_counts, float* g_r, float* n_r, float*
             auto c = r->getBinCenters()[0];
             std::memcpy(bin_centers, c.data(), bins * sizeof(float));
         }
+    });
+}
+
+// ---- CorrelationFunction --------------------------------------------------------------------------
+// CorrelationFunction(bins, r_max).accumulate(nq, values, query_points, query_values, n, nlist /*nullable*/, qargs)
+// once; outputs: correlation complex128[bins] (re, im interleaved), bin counts u32[bins]
+int fref_correlation(void* nq, const double* values, const float* qpts, const double* query_values, unsigned n_query,
+                     void* nlist_or_null, unsigned bins, float r_max, int exclude_ii, double* correlation,
+                     unsigned* bin_counts)
+{
+    return guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        std::shared_ptr<NeighborList> nl;
+        if (nlist_or_null != nullptr)
+        {
+            nl = *static_cast<std::shared_ptr<NeighborList>*>(nlist_or_null);
+        }
+        QueryArgs const args = makeArgs(/*ball*/ 1, 0xffffffffU, r_max, 0.0F, -1.0F, -1.0F, exclude_ii);
+        freud::density::CorrelationFunction cf(bins, r_max);
+        cf.accumulate(h->nq, reinterpret_cast<const std::complex<double>*>(values),
+                      reinterpret_cast<const vec3<float>*>(qpts),
+                      reinterpret_cast<const std::complex<double>*>(query_values), n_query, nl, args);
+        std::memcpy(correlation, cf.getCorrelation()->data(), bins * sizeof(std::complex<double>));
+        std::memcpy(bin_counts, cf.getBinCounts()->data(), bins * sizeof(unsigned));
     });
 }
 

@@ -88,6 +88,7 @@ def main():
     print("steinhardt", out["knn12_ql_6"][:3, 0])
     steinhardt_options()
     local_density()
+    correlation_function()
 
 
 STEINHARDT_OPTIONS = {
@@ -131,6 +132,29 @@ def local_density():
                                                                                    exclude_ii=True)
     np.savez_compressed(os.path.join(HERE, "local_density.npz"), **out)
     print("local density", out["cube_3_1_nlist_num"][:3], out["cube_3_1_nlist_density"][:3])
+
+
+def correlation_inputs(n, nq, seed):
+    """Seeded complex values for the points and the query points (regenerated by the tests)."""
+    rs = np.random.RandomState(seed)
+    v = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    qv = rs.standard_normal(nq) + 1j * rs.standard_normal(nq)
+    return v, qv
+
+
+def correlation_function():
+    """CorrelationFunction(bins=40, r_max=3) (CorrelationFunction.cc:26-95): complex values with separate query points,
+    real values of the points against themselves, in a cubic and a tilted 2-D box."""
+    out = {}
+    for name, box, n in (("cube", Box.cube(12), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 7), random_points(box, 700, 8)
+        v, qv = correlation_inputs(n, 700, 3)
+        Q = ref.Query("aabb", box, pts, is2d=box.is2D)
+        out[f"{name}_complex_corr"], out[f"{name}_complex_counts"] = ref.correlation_function(Q, v, q, qv, 40, 3.0)
+        out[f"{name}_real_corr"], out[f"{name}_real_counts"] = ref.correlation_function(Q, v.real, pts, v.real, 40, 3.0,
+                                                                                  exclude_ii=True)
+    np.savez_compressed(os.path.join(HERE, "correlation_function.npz"), **out)
+    print("correlation function", out["cube_complex_corr"][-2:], out["cube_complex_counts"][-2:])
 
 
 if __name__ == "__main__":

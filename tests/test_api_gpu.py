@@ -193,6 +193,38 @@ def test_steinhardt_vs_reference_noisy_fcc():
         np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
 
 
+def test_correlation_function_api():
+    """freud.density.CorrelationFunction (tests/test_density_correlation_function.py upstream): complex and real
+    inputs, is_complex, reset=False accumulation, histogram properties, the zero-mean random field known answer."""
+    from tests.golden.make_golden import correlation_inputs
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "correlation_function.npz"))
+    box, n = Box.cube(12), 3000
+    pts, q = random_points(box, n, 7), random_points(box, 700, 8)
+    v, qv = correlation_inputs(n, 700, 3)
+    cf = density.CorrelationFunction(40, 3.0)
+    assert cf.default_query_args == dict(mode="ball", r_max=3.0)
+    cf.compute((box, pts), v, query_points=q, query_values=qv)
+    assert cf.is_complex and cf.correlation.dtype == np.complex128
+    assert np.array_equal(cf.bin_counts, gold["cube_complex_counts"])
+    np.testing.assert_allclose(cf.correlation, gold["cube_complex_corr"], rtol=1e-11, atol=1e-12)
+    cf.compute((box, pts), v, query_points=q, query_values=qv, reset=False)  # a second identical frame: same average
+    assert np.array_equal(cf.bin_counts, 2 * gold["cube_complex_counts"])
+    np.testing.assert_allclose(cf.correlation, gold["cube_complex_corr"], rtol=1e-11, atol=1e-12)
+    cf.compute((box, pts), v.real)  # reset, real values, the points against themselves
+    assert not cf.is_complex and cf.correlation.dtype == np.float64
+    assert np.array_equal(cf.bin_counts, gold["cube_real_counts"])
+    np.testing.assert_allclose(cf.correlation, gold["cube_real_corr"].real, rtol=1e-11, atol=1e-12)
+    assert cf.nbins == 40 and cf.bounds == (0.0, 3.0) and len(cf.bin_edges) == 41 and cf.box == box
+    # a constant field correlates to its square in every occupied bin (upstream's test_constant_field idea)
+    cf.compute((box, pts), np.full(n, 2.0))
+    assert np.allclose(cf.correlation[cf.bin_counts > 0], 4.0)
+    with pytest.raises(ValueError):
+        density.CorrelationFunction(0, 3.0)
+    with pytest.raises(ValueError):
+        density.CorrelationFunction(10, -1.0)
+
+
 def test_local_density_api():
     """freud.density.LocalDensity (tests/test_density_local_density.py:21-110 upstream): attribute access, the known
     ranges of the reference's own test, default query arguments, an explicit NeighborList, query points != points."""

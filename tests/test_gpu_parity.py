@@ -285,6 +285,41 @@ def test_knn(ctx, name):
 GHOST = 2
 
 
+def test_correlation_function_over_a_neighbor_list(ctx):
+    """fgpu_corr_* (CorrelationFunction.cc:26-95) over device NeighborLists against the committed outputs of the
+    reference: bin counts identical, complex<double> sums to double rounding; accumulation over two calls."""
+    from freud_b200.box import Box
+    from tests.golden.make_golden import correlation_inputs
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "correlation_function.npz"))
+    for name, box, n in (("cube", Box.cube(12), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 7), random_points(box, 700, 8)
+        v, qv = correlation_inputs(n, 700, 3)
+        dp = capi.DevicePoints(ctx, box, pts)
+        cf = capi.DeviceCorrelation(ctx, 40, 3.0)
+        cf.accumulate_nlist(dp.ball_query(q, IMAGE, 3.0, 0.0, False), v, qv)
+        counts, sums = cf.read()
+        assert np.array_equal(counts, gold[f"{name}_complex_counts"])
+        np.testing.assert_allclose(sums / np.maximum(counts, 1), gold[f"{name}_complex_corr"], rtol=1e-11, atol=1e-12)
+        cf.accumulate_nlist(dp.ball_query(q, IMAGE, 3.0, 0.0, False), v, qv)  # reset=False: a second frame adds
+        counts2, sums2 = cf.read()
+        assert np.array_equal(counts2, 2 * counts)
+        np.testing.assert_allclose(sums2, 2 * sums, rtol=1e-11, atol=1e-11)
+        cf.reset()
+        cf.accumulate_nlist(dp.ball_query(None, IMAGE, 3.0, 0.0, True), v.real, v.real)
+        counts, sums = cf.read()
+        assert np.array_equal(counts, gold[f"{name}_real_counts"])
+        np.testing.assert_allclose(sums / np.maximum(counts, 1), gold[f"{name}_real_corr"], rtol=1e-11, atol=1e-12)
+    big = capi.DeviceCorrelation(ctx, 5000, 3.0)  # accumulators beyond shared memory: global atomics
+    big.accumulate_nlist(dp.ball_query(None, IMAGE, 3.0, 0.0, True), v.real, v.real)
+    nl = port.ball_nlist(port.IMAGE, box, box.is2D, pts, pts, 3.0, 0.0, True)
+    want_corr, want_counts = port.correlation_function(nl, v.real, v.real, 5000, 3.0)
+    counts, sums = big.read()
+    assert np.array_equal(counts, want_counts)
+    np.testing.assert_allclose(sums / np.maximum(counts, 1), want_corr, rtol=1e-11, atol=1e-12)
+
+
 def test_local_density_over_a_neighbor_list(ctx):
     """fgpu_local_density (LocalDensity.cc:38-84) over device NeighborLists: the same bits as the oracle over the same
     list, in 3-D and 2-D, and the committed outputs of the reference."""

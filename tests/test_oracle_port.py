@@ -146,6 +146,25 @@ def test_port_local_density_matches_golden():
             np.testing.assert_allclose(den, gold[f"{key}_query_density"], rtol=1e-5)
 
 
+def test_port_correlation_function_matches_golden():
+    """CorrelationFunction restated in oracle/port.c against outputs of the reference
+    (tests/golden/correlation_function.npz): identical bin counts, sums to double rounding."""
+    from tests.golden.make_golden import correlation_inputs
+
+    gold = np.load(os.path.join(GOLD, "correlation_function.npz"))
+    for name, box, n in (("cube", Box.cube(12), 3000), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500)):
+        pts, q = random_points(box, n, 7), random_points(box, 700, 8)
+        v, qv = correlation_inputs(n, 700, 3)
+        nl = port.ball_nlist(port.IMAGE, box, box.is2D, pts, q, 3.0, 0.0, False)
+        corr, counts = port.correlation_function(nl, v, qv, 40, 3.0)
+        assert np.array_equal(counts, gold[f"{name}_complex_counts"])
+        np.testing.assert_allclose(corr, gold[f"{name}_complex_corr"], rtol=1e-12, atol=1e-13)
+        nl = port.ball_nlist(port.IMAGE, box, box.is2D, pts, pts, 3.0, 0.0, True)
+        corr, counts = port.correlation_function(nl, v.real, v.real, 40, 3.0)
+        assert np.array_equal(counts, gold[f"{name}_real_counts"])
+        np.testing.assert_allclose(corr, gold[f"{name}_real_corr"], rtol=1e-12, atol=1e-13)
+
+
 def test_port_wigner3j_known_values():
     """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
     the reference is present, every tabulated l <= 20 as float."""
