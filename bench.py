@@ -318,6 +318,73 @@ def workload_correlation(ctx, rank, n, bins=100, r_max=3.0):
                 bins=bins, values=values, secondary={"bonds": n_bonds})
 
 
+def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
+    """SURVEY.md section 8f rank 3, third client: freud.pmft.PMFTXY(x_max, y_max, bins).compute((box, points),
+    orientations) on the 2-D system of config 5 (areal density 0.5): ball query of sqrt(x_max^2 + y_max^2) = 5 (IMAGE
+    arithmetic), then the rotated bond vectors binned in 2-D."""
+    from freud_b200 import _capi, data
+
+    L = (n / 0.5) ** 0.5
+    box, pts = data.make_random_system(L, n, is2D=True, seed=rank)
+    rs = np.random.RandomState(rank + 29)
+    angles, keep1 = pinned_empty((n,), np.float32)
+    angles[:] = rs.random_sample(n) * 2 * np.pi - np.pi
+    r_max = float(np.sqrt(x_max ** 2 + y_max ** 2))
+    dp = _capi.DevicePoints(ctx, box, pts)
+    pm = _capi.DevicePMFTXY(ctx, x_max, y_max, bins[0], bins[1])
+    n_bonds = dp.ball_query(None, IMAGE, r_max, 0.0, True).num_bonds
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+
+    def step_dev():
+        # the orientations (4 MB) are taken from the host in every call: cos / sin are evaluated there (host libm)
+        pm.reset()
+        dp.build_cells(r_max)
+        pm.accumulate_nlist(dp.ball_query(None, IMAGE, r_max, 0.0, True), angles)
+        return pm.read()
+
+    def step_e2e():
+        pm.reset()
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        pm.accumulate_nlist(d.ball_query(None, IMAGE, r_max, 0.0, True), angles)
+        return pm.read()
+
+    n_cells = int(np.prod(dp.build_cells(r_max)))
+    nb = bins[0] * bins[1]
+    algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
+            "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
+            "pmftxy": 20 * n_bonds + 8 * n + 4 * nb,  # (i, v.x, v.y, v.z stride) per bond + (cos, sin) per query
+            "pipeline": 16 * (n + n) + 8 * n + 4 * nb}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="pmftxy_particles_per_sec",
+                config={"workload": f"PMFTXY x_max={x_max:g} y_max={y_max:g} bins={bins[0]}x{bins[1]} (ball query "
+                                    f"r={r_max:g}, image flavour) N={n} 2-D square L={L:.4f} areal density 0.5",
+                        "bonds_per_step": n_bonds},
+                h2d=12 * n + 4 * n, d2h=4 * nb, algo=algo, keep=[keep0, keep1], box=box, pts=pts, angles=angles,
+                x_max=x_max, y_max=y_max, bins=bins, secondary={"bonds": n_bonds})
+
+
+def cpu_reference_pmftxy(box, pts, angles, x_max, y_max, bins, budget_s=12.0, threads=None):
+    """The reference's PMFTXY (AABBQuery engine, all host threads) on a bounded sample of query points."""
+    from oracle import ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        return {"value": None, "unit": "particles/s", "cores": threads, "kind": "port", "sample": "unavailable"}
+    q = ref.Query("aabb", box, pts, is2d=True)
+    probe = 20000
+    t0 = time.perf_counter()
+    ref.pmftxy(q, angles[:probe], pts[:probe], x_max, y_max, bins[0], bins[1], exclude_ii=True)
+    dt = time.perf_counter() - t0
+    m = int(min(len(pts), max(probe, probe * budget_s / max(dt, 1e-6) * 0.8)))
+    t0 = time.perf_counter()
+    ref.pmftxy(q, angles[:m], pts[:m], x_max, y_max, bins[0], bins[1], exclude_ii=True)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "particles/s", "cores": threads, "kind": "reference",
+            "sample": f"reference PMFTXY({x_max:g}, {y_max:g}, {bins}).compute via AABBQuery: first {m} of {len(pts)} "
+                      f"query points in {dt:.2f} s"}
+
+
 def cpu_reference_correlation(box, pts, values, bins, r_max, budget_s=12.0, threads=None):
     """The reference's CorrelationFunction (AABBQuery engine, all host threads) on a bounded sample of query points."""
     from oracle import ref
@@ -464,7 +531,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation"])
+    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy"])
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -474,7 +541,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
-                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000}[args.workload]
+                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000, "pmftxy": 1_000_000}[args.workload]
     n = args.n or n_default
 
     if args.impl == "reference":
@@ -511,6 +578,9 @@ def main():
         scaling = "weak"
     elif args.workload == "correlation":
         w = workload_correlation(ctx, rank, n)
+        scaling = "weak"
+    elif args.workload == "pmftxy":
+        w = workload_pmftxy(ctx, rank, n)
         scaling = "weak"
     elif args.workload == "rdf4m":
         w = workload_rdf4m(ctx, rank, world, n, comm)
@@ -555,7 +625,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density", "correlation")
+             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]
@@ -643,6 +713,9 @@ def main():
                 line["cpu_baseline"] = cpu_reference_local_density(w["box"], w["pts"], w["r_max"], w["diameter"])
             elif args.workload == "correlation":
                 line["cpu_baseline"] = cpu_reference_correlation(w["box"], w["pts"], w["values"], w["bins"], w["r_max"])
+            elif args.workload == "pmftxy":
+                line["cpu_baseline"] = cpu_reference_pmftxy(w["box"], w["pts"], w["angles"], w["x_max"], w["y_max"],
+                                                            w["bins"])
             else:
                 line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
@@ -771,6 +844,15 @@ def run_reference_arm(args, rank, world, n):
         runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "rdf_frames_per_sec", "frames/s"
         config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"}
+    elif args.workload == "pmftxy":
+        L = (n / 0.5) ** 0.5
+        box, pts = data.make_random_system(L, n, is2D=True, seed=0)
+        rs = np.random.RandomState(29)
+        angles = (rs.random_sample(n) * 2 * np.pi - np.pi).astype(np.float32)
+        runs = [cpu_reference_pmftxy(box, pts, angles, 4.0, 3.0, (100, 100), budget_s=budget, threads=threads)
+                for _ in range(steps)]
+        metric, unit = "pmftxy_particles_per_sec", "particles/s"
+        config = {"workload": f"PMFTXY x_max=4 y_max=3 bins=100x100 N={n} 2-D square L={L:.4f} areal density 0.5"}
     elif args.workload == "correlation":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)

@@ -66,6 +66,11 @@ SIGNATURES = {
     "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
     "fgpu_rdf_read": (C.c_int, [_vp, _up]),
     "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
+    "fgpu_pmftxy_create": (C.c_int, [_vp, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _vpp]),
+    "fgpu_pmftxy_destroy": (None, [_vp]),
+    "fgpu_pmftxy_reset": (C.c_int, [_vp]),
+    "fgpu_pmftxy_accumulate_nlist": (C.c_int, [_vp, _vp, _fp]),
+    "fgpu_pmftxy_read": (C.c_int, [_vp, _up]),
     "fgpu_corr_create": (C.c_int, [_vp, C.c_uint32, C.c_float, _vpp]),
     "fgpu_corr_destroy": (None, [_vp]),
     "fgpu_corr_reset": (C.c_int, [_vp]),
@@ -375,6 +380,32 @@ class DeviceRDF(_DeviceObject):
 
     def allreduce(self, comm):
         check(lib().fgpu_rdf_allreduce(self._h, comm._h))
+
+
+class DevicePMFTXY(_DeviceObject):
+    """Device-resident PMFTXY histogram (``fgpu_pmftxy``)."""
+
+    _destroy = "fgpu_pmftxy_destroy"
+
+    def __init__(self, ctx, x_max, y_max, n_x, n_y):
+        self._adopt(ctx)
+        self.shape = (int(n_x), int(n_y))
+        self._h = _vp()
+        check(lib().fgpu_pmftxy_create(ctx._h, float(x_max), float(y_max), int(n_x), int(n_y), C.byref(self._h)))
+
+    def reset(self):
+        check(lib().fgpu_pmftxy_reset(self._h))
+
+    def accumulate_nlist(self, nlist, query_orientations):
+        """query_orientations: angles in radians, one per query point."""
+        t = np.ascontiguousarray(query_orientations, dtype=np.float32).ravel()
+        assert len(t) == nlist.num_query_points
+        check(lib().fgpu_pmftxy_accumulate_nlist(self._h, nlist._h, ptr(t)))
+
+    def read(self):
+        counts = np.empty(self.shape, np.uint32)
+        check(lib().fgpu_pmftxy_read(self._h, ptr(counts, _up)))
+        return counts
 
 
 class DeviceCorrelation(_DeviceObject):

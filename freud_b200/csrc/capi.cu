@@ -12,6 +12,7 @@
 #include <limits>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "internal.h"
 
@@ -1460,6 +1461,119 @@ int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
 }
 
 // ---- Steinhardt ------------------------------------------------------------------------------------------
+static AxisDev regular_axis(uint32_t bins, float lo, float hi)
+{
+    // RegularAxis ctor, freud/util/Histogram.h:126-138
+    volatile float span = hi - lo;
+    volatile float width = span / (float) bins;
+    volatile float inv = 1.0f / width;
+    AxisDev a;
+    a.r_min = lo;
+    a.r_max = hi;
+    a.inv_width = inv;
+    a.bins = bins;
+    return a;
+}
+
+int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, uint32_t n_y, fgpu_pmftxy** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        // PMFTXY.cc:27-42
+        require(n_x >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in X.");
+        require(n_y >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in Y.");
+        require(!(x_max < 0), FGPU_EINVALID, "PMFTXY requires that x_max must be positive.");
+        require(!(y_max < 0), FGPU_EINVALID, "PMFTXY requires that y_max must be positive.");
+        require((uint64_t) n_x * n_y < (1ULL << 31), FGPU_EINVALID, "PMFTXY histogram too large");
+        bind_device(ctx);
+        std::unique_ptr<fgpu_pmftxy> p(new fgpu_pmftxy());
+        p->ctx = ctx;
+        p->ax = regular_axis(n_x, -x_max, x_max);
+        p->ay = regular_axis(n_y, -y_max, y_max);
+        p->hist.reserve((size_t) n_x * n_y);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(p->hist.ptr, 0, (size_t) n_x * n_y * sizeof(uint32_t), ctx->stream));
+        sync(ctx);
+        *out = p.release();
+    });
+}
+
+void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft)
+{
+    if (pmft != nullptr)
+    {
+        bind_quiet(pmft->ctx);
+        delete pmft;
+    }
+}
+
+int fgpu_pmftxy_reset(fgpu_pmftxy* pmft)
+{
+    return guarded([&] {
+        require(pmft != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(pmft->ctx);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(pmft->hist.ptr, 0, (size_t) pmft->ax.bins * pmft->ay.bins * sizeof(uint32_t),
+                                        pmft->ctx->stream));
+    });
+}
+
+int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host)
+{
+    return guarded([&] {
+        require(pmft != nullptr && nl != nullptr && query_orientations_host != nullptr, FGPU_EINVALID, "null argument");
+        require(pmft->ctx == nl->ctx, FGPU_EINVALID, "pmft and nlist belong to different contexts");
+        fgpu_ctx* ctx = pmft->ctx;
+        bind_device(ctx);
+        // rotmat2<float>::fromAngle(-theta), VectorMath.h:912-921: std::cos / std::sin of a float, i.e. the host
+        // libm's cosf / sinf -- evaluated here, on the host, because CUDA's differ from them in the last ulp
+        std::vector<float> cs(2 * (size_t) nl->n_query);
+        auto fill = [&](uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; ++i)
+            {
+                float const t = -query_orientations_host[i];
+                cs[2 * (size_t) i] = std::cos(t);
+                cs[2 * (size_t) i + 1] = std::sin(t);
+            }
+        };
+        // two libm calls per query point on one core cost more than the whole GPU frame: spread them over the host
+        unsigned const hw = std::max(1U, std::min(32U, std::thread::hardware_concurrency()));
+        unsigned const n_threads = nl->n_query >= 65536 ? hw : 1U;
+        if (n_threads == 1)
+        {
+            fill(0, nl->n_query);
+        }
+        else
+        {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < n_threads; ++t)
+            {
+                uint32_t const lo = (uint32_t) ((uint64_t) nl->n_query * t / n_threads);
+                uint32_t const hi = (uint32_t) ((uint64_t) nl->n_query * (t + 1) / n_threads);
+                pool.emplace_back(fill, lo, hi);
+            }
+            for (auto& th : pool)
+            {
+                th.join();
+            }
+        }
+        const float* cos_sin_host = cs.data();
+        pmft->cos_sin.reserve(2 * (size_t) nl->n_query + 2);
+        h2d(ctx, pmft->cos_sin.ptr, cos_sin_host, 2 * (size_t) nl->n_query * sizeof(float));
+        launch_pmftxy(ctx, nl->neighbors.ptr, nl->vectors.ptr, nl->n_bonds, pmft->cos_sin.ptr, pmft->ax, pmft->ay,
+                      pmft->hist.ptr);
+        sync(ctx); // the caller's array was consumed
+    });
+}
+
+int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host)
+{
+    return guarded([&] {
+        require(pmft != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(pmft->ctx);
+        d2h(pmft->ctx, counts_host, pmft->hist.ptr, (size_t) pmft->ax.bins * pmft->ay.bins * sizeof(uint32_t));
+        sync(pmft->ctx);
+    });
+}
+
 int fgpu_corr_create(fgpu_ctx* ctx, uint32_t bins, float r_max, fgpu_corr** out)
 {
     return guarded([&] {

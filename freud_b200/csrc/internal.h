@@ -196,6 +196,14 @@ struct fgpu_rdf
     fgpu::DevBuf<uint32_t> hist;
 };
 
+struct fgpu_pmftxy
+{
+    fgpu_ctx* ctx = nullptr;
+    fgpu::AxisDev ax, ay;
+    fgpu::DevBuf<uint32_t> hist;  // n_x * n_y, row-major (x slow)
+    fgpu::DevBuf<float> cos_sin;  // staged per call: (cos, sin)(-theta) per query point
+};
+
 struct fgpu_corr
 {
     fgpu_ctx* ctx = nullptr;
@@ -448,6 +456,8 @@ struct KnnSelectArgs
 void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs& a);
 
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
+void launch_pmftxy(fgpu_ctx* ctx, const uint32_t* neighbors, const float* vectors, uint64_t n_bonds, const float* cos_sin,
+                   AxisDev ax, AxisDev ay, uint32_t* hist);
 void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
                         const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums);
 void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,

@@ -18,6 +18,7 @@
 #include "NeighborQuery.h"
 #include "CorrelationFunction.h"
 #include "LocalDensity.h"
+#include "PMFT.h"
 #include "RDF.h"
 #include "Steinhardt.h"
 
@@ -277,6 +278,34 @@ PYBIND11_MODULE(_freud_b200, m)
         .def_property_readonly("density", [](const density::LocalDensity& ld) { return to_numpy<float>(ld.getDensity()); })
         .def_property_readonly("num_neighbors",
                                [](const density::LocalDensity& ld) { return to_numpy<float>(ld.getNumNeighbors()); });
+
+    // ---- _pmft -----------------------------------------------------------------------------------------
+    auto mpm = m.def_submodule("_pmft");
+    py::class_<pmft::PMFTXY, std::shared_ptr<pmft::PMFTXY>>(mpm, "PMFTXY")
+        .def(py::init<float, float, unsigned int, unsigned int>(), py::arg("x_max"), py::arg("y_max"), py::arg("n_x"),
+             py::arg("n_y"))
+        .def("accumulate",
+             [](pmft::PMFTXY& p, std::shared_ptr<locality::NeighborQuery> nq,
+                py::array_t<float, py::array::c_style | py::array::forcecast> query_orientations, points_array qp,
+                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 if ((size_t) query_orientations.size() != n)
+                 {
+                     throw std::invalid_argument("query_orientations must hold one angle per query point");
+                 }
+                 p.accumulate(nq, query_orientations.data(), q, n, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("query_orientations"), py::arg("query_points"),
+             py::arg("nlist").none(true), py::arg("qargs"))
+        .def("getPCF", [](pmft::PMFTXY& p) { return to_numpy<float>(p.getPCF()); })
+        .def("getBinCounts", [](pmft::PMFTXY& p) { return to_numpy<unsigned int>(p.getBinCounts()); })
+        .def("getBinEdges", &pmft::PMFTXY::getBinEdges)
+        .def("getBinCenters", &pmft::PMFTXY::getBinCenters)
+        .def("getBounds", &pmft::PMFTXY::getBounds)
+        .def("getAxisSizes", &pmft::PMFTXY::getAxisSizes)
+        .def("getBox", &pmft::PMFTXY::getBox)
+        .def("reset", &pmft::PMFTXY::reset);
 
     // ---- _order ----------------------------------------------------------------------------------------
     auto mord = m.def_submodule("_order");

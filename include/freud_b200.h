@@ -48,6 +48,7 @@ typedef struct fgpu_ctx fgpu_ctx;       /* one GPU + one stream + scratch memory
 typedef struct fgpu_points fgpu_points; /* device-resident reference points + box + cell list */
 typedef struct fgpu_nlist fgpu_nlist;   /* device-resident NeighborList (SoA, CSR)            */
 typedef struct fgpu_rdf fgpu_rdf;       /* device-resident RDF histogram accumulator          */
+typedef struct fgpu_pmftxy fgpu_pmftxy; /* device-resident PMFTXY histogram                      */
 typedef struct fgpu_corr fgpu_corr;     /* device-resident CorrelationFunction accumulators  */
 typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
 
@@ -80,7 +81,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, pmftxy, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -192,6 +193,21 @@ int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl);
 int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
 /* sum the histograms of all ranks in place: one ncclAllReduce(u32[bins], sum) */
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
+
+/* ---- PMFTXY ----------------------------------------------------------------------------------------------
+ * Device half of freud::pmft::PMFTXY (freud/pmft/PMFTXY.cc:25-87): a u32[n_x][n_y] histogram of the bond vectors
+ * of a NeighborList rotated into the frame of their query particle, resident across accumulate calls.
+ * query_orientations_host[n_query] are angles in radians; cos and sin of their negatives are evaluated on the host
+ * with libm's cosf / sinf -- what rotmat2::fromAngle calls upstream, VectorMath.h:912-921; CUDA's differ in the last
+ * ulp -- so the rotation and the binning reproduce the reference's float arithmetic bit for bit and the counts are
+ * identical.  Normalisation to the PCF (PMFT::reduce,
+ * freud/pmft/PMFT.h:73-83) is host arithmetic in freud_b200/host/PMFT.h.
+ * Errors: n_x, n_y < 1 or x_max, y_max < 0 -> FGPU_EINVALID (PMFTXY.cc:27-42). */
+int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, uint32_t n_y, fgpu_pmftxy** out);
+void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft);
+int fgpu_pmftxy_reset(fgpu_pmftxy* pmft);
+int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host);
+int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host);
 
 /* ---- CorrelationFunction ---------------------------------------------------------------------------------
  * Device half of freud::density::CorrelationFunction (freud/density/CorrelationFunction.cc:26-95): per bin of

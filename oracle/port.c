@@ -1541,3 +1541,49 @@ int fport_correlation(const uint32_t* nl_ij, const float* nl_d, uint64_t n_bonds
     }
     return 0;
 }
+
+/* ---- PMFTXY ------------------------------------------------------------------------------------------
+ * PMFTXY::accumulate (freud/pmft/PMFTXY.cc:65-87) over the bonds of a NeighborList: the bond vector rotated by
+ * rotmat2::fromAngle(-theta_i) (VectorMath.h:912-936: rows (cos, -sin), (sin, cos); products then one add per row),
+ * binned on RegularAxis(n_x, -x_max, x_max) x RegularAxis(n_y, -y_max, y_max) with linear index bx * n_y + by
+ * (Histogram.h:301-351; a bond outside either axis is dropped); then PMFT::reduce (freud/pmft/PMFT.h:73-83) with the
+ * constant Jacobian factor 1 / (dx dy) (PMFTXY.cc:49-51, 59-63).  cosf / sinf are this machine's libm, as upstream. */
+int fport_pmftxy(const uint32_t* nl_ij, const float* nl_v, uint64_t n_bonds, const float* query_orientations,
+                 float x_max, float y_max, uint32_t n_x, uint32_t n_y, float box_volume, uint32_t n_points,
+                 uint32_t n_query, uint32_t* counts, float* pcf)
+{
+    volatile float wx_v = (x_max - (-x_max)) / (float) n_x, wy_v = (y_max - (-y_max)) / (float) n_y;
+    volatile float ix_v = 1.0f / wx_v, iy_v = 1.0f / wy_v;
+    float inv_x = ix_v, inv_y = iy_v;
+    memset(counts, 0, (size_t) n_x * n_y * sizeof(uint32_t));
+    for (uint64_t k = 0; k < n_bonds; ++k)
+    {
+        float t = -query_orientations[nl_ij[2 * k]];
+        float c = cosf(t), s = sinf(t);
+        float vx = nl_v[3 * k], vy = nl_v[3 * k + 1];
+        float ms = -s;
+        float a1 = c * vx, a2 = ms * vy;
+        float rx = a1 + a2;
+        float b1 = s * vx, b2 = c * vy;
+        float ry = b1 + b2;
+        int64_t bx = axis_bin(rx, -x_max, x_max, inv_x, n_x);
+        int64_t by = axis_bin(ry, -y_max, y_max, inv_y, n_y);
+        if (bx >= 0 && by >= 0)
+        {
+            counts[(size_t) bx * n_y + (size_t) by] += 1;
+        }
+    }
+    volatile float dx = 2.0f * x_max / (float) n_x, dy = 2.0f * y_max / (float) n_y;
+    volatile float jac = dx * dy;
+    volatile float inv_num_dens = box_volume / (float) n_query;
+    volatile float den = 1.0f * (float) n_points; /* one frame */
+    volatile float norm_factor = 1.0f / den;
+    volatile float prefactor = inv_num_dens * norm_factor;
+    volatile float jf = 1.0f / jac;
+    for (size_t i = 0; i < (size_t) n_x * n_y; ++i)
+    {
+        volatile float t = (float) counts[i] * prefactor;
+        pcf[i] = t * jf;
+    }
+    return 0;
+}

@@ -144,6 +144,20 @@ def rdf_reduce(counts, r_max, r_min, box, is2d, n_points, n_query_points, frames
     return dict(bin_counts=c, rdf=g, n_r=n, bin_edges=e, bin_centers=ce)
 
 
+def pmftxy(box, n_points, nlist, query_orientations, x_max, y_max, n_x, n_y):
+    """(bin_counts u32[n_x, n_y], pcf f32[n_x, n_y]) of PMFTXY over the bonds of an oracle NeighborList (one frame)."""
+    ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)
+    v = _f32(nlist.vectors, 3)
+    t = _f32(query_orientations)
+    counts, pcf = np.zeros((n_x, n_y), np.uint32), np.zeros((n_x, n_y), np.float32)
+    L = lib()
+    L.fport_pmftxy.argtypes = [_up, _fp, C.c_uint64, _fp, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_float,
+                               C.c_uint32, C.c_uint32, _up, _fp]
+    L.fport_pmftxy(_p(ij, _up), _p(v), len(v), _p(t), float(x_max), float(y_max), int(n_x), int(n_y),
+                   float(np.float32(box.volume)), int(n_points), len(t), _p(counts, _up), _p(pcf))
+    return counts, pcf
+
+
 def correlation_function(nlist, values, query_values, bins, r_max):
     """(correlation complex128[bins], bin_counts) of CorrelationFunction over the bonds of an oracle NeighborList."""
     ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)

@@ -207,6 +207,22 @@ class RDF:
             self._h = None
 
 
+def pmftxy(query, query_orientations, query_points, x_max, y_max, n_x, n_y, nlist=None, exclude_ii=False):
+    """PMFTXY(x_max, y_max, (n_x, n_y)).compute(...) of the reference: (bin_counts u32[n_x, n_y], pcf f32[n_x, n_y]);
+    without a NeighborList it queries a ball of sqrt(x_max^2 + y_max^2) (freud/pmft.py:358)."""
+    q = _f32(query_points, 3)
+    t = _f32(query_orientations)
+    counts, pcf = np.zeros((n_x, n_y), np.uint32), np.zeros((n_x, n_y), np.float32)
+    L = lib()
+    L.fref_pmftxy.argtypes = [C.c_void_p, _fp, _fp, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_uint, C.c_uint,
+                              C.c_float, C.c_int, _up, _fp]
+    r_max = float(np.sqrt(x_max ** 2 + y_max ** 2))
+    if L.fref_pmftxy(query._h, _p(t), _p(q), len(q), nlist._h if nlist is not None else None, float(x_max), float(y_max),
+                     int(n_x), int(n_y), r_max, int(bool(exclude_ii)), _p(counts, _up), _p(pcf)):
+        _raise()
+    return counts, pcf
+
+
 def correlation_function(query, values, query_points, query_values, bins, r_max, nlist=None, exclude_ii=False):
     """CorrelationFunction(bins, r_max).compute(...) of the reference: (correlation complex128[bins], bin_counts)."""
     q = _f32(query_points, 3)

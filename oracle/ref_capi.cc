@@ -12,6 +12,7 @@
 //   freud::density::RDF                              freud/density/RDF.h:33
 //   freud::density::LocalDensity                     freud/density/LocalDensity.h:29
 //   freud::density::CorrelationFunction              freud/density/CorrelationFunction.h:52
+//   freud::pmft::PMFTXY                              freud/pmft/PMFTXY.h
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
 
@@ -30,6 +31,7 @@
 #include "LocalDensity.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
+#include "PMFTXY.h"
 #include "RDF.h"
 #include "RawPoints.h"
 #include "Steinhardt.h"
@@ -325,6 +327,28 @@ int fref_correlation(void* nq, const double* values, const float* qpts, const do
                       reinterpret_cast<const std::complex<double>*>(query_values), n_query, nl, args);
         std::memcpy(correlation, cf.getCorrelation()->data(), bins * sizeof(std::complex<double>));
         std::memcpy(bin_counts, cf.getBinCounts()->data(), bins * sizeof(unsigned));
+    });
+}
+
+// ---- PMFTXY -----------------------------------------------------------------------------------------
+// PMFTXY(x_max, y_max, n_x, n_y).accumulate(nq, query_orientations, query_points, n, nlist /*nullable*/, qargs) once;
+// outputs: bin counts u32[n_x * n_y], pcf f32[n_x * n_y]
+int fref_pmftxy(void* nq, const float* query_orientations, const float* qpts, unsigned n_query, void* nlist_or_null,
+                float x_max, float y_max, unsigned n_x, unsigned n_y, float r_max, int exclude_ii, unsigned* bin_counts,
+                float* pcf)
+{
+    return guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        std::shared_ptr<NeighborList> nl;
+        if (nlist_or_null != nullptr)
+        {
+            nl = *static_cast<std::shared_ptr<NeighborList>*>(nlist_or_null);
+        }
+        QueryArgs const args = makeArgs(/*ball*/ 1, 0xffffffffU, r_max, 0.0F, -1.0F, -1.0F, exclude_ii);
+        freud::pmft::PMFTXY p(x_max, y_max, n_x, n_y);
+        p.accumulate(h->nq, query_orientations, reinterpret_cast<const vec3<float>*>(qpts), n_query, nl, args);
+        std::memcpy(bin_counts, p.getBinCounts()->data(), size_t(n_x) * n_y * sizeof(unsigned));
+        std::memcpy(pcf, p.getPCF()->data(), size_t(n_x) * n_y * sizeof(float));
     });
 }
 

@@ -89,6 +89,7 @@ def main():
     steinhardt_options()
     local_density()
     correlation_function()
+    pmftxy()
 
 
 STEINHARDT_OPTIONS = {
@@ -155,6 +156,27 @@ def correlation_function():
                                                                                   exclude_ii=True)
     np.savez_compressed(os.path.join(HERE, "correlation_function.npz"), **out)
     print("correlation function", out["cube_complex_corr"][-2:], out["cube_complex_counts"][-2:])
+
+
+def pmftxy_inputs(n, nq, seed):
+    """Seeded orientation angles for the points and for a separate query set (regenerated by the tests)."""
+    rs = np.random.RandomState(seed)
+    return ((rs.random_sample(n) * 2 * np.pi - np.pi).astype(np.float32),
+            (rs.random_sample(nq) * 2 * np.pi).astype(np.float32))
+
+
+def pmftxy():
+    """PMFTXY(3, 2.5, (30, 24)) (PMFTXY.cc:25-87, PMFT.h:73-83) in a square and a tilted 2-D box: separate query points,
+    and the points against themselves."""
+    out = {}
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        Q = ref.Query("aabb", box, pts, is2d=True)
+        out[f"{name}_query_counts"], out[f"{name}_query_pcf"] = ref.pmftxy(Q, th_q, q, 3.0, 2.5, 30, 24)
+        out[f"{name}_self_counts"], out[f"{name}_self_pcf"] = ref.pmftxy(Q, th_p, pts, 3.0, 2.5, 30, 24, exclude_ii=True)
+    np.savez_compressed(os.path.join(HERE, "pmftxy.npz"), **out)
+    print("pmftxy", int(out["sq2d_query_counts"].sum()), out["sq2d_query_pcf"][15, 10:13])
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from freud_b200 import data, density, locality, order
+from freud_b200 import data, density, locality, order, pmft
 from freud_b200.box import Box
 from oracle import port, ref
 from tests.util import BOXES, bits, random_points
@@ -191,6 +191,39 @@ def test_steinhardt_vs_reference_noisy_fcc():
         pnl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True)
         want = port.steinhardt(box, False, pts, pnl, [4, 6])
         np.testing.assert_allclose(st.ql, want["ql"], rtol=1e-5, atol=1e-6)
+
+
+def test_pmftxy_api():
+    """freud.pmft.PMFTXY (tests/test_pmft.py upstream): bin counts and PCF bit for bit against the reference's committed
+    outputs, pmft = -log(pcf), histogram properties, reset=False, 3-D boxes refused."""
+    from tests.golden.make_golden import pmftxy_inputs
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pmftxy.npz"))
+    box = Box(30, 26, 0, 0.35, 0, 0, is2D=True)
+    pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+    th_p, th_q = pmftxy_inputs(3000, 800, 5)
+    pm = pmft.PMFTXY(3.0, 2.5, (30, 24))
+    assert pm.nbins == (30, 24) and np.isclose(pm.r_max, np.sqrt(3.0 ** 2 + 2.5 ** 2))
+    assert pm.bounds == [(-3.0, 3.0), (-2.5, 2.5)] and [len(e) for e in pm.bin_edges] == [31, 25]
+    pm.compute((box, pts), th_q, query_points=q)
+    assert np.array_equal(pm.bin_counts, gold["tilt2d_query_counts"])
+    assert np.array_equal(bits(pm._pcf), bits(gold["tilt2d_query_pcf"]))
+    with np.errstate(divide="ignore"):
+        assert np.array_equal(pm.pmft, -np.log(gold["tilt2d_query_pcf"]))
+    pm.compute((box, pts), th_q, query_points=q, reset=False)  # a second identical frame: same PCF
+    assert np.array_equal(pm.bin_counts, 2 * gold["tilt2d_query_counts"])
+    assert np.array_equal(bits(pm._pcf), bits(gold["tilt2d_query_pcf"]))
+    pm.compute((box, pts), th_p)
+    assert np.array_equal(pm.bin_counts, gold["tilt2d_self_counts"])
+    assert np.array_equal(bits(pm._pcf), bits(gold["tilt2d_self_pcf"])) and pm.box == box
+    # quaternions about z are reduced to their angle
+    quats = np.stack([np.cos(th_p / 2), np.zeros_like(th_p), np.zeros_like(th_p), np.sin(th_p / 2)], axis=1)
+    counts_q = pmft.PMFTXY(3.0, 2.5, (30, 24)).compute((box, pts), quats).bin_counts
+    assert abs(int(counts_q.sum()) - int(gold["tilt2d_self_counts"].sum())) < 50  # angles differ by rounding only
+    with pytest.raises(ValueError):
+        pmft.PMFTXY(3.0, 2.5, 10).compute((Box.cube(10), random_points(Box.cube(10), 100, 1)), np.zeros(100))
+    with pytest.raises(ValueError):
+        pmft.PMFTXY(3.0, 2.5, (0, 4))
 
 
 def test_correlation_function_api():

@@ -285,6 +285,39 @@ def test_knn(ctx, name):
 GHOST = 2
 
 
+def test_pmftxy_over_a_neighbor_list(ctx):
+    """fgpu_pmftxy_* (PMFTXY.cc:25-87) over device NeighborLists against the committed outputs of the reference: bin
+    counts bit for bit (the rotation's cos/sin come from the host libm), reset=False accumulation, a histogram too
+    large for shared memory."""
+    from freud_b200.box import Box
+    from tests.golden.make_golden import pmftxy_inputs
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "pmftxy.npz"))
+    r = float(np.sqrt(3.0 ** 2 + 2.5 ** 2))
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        dp = capi.DevicePoints(ctx, box, pts)
+        pm = capi.DevicePMFTXY(ctx, 3.0, 2.5, 30, 24)
+        pm.accumulate_nlist(dp.ball_query(q, IMAGE, r, 0.0, False), th_q)
+        assert np.array_equal(pm.read(), gold[f"{name}_query_counts"])
+        pm.accumulate_nlist(dp.ball_query(q, IMAGE, r, 0.0, False), th_q)
+        assert np.array_equal(pm.read(), 2 * gold[f"{name}_query_counts"])
+        pm.reset()
+        pm.accumulate_nlist(dp.ball_query(None, IMAGE, r, 0.0, True), th_p)
+        assert np.array_equal(pm.read(), gold[f"{name}_self_counts"])
+    big = capi.DevicePMFTXY(ctx, 3.0, 2.5, 150, 120)  # 72 KB of counters: global atomics
+    nl_dev = dp.ball_query(None, IMAGE, r, 0.0, True)
+    big.accumulate_nlist(nl_dev, th_p)
+    nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, r, 0.0, True)
+    assert np.array_equal(big.read(), port.pmftxy(box, 3000, nl, th_p, 3.0, 2.5, 150, 120)[0])
+    with pytest.raises(ValueError):
+        capi.DevicePMFTXY(ctx, 3.0, 2.5, 0, 4)
+    with pytest.raises(ValueError):
+        capi.DevicePMFTXY(ctx, -1.0, 2.5, 4, 4)
+
+
 def test_correlation_function_over_a_neighbor_list(ctx):
     """fgpu_corr_* (CorrelationFunction.cc:26-95) over device NeighborLists against the committed outputs of the
     reference: bin counts identical, complex<double> sums to double rounding; accumulation over two calls."""

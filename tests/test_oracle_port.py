@@ -165,6 +165,26 @@ def test_port_correlation_function_matches_golden():
         np.testing.assert_allclose(corr, gold[f"{name}_real_corr"], rtol=1e-12, atol=1e-13)
 
 
+def test_port_pmftxy_matches_golden():
+    """PMFTXY restated in oracle/port.c against outputs of the reference (tests/golden/pmftxy.npz): bin counts and PCF
+    bit for bit (cosf / sinf are the same libm's on both sides)."""
+    from tests.golden.make_golden import pmftxy_inputs
+
+    gold = np.load(os.path.join(GOLD, "pmftxy.npz"))
+    r = float(np.sqrt(3.0 ** 2 + 2.5 ** 2))
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, q, r, 0.0, False)
+        counts, pcf = port.pmftxy(box, 3000, nl, th_q, 3.0, 2.5, 30, 24)
+        assert np.array_equal(counts, gold[f"{name}_query_counts"])
+        assert np.array_equal(bits(pcf), bits(gold[f"{name}_query_pcf"]))
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, r, 0.0, True)
+        counts, pcf = port.pmftxy(box, 3000, nl, th_p, 3.0, 2.5, 30, 24)
+        assert np.array_equal(counts, gold[f"{name}_self_counts"])
+        assert np.array_equal(bits(pcf), bits(gold[f"{name}_self_pcf"]))
+
+
 def test_port_wigner3j_known_values():
     """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
     the reference is present, every tabulated l <= 20 as float."""
