@@ -356,7 +356,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         uint64_t n_bonds = 0;
         launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
         bool const evals_counted = s2.evals != nullptr;
-        for (int attempt = 0; attempt < 3 && !done && !general; ++attempt)
+        for (int attempt = 0; attempt < 4 && !done && !general; ++attempt)
         {
             cap = std::min<uint64_t>(cap, 0xffffffffULL);
             ctx->bag4.reserve(cap);
@@ -390,9 +390,16 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
             d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
             sync(ctx);
             int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
-            if (fail != 0)
+            uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
+            if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
             {
-                general = true; // 1: points outside the box, 2: a row may be longer than the warp buffer
+                // a tile denser than the uniform estimate (clustered system): same kernels, a hit buffer that holds
+                // it -- fewer resident warps, still far ahead of the thread-per-query family
+                s2.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
+            }
+            else if (fail != 0)
+            {
+                general = true; // 1: points outside the box, 2: a tile beyond the largest buffer
                 fast_counted_evals = evals_counted && fail != 1; // the count kernel skips case 1 itself
             }
             else if (ctx->h_scalars[5] <= cap)
@@ -1063,7 +1070,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                     double const shell = pts->box.is2d ? M_PI * (double) window * window
                                                        : 4.0 / 3.0 * M_PI * (double) window * window * window;
                     uint64_t cap = (uint64_t) (1.25 * (double) rows * density * shell) + 4096;
-                    for (int pass = 0; pass < 3; ++pass)
+                    for (int pass = 0; pass < 4; ++pass)
                     {
                         cap = std::min<uint64_t>(cap, 0x7fffffffULL); // the top bit of a bag offset names the bag
                         bag.reserve(cap);
@@ -1089,9 +1096,16 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                         exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
                         d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(unsigned long long));
                         sync(ctx);
-                        if ((ctx->h_scalars[4] & 0xffffffffULL) != 0)
+                        int const failed = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+                        uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
+                        if (failed == 2 && densest <= search2_max_out_cap() && args.out_cap < search2_max_out_cap())
                         {
-                            return WINDOW_GENERAL; // 1: points outside the box, 2: a row may be longer than the warp buffer
+                            args.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
+                            continue; // a denser tile than the uniform estimate: retry with a buffer that holds it
+                        }
+                        if (failed != 0)
+                        {
+                            return WINDOW_GENERAL; // 1: points outside the box, 2: a tile beyond the largest buffer
                         }
                         if (ctx->h_scalars[5] <= cap)
                         {

@@ -334,7 +334,8 @@ struct Search2Args
     uint32_t* counts;               // per query (original order)
     uint32_t* tmp_start;            // per query: offset of its row in the bag
     unsigned long long* cursor;     // bag records reserved so far (== total bonds at the end)
-    int* fail;                      // != 0: the result cannot be represented by this path, run the general kernels
+    int* fail;                      // != 0: the result cannot be represented by this path (1: points outside the box,
+                                    // 2: a tile has more candidates than out_cap; fail[1] = that count)
     // RDF mode
     AxisDev axis;
     uint32_t* hist;
@@ -356,6 +357,7 @@ ShardPlan shard_plan(const int dim[3], uint32_t n_points, int shard, int n_shard
 bool search2_supported(const Search2Args& a, int mode);
 void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a);
 uint32_t search2_out_cap(double expected_candidates_per_query);
+uint32_t search2_max_out_cap();
 // adds the pair evaluations of the query set to *a.evals (no-op when a.evals == nullptr)
 void launch_count_evals(fgpu_ctx* ctx, const Search2Args& a, uint32_t n_query, const uint32_t* cell_of_point,
                         uint32_t n_points);

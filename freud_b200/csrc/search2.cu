@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
             {
                 if (lane == 0)
                 {
-                    *a.fail = 2; // a single row may exceed the buffer: the general kernel takes over
+                    *a.fail = 2; // a single row may exceed the buffer: the host retries with a larger one
+                    atomicMax(reinterpret_cast<unsigned int*>(a.fail) + 1, T); // ... sized for the densest tile
                 }
                 q_per_batch = 0;
             }
@@ -733,6 +734,13 @@ bool search2_supported(const Search2Args& a, int mode)
     bool const grid_ok = a.dx >= 3 && a.dy >= 3 && (a.dz >= 3 || (a.box.is2d && a.dz == 1));
     bool const hist_ok = mode != S2_RDF || a.axis.bins * sizeof(uint32_t) <= 64 * 1024;
     return grid_ok && hist_ok;
+}
+
+// Largest hit buffer a block can hold (four warps, 20 B per record, under the 200 KB opted in below); a tile with
+// more candidates than this really needs the general kernels.
+uint32_t search2_max_out_cap()
+{
+    return 2048;
 }
 
 uint32_t search2_out_cap(double expected_candidates_per_tile)

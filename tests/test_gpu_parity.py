@@ -285,6 +285,29 @@ def test_knn(ctx, name):
 GHOST = 2
 
 
+@pytest.mark.parametrize("blob", [600, 3000])
+def test_clustered_system_dense_tiles(ctx, blob):
+    """A tile with far more candidates than the uniform estimate: the warp-cooperative kernels are retried with a hit
+    buffer sized for it (blob = 600), and hand over to the general family only beyond the largest buffer (3000)."""
+    from freud_b200.box import Box
+
+    capi = _capi()
+    box = Box.cube(20)
+    rs = np.random.RandomState(5)
+    cluster = (np.float32([3.0, -2.0, 1.0]) + 0.4 * rs.standard_normal((blob, 3))).astype(np.float32)
+    pts = np.concatenate([random_points(box, 4000, seed=71), box.wrap(cluster)]).astype(np.float32)
+    dp = capi.DevicePoints(ctx, box, pts)
+    for flavour in (WRAP, IMAGE):
+        got = dp.ball_query(None, flavour, 2.5, 0.0, True).to_host()
+        assert_nlist_equal(got, port.ball_nlist(flavour, box, False, pts, pts, 2.5, 0.0, True), f"blob {blob} fl {flavour}")
+    q = pts[::7]
+    got = dp.knn_query(q, 8, exclude_ii=False).to_host()
+    assert_nlist_equal(got, port.knn_nlist(box, False, pts, q, 8), f"blob {blob} knn")
+    rdf = capi.DeviceRDF(ctx, 60, 2.5)
+    rdf.accumulate(dp, None, IMAGE, 2.5, 0.0, True)
+    assert np.array_equal(rdf.read(), port.rdf_accumulate(port.IMAGE, box, False, pts, pts, 60, 2.5, 0.0, True))
+
+
 def test_pmftxy_over_a_neighbor_list(ctx):
     """fgpu_pmftxy_* (PMFTXY.cc:25-87) over device NeighborLists against the committed outputs of the reference: bin
     counts bit for bit (the rotation's cos/sin come from the host libm), reset=False accumulation, a histogram too
