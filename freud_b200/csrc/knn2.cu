@@ -1,12 +1,14 @@
 // k-nearest-neighbour selection on top of the warp-cooperative ball search (the production kNN path).
 //
-// Replaces AABBQueryIterator::next (freud/locality/AABBQuery.cc:152-281).  By E3 that
-// iterator returns, per query point, the k smallest closest-image distances in the IMAGE arithmetic
+// Replaces AABBQueryIterator::next (freud/locality/AABBQuery.cc:152-281) and, in the WRAP flavour,
+// LinkCellQueryIterator::next (freud/locality/LinkCell.cc:575-679).  By E3 the first
+// returns, per query point, the k smallest closest-image distances in the IMAGE arithmetic
 // r = p_j - (q + image_k) among the points with d >= r_min and r_sq < r_max^2, whatever r_guess and scale
-// are.  So the search is one ball query of k_search2<IMAGE, NL> (search2.cu) at a window radius r_win that is
-// expected to hold about 2(k + 1) points -- on a grid whose cells are at least r_win thick only one image of
-// a point can be inside the window, the one implied by how its cell was reached, and it is the closest one --
-// followed by a selection inside every bag row:
+// are; the second the k smallest wrapped distances with r_min^2 <= r_sq < r_max^2.  So the search is one ball
+// query of k_search2<flavour, NL> (search2.cu) at a window radius r_win that is expected to hold about
+// 1.5 (k + 1) points -- on a grid whose cells are at least r_win thick only one image of a point can be inside
+// the window, the one implied by how its cell was reached, and it is the closest one -- followed by a selection
+// inside every bag row:
 //
 //   k_knn_rows    counts[q] = min(hits[q], k); a row with fewer than k hits is unresolved unless the window
 //                 already is r_max.  The host searches the unresolved rows again -- only those, into a second
