@@ -40,28 +40,88 @@ class Box:
 
     @classmethod
     def from_box(cls, box, dimensions=None):
-        """Accepts a Box, an object with Lx/Ly/Lz/xy/xz/yz attributes, a dict, or a 2/3/6 sequence
-        (reference: freud/box.py:754-845)."""
-        if isinstance(box, cls):
+        """Coerces a box-like object (reference: freud/box.py:751-843): a Box, an object with ``Lx, Ly[, Lz, xy, xz,
+        yz, dimensions]`` attributes, a mapping with those keys, a 3x3 matrix of lattice vectors (columns), or a
+        sequence ``[Lx, Ly]``, ``[Lx, Ly, Lz]`` or ``[Lx, Ly, Lz, xy, xz, yz]``.  ``dimensions`` overrides the
+        detected dimensionality (2 if ``Lz == 0``) but may not contradict a ``dimensions`` the object carries."""
+        if isinstance(box, cls) and dimensions in (None, box.dimensions):
             return box
-        if hasattr(box, "Lx"):
-            vals = [box.Lx, box.Ly, getattr(box, "Lz", 0), getattr(box, "xy", 0), getattr(box, "xz", 0),
-                    getattr(box, "yz", 0)]
-            is2d = getattr(box, "is2D", getattr(box, "dimensions", 3) == 2)
-            if callable(is2d):
-                is2d = is2d()
-            return cls(*vals, is2D=bool(is2d) if dimensions is None else dimensions == 2)
-        if isinstance(box, dict):
-            return cls(box["Lx"], box["Ly"], box.get("Lz", 0), box.get("xy", 0), box.get("xz", 0), box.get("yz", 0),
-                       is2D=(box.get("dimensions", 3) == 2) if dimensions is None else dimensions == 2)
-        seq = np.asarray(box, dtype=np.float64).ravel()
-        if seq.size == 2:
-            return cls(seq[0], seq[1], 0, 0, 0, 0, is2D=True)
-        if seq.size == 3:
-            return cls(seq[0], seq[1], seq[2], 0, 0, 0, is2D=(seq[2] == 0) if dimensions is None else dimensions == 2)
-        if seq.size == 6:
-            return cls(*seq, is2D=(seq[2] == 0) if dimensions is None else dimensions == 2)
-        raise ValueError("Cannot interpret box: expected a Box, a dict, or a sequence of 2, 3 or 6 numbers.")
+        if not isinstance(box, dict) and not hasattr(box, "Lx") and np.shape(box) == (3, 3):
+            return cls.from_matrix(box, dimensions=dimensions)
+
+        def reconcile(own):
+            if dimensions is not None and own is not None and own != dimensions:
+                raise ValueError("The provided dimensions argument conflicts with the dimensions attribute of the "
+                                 "provided box object.")
+            return own if dimensions is None else dimensions
+
+        if hasattr(box, "Lx") and hasattr(box, "Ly"):
+            vals = [box.Lx, box.Ly] + [getattr(box, name, 0) for name in ("Lz", "xy", "xz", "yz")]
+            dims = reconcile(getattr(box, "dimensions", None))
+        elif isinstance(box, dict) or (hasattr(box, "keys") and hasattr(box, "get")):
+            try:
+                vals = [box["Lx"], box["Ly"]] + [box.get(name, 0) for name in ("Lz", "xy", "xz", "yz")]
+            except KeyError as exc:
+                raise ValueError("A box mapping needs at least the keys 'Lx' and 'Ly'.") from exc
+            dims = reconcile(box.get("dimensions", None))
+        else:
+            try:
+                n = len(box)
+            except TypeError as exc:
+                raise ValueError("Supplied box cannot be converted to a Box.") from exc
+            if n not in (2, 3, 6):
+                raise ValueError("List-like objects must have length 2, 3, or 6 to be converted to a Box.")
+            vals = [box[0], box[1], box[2] if n > 2 else 0] + (list(box[3:6]) if n == 6 else [0, 0, 0])
+            dims = dimensions
+        if dims is None:
+            dims = 2 if vals[2] == 0 else 3
+        return cls(*vals, is2D=dims == 2)
+
+    @classmethod
+    def from_matrix(cls, box_matrix, dimensions=None):
+        """Box from the 3x3 matrix whose columns are the lattice vectors, in float32 as upstream
+        (freud/box.py:846-882; the HOOMD-blue box-matrix convention)."""
+        m = np.asarray(box_matrix, dtype=_F)
+        if m.shape != (3, 3):
+            raise ValueError("A box matrix must be 3x3.")
+        v0, v1, v2 = m[:, 0], m[:, 1], m[:, 2]
+        Lx = np.sqrt(np.dot(v0, v0))
+        a2x = np.dot(v0, v1) / Lx
+        Ly = np.sqrt(np.dot(v1, v1) - a2x * a2x)
+        xy = a2x / Ly
+        n01 = np.cross(v0, v1)
+        Lz = np.dot(v2, n01) / np.sqrt(np.dot(n01, n01))
+        xz = yz = 0
+        if Lz != 0:
+            a3x = np.dot(v0, v2) / Lx
+            xz = a3x / Lz
+            yz = (np.dot(v1, v2) - a2x * a3x) / (Ly * Lz)
+        if dimensions is None:
+            dimensions = 2 if Lz == 0 else 3
+        return cls(Lx, Ly, Lz, xy, xz, yz, is2D=dimensions == 2)
+
+    @classmethod
+    def from_box_lengths_and_angles(cls, L1, L2, L3, alpha, beta, gamma, dimensions=None):
+        """Box from three lattice-vector lengths and the angles between them in radians (freud/box.py:921-983)."""
+        for name, ang in (("alpha", alpha), ("beta", beta), ("gamma", gamma)):
+            if not 0 < ang < np.pi:
+                raise ValueError(f"{name} must be between 0 and pi.")
+        a1 = np.array([L1, 0, 0])
+        a2 = np.array([L2 * np.cos(gamma), L2 * np.sin(gamma), 0])
+        a3x = np.cos(beta)
+        a3y = (np.cos(alpha) - np.cos(beta) * np.cos(gamma)) / np.sin(gamma)
+        under = 1 - a3x**2 - a3y**2
+        if under < 0:
+            raise ValueError("The provided angles can not form a valid box.")
+        a3 = L3 * np.array([a3x, a3y, np.sqrt(under)])
+        if dimensions is None:
+            dimensions = 2 if L3 == 0 else 3
+        return cls.from_matrix(np.array([a1, a2, a3]).T, dimensions=dimensions)
+
+    def to_matrix(self):
+        """Columns are the lattice vectors (freud/box.py:617-630)."""
+        L, (xy, xz, yz) = self._L.astype(np.float64), self._tilt.astype(np.float64)
+        return np.array([[L[0], xy * L[1], xz * L[2]], [0, L[1], yz * L[2]], [0, 0, L[2]]])
 
     # -- scalar properties ----------------------------------------------------------------------
     Lx = property(lambda self: float(self._L[0]))

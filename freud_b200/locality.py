@@ -62,6 +62,41 @@ def _query_args(d):
     return qa
 
 
+def _class_paths(obj):
+    return {f"{c.__module__}.{c.__name__}" for c in type(obj).__mro__}
+
+
+def _system_pair(system):
+    """(box-like, positions) of a system-like object; the cases of freud/locality.py:313-372."""
+    paths = _class_paths(system)
+    if paths & {"MDAnalysis.coordinates.base.Timestep", "MDAnalysis.coordinates.timestep.Timestep"}:
+        return system.triclinic_dimensions, system.positions
+    if paths & {"gsd.hoomd.Frame", "gsd.hoomd.Snapshot", "hoomd.snapshot.Snapshot"}:
+        # HOOMD writes Lz = 1 for 2-D boxes: the configuration's dimensions decide, not Lz
+        box = np.array(system.configuration.box, dtype=np.float64)
+        if system.configuration.dimensions == 2:
+            box[[2, 4, 5]] = 0
+        return box, system.particles.position
+    if "garnett.trajectory.Frame" in paths:
+        return system.box, system.position if hasattr(system, "position") else system.positions
+    if paths & {"ovito.data.DataCollection", "ovito.plugins.PyScript.DataCollection", "PyScript.DataCollection"}:
+        cell = system.cell
+        return Box.from_box(np.asarray(cell.matrix)[:, :3], dimensions=2 if cell.is2D else 3), system.particles.positions
+    if hasattr(system, "box") and hasattr(system, "particles") and hasattr(system.particles, "position"):
+        box = system.box  # HOOMD-blue 2 snapshot
+        if getattr(box, "dimensions", 3) == 2:
+            box = Box(box.Lx, box.Ly, xy=getattr(box, "xy", 0), is2D=True)
+        return box, system.particles.position
+    if hasattr(system, "box") and hasattr(system, "points"):
+        return system.box, system.points
+    try:
+        box, points = system
+    except (TypeError, ValueError) as exc:
+        raise ValueError("Cannot interpret the system: expected a NeighborQuery, a (box, points) pair, an object "
+                         "with box and points, or a frame of a supported reader.") from exc
+    return box, points
+
+
 class NeighborQueryResult:
     """Lazy result of ``NeighborQuery.query`` (freud/locality.py:178-229)."""
 
@@ -94,12 +129,21 @@ class NeighborQuery:
 
     @classmethod
     def from_system(cls, system, dimensions=None):
-        if isinstance(system, NeighborQuery):
+        """Anything system-like becomes a NeighborQuery (freud/locality.py:268-383): a NeighborQuery is returned as it
+        is; otherwise a box and an (N, 3) position array are taken from, in this order, an MDAnalysis ``Timestep``,
+        a GSD / HOOMD-blue 3 frame or snapshot, a garnett ``Frame``, an OVITO ``DataCollection``, a HOOMD-blue 2
+        snapshot, any object with ``box`` and ``points``, or a ``(box, points)`` pair.  Foreign types are recognised
+        by class path, so none of those packages is imported here."""
+        if isinstance(system, cls):
             return system
-        if hasattr(system, "box") and hasattr(system, "points"):
-            return _RawPoints(system.box, system.points)
+        if isinstance(system, NeighborQuery) and cls is not NeighborQuery:
+            system = (system.box, system.points)  # another engine over the same data
+        else:
+            system = _system_pair(system)
         box, points = system
-        return _RawPoints(Box.from_box(box, dimensions), points)
+        if dimensions is not None:
+            box = Box.from_box(box, dimensions)
+        return _RawPoints(box, points) if cls is NeighborQuery else cls(box, points)
 
     @property
     def box(self):
@@ -238,3 +282,75 @@ class _PairCompute:
     def default_query_args(self):
         raise NotImplementedError(f"The {type(self).__name__} class does not provide default query arguments. "
                                   "You must either provide query arguments or a neighbor list to this compute method.")
+
+
+class PeriodicBuffer:
+    """Replicates points across the periodic boundaries (freud/locality.py:1080-1156, PeriodicBuffer.cc:23-117);
+    host-side input preparation, float32 with one rounding per operation in the reference's order.
+
+    ``images=True``: ``buffer`` counts whole images appended on the +x/+y/+z side of the box and every replica is
+    wrapped into the grown box; otherwise ``buffer`` is a distance by which the box grows on every side and the
+    replicas inside the grown box are kept.  ``buffer_ids`` names the input point of every buffer point."""
+
+    def compute(self, system, buffer, images=False, include_input_points=False):
+        nq = NeighborQuery.from_system(system)
+        if np.ndim(buffer) == 0:
+            buffer = [buffer] * 3
+        elif len(buffer) != 3:
+            raise ValueError("buffer must be a scalar or have length 3.")
+        buff = np.asarray(buffer, dtype=np.float32)
+        for axis, b in zip("xyz", buff):
+            if b < 0:
+                raise ValueError(f"Buffer {axis} distance must be non-negative.")
+        box, f32 = nq.box, np.float32
+        L = box.L.astype(f32)
+        if images:
+            reps = np.ceil(buff).astype(np.int64)
+            grown = [f32(1 + reps[d]) * L[d] for d in range(3)]
+        else:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                reps = np.ceil(buff / L)
+            reps = np.where(np.isfinite(reps), reps, 0).astype(np.int64)
+            grown = [L[d] + f32(2) * buff[d] for d in range(3)]
+        if box.is2D:
+            reps[2] = 0
+        self._buffer_box = Box(grown[0], grown[1], grown[2], box.xy, box.xz, box.yz, is2D=box.is2D)
+        lo = np.zeros(3, dtype=np.int64) if images else -reps
+        shifts = np.array([(i, j, k) for i in range(lo[0], reps[0] + 1) for j in range(lo[1], reps[1] + 1)
+                           for k in range(lo[2], reps[2] + 1)], dtype=np.int64)
+        if not include_input_points:
+            shifts = shifts[np.any(shifts != 0, axis=1)]
+        a1 = np.array([L[0], 0, 0], dtype=f32)
+        a2 = np.array([L[1] * f32(box.xy), L[1], 0], dtype=f32)
+        a3 = np.array([L[2] * f32(box.xz), L[2] * f32(box.yz), L[2]], dtype=f32)
+        pts = nq.points.astype(f32)
+        n, m = len(pts), len(shifts)
+        out = np.repeat(pts, m, axis=0)  # point-major, images inner (PeriodicBuffer.cc:69-77)
+        sh = np.tile(shifts, (n, 1)).astype(f32)
+        out = out + sh[:, 0:1] * a1
+        out = out + sh[:, 1:2] * a2
+        if not box.is2D:
+            out = out + sh[:, 2:3] * a3
+        ids = np.repeat(np.arange(n, dtype=np.uint32), m)
+        if images:
+            out = self._buffer_box.wrap(out) if len(out) else out
+        else:
+            frac = self._buffer_box.make_fractional(out) if len(out) else np.zeros((0, 3), f32)
+            keep = (frac[:, 0] >= 0) & (frac[:, 0] < 1) & (frac[:, 1] >= 0) & (frac[:, 1] < 1)
+            if not box.is2D:
+                keep &= (frac[:, 2] >= 0) & (frac[:, 2] < 1)
+            out, ids = out[keep], ids[keep]
+        self._buffer_points, self._buffer_ids = np.ascontiguousarray(out, dtype=f32), ids
+        return self
+
+    def _result(self, name):
+        if not hasattr(self, name):
+            raise AttributeError("PeriodicBuffer: call compute() first.")
+        return getattr(self, name)
+
+    buffer_points = property(lambda self: self._result("_buffer_points"))
+    buffer_ids = property(lambda self: self._result("_buffer_ids"))
+    buffer_box = property(lambda self: self._result("_buffer_box"))
+
+    def __repr__(self):
+        return "freud_b200.locality.PeriodicBuffer()"

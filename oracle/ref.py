@@ -254,6 +254,26 @@ def local_density(query, query_points, r_max, diameter, nlist=None, q_r_max=None
     return num, den
 
 
+def periodic_buffer(query, buffer, images=False, include_input_points=False):
+    """PeriodicBuffer().compute(...) of the reference: (buffer_points, buffer_ids, box6 of the grown box)."""
+    L = lib()
+    L.fref_pbuff_compute.restype = C.c_void_p
+    L.fref_pbuff_compute.argtypes = [C.c_void_p, _fp, C.c_int, C.c_int]
+    L.fref_pbuff_size.argtypes = [C.c_void_p]
+    L.fref_pbuff_size.restype = C.c_uint
+    L.fref_pbuff_copy.argtypes = [C.c_void_p, _fp, _up, _fp]
+    L.fref_pbuff_destroy.argtypes = [C.c_void_p]
+    buff = np.ascontiguousarray(np.broadcast_to(np.asarray(buffer, np.float32), (3,)))
+    h = L.fref_pbuff_compute(query._h, _p(buff), int(bool(images)), int(bool(include_input_points)))
+    if not h:
+        _raise()
+    n = L.fref_pbuff_size(h)
+    pts, ids, box6 = np.zeros((n, 3), np.float32), np.zeros(n, np.uint32), np.zeros(6, np.float32)
+    L.fref_pbuff_copy(h, _p(pts), _p(ids, _up), _p(box6))
+    L.fref_pbuff_destroy(h)
+    return pts, ids, box6
+
+
 class Steinhardt:
     def __init__(self, l, average=False, wl=False, weighted=False, wl_normalize=False):
         self.ls = np.atleast_1d(np.asarray(l, dtype=np.uint32)).copy()

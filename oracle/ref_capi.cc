@@ -14,6 +14,7 @@
 //   freud::density::CorrelationFunction              freud/density/CorrelationFunction.h:52
 //   freud::pmft::PMFTXY                              freud/pmft/PMFTXY.h
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
+//   freud::locality::PeriodicBuffer                  freud/locality/PeriodicBuffer.h:22
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
 
 #include <complex>
@@ -32,6 +33,7 @@
 #include "NeighborList.h"
 #include "NeighborQuery.h"
 #include "PMFTXY.h"
+#include "PeriodicBuffer.h"
 #include "RDF.h"
 #include "RawPoints.h"
 #include "Steinhardt.h"
@@ -370,6 +372,50 @@ int fref_local_density(void* nq, const float* qpts, unsigned n_query, void* nlis
         std::memcpy(num_neighbors, ld.getNumNeighbors()->data(), n_query * sizeof(float));
         std::memcpy(density, ld.getDensity()->data(), n_query * sizeof(float));
     });
+}
+
+// ---- PeriodicBuffer -------------------------------------------------------------------------------
+// PeriodicBuffer().compute(nq, buffer, images, include_input_points).  Returns an owning handle; the count, the
+// grown box and the arrays are read with the calls below.
+void* fref_pbuff_compute(void* nq, const float* buffer3, int images, int include_input_points)
+{
+    freud::locality::PeriodicBuffer* pb = nullptr;
+    int const rc = guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        auto fresh = std::make_unique<freud::locality::PeriodicBuffer>();
+        fresh->compute(h->nq, {buffer3[0], buffer3[1], buffer3[2]}, images != 0, include_input_points != 0);
+        pb = fresh.release();
+    });
+    return rc == 0 ? pb : nullptr;
+}
+
+unsigned fref_pbuff_size(void* pb)
+{
+    return static_cast<unsigned>(static_cast<freud::locality::PeriodicBuffer*>(pb)->getBufferIds()->size());
+}
+
+void fref_pbuff_copy(void* pb, float* points, unsigned* ids, float* box6)
+{
+    auto* b = static_cast<freud::locality::PeriodicBuffer*>(pb);
+    auto const& pts = *b->getBufferPoints();
+    auto const& id = *b->getBufferIds();
+    if (!id.empty())
+    {
+        std::memcpy(points, pts.data(), pts.size() * sizeof(vec3<float>));
+        std::memcpy(ids, id.data(), id.size() * sizeof(unsigned));
+    }
+    Box const& box = b->getBufferBox();
+    box6[0] = box.getLx();
+    box6[1] = box.getLy();
+    box6[2] = box.getLz();
+    box6[3] = box.getTiltFactorXY();
+    box6[4] = box.getTiltFactorXZ();
+    box6[5] = box.getTiltFactorYZ();
+}
+
+void fref_pbuff_destroy(void* pb)
+{
+    delete static_cast<freud::locality::PeriodicBuffer*>(pb);
 }
 
 // ---- Steinhardt -----------------------------------------------------------------------------------

@@ -90,6 +90,7 @@ def main():
     local_density()
     correlation_function()
     pmftxy()
+    periodic_buffer()
 
 
 STEINHARDT_OPTIONS = {
@@ -177,6 +178,31 @@ def pmftxy():
         out[f"{name}_self_counts"], out[f"{name}_self_pcf"] = ref.pmftxy(Q, th_p, pts, 3.0, 2.5, 30, 24, exclude_ii=True)
     np.savez_compressed(os.path.join(HERE, "pmftxy.npz"), **out)
     print("pmftxy", int(out["sq2d_query_counts"].sum()), out["sq2d_query_pcf"][15, 10:13])
+
+
+PBUFF_BOXES = {"cube": Box.cube(5), "tri": Box(4, 5, 6, 0.3, -0.2, 0.1), "tilt2d": Box(4, 5, 0, 0.25, 0, 0, is2D=True)}
+PBUFF_MODES = {
+    # tag: (buffer, images, include_input_points) -- PeriodicBuffer.cc:23-117
+    "img2_all": (2, True, True),
+    "img120": ((1, 2, 0), True, False),
+    "dist13": (1.3, False, False),
+    "dist_mixed_all": ((0.5, 2.2, 1.0), False, True),
+}
+
+
+def periodic_buffer():
+    """PeriodicBuffer in both modes (whole images / a distance on every side) and the systems that
+    freud.data.UnitCell.generate_system builds on it (freud/data.py:58-150): here the replication only, which is
+    all of the reference's C++ involved; the noise is numpy's."""
+    out = {}
+    for name, box in PBUFF_BOXES.items():
+        pts = random_points(box, 40, 300 + len(name))
+        q = ref.Query("raw", box, pts, is2d=box.is2D)
+        for tag, (buffer, images, incl) in PBUFF_MODES.items():
+            bp, ids, box6 = ref.periodic_buffer(q, buffer, images, incl)
+            out[f"{name}_{tag}_points"], out[f"{name}_{tag}_ids"], out[f"{name}_{tag}_box"] = bp, ids, box6
+    np.savez_compressed(os.path.join(HERE, "periodic_buffer.npz"), **out)
+    print("periodic buffer", {k: v.shape for k, v in out.items() if k.endswith("ids")})
 
 
 if __name__ == "__main__":

@@ -118,3 +118,88 @@ def test_no_cpu_fallback():
         density.RDF(10, 2.0).compute((Box.cube(10), np.zeros((5, 3), np.float32)))
     with pytest.raises(RuntimeError):
         locality.LinkCell(Box.cube(10), np.zeros((5, 3), np.float32)).query(np.zeros((1, 3)), dict(r_max=2)).toNeighborList()
+
+
+# ---- system adapters (freud/locality.py:268-383, freud/box.py:751-882) -------------
+def _foreign(path, **attrs):
+    """Stand-in for a frame of a reader that is not installed: from_system recognises them by class path."""
+    module, name = path.rsplit(".", 1)
+    return type(name, (), {"__module__": module})(), attrs
+
+
+def _ns(**kw):
+    return type("NS", (), kw)()
+
+
+def _make(path, **attrs):
+    obj, attrs = _foreign(path, **attrs)
+    for k, v in attrs.items():
+        setattr(obj, k, v)
+    return obj
+
+
+def test_from_box_forms():
+    b = Box.from_box([2, 3, 4, 0.1, 0.2, 0.3])
+    assert (b.Lx, b.Ly, b.Lz, b.dimensions) == (2, 3, 4, 3) and np.allclose([b.xy, b.xz, b.yz], [0.1, 0.2, 0.3])
+    assert Box.from_box([2, 3]).is2D and Box.from_box([2, 3, 0]).is2D and not Box.from_box([2, 3, 4]).is2D
+    assert Box.from_box({"Lx": 2, "Ly": 3, "Lz": 4}).Lz == 4
+    assert Box.from_box({"Lx": 2, "Ly": 3, "Lz": 1, "dimensions": 2}).is2D
+    assert Box.from_box(_ns(Lx=2, Ly=3, Lz=5, xy=0.5)).xy == 0.5
+    assert Box.from_box(b) is b
+    with pytest.raises(ValueError):
+        Box.from_box([1, 2, 3, 4])
+    with pytest.raises(ValueError):
+        Box.from_box(_ns(Lx=2, Ly=3, Lz=5, dimensions=3), dimensions=2)
+    with pytest.raises(ValueError):
+        Box.from_box({"Lx": 2, "Ly": 3, "Lz": 5, "dimensions": 3}, dimensions=2)
+    # 3x3 matrix of lattice vectors (columns), round trip through to_matrix
+    tri = Box(4, 5, 6, 0.3, -0.2, 0.1)
+    back = Box.from_box(tri.to_matrix())
+    assert np.allclose(back.as_array6(), tri.as_array6(), atol=1e-6) and not back.is2D
+    flat = Box.from_matrix([[4, 1, 0], [0, 5, 0], [0, 0, 0]])
+    assert flat.is2D and np.isclose(flat.xy, 0.2)
+    ang = Box.from_box_lengths_and_angles(2, 3, 4, np.pi / 2, np.pi / 2, np.pi / 2)
+    assert np.allclose(ang.as_array6(), [2, 3, 4, 0, 0, 0], atol=1e-6)
+    with pytest.raises(ValueError):
+        Box.from_box_lengths_and_angles(2, 3, 4, 0, 1, 1)
+
+
+def test_from_system_adapters():
+    pts = np.array([[0, 0, 0], [1, 1, 0], [-1, 2, 0]], dtype=np.float32)
+    # pairs, attribute objects, existing engines
+    nq = locality.NeighborQuery.from_system((Box.cube(10), pts))
+    assert type(nq).__name__ == "_RawPoints" and np.array_equal(nq.points, pts) and nq.box == Box.cube(10)
+    assert locality.NeighborQuery.from_system(nq) is nq
+    duck = locality.NeighborQuery.from_system(_ns(box=[10, 10, 10], points=pts))
+    assert duck.box == Box.cube(10)
+    aq = locality.AABBQuery.from_system((Box.cube(10), pts))
+    assert isinstance(aq, locality.AABBQuery) and locality.AABBQuery.from_system(aq) is aq
+    many = np.random.default_rng(0).uniform(-5, 5, (500, 3)).astype(np.float32)
+    lc = locality.LinkCell.from_system(locality.AABBQuery(Box.cube(10), many))  # another engine over the same data
+    assert isinstance(lc, locality.LinkCell) and np.array_equal(lc.points, many)
+    # MDAnalysis Timestep (both class paths)
+    for path in ("MDAnalysis.coordinates.base.Timestep", "MDAnalysis.coordinates.timestep.Timestep"):
+        ts = _make(path, triclinic_dimensions=np.diag([10.0, 11.0, 12.0]), positions=pts)
+        got = locality.NeighborQuery.from_system(ts)
+        assert np.allclose(got.box.L, [10, 11, 12]) and np.array_equal(got.points, pts)
+    # GSD / HOOMD-blue 3: Lz = 1 with dimensions = 2 is a 2-D box
+    for path in ("gsd.hoomd.Frame", "gsd.hoomd.Snapshot", "hoomd.snapshot.Snapshot"):
+        frame = _make(path, configuration=_ns(box=[10, 10, 1, 0.5, 0, 0], dimensions=2), particles=_ns(position=pts))
+        got = locality.NeighborQuery.from_system(frame)
+        assert got.box.is2D and got.box.Lz == 0 and got.box.xy == 0.5
+        frame3 = _make(path, configuration=_ns(box=[10, 10, 8, 0, 0, 0], dimensions=3), particles=_ns(position=pts))
+        assert locality.NeighborQuery.from_system(frame3).box.Lz == 8
+    # garnett: position (>= 0.7) or positions
+    g_new = _make("garnett.trajectory.Frame", box=_ns(Lx=9, Ly=9, Lz=9), position=pts)
+    g_old = _make("garnett.trajectory.Frame", box=_ns(Lx=9, Ly=9, Lz=9), positions=pts)
+    assert locality.NeighborQuery.from_system(g_new).box == locality.NeighborQuery.from_system(g_old).box == Box.cube(9)
+    # OVITO: 3x4 cell matrix (last column is the origin)
+    cell = _ns(matrix=np.hstack([np.diag([7.0, 8.0, 9.0]), np.zeros((3, 1))]), is2D=False)
+    ov = _make("ovito.data.DataCollection", cell=cell, particles=_ns(positions=pts))
+    assert np.allclose(locality.NeighborQuery.from_system(ov).box.L, [7, 8, 9])
+    # HOOMD-blue 2 snapshot: box + particles.position
+    h2 = _ns(box=_ns(Lx=6, Ly=6, Lz=1, xy=0.25, dimensions=2), particles=_ns(position=pts))
+    got = locality.NeighborQuery.from_system(h2)
+    assert got.box.is2D and got.box.xy == 0.25
+    with pytest.raises(ValueError):
+        locality.NeighborQuery.from_system(42)
