@@ -71,6 +71,12 @@ SIGNATURES = {
     "fgpu_pmftxy_reset": (C.c_int, [_vp]),
     "fgpu_pmftxy_accumulate_nlist": (C.c_int, [_vp, _vp, _fp]),
     "fgpu_pmftxy_read": (C.c_int, [_vp, _up]),
+    "fgpu_pmft_create": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, _vpp]),
+    "fgpu_pmft_destroy": (None, [_vp]),
+    "fgpu_pmft_reset": (C.c_int, [_vp]),
+    "fgpu_pmft_accumulate_nlist": (C.c_int, [_vp, _vp, _fp, C.c_uint32, _fp, _fp, C.c_uint32]),
+    "fgpu_pmft_read": (C.c_int, [_vp, _up]),
+    "fgpu_pmft_deferred": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "fgpu_corr_create": (C.c_int, [_vp, C.c_uint32, C.c_float, _vpp]),
     "fgpu_corr_destroy": (None, [_vp]),
     "fgpu_corr_reset": (C.c_int, [_vp]),
@@ -406,6 +412,49 @@ class DevicePMFTXY(_DeviceObject):
         counts = np.empty(self.shape, np.uint32)
         check(lib().fgpu_pmftxy_read(self._h, ptr(counts, _up)))
         return counts
+
+
+PMFT_XYZ, PMFT_XYT, PMFT_R12 = 0, 1, 2
+
+
+class DevicePMFT(_DeviceObject):
+    """Device-resident PMFTXYZ / PMFTXYT / PMFTR12 histogram (``fgpu_pmft``); ``maxes`` and ``bins`` as the reference's
+    constructors order them (unused maxima 0)."""
+
+    _destroy = "fgpu_pmft_destroy"
+
+    def __init__(self, ctx, kind, maxes, bins):
+        self._adopt(ctx)
+        self.kind, self.shape = int(kind), tuple(int(b) for b in bins)
+        mx = [float(m) for m in maxes] + [0.0] * (3 - len(maxes))
+        self._h = _vp()
+        check(lib().fgpu_pmft_create(ctx._h, self.kind, mx[0], mx[1], mx[2], *self.shape, C.byref(self._h)))
+
+    def reset(self):
+        check(lib().fgpu_pmft_reset(self._h))
+
+    def accumulate_nlist(self, nlist, orientations, query_orientations, equiv_orientations=None):
+        """Angles (XYT, R12) or (N, 4) quaternions (XYZ: ``orientations`` is ignored, ``equiv_orientations`` required)."""
+        qo = np.ascontiguousarray(query_orientations, dtype=np.float32)
+        if self.kind == PMFT_XYZ:
+            eq = np.ascontiguousarray(equiv_orientations, dtype=np.float32).reshape(-1, 4)
+            assert qo.shape == (nlist.num_query_points, 4)
+            check(lib().fgpu_pmft_accumulate_nlist(self._h, nlist._h, None, nlist.num_points, ptr(qo), ptr(eq), len(eq)))
+            return
+        o = np.ascontiguousarray(orientations, dtype=np.float32).ravel()
+        assert len(o) == nlist.num_points and qo.size == nlist.num_query_points
+        check(lib().fgpu_pmft_accumulate_nlist(self._h, nlist._h, ptr(o), len(o), ptr(qo), None, 0))
+
+    def read(self):
+        counts = np.empty(self.shape, np.uint32)
+        check(lib().fgpu_pmft_read(self._h, ptr(counts, _up)))
+        return counts
+
+    @property
+    def host_binned_bonds(self):
+        n = C.c_uint64(0)
+        check(lib().fgpu_pmft_deferred(self._h, C.byref(n)))
+        return n.value
 
 
 class DeviceCorrelation(_DeviceObject):

@@ -1588,6 +1588,290 @@ int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host)
     });
 }
 
+// ---- PMFTXYZ / PMFTXYT / PMFTR12 ----------------------------------------------------------------------------------
+namespace {
+
+// (cos, sin)(-theta) of every query point with the host libm, spread over the host threads (see fgpu_pmftxy)
+std::vector<float> host_cos_sin(const float* theta, uint32_t n)
+{
+    std::vector<float> cs(2 * (size_t) n);
+    auto fill = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i)
+        {
+            float const t = -theta[i];
+            cs[2 * (size_t) i] = std::cos(t);
+            cs[2 * (size_t) i + 1] = std::sin(t);
+        }
+    };
+    unsigned const hw = std::max(1U, std::min(32U, std::thread::hardware_concurrency()));
+    unsigned const n_threads = n >= 65536 ? hw : 1U;
+    if (n_threads == 1)
+    {
+        fill(0, n);
+        return cs;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_threads; ++t)
+    {
+        pool.emplace_back(fill, (uint32_t) ((uint64_t) n * t / n_threads), (uint32_t) ((uint64_t) n * (t + 1) / n_threads));
+    }
+    for (auto& th : pool)
+    {
+        th.join();
+    }
+    return cs;
+}
+
+// RegularAxis::bin (Histogram.h:152-173) on the host; -1 = outside
+int host_axis_bin(const AxisDev& a, float value)
+{
+    if (!(value >= a.r_min) || value >= a.r_max)
+    {
+        return -1;
+    }
+    volatile float d = value - a.r_min;
+    volatile float val = d * a.inv_width;
+    int bin = (int) val;
+    return (uint32_t) bin == a.bins ? bin - 1 : bin;
+}
+
+float host_mod_two_pi(float a) // util::modulusPositive(a, TWO_PI), utils.h:29-32
+{
+    float const two_pi = (float) (2.0 * M_PI); // Box.h:24
+    volatile float inner = std::fmod(a, two_pi) + two_pi;
+    return std::fmod(inner, two_pi);
+}
+
+constexpr uint64_t kPmftChunk = 1ULL << 24; // bonds per launch: bounds the list of host-binned bonds (20 B each)
+
+} // namespace
+
+int fgpu_pmft_create(fgpu_ctx* ctx, int kind, float max0, float max1, float max2, uint32_t n0, uint32_t n1, uint32_t n2,
+                     fgpu_pmft** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        require(kind == FGPU_PMFT_XYZ || kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_R12, FGPU_EINVALID, "unknown PMFT kind");
+        float const two_pi = (float) (2.0 * M_PI);
+        std::unique_ptr<fgpu_pmft> p(new fgpu_pmft());
+        p->ctx = ctx;
+        p->kind = kind;
+        if (kind == FGPU_PMFT_XYZ) // PMFTXYZ.cc:27-50
+        {
+            require(n0 >= 1, FGPU_EINVALID, "PMFTXYZ requires at least 1 bin in X.");
+            require(n1 >= 1, FGPU_EINVALID, "PMFTXYZ requires at least 1 bin in Y.");
+            require(n2 >= 1, FGPU_EINVALID, "PMFTXYZ requires at least 1 bin in Z.");
+            require(!(max0 < 0), FGPU_EINVALID, "PMFTXYZ requires that x_max must be positive.");
+            require(!(max1 < 0), FGPU_EINVALID, "PMFTXYZ requires that y_max must be positive.");
+            require(!(max2 < 0), FGPU_EINVALID, "PMFTXYZ requires that z_max must be positive.");
+            p->a0 = regular_axis(n0, -max0, max0);
+            p->a1 = regular_axis(n1, -max1, max1);
+            p->a2 = regular_axis(n2, -max2, max2);
+        }
+        else if (kind == FGPU_PMFT_XYT) // PMFTXYT.cc:30-49
+        {
+            require(n0 >= 1, FGPU_EINVALID, "PMFTXYT requires at least 1 bin in X.");
+            require(n1 >= 1, FGPU_EINVALID, "PMFTXYT requires at least 1 bin in Y.");
+            require(n2 >= 1, FGPU_EINVALID, "PMFTXYT requires at least 1 bin in T.");
+            require(!(max0 < 0), FGPU_EINVALID, "PMFTXYT requires that x_max must be positive.");
+            require(!(max1 < 0), FGPU_EINVALID, "PMFTXYT requires that y_max must be positive.");
+            p->a0 = regular_axis(n0, -max0, max0);
+            p->a1 = regular_axis(n1, -max1, max1);
+            p->a2 = regular_axis(n2, 0.0f, two_pi);
+        }
+        else // PMFTR12.cc:30-45
+        {
+            require(n0 >= 1, FGPU_EINVALID, "PMFTR12 requires at least 1 bin in R.");
+            require(n1 >= 1, FGPU_EINVALID, "PMFTR12 requires at least 1 bin in T1.");
+            require(n2 >= 1, FGPU_EINVALID, "PMFTR12 requires at least 1 bin in T2.");
+            require(!(max0 < 0), FGPU_EINVALID, "PMFTR12 requires that r_max must be positive.");
+            p->a0 = regular_axis(n0, 0.0f, max0);
+            p->a1 = regular_axis(n1, 0.0f, two_pi);
+            p->a2 = regular_axis(n2, 0.0f, two_pi);
+        }
+        uint64_t const n_bins = (uint64_t) n0 * n1 * n2;
+        require(n_bins < (1ULL << 31), FGPU_EINVALID, "PMFT histogram too large");
+        bind_device(ctx);
+        p->hist.reserve((size_t) n_bins);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(p->hist.ptr, 0, (size_t) n_bins * sizeof(uint32_t), ctx->stream));
+        sync(ctx);
+        *out = p.release();
+    });
+}
+
+void fgpu_pmft_destroy(fgpu_pmft* pmft)
+{
+    if (pmft != nullptr)
+    {
+        bind_quiet(pmft->ctx);
+        delete pmft;
+    }
+}
+
+int fgpu_pmft_reset(fgpu_pmft* pmft)
+{
+    return guarded([&] {
+        require(pmft != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(pmft->ctx);
+        size_t const n_bins = (size_t) pmft->a0.bins * pmft->a1.bins * pmft->a2.bins;
+        FGPU_CUDA_CHECK(cudaMemsetAsync(pmft->hist.ptr, 0, n_bins * sizeof(uint32_t), pmft->ctx->stream));
+        pmft->deferred_total = 0;
+    });
+}
+
+int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const float* orientations_host, uint32_t n_points,
+                               const float* query_orientations_host, const float* equiv_orientations_host,
+                               uint32_t n_equiv)
+{
+    return guarded([&] {
+        require(pmft != nullptr && nl != nullptr && query_orientations_host != nullptr, FGPU_EINVALID, "null argument");
+        require(pmft->ctx == nl->ctx, FGPU_EINVALID, "pmft and nlist belong to different contexts");
+        fgpu_ctx* ctx = pmft->ctx;
+        int const kind = pmft->kind;
+        bind_device(ctx);
+        Pmft3Args a {};
+        a.a0 = pmft->a0;
+        a.a1 = pmft->a1;
+        a.a2 = pmft->a2;
+        a.hist = pmft->hist.ptr;
+        std::vector<float> cs;
+        if (kind == FGPU_PMFT_XYZ)
+        {
+            require(equiv_orientations_host != nullptr && n_equiv >= 1, FGPU_EINVALID,
+                    "PMFTXYZ needs at least one equivalent orientation");
+            pmft->stage_a.reserve(4 * (size_t) nl->n_query + 4);
+            pmft->stage_b.reserve(4 * (size_t) n_equiv);
+            h2d(ctx, pmft->stage_a.ptr, query_orientations_host, 4 * (size_t) nl->n_query * sizeof(float));
+            h2d(ctx, pmft->stage_b.ptr, equiv_orientations_host, 4 * (size_t) n_equiv * sizeof(float));
+            a.query_quats = reinterpret_cast<const float4*>(pmft->stage_a.ptr);
+            a.equiv_quats = reinterpret_cast<const float4*>(pmft->stage_b.ptr);
+            a.n_equiv = n_equiv;
+        }
+        else
+        {
+            require(orientations_host != nullptr, FGPU_EINVALID, "null orientations");
+            pmft->stage_b.reserve((size_t) n_points + 1);
+            h2d(ctx, pmft->stage_b.ptr, orientations_host, (size_t) n_points * sizeof(float));
+            a.orientations = pmft->stage_b.ptr;
+            if (kind == FGPU_PMFT_XYT)
+            {
+                cs = host_cos_sin(query_orientations_host, nl->n_query); // rotmat2::fromAngle, VectorMath.h:912-921
+                pmft->stage_a.reserve(2 * (size_t) nl->n_query + 2);
+                h2d(ctx, pmft->stage_a.ptr, cs.data(), cs.size() * sizeof(float));
+                a.cos_sin = reinterpret_cast<const float2*>(pmft->stage_a.ptr);
+            }
+            else
+            {
+                pmft->stage_a.reserve((size_t) nl->n_query + 1);
+                h2d(ctx, pmft->stage_a.ptr, query_orientations_host, (size_t) nl->n_query * sizeof(float));
+                a.query_orientations = pmft->stage_a.ptr;
+            }
+        }
+        std::vector<uint4> rec;
+        std::vector<float> rec_dist;
+        std::vector<uint32_t> bins;
+        for (uint64_t b0 = 0; b0 < nl->n_bonds; b0 += kPmftChunk)
+        {
+            uint64_t const nb = std::min<uint64_t>(kPmftChunk, nl->n_bonds - b0);
+            a.neighbors = nl->neighbors.ptr + 2 * b0;
+            a.vectors = nl->vectors.ptr + 3 * b0;
+            a.distances = nl->distances.ptr + b0;
+            a.n_bonds = nb;
+            if (kind != FGPU_PMFT_XYZ)
+            {
+                pmft->deferred.reserve((size_t) nb);
+                if (kind == FGPU_PMFT_R12)
+                {
+                    pmft->deferred_dist.reserve((size_t) nb);
+                }
+                a.deferred = pmft->deferred.ptr;
+                a.deferred_dist = pmft->deferred_dist.ptr;
+                a.deferred_cap = (uint32_t) nb;
+                a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
+                FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
+            }
+            launch_pmft3(ctx, kind, a);
+            if (kind == FGPU_PMFT_XYZ)
+            {
+                continue;
+            }
+            d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
+            sync(ctx);
+            uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
+            if (n_def == 0)
+            {
+                continue;
+            }
+            // the bonds whose angle sits within a few ulps of a bin edge: the reference's own libm decides
+            rec.resize(n_def);
+            d2h(ctx, rec.data(), pmft->deferred.ptr, (size_t) n_def * sizeof(uint4));
+            if (kind == FGPU_PMFT_R12)
+            {
+                rec_dist.resize(n_def);
+                d2h(ctx, rec_dist.data(), pmft->deferred_dist.ptr, (size_t) n_def * sizeof(float));
+            }
+            sync(ctx);
+            bins.clear();
+            for (uint32_t r = 0; r < n_def; ++r)
+            {
+                uint32_t const i = rec[r].x, j = rec[r].y;
+                float vx, vy;
+                std::memcpy(&vx, &rec[r].z, sizeof(float));
+                std::memcpy(&vy, &rec[r].w, sizeof(float));
+                int c0, c1, c2;
+                if (kind == FGPU_PMFT_XYT)
+                {
+                    float const c = cs[2 * (size_t) i], sn = cs[2 * (size_t) i + 1];
+                    volatile float x1 = c * vx, x2 = -sn * vy, y1 = sn * vx, y2 = c * vy;
+                    c0 = host_axis_bin(a.a0, x1 + x2);
+                    c1 = host_axis_bin(a.a1, y1 + y2);
+                    float const d_theta = std::atan2(-vy, -vx); // PMFTXYT.cc:94
+                    c2 = host_axis_bin(a.a2, host_mod_two_pi(orientations_host[j] - d_theta));
+                }
+                else
+                {
+                    c0 = host_axis_bin(a.a0, rec_dist[r]);
+                    float const d_theta1 = std::atan2(vy, vx), d_theta2 = std::atan2(-vy, -vx); // PMFTR12.cc:103-104
+                    c1 = host_axis_bin(a.a1, host_mod_two_pi(orientations_host[j] - d_theta1));
+                    c2 = host_axis_bin(a.a2, host_mod_two_pi(query_orientations_host[i] - d_theta2));
+                }
+                if (c0 >= 0 && c1 >= 0 && c2 >= 0)
+                {
+                    bins.push_back(((uint32_t) c0 * a.a1.bins + (uint32_t) c1) * a.a2.bins + (uint32_t) c2);
+                }
+            }
+            pmft->deferred_total += n_def;
+            if (!bins.empty())
+            {
+                pmft->host_bins.reserve(bins.size());
+                h2d(ctx, pmft->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
+                launch_add_bins(ctx, pmft->host_bins.ptr, (uint32_t) bins.size(), pmft->hist.ptr);
+                sync(ctx); // `bins` is reused by the next chunk
+            }
+        }
+        sync(ctx); // the caller's arrays were consumed
+    });
+}
+
+int fgpu_pmft_read(fgpu_pmft* pmft, uint32_t* counts_host)
+{
+    return guarded([&] {
+        require(pmft != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(pmft->ctx);
+        size_t const n_bins = (size_t) pmft->a0.bins * pmft->a1.bins * pmft->a2.bins;
+        d2h(pmft->ctx, counts_host, pmft->hist.ptr, n_bins * sizeof(uint32_t));
+        sync(pmft->ctx);
+    });
+}
+
+int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds)
+{
+    return guarded([&] {
+        require(pmft != nullptr && bonds != nullptr, FGPU_EINVALID, "null argument");
+        *bonds = pmft->deferred_total;
+    });
+}
+
 int fgpu_corr_create(fgpu_ctx* ctx, uint32_t bins, float r_max, fgpu_corr** out)
 {
     return guarded([&] {

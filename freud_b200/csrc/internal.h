@@ -204,6 +204,20 @@ struct fgpu_pmftxy
     fgpu::DevBuf<float> cos_sin;  // staged per call: (cos, sin)(-theta) per query point
 };
 
+struct fgpu_pmft
+{
+    fgpu_ctx* ctx = nullptr;
+    int kind = 0; // FGPU_PMFT_*
+    fgpu::AxisDev a0, a1, a2;
+    fgpu::DevBuf<uint32_t> hist;      // n0 * n1 * n2, row-major (axis 0 slow)
+    fgpu::DevBuf<float> stage_a;      // staged per call: XYT (cos, sin)(-theta_i) | R12 theta_i | XYZ query quaternions
+    fgpu::DevBuf<float> stage_b;      // staged per call: theta_j of the points | XYZ equivalent orientations
+    fgpu::DevBuf<uint4> deferred;     // bonds whose angle bin is left to the host's libm: (i, j, bits vx, bits vy)
+    fgpu::DevBuf<float> deferred_dist;
+    fgpu::DevBuf<uint32_t> host_bins; // ... and the bins the host found for them
+    uint64_t deferred_total = 0;      // statistics: bonds the host binned since the last reset
+};
+
 struct fgpu_corr
 {
     fgpu_ctx* ctx = nullptr;
@@ -460,6 +474,28 @@ void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs&
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
 void launch_pmftxy(fgpu_ctx* ctx, const uint32_t* neighbors, const float* vectors, uint64_t n_bonds, const float* cos_sin,
                    AxisDev ax, AxisDev ay, uint32_t* hist);
+struct Pmft3Args
+{
+    AxisDev a0, a1, a2;
+    const uint32_t* neighbors;
+    const float* vectors;
+    const float* distances;
+    uint64_t n_bonds;
+    const float2* cos_sin;           // XYT: per query point
+    const float* orientations;       // XYT, R12: per point
+    const float* query_orientations; // R12: per query point
+    const float4* query_quats;       // XYZ: per query point, (s, x, y, z)
+    const float4* equiv_quats;       // XYZ
+    uint32_t n_equiv;
+    uint32_t* hist;
+    uint4* deferred;
+    float* deferred_dist;
+    uint32_t deferred_cap;
+    uint32_t* deferred_count;
+    int use_shared;
+};
+void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a);
+void launch_add_bins(fgpu_ctx* ctx, const uint32_t* bins, uint32_t n, uint32_t* hist);
 void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
                         const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums);
 void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,

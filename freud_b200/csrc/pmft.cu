@@ -1,0 +1,211 @@
+// Three-axis PMFT histograms over the bonds of a device NeighborList: freud::pmft::PMFTXYZ, PMFTXYT and PMFTR12
+// (freud/pmft/PMFTXYZ.cc:111-147, PMFTXYT.cc:77-101, PMFTR12.cc:91-113).  One thread per bond, u32 bin counts in a
+// block-shared histogram when it fits and in global memory otherwise, linear index (b0 * n1 + b1) * n2 + b2
+// (Histogram.h:327-351).
+//
+//   XYZ  the bond vector rotated by conj(q_i) and then by every equivalent orientation, all in the reference's float
+//        operation order (VectorMath.h:810-818) -> three RegularAxis bins.  Pure float arithmetic: bit-exact counts.
+//   XYT  (x, y) rotated by -theta_i with the host libm's (cos, sin) as in PMFTXY, and the angle
+//        t = modulusPositive(theta_j - atan2f(-dy, -dx), 2 pi).
+//   R12  r = bond distance, t1 = modulusPositive(theta_j - atan2f(dy, dx), 2 pi),
+//        t2 = modulusPositive(theta_i - atan2f(-dy, -dx), 2 pi).
+//
+// atan2f is the host libm's in the reference and CUDA's differs from it in the last place.  The angle bin only
+// depends on that last place when t lies within a few float ulps of a bin edge, so the kernel evaluates atan2 in
+// double, follows the reference's float chain from the rounded value, and accepts the bin only if t is farther from
+// every bin edge than any last-place difference can move it (kAngleMargin, several times libm's error bound plus
+// the rounding of the chain).  The few bonds inside a margin (~3 in 10^4) are written to a list and binned by the
+// host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per bond.
+#include "internal.h"
+#include "pair_math.cuh"
+
+namespace fgpu {
+
+namespace {
+
+constexpr float kTwoPi = 6.28318548202514648f; // (float) (2.0 * M_PI), Box.h:24
+constexpr float kAngleMargin = 1.0e-5f;        // >> 3 ulp of atan2f at pi (7e-7) + the chain's roundings (1e-6)
+
+// util::modulusPositive(a, 2 pi), utils.h:29-32 (fmodf is exact on both sides)
+__device__ __forceinline__ float mod_two_pi(float a)
+{
+    return fmodf(__fadd_rn(fmodf(a, kTwoPi), kTwoPi), kTwoPi);
+}
+
+// Bin of t = modulusPositive(orientation - atan2f(y, x), 2 pi) on `axis` = RegularAxis(n, 0, 2 pi); *sure = false if a
+// last-place difference in atan2f could change it.
+__device__ __forceinline__ int angle_bin(const AxisDev& axis, float orientation, float y, float x, bool* sure)
+{
+    float const d = (float) atan2((double) y, (double) x);
+    float const t = mod_two_pi(__fsub_rn(orientation, d));
+    float const u = __fmul_rn(t, axis.inv_width);
+    float const frac = u - floorf(u);
+    float const margin = kAngleMargin * axis.inv_width + 1.0e-6f * (u + 1.0f);
+    // near 0 or 2 pi the wrap of the modulus sits on a bin edge too; a NaN orientation is never sure
+    *sure = frac > margin && frac < 1.0f - margin && t > kAngleMargin && t < kTwoPi - kAngleMargin;
+    return axis_bin(axis, t);
+}
+
+// rotate(q, v), VectorMath.h:810-818: (s^2 - v.v) b + (2 s) (v x b) + (2 v.b) v, one rounding per operation
+__device__ __forceinline__ void quat_rotate(float s, float qx, float qy, float qz, float& x, float& y, float& z)
+{
+    float const vv = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+    float const a = __fsub_rn(__fmul_rn(s, s), vv);
+    float const two_s = __fmul_rn(2.0f, s);
+    float const cx = __fsub_rn(__fmul_rn(qy, z), __fmul_rn(qz, y));
+    float const cy = __fsub_rn(__fmul_rn(qz, x), __fmul_rn(qx, z));
+    float const cz = __fsub_rn(__fmul_rn(qx, y), __fmul_rn(qy, x));
+    float const vb = __fadd_rn(__fadd_rn(__fmul_rn(qx, x), __fmul_rn(qy, y)), __fmul_rn(qz, z));
+    float const two_vb = __fmul_rn(2.0f, vb);
+    float const ox = __fadd_rn(__fadd_rn(__fmul_rn(x, a), __fmul_rn(cx, two_s)), __fmul_rn(qx, two_vb));
+    float const oy = __fadd_rn(__fadd_rn(__fmul_rn(y, a), __fmul_rn(cy, two_s)), __fmul_rn(qy, two_vb));
+    float const oz = __fadd_rn(__fadd_rn(__fmul_rn(z, a), __fmul_rn(cz, two_s)), __fmul_rn(qz, two_vb));
+    x = ox;
+    y = oy;
+    z = oz;
+}
+
+template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
+{
+    extern __shared__ uint32_t p3_hist[];
+    uint32_t const n_bins = a.a0.bins * a.a1.bins * a.a2.bins;
+    if (a.use_shared)
+    {
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+        {
+            p3_hist[b] = 0;
+        }
+        __syncthreads();
+    }
+    uint32_t* const h = a.use_shared ? p3_hist : a.hist;
+    auto count = [&](int b0, int b1, int b2) {
+        if (b0 >= 0 && b1 >= 0 && b2 >= 0)
+        {
+            atomicAdd(&h[((uint32_t) b0 * a.a1.bins + (uint32_t) b1) * a.a2.bins + (uint32_t) b2], 1U);
+        }
+    };
+    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
+    {
+        uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
+        float const vx = a.vectors[3 * k], vy = a.vectors[3 * k + 1];
+        if (KIND == FGPU_PMFT_XYZ)
+        {
+            float4 const q = a.query_quats[ij.x]; // (s, x, y, z); conj: (s, -v), VectorMath.h:765
+            float x = vx, y = vy, z = a.vectors[3 * k + 2];
+            quat_rotate(q.x, -q.y, -q.z, -q.w, x, y, z);
+            for (uint32_t e = 0; e < a.n_equiv; ++e)
+            {
+                float4 const eq = a.equiv_quats[e];
+                float ex = x, ey = y, ez = z;
+                quat_rotate(eq.x, eq.y, eq.z, eq.w, ex, ey, ez);
+                count(axis_bin(a.a0, ex), axis_bin(a.a1, ey), axis_bin(a.a2, ez));
+            }
+            continue;
+        }
+        bool sure = true;
+        int b0, b1, b2;
+        if (KIND == FGPU_PMFT_XYT)
+        {
+            float2 const cs = a.cos_sin[ij.x];
+            float const rx = __fadd_rn(__fmul_rn(cs.x, vx), __fmul_rn(-cs.y, vy)); // rotmat2 * v, VectorMath.h:929-936
+            float const ry = __fadd_rn(__fmul_rn(cs.y, vx), __fmul_rn(cs.x, vy));
+            b0 = axis_bin(a.a0, rx);
+            b1 = axis_bin(a.a1, ry);
+            b2 = angle_bin(a.a2, a.orientations[ij.y], -vy, -vx, &sure);
+        }
+        else
+        {
+            bool sure1 = true, sure2 = true;
+            b0 = axis_bin(a.a0, a.distances[k]);
+            b1 = angle_bin(a.a1, a.orientations[ij.y], vy, vx, &sure1);
+            b2 = angle_bin(a.a2, a.query_orientations[ij.x], -vy, -vx, &sure2);
+            sure = sure1 && sure2;
+        }
+        if (b0 < 0 || (KIND == FGPU_PMFT_XYT && b1 < 0))
+        {
+            continue; // outside an axis that does not involve atan2f: dropped whatever the angles are
+        }
+        if (sure)
+        {
+            count(b0, b1, b2);
+        }
+        else
+        {
+            uint32_t const slot = atomicAdd(a.deferred_count, 1U);
+            if (slot < a.deferred_cap)
+            {
+                a.deferred[slot] = make_uint4(ij.x, ij.y, __float_as_uint(vx), __float_as_uint(vy));
+                if (KIND == FGPU_PMFT_R12)
+                {
+                    a.deferred_dist[slot] = a.distances[k];
+                }
+            }
+        }
+    }
+    if (a.use_shared)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+        {
+            if (p3_hist[b] != 0)
+            {
+                atomicAdd(&a.hist[b], p3_hist[b]);
+            }
+        }
+    }
+}
+
+// the host's share: one count per listed bin
+__global__ void __launch_bounds__(256) k_add_bins(const uint32_t* __restrict__ bins, uint32_t n, uint32_t* __restrict__ hist)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        atomicAdd(&hist[bins[i]], 1U);
+    }
+}
+
+} // namespace
+
+void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
+{
+    if (a.n_bonds == 0)
+    {
+        return;
+    }
+    size_t const smem = (size_t) a.a0.bins * a.a1.bins * a.a2.bins * sizeof(uint32_t);
+    a.use_shared = smem <= 40 * 1024 ? 1 : 0;
+    size_t const dyn = a.use_shared ? smem : 0;
+    unsigned const blocks = (unsigned) std::min<uint64_t>((a.n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 8U);
+    {
+        KernelScope ks(ctx, "pmft3");
+        switch (kind)
+        {
+        case FGPU_PMFT_XYZ:
+            k_pmft3<FGPU_PMFT_XYZ><<<blocks, 256, dyn, ctx->stream>>>(a);
+            break;
+        case FGPU_PMFT_XYT:
+            k_pmft3<FGPU_PMFT_XYT><<<blocks, 256, dyn, ctx->stream>>>(a);
+            break;
+        default:
+            k_pmft3<FGPU_PMFT_R12><<<blocks, 256, dyn, ctx->stream>>>(a);
+            break;
+        }
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_add_bins(fgpu_ctx* ctx, const uint32_t* bins, uint32_t n, uint32_t* hist)
+{
+    if (n == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "pmft_add_bins");
+        k_add_bins<<<(n + 255) / 256, 256, 0, ctx->stream>>>(bins, n, hist);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace fgpu

@@ -10,3 +10,14 @@ template<typename T> struct vec3
     vec3(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
 };
 static_assert(sizeof(vec3<float>) == 12, "vec3<float> must alias three packed floats");
+
+// quat<T>: scalar part first, then the vector part -- the 16-byte POD the reference reinterprets (N, 4) float32 arrays
+// as (freud/util/VectorMath.h:588-640).  Layout only, like vec3.
+template<typename T> struct quat
+{
+    T s {1};
+    vec3<T> v;
+    quat() = default;
+    quat(T s_, const vec3<T>& v_) : s(s_), v(v_) {}
+};
+static_assert(sizeof(quat<float>) == 16, "quat<float> must alias four packed floats");

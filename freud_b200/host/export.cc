@@ -307,6 +307,84 @@ PYBIND11_MODULE(_freud_b200, m)
         .def("getBox", &pmft::PMFTXY::getBox)
         .def("reset", &pmft::PMFTXY::reset);
 
+    auto bind_pmft3 = [](auto& cls) {
+        using T = typename std::remove_reference_t<decltype(cls)>::type;
+        cls.def("getPCF", [](T& p) { return to_numpy<float>(p.getPCF()); })
+            .def("getBinCounts", [](T& p) { return to_numpy<unsigned int>(p.getBinCounts()); })
+            .def("getBinEdges", &T::getBinEdges)
+            .def("getBinCenters", &T::getBinCenters)
+            .def("getBounds", &T::getBounds)
+            .def("getAxisSizes", &T::getAxisSizes)
+            .def("getBox", &T::getBox)
+            .def("getHostBinnedBonds", &T::getHostBinnedBonds)
+            .def("reset", &T::reset);
+    };
+    using float_array = py::array_t<float, py::array::c_style | py::array::forcecast>;
+    py::class_<pmft::PMFTXYZ, std::shared_ptr<pmft::PMFTXYZ>> xyz(mpm, "PMFTXYZ");
+    xyz.def(py::init<float, float, float, unsigned int, unsigned int, unsigned int>(), py::arg("x_max"), py::arg("y_max"),
+            py::arg("z_max"), py::arg("n_x"), py::arg("n_y"), py::arg("n_z"))
+        .def("accumulate",
+             [](pmft::PMFTXYZ& p, std::shared_ptr<locality::NeighborQuery> nq, float_array query_orientations,
+                points_array qp, float_array equiv_orientations, std::shared_ptr<locality::NeighborList> nlist,
+                const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 if (query_orientations.ndim() != 2 || query_orientations.shape(1) != 4
+                     || (size_t) query_orientations.shape(0) != n)
+                 {
+                     throw std::invalid_argument("query_orientations must hold one quaternion per query point");
+                 }
+                 if (equiv_orientations.ndim() != 2 || equiv_orientations.shape(1) != 4)
+                 {
+                     throw std::invalid_argument("equiv_orientations must be an (N, 4) array of quaternions");
+                 }
+                 p.accumulate(nq, reinterpret_cast<const quat<float>*>(query_orientations.data()), q, n,
+                              reinterpret_cast<const quat<float>*>(equiv_orientations.data()),
+                              (unsigned int) equiv_orientations.shape(0), nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("query_orientations"), py::arg("query_points"),
+             py::arg("equiv_orientations"), py::arg("nlist").none(true), py::arg("qargs"));
+    bind_pmft3(xyz);
+    auto accumulate_angles = [](auto& p, std::shared_ptr<locality::NeighborQuery> nq, float_array orientations,
+                                points_array qp, float_array query_orientations,
+                                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+        unsigned int n = 0;
+        const vec3<float>* q = as_vec3(qp, n);
+        if ((size_t) orientations.size() != nq->getNPoints())
+        {
+            throw std::invalid_argument("orientations must hold one angle per point");
+        }
+        if ((size_t) query_orientations.size() != n)
+        {
+            throw std::invalid_argument("query_orientations must hold one angle per query point");
+        }
+        p.accumulate(nq, orientations.data(), q, query_orientations.data(), n, nlist, qargs);
+    };
+    py::class_<pmft::PMFTXYT, std::shared_ptr<pmft::PMFTXYT>> xyt(mpm, "PMFTXYT");
+    xyt.def(py::init<float, float, unsigned int, unsigned int, unsigned int>(), py::arg("x_max"), py::arg("y_max"),
+            py::arg("n_x"), py::arg("n_y"), py::arg("n_t"))
+        .def("accumulate",
+             [accumulate_angles](pmft::PMFTXYT& p, std::shared_ptr<locality::NeighborQuery> nq, float_array orientations,
+                                 points_array qp, float_array query_orientations,
+                                 std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 accumulate_angles(p, nq, orientations, qp, query_orientations, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("orientations"), py::arg("query_points"), py::arg("query_orientations"),
+             py::arg("nlist").none(true), py::arg("qargs"));
+    bind_pmft3(xyt);
+    py::class_<pmft::PMFTR12, std::shared_ptr<pmft::PMFTR12>> r12(mpm, "PMFTR12");
+    r12.def(py::init<float, unsigned int, unsigned int, unsigned int>(), py::arg("r_max"), py::arg("n_r"), py::arg("n_t1"),
+            py::arg("n_t2"))
+        .def("accumulate",
+             [accumulate_angles](pmft::PMFTR12& p, std::shared_ptr<locality::NeighborQuery> nq, float_array orientations,
+                                 points_array qp, float_array query_orientations,
+                                 std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 accumulate_angles(p, nq, orientations, qp, query_orientations, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("orientations"), py::arg("query_points"), py::arg("query_orientations"),
+             py::arg("nlist").none(true), py::arg("qargs"));
+    bind_pmft3(r12);
+
     // ---- _order ----------------------------------------------------------------------------------------
     auto mord = m.def_submodule("_order");
     py::class_<order::Steinhardt, std::shared_ptr<order::Steinhardt>>(mord, "Steinhardt")

@@ -49,6 +49,7 @@ typedef struct fgpu_points fgpu_points; /* device-resident reference points + bo
 typedef struct fgpu_nlist fgpu_nlist;   /* device-resident NeighborList (SoA, CSR)            */
 typedef struct fgpu_rdf fgpu_rdf;       /* device-resident RDF histogram accumulator          */
 typedef struct fgpu_pmftxy fgpu_pmftxy; /* device-resident PMFTXY histogram                      */
+typedef struct fgpu_pmft fgpu_pmft;     /* device-resident PMFTXYZ / PMFTXYT / PMFTR12 histogram  */
 typedef struct fgpu_corr fgpu_corr;     /* device-resident CorrelationFunction accumulators  */
 typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
 
@@ -81,7 +82,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, pmftxy, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, pmftxy, pmft3, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -208,6 +209,34 @@ void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft);
 int fgpu_pmftxy_reset(fgpu_pmftxy* pmft);
 int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host);
 int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host);
+
+/* ---- PMFTXYZ, PMFTXYT, PMFTR12 ---------------------------------------------------------------------------
+ * Device half of the three-axis PMFTs: a u32[n0][n1][n2] histogram over the bonds of a NeighborList, resident across
+ * accumulate calls.
+ *   FGPU_PMFT_XYZ  freud/pmft/PMFTXYZ.cc:24-147: axes x, y, z in [-max, max]; the bond vector rotated by
+ *                  conj(query_orientations[i]) and by each of the n_equiv equivalent orientations (one count per
+ *                  orientation); quaternions are (s, x, y, z) float[4]; `orientations` is not read.
+ *   FGPU_PMFT_XYT  freud/pmft/PMFTXYT.cc:28-101: axes x, y in [-max, max] and t in [0, 2 pi); `orientations[n_points]`
+ *                  and `query_orientations[n_query]` are angles in radians; max2 is not read.
+ *   FGPU_PMFT_R12  freud/pmft/PMFTR12.cc:28-113: axes r in [0, max0], t1 and t2 in [0, 2 pi); max1, max2 not read.
+ * Bin counts are bit-identical to the reference's: the float arithmetic runs on the GPU in the reference's operation
+ * order; cos/sin of the query angles (XYT) come from the host libm like fgpu_pmftxy's; the atan2f of the bond angle
+ * (XYT, R12) is bracketed on the GPU and the few bonds whose bin could depend on libm's last place are binned by the
+ * host (freud_b200/csrc/pmft.cu).  fgpu_pmft_deferred reports how many bonds took that route since the last reset.
+ * Errors: a bin count < 1 or a negative maximum -> FGPU_EINVALID with the reference's messages; XYZ with n_equiv = 0
+ * or null quaternions, XYT / R12 with null angles -> FGPU_EINVALID. */
+#define FGPU_PMFT_XYZ 0
+#define FGPU_PMFT_XYT 1
+#define FGPU_PMFT_R12 2
+int fgpu_pmft_create(fgpu_ctx* ctx, int kind, float max0, float max1, float max2, uint32_t n0, uint32_t n1, uint32_t n2,
+                     fgpu_pmft** out);
+void fgpu_pmft_destroy(fgpu_pmft* pmft);
+int fgpu_pmft_reset(fgpu_pmft* pmft);
+int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const float* orientations_host, uint32_t n_points,
+                               const float* query_orientations_host, const float* equiv_orientations_host,
+                               uint32_t n_equiv);
+int fgpu_pmft_read(fgpu_pmft* pmft, uint32_t* counts_host);
+int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds);
 
 /* ---- CorrelationFunction ---------------------------------------------------------------------------------
  * Device half of freud::density::CorrelationFunction (freud/density/CorrelationFunction.cc:26-95): per bin of

@@ -1587,3 +1587,153 @@ int fport_pmftxy(const uint32_t* nl_ij, const float* nl_v, uint64_t n_bonds, con
     }
     return 0;
 }
+
+/* ---- PMFTXYZ / PMFTXYT / PMFTR12 over the bonds of a NeighborList (one frame) ------------------------------------
+ * kind 0 = XYZ (freud/pmft/PMFTXYZ.cc:24-147): v = rotate(equiv[e], rotate(conj(q_i), delta)) for every equivalent
+ *          orientation e (VectorMath.h:765, 810-818), bins on x, y, z in [-max, max]; orientations are quaternions
+ *          (s, x, y, z); reduce divides by n_equiv as well (PMFTXYZ.cc:86-98).
+ * kind 1 = XYT (PMFTXYT.cc:28-101): (x, y) = rotmat2(-theta_i) * delta, t = modulusPositive(theta_j - atan2f(-dy, -dx),
+ *          2 pi); Jacobian dx dy (1 / n_t).
+ * kind 2 = R12 (PMFTR12.cc:28-113): r = bond distance, t1 = modulusPositive(theta_j - atan2f(dy, dx), 2 pi),
+ *          t2 = modulusPositive(theta_i - atan2f(-dy, -dx), 2 pi); inverse Jacobian 1 / (r_centre dr (2 pi / n_t1) (1 / n_t2)).
+ * cosf / sinf / atan2f / fmodf are this machine's libm, as upstream.  Linear bin index (b0 n1 + b1) n2 + b2
+ * (Histogram.h:327-351); PMFT::reduce as in freud/pmft/PMFT.h:73-83. */
+static void quat_rotate(float s, float qx, float qy, float qz, float* x, float* y, float* z)
+{
+    float bx = *x, by = *y, bz = *z;
+    float p1 = qx * qx, p2 = qy * qy, p3 = qz * qz;
+    float vv = (p1 + p2) + p3;
+    float ss = s * s;
+    float a = ss - vv;
+    float two_s = 2.0f * s;
+    float c1 = qy * bz, c2 = qz * by, c3 = qz * bx, c4 = qx * bz, c5 = qx * by, c6 = qy * bx;
+    float cx = c1 - c2, cy = c3 - c4, cz = c5 - c6;
+    float d1 = qx * bx, d2 = qy * by, d3 = qz * bz;
+    float vb = (d1 + d2) + d3;
+    float two_vb = 2.0f * vb;
+    float t1x = bx * a, t2x = cx * two_s, t3x = qx * two_vb;
+    float t1y = by * a, t2y = cy * two_s, t3y = qy * two_vb;
+    float t1z = bz * a, t2z = cz * two_s, t3z = qz * two_vb;
+    *x = (t1x + t2x) + t3x;
+    *y = (t1y + t2y) + t3y;
+    *z = (t1z + t2z) + t3z;
+}
+
+static float mod_two_pi(float a)
+{
+    const float two_pi = (float) (2.0 * M_PI); /* Box.h:24 */
+    float inner = fmodf(a, two_pi) + two_pi;
+    return fmodf(inner, two_pi);
+}
+
+int fport_pmft3(int kind, const uint32_t* nl_ij, const float* nl_v, const float* nl_d, uint64_t n_bonds,
+                const float* orientations, const float* query_orientations, const float* equiv, uint32_t n_equiv,
+                float max0, float max1, float max2, uint32_t n0, uint32_t n1, uint32_t n2, float box_volume,
+                uint32_t n_points, uint32_t n_query, uint32_t* counts, float* pcf)
+{
+    const float two_pi = (float) (2.0 * M_PI);
+    float lo[3], hi[3], inv[3], width[3];
+    uint32_t n[3] = {n0, n1, n2};
+    float mx[3] = {max0, max1, max2};
+    for (int ax = 0; ax < 3; ++ax)
+    {
+        int const angle = (kind == 1 && ax == 2) || (kind == 2 && ax > 0);
+        lo[ax] = angle || kind == 2 ? 0.0f : -mx[ax];
+        hi[ax] = angle ? two_pi : mx[ax];
+        axis_params(n[ax], lo[ax], hi[ax], &width[ax], &inv[ax]);
+    }
+    size_t const n_bins = (size_t) n0 * n1 * n2;
+    memset(counts, 0, n_bins * sizeof(uint32_t));
+    for (uint64_t k = 0; k < n_bonds; ++k)
+    {
+        uint32_t const i = nl_ij[2 * k], j = nl_ij[2 * k + 1];
+        float const dx = nl_v[3 * k], dy = nl_v[3 * k + 1], dz = nl_v[3 * k + 2];
+        if (kind == 0)
+        {
+            const float* q = query_orientations + 4 * (size_t) i;
+            float x = dx, y = dy, z = dz;
+            quat_rotate(q[0], -q[1], -q[2], -q[3], &x, &y, &z);
+            for (uint32_t e = 0; e < n_equiv; ++e)
+            {
+                float ex = x, ey = y, ez = z;
+                quat_rotate(equiv[4 * e], equiv[4 * e + 1], equiv[4 * e + 2], equiv[4 * e + 3], &ex, &ey, &ez);
+                int64_t b0 = axis_bin(ex, lo[0], hi[0], inv[0], n0), b1 = axis_bin(ey, lo[1], hi[1], inv[1], n1),
+                        b2 = axis_bin(ez, lo[2], hi[2], inv[2], n2);
+                if (b0 >= 0 && b1 >= 0 && b2 >= 0)
+                {
+                    counts[((size_t) b0 * n1 + (size_t) b1) * n2 + (size_t) b2] += 1;
+                }
+            }
+            continue;
+        }
+        int64_t b0, b1, b2;
+        if (kind == 1)
+        {
+            float t = -query_orientations[i];
+            float c = cosf(t), sn = sinf(t), ms = -sn;
+            float a1 = c * dx, a2 = ms * dy, g1 = sn * dx, g2 = c * dy;
+            float rx = a1 + a2, ry = g1 + g2;
+            float d_theta = atan2f(-dy, -dx);
+            float arg = orientations[j] - d_theta;
+            b0 = axis_bin(rx, lo[0], hi[0], inv[0], n0);
+            b1 = axis_bin(ry, lo[1], hi[1], inv[1], n1);
+            b2 = axis_bin(mod_two_pi(arg), lo[2], hi[2], inv[2], n2);
+        }
+        else
+        {
+            float d_theta1 = atan2f(dy, dx), d_theta2 = atan2f(-dy, -dx);
+            float arg1 = orientations[j] - d_theta1, arg2 = query_orientations[i] - d_theta2;
+            b0 = axis_bin(nl_d[k], lo[0], hi[0], inv[0], n0);
+            b1 = axis_bin(mod_two_pi(arg1), lo[1], hi[1], inv[1], n1);
+            b2 = axis_bin(mod_two_pi(arg2), lo[2], hi[2], inv[2], n2);
+        }
+        if (b0 >= 0 && b1 >= 0 && b2 >= 0)
+        {
+            counts[((size_t) b0 * n1 + (size_t) b1) * n2 + (size_t) b2] += 1;
+        }
+    }
+    float inv_num_dens = box_volume / (float) n_query;
+    float den = 1.0f * (float) n_points; /* one frame */
+    if (kind == 0)
+    {
+        den = den * (float) n_equiv;
+    }
+    float norm_factor = 1.0f / den;
+    float prefactor = inv_num_dens * norm_factor;
+    float jf = 0.0f;
+    if (kind == 0)
+    {
+        float ddx = 2.0f * max0 / (float) n0, ddy = 2.0f * max1 / (float) n1, ddz = 2.0f * max2 / (float) n2;
+        float jac = ddx * ddy;
+        jac = jac * ddz;
+        jf = 1.0f / jac;
+    }
+    else if (kind == 1)
+    {
+        float ddx = 2.0f * max0 / (float) n0, ddy = 2.0f * max1 / (float) n1, dt = 1 / (float) n2;
+        float jac = ddx * ddy;
+        jac = jac * dt;
+        jf = 1.0f / jac;
+    }
+    float dr = max0 / (float) n0, dt1 = two_pi / (float) n1, dt2 = 1 / (float) n2;
+    float product = dr * dt1;
+    product = product * dt2;
+    for (size_t b = 0; b < n_bins; ++b)
+    {
+        float f = jf;
+        if (kind == 2)
+        {
+            size_t const ir = b / ((size_t) n1 * n2);
+            float w = (float) ir * width[0], w1 = (float) (ir + 1) * width[0];
+            float e0 = lo[0] + w, e1 = lo[0] + w1; /* RegularAxis edges, Histogram.h:133-137 */
+            float sum = e0 + e1;
+            float r = sum / 2.0f;
+            float rp = r * product;
+            f = 1.0f / rp;
+        }
+        float t = (float) counts[b] * prefactor;
+        pcf[b] = t * f;
+    }
+    return 0;
+}
+

@@ -158,6 +158,29 @@ def pmftxy(box, n_points, nlist, query_orientations, x_max, y_max, n_x, n_y):
     return counts, pcf
 
 
+PMFT_XYZ, PMFT_XYT, PMFT_R12 = 0, 1, 2
+
+
+def pmft3(kind, box, n_points, nlist, orientations, query_orientations, maxes, bins, equiv=None):
+    """(bin_counts u32[bins], pcf f32[bins]) of PMFTXYZ / PMFTXYT / PMFTR12 over the bonds of an oracle NeighborList (one
+    frame); argument meaning as oracle.ref.pmft3."""
+    ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)
+    v, d = _f32(nlist.vectors, 3), _f32(nlist.distances)
+    width = 4 if kind == PMFT_XYZ else None
+    o = _f32(orientations, width) if orientations is not None else np.zeros(1, np.float32)
+    qo = _f32(query_orientations, width)
+    eq = _f32(equiv, 4) if equiv is not None else np.zeros((1, 4), np.float32)
+    mx = list(maxes) + [0.0] * (3 - len(maxes))
+    counts, pcf = np.zeros(bins, np.uint32), np.zeros(bins, np.float32)
+    L = lib()
+    L.fport_pmft3.argtypes = [C.c_int, _up, _fp, _fp, C.c_uint64, _fp, _fp, _fp, C.c_uint32, C.c_float, C.c_float,
+                              C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, _up, _fp]
+    L.fport_pmft3(int(kind), _p(ij, _up), _p(v), _p(d), len(d), _p(o), _p(qo), _p(eq), len(eq) if equiv is not None else 0,
+                  float(mx[0]), float(mx[1]), float(mx[2]), int(bins[0]), int(bins[1]), int(bins[2]),
+                  float(np.float32(box.volume)), int(n_points), len(qo), _p(counts, _up), _p(pcf))
+    return counts, pcf
+
+
 def correlation_function(nlist, values, query_values, bins, r_max):
     """(correlation complex128[bins], bin_counts) of CorrelationFunction over the bonds of an oracle NeighborList."""
     ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)

@@ -223,6 +223,33 @@ def pmftxy(query, query_orientations, query_points, x_max, y_max, n_x, n_y, nlis
     return counts, pcf
 
 
+PMFT_XYZ, PMFT_XYT, PMFT_R12 = 0, 1, 2
+
+
+def pmft3(kind, query, orientations, query_orientations, query_points, maxes, bins, equiv=None, nlist=None, r_max=None,
+          exclude_ii=False):
+    """PMFTXYZ / PMFTXYT / PMFTR12 of the reference, one compute: (bin_counts u32[bins], pcf f32[bins]).  ``maxes`` =
+    (x_max, y_max, z_max) | (x_max, y_max) | (r_max,); orientations are (N, 4) quaternions for XYZ, angles otherwise.
+    Without a NeighborList it queries a ball of r_max (default: the norm of ``maxes``, freud/pmft.py)."""
+    q = _f32(query_points, 3)
+    width = 4 if kind == PMFT_XYZ else None
+    o = _f32(orientations, width) if orientations is not None else np.zeros(1, np.float32)
+    qo = _f32(query_orientations, width)
+    eq = _f32(equiv, 4) if equiv is not None else np.zeros((1, 4), np.float32)
+    mx = list(maxes) + [0.0] * (3 - len(maxes))
+    counts, pcf = np.zeros(bins, np.uint32), np.zeros(bins, np.float32)
+    L = lib()
+    L.fref_pmft3.argtypes = [C.c_int, C.c_void_p, _fp, _fp, _fp, C.c_uint, _fp, C.c_uint, C.c_void_p, C.c_float, C.c_float,
+                             C.c_float, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_int, _up, _fp]
+    if r_max is None:
+        r_max = float(np.sqrt(sum(m * m for m in maxes)))
+    if L.fref_pmft3(int(kind), query._h, _p(o), _p(qo), _p(q), len(q), _p(eq), len(eq) if equiv is not None else 0,
+                    nlist._h if nlist is not None else None, float(mx[0]), float(mx[1]), float(mx[2]), int(bins[0]),
+                    int(bins[1]), int(bins[2]), float(r_max), int(bool(exclude_ii)), _p(counts, _up), _p(pcf)):
+        _raise()
+    return counts, pcf
+
+
 def correlation_function(query, values, query_points, query_values, bins, r_max, nlist=None, exclude_ii=False):
     """CorrelationFunction(bins, r_max).compute(...) of the reference: (correlation complex128[bins], bin_counts)."""
     q = _f32(query_points, 3)

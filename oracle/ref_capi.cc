@@ -13,6 +13,7 @@
 //   freud::density::LocalDensity                     freud/density/LocalDensity.h:29
 //   freud::density::CorrelationFunction              freud/density/CorrelationFunction.h:52
 //   freud::pmft::PMFTXY                              freud/pmft/PMFTXY.h
+//   freud::pmft::PMFTXYZ, PMFTXYT, PMFTR12           freud/pmft/PMFTXYZ.h, PMFTXYT.h, PMFTR12.h
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
 //   freud::locality::PeriodicBuffer                  freud/locality/PeriodicBuffer.h:22
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
@@ -32,7 +33,10 @@
 #include "LocalDensity.h"
 #include "NeighborList.h"
 #include "NeighborQuery.h"
+#include "PMFTR12.h"
 #include "PMFTXY.h"
+#include "PMFTXYT.h"
+#include "PMFTXYZ.h"
 #include "PeriodicBuffer.h"
 #include "RDF.h"
 #include "RawPoints.h"
@@ -351,6 +355,50 @@ int fref_pmftxy(void* nq, const float* query_orientations, const float* qpts, un
         p.accumulate(h->nq, query_orientations, reinterpret_cast<const vec3<float>*>(qpts), n_query, nl, args);
         std::memcpy(bin_counts, p.getBinCounts()->data(), size_t(n_x) * n_y * sizeof(unsigned));
         std::memcpy(pcf, p.getPCF()->data(), size_t(n_x) * n_y * sizeof(float));
+    });
+}
+
+// ---- PMFTXYZ (kind 0), PMFTXYT (1), PMFTR12 (2) -----------------------------------------------------
+// One accumulate of a fresh object; outputs: bin counts u32[n0 * n1 * n2], pcf f32[n0 * n1 * n2].  Orientations are
+// quaternions (s, x, y, z) for XYZ (`orientations` unused, `equiv` = n_equiv quaternions) and angles otherwise.
+int fref_pmft3(int kind, void* nq, const float* orientations, const float* query_orientations, const float* qpts,
+               unsigned n_query, const float* equiv, unsigned n_equiv, void* nlist_or_null, float max0, float max1,
+               float max2, unsigned n0, unsigned n1, unsigned n2, float r_max, int exclude_ii, unsigned* bin_counts,
+               float* pcf)
+{
+    return guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        std::shared_ptr<NeighborList> nl;
+        if (nlist_or_null != nullptr)
+        {
+            nl = *static_cast<std::shared_ptr<NeighborList>*>(nlist_or_null);
+        }
+        QueryArgs const args = makeArgs(/*ball*/ 1, 0xffffffffU, r_max, 0.0F, -1.0F, -1.0F, exclude_ii);
+        auto const* qp = reinterpret_cast<const vec3<float>*>(qpts);
+        size_t const n_bins = size_t(n0) * n1 * n2;
+        auto copy_out = [&](auto& p) {
+            std::memcpy(bin_counts, p.getBinCounts()->data(), n_bins * sizeof(unsigned));
+            std::memcpy(pcf, p.getPCF()->data(), n_bins * sizeof(float));
+        };
+        if (kind == 0)
+        {
+            freud::pmft::PMFTXYZ p(max0, max1, max2, n0, n1, n2);
+            p.accumulate(h->nq, reinterpret_cast<const quat<float>*>(query_orientations), qp, n_query,
+                         reinterpret_cast<const quat<float>*>(equiv), n_equiv, nl, args);
+            copy_out(p);
+        }
+        else if (kind == 1)
+        {
+            freud::pmft::PMFTXYT p(max0, max1, n0, n1, n2);
+            p.accumulate(h->nq, orientations, qp, query_orientations, n_query, nl, args);
+            copy_out(p);
+        }
+        else
+        {
+            freud::pmft::PMFTR12 p(max0, n0, n1, n2);
+            p.accumulate(h->nq, orientations, qp, query_orientations, n_query, nl, args);
+            copy_out(p);
+        }
     });
 }
 

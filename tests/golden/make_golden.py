@@ -91,6 +91,7 @@ def main():
     correlation_function()
     pmftxy()
     periodic_buffer()
+    pmft3()
 
 
 STEINHARDT_OPTIONS = {
@@ -178,6 +179,58 @@ def pmftxy():
         out[f"{name}_self_counts"], out[f"{name}_self_pcf"] = ref.pmftxy(Q, th_p, pts, 3.0, 2.5, 30, 24, exclude_ii=True)
     np.savez_compressed(os.path.join(HERE, "pmftxy.npz"), **out)
     print("pmftxy", int(out["sq2d_query_counts"].sum()), out["sq2d_query_pcf"][15, 10:13])
+
+
+def pmft3_quats(n, seed):
+    """Seeded unit quaternions (regenerated by the tests)."""
+    q = np.random.RandomState(seed).normal(size=(n, 4))
+    return (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+
+
+# the 4 proper rotations of a rectangular prism about its axes (w, x, y, z)
+PMFT3_EQUIV = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+
+def pmft3_lattice():
+    """A 12 x 12 square lattice (spacing 1.25) with orientations on multiples of pi / 4: every bond angle sits on a bin
+    edge of an 8-bin angular axis, where the bin depends on the last place of libm's atan2f."""
+    g = (np.arange(12) - 5.5) * 1.25
+    pts = np.stack([np.repeat(g, 12), np.tile(g, 12), np.zeros(144)], axis=1).astype(np.float32)
+    return Box.square(15), pts, (np.arange(144) % 8 * (np.pi / 4)).astype(np.float32)
+
+
+def pmft3():
+    """PMFTXYZ (PMFTXYZ.cc:24-147) in a triclinic box; PMFTXYT (PMFTXYT.cc:28-101) and PMFTR12 (PMFTR12.cc:28-113) in a
+    square box, a tilted 2-D box and on a square lattice whose bond angles all sit on bin edges."""
+    out = {}
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 1500, 31), random_points(box, 400, 32)
+    Q = ref.Query("aabb", box, pts)
+    mx, bins = (2.0, 2.5, 3.0), (12, 10, 8)
+    out["xyz_query_counts"], out["xyz_query_pcf"] = ref.pmft3(ref.PMFT_XYZ, Q, None, pmft3_quats(400, 6), q, mx, bins,
+                                                               equiv=PMFT3_EQUIV)
+    out["xyz_self_counts"], out["xyz_self_pcf"] = ref.pmft3(ref.PMFT_XYZ, Q, None, pmft3_quats(1500, 7), pts, mx, bins,
+                                                             equiv=PMFT3_EQUIV[:1], exclude_ii=True)
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        Q = ref.Query("aabb", box, pts, is2d=True)
+        out[f"{name}_xyt_query_counts"], out[f"{name}_xyt_query_pcf"] = ref.pmft3(ref.PMFT_XYT, Q, th_p, th_q, q,
+                                                                                   (3.0, 2.5), (14, 12, 9))
+        out[f"{name}_xyt_self_counts"], out[f"{name}_xyt_self_pcf"] = ref.pmft3(ref.PMFT_XYT, Q, th_p, th_p, pts,
+                                                                                 (3.0, 2.5), (14, 12, 9), exclude_ii=True)
+        out[f"{name}_r12_query_counts"], out[f"{name}_r12_query_pcf"] = ref.pmft3(ref.PMFT_R12, Q, th_p, th_q, q, (4.0,),
+                                                                                   (10, 11, 12))
+        out[f"{name}_r12_self_counts"], out[f"{name}_r12_self_pcf"] = ref.pmft3(ref.PMFT_R12, Q, th_p, th_p, pts, (4.0,),
+                                                                                 (10, 11, 12), exclude_ii=True)
+    box, pts, th = pmft3_lattice()
+    Q = ref.Query("aabb", box, pts, is2d=True)
+    out["lattice_xyt_counts"], out["lattice_xyt_pcf"] = ref.pmft3(ref.PMFT_XYT, Q, th, th, pts, (3.0, 3.0), (6, 6, 8),
+                                                                   exclude_ii=True)
+    out["lattice_r12_counts"], out["lattice_r12_pcf"] = ref.pmft3(ref.PMFT_R12, Q, th, th, pts, (3.0,), (6, 8, 8),
+                                                                   exclude_ii=True)
+    np.savez_compressed(os.path.join(HERE, "pmft3.npz"), **out)
+    print("pmft3", {k: int(v.sum()) for k, v in out.items() if k.endswith("counts")})
 
 
 PBUFF_BOXES = {"cube": Box.cube(5), "tri": Box(4, 5, 6, 0.3, -0.2, 0.1), "tilt2d": Box(4, 5, 0, 0.25, 0, 0, is2D=True)}

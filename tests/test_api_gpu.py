@@ -226,6 +226,103 @@ def test_pmftxy_api():
         pmft.PMFTXY(3.0, 2.5, (0, 4))
 
 
+def test_pmft3_api():
+    """freud.pmft.PMFTXYZ / PMFTXYT / PMFTR12 (tests/test_pmft.py upstream): bin counts and PCF bit for bit against the
+    reference's committed outputs (tests/golden/pmft3.npz) -- incl. the lattice whose bond angles all sit on bin edges,
+    where the bin hangs on the last place of libm's atan2f and the host decides -- reset=False, properties, errors."""
+    from tests.golden.make_golden import PMFT3_EQUIV, pmft3_lattice, pmft3_quats, pmftxy_inputs
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pmft3.npz"))
+
+    def same(pm, tag, frames=1):
+        assert np.array_equal(pm.bin_counts, frames * gold[f"{tag}_counts"]), tag
+        assert np.array_equal(bits(pm._pcf), bits(gold[f"{tag}_pcf"])), tag
+
+    # XYZ
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 1500, 31), random_points(box, 400, 32)
+    xyz = pmft.PMFTXYZ(2.0, 2.5, 3.0, (12, 10, 8))
+    assert xyz.nbins == (12, 10, 8) and xyz.bounds == [(-2.0, 2.0), (-2.5, 2.5), (-3.0, 3.0)]
+    assert np.isclose(xyz.r_max, np.sqrt(2.0 ** 2 + 2.5 ** 2 + 3.0 ** 2)) and [len(c) for c in xyz.bin_centers] == [12, 10, 8]
+    xyz.compute((box, pts), pmft3_quats(400, 6), query_points=q, equiv_orientations=PMFT3_EQUIV)
+    same(xyz, "xyz_query")
+    assert xyz.bin_counts.shape == (12, 10, 8) and xyz.box == box
+    xyz.compute((box, pts), pmft3_quats(400, 6), query_points=q, equiv_orientations=PMFT3_EQUIV, reset=False)
+    same(xyz, "xyz_query", frames=2)
+    with pytest.raises(RuntimeError):  # the number of equivalent orientations may not change while accumulating
+        xyz.compute((box, pts), pmft3_quats(400, 6), query_points=q, reset=False)
+    xyz.compute((box, pts), pmft3_quats(1500, 7))  # default: the identity only; self query excludes i == j
+    same(xyz, "xyz_self")
+    shifted = pmft.PMFTXYZ(2.0, 2.5, 3.0, (12, 10, 8), shiftvec=[0.5, 0, 0])
+    shifted.compute((box, pts), pmft3_quats(400, 6), query_points=q + np.float32([0.5, 0, 0]), equiv_orientations=PMFT3_EQUIV)
+    assert abs(int(shifted.bin_counts.sum()) - int(gold["xyz_query_counts"].sum())) < 200  # same bonds up to rounding
+    with pytest.raises(ValueError):
+        sq = Box.square(20)
+        pmft.PMFTXYZ(1, 1, 1, 4).compute((sq, random_points(sq, 50, 1)), pmft3_quats(50, 1))
+    with pytest.raises(ValueError):
+        pmft.PMFTXYZ(1, 1, -1, 4)
+
+    # XYT and R12
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        xyt = pmft.PMFTXYT(3.0, 2.5, (14, 12, 9))
+        xyt.compute((box, pts), th_p, query_points=q, query_orientations=th_q)
+        same(xyt, f"{name}_xyt_query")
+        xyt.compute((box, pts), th_p, query_points=q, query_orientations=th_q, reset=False)
+        same(xyt, f"{name}_xyt_query", frames=2)
+        xyt.compute((box, pts), th_p)
+        same(xyt, f"{name}_xyt_self")
+        r12 = pmft.PMFTR12(4.0, (10, 11, 12))
+        r12.compute((box, pts), th_p, query_points=q, query_orientations=th_q)
+        same(r12, f"{name}_r12_query")
+        r12.compute((box, pts), th_p)
+        same(r12, f"{name}_r12_self")
+        # random angles: only a sliver of the bonds sits close enough to a bin edge to need the host
+        assert 0 <= r12.host_binned_bonds < 0.01 * int(gold[f"{name}_r12_self_counts"].sum()) + 50
+    assert xyt.bounds[2] == (0.0, float(np.float32(2 * np.pi))) and r12.bounds[0] == (0.0, 4.0)
+    box, pts, th = pmft3_lattice()
+    xyt = pmft.PMFTXYT(3.0, 3.0, (6, 6, 8)).compute((box, pts), th)
+    same(xyt, "lattice_xyt")
+    r12 = pmft.PMFTR12(3.0, (6, 8, 8)).compute((box, pts), th)
+    same(r12, "lattice_r12")
+    assert xyt.host_binned_bonds > 1000 and r12.host_binned_bonds > 1000  # every bond angle is on a bin edge here
+    with pytest.raises(ValueError):
+        cube = Box.cube(10)
+        pmft.PMFTXYT(3.0, 2.5, 5).compute((cube, random_points(cube, 100, 1)), np.zeros(100))
+    with pytest.raises(ValueError):
+        pmft.PMFTR12(3.0, (4, 0, 4))
+    with pytest.raises(ValueError):
+        pmft.PMFTR12(3.0, 4).compute((box, pts), th[:10])
+
+
+def test_pmft3_matches_the_port_at_scale():
+    """100 k particles (2.5 M bonds in 2-D, 3 M in 3-D): bin counts of all three classes bit for bit against oracle/port.c
+    over the same NeighborList; the host's share of the angle bins stays a sliver."""
+    from tests.golden.make_golden import pmft3_quats
+
+    rs = np.random.RandomState(9)
+    box, pts = data.make_random_system(450.0, 100_000, is2D=True, seed=4)
+    th = (rs.random_sample(len(pts)) * 4 * np.pi - 2 * np.pi).astype(np.float32)  # also outside [0, 2 pi)
+    nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 4.0, exclude_ii=True)
+    xyt = pmft.PMFTXYT(3.0, 2.5, (40, 30, 36)).compute((box, pts), th, neighbors=dict(mode="ball", r_max=4.0))
+    want, want_pcf = port.pmft3(port.PMFT_XYT, box, len(pts), nl, th, th, (3.0, 2.5), (40, 30, 36))
+    assert np.array_equal(xyt.bin_counts, want) and np.array_equal(bits(xyt._pcf), bits(want_pcf))
+    r12 = pmft.PMFTR12(4.0, (20, 36, 36)).compute((box, pts), th, neighbors=dict(mode="ball", r_max=4.0))
+    want, want_pcf = port.pmft3(port.PMFT_R12, box, len(pts), nl, th, th, (4.0,), (20, 36, 36))
+    assert np.array_equal(r12.bin_counts, want) and np.array_equal(bits(r12._pcf), bits(want_pcf))
+    n_bonds = len(nl.distances)
+    assert xyt.host_binned_bonds < 2e-3 * n_bonds and r12.host_binned_bonds < 4e-3 * n_bonds
+    box, pts = data.make_random_system(60.0, 100_000, seed=5)
+    quats = pmft3_quats(len(pts), 8)
+    equiv = pmft3_quats(6, 9)
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, pts, 2.5, exclude_ii=True)
+    xyz = pmft.PMFTXYZ(2.0, 2.0, 2.0, (24, 20, 16)).compute((box, pts), quats, equiv_orientations=equiv,
+                                                           neighbors=dict(mode="ball", r_max=2.5))
+    want, want_pcf = port.pmft3(port.PMFT_XYZ, box, len(pts), nl, None, quats, (2.0, 2.0, 2.0), (24, 20, 16), equiv=equiv)
+    assert np.array_equal(xyz.bin_counts, want) and np.array_equal(bits(xyz._pcf), bits(want_pcf))
+
+
 def test_correlation_function_api():
     """freud.density.CorrelationFunction (tests/test_density_correlation_function.py upstream): complex and real
     inputs, is_complex, reset=False accumulation, histogram properties, the zero-mean random field known answer."""

@@ -341,6 +341,56 @@ def test_pmftxy_over_a_neighbor_list(ctx):
         capi.DevicePMFTXY(ctx, -1.0, 2.5, 4, 4)
 
 
+def test_pmft3_over_a_neighbor_list(ctx):
+    """fgpu_pmft_* (PMFTXYZ.cc:111-147, PMFTXYT.cc:77-101, PMFTR12.cc:91-113) over device NeighborLists against the
+    committed outputs of the reference: bin counts bit for bit.  XYZ is float arithmetic only; the angle axes of XYT / R12
+    hang on libm's atan2f, which the kernel brackets, leaving bonds next to a bin edge to the host -- all of them on the
+    lattice case.  Accumulation over two calls, a histogram too large for shared memory, constructor errors."""
+    from freud_b200.box import Box
+    from tests.golden.make_golden import PMFT3_EQUIV, pmft3_lattice, pmft3_quats, pmftxy_inputs
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "pmft3.npz"))
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 1500, 31), random_points(box, 400, 32)
+    r = float(np.sqrt(2.0 ** 2 + 2.5 ** 2 + 3.0 ** 2))
+    dp = capi.DevicePoints(ctx, box, pts)
+    xyz = capi.DevicePMFT(ctx, capi.PMFT_XYZ, (2.0, 2.5, 3.0), (12, 10, 8))
+    xyz.accumulate_nlist(dp.ball_query(q, IMAGE, r, 0.0, False), None, pmft3_quats(400, 6), PMFT3_EQUIV)
+    assert np.array_equal(xyz.read(), gold["xyz_query_counts"])
+    xyz.accumulate_nlist(dp.ball_query(q, IMAGE, r, 0.0, False), None, pmft3_quats(400, 6), PMFT3_EQUIV)
+    assert np.array_equal(xyz.read(), 2 * gold["xyz_query_counts"]) and xyz.host_binned_bonds == 0
+    xyz.reset()
+    xyz.accumulate_nlist(dp.ball_query(None, IMAGE, r, 0.0, True), None, pmft3_quats(1500, 7), PMFT3_EQUIV[:1])
+    assert np.array_equal(xyz.read(), gold["xyz_self_counts"])
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        dp = capi.DevicePoints(ctx, box, pts)
+        xyt = capi.DevicePMFT(ctx, capi.PMFT_XYT, (3.0, 2.5), (14, 12, 9))
+        xyt.accumulate_nlist(dp.ball_query(q, IMAGE, float(np.sqrt(3.0 ** 2 + 2.5 ** 2)), 0.0, False), th_p, th_q)
+        assert np.array_equal(xyt.read(), gold[f"{name}_xyt_query_counts"])
+        r12 = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (10, 11, 12))
+        r12.accumulate_nlist(dp.ball_query(None, IMAGE, 4.0, 0.0, True), th_p, th_p)
+        assert np.array_equal(r12.read(), gold[f"{name}_r12_self_counts"])
+    big = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (20, 36, 36))  # 104 KB of counters: global atomics
+    big.accumulate_nlist(dp.ball_query(None, IMAGE, 4.0, 0.0, True), th_p, th_p)
+    nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 4.0, 0.0, True)
+    assert np.array_equal(big.read(), port.pmft3(port.PMFT_R12, box, 3000, nl, th_p, th_p, (4.0,), (20, 36, 36))[0])
+    box, pts, th = pmft3_lattice()
+    dp = capi.DevicePoints(ctx, box, pts)
+    xyt = capi.DevicePMFT(ctx, capi.PMFT_XYT, (3.0, 3.0), (6, 6, 8))
+    xyt.accumulate_nlist(dp.ball_query(None, IMAGE, float(np.sqrt(18.0)), 0.0, True), th, th)
+    assert np.array_equal(xyt.read(), gold["lattice_xyt_counts"]) and xyt.host_binned_bonds > 1000
+    r12 = capi.DevicePMFT(ctx, capi.PMFT_R12, (3.0,), (6, 8, 8))
+    r12.accumulate_nlist(dp.ball_query(None, IMAGE, 3.0, 0.0, True), th, th)
+    assert np.array_equal(r12.read(), gold["lattice_r12_counts"])
+    for kind, maxes, bins in ((capi.PMFT_XYZ, (1, 1, 1), (4, 0, 4)), (capi.PMFT_XYT, (-1, 1), (4, 4, 4)),
+                              (capi.PMFT_R12, (-1,), (4, 4, 4)), (7, (1, 1, 1), (4, 4, 4))):
+        with pytest.raises(ValueError):
+            capi.DevicePMFT(ctx, kind, maxes, bins)
+
+
 def test_correlation_function_over_a_neighbor_list(ctx):
     """fgpu_corr_* (CorrelationFunction.cc:26-95) over device NeighborLists against the committed outputs of the
     reference: bin counts identical, complex<double> sums to double rounding; accumulation over two calls."""

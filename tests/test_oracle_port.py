@@ -185,6 +185,45 @@ def test_port_pmftxy_matches_golden():
         assert np.array_equal(bits(pcf), bits(gold[f"{name}_self_pcf"]))
 
 
+def test_port_pmft3_matches_golden():
+    """PMFTXYZ / PMFTXYT / PMFTR12 restated in oracle/port.c against outputs of the reference (tests/golden/pmft3.npz):
+    bin counts and PCF bit for bit (same libm), incl. the lattice whose bond angles all sit on bin edges."""
+    from tests.golden.make_golden import PMFT3_EQUIV, pmft3_lattice, pmft3_quats, pmftxy_inputs
+
+    gold = np.load(os.path.join(GOLD, "pmft3.npz"))
+
+    def same(got, tag):
+        assert np.array_equal(got[0], gold[f"{tag}_counts"]), tag
+        assert np.array_equal(bits(got[1]), bits(gold[f"{tag}_pcf"])), tag
+
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 1500, 31), random_points(box, 400, 32)
+    mx, bins = (2.0, 2.5, 3.0), (12, 10, 8)
+    r = float(np.sqrt(sum(m * m for m in mx)))
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, q, r)
+    same(port.pmft3(port.PMFT_XYZ, box, len(pts), nl, None, pmft3_quats(400, 6), mx, bins, equiv=PMFT3_EQUIV), "xyz_query")
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, pts, r, exclude_ii=True)
+    same(port.pmft3(port.PMFT_XYZ, box, len(pts), nl, None, pmft3_quats(1500, 7), mx, bins, equiv=PMFT3_EQUIV[:1]),
+         "xyz_self")
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        r_xyt = float(np.sqrt(3.0 ** 2 + 2.5 ** 2))
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, q, r_xyt)
+        same(port.pmft3(port.PMFT_XYT, box, len(pts), nl, th_p, th_q, (3.0, 2.5), (14, 12, 9)), f"{name}_xyt_query")
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, r_xyt, exclude_ii=True)
+        same(port.pmft3(port.PMFT_XYT, box, len(pts), nl, th_p, th_p, (3.0, 2.5), (14, 12, 9)), f"{name}_xyt_self")
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, q, 4.0)
+        same(port.pmft3(port.PMFT_R12, box, len(pts), nl, th_p, th_q, (4.0,), (10, 11, 12)), f"{name}_r12_query")
+        nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 4.0, exclude_ii=True)
+        same(port.pmft3(port.PMFT_R12, box, len(pts), nl, th_p, th_p, (4.0,), (10, 11, 12)), f"{name}_r12_self")
+    box, pts, th = pmft3_lattice()
+    nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, float(np.sqrt(18.0)), exclude_ii=True)
+    same(port.pmft3(port.PMFT_XYT, box, len(pts), nl, th, th, (3.0, 3.0), (6, 6, 8)), "lattice_xyt")
+    nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 3.0, exclude_ii=True)
+    same(port.pmft3(port.PMFT_R12, box, len(pts), nl, th, th, (3.0,), (6, 8, 8)), "lattice_r12")
+
+
 def test_port_wigner3j_known_values():
     """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
     the reference is present, every tabulated l <= 20 as float."""
