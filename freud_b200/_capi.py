@@ -77,6 +77,12 @@ SIGNATURES = {
     "fgpu_pmft_accumulate_nlist": (C.c_int, [_vp, _vp, _fp, C.c_uint32, _fp, _fp, C.c_uint32]),
     "fgpu_pmft_read": (C.c_int, [_vp, _up]),
     "fgpu_pmft_deferred": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "fgpu_bondorder_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _vpp]),
+    "fgpu_bondorder_destroy": (None, [_vp]),
+    "fgpu_bondorder_reset": (C.c_int, [_vp]),
+    "fgpu_bondorder_accumulate_nlist": (C.c_int, [_vp, _vp, _fp, C.c_uint32, _fp]),
+    "fgpu_bondorder_read": (C.c_int, [_vp, _up]),
+    "fgpu_bondorder_deferred": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "fgpu_corr_create": (C.c_int, [_vp, C.c_uint32, C.c_float, _vpp]),
     "fgpu_corr_destroy": (None, [_vp]),
     "fgpu_corr_reset": (C.c_int, [_vp]),
@@ -454,6 +460,46 @@ class DevicePMFT(_DeviceObject):
     def host_binned_bonds(self):
         n = C.c_uint64(0)
         check(lib().fgpu_pmft_deferred(self._h, C.byref(n)))
+        return n.value
+
+
+BOND_ORDER_MODES = {"bod": 0, "lbod": 1, "obcd": 2, "oocd": 3}
+
+
+class DeviceBondOrder(_DeviceObject):
+    """Device-resident BondOrder histogram (``fgpu_bondorder``)."""
+
+    _destroy = "fgpu_bondorder_destroy"
+
+    def __init__(self, ctx, n_theta, n_phi, mode="bod"):
+        self._adopt(ctx)
+        self.shape = (int(n_theta), int(n_phi))
+        self._h = _vp()
+        check(lib().fgpu_bondorder_create(ctx._h, self.shape[0], self.shape[1], BOND_ORDER_MODES.get(mode, -1),
+                                          C.byref(self._h)))
+
+    def reset(self):
+        check(lib().fgpu_bondorder_reset(self._h))
+
+    def accumulate_nlist(self, nlist, orientations=None, query_orientations=None):
+        """(N, 4) quaternions of the points and of the query points; mode 'bod' needs neither."""
+        o = qo = None
+        if orientations is not None:
+            o = np.ascontiguousarray(orientations, dtype=np.float32).reshape(-1, 4)
+            qo = np.ascontiguousarray(query_orientations, dtype=np.float32).reshape(-1, 4)
+            assert len(o) == nlist.num_points and len(qo) == nlist.num_query_points
+        check(lib().fgpu_bondorder_accumulate_nlist(self._h, nlist._h, ptr(o) if o is not None else None,
+                                                    nlist.num_points, ptr(qo) if qo is not None else None))
+
+    def read(self):
+        counts = np.empty(self.shape, np.uint32)
+        check(lib().fgpu_bondorder_read(self._h, ptr(counts, _up)))
+        return counts
+
+    @property
+    def host_binned_bonds(self):
+        n = C.c_uint64(0)
+        check(lib().fgpu_bondorder_deferred(self._h, C.byref(n)))
         return n.value
 
 

@@ -1872,6 +1872,195 @@ int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds)
     });
 }
 
+// ---- BondOrder ----------------------------------------------------------------------------------------------------
+namespace {
+
+// rotate(q, v), VectorMath.h:810-818, in float with one rounding per operation (this file is built without contraction)
+void host_quat_rotate(float s, float qx, float qy, float qz, float& x, float& y, float& z)
+{
+    float const bx = x, by = y, bz = z;
+    float const p1 = qx * qx, p2 = qy * qy, p3 = qz * qz;
+    float const vv = (p1 + p2) + p3;
+    float const ss = s * s;
+    float const a = ss - vv;
+    float const two_s = 2.0f * s;
+    float const c1 = qy * bz, c2 = qz * by, c3 = qz * bx, c4 = qx * bz, c5 = qx * by, c6 = qy * bx;
+    float const cx = c1 - c2, cy = c3 - c4, cz = c5 - c6;
+    float const d1 = qx * bx, d2 = qy * by, d3 = qz * bz;
+    float const vb = (d1 + d2) + d3;
+    float const two_vb = 2.0f * vb;
+    float const t1x = bx * a, t2x = cx * two_s, t3x = qx * two_vb;
+    float const t1y = by * a, t2y = cy * two_s, t3y = qy * two_vb;
+    float const t1z = bz * a, t2z = cz * two_s, t3z = qz * two_vb;
+    x = (t1x + t2x) + t3x;
+    y = (t1y + t2y) + t3y;
+    z = (t1z + t2z) + t3z;
+}
+
+} // namespace
+
+int fgpu_bondorder_create(fgpu_ctx* ctx, uint32_t n_theta, uint32_t n_phi, int mode, fgpu_bondorder** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        // BondOrder.cc:34-41
+        require(n_theta >= 2, FGPU_EINVALID, "BondOrder requires at least 2 bins in theta.");
+        require(n_phi >= 2, FGPU_EINVALID, "BondOrder requires at least 2 bins in phi.");
+        require(mode >= FGPU_BOND_ORDER_BOD && mode <= FGPU_BOND_ORDER_OOCD, FGPU_EINVALID, "unknown BondOrder mode");
+        require((uint64_t) n_theta * n_phi < (1ULL << 31), FGPU_EINVALID, "BondOrder histogram too large");
+        bind_device(ctx);
+        std::unique_ptr<fgpu_bondorder> b(new fgpu_bondorder());
+        b->ctx = ctx;
+        b->mode = mode;
+        b->at = regular_axis(n_theta, 0.0f, (float) (2.0 * M_PI)); // BondOrder.cc:70-71
+        b->ap = regular_axis(n_phi, 0.0f, (float) M_PI);
+        b->hist.reserve((size_t) n_theta * n_phi);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(b->hist.ptr, 0, (size_t) n_theta * n_phi * sizeof(uint32_t), ctx->stream));
+        sync(ctx);
+        *out = b.release();
+    });
+}
+
+void fgpu_bondorder_destroy(fgpu_bondorder* bo)
+{
+    if (bo != nullptr)
+    {
+        bind_quiet(bo->ctx);
+        delete bo;
+    }
+}
+
+int fgpu_bondorder_reset(fgpu_bondorder* bo)
+{
+    return guarded([&] {
+        require(bo != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(bo->ctx);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(bo->hist.ptr, 0, (size_t) bo->at.bins * bo->ap.bins * sizeof(uint32_t),
+                                        bo->ctx->stream));
+        bo->deferred_total = 0;
+    });
+}
+
+int fgpu_bondorder_accumulate_nlist(fgpu_bondorder* bo, const fgpu_nlist* nl, const float* orientations_host,
+                                    uint32_t n_points, const float* query_orientations_host)
+{
+    return guarded([&] {
+        require(bo != nullptr && nl != nullptr, FGPU_EINVALID, "null argument");
+        require(bo->ctx == nl->ctx, FGPU_EINVALID, "bond order and nlist belong to different contexts");
+        int const mode = bo->mode;
+        require(mode == FGPU_BOND_ORDER_BOD || (orientations_host != nullptr && query_orientations_host != nullptr),
+                FGPU_EINVALID, "null orientations");
+        fgpu_ctx* ctx = bo->ctx;
+        bind_device(ctx);
+        BondOrderArgs a {};
+        a.at = bo->at;
+        a.ap = bo->ap;
+        a.mode = mode;
+        a.hist = bo->hist.ptr;
+        if (mode != FGPU_BOND_ORDER_BOD)
+        {
+            bo->stage_a.reserve(4 * (size_t) n_points + 4);
+            bo->stage_b.reserve(4 * (size_t) nl->n_query + 4);
+            h2d(ctx, bo->stage_a.ptr, orientations_host, 4 * (size_t) n_points * sizeof(float));
+            h2d(ctx, bo->stage_b.ptr, query_orientations_host, 4 * (size_t) nl->n_query * sizeof(float));
+            a.orientations = reinterpret_cast<const float4*>(bo->stage_a.ptr);
+            a.query_orientations = reinterpret_cast<const float4*>(bo->stage_b.ptr);
+        }
+        std::vector<uint4> rec;
+        std::vector<float> rec_z;
+        std::vector<uint32_t> bins;
+        for (uint64_t b0 = 0; b0 < nl->n_bonds; b0 += kPmftChunk)
+        {
+            uint64_t const nb = std::min<uint64_t>(kPmftChunk, nl->n_bonds - b0);
+            a.neighbors = nl->neighbors.ptr + 2 * b0;
+            a.vectors = nl->vectors.ptr + 3 * b0;
+            a.n_bonds = nb;
+            bo->deferred.reserve((size_t) nb);
+            bo->deferred_z.reserve((size_t) nb);
+            a.deferred = bo->deferred.ptr;
+            a.deferred_z = bo->deferred_z.ptr;
+            a.deferred_cap = (uint32_t) nb;
+            a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
+            FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
+            launch_bond_order(ctx, a);
+            d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
+            sync(ctx);
+            uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
+            if (n_def == 0)
+            {
+                continue;
+            }
+            rec.resize(n_def);
+            rec_z.resize(n_def);
+            d2h(ctx, rec.data(), bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
+            d2h(ctx, rec_z.data(), bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
+            sync(ctx);
+            bins.clear();
+            for (uint32_t r = 0; r < n_def; ++r)
+            {
+                uint32_t const i = rec[r].x, j = rec[r].y;
+                float x, y, z = rec_z[r];
+                std::memcpy(&x, &rec[r].z, sizeof(float));
+                std::memcpy(&y, &rec[r].w, sizeof(float));
+                if (mode != FGPU_BOND_ORDER_BOD) // BondOrder.cc:108-134
+                {
+                    const float* rq = orientations_host + 4 * (size_t) j;
+                    const float* q = query_orientations_host + 4 * (size_t) i;
+                    if (mode == FGPU_BOND_ORDER_OOCD)
+                    {
+                        x = 0.0f;
+                        y = 0.0f;
+                        z = 1.0f;
+                        host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+                    }
+                    host_quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], x, y, z);
+                    if (mode == FGPU_BOND_ORDER_OBCD)
+                    {
+                        host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+                    }
+                }
+                float const theta = host_mod_two_pi(std::atan2(y, x)); // BondOrder.cc:140-141
+                float const xx = x * x, yy = y * y, zz = z * z;
+                float const dot = (xx + yy) + zz;
+                float const arg = z / std::sqrt(dot);
+                float const phi = std::acos(arg); // :144
+                int const bt = host_axis_bin(a.at, theta), bp = host_axis_bin(a.ap, phi);
+                if (bt >= 0 && bp >= 0)
+                {
+                    bins.push_back((uint32_t) bt * a.ap.bins + (uint32_t) bp);
+                }
+            }
+            bo->deferred_total += n_def;
+            if (!bins.empty())
+            {
+                bo->host_bins.reserve(bins.size());
+                h2d(ctx, bo->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
+                launch_add_bins(ctx, bo->host_bins.ptr, (uint32_t) bins.size(), bo->hist.ptr);
+                sync(ctx);
+            }
+        }
+        sync(ctx); // the caller's arrays were consumed
+    });
+}
+
+int fgpu_bondorder_read(fgpu_bondorder* bo, uint32_t* counts_host)
+{
+    return guarded([&] {
+        require(bo != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(bo->ctx);
+        d2h(bo->ctx, counts_host, bo->hist.ptr, (size_t) bo->at.bins * bo->ap.bins * sizeof(uint32_t));
+        sync(bo->ctx);
+    });
+}
+
+int fgpu_bondorder_deferred(const fgpu_bondorder* bo, uint64_t* bonds)
+{
+    return guarded([&] {
+        require(bo != nullptr && bonds != nullptr, FGPU_EINVALID, "null argument");
+        *bonds = bo->deferred_total;
+    });
+}
+
 int fgpu_corr_create(fgpu_ctx* ctx, uint32_t bins, float r_max, fgpu_corr** out)
 {
     return guarded([&] {

@@ -218,6 +218,19 @@ struct fgpu_pmft
     uint64_t deferred_total = 0;      // statistics: bonds the host binned since the last reset
 };
 
+struct fgpu_bondorder
+{
+    fgpu_ctx* ctx = nullptr;
+    int mode = 0; // FGPU_BOND_ORDER_*
+    fgpu::AxisDev at, ap;
+    fgpu::DevBuf<uint32_t> hist;           // n_theta * n_phi, row-major (theta slow)
+    fgpu::DevBuf<float> stage_a, stage_b;  // staged per call: orientations of the points | of the query points
+    fgpu::DevBuf<uint4> deferred;          // bonds left to the host's libm: (i, j, bits vx, bits vy) ...
+    fgpu::DevBuf<float> deferred_z;        // ... and vz
+    fgpu::DevBuf<uint32_t> host_bins;
+    uint64_t deferred_total = 0;
+};
+
 struct fgpu_corr
 {
     fgpu_ctx* ctx = nullptr;
@@ -496,6 +509,23 @@ struct Pmft3Args
 };
 void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a);
 void launch_add_bins(fgpu_ctx* ctx, const uint32_t* bins, uint32_t n, uint32_t* hist);
+struct BondOrderArgs
+{
+    AxisDev at, ap;
+    int mode;
+    const uint32_t* neighbors;
+    const float* vectors;
+    uint64_t n_bonds;
+    const float4* orientations;       // per point, (s, x, y, z)
+    const float4* query_orientations; // per query point
+    uint32_t* hist;
+    uint4* deferred;
+    float* deferred_z;
+    uint32_t deferred_cap;
+    uint32_t* deferred_count;
+    int use_shared;
+};
+void launch_bond_order(fgpu_ctx* ctx, BondOrderArgs a);
 void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
                         const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums);
 void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,

@@ -1,7 +1,8 @@
 // Three-axis PMFT histograms over the bonds of a device NeighborList: freud::pmft::PMFTXYZ, PMFTXYT and PMFTR12
-// (freud/pmft/PMFTXYZ.cc:111-147, PMFTXYT.cc:77-101, PMFTR12.cc:91-113).  One thread per bond, u32 bin counts in a
-// block-shared histogram when it fits and in global memory otherwise, linear index (b0 * n1 + b1) * n2 + b2
-// (Histogram.h:327-351).
+// (freud/pmft/PMFTXYZ.cc:111-147, PMFTXYT.cc:77-101, PMFTR12.cc:91-113) -- and, built from the same parts, the bond
+// orientational order diagram freud::environment::BondOrder (freud/environment/BondOrder.cc:100-153; end of file).
+// One thread per bond, u32 bin counts in a block-shared histogram when it fits and in global memory otherwise, linear
+// index (b0 * n1 + b1) * n2 + b2 (Histogram.h:327-351).
 //
 //   XYZ  the bond vector rotated by conj(q_i) and then by every equivalent orientation, all in the reference's float
 //        operation order (VectorMath.h:810-818) -> three RegularAxis bins.  Pure float arithmetic: bit-exact counts.
@@ -155,6 +156,90 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
     }
 }
 
+// BondOrder::accumulate: the bond vector (or, mode oocd, the z director of the query particle) rotated as the mode
+// asks, then theta = modulusPositive(atan2f(v.y, v.x), 2 pi) on RegularAxis(n_theta, 0, 2 pi) and
+// phi = acosf(v.z / sqrt(v.v)) on RegularAxis(n_phi, 0, pi).  Both angles are bracketed like the PMFT angles: double
+// atan2 / acos of the reference's float arguments, bins accepted away from the bin edges, the rest left to the host.
+__global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
+{
+    extern __shared__ uint32_t bo_hist[];
+    uint32_t const n_bins = a.at.bins * a.ap.bins;
+    if (a.use_shared)
+    {
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+        {
+            bo_hist[b] = 0;
+        }
+        __syncthreads();
+    }
+    uint32_t* const h = a.use_shared ? bo_hist : a.hist;
+    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
+    {
+        uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
+        float const vx = a.vectors[3 * k], vy = a.vectors[3 * k + 1], vz = a.vectors[3 * k + 2];
+        float x = vx, y = vy, z = vz;
+        if (a.mode != FGPU_BOND_ORDER_BOD)
+        {
+            float4 const rq = a.orientations[ij.y];      // ref_q = orientations[point], BondOrder.cc:108
+            float4 const q = a.query_orientations[ij.x]; // q = query_orientations[query point], :110
+            if (a.mode == FGPU_BOND_ORDER_OOCD)
+            {
+                x = 0.0f;
+                y = 0.0f;
+                z = 1.0f;
+                quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :127-130
+            }
+            quat_rotate(rq.x, -rq.y, -rq.z, -rq.w, x, y, z); // rotate(conj(ref_q), .), :116, :123, :133
+            if (a.mode == FGPU_BOND_ORDER_OBCD)
+            {
+                quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :117
+            }
+        }
+        // theta: the chain of angle_bin with orientation - d replaced by d itself
+        float const d = (float) atan2((double) y, (double) x);
+        float const theta = mod_two_pi(d);
+        float const ut = __fmul_rn(theta, a.at.inv_width);
+        float const ft = ut - floorf(ut);
+        float const mt = kAngleMargin * a.at.inv_width + 1.0e-6f * (ut + 1.0f);
+        bool sure = ft > mt && ft < 1.0f - mt && theta > kAngleMargin && theta < kTwoPi - kAngleMargin;
+        // phi: the argument is float arithmetic (one division, one square root), acosf is libm's
+        float const c = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
+        float const phi = (float) acos((double) c);
+        float const up = __fmul_rn(phi, a.ap.inv_width);
+        float const fp = up - floorf(up);
+        float const mp = kAngleMargin * a.ap.inv_width + 1.0e-6f * (up + 1.0f);
+        sure = sure && fp > mp && fp < 1.0f - mp && phi > kAngleMargin && phi < a.ap.r_max - kAngleMargin;
+        if (sure)
+        {
+            int const bt = axis_bin(a.at, theta), bp = axis_bin(a.ap, phi);
+            if (bt >= 0 && bp >= 0)
+            {
+                atomicAdd(&h[(uint32_t) bt * a.ap.bins + (uint32_t) bp], 1U);
+            }
+        }
+        else
+        {
+            uint32_t const slot = atomicAdd(a.deferred_count, 1U);
+            if (slot < a.deferred_cap)
+            {
+                a.deferred[slot] = make_uint4(ij.x, ij.y, __float_as_uint(vx), __float_as_uint(vy));
+                a.deferred_z[slot] = vz;
+            }
+        }
+    }
+    if (a.use_shared)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+        {
+            if (bo_hist[b] != 0)
+            {
+                atomicAdd(&a.hist[b], bo_hist[b]);
+            }
+        }
+    }
+}
+
 // the host's share: one count per listed bin
 __global__ void __launch_bounds__(256) k_add_bins(const uint32_t* __restrict__ bins, uint32_t n, uint32_t* __restrict__ hist)
 {
@@ -191,6 +276,22 @@ void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
             k_pmft3<FGPU_PMFT_R12><<<blocks, 256, dyn, ctx->stream>>>(a);
             break;
         }
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bond_order(fgpu_ctx* ctx, BondOrderArgs a)
+{
+    if (a.n_bonds == 0)
+    {
+        return;
+    }
+    size_t const smem = (size_t) a.at.bins * a.ap.bins * sizeof(uint32_t);
+    a.use_shared = smem <= 40 * 1024 ? 1 : 0;
+    unsigned const blocks = (unsigned) std::min<uint64_t>((a.n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 8U);
+    {
+        KernelScope ks(ctx, "bond_order");
+        k_bond_order<<<blocks, 256, a.use_shared ? smem : 0, ctx->stream>>>(a);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }

@@ -18,6 +18,7 @@
 #include "NeighborQuery.h"
 #include "CorrelationFunction.h"
 #include "LocalDensity.h"
+#include "BondOrder.h"
 #include "PMFT.h"
 #include "RDF.h"
 #include "Steinhardt.h"
@@ -384,6 +385,50 @@ PYBIND11_MODULE(_freud_b200, m)
              py::arg("neighbor_query"), py::arg("orientations"), py::arg("query_points"), py::arg("query_orientations"),
              py::arg("nlist").none(true), py::arg("qargs"));
     bind_pmft3(r12);
+
+    // ---- _environment ----------------------------------------------------------------------------------
+    auto menv = m.def_submodule("_environment");
+    py::enum_<environment::BondOrderMode>(menv, "BondOrderMode")
+        .value("bod", environment::bod)
+        .value("lbod", environment::lbod)
+        .value("obcd", environment::obcd)
+        .value("oocd", environment::oocd)
+        .export_values();
+    py::class_<environment::BondOrder, std::shared_ptr<environment::BondOrder>>(menv, "BondOrder")
+        .def(py::init<unsigned int, unsigned int, environment::BondOrderMode>(), py::arg("n_bins_theta"),
+             py::arg("n_bins_phi"), py::arg("mode"))
+        .def("accumulate",
+             [](environment::BondOrder& b, std::shared_ptr<locality::NeighborQuery> nq,
+                py::array_t<float, py::array::c_style | py::array::forcecast> orientations, points_array qp,
+                py::array_t<float, py::array::c_style | py::array::forcecast> query_orientations,
+                std::shared_ptr<locality::NeighborList> nlist, const locality::QueryArgs& qargs) {
+                 unsigned int n = 0;
+                 const vec3<float>* q = as_vec3(qp, n);
+                 if (orientations.ndim() != 2 || orientations.shape(1) != 4
+                     || (size_t) orientations.shape(0) != nq->getNPoints())
+                 {
+                     throw std::invalid_argument("orientations must hold one quaternion per point");
+                 }
+                 if (query_orientations.ndim() != 2 || query_orientations.shape(1) != 4
+                     || (size_t) query_orientations.shape(0) != n)
+                 {
+                     throw std::invalid_argument("query_orientations must hold one quaternion per query point");
+                 }
+                 b.accumulate(nq, reinterpret_cast<const quat<float>*>(orientations.data()), q,
+                              reinterpret_cast<const quat<float>*>(query_orientations.data()), n, nlist, qargs);
+             },
+             py::arg("neighbor_query"), py::arg("orientations"), py::arg("query_points"), py::arg("query_orientations"),
+             py::arg("nlist").none(true), py::arg("qargs"))
+        .def("getBondOrder", [](environment::BondOrder& b) { return to_numpy<float>(b.getBondOrder()); })
+        .def("getBinCounts", [](environment::BondOrder& b) { return to_numpy<unsigned int>(b.getBinCounts()); })
+        .def("getBinEdges", &environment::BondOrder::getBinEdges)
+        .def("getBinCenters", &environment::BondOrder::getBinCenters)
+        .def("getBounds", &environment::BondOrder::getBounds)
+        .def("getAxisSizes", &environment::BondOrder::getAxisSizes)
+        .def("getBox", &environment::BondOrder::getBox)
+        .def("getMode", &environment::BondOrder::getMode)
+        .def("getHostBinnedBonds", &environment::BondOrder::getHostBinnedBonds)
+        .def("reset", &environment::BondOrder::reset);
 
     // ---- _order ----------------------------------------------------------------------------------------
     auto mord = m.def_submodule("_order");

@@ -50,6 +50,7 @@ typedef struct fgpu_nlist fgpu_nlist;   /* device-resident NeighborList (SoA, CS
 typedef struct fgpu_rdf fgpu_rdf;       /* device-resident RDF histogram accumulator          */
 typedef struct fgpu_pmftxy fgpu_pmftxy; /* device-resident PMFTXY histogram                      */
 typedef struct fgpu_pmft fgpu_pmft;     /* device-resident PMFTXYZ / PMFTXYT / PMFTR12 histogram  */
+typedef struct fgpu_bondorder fgpu_bondorder; /* device-resident BondOrder histogram              */
 typedef struct fgpu_corr fgpu_corr;     /* device-resident CorrelationFunction accumulators  */
 typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
 
@@ -82,7 +83,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, pmftxy, pmft3, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, pmftxy, pmft3, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -237,6 +238,27 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
                                uint32_t n_equiv);
 int fgpu_pmft_read(fgpu_pmft* pmft, uint32_t* counts_host);
 int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds);
+
+/* ---- BondOrder -------------------------------------------------------------------------------------------
+ * Device half of freud::environment::BondOrder (freud/environment/BondOrder.cc:30-153): a u32[n_theta][n_phi]
+ * histogram of bond directions over the bonds of a NeighborList, theta in [0, 2 pi), phi in [0, pi), resident across
+ * accumulate calls.  mode = BondOrderMode (BondOrder.h:23-29).  orientations_host[n_points] and
+ * query_orientations_host[n_query] are quaternions (s, x, y, z) float[4]; mode bod reads neither (both may be NULL).
+ * Counts are bit-identical to the reference's: rotations in its float order on the GPU, atan2f / acosf bracketed on
+ * the GPU with the bonds next to a bin edge binned by the host's libm (as for fgpu_pmft).  The normalisation by the
+ * solid angle of the bins (BondOrder::reduce) is host arithmetic in freud_b200/host/BondOrder.h.
+ * Errors: n_theta or n_phi < 2, unknown mode -> FGPU_EINVALID (BondOrder.cc:34-41). */
+#define FGPU_BOND_ORDER_BOD 0
+#define FGPU_BOND_ORDER_LBOD 1
+#define FGPU_BOND_ORDER_OBCD 2
+#define FGPU_BOND_ORDER_OOCD 3
+int fgpu_bondorder_create(fgpu_ctx* ctx, uint32_t n_theta, uint32_t n_phi, int mode, fgpu_bondorder** out);
+void fgpu_bondorder_destroy(fgpu_bondorder* bo);
+int fgpu_bondorder_reset(fgpu_bondorder* bo);
+int fgpu_bondorder_accumulate_nlist(fgpu_bondorder* bo, const fgpu_nlist* nl, const float* orientations_host,
+                                    uint32_t n_points, const float* query_orientations_host);
+int fgpu_bondorder_read(fgpu_bondorder* bo, uint32_t* counts_host);
+int fgpu_bondorder_deferred(const fgpu_bondorder* bo, uint64_t* bonds);
 
 /* ---- CorrelationFunction ---------------------------------------------------------------------------------
  * Device half of freud::density::CorrelationFunction (freud/density/CorrelationFunction.cc:26-95): per bin of

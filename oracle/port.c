@@ -1737,3 +1737,65 @@ int fport_pmft3(int kind, const uint32_t* nl_ij, const float* nl_v, const float*
     return 0;
 }
 
+/* ---- BondOrder over the bonds of a NeighborList (one frame), freud/environment/BondOrder.cc:30-153 ---------------
+ * mode 0 bod: v = bond vector; 1 lbod: v = rotate(conj(o_j), v); 2 obcd: v = rotate(q_i, rotate(conj(o_j), v));
+ * 3 oocd: v = rotate(conj(o_j), rotate(q_i, z)).  theta = modulusPositive(atan2f(v.y, v.x), 2 pi),
+ * phi = acosf(v.z / sqrtf(v.v)); bins on RegularAxis(n_theta, 0, 2 pi) x RegularAxis(n_phi, 0, pi); the diagram divides
+ * the counts by the solid angle of the bin, dt (cos(phi_j) - cos(phi_j + dp)), and by the number of frames (:88-93). */
+int fport_bond_order(int mode, const uint32_t* nl_ij, const float* nl_v, uint64_t n_bonds, const float* orientations,
+                     const float* query_orientations, uint32_t n_theta, uint32_t n_phi, uint32_t* counts, float* bond_order)
+{
+    const float two_pi = (float) (2.0 * M_PI), pi_f = (float) M_PI;
+    float wt, it, wp, ip;
+    axis_params(n_theta, 0.0f, two_pi, &wt, &it);
+    axis_params(n_phi, 0.0f, pi_f, &wp, &ip);
+    memset(counts, 0, (size_t) n_theta * n_phi * sizeof(uint32_t));
+    for (uint64_t k = 0; k < n_bonds; ++k)
+    {
+        uint32_t const i = nl_ij[2 * k], j = nl_ij[2 * k + 1];
+        float x = nl_v[3 * k], y = nl_v[3 * k + 1], z = nl_v[3 * k + 2];
+        if (mode != 0)
+        {
+            const float* rq = orientations + 4 * (size_t) j;
+            const float* q = query_orientations + 4 * (size_t) i;
+            if (mode == 3)
+            {
+                x = 0.0f;
+                y = 0.0f;
+                z = 1.0f;
+                quat_rotate(q[0], q[1], q[2], q[3], &x, &y, &z);
+            }
+            quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], &x, &y, &z);
+            if (mode == 2)
+            {
+                quat_rotate(q[0], q[1], q[2], q[3], &x, &y, &z);
+            }
+        }
+        float theta = mod_two_pi(atan2f(y, x));
+        float xx = x * x, yy = y * y, zz = z * z;
+        float dot = (xx + yy) + zz;
+        float arg = z / sqrtf(dot);
+        float phi = acosf(arg);
+        int64_t bt = axis_bin(theta, 0.0f, two_pi, it, n_theta), bp = axis_bin(phi, 0.0f, pi_f, ip, n_phi);
+        if (bt >= 0 && bp >= 0)
+        {
+            counts[(size_t) bt * n_phi + (size_t) bp] += 1;
+        }
+    }
+    float dt = two_pi / (float) n_theta;
+    float dp = (float) (M_PI / (double) (float) n_phi);
+    for (uint32_t a = 0; a < n_theta; ++a)
+    {
+        for (uint32_t b = 0; b < n_phi; ++b)
+        {
+            float phi = (float) b * dp;
+            float phi2 = phi + dp;
+            float diff = cosf(phi) - cosf(phi2);
+            float sa = dt * diff;
+            float t = (float) counts[(size_t) a * n_phi + b] / sa;
+            bond_order[(size_t) a * n_phi + b] = t / 1.0f; /* one frame */
+        }
+    }
+    return 0;
+}
+

@@ -181,6 +181,22 @@ def pmft3(kind, box, n_points, nlist, orientations, query_orientations, maxes, b
     return counts, pcf
 
 
+BOND_ORDER_MODES = {"bod": 0, "lbod": 1, "obcd": 2, "oocd": 3}
+
+
+def bond_order(mode, nlist, orientations, query_orientations, bins):
+    """(bin_counts u32[n_theta, n_phi], bond_order f32[...]) of BondOrder over the bonds of an oracle NeighborList."""
+    ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)
+    v = _f32(nlist.vectors, 3)
+    o, qo = _f32(orientations, 4), _f32(query_orientations, 4)
+    counts, bo = np.zeros(bins, np.uint32), np.zeros(bins, np.float32)
+    L = lib()
+    L.fport_bond_order.argtypes = [C.c_int, _up, _fp, C.c_uint64, _fp, _fp, C.c_uint32, C.c_uint32, _up, _fp]
+    L.fport_bond_order(BOND_ORDER_MODES[mode], _p(ij, _up), _p(v), len(v), _p(o), _p(qo), int(bins[0]), int(bins[1]),
+                       _p(counts, _up), _p(bo))
+    return counts, bo
+
+
 def correlation_function(nlist, values, query_values, bins, r_max):
     """(correlation complex128[bins], bin_counts) of CorrelationFunction over the bonds of an oracle NeighborList."""
     ij = np.ascontiguousarray(nlist.neighbors, dtype=np.uint32)

@@ -250,6 +250,27 @@ def pmft3(kind, query, orientations, query_orientations, query_points, maxes, bi
     return counts, pcf
 
 
+BOND_ORDER_MODES = {"bod": 0, "lbod": 1, "obcd": 2, "oocd": 3}
+
+
+def bond_order(bo_mode, query, orientations, query_points, query_orientations, bins, nlist=None, **qargs):
+    """BondOrder(bins, mode).compute(...) of the reference: (bin_counts u32[n_theta, n_phi], bond_order f32[...]);
+    orientations are (N, 4) quaternions; the bonds are ``nlist`` or the query ``qargs`` describe."""
+    q = _f32(query_points, 3)
+    o, qo = _f32(orientations, 4), _f32(query_orientations, 4)
+    counts, bo = np.zeros(bins, np.uint32), np.zeros(bins, np.float32)
+    L = lib()
+    L.fref_bond_order.argtypes = [C.c_int, C.c_void_p, _fp, _fp, _fp, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int,
+                                  C.c_uint, C.c_float, C.c_int, _up, _fp]
+    qa = _qargs(**qargs) if qargs else _qargs(mode="ball", r_max=1.0)
+    mode_q, num_neighbors, r_max, exclude_ii = qa[0], qa[1], qa[2], qa[-1]
+    if L.fref_bond_order(BOND_ORDER_MODES[bo_mode], query._h, _p(o), _p(q), _p(qo), len(q),
+                         nlist._h if nlist is not None else None, int(bins[0]), int(bins[1]), mode_q, num_neighbors,
+                         r_max, exclude_ii, _p(counts, _up), _p(bo)):
+        _raise()
+    return counts, bo
+
+
 def correlation_function(query, values, query_points, query_values, bins, r_max, nlist=None, exclude_ii=False):
     """CorrelationFunction(bins, r_max).compute(...) of the reference: (correlation complex128[bins], bin_counts)."""
     q = _f32(query_points, 3)

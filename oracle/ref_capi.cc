@@ -15,6 +15,7 @@
 //   freud::pmft::PMFTXY                              freud/pmft/PMFTXY.h
 //   freud::pmft::PMFTXYZ, PMFTXYT, PMFTR12           freud/pmft/PMFTXYZ.h, PMFTXYT.h, PMFTR12.h
 //   freud::order::Steinhardt                         freud/order/Steinhardt.h:66
+//   freud::environment::BondOrder                    freud/environment/BondOrder.h:32
 //   freud::locality::PeriodicBuffer                  freud/locality/PeriodicBuffer.h:22
 //   freud::parallel::setNumThreads                   freud/parallel/tbb_config.cc:25
 
@@ -26,6 +27,7 @@
 #include <vector>
 
 #include "AABBQuery.h"
+#include "BondOrder.h"
 #include "Box.h"
 #include "CellQuery.h"
 #include "CorrelationFunction.h"
@@ -399,6 +401,30 @@ int fref_pmft3(int kind, void* nq, const float* orientations, const float* query
             p.accumulate(h->nq, orientations, qp, query_orientations, n_query, nl, args);
             copy_out(p);
         }
+    });
+}
+
+// ---- BondOrder --------------------------------------------------------------------------------------
+// BondOrder(n_theta, n_phi, mode).accumulate(nq, orientations, query_points, query_orientations, n, nlist, qargs) once;
+// outputs: bin counts u32[n_theta * n_phi], bond order f32[n_theta * n_phi]
+int fref_bond_order(int mode, void* nq, const float* orientations, const float* qpts, const float* query_orientations,
+                    unsigned n_query, void* nlist_or_null, unsigned n_theta, unsigned n_phi, int query_mode,
+                    unsigned num_neighbors, float r_max, int exclude_ii, unsigned* bin_counts, float* bond_order)
+{
+    return guarded([&] {
+        auto* h = static_cast<QueryHandle*>(nq);
+        std::shared_ptr<NeighborList> nl;
+        if (nlist_or_null != nullptr)
+        {
+            nl = *static_cast<std::shared_ptr<NeighborList>*>(nlist_or_null);
+        }
+        QueryArgs const args = makeArgs(query_mode, num_neighbors, r_max, 0.0F, -1.0F, -1.0F, exclude_ii);
+        freud::environment::BondOrder bo(n_theta, n_phi, static_cast<freud::environment::BondOrderMode>(mode));
+        bo.accumulate(h->nq, reinterpret_cast<const quat<float>*>(orientations),
+                      reinterpret_cast<const vec3<float>*>(qpts), reinterpret_cast<const quat<float>*>(query_orientations),
+                      n_query, nl, args);
+        std::memcpy(bin_counts, bo.getBinCounts()->data(), size_t(n_theta) * n_phi * sizeof(unsigned));
+        std::memcpy(bond_order, bo.getBondOrder()->data(), size_t(n_theta) * n_phi * sizeof(float));
     });
 }
 

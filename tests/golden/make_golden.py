@@ -92,6 +92,7 @@ def main():
     pmftxy()
     periodic_buffer()
     pmft3()
+    bond_order()
 
 
 STEINHARDT_OPTIONS = {
@@ -231,6 +232,29 @@ def pmft3():
                                                                    exclude_ii=True)
     np.savez_compressed(os.path.join(HERE, "pmft3.npz"), **out)
     print("pmft3", {k: int(v.sum()) for k, v in out.items() if k.endswith("counts")})
+
+
+def bond_order():
+    """BondOrder (BondOrder.cc:30-153), all four modes over the 8 nearest neighbours of separate query points in a
+    triclinic box, and mode bod on a perfect FCC lattice (12 nearest neighbours), whose bond directions all sit on the
+    edges of an (8, 4) grid of bins -- there the bin hangs on the last place of libm's atan2f / acosf."""
+    out = {}
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 800, 41), random_points(box, 300, 42)
+    o, qo = pmft3_quats(800, 1), pmft3_quats(300, 2)
+    Q = ref.Query("aabb", box, pts)
+    for mode in ("bod", "lbod", "obcd", "oocd"):
+        out[f"tri_{mode}_counts"], out[f"tri_{mode}_bo"] = ref.bond_order(mode, Q, o, q, qo, (12, 9), mode="nearest",
+                                                                            num_neighbors=8)
+    box, pts = data.UnitCell.fcc().generate_system(4)
+    ident = np.tile(np.float32([1, 0, 0, 0]), (len(pts), 1))
+    Q = ref.Query("aabb", box, pts)
+    for bins in ((8, 4), (7, 5)):
+        tag = f"fcc_{bins[0]}x{bins[1]}"
+        out[f"{tag}_counts"], out[f"{tag}_bo"] = ref.bond_order("bod", Q, ident, pts, ident, bins, mode="nearest",
+                                                                  num_neighbors=12, exclude_ii=True)
+    np.savez_compressed(os.path.join(HERE, "bond_order.npz"), **out)
+    print("bond order", {k: int(v.sum()) for k, v in out.items() if k.endswith("counts")})
 
 
 PBUFF_BOXES = {"cube": Box.cube(5), "tri": Box(4, 5, 6, 0.3, -0.2, 0.1), "tilt2d": Box(4, 5, 0, 0.25, 0, 0, is2D=True)}

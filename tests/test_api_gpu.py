@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from freud_b200 import data, density, locality, order, pmft
+from freud_b200 import data, density, environment, locality, order, pmft
 from freud_b200.box import Box
 from oracle import port, ref
 from tests.util import BOXES, bits, random_points
@@ -321,6 +321,67 @@ def test_pmft3_matches_the_port_at_scale():
                                                            neighbors=dict(mode="ball", r_max=2.5))
     want, want_pcf = port.pmft3(port.PMFT_XYZ, box, len(pts), nl, None, quats, (2.0, 2.0, 2.0), (24, 20, 16), equiv=equiv)
     assert np.array_equal(xyz.bin_counts, want) and np.array_equal(bits(xyz._pcf), bits(want_pcf))
+
+
+def test_bond_order_api():
+    """freud.environment.BondOrder (tests/test_environment_BondOrder.py upstream): bin counts and the diagram bit for bit
+    against the reference's committed outputs in all four modes, the FCC lattice whose bond directions sit on bin edges
+    (the host's libm decides those), reset=False, default orientations, properties, errors."""
+    from tests.golden.make_golden import pmft3_quats
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bond_order.npz"))
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 800, 41), random_points(box, 300, 42)
+    o, qo = pmft3_quats(800, 1), pmft3_quats(300, 2)
+    knn = dict(mode="nearest", num_neighbors=8)
+    for mode in ("bod", "lbod", "obcd", "oocd"):
+        bo = environment.BondOrder((12, 9), mode=mode)
+        bo.compute((box, pts), o, query_points=q, query_orientations=qo, neighbors=knn)
+        assert np.array_equal(bo.bin_counts, gold[f"tri_{mode}_counts"]), mode
+        assert np.array_equal(bits(bo.bond_order), bits(gold[f"tri_{mode}_bo"])), mode
+        assert bo.mode == mode and bo.nbins == (12, 9) and bo.box == box
+    bo.compute((box, pts), o, query_points=q, query_orientations=qo, neighbors=knn, reset=False)  # two equal frames
+    assert np.array_equal(bo.bin_counts, 2 * gold["tri_oocd_counts"])
+    assert np.array_equal(bits(bo.bond_order), bits(gold["tri_oocd_bo"]))
+    assert bo.bounds == [(0.0, float(np.float32(2 * np.pi))), (0.0, float(np.float32(np.pi)))]
+    assert [len(e) for e in bo.bin_edges] == [13, 10] and [len(c) for c in bo.bin_centers] == [12, 9]
+    ident = np.tile(np.float32([1, 0, 0, 0]), (300, 1))  # default orientations are identities, one per point
+    plain = environment.BondOrder((12, 9)).compute((box, pts), query_points=q, query_orientations=ident, neighbors=knn)
+    assert np.array_equal(plain.bin_counts, gold["tri_bod_counts"])
+    with pytest.raises(ValueError):  # as upstream: query_orientations default to orientations, whose length differs
+        environment.BondOrder((12, 9)).compute((box, pts), query_points=q, neighbors=knn)
+    nlist = locality.AABBQuery(box, pts).query(q, knn).toNeighborList()
+    from_list = environment.BondOrder((12, 9), mode="lbod").compute((box, pts), o, query_points=q, query_orientations=qo,
+                                                                    neighbors=nlist)
+    assert np.array_equal(from_list.bin_counts, gold["tri_lbod_counts"])
+    fbox, fpts = data.UnitCell.fcc().generate_system(4)
+    for bins in ((8, 4), (7, 5)):
+        fcc = environment.BondOrder(bins).compute((fbox, fpts), neighbors=dict(mode="nearest", num_neighbors=12))
+        assert np.array_equal(fcc.bin_counts, gold[f"fcc_{bins[0]}x{bins[1]}_counts"])
+        assert np.array_equal(bits(fcc.bond_order), bits(gold[f"fcc_{bins[0]}x{bins[1]}_bo"]))
+        assert fcc.host_binned_bonds > 0
+    with pytest.raises(NotImplementedError):
+        environment.BondOrder(4).compute((box, pts))
+    with pytest.raises(ValueError):
+        environment.BondOrder((1, 4))
+    with pytest.raises(ValueError):
+        environment.BondOrder(4, mode="nope")
+    with pytest.raises(ValueError):
+        environment.BondOrder(4).compute((box, pts), o[:10], neighbors=knn)
+
+
+def test_bond_order_matches_the_port_at_scale():
+    """100 k particles, bonds within r = 2 (1.5 M of them), mode obcd: counts bit for bit against oracle/port.c over the
+    same NeighborList; the host's share of the bins stays a sliver."""
+    from tests.golden.make_golden import pmft3_quats
+
+    box, pts = data.make_random_system(60.0, 100_000, seed=6)
+    o = pmft3_quats(len(pts), 3)
+    nl = port.ball_nlist(port.IMAGE, box, False, pts, pts, 2.0, exclude_ii=True)
+    bo = environment.BondOrder((48, 24), mode="obcd").compute((box, pts), o, neighbors=dict(mode="ball", r_max=2.0))
+    want, want_bo = port.bond_order("obcd", nl, o, o, (48, 24))
+    assert np.array_equal(bo.bin_counts, want) and np.array_equal(bits(bo.bond_order), bits(want_bo))
+    assert 0 < bo.host_binned_bonds < 5e-3 * len(nl.distances)
 
 
 def test_correlation_function_api():

@@ -391,6 +391,46 @@ def test_pmft3_over_a_neighbor_list(ctx):
             capi.DevicePMFT(ctx, kind, maxes, bins)
 
 
+def test_bond_order_over_a_neighbor_list(ctx):
+    """fgpu_bondorder_* (BondOrder.cc:100-153) over device NeighborLists against the committed outputs of the reference:
+    bin counts bit for bit in all four modes, on the FCC lattice whose bond directions sit on bin edges, accumulated over
+    two calls, with a histogram too large for shared memory; constructor errors."""
+    from freud_b200 import data
+    from freud_b200.box import Box
+    from tests.golden.make_golden import pmft3_quats
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "bond_order.npz"))
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 800, 41), random_points(box, 300, 42)
+    o, qo = pmft3_quats(800, 1), pmft3_quats(300, 2)
+    dp = capi.DevicePoints(ctx, box, pts)
+    for mode in ("bod", "lbod", "obcd", "oocd"):
+        bo = capi.DeviceBondOrder(ctx, 12, 9, mode)
+        bo.accumulate_nlist(dp.knn_query(q, 8), o, qo)
+        assert np.array_equal(bo.read(), gold[f"tri_{mode}_counts"]), mode
+        bo.accumulate_nlist(dp.knn_query(q, 8), o, qo)
+        assert np.array_equal(bo.read(), 2 * gold[f"tri_{mode}_counts"]), mode
+        bo.reset()
+        assert bo.read().sum() == 0
+    plain = capi.DeviceBondOrder(ctx, 12, 9)
+    plain.accumulate_nlist(dp.knn_query(q, 8))  # bod reads no orientations
+    assert np.array_equal(plain.read(), gold["tri_bod_counts"])
+    big = capi.DeviceBondOrder(ctx, 160, 80, "obcd")  # 51 KB of counters: global atomics
+    big.accumulate_nlist(dp.knn_query(q, 8), o, qo)
+    nl = port.knn_nlist(box, False, pts, q, 8)
+    assert np.array_equal(big.read(), port.bond_order("obcd", nl, o, qo, (160, 80))[0])
+    fbox, fpts = data.UnitCell.fcc().generate_system(4)
+    fdp = capi.DevicePoints(ctx, fbox, fpts)
+    for bins in ((8, 4), (7, 5)):
+        fcc = capi.DeviceBondOrder(ctx, *bins)
+        fcc.accumulate_nlist(fdp.knn_query(None, 12, exclude_ii=True))
+        assert np.array_equal(fcc.read(), gold[f"fcc_{bins[0]}x{bins[1]}_counts"]) and fcc.host_binned_bonds > 0
+    for n_theta, n_phi, mode in ((1, 4, "bod"), (4, 1, "bod"), (4, 4, "nope")):
+        with pytest.raises(ValueError):
+            capi.DeviceBondOrder(ctx, n_theta, n_phi, mode)
+
+
 def test_correlation_function_over_a_neighbor_list(ctx):
     """fgpu_corr_* (CorrelationFunction.cc:26-95) over device NeighborLists against the committed outputs of the
     reference: bin counts identical, complex<double> sums to double rounding; accumulation over two calls."""

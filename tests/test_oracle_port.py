@@ -224,6 +224,29 @@ def test_port_pmft3_matches_golden():
     same(port.pmft3(port.PMFT_R12, box, len(pts), nl, th, th, (3.0,), (6, 8, 8)), "lattice_r12")
 
 
+def test_port_bond_order_matches_golden():
+    """BondOrder restated in oracle/port.c against outputs of the reference (tests/golden/bond_order.npz): bin counts and
+    the diagram bit for bit (same libm), all four modes and the FCC lattice whose bond directions sit on bin edges."""
+    from tests.golden.make_golden import pmft3_quats
+
+    gold = np.load(os.path.join(GOLD, "bond_order.npz"))
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 800, 41), random_points(box, 300, 42)
+    o, qo = pmft3_quats(800, 1), pmft3_quats(300, 2)
+    nl = port.knn_nlist(box, False, pts, q, 8)
+    for mode in ("bod", "lbod", "obcd", "oocd"):
+        counts, bo = port.bond_order(mode, nl, o, qo, (12, 9))
+        assert np.array_equal(counts, gold[f"tri_{mode}_counts"]), mode
+        assert np.array_equal(bits(bo), bits(gold[f"tri_{mode}_bo"])), mode
+    box, pts = data.UnitCell.fcc().generate_system(4)
+    ident = np.tile(np.float32([1, 0, 0, 0]), (len(pts), 1))
+    nl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True)
+    for bins in ((8, 4), (7, 5)):
+        counts, bo = port.bond_order("bod", nl, ident, ident, bins)
+        assert np.array_equal(counts, gold[f"fcc_{bins[0]}x{bins[1]}_counts"])
+        assert np.array_equal(bits(bo), bits(gold[f"fcc_{bins[0]}x{bins[1]}_bo"]))
+
+
 def test_port_wigner3j_known_values():
     """(0 0 0; 0 0 0) = 1; (1 1 1; m1 m2 m3) = +-1/sqrt(6) or 0 in the table order of Wigner3j.cc:43-55; and, where
     the reference is present, every tabulated l <= 20 as float."""
