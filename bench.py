@@ -385,6 +385,141 @@ def cpu_reference_pmftxy(box, pts, angles, x_max, y_max, bins, budget_s=12.0, th
                       f"query points in {dt:.2f} s"}
 
 
+HIST_CLIENTS = ("pmftxyz", "pmftxyt", "pmftr12", "bond_order")
+
+
+def hist_client_inputs(name, n, seed):
+    """Synthetic input of the four histogram clients of SURVEY.md section 8f rank 3 that came last: the 2-D system of
+    config 5 with random angles (PMFTXYT, PMFTR12), config 2's cubic system with random unit quaternions (PMFTXYZ), and
+    config 3's noisy FCC lattice (BondOrder, mode bod, 12 nearest neighbours).  Shared by both bench arms."""
+    from freud_b200 import data
+
+    rs = np.random.RandomState(seed + 31)
+    if name in ("pmftxyt", "pmftr12"):
+        L = (n / 0.5) ** 0.5
+        box, pts = data.make_random_system(L, n, is2D=True, seed=seed)
+        orient = (rs.random_sample(n) * 2 * np.pi - np.pi).astype(np.float32)
+        if name == "pmftxyt":
+            spec = dict(kind=1, maxes=(4.0, 3.0), bins=(50, 50, 36), r_max=5.0,
+                        label=f"PMFTXYT x_max=4 y_max=3 bins=50x50x36 (ball query r=5, image flavour) N={n} 2-D square "
+                              f"L={L:.4f} areal density 0.5")
+        else:
+            spec = dict(kind=2, maxes=(5.0,), bins=(50, 36, 36), r_max=5.0,
+                        label=f"PMFTR12 r_max=5 bins=50x36x36 (ball query r=5, image flavour) N={n} 2-D square L={L:.4f} "
+                              f"areal density 0.5")
+    elif name == "pmftxyz":
+        L = (n / RHO) ** (1.0 / 3.0)
+        box, pts = data.make_random_system(L, n, seed=seed)
+        q = rs.normal(size=(n, 4))
+        orient = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+        spec = dict(kind=0, maxes=(2.0, 2.0, 2.0), bins=(40, 40, 40), r_max=float(np.sqrt(12.0)),
+                    label=f"PMFTXYZ x_max=y_max=z_max=2 bins=40^3, identity equivalent orientation (ball query r=3.464, "
+                          f"image flavour) N={n} cubic L={L:.4f} rho=0.08")
+    else:
+        m = max(2, round((n / 4) ** (1.0 / 3.0)))
+        box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=seed)
+        orient = None
+        spec = dict(kind=None, bins=(72, 36), k=12,
+                    label=f"BondOrder bins=72x36 mode=bod num_neighbors=12 FCC {m}^3x4={len(pts)} sigma=0.05")
+    return box, pts, orient, spec
+
+
+def workload_hist_client(ctx, rank, n, name):
+    """One frame of PMFTXYZ / PMFTXYT / PMFTR12 / BondOrder through the C ABI: cell list, neighbour search into a device
+    NeighborList, the histogram kernel over its bonds, bin counts back."""
+    from freud_b200 import _capi
+
+    box, pts, orient, spec = hist_client_inputs(name, n, rank)
+    n = len(pts)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+    keep = [keep0]
+    if orient is not None:
+        pin_o, keep1 = pinned_empty(orient.shape, np.float32)
+        pin_o[:] = orient
+        keep.append(keep1)
+    if name == "bond_order":
+        hist = _capi.DeviceBondOrder(ctx, spec["bins"][0], spec["bins"][1], "bod")
+        query = lambda d: d.knn_query(None, spec["k"], exclude_ii=True)
+        accumulate = lambda nl: hist.accumulate_nlist(nl)
+        kernel, r_build = "bond_order", None
+    else:
+        hist = _capi.DevicePMFT(ctx, spec["kind"], spec["maxes"], spec["bins"])
+        equiv = np.float32([[1, 0, 0, 0]])
+        query = lambda d: d.ball_query(None, IMAGE, spec["r_max"], 0.0, True)
+        accumulate = lambda nl: hist.accumulate_nlist(nl, pin_o, pin_o, equiv)
+        kernel, r_build = "pmft3", spec["r_max"]
+    n_bonds = query(dp).num_bonds
+
+    def step_dev():
+        hist.reset()
+        if r_build is not None:
+            dp.build_cells(r_build)
+        accumulate(query(dp))
+        return hist.read()
+
+    trace = []
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        hist.reset()
+        d = _capi.DevicePoints(ctx, box, pin_pts)
+        t1 = time.perf_counter()
+        nl = query(d)
+        t2 = time.perf_counter()
+        accumulate(nl)
+        t3 = time.perf_counter()
+        out = hist.read()
+        del nl, d
+        t4 = time.perf_counter()
+        if os.environ.get("FGPU_BENCH_TRACE"):
+            trace.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
+            if len(trace) == 22:
+                print("e2e phases (points, query, accumulate, read+free) ms:", trace, file=sys.stderr)
+        return out
+
+    nb = int(np.prod(spec["bins"]))
+    o_bytes = 0 if orient is None else orient.nbytes
+    algo = {kernel: 20 * n_bonds + 2 * o_bytes + 4 * nb, "pipeline": 16 * (n + n) + 2 * o_bytes + 4 * nb,
+            "search_nl": 16 * (n + n) + 16 * n_bonds + 8 * n, "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
+            "knn_select": (16 * 26 + 12 + 28 * 12) * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric=f"{name}_particles_per_sec",
+                config={"workload": spec["label"], "bonds_per_step": n_bonds}, h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
+                keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds})
+
+
+def cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=12.0, threads=None):
+    """The reference's PMFTXYZ / PMFTXYT / PMFTR12 / BondOrder (AABBQuery engine, all host threads) on a bounded sample of
+    query points."""
+    from oracle import ref
+
+    threads = threads or os.cpu_count()
+    ref.set_num_threads(threads)
+    if not ref.available():
+        return {"value": None, "unit": "particles/s", "cores": threads, "kind": "port", "sample": "unavailable"}
+    q = ref.Query("aabb", box, pts, is2d=box.is2D)
+    if name == "bond_order":
+        ident = np.tile(np.float32([1, 0, 0, 0]), (len(pts), 1))
+        run = lambda m: ref.bond_order("bod", q, ident, pts[:m], ident[:m], spec["bins"], mode="nearest",
+                                       num_neighbors=spec["k"], exclude_ii=True)
+    else:
+        equiv = np.float32([[1, 0, 0, 0]]) if spec["kind"] == 0 else None
+        run = lambda m: ref.pmft3(spec["kind"], q, None if spec["kind"] == 0 else orient, orient[:m], pts[:m],
+                                  spec["maxes"], spec["bins"], equiv=equiv, r_max=spec["r_max"], exclude_ii=True)
+    probe = 20000
+    t0 = time.perf_counter()
+    run(probe)
+    dt = time.perf_counter() - t0
+    m = int(min(len(pts), max(probe, probe * budget_s / max(dt, 1e-6) * 0.8)))
+    t0 = time.perf_counter()
+    run(m)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "particles/s", "cores": threads, "kind": "reference",
+            "sample": f"reference {spec['label'].split(' N=')[0].split(' FCC')[0]} via AABBQuery: first {m} of {len(pts)} "
+                      f"query points in {dt:.2f} s"}
+
+
 def cpu_reference_correlation(box, pts, values, bins, r_max, budget_s=12.0, threads=None):
     """The reference's CorrelationFunction (AABBQuery engine, all host threads) on a bounded sample of query points."""
     from oracle import ref
@@ -531,7 +666,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy"])
+    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy", "pmftxyz", "pmftxyt", "pmftr12", "bond_order"])
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -541,7 +676,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
-                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000, "pmftxy": 1_000_000}[args.workload]
+                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000, "pmftxy": 1_000_000, "pmftxyz": 1_000_000, "pmftxyt": 1_000_000,
+                 "pmftr12": 1_000_000, "bond_order": 1_000_188}[args.workload]
     n = args.n or n_default
 
     if args.impl == "reference":
@@ -581,6 +717,9 @@ def main():
         scaling = "weak"
     elif args.workload == "pmftxy":
         w = workload_pmftxy(ctx, rank, n)
+        scaling = "weak"
+    elif args.workload in HIST_CLIENTS:
+        w = workload_hist_client(ctx, rank, n, args.workload)
         scaling = "weak"
     elif args.workload == "rdf4m":
         w = workload_rdf4m(ctx, rank, world, n, comm)
@@ -625,7 +764,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy")
+             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy", "pmft3", "bond_order", "pmft_add_bins")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]
@@ -647,10 +786,13 @@ def main():
         w["step_e2e"]()
     barrier()
     t0 = time.perf_counter()
+    e2e_marks = [t0]
     for _ in range(args.steps):
-        w["step_e2e"]()
+        w["step_e2e"]()  # returns once the step's result is on the host
+        e2e_marks.append(time.perf_counter())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_steps_ms = np.diff(e2e_marks) * 1e3
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -690,6 +832,8 @@ def main():
                        timing="CUDA events on the library's stream, max over ranks"),
         "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(w["h2d"]),
                 "d2h_bytes_per_step": int(w["d2h"]), "ms_per_step": e2e_s * 1e3 / args.steps,
+                "ms_per_step_min_median_max": [round(float(x), 3) for x in (e2e_steps_ms.min(), np.median(e2e_steps_ms),
+                                                                            e2e_steps_ms.max())],
                 "host_buffers": "pinned"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
@@ -716,6 +860,8 @@ def main():
             elif args.workload == "pmftxy":
                 line["cpu_baseline"] = cpu_reference_pmftxy(w["box"], w["pts"], w["angles"], w["x_max"], w["y_max"],
                                                             w["bins"])
+            elif args.workload in HIST_CLIENTS:
+                line["cpu_baseline"] = cpu_reference_hist_client(args.workload, w["box"], w["pts"], w["orient"], w["spec"])
             else:
                 line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
@@ -853,6 +999,12 @@ def run_reference_arm(args, rank, world, n):
                 for _ in range(steps)]
         metric, unit = "pmftxy_particles_per_sec", "particles/s"
         config = {"workload": f"PMFTXY x_max=4 y_max=3 bins=100x100 N={n} 2-D square L={L:.4f} areal density 0.5"}
+    elif args.workload in HIST_CLIENTS:
+        box, pts, orient, spec = hist_client_inputs(args.workload, n, 0)
+        runs = [cpu_reference_hist_client(args.workload, box, pts, orient, spec, budget_s=budget, threads=threads)
+                for _ in range(steps)]
+        metric, unit = f"{args.workload}_particles_per_sec", "particles/s"
+        config = {"workload": spec["label"]}
     elif args.workload == "correlation":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)

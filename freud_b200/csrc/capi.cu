@@ -284,6 +284,7 @@ std::unique_ptr<fgpu_nlist> new_nlist(fgpu_ctx* ctx, uint32_t n_query, uint32_t 
     nl->ctx = ctx;
     nl->n_query = n_query;
     nl->n_points = n_points;
+    nl->swap(ctx->spare_nlist); // the arrays the last destroyed list left behind (empty if none)
     nl->row_start.reserve((size_t) n_query + 1);
     nl->counts.reserve((size_t) n_query + 1);
     nl->segments.reserve((size_t) n_query + 1);
@@ -1365,6 +1366,10 @@ void fgpu_nlist_destroy(fgpu_nlist* nl)
     if (nl != nullptr)
     {
         bind_quiet(nl->ctx);
+        if (nl->bytes() > nl->ctx->spare_nlist.bytes())
+        {
+            nl->swap(nl->ctx->spare_nlist); // keep the larger set for the next list, free the smaller one
+        }
         delete nl;
     }
 }

@@ -5,6 +5,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/freud_b200.h"
@@ -57,6 +58,11 @@ template<typename T> struct DevBuf
         ptr = nullptr;
         cap = 0;
     }
+    void swap(DevBuf& other)
+    {
+        std::swap(ptr, other.ptr);
+        std::swap(cap, other.cap);
+    }
     // contents are NOT preserved on growth
     void reserve(size_t n)
     {
@@ -73,9 +79,39 @@ template<typename T> struct DevBuf
 
 } // namespace fgpu
 
+// The arrays of a NeighborList.  A destroyed list leaves them with its context (one spare set, the largest seen),
+// and the next list starts from them: a trajectory loop that drops each frame's list before the next query runs
+// without a single allocation per frame -- gigabyte-sized blocks otherwise come and go in the stream-ordered pool,
+// which now and then has to map fresh memory for them (tens to hundreds of milliseconds).
+struct NlistStorage
+{
+    fgpu::DevBuf<uint32_t> neighbors; // n_bonds x 2
+    fgpu::DevBuf<float> distances;
+    fgpu::DevBuf<float> weights;
+    fgpu::DevBuf<float> vectors;      // n_bonds x 3
+    fgpu::DevBuf<uint32_t> row_start; // n_query + 1 (exclusive scan; internal)
+    fgpu::DevBuf<uint32_t> counts;    // n_query
+    fgpu::DevBuf<uint32_t> segments;  // n_query (0 for empty rows, as upstream)
+    void swap(NlistStorage& o)
+    {
+        neighbors.swap(o.neighbors);
+        distances.swap(o.distances);
+        weights.swap(o.weights);
+        vectors.swap(o.vectors);
+        row_start.swap(o.row_start);
+        counts.swap(o.counts);
+        segments.swap(o.segments);
+    }
+    size_t bytes() const
+    {
+        return 4 * (neighbors.cap + distances.cap + weights.cap + vectors.cap + row_start.cap + counts.cap + segments.cap);
+    }
+};
+
 // ---- opaque handle definitions ----------------------------------------------------------------------
 struct fgpu_ctx
 {
+    NlistStorage spare_nlist;
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
@@ -174,19 +210,12 @@ struct fgpu_points
     int shard = 0, n_shards = 1; // > 1: this rank searches one share of the home tiles (self-query RDF only)
 };
 
-struct fgpu_nlist
+struct fgpu_nlist : NlistStorage
 {
     fgpu_ctx* ctx = nullptr;
     uint64_t n_bonds = 0;
     uint32_t n_query = 0;
     uint32_t n_points = 0;
-    fgpu::DevBuf<uint32_t> neighbors; // n_bonds x 2
-    fgpu::DevBuf<float> distances;
-    fgpu::DevBuf<float> weights;
-    fgpu::DevBuf<float> vectors;     // n_bonds x 3
-    fgpu::DevBuf<uint32_t> row_start; // n_query + 1 (exclusive scan; internal)
-    fgpu::DevBuf<uint32_t> counts;    // n_query
-    fgpu::DevBuf<uint32_t> segments;  // n_query (0 for empty rows, as upstream)
 };
 
 struct fgpu_rdf
