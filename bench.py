@@ -337,7 +337,7 @@ def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
     pin_pts[:] = pts
 
     def step_dev():
-        # the orientations (4 MB) are taken from the host in every call: cos / sin are evaluated there (host libm)
+        # the orientations (4 MB) are taken from the host in every call
         pm.reset()
         dp.build_cells(r_max)
         pm.accumulate_nlist(dp.ball_query(None, IMAGE, r_max, 0.0, True), angles)
@@ -353,7 +353,7 @@ def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
     nb = bins[0] * bins[1]
     algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
             "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
-            "pmftxy": 20 * n_bonds + 8 * n + 4 * nb,  # (i, v.x, v.y, v.z stride) per bond + (cos, sin) per query
+            "pmft3": 20 * n_bonds + 4 * n + 4 * nb,  # (i, v.x, v.y, v.z stride) per bond + the angle per query
             "pipeline": 16 * (n + n) + 8 * n + 4 * nb}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="pmftxy_particles_per_sec",
                 config={"workload": f"PMFTXY x_max={x_max:g} y_max={y_max:g} bins={bins[0]}x{bins[1]} (ball query "

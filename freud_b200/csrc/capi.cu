@@ -1494,138 +1494,8 @@ static AxisDev regular_axis(uint32_t bins, float lo, float hi)
     return a;
 }
 
-int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, uint32_t n_y, fgpu_pmftxy** out)
-{
-    return guarded([&] {
-        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
-        // PMFTXY.cc:27-42
-        require(n_x >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in X.");
-        require(n_y >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in Y.");
-        require(!(x_max < 0), FGPU_EINVALID, "PMFTXY requires that x_max must be positive.");
-        require(!(y_max < 0), FGPU_EINVALID, "PMFTXY requires that y_max must be positive.");
-        require((uint64_t) n_x * n_y < (1ULL << 31), FGPU_EINVALID, "PMFTXY histogram too large");
-        bind_device(ctx);
-        std::unique_ptr<fgpu_pmftxy> p(new fgpu_pmftxy());
-        p->ctx = ctx;
-        p->ax = regular_axis(n_x, -x_max, x_max);
-        p->ay = regular_axis(n_y, -y_max, y_max);
-        p->hist.reserve((size_t) n_x * n_y);
-        FGPU_CUDA_CHECK(cudaMemsetAsync(p->hist.ptr, 0, (size_t) n_x * n_y * sizeof(uint32_t), ctx->stream));
-        sync(ctx);
-        *out = p.release();
-    });
-}
-
-void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft)
-{
-    if (pmft != nullptr)
-    {
-        bind_quiet(pmft->ctx);
-        delete pmft;
-    }
-}
-
-int fgpu_pmftxy_reset(fgpu_pmftxy* pmft)
-{
-    return guarded([&] {
-        require(pmft != nullptr, FGPU_EINVALID, "null argument");
-        bind_device(pmft->ctx);
-        FGPU_CUDA_CHECK(cudaMemsetAsync(pmft->hist.ptr, 0, (size_t) pmft->ax.bins * pmft->ay.bins * sizeof(uint32_t),
-                                        pmft->ctx->stream));
-    });
-}
-
-int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host)
-{
-    return guarded([&] {
-        require(pmft != nullptr && nl != nullptr && query_orientations_host != nullptr, FGPU_EINVALID, "null argument");
-        require(pmft->ctx == nl->ctx, FGPU_EINVALID, "pmft and nlist belong to different contexts");
-        fgpu_ctx* ctx = pmft->ctx;
-        bind_device(ctx);
-        // rotmat2<float>::fromAngle(-theta), VectorMath.h:912-921: std::cos / std::sin of a float, i.e. the host
-        // libm's cosf / sinf -- evaluated here, on the host, because CUDA's differ from them in the last ulp
-        std::vector<float> cs(2 * (size_t) nl->n_query);
-        auto fill = [&](uint32_t lo, uint32_t hi) {
-            for (uint32_t i = lo; i < hi; ++i)
-            {
-                float const t = -query_orientations_host[i];
-                cs[2 * (size_t) i] = std::cos(t);
-                cs[2 * (size_t) i + 1] = std::sin(t);
-            }
-        };
-        // two libm calls per query point on one core cost more than the whole GPU frame: spread them over the host
-        unsigned const hw = std::max(1U, std::min(32U, std::thread::hardware_concurrency()));
-        unsigned const n_threads = nl->n_query >= 65536 ? hw : 1U;
-        if (n_threads == 1)
-        {
-            fill(0, nl->n_query);
-        }
-        else
-        {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < n_threads; ++t)
-            {
-                uint32_t const lo = (uint32_t) ((uint64_t) nl->n_query * t / n_threads);
-                uint32_t const hi = (uint32_t) ((uint64_t) nl->n_query * (t + 1) / n_threads);
-                pool.emplace_back(fill, lo, hi);
-            }
-            for (auto& th : pool)
-            {
-                th.join();
-            }
-        }
-        const float* cos_sin_host = cs.data();
-        pmft->cos_sin.reserve(2 * (size_t) nl->n_query + 2);
-        h2d(ctx, pmft->cos_sin.ptr, cos_sin_host, 2 * (size_t) nl->n_query * sizeof(float));
-        launch_pmftxy(ctx, nl->neighbors.ptr, nl->vectors.ptr, nl->n_bonds, pmft->cos_sin.ptr, pmft->ax, pmft->ay,
-                      pmft->hist.ptr);
-        sync(ctx); // the caller's array was consumed
-    });
-}
-
-int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host)
-{
-    return guarded([&] {
-        require(pmft != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
-        bind_device(pmft->ctx);
-        d2h(pmft->ctx, counts_host, pmft->hist.ptr, (size_t) pmft->ax.bins * pmft->ay.bins * sizeof(uint32_t));
-        sync(pmft->ctx);
-    });
-}
-
 // ---- PMFTXYZ / PMFTXYT / PMFTR12 ----------------------------------------------------------------------------------
 namespace {
-
-// (cos, sin)(-theta) of every query point with the host libm, spread over the host threads (see fgpu_pmftxy)
-std::vector<float> host_cos_sin(const float* theta, uint32_t n)
-{
-    std::vector<float> cs(2 * (size_t) n);
-    auto fill = [&](uint32_t lo, uint32_t hi) {
-        for (uint32_t i = lo; i < hi; ++i)
-        {
-            float const t = -theta[i];
-            cs[2 * (size_t) i] = std::cos(t);
-            cs[2 * (size_t) i + 1] = std::sin(t);
-        }
-    };
-    unsigned const hw = std::max(1U, std::min(32U, std::thread::hardware_concurrency()));
-    unsigned const n_threads = n >= 65536 ? hw : 1U;
-    if (n_threads == 1)
-    {
-        fill(0, n);
-        return cs;
-    }
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < n_threads; ++t)
-    {
-        pool.emplace_back(fill, (uint32_t) ((uint64_t) n * t / n_threads), (uint32_t) ((uint64_t) n * (t + 1) / n_threads));
-    }
-    for (auto& th : pool)
-    {
-        th.join();
-    }
-    return cs;
-}
 
 // RegularAxis::bin (Histogram.h:152-173) on the host; -1 = outside
 int host_axis_bin(const AxisDev& a, float value)
@@ -1656,7 +1526,8 @@ int fgpu_pmft_create(fgpu_ctx* ctx, int kind, float max0, float max1, float max2
 {
     return guarded([&] {
         require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
-        require(kind == FGPU_PMFT_XYZ || kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_R12, FGPU_EINVALID, "unknown PMFT kind");
+        require(kind == FGPU_PMFT_XYZ || kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_R12 || kind == FGPU_PMFT_XY,
+                FGPU_EINVALID, "unknown PMFT kind");
         float const two_pi = (float) (2.0 * M_PI);
         std::unique_ptr<fgpu_pmft> p(new fgpu_pmft());
         p->ctx = ctx;
@@ -1672,6 +1543,17 @@ int fgpu_pmft_create(fgpu_ctx* ctx, int kind, float max0, float max1, float max2
             p->a0 = regular_axis(n0, -max0, max0);
             p->a1 = regular_axis(n1, -max1, max1);
             p->a2 = regular_axis(n2, -max2, max2);
+        }
+        else if (kind == FGPU_PMFT_XY) // PMFTXY.cc:27-42; the third axis is a single bin that every bond falls into
+        {
+            require(n0 >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in X.");
+            require(n1 >= 1, FGPU_EINVALID, "PMFTXY requires at least 1 bin in Y.");
+            require(!(max0 < 0), FGPU_EINVALID, "PMFTXY requires that x_max must be positive.");
+            require(!(max1 < 0), FGPU_EINVALID, "PMFTXY requires that y_max must be positive.");
+            p->a0 = regular_axis(n0, -max0, max0);
+            p->a1 = regular_axis(n1, -max1, max1);
+            p->a2 = regular_axis(1, 0.0f, 1.0f);
+            n2 = 1;
         }
         else if (kind == FGPU_PMFT_XYT) // PMFTXYT.cc:30-49
         {
@@ -1739,7 +1621,6 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
         a.a1 = pmft->a1;
         a.a2 = pmft->a2;
         a.hist = pmft->hist.ptr;
-        std::vector<float> cs;
         if (kind == FGPU_PMFT_XYZ)
         {
             require(equiv_orientations_host != nullptr && n_equiv >= 1, FGPU_EINVALID,
@@ -1754,23 +1635,16 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
         }
         else
         {
-            require(orientations_host != nullptr, FGPU_EINVALID, "null orientations");
-            pmft->stage_b.reserve((size_t) n_points + 1);
-            h2d(ctx, pmft->stage_b.ptr, orientations_host, (size_t) n_points * sizeof(float));
-            a.orientations = pmft->stage_b.ptr;
-            if (kind == FGPU_PMFT_XYT)
+            if (kind != FGPU_PMFT_XY)
             {
-                cs = host_cos_sin(query_orientations_host, nl->n_query); // rotmat2::fromAngle, VectorMath.h:912-921
-                pmft->stage_a.reserve(2 * (size_t) nl->n_query + 2);
-                h2d(ctx, pmft->stage_a.ptr, cs.data(), cs.size() * sizeof(float));
-                a.cos_sin = reinterpret_cast<const float2*>(pmft->stage_a.ptr);
+                require(orientations_host != nullptr, FGPU_EINVALID, "null orientations");
+                pmft->stage_b.reserve((size_t) n_points + 1);
+                h2d(ctx, pmft->stage_b.ptr, orientations_host, (size_t) n_points * sizeof(float));
+                a.orientations = pmft->stage_b.ptr;
             }
-            else
-            {
-                pmft->stage_a.reserve((size_t) nl->n_query + 1);
-                h2d(ctx, pmft->stage_a.ptr, query_orientations_host, (size_t) nl->n_query * sizeof(float));
-                a.query_orientations = pmft->stage_a.ptr;
-            }
+            pmft->stage_a.reserve((size_t) nl->n_query + 1);
+            h2d(ctx, pmft->stage_a.ptr, query_orientations_host, (size_t) nl->n_query * sizeof(float));
+            a.query_orientations = pmft->stage_a.ptr;
         }
         std::vector<uint4> rec;
         std::vector<float> rec_dist;
@@ -1824,14 +1698,19 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
                 std::memcpy(&vx, &rec[r].z, sizeof(float));
                 std::memcpy(&vy, &rec[r].w, sizeof(float));
                 int c0, c1, c2;
-                if (kind == FGPU_PMFT_XYT)
+                if (kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_XY)
                 {
-                    float const c = cs[2 * (size_t) i], sn = cs[2 * (size_t) i + 1];
+                    float const t = -query_orientations_host[i]; // rotmat2::fromAngle, VectorMath.h:912-921
+                    float const c = std::cos(t), sn = std::sin(t);
                     volatile float x1 = c * vx, x2 = -sn * vy, y1 = sn * vx, y2 = c * vy;
                     c0 = host_axis_bin(a.a0, x1 + x2);
                     c1 = host_axis_bin(a.a1, y1 + y2);
-                    float const d_theta = std::atan2(-vy, -vx); // PMFTXYT.cc:94
-                    c2 = host_axis_bin(a.a2, host_mod_two_pi(orientations_host[j] - d_theta));
+                    c2 = 0;
+                    if (kind == FGPU_PMFT_XYT)
+                    {
+                        float const d_theta = std::atan2(-vy, -vx); // PMFTXYT.cc:94
+                        c2 = host_axis_bin(a.a2, host_mod_two_pi(orientations_host[j] - d_theta));
+                    }
                 }
                 else
                 {
@@ -1875,6 +1754,48 @@ int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds)
         require(pmft != nullptr && bonds != nullptr, FGPU_EINVALID, "null argument");
         *bonds = pmft->deferred_total;
     });
+}
+
+// ---- PMFTXY: the two-axis histogram is the XY kind of fgpu_pmft ------------------------------------------------
+int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, uint32_t n_y, fgpu_pmftxy** out)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
+        fgpu_pmft* inner = nullptr;
+        int const rc = fgpu_pmft_create(ctx, FGPU_PMFT_XY, x_max, y_max, 0.0f, n_x, n_y, 1, &inner);
+        if (rc != FGPU_OK)
+        {
+            throw Error(rc, fgpu_last_error());
+        }
+        std::unique_ptr<fgpu_pmftxy> p(new fgpu_pmftxy());
+        p->inner = inner;
+        *out = p.release();
+    });
+}
+
+void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft)
+{
+    if (pmft != nullptr)
+    {
+        fgpu_pmft_destroy(pmft->inner);
+        delete pmft;
+    }
+}
+
+int fgpu_pmftxy_reset(fgpu_pmftxy* pmft)
+{
+    return pmft == nullptr ? fgpu_pmft_reset(nullptr) : fgpu_pmft_reset(pmft->inner);
+}
+
+int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host)
+{
+    return fgpu_pmft_accumulate_nlist(pmft == nullptr ? nullptr : pmft->inner, nl, nullptr, 0, query_orientations_host,
+                                      nullptr, 0);
+}
+
+int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host)
+{
+    return fgpu_pmft_read(pmft == nullptr ? nullptr : pmft->inner, counts_host);
 }
 
 // ---- BondOrder ----------------------------------------------------------------------------------------------------

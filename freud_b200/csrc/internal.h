@@ -225,12 +225,10 @@ struct fgpu_rdf
     fgpu::DevBuf<uint32_t> hist;
 };
 
+struct fgpu_pmft;
 struct fgpu_pmftxy
 {
-    fgpu_ctx* ctx = nullptr;
-    fgpu::AxisDev ax, ay;
-    fgpu::DevBuf<uint32_t> hist;  // n_x * n_y, row-major (x slow)
-    fgpu::DevBuf<float> cos_sin;  // staged per call: (cos, sin)(-theta) per query point
+    fgpu_pmft* inner = nullptr; // kind FGPU_PMFT_XY
 };
 
 struct fgpu_pmft
@@ -514,8 +512,7 @@ struct KnnSelectArgs
 void launch_knn_select(fgpu_ctx* ctx, int sort_by_distance, const KnnSelectArgs& a);
 
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist);
-void launch_pmftxy(fgpu_ctx* ctx, const uint32_t* neighbors, const float* vectors, uint64_t n_bonds, const float* cos_sin,
-                   AxisDev ax, AxisDev ay, uint32_t* hist);
+#define FGPU_PMFT_XY 3 // internal: PMFTXY as a three-axis histogram whose last axis has one bin (fgpu_pmftxy_*)
 struct Pmft3Args
 {
     AxisDev a0, a1, a2;
@@ -523,9 +520,8 @@ struct Pmft3Args
     const float* vectors;
     const float* distances;
     uint64_t n_bonds;
-    const float2* cos_sin;           // XYT: per query point
     const float* orientations;       // XYT, R12: per point
-    const float* query_orientations; // R12: per query point
+    const float* query_orientations; // XY, XYT, R12: per query point
     const float4* query_quats;       // XYZ: per query point, (s, x, y, z)
     const float4* equiv_quats;       // XYZ
     uint32_t n_equiv;

@@ -6,8 +6,9 @@
 //
 //   XYZ  the bond vector rotated by conj(q_i) and then by every equivalent orientation, all in the reference's float
 //        operation order (VectorMath.h:810-818) -> three RegularAxis bins.  Pure float arithmetic: bit-exact counts.
-//   XYT  (x, y) rotated by -theta_i with the host libm's (cos, sin) as in PMFTXY, and the angle
-//        t = modulusPositive(theta_j - atan2f(-dy, -dx), 2 pi).
+//   XY   freud::pmft::PMFTXY (PMFTXY.cc:65-87): (x, y) = rotmat2(-theta_i) * (dx, dy) on two RegularAxis; the third
+//        axis has one bin.
+//   XYT  the same (x, y), and the angle t = modulusPositive(theta_j - atan2f(-dy, -dx), 2 pi).
 //   R12  r = bond distance, t1 = modulusPositive(theta_j - atan2f(dy, dx), 2 pi),
 //        t2 = modulusPositive(theta_i - atan2f(-dy, -dx), 2 pi).
 //
@@ -17,6 +18,9 @@
 // every bin edge than any last-place difference can move it (kAngleMargin, several times libm's error bound plus
 // the rounding of the chain).  The few bonds inside a margin (~3 in 10^4) are written to a list and binned by the
 // host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per bond.
+// cosf / sinf of the query particle's angle (rotmat2::fromAngle, VectorMath.h:912-921) get the same treatment: double
+// sincos rounded to float, and the rotated coordinate must clear every bin edge by more than a last-place change of
+// (cos, sin) can move it -- the host evaluates libm only for the bonds that do not (it used to for every particle).
 #include "internal.h"
 #include "pair_math.cuh"
 
@@ -45,6 +49,36 @@ __device__ __forceinline__ int angle_bin(const AxisDev& axis, float orientation,
     // near 0 or 2 pi the wrap of the modulus sits on a bin edge too; a NaN orientation is never sure
     *sure = frac > margin && frac < 1.0f - margin && t > kAngleMargin && t < kTwoPi - kAngleMargin;
     return axis_bin(axis, t);
+}
+
+// Bin of `value` on a RegularAxis when `value` is only known to +-slack: *sure = false if some value within the slack
+// falls into another bin (or on the other side of an end of the axis).
+__device__ __forceinline__ int slack_bin(const AxisDev& axis, float value, float slack, bool* sure)
+{
+    float const u = (value - axis.r_min) * axis.inv_width;
+    float const m = slack * axis.inv_width + 1.0e-6f * (fabsf(u) + 1.0f);
+    float const n = (float) axis.bins;
+    if (u < -m || u > n + m)
+    {
+        return -1; // outside for every value within the slack
+    }
+    float const frac = u - floorf(u);
+    bool const clear = frac > m && frac < 1.0f - m && u > m && u < n - m;
+    *sure = *sure && clear;
+    int const bin = axis_bin(axis, value);
+    return clear ? bin : max(bin, 0); // not clear: the host decides, also whether the bond is inside at all
+}
+
+// (x, y) = rotmat2::fromAngle(-theta) * (vx, vy), VectorMath.h:912-936, with (cos, sin) from double sincos; the slack
+// of the result for a last-place (and then some) difference to libm's cosf / sinf
+__device__ __forceinline__ void rotate_xy(float theta, float vx, float vy, float& rx, float& ry, float& slack)
+{
+    double sd, cd;
+    sincos((double) -theta, &sd, &cd);
+    float const c = (float) cd, sn = (float) sd;
+    rx = __fadd_rn(__fmul_rn(c, vx), __fmul_rn(-sn, vy));
+    ry = __fadd_rn(__fmul_rn(sn, vx), __fmul_rn(c, vy));
+    slack = 1.0e-6f * (fabsf(vx) + fabsf(vy)); // 4 ulp of (cos, sin) move a coordinate by < 5e-7 (|vx| + |vy|)
 }
 
 // rotate(q, v), VectorMath.h:810-818: (s^2 - v.v) b + (2 s) (v x b) + (2 v.b) v, one rounding per operation
@@ -105,14 +139,19 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
         }
         bool sure = true;
         int b0, b1, b2;
-        if (KIND == FGPU_PMFT_XYT)
+        if (KIND == FGPU_PMFT_XYT || KIND == FGPU_PMFT_XY)
         {
-            float2 const cs = a.cos_sin[ij.x];
-            float const rx = __fadd_rn(__fmul_rn(cs.x, vx), __fmul_rn(-cs.y, vy)); // rotmat2 * v, VectorMath.h:929-936
-            float const ry = __fadd_rn(__fmul_rn(cs.y, vx), __fmul_rn(cs.x, vy));
-            b0 = axis_bin(a.a0, rx);
-            b1 = axis_bin(a.a1, ry);
-            b2 = angle_bin(a.a2, a.orientations[ij.y], -vy, -vx, &sure);
+            float rx, ry, slack;
+            rotate_xy(a.query_orientations[ij.x], vx, vy, rx, ry, slack);
+            b0 = slack_bin(a.a0, rx, slack, &sure);
+            b1 = slack_bin(a.a1, ry, slack, &sure);
+            b2 = 0;
+            if (KIND == FGPU_PMFT_XYT && b0 >= 0 && b1 >= 0)
+            {
+                bool sure_t = true;
+                b2 = angle_bin(a.a2, a.orientations[ij.y], -vy, -vx, &sure_t);
+                sure = sure && sure_t;
+            }
         }
         else
         {
@@ -122,9 +161,9 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
             b2 = angle_bin(a.a2, a.query_orientations[ij.x], -vy, -vx, &sure2);
             sure = sure1 && sure2;
         }
-        if (b0 < 0 || (KIND == FGPU_PMFT_XYT && b1 < 0))
+        if (b0 < 0 || (KIND != FGPU_PMFT_R12 && b1 < 0))
         {
-            continue; // outside an axis that does not involve atan2f: dropped whatever the angles are
+            continue; // surely outside an axis
         }
         if (sure)
         {
@@ -271,6 +310,9 @@ void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
             break;
         case FGPU_PMFT_XYT:
             k_pmft3<FGPU_PMFT_XYT><<<blocks, 256, dyn, ctx->stream>>>(a);
+            break;
+        case FGPU_PMFT_XY:
+            k_pmft3<FGPU_PMFT_XY><<<blocks, 256, dyn, ctx->stream>>>(a);
             break;
         default:
             k_pmft3<FGPU_PMFT_R12><<<blocks, 256, dyn, ctx->stream>>>(a);

@@ -483,71 +483,6 @@ void launch_segments(fgpu_ctx* ctx, const uint32_t* row_start, const uint32_t* c
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
-// PMFTXY::accumulate (freud/pmft/PMFTXY.cc:65-87) over a NeighborList: the bond vector rotated into the frame of its
-// query particle, rot = rotmat2::fromAngle(-theta_i) * (v.x, v.y) = (c v.x + (-s) v.y, s v.x + c v.y) with
-// (c, s) = (cos, sin)(-theta_i) (VectorMath.h:912-936), binned on RegularAxis(n_x, -x_max, x_max) x
-// RegularAxis(n_y, -y_max, y_max), linear index bx * n_y + by (Histogram.h:327-351).  (c, s) come from the HOST's
-// libm -- the one the reference calls -- so the rotated components, and with them the counts, are bit-identical.
-__global__ void __launch_bounds__(256) k_pmftxy(const uint32_t* __restrict__ neighbors, const float* __restrict__ vectors,
-                                                uint64_t n_bonds, const float2* __restrict__ cos_sin, AxisDev ax, AxisDev ay,
-                                                uint32_t* __restrict__ hist, int use_shared)
-{
-    extern __shared__ uint32_t pm_hist[];
-    uint32_t const n_bins = ax.bins * ay.bins;
-    if (use_shared)
-    {
-        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
-        {
-            pm_hist[b] = 0;
-        }
-        __syncthreads();
-    }
-    uint32_t* const h = use_shared ? pm_hist : hist;
-    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
-    {
-        uint32_t const i = neighbors[2 * k];
-        float const vx = vectors[3 * k], vy = vectors[3 * k + 1];
-        float2 const cs = cos_sin[i];
-        float const rx = __fadd_rn(__fmul_rn(cs.x, vx), __fmul_rn(-cs.y, vy)); // dot(row0, v), row0 = (c, -s)
-        float const ry = __fadd_rn(__fmul_rn(cs.y, vx), __fmul_rn(cs.x, vy));  // dot(row1, v), row1 = (s, c)
-        int const bx = axis_bin(ax, rx), by = axis_bin(ay, ry);
-        if (bx >= 0 && by >= 0)
-        {
-            atomicAdd(&h[(uint32_t) bx * ay.bins + (uint32_t) by], 1U);
-        }
-    }
-    if (use_shared)
-    {
-        __syncthreads();
-        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
-        {
-            if (pm_hist[b] != 0)
-            {
-                atomicAdd(&hist[b], pm_hist[b]);
-            }
-        }
-    }
-}
-
-void launch_pmftxy(fgpu_ctx* ctx, const uint32_t* neighbors, const float* vectors, uint64_t n_bonds, const float* cos_sin,
-                   AxisDev ax, AxisDev ay, uint32_t* hist)
-{
-    if (n_bonds == 0)
-    {
-        return;
-    }
-    size_t const smem = (size_t) ax.bins * ay.bins * sizeof(uint32_t);
-    int const use_shared = smem <= 40 * 1024 ? 1 : 0;
-    unsigned const blocks = (unsigned) std::min<uint64_t>((n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 8U);
-    {
-        KernelScope ks(ctx, "pmftxy");
-        k_pmftxy<<<blocks, 256, use_shared ? smem : 0, ctx->stream>>>(neighbors, vectors, n_bonds,
-                                                                      reinterpret_cast<const float2*>(cos_sin), ax, ay,
-                                                                      hist, use_shared);
-    }
-    FGPU_CUDA_CHECK(cudaGetLastError());
-}
-
 // CorrelationFunction::accumulate (freud/density/CorrelationFunction.cc:81-95) over a NeighborList: per bond the bin of
 // its distance (RegularAxis(bins, 0, r_max)), one count and conj(values[j]) * query_values[i] in complex<double>.
 // Block-shared accumulators (u32 + two doubles per bin) merged once per block; bins that do not fit shared memory

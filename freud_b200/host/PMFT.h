@@ -4,10 +4,10 @@
 // query_orientations, query_points, n_query_points, nlist /*nullable*/, qargs) (PMFTXY.cc:65-87), reset / getPCF
 // (freud/pmft/PMFT.h:36-49) and the BondHistogramCompute getters the bindings expose
 // (freud/locality/BondHistogramCompute.h:29-140).  The bonds are the list handed in or the query over the points,
-// materialised as a NeighborList on the device.  cos/sin of the orientations are evaluated on the host (inside
-// fgpu_pmftxy_accumulate_nlist) with the same libm the reference calls (rotmat2::fromAngle, VectorMath.h:912-921)
-// and the rotation + binning run on the GPU in the reference's float operation order: bit-identical bin counts; PMFT::reduce
-// (PMFT.h:73-83) is host float arithmetic in the same order.
+// materialised as a NeighborList on the device.  Rotation and binning run on the GPU in the reference's float
+// operation order; wherever libm (cosf / sinf / atan2f) could decide a bin by its last place the bond is handed to
+// the host's libm instead (csrc/pmft.cu): bit-identical bin counts.  PMFT::reduce (PMFT.h:73-83) is host float
+// arithmetic in the same order.
 #pragma once
 #include <cmath>
 #include <memory>

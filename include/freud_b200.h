@@ -83,7 +83,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, pmftxy, pmft3, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, pmft3, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -199,11 +199,12 @@ int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
 /* ---- PMFTXY ----------------------------------------------------------------------------------------------
  * Device half of freud::pmft::PMFTXY (freud/pmft/PMFTXY.cc:25-87): a u32[n_x][n_y] histogram of the bond vectors
  * of a NeighborList rotated into the frame of their query particle, resident across accumulate calls.
- * query_orientations_host[n_query] are angles in radians; cos and sin of their negatives are evaluated on the host
- * with libm's cosf / sinf -- what rotmat2::fromAngle calls upstream, VectorMath.h:912-921; CUDA's differ in the last
- * ulp -- so the rotation and the binning reproduce the reference's float arithmetic bit for bit and the counts are
- * identical.  Normalisation to the PCF (PMFT::reduce,
- * freud/pmft/PMFT.h:73-83) is host arithmetic in freud_b200/host/PMFT.h.
+ * query_orientations_host[n_query] are angles in radians.  The rotation uses cosf / sinf of the host libm upstream
+ * (rotmat2::fromAngle, VectorMath.h:912-921) and CUDA's differ from them in the last place: the kernel rotates with
+ * double sincos rounded to float and accepts a bin only when the rotated coordinate clears every bin edge by more
+ * than a last-place change of (cos, sin) can move it; the other bonds (a few in 10^4) are binned by the host with
+ * its libm (freud_b200/csrc/pmft.cu) -- the counts are identical to the reference's.  Normalisation to the PCF
+ * (PMFT::reduce, freud/pmft/PMFT.h:73-83) is host arithmetic in freud_b200/host/PMFT.h.
  * Errors: n_x, n_y < 1 or x_max, y_max < 0 -> FGPU_EINVALID (PMFTXY.cc:27-42). */
 int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, uint32_t n_y, fgpu_pmftxy** out);
 void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft);
@@ -221,9 +222,8 @@ int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host);
  *                  and `query_orientations[n_query]` are angles in radians; max2 is not read.
  *   FGPU_PMFT_R12  freud/pmft/PMFTR12.cc:28-113: axes r in [0, max0], t1 and t2 in [0, 2 pi); max1, max2 not read.
  * Bin counts are bit-identical to the reference's: the float arithmetic runs on the GPU in the reference's operation
- * order; cos/sin of the query angles (XYT) come from the host libm like fgpu_pmftxy's; the atan2f of the bond angle
- * (XYT, R12) is bracketed on the GPU and the few bonds whose bin could depend on libm's last place are binned by the
- * host (freud_b200/csrc/pmft.cu).  fgpu_pmft_deferred reports how many bonds took that route since the last reset.
+ * order; cosf / sinf of the query angles (XYT) and atan2f of the bond angle (XYT, R12) are bracketed on the GPU and
+ * the few bonds whose bin could depend on libm's last place are binned by the host (freud_b200/csrc/pmft.cu).  fgpu_pmft_deferred reports how many bonds took that route since the last reset.
  * Errors: a bin count < 1 or a negative maximum -> FGPU_EINVALID with the reference's messages; XYZ with n_equiv = 0
  * or null quaternions, XYT / R12 with null angles -> FGPU_EINVALID. */
 #define FGPU_PMFT_XYZ 0
