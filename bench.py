@@ -360,7 +360,7 @@ def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
                                     f"r={r_max:g}, image flavour) N={n} 2-D square L={L:.4f} areal density 0.5",
                         "bonds_per_step": n_bonds},
                 h2d=12 * n + 4 * n, d2h=4 * nb, algo=algo, keep=[keep0, keep1], box=box, pts=pts, angles=angles,
-                x_max=x_max, y_max=y_max, bins=bins, secondary={"bonds": n_bonds})
+                x_max=x_max, y_max=y_max, bins=bins, secondary={"bonds": n_bonds}, algo_per_step=True)
 
 
 def cpu_reference_pmftxy(box, pts, angles, x_max, y_max, bins, budget_s=12.0, threads=None):
@@ -486,7 +486,8 @@ def workload_hist_client(ctx, rank, n, name):
             "knn_select": (16 * 26 + 12 + 28 * 12) * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric=f"{name}_particles_per_sec",
                 config={"workload": spec["label"], "bonds_per_step": n_bonds}, h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
-                keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds})
+                keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds},
+                algo_per_step=True)
 
 
 def cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=12.0, threads=None):
@@ -813,6 +814,8 @@ def main():
         avg_ms = ms / cnt
         algo = w["algo"].get(name)
         if algo:
+            # w["algo"] holds bytes per step; a kernel launched in several chunks per step moves its share per launch
+            algo = algo * args.steps / cnt if cnt > args.steps and w.get("algo_per_step") else algo
             achieved = algo / (avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(name),

@@ -12,15 +12,16 @@
 //   R12  r = bond distance, t1 = modulusPositive(theta_j - atan2f(dy, dx), 2 pi),
 //        t2 = modulusPositive(theta_i - atan2f(-dy, -dx), 2 pi).
 //
-// atan2f is the host libm's in the reference and CUDA's differs from it in the last place.  The angle bin only
-// depends on that last place when t lies within a few float ulps of a bin edge, so the kernel evaluates atan2 in
-// double, follows the reference's float chain from the rounded value, and accepts the bin only if t is farther from
-// every bin edge than any last-place difference can move it (kAngleMargin, several times libm's error bound plus
-// the rounding of the chain).  The few bonds inside a margin (~3 in 10^4) are written to a list and binned by the
-// host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per bond.
-// cosf / sinf of the query particle's angle (rotmat2::fromAngle, VectorMath.h:912-921) get the same treatment: double
-// sincos rounded to float, and the rotated coordinate must clear every bin edge by more than a last-place change of
-// (cos, sin) can move it -- the host evaluates libm only for the bonds that do not (it used to for every particle).
+// atan2f is the host libm's in the reference and CUDA's differs from it in the last place (both are within 2-3 ulp of
+// the true value).  The angle bin only depends on those last places when t lies within a few float ulps of a bin
+// edge, so the kernel evaluates CUDA's atan2f, follows the reference's float chain from it, and accepts the bin only
+// if t is farther from every bin edge than any such difference can move it (kAngleMargin, several times the two error
+// bounds plus the rounding of the chain).  The few bonds inside a margin (~3 in 10^4) are written to a list and
+// binned by the host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per
+// bond.  cosf / sinf of the query particle's angle (rotmat2::fromAngle, VectorMath.h:912-921) get the same treatment:
+// CUDA's sincosf, and the rotated coordinate must clear every bin edge by more than a few last places of (cos, sin)
+// can move it -- the host evaluates libm only for the bonds that do not (it used to for every particle).  (Double
+// precision atan2 / sincos were tried first: 390 instructions per bond, the kernel issue-bound at 0.59 ms per frame.)
 #include "internal.h"
 #include "pair_math.cuh"
 
@@ -29,19 +30,54 @@ namespace fgpu {
 namespace {
 
 constexpr float kTwoPi = 6.28318548202514648f; // (float) (2.0 * M_PI), Box.h:24
-constexpr float kAngleMargin = 1.0e-5f;        // >> 3 ulp of atan2f at pi (7e-7) + the chain's roundings (1e-6)
+constexpr float kAngleMargin = 1.0e-5f;        // >> (2 + 3) ulp of the two atan2f at pi (1.2e-6) + the chain's roundings (1e-6)
 
-// util::modulusPositive(a, 2 pi), utils.h:29-32 (fmodf is exact on both sides)
+// fmodf(a, 2 pi) for moderate |a| without the library's bit-serial loop: the remainder of a truncated division is a
+// float, so |a| - q 2 pi comes out of one fused multiply-add exactly once q is the right integer (the quotient from
+// one multiplication can be off by one).  The result carries the sign of a, like fmodf's.
+__device__ __forceinline__ float fmod_two_pi(float a)
+{
+    float const m = fabsf(a);
+    if (!(m < 1.0e5f))
+    {
+        return fmodf(a, kTwoPi); // huge, infinite or NaN arguments: the library's path
+    }
+    float q = truncf(m * 0.15915494f);
+    float r = __fmaf_rn(-q, kTwoPi, m);
+    if (r < 0.0f)
+    {
+        q -= 1.0f;
+        r = __fmaf_rn(-q, kTwoPi, m);
+    }
+    else if (r >= kTwoPi)
+    {
+        q += 1.0f;
+        r = __fmaf_rn(-q, kTwoPi, m);
+    }
+    return copysignf(r, a);
+}
+
+// util::modulusPositive(a, 2 pi) = fmodf(fmodf(a, 2 pi) + 2 pi, 2 pi), utils.h:29-32.  The sum lies in [0, 4 pi], so the
+// outer fmodf is at most two exact subtractions (Sterbenz).
 __device__ __forceinline__ float mod_two_pi(float a)
 {
-    return fmodf(__fadd_rn(fmodf(a, kTwoPi), kTwoPi), kTwoPi);
+    float r = __fadd_rn(fmod_two_pi(a), kTwoPi);
+    if (r >= kTwoPi)
+    {
+        r = __fsub_rn(r, kTwoPi);
+    }
+    if (r >= kTwoPi)
+    {
+        r = __fsub_rn(r, kTwoPi);
+    }
+    return r;
 }
 
 // Bin of t = modulusPositive(orientation - atan2f(y, x), 2 pi) on `axis` = RegularAxis(n, 0, 2 pi); *sure = false if a
 // last-place difference in atan2f could change it.
 __device__ __forceinline__ int angle_bin(const AxisDev& axis, float orientation, float y, float x, bool* sure)
 {
-    float const d = (float) atan2((double) y, (double) x);
+    float const d = atan2f(y, x);
     float const t = mod_two_pi(__fsub_rn(orientation, d));
     float const u = __fmul_rn(t, axis.inv_width);
     float const frac = u - floorf(u);
@@ -69,16 +105,15 @@ __device__ __forceinline__ int slack_bin(const AxisDev& axis, float value, float
     return clear ? bin : max(bin, 0); // not clear: the host decides, also whether the bond is inside at all
 }
 
-// (x, y) = rotmat2::fromAngle(-theta) * (vx, vy), VectorMath.h:912-936, with (cos, sin) from double sincos; the slack
-// of the result for a last-place (and then some) difference to libm's cosf / sinf
+// (x, y) = rotmat2::fromAngle(-theta) * (vx, vy), VectorMath.h:912-936, with CUDA's sincosf (2 ulp); the slack of the
+// result covers its difference to libm's cosf / sinf (1 ulp) several times
 __device__ __forceinline__ void rotate_xy(float theta, float vx, float vy, float& rx, float& ry, float& slack)
 {
-    double sd, cd;
-    sincos((double) -theta, &sd, &cd);
-    float const c = (float) cd, sn = (float) sd;
+    float c, sn;
+    sincosf(-theta, &sn, &c);
     rx = __fadd_rn(__fmul_rn(c, vx), __fmul_rn(-sn, vy));
     ry = __fadd_rn(__fmul_rn(sn, vx), __fmul_rn(c, vy));
-    slack = 1.0e-6f * (fabsf(vx) + fabsf(vy)); // 4 ulp of (cos, sin) move a coordinate by < 5e-7 (|vx| + |vy|)
+    slack = 1.0e-6f * (fabsf(vx) + fabsf(vy)); // 3 ulp of (cos, sin) move a coordinate by < 2e-7 (|vx| + |vy|)
 }
 
 // rotate(q, v), VectorMath.h:810-818: (s^2 - v.v) b + (2 s) (v x b) + (2 v.b) v, one rounding per operation
@@ -197,8 +232,8 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
 
 // BondOrder::accumulate: the bond vector (or, mode oocd, the z director of the query particle) rotated as the mode
 // asks, then theta = modulusPositive(atan2f(v.y, v.x), 2 pi) on RegularAxis(n_theta, 0, 2 pi) and
-// phi = acosf(v.z / sqrt(v.v)) on RegularAxis(n_phi, 0, pi).  Both angles are bracketed like the PMFT angles: double
-// atan2 / acos of the reference's float arguments, bins accepted away from the bin edges, the rest left to the host.
+// phi = acosf(v.z / sqrt(v.v)) on RegularAxis(n_phi, 0, pi).  Both angles are bracketed like the PMFT angles: CUDA's
+// atan2f / acosf of the reference's float arguments, bins accepted away from the bin edges, the rest left to the host.
 __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
 {
     extern __shared__ uint32_t bo_hist[];
@@ -235,7 +270,7 @@ __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
             }
         }
         // theta: the chain of angle_bin with orientation - d replaced by d itself
-        float const d = (float) atan2((double) y, (double) x);
+        float const d = atan2f(y, x);
         float const theta = mod_two_pi(d);
         float const ut = __fmul_rn(theta, a.at.inv_width);
         float const ft = ut - floorf(ut);
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
         bool sure = ft > mt && ft < 1.0f - mt && theta > kAngleMargin && theta < kTwoPi - kAngleMargin;
         // phi: the argument is float arithmetic (one division, one square root), acosf is libm's
         float const c = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
-        float const phi = (float) acos((double) c);
+        float const phi = acosf(c);
         float const up = __fmul_rn(phi, a.ap.inv_width);
         float const fp = up - floorf(up);
         float const mp = kAngleMargin * a.ap.inv_width + 1.0e-6f * (up + 1.0f);

@@ -304,6 +304,9 @@ def test_pmft3_matches_the_port_at_scale():
     rs = np.random.RandomState(9)
     box, pts = data.make_random_system(450.0, 100_000, is2D=True, seed=4)
     th = (rs.random_sample(len(pts)) * 4 * np.pi - 2 * np.pi).astype(np.float32)  # also outside [0, 2 pi)
+    th[::7] *= np.float32(300.0)  # many turns: the kernel's own remainder ...
+    th[::41] *= np.float32(1.0e4)  # ... and the library's for huge angles
+    th[5], th[6] = np.float32(2 * np.pi), np.float32(-4 * np.pi)
     nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 4.0, exclude_ii=True)
     xyt = pmft.PMFTXYT(3.0, 2.5, (40, 30, 36)).compute((box, pts), th, neighbors=dict(mode="ball", r_max=4.0))
     want, want_pcf = port.pmft3(port.PMFT_XYT, box, len(pts), nl, th, th, (3.0, 2.5), (40, 30, 36))
