@@ -3,7 +3,7 @@ NeighborList container semantics.  Each case restates a test of the reference's 
 import numpy as np
 import pytest
 
-from freud_b200 import density, locality, order
+from freud_b200 import density, environment, locality, order, pmft
 from freud_b200.box import Box
 
 
@@ -106,6 +106,52 @@ def test_steinhardt_constructor():
         order.Steinhardt(-1)
     with pytest.raises(NotImplementedError):  # no default query arguments, as upstream
         order.Steinhardt(6).compute((Box.cube(5), np.zeros((3, 3), np.float32)))
+
+
+def test_histogram_clients_host_side():
+    """Constructors, axes and errors of the PMFT family and BondOrder need no GPU (freud/pmft.py:124-590,
+    freud/environment.py:204-391; RegularAxis edges and centres as freud/util/Histogram.h:87-138)."""
+    f32 = np.float32
+    xyz = pmft.PMFTXYZ(1.0, 2.0, 3.0, (4, 5, 6), shiftvec=[0.5, 0, 0])
+    assert xyz.nbins == (4, 5, 6) and xyz.bounds == [(-1.0, 1.0), (-2.0, 2.0), (-3.0, 3.0)]
+    assert np.isclose(xyz.r_max, np.sqrt(14.0)) and xyz.default_query_args == dict(mode="ball", r_max=xyz.r_max)
+    assert np.array_equal(xyz.bin_edges[0], f32([-1, -0.5, 0, 0.5, 1])) and np.array_equal(xyz.shiftvec, f32([0.5, 0, 0]))
+    assert np.array_equal(xyz.bin_centers[0], f32([-0.75, -0.25, 0.25, 0.75]))
+    assert xyz.bin_counts.shape == (4, 5, 6) and not xyz.bin_counts.any()  # nothing computed yet: zeros, as upstream
+    xyt = pmft.PMFTXYT(2.0, 1.0, 8)
+    two_pi = float(f32(2 * np.pi))
+    assert xyt.nbins == (8, 8, 8) and xyt.bounds[2] == (0.0, two_pi) and np.isclose(xyt.r_max, np.sqrt(5.0))
+    width = f32(two_pi) / f32(8)
+    assert np.array_equal(xyt.bin_edges[2], f32(0) + np.arange(9, dtype=f32) * width)
+    r12 = pmft.PMFTR12(3.0, (3, 4, 5))
+    assert r12.nbins == (3, 4, 5) and r12.bounds == [(0.0, 3.0), (0.0, two_pi), (0.0, two_pi)] and r12.r_max == 3.0
+    assert "PMFTR12(r_max=3.0, bins=(3, 4, 5))" in repr(r12) and "shiftvec=[0.5, 0.0, 0.0]" in repr(xyz)
+    for make in (lambda: pmft.PMFTXYZ(1, 1, 1, (0, 2, 2)), lambda: pmft.PMFTXYZ(1, -1, 1, 2), lambda: pmft.PMFTXYT(1, 1, (2, 2, 0)),
+                 lambda: pmft.PMFTXYT(-1, 1, 2), lambda: pmft.PMFTR12(-1.0, 2), lambda: pmft.PMFTR12(1.0, (2, 0, 2)),
+                 lambda: pmft.PMFTXY(1, 1, (0, 2))):
+        with pytest.raises(ValueError):
+            make()
+    bo = environment.BondOrder((6, 3), mode="lbod")
+    pi = float(f32(np.pi))
+    assert bo.nbins == (6, 3) and bo.mode == "lbod" and bo.bounds == [(0.0, two_pi), (0.0, pi)]
+    assert [len(e) for e in bo.bin_edges] == [7, 4] and "mode='lbod'" in repr(bo)
+    assert bo.bond_order.shape == (6, 3) and not bo.bin_counts.any()
+    with pytest.raises(NotImplementedError):
+        bo.default_query_args
+    for make in (lambda: environment.BondOrder((1, 3)), lambda: environment.BondOrder((3, 1)),
+                 lambda: environment.BondOrder(4, mode="other")):
+        with pytest.raises(ValueError):
+            make()
+    # argument checks that come before any device work
+    box, pts = Box.cube(10), np.zeros((6, 3), np.float32)
+    with pytest.raises(ValueError):
+        pmft.PMFTXYZ(1, 1, 1, 2).compute((box, pts), np.zeros((5, 4)))  # one quaternion per query point
+    with pytest.raises(ValueError):
+        pmft.PMFTXYZ(1, 1, 1, 2).compute((box, pts), np.zeros((6, 4)), equiv_orientations=np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        pmft.PMFTR12(1.0, 2).compute((Box.square(10), pts), np.zeros(5))
+    with pytest.raises(ValueError):
+        bo.compute((box, pts), np.zeros((6, 3)), neighbors=dict(num_neighbors=2))
 
 
 def test_no_cpu_fallback():
