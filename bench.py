@@ -217,7 +217,7 @@ def workload_q6(ctx, rank, n):
     def step_dev():
         dp.build_cells(r_window)
         nl = dp.knn_query(None, 12, exclude_ii=True)
-        return dp.steinhardt(nl, [6], want_qlm=False)
+        return dp.steinhardt(nl, [6], want_qlm=False, out={"ql": pin_ql})  # q_l (4 MB) lands in page-locked memory
 
     pin_ql, keep1 = pinned_empty((n, 1), np.float32)
     pin_qlm, keep2 = pinned_empty((n * 13 * 2,), np.float32)
