@@ -158,7 +158,8 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
                 config={"workload": f"LinkCell NeighborList r_max={r_max:g} exclude_ii N={n} cubic L={L:.4f} rho=0.08 "
                                     f"flavour={'wrap' if flavour == WRAP else 'image'}",
                         "bonds_per_step": n_bonds, "pair_evals_per_step": evals, "n_cells": n_cells},
-                h2d=12 * n, d2h=28 * n_bonds + 8 * n, algo=algo, keep=keep, box=box, pts=pts, r_max=r_max,
+                # 24 B per bond cross PCIe (indices, distance, vector); the unit weights are written by the host
+                h2d=12 * n, d2h=24 * n_bonds + 8 * n, algo=algo, keep=keep, box=box, pts=pts, r_max=r_max,
                 secondary={"bonds": n_bonds})
 
 

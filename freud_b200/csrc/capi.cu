@@ -285,6 +285,7 @@ std::unique_ptr<fgpu_nlist> new_nlist(fgpu_ctx* ctx, uint32_t n_query, uint32_t 
     nl->n_query = n_query;
     nl->n_points = n_points;
     nl->swap(ctx->spare_nlist); // the arrays the last destroyed list left behind (empty if none)
+    nl->unit_weights = true;    // every query writes weight 1; fgpu_nlist_from_host clears this for given weights
     nl->row_start.reserve((size_t) n_query + 1);
     nl->counts.reserve((size_t) n_query + 1);
     nl->segments.reserve((size_t) n_query + 1);
@@ -1284,7 +1285,8 @@ int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* dista
         {
             d2h(ctx, distances_host, nl->distances.ptr, nb * sizeof(float));
         }
-        if (weights_host != nullptr)
+        bool const fill_weights = weights_host != nullptr && nl->unit_weights;
+        if (weights_host != nullptr && !fill_weights)
         {
             d2h(ctx, weights_host, nl->weights.ptr, nb * sizeof(float));
         }
@@ -1299,6 +1301,24 @@ int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* dista
         if (counts_host != nullptr)
         {
             d2h(ctx, counts_host, nl->counts.ptr, (size_t) nl->n_query * sizeof(uint32_t));
+        }
+        if (fill_weights)
+        {
+            // A list built by a query carries weight 1 on every bond: write the ones here, on host threads, while
+            // the other arrays cross PCIe (the copy of a frame's list is bound by that link) instead of sending a
+            // seventh of the bytes for a constant.
+            unsigned const n_threads = nb >= (1U << 20) ? std::max(1U, std::min(4U, std::thread::hardware_concurrency())) : 1U;
+            auto fill = [&](size_t lo, size_t hi) { std::fill(weights_host + lo, weights_host + hi, 1.0f); };
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < n_threads; ++t)
+            {
+                pool.emplace_back(fill, nb * t / n_threads, nb * (t + 1) / n_threads);
+            }
+            fill(0, nb / n_threads);
+            for (auto& th : pool)
+            {
+                th.join();
+            }
         }
         sync(ctx);
     });
@@ -1339,6 +1359,7 @@ int fgpu_nlist_from_host(fgpu_ctx* ctx, uint64_t n_bonds, uint32_t n_query, uint
         std::vector<float> ones;
         h2d(ctx, nl->neighbors.ptr, neighbors_host, n_bonds * 2 * sizeof(uint32_t));
         h2d(ctx, nl->distances.ptr, distances_host, n_bonds * sizeof(float));
+        nl->unit_weights = weights_host == nullptr;
         if (weights_host == nullptr)
         {
             ones.assign(n_bonds, 1.0f);

@@ -216,6 +216,7 @@ struct fgpu_nlist : NlistStorage
     uint64_t n_bonds = 0;
     uint32_t n_query = 0;
     uint32_t n_points = 0;
+    bool unit_weights = false; // built by a query: every weight is 1 (NeighborQuery.h:470-478)
 };
 
 struct fgpu_rdf
