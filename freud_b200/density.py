@@ -4,7 +4,7 @@
 
 import numpy as np
 
-from .locality import _ext, _PairCompute
+from .locality import _computed, _ext, _PairCompute
 
 
 class RDF(_PairCompute):
@@ -34,17 +34,18 @@ class RDF(_PairCompute):
             self._cpp_obj.reset()
         nq, nlist, qargs, qp = self._preprocess_arguments(system, query_points, neighbors)
         self._cpp_obj.accumulateRDF(nq._cpp_obj, qp, nlist, qargs)
+        self._called_compute = True
         return self
 
-    rdf = property(lambda self: self._cpp_obj.getRDF())
-    n_r = property(lambda self: self._cpp_obj.getNr())
-    bin_counts = property(lambda self: self._cpp_obj.getBinCounts())
+    rdf = _computed(lambda self: self._cpp_obj.getRDF())
+    n_r = _computed(lambda self: self._cpp_obj.getNr())
+    bin_counts = _computed(lambda self: self._cpp_obj.getBinCounts())
     bin_edges = property(lambda self: np.array(self._cpp_obj.getBinEdges()[0], dtype=np.float32))
     bin_centers = property(lambda self: np.array(self._cpp_obj.getBinCenters()[0], dtype=np.float32))
     bounds = property(lambda self: tuple(self._cpp_obj.getBounds()[0]))
     nbins = property(lambda self: self._cpp_obj.getAxisSizes()[0])
 
-    @property
+    @_computed
     def box(self):
         from .box import Box
 
@@ -65,7 +66,6 @@ class LocalDensity(_PairCompute):
 
     def __init__(self, r_max, diameter):
         self._cpp_obj = _ext()._density.LocalDensity(float(r_max), float(diameter))
-        self._computed = False
 
     r_max = property(lambda self: self._cpp_obj.getRMax())
     diameter = property(lambda self: self._cpp_obj.getDiameter())
@@ -77,27 +77,12 @@ class LocalDensity(_PairCompute):
     def compute(self, system, query_points=None, neighbors=None):
         nq, nlist, qargs, qp = self._preprocess_arguments(system, query_points, neighbors)
         self._cpp_obj.compute(nq._cpp_obj, qp, nlist, qargs)
-        self._computed = True
+        self._called_compute = True
         return self
 
-    def _need(self):
-        if not self._computed:  # _Compute._computed_property, freud/util.py
-            raise AttributeError("Property not computed. Call compute first.")
-
-    @property
-    def box(self):
-        self._need()
-        return _box_of(self._cpp_obj.box)
-
-    @property
-    def density(self):
-        self._need()
-        return self._cpp_obj.density
-
-    @property
-    def num_neighbors(self):
-        self._need()
-        return self._cpp_obj.num_neighbors
+    box = _computed(lambda self: _box_of(self._cpp_obj.box))
+    density = _computed(lambda self: self._cpp_obj.density)
+    num_neighbors = _computed(lambda self: self._cpp_obj.num_neighbors)
 
     def __repr__(self):
         return f"freud.density.{type(self).__name__}(r_max={self.r_max}, diameter={self.diameter})"
@@ -127,16 +112,17 @@ class CorrelationFunction(_PairCompute):
         # freud/density.py:131-135: the points correlate with themselves unless query points (and values) are given
         query_values = values if query_values is None else np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
         self._cpp_obj.accumulateCF(nq._cpp_obj, values, qp, query_values, nlist, qargs)
+        self._called_compute = True
         return self
 
-    @property
+    @_computed
     def correlation(self):
         c = self._cpp_obj.getCorrelation()
         return c if self.is_complex else np.real(c)  # freud/density.py:139-144
 
-    bin_counts = property(lambda self: self._cpp_obj.getBinCounts())
+    bin_counts = _computed(lambda self: self._cpp_obj.getBinCounts())
     bin_edges = property(lambda self: np.array(self._cpp_obj.getBinEdges()[0], dtype=np.float32))
     bin_centers = property(lambda self: np.array(self._cpp_obj.getBinCenters()[0], dtype=np.float32))
     bounds = property(lambda self: tuple(self._cpp_obj.getBounds()[0]))
     nbins = property(lambda self: self._cpp_obj.getAxisSizes()[0])
-    box = property(lambda self: _box_of(self._cpp_obj.getBox()))
+    box = _computed(lambda self: _box_of(self._cpp_obj.getBox()))

@@ -4,7 +4,7 @@
 import numpy as np
 
 from .density import _box_of
-from .locality import _ext, _PairCompute
+from .locality import _computed, _ext, _PairCompute
 
 
 def _quats(orientations, n, name):
@@ -50,15 +50,16 @@ class BondOrder(_PairCompute):
         if len(qo) != len(qp):
             raise ValueError("query_orientations must hold one quaternion per query point")
         self._cpp_obj.accumulate(nq._cpp_obj, o, qp, qo, nlist, qargs)
+        self._called_compute = True
         return self
 
-    bond_order = property(lambda self: self._cpp_obj.getBondOrder())
-    bin_counts = property(lambda self: self._cpp_obj.getBinCounts())
+    bond_order = _computed(lambda self: self._cpp_obj.getBondOrder())
+    bin_counts = _computed(lambda self: self._cpp_obj.getBinCounts())
+    box = _computed(lambda self: _box_of(self._cpp_obj.getBox()))
     bin_edges = property(lambda self: [np.array(e, dtype=np.float32) for e in self._cpp_obj.getBinEdges()])
     bin_centers = property(lambda self: [np.array(c, dtype=np.float32) for c in self._cpp_obj.getBinCenters()])
     bounds = property(lambda self: [tuple(b) for b in self._cpp_obj.getBounds()])
     nbins = property(lambda self: tuple(self._cpp_obj.getAxisSizes()))
-    box = property(lambda self: _box_of(self._cpp_obj.getBox()))
     mode = property(lambda self: self.known_modes[int(self._cpp_obj.getMode())])
     #: bonds whose bin was decided by the host's libm rather than on the GPU (see csrc/pmft.cu)
     host_binned_bonds = property(lambda self: self._cpp_obj.getHostBinnedBonds())

@@ -259,8 +259,23 @@ class NeighborList:
         return self
 
 
+def _computed(fn):
+    """Property that raises AttributeError until compute() ran (``_Compute._computed_property``, freud/util.py:61-80)."""
+
+    def getter(self):
+        if not self._called_compute:
+            raise AttributeError("Property not computed. Call compute first.")
+        return fn(self)
+
+    getter.__doc__ = fn.__doc__
+    return property(getter)
+
+
 class _PairCompute:
-    """Argument resolution shared by the computes (freud/locality.py:924-1016)."""
+    """Argument resolution shared by the computes (freud/locality.py:924-1016); ``compute`` of a subclass sets
+    ``_called_compute`` once it ran (freud/util.py:39-59)."""
+
+    _called_compute = False
 
     def _preprocess_arguments(self, system, query_points=None, neighbors=None):
         nq = NeighborQuery.from_system(system)

@@ -2,7 +2,7 @@
 
 import numpy as np
 
-from .locality import _ext, _PairCompute
+from .locality import _computed, _ext, _PairCompute
 
 
 class Steinhardt(_PairCompute):
@@ -26,21 +26,22 @@ class Steinhardt(_PairCompute):
     def compute(self, system, neighbors=None):
         nq, nlist, qargs, _ = self._preprocess_arguments(system, None, neighbors)
         self._cpp_obj.compute(nlist, nq._cpp_obj, qargs)
+        self._called_compute = True
         return self
 
-    @property
+    @_computed
     def order(self):
         o = self._cpp_obj.getOrder()
         return o[0] if self._scalar_l else o
 
-    @property
+    @_computed
     def particle_order(self):
         a = self._cpp_obj.getParticleOrder()
         return a[:, 0] if self._scalar_l else a
 
-    ql = property(lambda self: self._cpp_obj.getQl()[:, 0] if self._scalar_l else self._cpp_obj.getQl())
+    ql = _computed(lambda self: self._cpp_obj.getQl()[:, 0] if self._scalar_l else self._cpp_obj.getQl())
 
-    @property
+    @_computed
     def particle_harmonics(self):
         q = self._cpp_obj.getQlm()
         return q[0] if self._scalar_l else q

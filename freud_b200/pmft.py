@@ -4,7 +4,7 @@
 import numpy as np
 
 from .density import _box_of
-from .locality import _ext, _PairCompute
+from .locality import _computed, _ext, _PairCompute
 
 
 def _angles(orientations, n):
@@ -26,21 +26,19 @@ class _PMFT(_PairCompute):
     def default_query_args(self):
         return dict(mode="ball", r_max=self.r_max)  # freud/locality.py:1013-1016
 
-    @property
-    def _pcf(self):
-        return self._cpp_obj.getPCF()
+    _pcf = _computed(lambda self: self._cpp_obj.getPCF())
+    bin_counts = _computed(lambda self: self._cpp_obj.getBinCounts())
+    box = _computed(lambda self: _box_of(self._cpp_obj.getBox()))
 
     @property
     def pmft(self):
         with np.errstate(divide="ignore"):
             return -np.log(np.copy(self._pcf))  # freud/pmft.py:111-116
 
-    bin_counts = property(lambda self: self._cpp_obj.getBinCounts())
     bin_edges = property(lambda self: [np.array(e, dtype=np.float32) for e in self._cpp_obj.getBinEdges()])
     bin_centers = property(lambda self: [np.array(c, dtype=np.float32) for c in self._cpp_obj.getBinCenters()])
     bounds = property(lambda self: [tuple(b) for b in self._cpp_obj.getBounds()])
     nbins = property(lambda self: tuple(self._cpp_obj.getAxisSizes()))
-    box = property(lambda self: _box_of(self._cpp_obj.getBox()))
 
     def _bins_repr(self):
         return ", ".join(str(n) for n in self.nbins)
@@ -68,6 +66,7 @@ class PMFTXY(_PMFT):
             self._cpp_obj.reset()
         nq, nlist, qargs, qp = self._preprocess_arguments(system, query_points, neighbors)
         self._cpp_obj.accumulate(nq._cpp_obj, _angles(query_orientations, len(qp)), qp, nlist, qargs)
+        self._called_compute = True
         return self
 
     def __repr__(self):
@@ -87,6 +86,7 @@ class _PMFTAngles(_PMFT):
         if len(qo) != len(qp):
             raise ValueError("query_orientations must hold one orientation per query point")
         self._cpp_obj.accumulate(nq._cpp_obj, o, qp, qo, nlist, qargs)
+        self._called_compute = True
         return self
 
     #: bonds whose angle bin was decided by the host's libm rather than on the GPU (see csrc/pmft.cu)
@@ -144,6 +144,7 @@ class PMFTXYZ(_PMFT):
             if eq.ndim != 2 or eq.shape[1] != 4:
                 raise ValueError("equiv_orientations must have shape (N, 4)")
         self._cpp_obj.accumulate(nq._cpp_obj, qo, qp, eq, nlist, qargs)
+        self._called_compute = True
         return self
 
     def __repr__(self):

@@ -387,6 +387,74 @@ def test_bond_order_matches_the_port_at_scale():
     assert 0 < bo.host_binned_bonds < 5e-3 * len(nl.distances)
 
 
+def test_histogram_clients_reference_suite_cases():
+    """Cases restated from the reference's own suite: the two-particle system of tests/test_pmft.py:119-154, 663-706
+    (expected bins from the definition, equivalent orientations double the counts and leave the PMFT unchanged), the
+    shifted dead pixel (:708-727), PMFTXY against the middle z layer of PMFTXYZ (:992-1026) and against PMFTXYT with one
+    angular bin (:1028-1056); empty neighbour lists; results available only after compute()."""
+    box = Box.cube(16)
+    pts = np.array([[-1.0, 0.0, 0.0], [1.0, 0.1, 0.0]], dtype=np.float32)
+    ident = np.array([[1, 0, 0, 0], [1, 0, 0, 0]], dtype=np.float32)
+    limits, bins = np.array([3.6, 4.2, 4.8]), (20, 30, 40)
+
+    def xyz_bin(a, b):
+        return tuple(np.floor((b - a + limits) * np.asarray(bins) / (2 * limits)).astype(int))
+
+    want = np.zeros(bins, np.uint32)
+    want[xyz_bin(pts[0], pts[1])] = 1
+    want[xyz_bin(pts[1], pts[0])] = 1
+    xyz = pmft.PMFTXYZ(*limits, bins)
+    with pytest.raises(AttributeError):
+        xyz.bin_counts
+    for system in ((box, pts), locality.AABBQuery(box, pts), locality.LinkCell(box, pts, 7.0)):
+        xyz.compute(system, ident, reset=False)
+        xyz.compute(system, ident)
+        assert np.array_equal(xyz.bin_counts, want)
+    first = xyz.pmft
+    xyz.compute((box, pts), ident, equiv_orientations=[[1, 0, 0, 0]] * 2)
+    assert np.array_equal(xyz.bin_counts, 2 * want)
+    with np.errstate(invalid="ignore"):
+        assert np.allclose(xyz.pmft[np.isfinite(first)], first[np.isfinite(first)], atol=1e-6)
+    # r12 / xyt of the same pair in 2-D, bins from the definitions (tests/test_pmft.py:214-232, 641-660)
+    sq = Box.square(16)
+    two_pi = 2 * np.pi
+    r_ij = pts[1] - pts[0]
+    r12 = pmft.PMFTR12(5.23, (10, 20, 30)).compute((sq, pts), np.zeros(2))
+    want = np.zeros((10, 20, 30), np.uint32)
+    for v in (r_ij, -r_ij):
+        want[int(np.linalg.norm(v) * 10 / 5.23), int(((0 - np.arctan2(v[1], v[0])) % two_pi) * 20 / two_pi),
+             int(((0 - np.arctan2(-v[1], -v[0])) % two_pi) * 30 / two_pi)] = 1
+    assert np.array_equal(r12.bin_counts, want)
+    # the shifted dead pixel
+    cube3, pair = Box.cube(3), np.array([[1, 1, 1], [0, 0, 0]], dtype=np.float32)
+    noshift = pmft.PMFTXYZ(0.5, 0.5, 0.5, 3).compute((cube3, pair), ident)
+    shift = pmft.PMFTXYZ(0.5, 0.5, 0.5, 3, shiftvec=[1, 1, 1]).compute((cube3, pair), ident)
+    with np.errstate(divide="ignore"):
+        assert np.isfinite(noshift.pmft).sum() == 0 and np.isfinite(shift.pmft).sum() == 1
+    # XY == the middle z layer of XYZ == XYT with a single angular bin
+    rs = np.random.RandomState(0)
+    flat = rs.random_sample((100, 3)).astype(np.float32)
+    flat[:, 2] = 0
+    quat0 = np.tile(np.float32([1, 0, 0, 0]), (100, 1))
+    xy = pmft.PMFTXY(2.5, 2.5, 4).compute((Box.square(10), flat), quat0)
+    xyz4 = pmft.PMFTXYZ(2.5, 2.5, 1, 4).compute((Box.cube(10), flat), quat0)
+    assert np.array_equal(xy.bin_counts, xyz4.bin_counts[:, :, 2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a, b = np.exp(xy.pmft), np.exp(xyz4.pmft[:, :, 2]) * (4 / 2) * 10
+    assert np.allclose(a, b, atol=1e-6)
+    xy3 = pmft.PMFTXY(2.5, 2.5, 3).compute((Box.square(10), flat), np.zeros(100))
+    xyt = pmft.PMFTXYT(2.5, 2.5, (3, 3, 1)).compute((Box.square(10), flat), np.zeros(100))
+    assert np.array_equal(xy3.bin_counts, xyt.bin_counts.reshape(3, 3))
+    with np.errstate(divide="ignore"):
+        assert np.allclose(np.exp(xy3.pmft), np.exp(xyt.pmft).reshape(3, 3), atol=1e-6)
+    # nothing within reach: all-zero histograms, no error
+    far = np.array([[-4, -4, 0], [4, 4, 0]], dtype=np.float32)
+    assert pmft.PMFTXYT(1, 1, 4).compute((sq, far), np.zeros(2)).bin_counts.sum() == 0
+    assert pmft.PMFTXYZ(1, 1, 1, 4).compute((box, far), ident).bin_counts.sum() == 0
+    bo = environment.BondOrder(4).compute((box, far), neighbors=dict(r_max=1.0))
+    assert bo.bin_counts.sum() == 0 and not bo.bond_order.any()
+
+
 def test_correlation_function_api():
     """freud.density.CorrelationFunction (tests/test_density_correlation_function.py upstream): complex and real
     inputs, is_complex, reset=False accumulation, histogram properties, the zero-mean random field known answer."""

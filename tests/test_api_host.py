@@ -117,7 +117,9 @@ def test_histogram_clients_host_side():
     assert np.isclose(xyz.r_max, np.sqrt(14.0)) and xyz.default_query_args == dict(mode="ball", r_max=xyz.r_max)
     assert np.array_equal(xyz.bin_edges[0], f32([-1, -0.5, 0, 0.5, 1])) and np.array_equal(xyz.shiftvec, f32([0.5, 0, 0]))
     assert np.array_equal(xyz.bin_centers[0], f32([-0.75, -0.25, 0.25, 0.75]))
-    assert xyz.bin_counts.shape == (4, 5, 6) and not xyz.bin_counts.any()  # nothing computed yet: zeros, as upstream
+    for prop in ("bin_counts", "pmft", "box"):  # _Compute._computed_property, tests/test_pmft.py:93-105 upstream
+        with pytest.raises(AttributeError):
+            getattr(xyz, prop)
     xyt = pmft.PMFTXYT(2.0, 1.0, 8)
     two_pi = float(f32(2 * np.pi))
     assert xyt.nbins == (8, 8, 8) and xyt.bounds[2] == (0.0, two_pi) and np.isclose(xyt.r_max, np.sqrt(5.0))
@@ -135,7 +137,9 @@ def test_histogram_clients_host_side():
     pi = float(f32(np.pi))
     assert bo.nbins == (6, 3) and bo.mode == "lbod" and bo.bounds == [(0.0, two_pi), (0.0, pi)]
     assert [len(e) for e in bo.bin_edges] == [7, 4] and "mode='lbod'" in repr(bo)
-    assert bo.bond_order.shape == (6, 3) and not bo.bin_counts.any()
+    for prop in ("bond_order", "bin_counts", "box"):
+        with pytest.raises(AttributeError):
+            getattr(bo, prop)
     with pytest.raises(NotImplementedError):
         bo.default_query_args
     for make in (lambda: environment.BondOrder((1, 3)), lambda: environment.BondOrder((3, 1)),
@@ -152,6 +156,22 @@ def test_histogram_clients_host_side():
         pmft.PMFTR12(1.0, 2).compute((Box.square(10), pts), np.zeros(5))
     with pytest.raises(ValueError):
         bo.compute((box, pts), np.zeros((6, 3)), neighbors=dict(num_neighbors=2))
+
+
+def test_results_need_compute_first():
+    """``_Compute._computed_property`` (freud/util.py:61-80; tests/test_density_rdf.py:42-59 and its siblings upstream):
+    every result raises AttributeError until compute() ran; the histogram geometry does not."""
+    cases = [(density.RDF(10, 2.0), ("rdf", "n_r", "bin_counts", "box"), ("bin_edges", "bin_centers", "bounds", "nbins")),
+             (density.CorrelationFunction(10, 2.0), ("correlation", "bin_counts", "box"), ("bin_edges", "bounds", "nbins")),
+             (density.LocalDensity(2.0, 1.0), ("density", "num_neighbors", "box"), ("r_max", "diameter")),
+             (order.Steinhardt(6), ("order", "particle_order", "ql", "particle_harmonics"), ("l", "average", "wl")),
+             (pmft.PMFTXY(1, 1, 4), ("pmft", "bin_counts", "box"), ("bin_edges", "bin_centers", "bounds", "nbins"))]
+    for obj, results, geometry in cases:
+        for name in results:
+            with pytest.raises(AttributeError):
+                getattr(obj, name)
+        for name in geometry:
+            getattr(obj, name)
 
 
 def test_no_cpu_fallback():
