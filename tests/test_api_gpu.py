@@ -455,6 +455,36 @@ def test_histogram_clients_reference_suite_cases():
     assert bo.bin_counts.sum() == 0 and not bo.bond_order.any()
 
 
+def test_bond_order_reference_suite_case():
+    """tests/test_environment_bond_order.py:14-105 upstream: a perfect FCC crystal fills exactly 12 bins of a 6 x 6 diagram;
+    lbod and obcd equal bod when all orientations are equal; bod ignores random orientations while obcd smears them over
+    every bin; oocd of equal orientations is a single peak at (0, 0) and of random ones is broad."""
+    box, pts = data.UnitCell.fcc().generate_system(4)
+    quats = np.tile(np.float32([1, 0, 0, 0]), (len(pts), 1))
+    nn = dict(num_neighbors=12, r_max=1.5)
+    bo = environment.BondOrder(6).compute((box, pts), quats, neighbors=nn)
+    ref_bod = bo.bond_order.copy()
+    assert np.sum(ref_bod > 0) == 12 and bo.box == box
+    assert np.allclose(bo.bin_centers[0], (2 * np.arange(6) + 1) * np.pi / 6)
+    assert np.allclose(bo.bin_centers[1], (2 * np.arange(6) + 1) * np.pi / 12)
+    rs = np.random.RandomState(10893)
+    rq = rs.normal(size=(len(pts), 4))
+    rq = (rq / np.linalg.norm(rq, axis=1, keepdims=True)).astype(np.float32)
+    nlist = locality.AABBQuery(box, pts).query(pts, dict(nn, exclude_ii=True)).toNeighborList()
+    for system, neighbors in (((box, pts), nn), (locality.AABBQuery(box, pts), nn), (locality.LinkCell(box, pts, 1.5), nn),
+                              ((box, pts), nlist)):
+        lbod = environment.BondOrder(6, mode="lbod").compute(system, quats, neighbors=neighbors, reset=False)
+        assert np.allclose(lbod.bond_order, ref_bod)
+        assert np.allclose(environment.BondOrder(6, mode="obcd").compute(system, quats, neighbors=neighbors).bond_order,
+                           ref_bod)
+        assert np.allclose(environment.BondOrder(6).compute(system, rq, neighbors=neighbors).bond_order, ref_bod)
+        smeared = environment.BondOrder(6, mode="obcd").compute(system, rq, neighbors=neighbors).bond_order
+        assert not np.allclose(smeared, ref_bod) and np.sum(smeared > 0) == smeared.size
+        peak = environment.BondOrder(6, mode="oocd").compute(system, quats, neighbors=neighbors, reset=False).bond_order
+        assert np.sum(peak > 0) == 1 and peak[0, 0] > 0
+        assert np.sum(environment.BondOrder(6, mode="oocd").compute(system, rq, neighbors=neighbors).bond_order > 0) > 30
+
+
 def test_correlation_function_api():
     """freud.density.CorrelationFunction (tests/test_density_correlation_function.py upstream): complex and real
     inputs, is_complex, reset=False accumulation, histogram properties, the zero-mean random field known answer."""
