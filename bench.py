@@ -198,6 +198,9 @@ def workload_rdf(ctx, rank, n, bins=100, r_max=5.0, flavour=IMAGE, tilt=None, is
                                     f"flavour={'wrap' if flavour == WRAP else 'image'} fused (no NeighborList)",
                         "bonds_per_step": n_bonds, "pair_evals_per_step": evals},
                 h2d=12 * n, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max, rdf=rdf, dp=dp,
+                # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v6_summary.md "full_rdf"): config 1 M / r=5 / image
+                traffic={"search_rdf": 16412672} if (n, r_max, flavour, bins, tilt, is2d) == (1_000_000, 5.0, IMAGE, 100, None, False)
+                else {},
                 secondary={"pair_evals_per_sec_factor": evals})
 
 
@@ -234,7 +237,10 @@ def workload_q6(ctx, rank, n):
             "knn_select": (16 * 26 + 12 + 28 * 12) * n, "pipeline": 124 * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
                 config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
-                h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={})
+                h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={},
+                # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v6_summary.md "full_q6")
+                traffic={"search_nl": 20075008 + 221451008, "knn_select": 366002432 + 323085568,
+                         "steinhardt": 162739968 + 6141952} if n == 1_000_188 else {})
 
 
 def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
@@ -488,7 +494,12 @@ def workload_hist_client(ctx, rank, n, name):
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric=f"{name}_particles_per_sec",
                 config={"workload": spec["label"], "bonds_per_step": n_bonds}, h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
                 keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds},
-                algo_per_step=True)
+                algo_per_step=True,
+                # measured DRAM bytes of one launch of the client's kernel (ncu, profiles/ncu_r1_v8_summary.md; the 2-D
+                # workloads launch it in chunks of 16.7 M bonds, one chunk was captured)
+                traffic={"pmftxyz": {"pmft3": 294862336 + 7012096}, "pmftxyt": {"pmft3": 341697536 + 5376512},
+                         "pmftr12": {"pmft3": 408724736 + 6640128}, "bond_order": {"bond_order": 240091648 + 5901312}}
+                [name] if n in (1_000_000, 1_000_188) else {})
 
 
 def cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=12.0, threads=None):
@@ -821,7 +832,7 @@ def main():
             roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(name),
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                          "capture of this workload (profiles/ncu_r1_v6_summary.md)"
+                                          "capture of this workload (profiles/ncu_r1_v6_summary.md, ncu_r1_v8_summary.md)"
                         if w.get("traffic", {}).get(name) else None,
                         "avg_launch_ms": round(avg_ms, 4),
                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
