@@ -30,6 +30,7 @@ SIGNATURES = {
     "fgpu_device_count": (C.c_int, []),
     "fgpu_ctx_create": (C.c_int, [C.c_int, _vpp]),
     "fgpu_ctx_destroy": (None, [_vp]),
+    "fgpu_ctx_trim": (C.c_int, [_vp]),
     "fgpu_ctx_synchronize": (C.c_int, [_vp]),
     "fgpu_ctx_stream": (_vp, [_vp]),
     "fgpu_ctx_launch_count": (C.c_uint64, [_vp]),
@@ -211,6 +212,10 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         check(lib().fgpu_ctx_kernel_time(self._h, prefix.encode(), C.byref(ms), C.byref(n), int(reset)))
         return ms.value, int(n.value)
+
+    def trim(self):
+        """Release the context's grow-only scratch and the arrays kept from the last NeighborList (``fgpu_ctx_trim``)."""
+        check(lib().fgpu_ctx_trim(self._h))
 
     def close(self):
         if self._h:

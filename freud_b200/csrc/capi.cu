@@ -697,6 +697,33 @@ int fgpu_ctx_create(int device, fgpu_ctx** out)
     });
 }
 
+int fgpu_ctx_trim(fgpu_ctx* ctx)
+{
+    return guarded([&] {
+        require(ctx != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(ctx);
+        NlistStorage empty;
+        ctx->spare_nlist.swap(empty); // freed when `empty` goes out of scope
+        ctx->bag.release();
+        ctx->bag4.release();
+        ctx->bag4b.release();
+        ctx->tmp_start.release();
+        ctx->knn_hits.release();
+        ctx->knn_unresolved.release();
+        ctx->knn_subset.release();
+        ctx->knn_d.release();
+        ctx->knn_s.release();
+        ctx->q_stage.release();
+        ctx->q_sorted.release();
+        ctx->row_counts.release();
+        ctx->row_start.release();
+        sync(ctx);
+        cudaMemPool_t pool = nullptr;
+        FGPU_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        FGPU_CUDA_CHECK(cudaMemPoolTrimTo(pool, 0));
+    });
+}
+
 void fgpu_ctx_destroy(fgpu_ctx* ctx)
 {
     if (ctx == nullptr)

@@ -62,6 +62,10 @@ int fgpu_device_count(void);
 /* ---- context -------------------------------------------------------------------------------------- */
 int fgpu_ctx_create(int device, fgpu_ctx** out);
 void fgpu_ctx_destroy(fgpu_ctx* ctx);
+/* Hands the context's grow-only scratch (hit bags, the arrays kept from the last destroyed NeighborList, kNN scratch)
+ * back to the device's memory pool and trims the pool: after a frame far larger than the ones to come.  Everything is
+ * re-grown on demand; live objects (points, lists, histograms) are untouched. */
+int fgpu_ctx_trim(fgpu_ctx* ctx);
 int fgpu_ctx_synchronize(fgpu_ctx* ctx);
 /* the context's cudaStream_t, for callers that time with CUDA events on the launching stream */
 void* fgpu_ctx_stream(fgpu_ctx* ctx);

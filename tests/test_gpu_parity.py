@@ -431,6 +431,28 @@ def test_bond_order_over_a_neighbor_list(ctx):
             capi.DeviceBondOrder(ctx, n_theta, n_phi, mode)
 
 
+def test_context_trim_keeps_results_identical(ctx):
+    """fgpu_ctx_trim drops the grow-only scratch and the spare NeighborList arrays; the next queries re-grow them and give
+    the same lists; a list that is alive across the trim is untouched."""
+    from freud_b200.box import Box
+
+    capi = _capi()
+    box = Box(14, 15, 16, 0.3, 0.2, 0.1)
+    pts = random_points(box, 3000, 5)
+    dp = capi.DevicePoints(ctx, box, pts)
+    first = dp.ball_query(None, IMAGE, 3.0, 0.0, True).to_host()
+    alive = dp.knn_query(None, 6, exclude_ii=True)
+    ctx.trim()
+    again = dp.ball_query(None, IMAGE, 3.0, 0.0, True).to_host()
+    for key in ("neighbors", "distances", "weights", "vectors", "segments", "counts"):
+        assert np.array_equal(first[key], again[key]), key
+    want = port.knn_nlist(box, False, pts, pts, 6, exclude_ii=True)
+    assert np.array_equal(alive.to_host()["neighbors"], want.neighbors)
+    ctx.trim()
+    ctx.trim()
+    assert np.array_equal(dp.knn_query(None, 6, exclude_ii=True).to_host()["neighbors"], want.neighbors)
+
+
 def test_correlation_function_over_a_neighbor_list(ctx):
     """fgpu_corr_* (CorrelationFunction.cc:26-95) over device NeighborLists against the committed outputs of the
     reference: bin counts identical, complex<double> sums to double rounding; accumulation over two calls."""
