@@ -347,20 +347,20 @@ def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
         # the orientations (4 MB) are taken from the host in every call
         pm.reset()
         dp.build_cells(r_max)
-        pm.accumulate_nlist(dp.ball_query(None, IMAGE, r_max, 0.0, True), angles)
+        pm.accumulate(dp, None, IMAGE, r_max, angles, exclude_ii=True)  # query + histogram, no NeighborList
         return pm.read()
 
     def step_e2e():
         pm.reset()
         d = _capi.DevicePoints(ctx, box, pin_pts)
-        pm.accumulate_nlist(d.ball_query(None, IMAGE, r_max, 0.0, True), angles)
+        pm.accumulate(d, None, IMAGE, r_max, angles, exclude_ii=True)
         return pm.read()
 
     n_cells = int(np.prod(dp.build_cells(r_max)))
     nb = bins[0] * bins[1]
     algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
             "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
-            "pmft3": 20 * n_bonds + 4 * n + 4 * nb,  # (i, v.x, v.y, v.z stride) per bond + the angle per query
+            "pmft3_rows": 16 * n_bonds + 12 * n + 4 * nb,  # 16 B bag record per bond; offset, count and angle per query
             "pipeline": 16 * (n + n) + 8 * n + 4 * nb}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="pmftxy_particles_per_sec",
                 config={"workload": f"PMFTXY x_max={x_max:g} y_max={y_max:g} bins={bins[0]}x{bins[1]} (ball query "
@@ -454,10 +454,13 @@ def workload_hist_client(ctx, rank, n, name):
     else:
         hist = _capi.DevicePMFT(ctx, spec["kind"], spec["maxes"], spec["bins"])
         equiv = np.float32([[1, 0, 0, 0]])
-        query = lambda d: d.ball_query(None, IMAGE, spec["r_max"], 0.0, True)
-        accumulate = lambda nl: hist.accumulate_nlist(nl, pin_o, pin_o, equiv)
-        kernel, r_build = "pmft3", spec["r_max"]
-    n_bonds = query(dp).num_bonds
+        # the call behind PMFT*.compute(system, orientations) without a NeighborList handed in: query and histogram
+        # in one call, the bonds go from the search's bag straight into the bins
+        query = lambda d: d
+        accumulate = lambda d: hist.accumulate(d, None, IMAGE, spec["r_max"], pin_o, pin_o, equiv, exclude_ii=True)
+        kernel, r_build = "pmft3_rows", spec["r_max"]
+    n_bonds = (dp.knn_query(None, spec["k"], exclude_ii=True) if name == "bond_order"
+               else dp.ball_query(None, IMAGE, spec["r_max"], 0.0, True)).num_bonds
 
     def step_dev():
         hist.reset()
@@ -495,11 +498,8 @@ def workload_hist_client(ctx, rank, n, name):
                 config={"workload": spec["label"], "bonds_per_step": n_bonds}, h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
                 keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds},
                 algo_per_step=True,
-                # measured DRAM bytes of one launch of the client's kernel (ncu, profiles/ncu_r1_v8_summary.md; the 2-D
-                # workloads launch it in chunks of 16.7 M bonds, one chunk was captured)
-                traffic={"pmftxyz": {"pmft3": 294862336 + 7012096}, "pmftxyt": {"pmft3": 341697536 + 5376512},
-                         "pmftr12": {"pmft3": 408724736 + 6640128}, "bond_order": {"bond_order": 240091648 + 5901312}}
-                [name] if n in (1_000_000, 1_000_188) else {})
+                # measured DRAM bytes of one launch of the client's kernel (ncu, profiles/ncu_r1_v8_summary.md)
+                traffic={"bond_order": 240091648 + 5901312} if name == "bond_order" and n == 1_000_188 else {})
 
 
 def cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=12.0, threads=None):
@@ -777,7 +777,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy", "pmft3", "bond_order", "pmft_add_bins")
+             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]

@@ -71,11 +71,14 @@ SIGNATURES = {
     "fgpu_pmftxy_destroy": (None, [_vp]),
     "fgpu_pmftxy_reset": (C.c_int, [_vp]),
     "fgpu_pmftxy_accumulate_nlist": (C.c_int, [_vp, _vp, _fp]),
+    "fgpu_pmftxy_accumulate": (C.c_int, [_vp, _vp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, _fp]),
     "fgpu_pmftxy_read": (C.c_int, [_vp, _up]),
     "fgpu_pmft_create": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, _vpp]),
     "fgpu_pmft_destroy": (None, [_vp]),
     "fgpu_pmft_reset": (C.c_int, [_vp]),
     "fgpu_pmft_accumulate_nlist": (C.c_int, [_vp, _vp, _fp, C.c_uint32, _fp, _fp, C.c_uint32]),
+    "fgpu_pmft_accumulate": (C.c_int, [_vp, _vp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, _fp, _fp, _fp,
+                                       C.c_uint32]),
     "fgpu_pmft_read": (C.c_int, [_vp, _up]),
     "fgpu_pmft_deferred": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "fgpu_bondorder_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _vpp]),
@@ -419,6 +422,16 @@ class DevicePMFTXY(_DeviceObject):
         assert len(t) == nlist.num_query_points
         check(lib().fgpu_pmftxy_accumulate_nlist(self._h, nlist._h, ptr(t)))
 
+    def accumulate(self, points, query_points, flavour, r_max, query_orientations, r_min=0.0, exclude_ii=False):
+        """Ball query of ``points`` (``query_points=None``: against themselves) and the histogram in one call -- no
+        NeighborList (``fgpu_pmftxy_accumulate``)."""
+        q = None if query_points is None else f32(query_points, 3)
+        nq = points.n if q is None else len(q)
+        t = np.ascontiguousarray(query_orientations, dtype=np.float32).ravel()
+        assert len(t) == nq
+        check(lib().fgpu_pmftxy_accumulate(self._h, points._h, ptr(q), nq, int(flavour), float(r_max), float(r_min),
+                                           int(bool(exclude_ii)), ptr(t)))
+
     def read(self):
         counts = np.empty(self.shape, np.uint32)
         check(lib().fgpu_pmftxy_read(self._h, ptr(counts, _up)))
@@ -455,6 +468,24 @@ class DevicePMFT(_DeviceObject):
         o = np.ascontiguousarray(orientations, dtype=np.float32).ravel()
         assert len(o) == nlist.num_points and qo.size == nlist.num_query_points
         check(lib().fgpu_pmft_accumulate_nlist(self._h, nlist._h, ptr(o), len(o), ptr(qo), None, 0))
+
+    def accumulate(self, points, query_points, flavour, r_max, orientations, query_orientations, equiv_orientations=None,
+                   r_min=0.0, exclude_ii=False):
+        """Ball query of ``points`` (``query_points=None``: against themselves) and the histogram in one call -- no
+        NeighborList (``fgpu_pmft_accumulate``); orientation arguments as ``accumulate_nlist``."""
+        q = None if query_points is None else f32(query_points, 3)
+        nq = points.n if q is None else len(q)
+        qo = np.ascontiguousarray(query_orientations, dtype=np.float32)
+        o = eq = None
+        if self.kind == PMFT_XYZ:
+            eq = np.ascontiguousarray(equiv_orientations, dtype=np.float32).reshape(-1, 4)
+            assert qo.shape == (nq, 4)
+        else:
+            o = np.ascontiguousarray(orientations, dtype=np.float32).ravel()
+            assert len(o) == points.n and qo.size == nq
+        check(lib().fgpu_pmft_accumulate(self._h, points._h, ptr(q), nq, int(flavour), float(r_max), float(r_min),
+                                         int(bool(exclude_ii)), ptr(o) if o is not None else None, ptr(qo),
+                                         ptr(eq) if eq is not None else None, 0 if eq is None else len(eq)))
 
     def read(self):
         counts = np.empty(self.shape, np.uint32)

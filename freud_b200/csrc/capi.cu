@@ -1654,6 +1654,167 @@ int fgpu_pmft_reset(fgpu_pmft* pmft)
     });
 }
 
+namespace {
+
+struct PmftHostInputs
+{
+    const float* orientations;
+    const float* query_orientations;
+};
+
+// uploads the orientations of one frame and fills the kernel arguments that do not depend on where the bonds are
+Pmft3Args stage_pmft(fgpu_pmft* pmft, uint32_t n_points, uint32_t n_query, const float* orientations_host,
+                     const float* query_orientations_host, const float* equiv_orientations_host, uint32_t n_equiv)
+{
+    fgpu_ctx* ctx = pmft->ctx;
+    int const kind = pmft->kind;
+    Pmft3Args a {};
+    a.a0 = pmft->a0;
+    a.a1 = pmft->a1;
+    a.a2 = pmft->a2;
+    a.hist = pmft->hist.ptr;
+    if (kind == FGPU_PMFT_XYZ)
+    {
+        require(equiv_orientations_host != nullptr && n_equiv >= 1, FGPU_EINVALID,
+                "PMFTXYZ needs at least one equivalent orientation");
+        pmft->stage_a.reserve(4 * (size_t) n_query + 4);
+        pmft->stage_b.reserve(4 * (size_t) n_equiv);
+        h2d(ctx, pmft->stage_a.ptr, query_orientations_host, 4 * (size_t) n_query * sizeof(float));
+        h2d(ctx, pmft->stage_b.ptr, equiv_orientations_host, 4 * (size_t) n_equiv * sizeof(float));
+        a.query_quats = reinterpret_cast<const float4*>(pmft->stage_a.ptr);
+        a.equiv_quats = reinterpret_cast<const float4*>(pmft->stage_b.ptr);
+        a.n_equiv = n_equiv;
+        return a;
+    }
+    if (kind != FGPU_PMFT_XY)
+    {
+        require(orientations_host != nullptr, FGPU_EINVALID, "null orientations");
+        pmft->stage_b.reserve((size_t) n_points + 1);
+        h2d(ctx, pmft->stage_b.ptr, orientations_host, (size_t) n_points * sizeof(float));
+        a.orientations = pmft->stage_b.ptr;
+    }
+    pmft->stage_a.reserve((size_t) n_query + 1);
+    h2d(ctx, pmft->stage_a.ptr, query_orientations_host, (size_t) n_query * sizeof(float));
+    a.query_orientations = pmft->stage_a.ptr;
+    return a;
+}
+
+// One launch of the histogram kernel over the bonds `a` describes, counting into a.hist, with room for `cap` bonds
+// left to the host; those are binned here with the host's libm and added to a.hist.  Returns false -- nothing
+// reliable in a.hist -- if more than `cap` bonds were left over.
+bool run_pmft_pass(fgpu_pmft* pmft, Pmft3Args& a, uint64_t cap, const PmftHostInputs& in)
+{
+    fgpu_ctx* ctx = pmft->ctx;
+    int const kind = pmft->kind;
+    if (kind == FGPU_PMFT_XYZ)
+    {
+        launch_pmft3(ctx, kind, a);
+        return true;
+    }
+    pmft->deferred.reserve((size_t) cap);
+    if (kind == FGPU_PMFT_R12)
+    {
+        pmft->deferred_dist.reserve((size_t) cap);
+    }
+    a.deferred = pmft->deferred.ptr;
+    a.deferred_dist = pmft->deferred_dist.ptr;
+    a.deferred_cap = (uint32_t) cap;
+    a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
+    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
+    launch_pmft3(ctx, kind, a);
+    d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
+    sync(ctx);
+    uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
+    if (n_def > cap)
+    {
+        return false;
+    }
+    if (n_def == 0)
+    {
+        return true;
+    }
+    // the bonds whose coordinate or angle sits within a few ulps of a bin edge: the reference's own libm decides
+    std::vector<uint4> rec(n_def);
+    std::vector<float> rec_dist;
+    d2h(ctx, rec.data(), pmft->deferred.ptr, (size_t) n_def * sizeof(uint4));
+    if (kind == FGPU_PMFT_R12)
+    {
+        rec_dist.resize(n_def);
+        d2h(ctx, rec_dist.data(), pmft->deferred_dist.ptr, (size_t) n_def * sizeof(float));
+    }
+    sync(ctx);
+    // a few libm calls per bond: tens of thousands of bonds per frame are worth a handful of host threads
+    std::vector<uint32_t> slot(n_def);
+    uint32_t const kNone = 0xffffffffU;
+    auto bin_range = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t r = lo; r < hi; ++r)
+    {
+        uint32_t const i = rec[r].x, j = rec[r].y;
+        float vx, vy;
+        std::memcpy(&vx, &rec[r].z, sizeof(float));
+        std::memcpy(&vy, &rec[r].w, sizeof(float));
+        int c0, c1, c2;
+        if (kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_XY)
+        {
+            float const t = -in.query_orientations[i]; // rotmat2::fromAngle, VectorMath.h:912-921
+            float const c = std::cos(t), sn = std::sin(t);
+            volatile float x1 = c * vx, x2 = -sn * vy, y1 = sn * vx, y2 = c * vy;
+            c0 = host_axis_bin(a.a0, x1 + x2);
+            c1 = host_axis_bin(a.a1, y1 + y2);
+            c2 = 0;
+            if (kind == FGPU_PMFT_XYT)
+            {
+                float const d_theta = std::atan2(-vy, -vx); // PMFTXYT.cc:94
+                c2 = host_axis_bin(a.a2, host_mod_two_pi(in.orientations[j] - d_theta));
+            }
+        }
+        else
+        {
+            c0 = host_axis_bin(a.a0, rec_dist[r]);
+            float const d_theta1 = std::atan2(vy, vx), d_theta2 = std::atan2(-vy, -vx); // PMFTR12.cc:103-104
+            c1 = host_axis_bin(a.a1, host_mod_two_pi(in.orientations[j] - d_theta1));
+            c2 = host_axis_bin(a.a2, host_mod_two_pi(in.query_orientations[i] - d_theta2));
+        }
+        slot[r] = c0 >= 0 && c1 >= 0 && c2 >= 0 ? ((uint32_t) c0 * a.a1.bins + (uint32_t) c1) * a.a2.bins + (uint32_t) c2
+                                                : kNone;
+    }
+    };
+    unsigned const n_threads = n_def >= 4096 ? std::max(1U, std::min(8U, std::thread::hardware_concurrency())) : 1U;
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_threads; ++t)
+        {
+            pool.emplace_back(bin_range, (uint32_t) ((uint64_t) n_def * t / n_threads),
+                              (uint32_t) ((uint64_t) n_def * (t + 1) / n_threads));
+        }
+        bin_range(0, n_def / n_threads);
+        for (auto& th : pool)
+        {
+            th.join();
+        }
+    }
+    std::vector<uint32_t> bins;
+    bins.reserve(n_def);
+    for (uint32_t r = 0; r < n_def; ++r)
+    {
+        if (slot[r] != kNone)
+        {
+            bins.push_back(slot[r]);
+        }
+    }
+    pmft->deferred_total += n_def;
+    if (!bins.empty())
+    {
+        pmft->host_bins.reserve(bins.size());
+        h2d(ctx, pmft->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
+        launch_add_bins(ctx, pmft->host_bins.ptr, (uint32_t) bins.size(), a.hist);
+        sync(ctx); // `bins` goes out of scope
+    }
+    return true;
+}
+
+} // namespace
+
 int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const float* orientations_host, uint32_t n_points,
                                const float* query_orientations_host, const float* equiv_orientations_host,
                                uint32_t n_equiv)
@@ -1662,41 +1823,10 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
         require(pmft != nullptr && nl != nullptr && query_orientations_host != nullptr, FGPU_EINVALID, "null argument");
         require(pmft->ctx == nl->ctx, FGPU_EINVALID, "pmft and nlist belong to different contexts");
         fgpu_ctx* ctx = pmft->ctx;
-        int const kind = pmft->kind;
         bind_device(ctx);
-        Pmft3Args a {};
-        a.a0 = pmft->a0;
-        a.a1 = pmft->a1;
-        a.a2 = pmft->a2;
-        a.hist = pmft->hist.ptr;
-        if (kind == FGPU_PMFT_XYZ)
-        {
-            require(equiv_orientations_host != nullptr && n_equiv >= 1, FGPU_EINVALID,
-                    "PMFTXYZ needs at least one equivalent orientation");
-            pmft->stage_a.reserve(4 * (size_t) nl->n_query + 4);
-            pmft->stage_b.reserve(4 * (size_t) n_equiv);
-            h2d(ctx, pmft->stage_a.ptr, query_orientations_host, 4 * (size_t) nl->n_query * sizeof(float));
-            h2d(ctx, pmft->stage_b.ptr, equiv_orientations_host, 4 * (size_t) n_equiv * sizeof(float));
-            a.query_quats = reinterpret_cast<const float4*>(pmft->stage_a.ptr);
-            a.equiv_quats = reinterpret_cast<const float4*>(pmft->stage_b.ptr);
-            a.n_equiv = n_equiv;
-        }
-        else
-        {
-            if (kind != FGPU_PMFT_XY)
-            {
-                require(orientations_host != nullptr, FGPU_EINVALID, "null orientations");
-                pmft->stage_b.reserve((size_t) n_points + 1);
-                h2d(ctx, pmft->stage_b.ptr, orientations_host, (size_t) n_points * sizeof(float));
-                a.orientations = pmft->stage_b.ptr;
-            }
-            pmft->stage_a.reserve((size_t) nl->n_query + 1);
-            h2d(ctx, pmft->stage_a.ptr, query_orientations_host, (size_t) nl->n_query * sizeof(float));
-            a.query_orientations = pmft->stage_a.ptr;
-        }
-        std::vector<uint4> rec;
-        std::vector<float> rec_dist;
-        std::vector<uint32_t> bins;
+        Pmft3Args a = stage_pmft(pmft, n_points, nl->n_query, orientations_host, query_orientations_host,
+                                 equiv_orientations_host, n_equiv);
+        PmftHostInputs const in {orientations_host, query_orientations_host};
         for (uint64_t b0 = 0; b0 < nl->n_bonds; b0 += kPmftChunk)
         {
             uint64_t const nb = std::min<uint64_t>(kPmftChunk, nl->n_bonds - b0);
@@ -1704,83 +1834,122 @@ int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const floa
             a.vectors = nl->vectors.ptr + 3 * b0;
             a.distances = nl->distances.ptr + b0;
             a.n_bonds = nb;
-            if (kind != FGPU_PMFT_XYZ)
+            run_pmft_pass(pmft, a, nb, in); // room for every bond of the chunk: cannot fail
+        }
+        sync(ctx); // the caller's arrays were consumed
+    });
+}
+
+// The query and the histogram in one call, without a NeighborList: the search leaves its hits in the bag, grouped by
+// query row, and the histogram kernel reads them there (k_pmft3<., ROWS>) -- no ranking, no 28 B per bond written and
+// read back.  The frame is counted into a histogram of its own first, so that a frame that leaves more bonds to the
+// host than the list has room for can simply be repeated with a longer list.
+int fgpu_pmft_accumulate(fgpu_pmft* pmft, fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour,
+                         float r_max, float r_min, int exclude_ii, const float* orientations_host,
+                         const float* query_orientations_host, const float* equiv_orientations_host, uint32_t n_equiv)
+{
+    return guarded([&] {
+        require(pmft != nullptr && pts != nullptr && query_orientations_host != nullptr, FGPU_EINVALID, "null argument");
+        require(pmft->ctx == pts->ctx, FGPU_EINVALID, "pmft and points belong to different contexts");
+        fgpu_ctx* ctx = pmft->ctx;
+        bind_device(ctx);
+        validate_ball(pts, flavour, r_max, r_min);
+        bool const self = query_points_host == nullptr;
+        require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
+        bool fused = false;
+        uint64_t n_bonds = 0;
+        if (n_query != 0 && !ctx->force_general)
+        {
+            build_grid(pts, r_max);
+            QueryView const qv = prepare_queries(pts, query_points_host, nullptr, n_query);
+            Search2Args s2 = base_search2_args(pts, qv, 0, r_max, r_min, exclude_ii);
+            if (search2_supported(s2, S2_NL))
             {
-                pmft->deferred.reserve((size_t) nb);
-                if (kind == FGPU_PMFT_R12)
+                double const vol = box_volume(pts->box);
+                double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max
+                                                   : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
+                uint64_t cap = ctx->bag_hint != 0
+                    ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
+                    : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
+                ctx->tmp_start.reserve((size_t) n_query + 1);
+                ctx->row_counts.reserve((size_t) n_query + 1);
+                launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+                s2.evals = nullptr;
+                for (int attempt = 0; attempt < 4 && !fused; ++attempt)
                 {
-                    pmft->deferred_dist.reserve((size_t) nb);
-                }
-                a.deferred = pmft->deferred.ptr;
-                a.deferred_dist = pmft->deferred_dist.ptr;
-                a.deferred_cap = (uint32_t) nb;
-                a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
-                FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
-            }
-            launch_pmft3(ctx, kind, a);
-            if (kind == FGPU_PMFT_XYZ)
-            {
-                continue;
-            }
-            d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
-            sync(ctx);
-            uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
-            if (n_def == 0)
-            {
-                continue;
-            }
-            // the bonds whose angle sits within a few ulps of a bin edge: the reference's own libm decides
-            rec.resize(n_def);
-            d2h(ctx, rec.data(), pmft->deferred.ptr, (size_t) n_def * sizeof(uint4));
-            if (kind == FGPU_PMFT_R12)
-            {
-                rec_dist.resize(n_def);
-                d2h(ctx, rec_dist.data(), pmft->deferred_dist.ptr, (size_t) n_def * sizeof(float));
-            }
-            sync(ctx);
-            bins.clear();
-            for (uint32_t r = 0; r < n_def; ++r)
-            {
-                uint32_t const i = rec[r].x, j = rec[r].y;
-                float vx, vy;
-                std::memcpy(&vx, &rec[r].z, sizeof(float));
-                std::memcpy(&vy, &rec[r].w, sizeof(float));
-                int c0, c1, c2;
-                if (kind == FGPU_PMFT_XYT || kind == FGPU_PMFT_XY)
-                {
-                    float const t = -query_orientations_host[i]; // rotmat2::fromAngle, VectorMath.h:912-921
-                    float const c = std::cos(t), sn = std::sin(t);
-                    volatile float x1 = c * vx, x2 = -sn * vy, y1 = sn * vx, y2 = c * vy;
-                    c0 = host_axis_bin(a.a0, x1 + x2);
-                    c1 = host_axis_bin(a.a1, y1 + y2);
-                    c2 = 0;
-                    if (kind == FGPU_PMFT_XYT)
+                    cap = std::min<uint64_t>(cap, 0xffffffffULL);
+                    ctx->bag4.reserve(cap);
+                    s2.bag = ctx->bag4.ptr;
+                    s2.temp_cap = (uint32_t) cap;
+                    s2.counts = ctx->row_counts.ptr;
+                    s2.tmp_start = ctx->tmp_start.ptr;
+                    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+                    launch_search2(ctx, flavour, S2_NL, s2);
+                    d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
+                    sync(ctx);
+                    int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+                    uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
+                    if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
                     {
-                        float const d_theta = std::atan2(-vy, -vx); // PMFTXYT.cc:94
-                        c2 = host_axis_bin(a.a2, host_mod_two_pi(orientations_host[j] - d_theta));
+                        s2.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
+                    }
+                    else if (fail != 0)
+                    {
+                        break; // points outside the box or a tile beyond the largest buffer: the general kernels
+                    }
+                    else if (ctx->h_scalars[5] <= cap)
+                    {
+                        n_bonds = ctx->h_scalars[5];
+                        fused = true;
+                    }
+                    else
+                    {
+                        cap = ctx->h_scalars[5]; // exact size, the search is deterministic
                     }
                 }
-                else
-                {
-                    c0 = host_axis_bin(a.a0, rec_dist[r]);
-                    float const d_theta1 = std::atan2(vy, vx), d_theta2 = std::atan2(-vy, -vx); // PMFTR12.cc:103-104
-                    c1 = host_axis_bin(a.a1, host_mod_two_pi(orientations_host[j] - d_theta1));
-                    c2 = host_axis_bin(a.a2, host_mod_two_pi(query_orientations_host[i] - d_theta2));
-                }
-                if (c0 >= 0 && c1 >= 0 && c2 >= 0)
-                {
-                    bins.push_back(((uint32_t) c0 * a.a1.bins + (uint32_t) c1) * a.a2.bins + (uint32_t) c2);
-                }
-            }
-            pmft->deferred_total += n_def;
-            if (!bins.empty())
-            {
-                pmft->host_bins.reserve(bins.size());
-                h2d(ctx, pmft->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
-                launch_add_bins(ctx, pmft->host_bins.ptr, (uint32_t) bins.size(), pmft->hist.ptr);
-                sync(ctx); // `bins` is reused by the next chunk
             }
         }
+        if (!fused)
+        {
+            // tiny grids, points outside the box, ...: through a NeighborList
+            fgpu_nlist* nl = nullptr;
+            ball_query_impl(pts, query_points_host, nullptr, n_query, 0, flavour, r_max, r_min, exclude_ii, 0, &nl);
+            std::unique_ptr<fgpu_nlist, void (*)(fgpu_nlist*)> guard(nl, fgpu_nlist_destroy);
+            int const rc = fgpu_pmft_accumulate_nlist(pmft, nl, orientations_host, pts->n, query_orientations_host,
+                                                      equiv_orientations_host, n_equiv);
+            if (rc != FGPU_OK)
+            {
+                throw Error(rc, fgpu_last_error());
+            }
+            return;
+        }
+        ctx->bag_hint = n_bonds;
+        Pmft3Args a = stage_pmft(pmft, pts->n, n_query, orientations_host, query_orientations_host,
+                                 equiv_orientations_host, n_equiv);
+        PmftHostInputs const in {orientations_host, query_orientations_host};
+        size_t const n_bins = (size_t) pmft->a0.bins * pmft->a1.bins * pmft->a2.bins;
+        pmft->frame_hist.reserve(n_bins);
+        a.hist = pmft->frame_hist.ptr;
+        a.bag = ctx->bag4.ptr;
+        a.row_bag_start = ctx->tmp_start.ptr;
+        a.row_counts = ctx->row_counts.ptr;
+        a.n_rows = n_query;
+        double const per_row = (double) n_bonds / (double) n_query;
+        a.group = per_row < 6.0 ? 4U : (per_row <= 96.0 ? 8U : 32U);
+        uint64_t room = std::min<uint64_t>(std::max<uint64_t>(n_bonds / 16, 4096), n_bonds);
+        uint64_t const before = pmft->deferred_total;
+        for (;;)
+        {
+            FGPU_CUDA_CHECK(cudaMemsetAsync(pmft->frame_hist.ptr, 0, n_bins * sizeof(uint32_t), ctx->stream));
+            pmft->deferred_total = before;
+            if (run_pmft_pass(pmft, a, room, in))
+            {
+                break;
+            }
+            room = n_bonds; // e.g. a lattice whose every bond angle sits on a bin edge
+        }
+        launch_add_hist(ctx, pmft->frame_hist.ptr, (uint32_t) n_bins, pmft->hist.ptr);
         sync(ctx); // the caller's arrays were consumed
     });
 }
@@ -1839,6 +2008,13 @@ int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const 
 {
     return fgpu_pmft_accumulate_nlist(pmft == nullptr ? nullptr : pmft->inner, nl, nullptr, 0, query_orientations_host,
                                       nullptr, 0);
+}
+
+int fgpu_pmftxy_accumulate(fgpu_pmftxy* pmft, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                           int flavour, float r_max, float r_min, int exclude_ii, const float* query_orientations_host)
+{
+    return fgpu_pmft_accumulate(pmft == nullptr ? nullptr : pmft->inner, pts, query_points_host, n_query, flavour, r_max,
+                                r_min, exclude_ii, nullptr, query_orientations_host, nullptr, 0);
 }
 
 int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host)

@@ -243,6 +243,7 @@ struct fgpu_pmft
     fgpu::DevBuf<uint4> deferred;     // bonds whose angle bin is left to the host's libm: (i, j, bits vx, bits vy)
     fgpu::DevBuf<float> deferred_dist;
     fgpu::DevBuf<uint32_t> host_bins; // ... and the bins the host found for them
+    fgpu::DevBuf<uint32_t> frame_hist; // fused path: the histogram of the frame being accumulated
     uint64_t deferred_total = 0;      // statistics: bonds the host binned since the last reset
 };
 
@@ -521,6 +522,12 @@ struct Pmft3Args
     const float* vectors;
     const float* distances;
     uint64_t n_bonds;
+    // ... or the bonds still in the search's bag, grouped by query row (no NeighborList): bag != nullptr
+    const float4* bag;
+    const uint32_t* row_bag_start;
+    const uint32_t* row_counts;
+    uint32_t n_rows;
+    uint32_t group;                  // lanes per row: 4, 8 or 32
     const float* orientations;       // XYT, R12: per point
     const float* query_orientations; // XY, XYT, R12: per query point
     const float4* query_quats;       // XYZ: per query point, (s, x, y, z)
@@ -535,6 +542,7 @@ struct Pmft3Args
 };
 void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a);
 void launch_add_bins(fgpu_ctx* ctx, const uint32_t* bins, uint32_t n, uint32_t* hist);
+void launch_add_hist(fgpu_ctx* ctx, const uint32_t* frame, uint32_t n, uint32_t* hist);
 struct BondOrderArgs
 {
     AxisDev at, ap;

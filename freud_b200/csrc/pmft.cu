@@ -12,14 +12,14 @@
 //   R12  r = bond distance, t1 = modulusPositive(theta_j - atan2f(dy, dx), 2 pi),
 //        t2 = modulusPositive(theta_i - atan2f(-dy, -dx), 2 pi).
 //
-// atan2f is the host libm's in the reference and CUDA's differs from it in the last place (both are within 2-3 ulp of
-// the true value).  The angle bin only depends on those last places when t lies within a few float ulps of a bin
-// edge, so the kernel evaluates CUDA's atan2f, follows the reference's float chain from it, and accepts the bin only
-// if t is farther from every bin edge than any such difference can move it (kAngleMargin, several times the two error
-// bounds plus the rounding of the chain).  The few bonds inside a margin (~3 in 10^4) are written to a list and
-// binned by the host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per
-// bond.  cosf / sinf of the query particle's angle (rotmat2::fromAngle, VectorMath.h:912-921) get the same treatment:
-// CUDA's sincosf, and the rotated coordinate must clear every bin edge by more than a few last places of (cos, sin)
+// atan2f is the host libm's in the reference and CUDA's differs from it in the last place (both are within 2 ulp of
+// the true value).  Everything between atan2f and the bin index is float arithmetic that host and device evaluate
+// identically and that is monotone in the angle, so the kernel follows that chain from CUDA's atan2f and from the two
+// values a margin (twice the sum of the error bounds) below and above it: the same bin three times means the bin
+// cannot depend on whose atan2f it was.  Otherwise -- about 1 bond in 10^4 -- the bond goes to a list and is binned
+// by the host with its libm (capi.cu): counts are bit-identical to the reference's, and no libm call runs per bond.
+// cosf / sinf of the query particle's angle (rotmat2::fromAngle, VectorMath.h:912-921) get the same treatment: CUDA's
+// sincosf, and the rotated coordinate must land in the same bin when moved by what a few last places of (cos, sin)
 // can move it -- the host evaluates libm only for the bonds that do not (it used to for every particle).  (Double
 // precision atan2 / sincos were tried first: 390 instructions per bond, the kernel issue-bound at 0.59 ms per frame.)
 #include "internal.h"
@@ -30,7 +30,10 @@ namespace fgpu {
 namespace {
 
 constexpr float kTwoPi = 6.28318548202514648f; // (float) (2.0 * M_PI), Box.h:24
-constexpr float kAngleMargin = 1.0e-5f;        // >> (2 + 3) ulp of the two atan2f at pi (1.2e-6) + the chain's roundings (1e-6)
+// 2 ulp (CUDA) + 2 ulp (libm) of atan2f at pi = 9.6e-7: the margin is twice that.  kEdgeGuard keeps the kernel away
+// from the wrap of the modulus.
+constexpr float kAngleMargin = 2.0e-6f;
+constexpr float kEdgeGuard = 1.0e-5f;
 
 // fmodf(a, 2 pi) for moderate |a| without the library's bit-serial loop: the remainder of a truncated division is a
 // float, so |a| - q 2 pi comes out of one fused multiply-add exactly once q is the right integer (the quotient from
@@ -74,46 +77,47 @@ __device__ __forceinline__ float mod_two_pi(float a)
 }
 
 // Bin of t = modulusPositive(orientation - atan2f(y, x), 2 pi) on `axis` = RegularAxis(n, 0, 2 pi); *sure = false if a
-// last-place difference in atan2f could change it.
+// last-place difference in atan2f could change it.  The chain from d to the bin is float arithmetic that both sides
+// evaluate identically and that is monotone in d between two wraps of the modulus, so it is followed at d - m, d and
+// d + m (m = kAngleMargin covers the two atan2f): same bin at all three and no wrap in between -- t falls as d grows
+// -- settle it.  Close to 0 and 2 pi, where the modulus wraps (and can round onto 2 pi), the host decides.
 __device__ __forceinline__ int angle_bin(const AxisDev& axis, float orientation, float y, float x, bool* sure)
 {
     float const d = atan2f(y, x);
     float const t = mod_two_pi(__fsub_rn(orientation, d));
-    float const u = __fmul_rn(t, axis.inv_width);
-    float const frac = u - floorf(u);
-    float const margin = kAngleMargin * axis.inv_width + 1.0e-6f * (u + 1.0f);
-    // near 0 or 2 pi the wrap of the modulus sits on a bin edge too; a NaN orientation is never sure
-    *sure = frac > margin && frac < 1.0f - margin && t > kAngleMargin && t < kTwoPi - kAngleMargin;
-    return axis_bin(axis, t);
+    float const t_lo = mod_two_pi(__fsub_rn(orientation, d + kAngleMargin));
+    float const t_hi = mod_two_pi(__fsub_rn(orientation, d - kAngleMargin));
+    int const bin = axis_bin(axis, t);
+    // a NaN orientation is never sure
+    *sure = axis_bin(axis, t_lo) == bin && axis_bin(axis, t_hi) == bin && t_lo <= t && t <= t_hi && t > kEdgeGuard
+        && t < kTwoPi - kEdgeGuard;
+    return bin;
 }
 
-// Bin of `value` on a RegularAxis when `value` is only known to +-slack: *sure = false if some value within the slack
-// falls into another bin (or on the other side of an end of the axis).
+// Bin of `value` on a RegularAxis when `value` is only known to +-slack: the bin is a monotone function of the value
+// (float arithmetic both sides evaluate identically), so the bins of value - slack and value + slack decide: equal ->
+// settled (both outside: the bond is dropped for good), else the host decides.
 __device__ __forceinline__ int slack_bin(const AxisDev& axis, float value, float slack, bool* sure)
 {
-    float const u = (value - axis.r_min) * axis.inv_width;
-    float const m = slack * axis.inv_width + 1.0e-6f * (fabsf(u) + 1.0f);
-    float const n = (float) axis.bins;
-    if (u < -m || u > n + m)
+    int const lo = axis_bin(axis, value - slack), hi = axis_bin(axis, value + slack);
+    if (lo == hi)
     {
-        return -1; // outside for every value within the slack
+        return lo;
     }
-    float const frac = u - floorf(u);
-    bool const clear = frac > m && frac < 1.0f - m && u > m && u < n - m;
-    *sure = *sure && clear;
-    int const bin = axis_bin(axis, value);
-    return clear ? bin : max(bin, 0); // not clear: the host decides, also whether the bond is inside at all
+    *sure = false;
+    return max(axis_bin(axis, value), 0); // the host decides, also whether the bond is inside at all
 }
 
 // (x, y) = rotmat2::fromAngle(-theta) * (vx, vy), VectorMath.h:912-936, with CUDA's sincosf (2 ulp); the slack of the
-// result covers its difference to libm's cosf / sinf (1 ulp) several times
+// result covers its difference to libm's cosf / sinf (1 ulp each way: < 2e-7 (|vx| + |vy|)) and the roundings of
+// the two products and the sum, which may fall differently for a neighbouring (cos, sin) (< 1.5 ulp of |v|)
 __device__ __forceinline__ void rotate_xy(float theta, float vx, float vy, float& rx, float& ry, float& slack)
 {
     float c, sn;
     sincosf(-theta, &sn, &c);
     rx = __fadd_rn(__fmul_rn(c, vx), __fmul_rn(-sn, vy));
     ry = __fadd_rn(__fmul_rn(sn, vx), __fmul_rn(c, vy));
-    slack = 1.0e-6f * (fabsf(vx) + fabsf(vy)); // 3 ulp of (cos, sin) move a coordinate by < 2e-7 (|vx| + |vy|)
+    slack = 5.0e-7f * (fabsf(vx) + fabsf(vy));
 }
 
 // rotate(q, v), VectorMath.h:810-818: (s^2 - v.v) b + (2 s) (v x b) + (2 v.b) v, one rounding per operation
@@ -135,7 +139,74 @@ __device__ __forceinline__ void quat_rotate(float s, float qx, float qy, float q
     z = oz;
 }
 
-template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
+// One bond of the histogram: i = query point, j = point, (vx, vy, vz) = bond vector, dist = its length (R12)
+template<int KIND, typename Count>
+__device__ __forceinline__ void pmft3_bond(const Pmft3Args& a, uint32_t i, uint32_t j, float vx, float vy, float vz,
+                                           float dist, Count count)
+{
+    if (KIND == FGPU_PMFT_XYZ)
+    {
+        float4 const q = a.query_quats[i]; // (s, x, y, z); conj: (s, -v), VectorMath.h:765
+        float x = vx, y = vy, z = vz;
+        quat_rotate(q.x, -q.y, -q.z, -q.w, x, y, z);
+        for (uint32_t e = 0; e < a.n_equiv; ++e)
+        {
+            float4 const eq = a.equiv_quats[e];
+            float ex = x, ey = y, ez = z;
+            quat_rotate(eq.x, eq.y, eq.z, eq.w, ex, ey, ez);
+            count(axis_bin(a.a0, ex), axis_bin(a.a1, ey), axis_bin(a.a2, ez));
+        }
+        return;
+    }
+    bool sure = true;
+    int b0, b1, b2;
+    if (KIND == FGPU_PMFT_XYT || KIND == FGPU_PMFT_XY)
+    {
+        float rx, ry, slack;
+        rotate_xy(a.query_orientations[i], vx, vy, rx, ry, slack);
+        b0 = slack_bin(a.a0, rx, slack, &sure);
+        b1 = slack_bin(a.a1, ry, slack, &sure);
+        b2 = 0;
+        if (KIND == FGPU_PMFT_XYT && b0 >= 0 && b1 >= 0)
+        {
+            bool sure_t = true;
+            b2 = angle_bin(a.a2, a.orientations[j], -vy, -vx, &sure_t);
+            sure = sure && sure_t;
+        }
+    }
+    else
+    {
+        bool sure1 = true, sure2 = true;
+        b0 = axis_bin(a.a0, dist);
+        b1 = angle_bin(a.a1, a.orientations[j], vy, vx, &sure1);
+        b2 = angle_bin(a.a2, a.query_orientations[i], -vy, -vx, &sure2);
+        sure = sure1 && sure2;
+    }
+    if (b0 < 0 || (KIND != FGPU_PMFT_R12 && b1 < 0))
+    {
+        return; // surely outside an axis
+    }
+    if (sure)
+    {
+        count(b0, b1, b2);
+    }
+    else
+    {
+        uint32_t const slot = atomicAdd(a.deferred_count, 1U);
+        if (slot < a.deferred_cap)
+        {
+            a.deferred[slot] = make_uint4(i, j, __float_as_uint(vx), __float_as_uint(vy));
+            if (KIND == FGPU_PMFT_R12)
+            {
+                a.deferred_dist[slot] = dist;
+            }
+        }
+    }
+}
+
+// ROWS = false: one thread per bond of a NeighborList.  ROWS = true: the bonds are still in the search's bag (no
+// NeighborList was built): a group of lanes per query row, over the row's records {bond vector, bits(point index)}.
+template<int KIND, bool ROWS> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
 {
     extern __shared__ uint32_t p3_hist[];
     uint32_t const n_bins = a.a0.bins * a.a1.bins * a.a2.bins;
@@ -154,67 +225,30 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
             atomicAdd(&h[((uint32_t) b0 * a.a1.bins + (uint32_t) b1) * a.a2.bins + (uint32_t) b2], 1U);
         }
     };
-    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
+    if (ROWS)
     {
-        uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
-        float const vx = a.vectors[3 * k], vy = a.vectors[3 * k + 1];
-        if (KIND == FGPU_PMFT_XYZ)
+        // a.group (4, 8 or 32) lanes share a row: rows of a few dozen bonds would leave most of a whole warp idle
+        uint32_t const g = a.group, sub = threadIdx.x & (g - 1U);
+        uint32_t const groups = gridDim.x * blockDim.x / g;
+        for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / g; row < a.n_rows; row += groups)
         {
-            float4 const q = a.query_quats[ij.x]; // (s, x, y, z); conj: (s, -v), VectorMath.h:765
-            float x = vx, y = vy, z = a.vectors[3 * k + 2];
-            quat_rotate(q.x, -q.y, -q.z, -q.w, x, y, z);
-            for (uint32_t e = 0; e < a.n_equiv; ++e)
+            uint32_t const n = a.row_counts[row], start = a.row_bag_start[row];
+            for (uint32_t k = sub; k < n; k += g)
             {
-                float4 const eq = a.equiv_quats[e];
-                float ex = x, ey = y, ez = z;
-                quat_rotate(eq.x, eq.y, eq.z, eq.w, ex, ey, ez);
-                count(axis_bin(a.a0, ex), axis_bin(a.a1, ey), axis_bin(a.a2, ez));
-            }
-            continue;
-        }
-        bool sure = true;
-        int b0, b1, b2;
-        if (KIND == FGPU_PMFT_XYT || KIND == FGPU_PMFT_XY)
-        {
-            float rx, ry, slack;
-            rotate_xy(a.query_orientations[ij.x], vx, vy, rx, ry, slack);
-            b0 = slack_bin(a.a0, rx, slack, &sure);
-            b1 = slack_bin(a.a1, ry, slack, &sure);
-            b2 = 0;
-            if (KIND == FGPU_PMFT_XYT && b0 >= 0 && b1 >= 0)
-            {
-                bool sure_t = true;
-                b2 = angle_bin(a.a2, a.orientations[ij.y], -vy, -vx, &sure_t);
-                sure = sure && sure_t;
+                float4 const r = a.bag[start + k];
+                float const dist = KIND == FGPU_PMFT_R12 ? __fsqrt_rn(dot_exact(r.x, r.y, r.z)) : 0.0f; // NeighborBond.h:41-44
+                pmft3_bond<KIND>(a, row, __float_as_uint(r.w), r.x, r.y, r.z, dist, count);
             }
         }
-        else
+    }
+    else
+    {
+        for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
         {
-            bool sure1 = true, sure2 = true;
-            b0 = axis_bin(a.a0, a.distances[k]);
-            b1 = angle_bin(a.a1, a.orientations[ij.y], vy, vx, &sure1);
-            b2 = angle_bin(a.a2, a.query_orientations[ij.x], -vy, -vx, &sure2);
-            sure = sure1 && sure2;
-        }
-        if (b0 < 0 || (KIND != FGPU_PMFT_R12 && b1 < 0))
-        {
-            continue; // surely outside an axis
-        }
-        if (sure)
-        {
-            count(b0, b1, b2);
-        }
-        else
-        {
-            uint32_t const slot = atomicAdd(a.deferred_count, 1U);
-            if (slot < a.deferred_cap)
-            {
-                a.deferred[slot] = make_uint4(ij.x, ij.y, __float_as_uint(vx), __float_as_uint(vy));
-                if (KIND == FGPU_PMFT_R12)
-                {
-                    a.deferred_dist[slot] = a.distances[k];
-                }
-            }
+            uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
+            float const vz = KIND == FGPU_PMFT_XYZ ? a.vectors[3 * k + 2] : 0.0f;
+            float const dist = KIND == FGPU_PMFT_R12 ? a.distances[k] : 0.0f;
+            pmft3_bond<KIND>(a, ij.x, ij.y, a.vectors[3 * k], a.vectors[3 * k + 1], vz, dist, count);
         }
     }
     if (a.use_shared)
@@ -227,6 +261,16 @@ template<int KIND> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
                 atomicAdd(&a.hist[b], p3_hist[b]);
             }
         }
+    }
+}
+
+// resident histogram += the histogram of one frame
+__global__ void __launch_bounds__(256) k_add_hist(const uint32_t* __restrict__ frame, uint32_t n, uint32_t* __restrict__ hist)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && frame[i] != 0)
+    {
+        hist[i] += frame[i];
     }
 }
 
@@ -269,20 +313,20 @@ __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
                 quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :117
             }
         }
-        // theta: the chain of angle_bin with orientation - d replaced by d itself
+        // theta: the chain of angle_bin with orientation - d replaced by d itself (t grows with d here)
         float const d = atan2f(y, x);
         float const theta = mod_two_pi(d);
-        float const ut = __fmul_rn(theta, a.at.inv_width);
-        float const ft = ut - floorf(ut);
-        float const mt = kAngleMargin * a.at.inv_width + 1.0e-6f * (ut + 1.0f);
-        bool sure = ft > mt && ft < 1.0f - mt && theta > kAngleMargin && theta < kTwoPi - kAngleMargin;
-        // phi: the argument is float arithmetic (one division, one square root), acosf is libm's
+        int const bt0 = axis_bin(a.at, theta);
+        float const th_lo = mod_two_pi(d - kAngleMargin), th_hi = mod_two_pi(d + kAngleMargin);
+        bool sure = axis_bin(a.at, th_lo) == bt0 && axis_bin(a.at, th_hi) == bt0 && th_lo <= theta && theta <= th_hi
+            && theta > kEdgeGuard && theta < kTwoPi - kEdgeGuard;
+        // phi: the argument is float arithmetic (one division, one square root), acosf is libm's; the bin is a
+        // monotone function of phi
         float const c = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
         float const phi = acosf(c);
-        float const up = __fmul_rn(phi, a.ap.inv_width);
-        float const fp = up - floorf(up);
-        float const mp = kAngleMargin * a.ap.inv_width + 1.0e-6f * (up + 1.0f);
-        sure = sure && fp > mp && fp < 1.0f - mp && phi > kAngleMargin && phi < a.ap.r_max - kAngleMargin;
+        int const bp0 = axis_bin(a.ap, phi);
+        sure = sure && axis_bin(a.ap, phi - kAngleMargin) == bp0 && axis_bin(a.ap, phi + kAngleMargin) == bp0
+            && phi > kEdgeGuard && phi < a.ap.r_max - kEdgeGuard;
         if (sure)
         {
             int const bt = axis_bin(a.at, theta), bp = axis_bin(a.ap, phi);
@@ -328,31 +372,52 @@ __global__ void __launch_bounds__(256) k_add_bins(const uint32_t* __restrict__ b
 
 void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
 {
-    if (a.n_bonds == 0)
+    bool const rows = a.bag != nullptr;
+    if (rows ? a.n_rows == 0 : a.n_bonds == 0)
     {
         return;
     }
     size_t const smem = (size_t) a.a0.bins * a.a1.bins * a.a2.bins * sizeof(uint32_t);
     a.use_shared = smem <= 40 * 1024 ? 1 : 0;
     size_t const dyn = a.use_shared ? smem : 0;
-    unsigned const blocks = (unsigned) std::min<uint64_t>((a.n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 8U);
+    uint64_t const want = rows ? ((uint64_t) a.n_rows * a.group + 255) / 256 : (a.n_bonds + 255) / 256;
+    unsigned const blocks = (unsigned) std::min<uint64_t>(want, (uint64_t) ctx->sm_count * 8U);
     {
-        KernelScope ks(ctx, "pmft3");
+        KernelScope ks(ctx, rows ? "pmft3_rows" : "pmft3");
+#define FGPU_PMFT3_LAUNCH(KIND)                                                                                  \
+    if (rows)                                                                                                    \
+    {                                                                                                            \
+        k_pmft3<KIND, true><<<blocks, 256, dyn, ctx->stream>>>(a);                                               \
+    }                                                                                                            \
+    else                                                                                                         \
+    {                                                                                                            \
+        k_pmft3<KIND, false><<<blocks, 256, dyn, ctx->stream>>>(a);                                              \
+    }
         switch (kind)
         {
         case FGPU_PMFT_XYZ:
-            k_pmft3<FGPU_PMFT_XYZ><<<blocks, 256, dyn, ctx->stream>>>(a);
+            FGPU_PMFT3_LAUNCH(FGPU_PMFT_XYZ)
             break;
         case FGPU_PMFT_XYT:
-            k_pmft3<FGPU_PMFT_XYT><<<blocks, 256, dyn, ctx->stream>>>(a);
+            FGPU_PMFT3_LAUNCH(FGPU_PMFT_XYT)
             break;
         case FGPU_PMFT_XY:
-            k_pmft3<FGPU_PMFT_XY><<<blocks, 256, dyn, ctx->stream>>>(a);
+            FGPU_PMFT3_LAUNCH(FGPU_PMFT_XY)
             break;
         default:
-            k_pmft3<FGPU_PMFT_R12><<<blocks, 256, dyn, ctx->stream>>>(a);
+            FGPU_PMFT3_LAUNCH(FGPU_PMFT_R12)
             break;
         }
+#undef FGPU_PMFT3_LAUNCH
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_add_hist(fgpu_ctx* ctx, const uint32_t* frame, uint32_t n, uint32_t* hist)
+{
+    {
+        KernelScope ks(ctx, "pmft_add_hist");
+        k_add_hist<<<(n + 255) / 256, 256, 0, ctx->stream>>>(frame, n, hist);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }

@@ -271,6 +271,14 @@ private:
     size_t m_cursor {0};
 };
 
+// The query points as the C ABI takes them: nullptr when they are the reference points themselves (no upload, no
+// second cell sort), else the packed floats.
+inline const float* selfOrHost(const NeighborQuery& nq, const vec3<float>* query_points, unsigned int n_query_points)
+{
+    bool const self = query_points == nq.getPoints() && n_query_points == nq.getNPoints();
+    return self ? nullptr : reinterpret_cast<const float*>(query_points);
+}
+
 inline std::shared_ptr<NeighborQueryIterator> NeighborQuery::query(const vec3<float>* query_points,
                                                                    unsigned int n_query_points,
                                                                    QueryArgs query_args) const

@@ -72,22 +72,38 @@ public:
             throw std::invalid_argument("A 3D box was provided to a class that only supports 2D systems.");
         }
         m_box = neighbor_query->getBox();
-        std::shared_ptr<locality::NeighborList> list = nlist;
-        if (!list)
-        {
-            list = neighbor_query->query(query_points, n_query_points, qargs)->toNeighborList();
-        }
-        else
-        {
-            list->validate(n_query_points, neighbor_query->getNPoints());
-        }
         if (!m_dev)
         {
             fgpu_pmftxy* h = nullptr;
             gpu::check(fgpu_pmftxy_create(gpu::context(), m_x_max, m_y_max, m_nx, m_ny, &h));
             m_dev = std::shared_ptr<fgpu_pmftxy>(h, fgpu_pmftxy_destroy);
         }
-        gpu::check(fgpu_pmftxy_accumulate_nlist(m_dev.get(), list->device(gpu::context()), query_orientations));
+        std::shared_ptr<locality::NeighborList> list = nlist;
+        if (!list)
+        {
+            auto query = neighbor_query->query(query_points, n_query_points, qargs); // validates, infers the mode
+            locality::QueryArgs const& args = query->getQueryArgs();
+            if (args.mode == locality::QueryType::ball)
+            {
+                // a ball query made for this histogram alone: the bonds go from the search straight into the bins
+                gpu::check(fgpu_pmftxy_accumulate(m_dev.get(), neighbor_query->device(),
+                                                  locality::selfOrHost(*neighbor_query, query_points, n_query_points),
+                                                  n_query_points, neighbor_query->getFlavour(), args.r_max, args.r_min,
+                                                  args.exclude_ii ? 1 : 0, query_orientations));
+            }
+            else
+            {
+                list = query->toNeighborList();
+            }
+        }
+        else
+        {
+            list->validate(n_query_points, neighbor_query->getNPoints());
+        }
+        if (list)
+        {
+            gpu::check(fgpu_pmftxy_accumulate_nlist(m_dev.get(), list->device(gpu::context()), query_orientations));
+        }
         m_frame_counter++;
         m_n_points = neighbor_query->getNPoints();
         m_n_query_points = n_query_points;
@@ -244,24 +260,12 @@ protected:
         m_edges[ax] = edges(m_n[ax], lo, hi);
     }
 
-    // the bonds: the list handed in, or the query over the points, on the device
-    std::shared_ptr<locality::NeighborList> bonds(const std::shared_ptr<locality::NeighborQuery>& neighbor_query,
-                                                  const vec3<float>* query_points, unsigned int n_query_points,
-                                                  const std::shared_ptr<locality::NeighborList>& nlist,
-                                                  const locality::QueryArgs& qargs)
-    {
-        if (!nlist)
-        {
-            return neighbor_query->query(query_points, n_query_points, qargs)->toNeighborList();
-        }
-        nlist->validate(n_query_points, neighbor_query->getNPoints());
-        return nlist;
-    }
-
-    void accumulateDevice(const std::shared_ptr<locality::NeighborQuery>& neighbor_query,
-                          const std::shared_ptr<locality::NeighborList>& list, unsigned int n_query_points,
-                          const float* orientations, const float* query_orientations, const float* equiv,
-                          unsigned int n_equiv)
+    // the bonds: the list handed in, or the query over the points -- a ball query goes from the search straight into
+    // the bins (fgpu_pmft_accumulate), anything else through a NeighborList on the device
+    void accumulateDevice(const std::shared_ptr<locality::NeighborQuery>& neighbor_query, const vec3<float>* query_points,
+                          unsigned int n_query_points, const std::shared_ptr<locality::NeighborList>& nlist,
+                          const locality::QueryArgs& qargs, const float* orientations, const float* query_orientations,
+                          const float* equiv, unsigned int n_equiv)
     {
         m_box = neighbor_query->getBox();
         if (!m_dev)
@@ -271,8 +275,33 @@ protected:
                                         (uint32_t) m_n[1], (uint32_t) m_n[2], &h));
             m_dev = std::shared_ptr<fgpu_pmft>(h, fgpu_pmft_destroy);
         }
-        gpu::check(fgpu_pmft_accumulate_nlist(m_dev.get(), list->device(gpu::context()), orientations,
-                                              neighbor_query->getNPoints(), query_orientations, equiv, n_equiv));
+        std::shared_ptr<locality::NeighborList> list = nlist;
+        if (!list)
+        {
+            auto query = neighbor_query->query(query_points, n_query_points, qargs); // validates, infers the mode
+            locality::QueryArgs const& args = query->getQueryArgs();
+            if (args.mode == locality::QueryType::ball)
+            {
+                gpu::check(fgpu_pmft_accumulate(m_dev.get(), neighbor_query->device(),
+                                                locality::selfOrHost(*neighbor_query, query_points, n_query_points),
+                                                n_query_points, neighbor_query->getFlavour(), args.r_max, args.r_min,
+                                                args.exclude_ii ? 1 : 0, orientations, query_orientations, equiv,
+                                                n_equiv));
+            }
+            else
+            {
+                list = query->toNeighborList();
+            }
+        }
+        else
+        {
+            list->validate(n_query_points, neighbor_query->getNPoints());
+        }
+        if (list)
+        {
+            gpu::check(fgpu_pmft_accumulate_nlist(m_dev.get(), list->device(gpu::context()), orientations,
+                                                  neighbor_query->getNPoints(), query_orientations, equiv, n_equiv));
+        }
         m_frame_counter++;
         m_n_points = neighbor_query->getNPoints();
         m_n_query_points = n_query_points;
@@ -417,8 +446,8 @@ public:
         {
             throw std::invalid_argument("A 2D box was provided to a class that only supports 3D systems.");
         }
-        auto list = bonds(neighbor_query, query_points, n_query_points, nlist, qargs);
-        accumulateDevice(neighbor_query, list, n_query_points, nullptr, reinterpret_cast<const float*>(query_orientations),
+        accumulateDevice(neighbor_query, query_points, n_query_points, nlist, qargs, nullptr,
+                         reinterpret_cast<const float*>(query_orientations),
                          reinterpret_cast<const float*>(equiv_orientations), num_equiv_orientations);
     }
 
@@ -478,8 +507,8 @@ public:
         {
             throw std::invalid_argument("A 3D box was provided to a class that only supports 2D systems.");
         }
-        auto list = bonds(neighbor_query, query_points, n_query_points, nlist, qargs);
-        accumulateDevice(neighbor_query, list, n_query_points, orientations, query_orientations, nullptr, 0);
+        accumulateDevice(neighbor_query, query_points, n_query_points, nlist, qargs, orientations, query_orientations,
+                         nullptr, 0);
     }
 
 private:
@@ -537,8 +566,8 @@ public:
         {
             throw std::invalid_argument("A 3D box was provided to a class that only supports 2D systems.");
         }
-        auto list = bonds(neighbor_query, query_points, n_query_points, nlist, qargs);
-        accumulateDevice(neighbor_query, list, n_query_points, orientations, query_orientations, nullptr, 0);
+        accumulateDevice(neighbor_query, query_points, n_query_points, nlist, qargs, orientations, query_orientations,
+                         nullptr, 0);
     }
 
 private:

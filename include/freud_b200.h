@@ -87,7 +87,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, pmft3, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, correlation, pmft3, pmft3_rows, pmft_add_hist, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -214,6 +214,9 @@ int fgpu_pmftxy_create(fgpu_ctx* ctx, float x_max, float y_max, uint32_t n_x, ui
 void fgpu_pmftxy_destroy(fgpu_pmftxy* pmft);
 int fgpu_pmftxy_reset(fgpu_pmftxy* pmft);
 int fgpu_pmftxy_accumulate_nlist(fgpu_pmftxy* pmft, const fgpu_nlist* nl, const float* query_orientations_host);
+/* query + histogram in one call, no NeighborList (see fgpu_pmft_accumulate) */
+int fgpu_pmftxy_accumulate(fgpu_pmftxy* pmft, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                           int flavour, float r_max, float r_min, int exclude_ii, const float* query_orientations_host);
 int fgpu_pmftxy_read(fgpu_pmftxy* pmft, uint32_t* counts_host);
 
 /* ---- PMFTXYZ, PMFTXYT, PMFTR12 ---------------------------------------------------------------------------
@@ -240,6 +243,12 @@ int fgpu_pmft_reset(fgpu_pmft* pmft);
 int fgpu_pmft_accumulate_nlist(fgpu_pmft* pmft, const fgpu_nlist* nl, const float* orientations_host, uint32_t n_points,
                                const float* query_orientations_host, const float* equiv_orientations_host,
                                uint32_t n_equiv);
+/* The ball query (fgpu_ball_query's arguments; query_points_host = NULL: the points themselves) and the histogram in
+ * one call: the bonds go from the search's hit bag straight into the histogram kernel, no NeighborList is built
+ * (NeighborComputeFunctional.h:137-178, the nlist == nullptr branch).  Same counts as the two-call route. */
+int fgpu_pmft_accumulate(fgpu_pmft* pmft, fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour,
+                         float r_max, float r_min, int exclude_ii, const float* orientations_host,
+                         const float* query_orientations_host, const float* equiv_orientations_host, uint32_t n_equiv);
 int fgpu_pmft_read(fgpu_pmft* pmft, uint32_t* counts_host);
 int fgpu_pmft_deferred(const fgpu_pmft* pmft, uint64_t* bonds);
 

@@ -391,6 +391,68 @@ def test_pmft3_over_a_neighbor_list(ctx):
             capi.DevicePMFT(ctx, kind, maxes, bins)
 
 
+def test_pmft_query_and_histogram_in_one_call(ctx):
+    """fgpu_pmft_accumulate / fgpu_pmftxy_accumulate: the ball query and the histogram without a NeighborList in between
+    (the bonds are read from the search's bag) -- the committed outputs of the reference again, bit for bit, for all
+    four classes, both engines' arithmetic, separate query points and self queries, two accumulated frames, the lattice
+    whose every bond goes to the host (its list outgrows the first guess and the frame is repeated), and the tiny box
+    that the warp-cooperative search does not take (fallback through a NeighborList)."""
+    from freud_b200.box import Box
+    from tests.golden.make_golden import PMFT3_EQUIV, pmft3_lattice, pmft3_quats, pmftxy_inputs
+
+    capi = _capi()
+    gold = np.load(os.path.join(GOLD, "pmft3.npz"))
+    gold_xy = np.load(os.path.join(GOLD, "pmftxy.npz"))
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 1500, 31), random_points(box, 400, 32)
+    r = float(np.sqrt(2.0 ** 2 + 2.5 ** 2 + 3.0 ** 2))
+    dp = capi.DevicePoints(ctx, box, pts)
+    xyz = capi.DevicePMFT(ctx, capi.PMFT_XYZ, (2.0, 2.5, 3.0), (12, 10, 8))
+    xyz.accumulate(dp, q, IMAGE, r, None, pmft3_quats(400, 6), PMFT3_EQUIV)
+    assert np.array_equal(xyz.read(), gold["xyz_query_counts"])
+    xyz.accumulate(dp, q, IMAGE, r, None, pmft3_quats(400, 6), PMFT3_EQUIV)
+    assert np.array_equal(xyz.read(), 2 * gold["xyz_query_counts"])
+    xyz.reset()
+    xyz.accumulate(dp, None, IMAGE, r, None, pmft3_quats(1500, 7), PMFT3_EQUIV[:1], exclude_ii=True)
+    assert np.array_equal(xyz.read(), gold["xyz_self_counts"])
+    for name, box in (("sq2d", Box.square(40)), ("tilt2d", Box(30, 26, 0, 0.35, 0, 0, is2D=True))):
+        pts, q = random_points(box, 3000, 11), random_points(box, 800, 12)
+        th_p, th_q = pmftxy_inputs(3000, 800, 5)
+        dp = capi.DevicePoints(ctx, box, pts)
+        r_xy = float(np.sqrt(3.0 ** 2 + 2.5 ** 2))
+        xy = capi.DevicePMFTXY(ctx, 3.0, 2.5, 30, 24)
+        xy.accumulate(dp, q, IMAGE, r_xy, th_q)
+        assert np.array_equal(xy.read(), gold_xy[f"{name}_query_counts"])
+        xy.reset()
+        xy.accumulate(dp, None, IMAGE, r_xy, th_p, exclude_ii=True)
+        assert np.array_equal(xy.read(), gold_xy[f"{name}_self_counts"])
+        xyt = capi.DevicePMFT(ctx, capi.PMFT_XYT, (3.0, 2.5), (14, 12, 9))
+        xyt.accumulate(dp, q, IMAGE, r_xy, th_p, th_q)
+        assert np.array_equal(xyt.read(), gold[f"{name}_xyt_query_counts"])
+        r12 = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (10, 11, 12))
+        r12.accumulate(dp, None, IMAGE, 4.0, th_p, th_p, exclude_ii=True)
+        assert np.array_equal(r12.read(), gold[f"{name}_r12_self_counts"])
+        # the LinkCell arithmetic gives the same bonds up to the last place of their vectors: same totals here
+        r12w = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (10, 11, 12))
+        r12w.accumulate(dp, None, WRAP, 4.0, th_p, th_p, exclude_ii=True)
+        nl = port.ball_nlist(port.WRAP, box, True, pts, pts, 4.0, 0.0, True)
+        assert np.array_equal(r12w.read(), port.pmft3(port.PMFT_R12, box, 3000, nl, th_p, th_p, (4.0,), (10, 11, 12))[0])
+    box, pts, th = pmft3_lattice()
+    dp = capi.DevicePoints(ctx, box, pts)
+    xyt = capi.DevicePMFT(ctx, capi.PMFT_XYT, (3.0, 3.0), (6, 6, 8))
+    xyt.accumulate(dp, None, IMAGE, float(np.sqrt(18.0)), th, th, exclude_ii=True)
+    assert np.array_equal(xyt.read(), gold["lattice_xyt_counts"]) and xyt.host_binned_bonds > 1000
+    # 2 cells per axis: not the warp-cooperative search's case
+    tiny = Box.square(7)
+    tp = random_points(tiny, 60, 3)
+    ta = np.linspace(0, 6, 60).astype(np.float32)
+    tdp = capi.DevicePoints(ctx, tiny, tp)
+    small = capi.DevicePMFT(ctx, capi.PMFT_XYT, (2.0, 2.0), (5, 5, 4))
+    small.accumulate(tdp, None, IMAGE, 3.0, ta, ta, exclude_ii=True)
+    nl = port.ball_nlist(port.IMAGE, tiny, True, tp, tp, 3.0, 0.0, True)
+    assert np.array_equal(small.read(), port.pmft3(port.PMFT_XYT, tiny, 60, nl, ta, ta, (2.0, 2.0), (5, 5, 4))[0])
+
+
 def test_bond_order_over_a_neighbor_list(ctx):
     """fgpu_bondorder_* (BondOrder.cc:100-153) over device NeighborLists against the committed outputs of the reference:
     bin counts bit for bit in all four modes, on the FCC lattice whose bond directions sit on bin edges, accumulated over
