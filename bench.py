@@ -367,7 +367,9 @@ def workload_pmftxy(ctx, rank, n, x_max=4.0, y_max=3.0, bins=(100, 100)):
                                     f"r={r_max:g}, image flavour) N={n} 2-D square L={L:.4f} areal density 0.5",
                         "bonds_per_step": n_bonds},
                 h2d=12 * n + 4 * n, d2h=4 * nb, algo=algo, keep=[keep0, keep1], box=box, pts=pts, angles=angles,
-                x_max=x_max, y_max=y_max, bins=bins, secondary={"bonds": n_bonds}, algo_per_step=True)
+                x_max=x_max, y_max=y_max, bins=bins, secondary={"bonds": n_bonds}, algo_per_step=True,
+                # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v9_summary.md)
+                traffic={"pmft3_rows": 705748736 + 4108544} if (n, x_max, y_max) == (1_000_000, 4.0, 3.0) else {})
 
 
 def cpu_reference_pmftxy(box, pts, angles, x_max, y_max, bins, budget_s=12.0, threads=None):
@@ -499,7 +501,10 @@ def workload_hist_client(ctx, rank, n, name):
                 keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds},
                 algo_per_step=True,
                 # measured DRAM bytes of one launch of the client's kernel (ncu, profiles/ncu_r1_v8_summary.md)
-                traffic={"bond_order": 240091648 + 5901312} if name == "bond_order" and n == 1_000_188 else {})
+                traffic={"bond_order": {"bond_order": 240091648 + 5901312},
+                         # ... and profiles/ncu_r1_v9_summary.md for the bag-reading kernels
+                         "pmftr12": {"pmft3_rows": 869713664 + 4264960}, "pmftxyz": {"pmft3_rows": 301006592 + 4494592}}
+                .get(name, {}) if n in (1_000_000, 1_000_188) else {})
 
 
 def cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=12.0, threads=None):
@@ -832,7 +837,7 @@ def main():
             roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(name),
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                          "capture of this workload (profiles/ncu_r1_v6_summary.md, ncu_r1_v8_summary.md)"
+                                          "capture of this workload (profiles/ncu_r1_v6_summary.md, ncu_r1_v8_summary.md, ncu_r1_v9_summary.md)"
                         if w.get("traffic", {}).get(name) else None,
                         "avg_launch_ms": round(avg_ms, 4),
                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
