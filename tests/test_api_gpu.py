@@ -455,6 +455,39 @@ def test_histogram_clients_reference_suite_cases():
     assert bo.bin_counts.sum() == 0 and not bo.bond_order.any()
 
 
+def test_pmft_routes_agree_across_engines_and_query_modes():
+    """The one-call route (ball query, bonds from the search's bag) and the NeighborList route (nearest-neighbour query
+    arguments, or a list handed in) of the same class give what the oracle gives over the engine's own bonds: LinkCell
+    (wrap arithmetic), CellQuery (ghost arithmetic) and AABBQuery (image arithmetic), tests/test_pmft.py:455-485 upstream
+    for the nearest-neighbour arguments."""
+    rs = np.random.RandomState(12)
+    box = Box(24, 22, 0, 0.3, 0, 0, is2D=True)
+    pts = random_points(box, 2000, 51)
+    th = (rs.random_sample(2000) * 2 * np.pi).astype(np.float32)
+    for make, flavour in ((lambda: locality.LinkCell(box, pts, 3.0), port.WRAP), (lambda: locality.CellQuery(box, pts), port.GHOST),
+                          (lambda: locality.AABBQuery(box, pts), port.IMAGE)):
+        nl = port.ball_nlist(flavour, box, True, pts, pts, 3.0, 0.0, True)
+        want_xyt = port.pmft3(port.PMFT_XYT, box, 2000, nl, th, th, (2.0, 2.0), (10, 10, 12))[0]
+        want_xy = port.pmftxy(box, 2000, nl, th, 2.0, 2.0, 10, 10)[0]
+        ball = dict(mode="ball", r_max=3.0)
+        assert np.array_equal(pmft.PMFTXYT(2.0, 2.0, (10, 10, 12)).compute(make(), th, neighbors=ball).bin_counts, want_xyt)
+        assert np.array_equal(pmft.PMFTXY(2.0, 2.0, 10).compute(make(), th, neighbors=ball).bin_counts, want_xy)
+        handed = make().query(pts, dict(ball, exclude_ii=True)).toNeighborList()
+        assert np.array_equal(pmft.PMFTXYT(2.0, 2.0, (10, 10, 12)).compute(make(), th, neighbors=handed).bin_counts, want_xyt)
+    knn = port.knn_nlist(box, True, pts, pts, 6, exclude_ii=True)
+    want = port.pmft3(port.PMFT_R12, box, 2000, knn, th, th, (3.0,), (6, 8, 8))[0]
+    got = pmft.PMFTR12(3.0, (6, 8, 8)).compute(locality.AABBQuery(box, pts), th, neighbors=dict(num_neighbors=6))
+    assert np.array_equal(got.bin_counts, want)
+    cube = Box.cube(14)
+    p3 = random_points(cube, 1500, 52)
+    q = rs.normal(size=(1500, 4))
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    knn3 = port.knn_nlist(cube, False, p3, p3, 8, exclude_ii=True)
+    want = port.pmft3(port.PMFT_XYZ, cube, 1500, knn3, None, q, (2.0, 2.0, 2.0), (8, 8, 8), equiv=np.float32([[1, 0, 0, 0]]))[0]
+    got = pmft.PMFTXYZ(2.0, 2.0, 2.0, 8).compute((cube, p3), q, neighbors=dict(num_neighbors=8))
+    assert np.array_equal(got.bin_counts, want)
+
+
 def test_bond_order_reference_suite_case():
     """tests/test_environment_bond_order.py:14-105 upstream: a perfect FCC crystal fills exactly 12 bins of a 6 x 6 diagram;
     lbod and obcd equal bod when all orientations are equal; bod ignores random orientations while obcd smears them over
