@@ -262,16 +262,17 @@ def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
     def step_dev():
         # the C ABI hands the two result arrays (8 MB) to the host: that copy is part of every call
         dp.build_cells(rq)
-        return dp.ball_query(None, IMAGE, rq, 0.0, True).local_density(r_max, diameter, out=(pin_num, pin_den))
+        # query + count in one call: the bonds are summed where the search left them, no NeighborList
+        return dp.local_density(None, IMAGE, rq, r_max, diameter, exclude_ii=True, out=(pin_num, pin_den))
 
     def step_e2e():
         d = _capi.DevicePoints(ctx, box, pin_pts)
-        return d.ball_query(None, IMAGE, rq, 0.0, True).local_density(r_max, diameter, out=(pin_num, pin_den))[1]
+        return d.local_density(None, IMAGE, rq, r_max, diameter, exclude_ii=True, out=(pin_num, pin_den))[1]
 
     n_cells = int(np.prod(dp.build_cells(rq)))
     algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
             "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
-            "local_density": 4 * n_bonds + 8 * n + 8 * n,
+            "local_density_rows": 16 * n_bonds + 8 * n + 8 * n,
             "pipeline": 16 * (n + n) + 8 * n}  # fused search + count would read the positions and write two floats
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s",
                 metric="local_density_particles_per_sec",
@@ -303,19 +304,19 @@ def workload_correlation(ctx, rank, n, bins=100, r_max=3.0):
         # the values (16 MB of complex128, page-locked) cross PCIe in every call: the C ABI takes them from the host
         cf.reset()
         dp.build_cells(r_max)
-        cf.accumulate_nlist(dp.ball_query(None, IMAGE, r_max, 0.0, True), values, values)
+        cf.accumulate(dp, None, IMAGE, r_max, values, values, exclude_ii=True)  # query + accumulation, no NeighborList
         return cf.read()
 
     def step_e2e():
         cf.reset()
         d = _capi.DevicePoints(ctx, box, pin_pts)
-        cf.accumulate_nlist(d.ball_query(None, IMAGE, r_max, 0.0, True), values, values)
+        cf.accumulate(d, None, IMAGE, r_max, values, values, exclude_ii=True)
         return cf.read()[1]
 
     n_cells = int(np.prod(dp.build_cells(r_max)))
     algo = {"search_nl": 16 * (n + n) + 4 * n_cells + 16 * n_bonds + 8 * n,
             "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
-            "correlation": 12 * n_bonds + 32 * n_bonds + 20 * bins,  # (i, j, d) per bond + two gathered complex128
+            "correlation_rows": 16 * n_bonds + 16 * n_bonds + 16 * n + 20 * bins,  # bag record + gathered complex128 per bond
             "pipeline": 16 * (n + n) + 32 * n + 20 * bins}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s",
                 metric="correlation_function_particles_per_sec",
@@ -782,7 +783,7 @@ def main():
     per_kernel = {}
     names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
+             "rdf_distances", "steinhardt", "local_density_rows", "local_density", "correlation_rows", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
     raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
     for name in names:
         ms, cnt = raw[name]

@@ -91,8 +91,11 @@ SIGNATURES = {
     "fgpu_corr_destroy": (None, [_vp]),
     "fgpu_corr_reset": (C.c_int, [_vp]),
     "fgpu_corr_accumulate_nlist": (C.c_int, [_vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "fgpu_corr_accumulate": (C.c_int, [_vp, _vp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fgpu_corr_read": (C.c_int, [_vp, _up, C.POINTER(C.c_double)]),
     "fgpu_local_density": (C.c_int, [_vp, C.c_float, C.c_float, C.c_int, _fp, _fp]),
+    "fgpu_local_density_query": (C.c_int, [_vp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                           C.c_float, _fp, _fp]),
     "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp,
                                          _fp]),
     "fgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
@@ -337,6 +340,17 @@ class DevicePoints(_DeviceObject):
                                    C.byref(h)))
         return DeviceNeighborList(self.ctx, h)
 
+    def local_density(self, query_points, flavour, q_r_max, r_max, diameter, exclude_ii=False, q_r_min=0.0, out=None):
+        """(num_neighbors, density) of LocalDensity(r_max, diameter) over a ball query of ``q_r_max`` made for it alone
+        (``query_points=None``: the points themselves) -- no NeighborList (``fgpu_local_density_query``)."""
+        q = None if query_points is None else f32(query_points, 3)
+        nq = self.n if q is None else len(q)
+        num, den = out if out is not None else (np.empty(nq, np.float32), np.empty(nq, np.float32))
+        assert num.dtype == np.float32 and den.dtype == np.float32 and num.size == den.size == nq
+        check(lib().fgpu_local_density_query(self._h, ptr(q), nq, int(flavour), float(q_r_max), float(q_r_min),
+                                             int(bool(exclude_ii)), float(r_max), float(diameter), ptr(num), ptr(den)))
+        return num, den
+
     def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0, out=None, average=False,
                    wl=False, wl_normalize=False):
         """``out``: optional dict of preallocated (e.g. page-locked) float32 arrays ``ql`` (n, len(ls)) and
@@ -559,6 +573,18 @@ class DeviceCorrelation(_DeviceObject):
         assert len(v) == nlist.num_points and len(q) == nlist.num_query_points
         dp = C.POINTER(C.c_double)
         check(lib().fgpu_corr_accumulate_nlist(self._h, nlist._h, v.ctypes.data_as(dp), q.ctypes.data_as(dp)))
+
+    def accumulate(self, points, query_points, flavour, r_max, values, query_values, r_min=0.0, exclude_ii=False):
+        """Ball query of ``points`` (``query_points=None``: against themselves) and the accumulation in one call -- no
+        NeighborList (``fgpu_corr_accumulate``)."""
+        qp = None if query_points is None else f32(query_points, 3)
+        nq = points.n if qp is None else len(qp)
+        v = np.ascontiguousarray(values, dtype=np.complex128).ravel()
+        q = v if query_values is values else np.ascontiguousarray(query_values, dtype=np.complex128).ravel()
+        assert len(v) == points.n and len(q) == nq
+        dp = C.POINTER(C.c_double)
+        check(lib().fgpu_corr_accumulate(self._h, points._h, ptr(qp), nq, int(flavour), float(r_max), float(r_min),
+                                         int(bool(exclude_ii)), v.ctypes.data_as(dp), q.ctypes.data_as(dp)))
 
     def read(self):
         counts = np.empty(self.bins, np.uint32)

@@ -465,6 +465,70 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     *out = nl.release();
 }
 
+// Ball search of n_query rows that leaves its hits in ctx->bag4, grouped by query row: row r owns the records
+// [ctx->tmp_start[r], + ctx->row_counts[r]) = {bond vector, bits(point index)}.  For the computes that only bin or
+// sum the bonds of a query made for them alone: no ranked emit, no NeighborList.  Returns false when the
+// warp-cooperative search does not take the frame (tiny grids, points outside the box, a tile beyond the largest
+// buffer, FGPU_SEARCH=general): the caller goes through a NeighborList then.
+bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int flavour, float r_max, float r_min,
+                   int exclude_ii, uint64_t* n_bonds)
+{
+    fgpu_ctx* ctx = pts->ctx;
+    if (n_query == 0 || ctx->force_general)
+    {
+        return false;
+    }
+    build_grid(pts, r_max);
+    QueryView const qv = prepare_queries(pts, q_host, nullptr, n_query);
+    Search2Args s2 = base_search2_args(pts, qv, 0, r_max, r_min, exclude_ii);
+    if (!search2_supported(s2, S2_NL))
+    {
+        return false;
+    }
+    double const vol = box_volume(pts->box);
+    double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
+    uint64_t cap = ctx->bag_hint != 0 ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
+                                      : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
+    ctx->tmp_start.reserve((size_t) n_query + 1);
+    ctx->row_counts.reserve((size_t) n_query + 1);
+    launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+    s2.evals = nullptr;
+    for (int attempt = 0; attempt < 4; ++attempt)
+    {
+        cap = std::min<uint64_t>(cap, 0xffffffffULL);
+        ctx->bag4.reserve(cap);
+        s2.bag = ctx->bag4.ptr;
+        s2.temp_cap = (uint32_t) cap;
+        s2.counts = ctx->row_counts.ptr;
+        s2.tmp_start = ctx->tmp_start.ptr;
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        launch_search2(ctx, flavour, S2_NL, s2);
+        d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
+        sync(ctx);
+        int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
+        uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
+        if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
+        {
+            s2.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
+        }
+        else if (fail != 0)
+        {
+            return false;
+        }
+        else if (ctx->h_scalars[5] <= cap)
+        {
+            *n_bonds = ctx->h_scalars[5];
+            ctx->bag_hint = *n_bonds;
+            return true;
+        }
+        else
+        {
+            cap = ctx->h_scalars[5]; // exact size, the search is deterministic
+        }
+    }
+    return false;
+}
+
 void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query,
                          uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii)
 {
@@ -1857,59 +1921,8 @@ int fgpu_pmft_accumulate(fgpu_pmft* pmft, fgpu_points* pts, const float* query_p
         bool const self = query_points_host == nullptr;
         require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
         require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
-        bool fused = false;
         uint64_t n_bonds = 0;
-        if (n_query != 0 && !ctx->force_general)
-        {
-            build_grid(pts, r_max);
-            QueryView const qv = prepare_queries(pts, query_points_host, nullptr, n_query);
-            Search2Args s2 = base_search2_args(pts, qv, 0, r_max, r_min, exclude_ii);
-            if (search2_supported(s2, S2_NL))
-            {
-                double const vol = box_volume(pts->box);
-                double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max
-                                                   : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
-                uint64_t cap = ctx->bag_hint != 0
-                    ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
-                    : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
-                ctx->tmp_start.reserve((size_t) n_query + 1);
-                ctx->row_counts.reserve((size_t) n_query + 1);
-                launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
-                s2.evals = nullptr;
-                for (int attempt = 0; attempt < 4 && !fused; ++attempt)
-                {
-                    cap = std::min<uint64_t>(cap, 0xffffffffULL);
-                    ctx->bag4.reserve(cap);
-                    s2.bag = ctx->bag4.ptr;
-                    s2.temp_cap = (uint32_t) cap;
-                    s2.counts = ctx->row_counts.ptr;
-                    s2.tmp_start = ctx->tmp_start.ptr;
-                    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
-                    launch_search2(ctx, flavour, S2_NL, s2);
-                    d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
-                    sync(ctx);
-                    int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
-                    uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
-                    if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
-                    {
-                        s2.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
-                    }
-                    else if (fail != 0)
-                    {
-                        break; // points outside the box or a tile beyond the largest buffer: the general kernels
-                    }
-                    else if (ctx->h_scalars[5] <= cap)
-                    {
-                        n_bonds = ctx->h_scalars[5];
-                        fused = true;
-                    }
-                    else
-                    {
-                        cap = ctx->h_scalars[5]; // exact size, the search is deterministic
-                    }
-                }
-            }
-        }
+        bool const fused = search_to_bag(pts, query_points_host, n_query, flavour, r_max, r_min, exclude_ii, &n_bonds);
         if (!fused)
         {
             // tiny grids, points outside the box, ...: through a NeighborList
@@ -1924,7 +1937,6 @@ int fgpu_pmft_accumulate(fgpu_pmft* pmft, fgpu_points* pts, const float* query_p
             }
             return;
         }
-        ctx->bag_hint = n_bonds;
         Pmft3Args a = stage_pmft(pmft, pts->n, n_query, orientations_host, query_orientations_host,
                                  equiv_orientations_host, n_equiv);
         PmftHostInputs const in {orientations_host, query_orientations_host};
@@ -2281,6 +2293,48 @@ int fgpu_corr_accumulate_nlist(fgpu_corr* corr, const fgpu_nlist* nl, const doub
     });
 }
 
+int fgpu_corr_accumulate(fgpu_corr* corr, fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour,
+                         float r_max, float r_min, int exclude_ii, const double* values_host,
+                         const double* query_values_host)
+{
+    return guarded([&] {
+        require(corr != nullptr && pts != nullptr && values_host != nullptr && query_values_host != nullptr, FGPU_EINVALID,
+                "null argument");
+        require(corr->ctx == pts->ctx, FGPU_EINVALID, "corr and points belong to different contexts");
+        fgpu_ctx* ctx = corr->ctx;
+        bind_device(ctx);
+        validate_ball(pts, flavour, r_max, r_min);
+        bool const self = query_points_host == nullptr;
+        require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
+        uint64_t n_bonds = 0;
+        if (!search_to_bag(pts, query_points_host, n_query, flavour, r_max, r_min, exclude_ii, &n_bonds))
+        {
+            fgpu_nlist* nl = nullptr;
+            ball_query_impl(pts, query_points_host, nullptr, n_query, 0, flavour, r_max, r_min, exclude_ii, 0, &nl);
+            std::unique_ptr<fgpu_nlist, void (*)(fgpu_nlist*)> guard(nl, fgpu_nlist_destroy);
+            int const rc = fgpu_corr_accumulate_nlist(corr, nl, values_host, query_values_host);
+            if (rc != FGPU_OK)
+            {
+                throw Error(rc, fgpu_last_error());
+            }
+            return;
+        }
+        corr->values.reserve(2 * (size_t) pts->n + 2);
+        h2d(ctx, corr->values.ptr, values_host, 2 * (size_t) pts->n * sizeof(double));
+        const double* d_query_values = corr->values.ptr;
+        if (query_values_host != values_host || n_query != pts->n)
+        {
+            corr->query_values.reserve(2 * (size_t) n_query + 2);
+            h2d(ctx, corr->query_values.ptr, query_values_host, 2 * (size_t) n_query * sizeof(double));
+            d_query_values = corr->query_values.ptr;
+        }
+        launch_correlation_rows(ctx, ctx->bag4.ptr, ctx->tmp_start.ptr, ctx->row_counts.ptr, n_query, corr->values.ptr,
+                                d_query_values, corr->axis, corr->counts.ptr, corr->sums.ptr);
+        sync(ctx); // the caller's value arrays were consumed
+    });
+}
+
 int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host)
 {
     return guarded([&] {
@@ -2299,6 +2353,64 @@ int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host)
     });
 }
 
+namespace {
+
+// LocalDensity.cc:48-49: area = M_PI * r * r (double, rounded once); volume = float(4/3 pi) * r * r * r
+float local_density_measure(float r_max, int is2d)
+{
+    volatile float vol = static_cast<float>(4.0 / 3.0 * M_PI);
+    vol = vol * r_max;
+    vol = vol * r_max;
+    vol = vol * r_max;
+    return is2d ? (float) (M_PI * (double) r_max * (double) r_max) : (float) vol;
+}
+
+} // namespace
+
+int fgpu_local_density_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour, float q_r_max,
+                             float q_r_min, int exclude_ii, float r_max, float diameter, float* num_neighbors_host,
+                             float* density_host)
+{
+    return guarded([&] {
+        require(pts != nullptr, FGPU_EINVALID, "null argument");
+        require(r_max > 0, FGPU_EINVALID, "LocalDensity requires r_max to be positive.");
+        require(!(diameter < 0), FGPU_EINVALID, "LocalDensity requires diameter to be non-negative.");
+        fgpu_ctx* ctx = pts->ctx;
+        bind_device(ctx);
+        validate_ball(pts, flavour, q_r_max, q_r_min);
+        bool const self = query_points_host == nullptr;
+        require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
+        uint64_t n_bonds = 0;
+        if (!search_to_bag(pts, query_points_host, n_query, flavour, q_r_max, q_r_min, exclude_ii, &n_bonds))
+        {
+            fgpu_nlist* nl = nullptr;
+            ball_query_impl(pts, query_points_host, nullptr, n_query, 0, flavour, q_r_max, q_r_min, exclude_ii, 0, &nl);
+            std::unique_ptr<fgpu_nlist, void (*)(fgpu_nlist*)> guard(nl, fgpu_nlist_destroy);
+            int const rc = fgpu_local_density(nl, r_max, diameter, pts->box.is2d ? 1 : 0, num_neighbors_host, density_host);
+            if (rc != FGPU_OK)
+            {
+                throw Error(rc, fgpu_last_error());
+            }
+            return;
+        }
+        DevBuf<float> d_num, d_den;
+        d_num.reserve((size_t) n_query + 1);
+        d_den.reserve((size_t) n_query + 1);
+        launch_local_density_rows(ctx, ctx->bag4.ptr, ctx->tmp_start.ptr, ctx->row_counts.ptr, n_query, r_max, diameter,
+                                  local_density_measure(r_max, pts->box.is2d ? 1 : 0), d_num.ptr, d_den.ptr);
+        if (num_neighbors_host != nullptr)
+        {
+            d2h(ctx, num_neighbors_host, d_num.ptr, (size_t) n_query * sizeof(float));
+        }
+        if (density_host != nullptr)
+        {
+            d2h(ctx, density_host, d_den.ptr, (size_t) n_query * sizeof(float));
+        }
+        sync(ctx);
+    });
+}
+
 int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is2d, float* num_neighbors_host,
                        float* density_host)
 {
@@ -2309,12 +2421,7 @@ int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is
         fgpu_ctx* ctx = nl->ctx;
         bind_device(ctx);
         uint32_t const n = nl->n_query;
-        // LocalDensity.cc:48-49: area = M_PI * r * r (double, rounded once); volume = float(4/3 pi) * r * r * r
-        volatile float vol = static_cast<float>(4.0 / 3.0 * M_PI);
-        vol = vol * r_max;
-        vol = vol * r_max;
-        vol = vol * r_max;
-        float const measure = is2d ? (float) (M_PI * (double) r_max * (double) r_max) : (float) vol;
+        float const measure = local_density_measure(r_max, is2d);
         DevBuf<float> d_num, d_den;
         d_num.reserve((size_t) n + 1);
         d_den.reserve((size_t) n + 1);

@@ -562,6 +562,12 @@ struct BondOrderArgs
 void launch_bond_order(fgpu_ctx* ctx, BondOrderArgs a);
 void launch_correlation(fgpu_ctx* ctx, const uint32_t* neighbors, const float* distances, uint64_t n_bonds,
                         const double* values, const double* query_values, AxisDev axis, uint32_t* counts, double* sums);
+void launch_local_density_rows(fgpu_ctx* ctx, const float4* bag, const uint32_t* row_bag_start, const uint32_t* row_counts,
+                               uint32_t n_query, float r_max, float diameter, float measure, float* num_neighbors,
+                               float* density);
+void launch_correlation_rows(fgpu_ctx* ctx, const float4* bag, const uint32_t* row_bag_start, const uint32_t* row_counts,
+                             uint32_t n_query, const double* values, const double* query_values, AxisDev axis,
+                             uint32_t* counts, double* sums);
 void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float* distances, uint32_t n_query, float r_max,
                           float diameter, float measure, float* num_neighbors, float* density);
 

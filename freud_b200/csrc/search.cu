@@ -616,6 +616,140 @@ void launch_local_density(fgpu_ctx* ctx, const uint32_t* row_start, const float*
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 
+// LocalDensity::compute over the rows of the search's bag (the query was made for this compute alone, no
+// NeighborList): 8 lanes per query row sum their bonds' contributions -- distance = sqrt(dot(v, v)) as
+// NeighborBond.h:41-44 -- and are added up by a butterfly.  The order of the float sum is neither the list's nor
+// upstream's iteration order (which is the engine's): results agree to float rounding, as on every on-the-fly query.
+__global__ void __launch_bounds__(256) k_local_density_rows(const float4* __restrict__ bag, const uint32_t* __restrict__ row_bag_start,
+                                                            const uint32_t* __restrict__ row_counts, uint32_t n_query,
+                                                            float r_max, float diameter, float measure,
+                                                            float* __restrict__ num_neighbors, float* __restrict__ density)
+{
+    uint32_t const row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7U;
+    bool const live = row < n_query;
+    uint32_t const n = live ? row_counts[row] : 0U, start = live ? row_bag_start[row] : 0U;
+    float const half = __fdiv_rn(diameter, 2.0f);
+    float const inner = __fsub_rn(r_max, half);
+    float num = 0.0f;
+    for (uint32_t k = sub; k < n; k += 8)
+    {
+        float4 const r = bag[start + k];
+        float const d = __fsqrt_rn(dot_exact(r.x, r.y, r.z));
+        num = __fadd_rn(num, d < inner ? 1.0f : __fadd_rn(1.0f, __fdiv_rn(__fsub_rn(r_max, __fadd_rn(d, half)), diameter)));
+    }
+    num = __fadd_rn(num, __shfl_xor_sync(0xffffffffU, num, 4));
+    num = __fadd_rn(num, __shfl_xor_sync(0xffffffffU, num, 2));
+    num = __fadd_rn(num, __shfl_xor_sync(0xffffffffU, num, 1));
+    if (live && sub == 0)
+    {
+        num_neighbors[row] = num;
+        density[row] = n == 0 ? 0.0f : __fdiv_rn(num, measure);
+    }
+}
+
+void launch_local_density_rows(fgpu_ctx* ctx, const float4* bag, const uint32_t* row_bag_start, const uint32_t* row_counts,
+                               uint32_t n_query, float r_max, float diameter, float measure, float* num_neighbors,
+                               float* density)
+{
+    if (n_query == 0)
+    {
+        return;
+    }
+    {
+        KernelScope ks(ctx, "local_density_rows");
+        k_local_density_rows<<<(unsigned) (((uint64_t) n_query * 8 + 255) / 256), 256, 0, ctx->stream>>>(
+            bag, row_bag_start, row_counts, n_query, r_max, diameter, measure, num_neighbors, density);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
+// CorrelationFunction::accumulate over the rows of the search's bag: k_correlation's bond body, 8 lanes per query row
+__global__ void __launch_bounds__(256) k_correlation_rows(const float4* __restrict__ bag, const uint32_t* __restrict__ row_bag_start,
+                                                          const uint32_t* __restrict__ row_counts, uint32_t n_query,
+                                                          const double2* __restrict__ values,
+                                                          const double2* __restrict__ query_values, AxisDev axis,
+                                                          uint32_t* __restrict__ counts, double* __restrict__ sums,
+                                                          int use_shared)
+{
+    extern __shared__ __align__(16) unsigned char corr_rows_smem[];
+    double* const s_sum = reinterpret_cast<double*>(corr_rows_smem);
+    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(s_sum + 2 * (size_t) axis.bins);
+    if (use_shared)
+    {
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            s_sum[2 * b] = 0.0;
+            s_sum[2 * b + 1] = 0.0;
+            s_cnt[b] = 0;
+        }
+        __syncthreads();
+    }
+    uint32_t const sub = threadIdx.x & 7U, groups = gridDim.x * blockDim.x / 8U;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < n_query; row += groups)
+    {
+        uint32_t const n = row_counts[row], start = row_bag_start[row];
+        double2 const y = query_values[row];
+        for (uint32_t k = sub; k < n; k += 8)
+        {
+            float4 const r = bag[start + k];
+            int const bin = axis_bin(axis, __fsqrt_rn(dot_exact(r.x, r.y, r.z)));
+            if (bin < 0)
+            {
+                continue;
+            }
+            double2 const x = values[__float_as_uint(r.w)];
+            double const re = __dadd_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)); // std::conj(x) * y
+            double const im = __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x));
+            if (use_shared)
+            {
+                atomicAdd(&s_cnt[bin], 1U);
+                atomicAdd(&s_sum[2 * bin], re);
+                atomicAdd(&s_sum[2 * bin + 1], im);
+            }
+            else
+            {
+                atomicAdd(&counts[bin], 1U);
+                atomicAdd(&sums[2 * bin], re);
+                atomicAdd(&sums[2 * bin + 1], im);
+            }
+        }
+    }
+    if (use_shared)
+    {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < axis.bins; b += blockDim.x)
+        {
+            if (s_cnt[b] != 0)
+            {
+                atomicAdd(&counts[b], s_cnt[b]);
+                atomicAdd(&sums[2 * b], s_sum[2 * b]);
+                atomicAdd(&sums[2 * b + 1], s_sum[2 * b + 1]);
+            }
+        }
+    }
+}
+
+void launch_correlation_rows(fgpu_ctx* ctx, const float4* bag, const uint32_t* row_bag_start, const uint32_t* row_counts,
+                             uint32_t n_query, const double* values, const double* query_values, AxisDev axis,
+                             uint32_t* counts, double* sums)
+{
+    if (n_query == 0)
+    {
+        return;
+    }
+    size_t const smem = (size_t) axis.bins * (2 * sizeof(double) + sizeof(uint32_t));
+    int const use_shared = smem <= 40 * 1024 ? 1 : 0;
+    unsigned const blocks
+        = (unsigned) std::min<uint64_t>(((uint64_t) n_query * 8 + 255) / 256, (uint64_t) ctx->sm_count * 8U);
+    {
+        KernelScope ks(ctx, "correlation_rows");
+        k_correlation_rows<<<blocks, 256, use_shared ? smem : 0, ctx->stream>>>(
+            bag, row_bag_start, row_counts, n_query, reinterpret_cast<const double2*>(values),
+            reinterpret_cast<const double2*>(query_values), axis, counts, sums, use_shared);
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_rdf_from_distances(fgpu_ctx* ctx, const float* distances, uint64_t n, AxisDev axis, uint32_t* hist)
 {
     if (n == 0)

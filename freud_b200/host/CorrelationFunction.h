@@ -63,24 +63,41 @@ public:
                     locality::QueryArgs qargs)
     {
         m_box = neighbor_query->getBox();
-        std::shared_ptr<locality::NeighborList> list = nlist;
-        if (!list)
-        {
-            list = neighbor_query->query(query_points, n_query_points, qargs)->toNeighborList();
-        }
-        else
-        {
-            list->validate(n_query_points, neighbor_query->getNPoints());
-        }
         if (!m_dev)
         {
             fgpu_corr* h = nullptr;
             gpu::check(fgpu_corr_create(gpu::context(), (uint32_t) m_bins, m_r_max, &h));
             m_dev = std::shared_ptr<fgpu_corr>(h, fgpu_corr_destroy);
         }
-        gpu::check(fgpu_corr_accumulate_nlist(m_dev.get(), list->device(gpu::context()),
-                                              reinterpret_cast<const double*>(values),
-                                              reinterpret_cast<const double*>(query_values)));
+        std::shared_ptr<locality::NeighborList> list = nlist;
+        if (!list)
+        {
+            auto query = neighbor_query->query(query_points, n_query_points, qargs); // validates, infers the mode
+            locality::QueryArgs const& args = query->getQueryArgs();
+            if (args.mode == locality::QueryType::ball)
+            {
+                // a ball query made for this compute alone: the bonds are binned where the search left them
+                gpu::check(fgpu_corr_accumulate(m_dev.get(), neighbor_query->device(),
+                                                locality::selfOrHost(*neighbor_query, query_points, n_query_points),
+                                                n_query_points, neighbor_query->getFlavour(), args.r_max, args.r_min,
+                                                args.exclude_ii ? 1 : 0, reinterpret_cast<const double*>(values),
+                                                reinterpret_cast<const double*>(query_values)));
+            }
+            else
+            {
+                list = query->toNeighborList();
+            }
+        }
+        else
+        {
+            list->validate(n_query_points, neighbor_query->getNPoints());
+        }
+        if (list)
+        {
+            gpu::check(fgpu_corr_accumulate_nlist(m_dev.get(), list->device(gpu::context()),
+                                                  reinterpret_cast<const double*>(values),
+                                                  reinterpret_cast<const double*>(query_values)));
+        }
         m_frame_counter++;
         m_reduce = true;
     }

@@ -44,20 +44,37 @@ public:
                  const locality::QueryArgs& qargs)
     {
         m_box = neighbor_query->getBox();
+        // fresh outputs every call (LocalDensity.cc:45-46)
+        auto density = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {n_query_points});
+        auto counts = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {n_query_points});
         std::shared_ptr<locality::NeighborList> list = nlist;
         if (!list)
         {
-            list = neighbor_query->query(query_points, n_query_points, qargs)->toNeighborList();
+            auto query = neighbor_query->query(query_points, n_query_points, qargs); // validates, infers the mode
+            locality::QueryArgs const& args = query->getQueryArgs();
+            if (args.mode == locality::QueryType::ball)
+            {
+                // a ball query made for this compute alone: the bonds are summed where the search left them
+                gpu::check(fgpu_local_density_query(neighbor_query->device(),
+                                                    locality::selfOrHost(*neighbor_query, query_points, n_query_points),
+                                                    n_query_points, neighbor_query->getFlavour(), args.r_max, args.r_min,
+                                                    args.exclude_ii ? 1 : 0, m_r_max, m_diameter, counts->data(),
+                                                    density->data()));
+            }
+            else
+            {
+                list = query->toNeighborList();
+            }
         }
         else
         {
             list->validate(n_query_points, neighbor_query->getNPoints());
         }
-        // fresh outputs every call (LocalDensity.cc:45-46)
-        auto density = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {n_query_points});
-        auto counts = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {n_query_points});
-        gpu::check(fgpu_local_density(list->device(gpu::context()), m_r_max, m_diameter, m_box.is2D() ? 1 : 0,
-                                      counts->data(), density->data()));
+        if (list)
+        {
+            gpu::check(fgpu_local_density(list->device(gpu::context()), m_r_max, m_diameter, m_box.is2D() ? 1 : 0,
+                                          counts->data(), density->data()));
+        }
         m_density_array = density;
         m_num_neighbors_array = counts;
     }

@@ -87,7 +87,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, correlation, pmft3, pmft3_rows, pmft_add_hist, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, local_density_rows, correlation, correlation_rows, pmft3, pmft3_rows, pmft_add_hist, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -285,6 +285,11 @@ void fgpu_corr_destroy(fgpu_corr* corr);
 int fgpu_corr_reset(fgpu_corr* corr);
 int fgpu_corr_accumulate_nlist(fgpu_corr* corr, const fgpu_nlist* nl, const double* values_host,
                                const double* query_values_host);
+/* query + accumulation in one call, no NeighborList (see fgpu_pmft_accumulate); identical bin counts, sums to double
+ * rounding like every accumulation order */
+int fgpu_corr_accumulate(fgpu_corr* corr, fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour,
+                         float r_max, float r_min, int exclude_ii, const double* values_host,
+                         const double* query_values_host);
 int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host);
 
 /* ---- LocalDensity --------------------------------------------------------------------------------------
@@ -295,6 +300,12 @@ int fgpu_corr_read(fgpu_corr* corr, uint32_t* counts_host, double* sums_host);
  * Errors: r_max <= 0 or diameter < 0 -> FGPU_EINVALID (LocalDensity.cc:25-36).  Outputs: f32[n_query] each. */
 int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is2d, float* num_neighbors_host,
                        float* density_host);
+/* The ball query (q_r_max, q_r_min, exclude_ii; query_points_host = NULL: the points themselves) and the count in one
+ * call, the bonds read from the search's hit bag instead of a NeighborList (the nlist == nullptr branch of
+ * LocalDensity::compute).  Sums in bag order: agrees with the list route to float rounding. */
+int fgpu_local_density_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, int flavour, float q_r_max,
+                             float q_r_min, int exclude_ii, float r_max, float diameter, float* num_neighbors_host,
+                             float* density_host);
 
 /* ---- Steinhardt --------------------------------------------------------------------------------------
  * Replaces Steinhardt::compute (freud/order/Steinhardt.cc:85-118): baseCompute :120-222 with

@@ -453,6 +453,46 @@ def test_pmft_query_and_histogram_in_one_call(ctx):
     assert np.array_equal(small.read(), port.pmft3(port.PMFT_XYT, tiny, 60, nl, ta, ta, (2.0, 2.0), (5, 5, 4))[0])
 
 
+def test_local_density_and_correlation_in_one_call(ctx):
+    """fgpu_local_density_query / fgpu_corr_accumulate: the ball query and the sums without a NeighborList in between (the
+    bonds are read from the search's bag).  Correlation bin counts are identical to the list route's and the oracle's;
+    the float / double sums run in bag order and agree to rounding -- the bar every on-the-fly query is held to; rows
+    without bonds stay 0; the tiny box falls back to the list route."""
+    from freud_b200.box import Box
+    from tests.golden.make_golden import correlation_inputs
+
+    capi = _capi()
+    for box, n, flavour in ((Box.cube(12), 3000, IMAGE), (Box(30, 26, 0, 0.35, 0, 0, is2D=True), 2500, WRAP),
+                            (Box(14, 15, 16, 0.3, 0.2, 0.1), 2500, IMAGE)):
+        pts, q = random_points(box, n, 7), random_points(box, 700, 8)
+        v, qv = correlation_inputs(n, 700, 3)
+        dp = capi.DevicePoints(ctx, box, pts)
+        for qpts, qvals, excl in ((q, qv, False), (None, v, True)):
+            nl_dev = dp.ball_query(qpts, flavour, 3.0, 0.0, excl)
+            num_l, den_l = nl_dev.local_density(2.5, 1.0, is2d=box.is2D)
+            num_f, den_f = dp.local_density(qpts, flavour, 3.0, 2.5, 1.0, exclude_ii=excl)
+            assert np.allclose(num_f, num_l, rtol=2e-6, atol=1e-6) and np.allclose(den_f, den_l, rtol=2e-6, atol=1e-7)
+            assert np.array_equal(num_f == 0, num_l == 0)
+            listed = capi.DeviceCorrelation(ctx, 40, 3.0)
+            listed.accumulate_nlist(nl_dev, v, qvals)
+            fused = capi.DeviceCorrelation(ctx, 40, 3.0)
+            fused.accumulate(dp, qpts, flavour, 3.0, v, qvals, exclude_ii=excl)
+            fused.accumulate(dp, qpts, flavour, 3.0, v, qvals, exclude_ii=excl)  # a second frame accumulates
+            (c_l, s_l), (c_f, s_f) = listed.read(), fused.read()
+            assert np.array_equal(c_f, 2 * c_l)
+            assert np.allclose(s_f, 2 * s_l, rtol=1e-12, atol=1e-9 * np.abs(s_l).max())
+    sparse = Box.cube(40)
+    far = random_points(sparse, 50, 1)  # hardly any bonds within 1.5: empty rows
+    num, den = capi.DevicePoints(ctx, sparse, far).local_density(None, IMAGE, 1.5, 1.0, 1.0, exclude_ii=True)
+    want = port.local_density(port.ball_nlist(port.IMAGE, sparse, False, far, far, 1.5, 0.0, True), 1.0, 1.0)
+    assert np.allclose(num, want[0], rtol=2e-6) and np.allclose(den, want[1], rtol=2e-6) and (num == 0).sum() > 10
+    tiny = Box.cube(5)
+    tp = random_points(tiny, 80, 2)
+    num, den = capi.DevicePoints(ctx, tiny, tp).local_density(None, IMAGE, 2.4, 2.0, 0.8, exclude_ii=True)
+    want = port.local_density(port.ball_nlist(port.IMAGE, tiny, False, tp, tp, 2.4, 0.0, True), 2.0, 0.8)
+    assert np.array_equal(bits(num), bits(want[0]))  # the list route (2 cells per axis): list order, bit for bit
+
+
 def test_bond_order_over_a_neighbor_list(ctx):
     """fgpu_bondorder_* (BondOrder.cc:100-153) over device NeighborLists against the committed outputs of the reference:
     bin counts bit for bit in all four modes, on the FCC lattice whose bond directions sit on bin edges, accumulated over
