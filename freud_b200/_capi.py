@@ -85,6 +85,7 @@ SIGNATURES = {
     "fgpu_bondorder_destroy": (None, [_vp]),
     "fgpu_bondorder_reset": (C.c_int, [_vp]),
     "fgpu_bondorder_accumulate_nlist": (C.c_int, [_vp, _vp, _fp, C.c_uint32, _fp]),
+    "fgpu_bondorder_accumulate": (C.c_int, [_vp, _vp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int, _fp, _fp]),
     "fgpu_bondorder_read": (C.c_int, [_vp, _up]),
     "fgpu_bondorder_deferred": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "fgpu_corr_create": (C.c_int, [_vp, C.c_uint32, C.c_float, _vpp]),
@@ -540,6 +541,21 @@ class DeviceBondOrder(_DeviceObject):
             assert len(o) == nlist.num_points and len(qo) == nlist.num_query_points
         check(lib().fgpu_bondorder_accumulate_nlist(self._h, nlist._h, ptr(o) if o is not None else None,
                                                     nlist.num_points, ptr(qo) if qo is not None else None))
+
+    def accumulate(self, points, query_points, flavour, r_max, orientations=None, query_orientations=None, r_min=0.0,
+                   exclude_ii=False):
+        """Ball query of ``points`` (``query_points=None``: against themselves) and the histogram in one call -- no
+        NeighborList (``fgpu_bondorder_accumulate``)."""
+        q = None if query_points is None else f32(query_points, 3)
+        nq = points.n if q is None else len(q)
+        o = qo = None
+        if orientations is not None:
+            o = np.ascontiguousarray(orientations, dtype=np.float32).reshape(-1, 4)
+            qo = np.ascontiguousarray(query_orientations, dtype=np.float32).reshape(-1, 4)
+            assert len(o) == points.n and len(qo) == nq
+        check(lib().fgpu_bondorder_accumulate(self._h, points._h, ptr(q), nq, int(flavour), float(r_max), float(r_min),
+                                              int(bool(exclude_ii)), ptr(o) if o is not None else None,
+                                              ptr(qo) if qo is not None else None))
 
     def read(self):
         counts = np.empty(self.shape, np.uint32)

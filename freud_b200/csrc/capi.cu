@@ -2103,104 +2103,182 @@ int fgpu_bondorder_reset(fgpu_bondorder* bo)
     });
 }
 
+namespace {
+
+// uploads the orientations of one frame and fills the kernel arguments that do not depend on where the bonds are
+BondOrderArgs stage_bond_order(fgpu_bondorder* bo, uint32_t n_points, uint32_t n_query, const float* orientations_host,
+                               const float* query_orientations_host)
+{
+    fgpu_ctx* ctx = bo->ctx;
+    require(bo->mode == FGPU_BOND_ORDER_BOD || (orientations_host != nullptr && query_orientations_host != nullptr),
+            FGPU_EINVALID, "null orientations");
+    BondOrderArgs a {};
+    a.at = bo->at;
+    a.ap = bo->ap;
+    a.mode = bo->mode;
+    a.hist = bo->hist.ptr;
+    if (bo->mode != FGPU_BOND_ORDER_BOD)
+    {
+        bo->stage_a.reserve(4 * (size_t) n_points + 4);
+        bo->stage_b.reserve(4 * (size_t) n_query + 4);
+        h2d(ctx, bo->stage_a.ptr, orientations_host, 4 * (size_t) n_points * sizeof(float));
+        h2d(ctx, bo->stage_b.ptr, query_orientations_host, 4 * (size_t) n_query * sizeof(float));
+        a.orientations = reinterpret_cast<const float4*>(bo->stage_a.ptr);
+        a.query_orientations = reinterpret_cast<const float4*>(bo->stage_b.ptr);
+    }
+    return a;
+}
+
+// One launch of k_bond_order over the bonds `a` describes, counting into a.hist, with room for `cap` bonds left to
+// the host (binned here with its libm and added to a.hist).  Returns false if more than `cap` were left over.
+bool run_bond_order_pass(fgpu_bondorder* bo, BondOrderArgs& a, uint64_t cap, const float* orientations_host,
+                         const float* query_orientations_host)
+{
+    fgpu_ctx* ctx = bo->ctx;
+    int const mode = bo->mode;
+    bo->deferred.reserve((size_t) cap);
+    bo->deferred_z.reserve((size_t) cap);
+    a.deferred = bo->deferred.ptr;
+    a.deferred_z = bo->deferred_z.ptr;
+    a.deferred_cap = (uint32_t) cap;
+    a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
+    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
+    launch_bond_order(ctx, a);
+    d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
+    sync(ctx);
+    uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
+    if (n_def > cap)
+    {
+        return false;
+    }
+    if (n_def == 0)
+    {
+        return true;
+    }
+    std::vector<uint4> rec(n_def);
+    std::vector<float> rec_z(n_def);
+    d2h(ctx, rec.data(), bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
+    d2h(ctx, rec_z.data(), bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
+    sync(ctx);
+    std::vector<uint32_t> bins;
+    for (uint32_t r = 0; r < n_def; ++r)
+    {
+        uint32_t const i = rec[r].x, j = rec[r].y;
+        float x, y, z = rec_z[r];
+        std::memcpy(&x, &rec[r].z, sizeof(float));
+        std::memcpy(&y, &rec[r].w, sizeof(float));
+        if (mode != FGPU_BOND_ORDER_BOD) // BondOrder.cc:108-134
+        {
+            const float* rq = orientations_host + 4 * (size_t) j;
+            const float* q = query_orientations_host + 4 * (size_t) i;
+            if (mode == FGPU_BOND_ORDER_OOCD)
+            {
+                x = 0.0f;
+                y = 0.0f;
+                z = 1.0f;
+                host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+            }
+            host_quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], x, y, z);
+            if (mode == FGPU_BOND_ORDER_OBCD)
+            {
+                host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+            }
+        }
+        float const theta = host_mod_two_pi(std::atan2(y, x)); // BondOrder.cc:140-141
+        float const xx = x * x, yy = y * y, zz = z * z;
+        float const dot = (xx + yy) + zz;
+        float const arg = z / std::sqrt(dot);
+        float const phi = std::acos(arg); // :144
+        int const bt = host_axis_bin(a.at, theta), bp = host_axis_bin(a.ap, phi);
+        if (bt >= 0 && bp >= 0)
+        {
+            bins.push_back((uint32_t) bt * a.ap.bins + (uint32_t) bp);
+        }
+    }
+    bo->deferred_total += n_def;
+    if (!bins.empty())
+    {
+        bo->host_bins.reserve(bins.size());
+        h2d(ctx, bo->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
+        launch_add_bins(ctx, bo->host_bins.ptr, (uint32_t) bins.size(), a.hist);
+        sync(ctx);
+    }
+    return true;
+}
+
+} // namespace
+
 int fgpu_bondorder_accumulate_nlist(fgpu_bondorder* bo, const fgpu_nlist* nl, const float* orientations_host,
                                     uint32_t n_points, const float* query_orientations_host)
 {
     return guarded([&] {
         require(bo != nullptr && nl != nullptr, FGPU_EINVALID, "null argument");
         require(bo->ctx == nl->ctx, FGPU_EINVALID, "bond order and nlist belong to different contexts");
-        int const mode = bo->mode;
-        require(mode == FGPU_BOND_ORDER_BOD || (orientations_host != nullptr && query_orientations_host != nullptr),
-                FGPU_EINVALID, "null orientations");
         fgpu_ctx* ctx = bo->ctx;
         bind_device(ctx);
-        BondOrderArgs a {};
-        a.at = bo->at;
-        a.ap = bo->ap;
-        a.mode = mode;
-        a.hist = bo->hist.ptr;
-        if (mode != FGPU_BOND_ORDER_BOD)
-        {
-            bo->stage_a.reserve(4 * (size_t) n_points + 4);
-            bo->stage_b.reserve(4 * (size_t) nl->n_query + 4);
-            h2d(ctx, bo->stage_a.ptr, orientations_host, 4 * (size_t) n_points * sizeof(float));
-            h2d(ctx, bo->stage_b.ptr, query_orientations_host, 4 * (size_t) nl->n_query * sizeof(float));
-            a.orientations = reinterpret_cast<const float4*>(bo->stage_a.ptr);
-            a.query_orientations = reinterpret_cast<const float4*>(bo->stage_b.ptr);
-        }
-        std::vector<uint4> rec;
-        std::vector<float> rec_z;
-        std::vector<uint32_t> bins;
+        BondOrderArgs a = stage_bond_order(bo, n_points, nl->n_query, orientations_host, query_orientations_host);
         for (uint64_t b0 = 0; b0 < nl->n_bonds; b0 += kPmftChunk)
         {
             uint64_t const nb = std::min<uint64_t>(kPmftChunk, nl->n_bonds - b0);
             a.neighbors = nl->neighbors.ptr + 2 * b0;
             a.vectors = nl->vectors.ptr + 3 * b0;
             a.n_bonds = nb;
-            bo->deferred.reserve((size_t) nb);
-            bo->deferred_z.reserve((size_t) nb);
-            a.deferred = bo->deferred.ptr;
-            a.deferred_z = bo->deferred_z.ptr;
-            a.deferred_cap = (uint32_t) nb;
-            a.deferred_count = reinterpret_cast<uint32_t*>(ctx->d_scalars + 7);
-            FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 7, 0, sizeof(unsigned long long), ctx->stream));
-            launch_bond_order(ctx, a);
-            d2h(ctx, ctx->h_scalars + 7, ctx->d_scalars + 7, sizeof(unsigned long long));
-            sync(ctx);
-            uint32_t const n_def = (uint32_t) (ctx->h_scalars[7] & 0xffffffffULL);
-            if (n_def == 0)
-            {
-                continue;
-            }
-            rec.resize(n_def);
-            rec_z.resize(n_def);
-            d2h(ctx, rec.data(), bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
-            d2h(ctx, rec_z.data(), bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
-            sync(ctx);
-            bins.clear();
-            for (uint32_t r = 0; r < n_def; ++r)
-            {
-                uint32_t const i = rec[r].x, j = rec[r].y;
-                float x, y, z = rec_z[r];
-                std::memcpy(&x, &rec[r].z, sizeof(float));
-                std::memcpy(&y, &rec[r].w, sizeof(float));
-                if (mode != FGPU_BOND_ORDER_BOD) // BondOrder.cc:108-134
-                {
-                    const float* rq = orientations_host + 4 * (size_t) j;
-                    const float* q = query_orientations_host + 4 * (size_t) i;
-                    if (mode == FGPU_BOND_ORDER_OOCD)
-                    {
-                        x = 0.0f;
-                        y = 0.0f;
-                        z = 1.0f;
-                        host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
-                    }
-                    host_quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], x, y, z);
-                    if (mode == FGPU_BOND_ORDER_OBCD)
-                    {
-                        host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
-                    }
-                }
-                float const theta = host_mod_two_pi(std::atan2(y, x)); // BondOrder.cc:140-141
-                float const xx = x * x, yy = y * y, zz = z * z;
-                float const dot = (xx + yy) + zz;
-                float const arg = z / std::sqrt(dot);
-                float const phi = std::acos(arg); // :144
-                int const bt = host_axis_bin(a.at, theta), bp = host_axis_bin(a.ap, phi);
-                if (bt >= 0 && bp >= 0)
-                {
-                    bins.push_back((uint32_t) bt * a.ap.bins + (uint32_t) bp);
-                }
-            }
-            bo->deferred_total += n_def;
-            if (!bins.empty())
-            {
-                bo->host_bins.reserve(bins.size());
-                h2d(ctx, bo->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
-                launch_add_bins(ctx, bo->host_bins.ptr, (uint32_t) bins.size(), bo->hist.ptr);
-                sync(ctx);
-            }
+            run_bond_order_pass(bo, a, nb, orientations_host, query_orientations_host); // room for every bond
         }
+        sync(ctx); // the caller's arrays were consumed
+    });
+}
+
+// query + histogram in one call, the bonds read from the search's bag (see fgpu_pmft_accumulate)
+int fgpu_bondorder_accumulate(fgpu_bondorder* bo, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                              int flavour, float r_max, float r_min, int exclude_ii, const float* orientations_host,
+                              const float* query_orientations_host)
+{
+    return guarded([&] {
+        require(bo != nullptr && pts != nullptr, FGPU_EINVALID, "null argument");
+        require(bo->ctx == pts->ctx, FGPU_EINVALID, "bond order and points belong to different contexts");
+        fgpu_ctx* ctx = bo->ctx;
+        bind_device(ctx);
+        validate_ball(pts, flavour, r_max, r_min);
+        bool const self = query_points_host == nullptr;
+        require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
+        require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
+        uint64_t n_bonds = 0;
+        if (!search_to_bag(pts, query_points_host, n_query, flavour, r_max, r_min, exclude_ii, &n_bonds))
+        {
+            fgpu_nlist* nl = nullptr;
+            ball_query_impl(pts, query_points_host, nullptr, n_query, 0, flavour, r_max, r_min, exclude_ii, 0, &nl);
+            std::unique_ptr<fgpu_nlist, void (*)(fgpu_nlist*)> guard(nl, fgpu_nlist_destroy);
+            int const rc = fgpu_bondorder_accumulate_nlist(bo, nl, orientations_host, pts->n, query_orientations_host);
+            if (rc != FGPU_OK)
+            {
+                throw Error(rc, fgpu_last_error());
+            }
+            return;
+        }
+        BondOrderArgs a = stage_bond_order(bo, pts->n, n_query, orientations_host, query_orientations_host);
+        size_t const n_bins = (size_t) bo->at.bins * bo->ap.bins;
+        bo->frame_hist.reserve(n_bins);
+        a.hist = bo->frame_hist.ptr;
+        a.bag = ctx->bag4.ptr;
+        a.row_bag_start = ctx->tmp_start.ptr;
+        a.row_counts = ctx->row_counts.ptr;
+        a.n_rows = n_query;
+        double const per_row = (double) n_bonds / (double) n_query;
+        a.group = per_row < 6.0 ? 4U : (per_row <= 96.0 ? 8U : 32U);
+        uint64_t room = std::min<uint64_t>(std::max<uint64_t>(n_bonds / 16, 4096), n_bonds);
+        uint64_t const before = bo->deferred_total;
+        for (;;)
+        {
+            FGPU_CUDA_CHECK(cudaMemsetAsync(bo->frame_hist.ptr, 0, n_bins * sizeof(uint32_t), ctx->stream));
+            bo->deferred_total = before;
+            if (run_bond_order_pass(bo, a, room, orientations_host, query_orientations_host))
+            {
+                break;
+            }
+            room = n_bonds; // e.g. a perfect lattice: every bond direction on a bin edge
+        }
+        launch_add_hist(ctx, bo->frame_hist.ptr, (uint32_t) n_bins, bo->hist.ptr);
         sync(ctx); // the caller's arrays were consumed
     });
 }

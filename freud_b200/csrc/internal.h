@@ -257,6 +257,7 @@ struct fgpu_bondorder
     fgpu::DevBuf<uint4> deferred;          // bonds left to the host's libm: (i, j, bits vx, bits vy) ...
     fgpu::DevBuf<float> deferred_z;        // ... and vz
     fgpu::DevBuf<uint32_t> host_bins;
+    fgpu::DevBuf<uint32_t> frame_hist;     // one-call route: the histogram of the frame being accumulated
     uint64_t deferred_total = 0;
 };
 
@@ -550,6 +551,12 @@ struct BondOrderArgs
     const uint32_t* neighbors;
     const float* vectors;
     uint64_t n_bonds;
+    // ... or the bonds still in the search's bag, grouped by query row: bag != nullptr (as Pmft3Args)
+    const float4* bag;
+    const uint32_t* row_bag_start;
+    const uint32_t* row_counts;
+    uint32_t n_rows;
+    uint32_t group;
     const float4* orientations;       // per point, (s, x, y, z)
     const float4* query_orientations; // per query point
     uint32_t* hist;

@@ -278,7 +278,63 @@ __global__ void __launch_bounds__(256) k_add_hist(const uint32_t* __restrict__ f
 // asks, then theta = modulusPositive(atan2f(v.y, v.x), 2 pi) on RegularAxis(n_theta, 0, 2 pi) and
 // phi = acosf(v.z / sqrt(v.v)) on RegularAxis(n_phi, 0, pi).  Both angles are bracketed like the PMFT angles: CUDA's
 // atan2f / acosf of the reference's float arguments, bins accepted away from the bin edges, the rest left to the host.
-__global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
+template<typename Hist>
+__device__ __forceinline__ void bond_order_bond(const BondOrderArgs& a, uint32_t i, uint32_t j, float vx, float vy, float vz,
+                                                Hist* h)
+{
+    float x = vx, y = vy, z = vz;
+    if (a.mode != FGPU_BOND_ORDER_BOD)
+    {
+        float4 const rq = a.orientations[j];      // ref_q = orientations[point], BondOrder.cc:108
+        float4 const q = a.query_orientations[i]; // q = query_orientations[query point], :110
+        if (a.mode == FGPU_BOND_ORDER_OOCD)
+        {
+            x = 0.0f;
+            y = 0.0f;
+            z = 1.0f;
+            quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :127-130
+        }
+        quat_rotate(rq.x, -rq.y, -rq.z, -rq.w, x, y, z); // rotate(conj(ref_q), .), :116, :123, :133
+        if (a.mode == FGPU_BOND_ORDER_OBCD)
+        {
+            quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :117
+        }
+    }
+    // theta: the chain of angle_bin with orientation - d replaced by d itself (t grows with d here)
+    float const d = atan2f(y, x);
+    float const theta = mod_two_pi(d);
+    int const bt0 = axis_bin(a.at, theta);
+    float const th_lo = mod_two_pi(d - kAngleMargin), th_hi = mod_two_pi(d + kAngleMargin);
+    bool sure = axis_bin(a.at, th_lo) == bt0 && axis_bin(a.at, th_hi) == bt0 && th_lo <= theta && theta <= th_hi
+        && theta > kEdgeGuard && theta < kTwoPi - kEdgeGuard;
+    // phi: the argument is float arithmetic (one division, one square root), acosf is libm's; the bin is a
+    // monotone function of phi
+    float const c = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
+    float const phi = acosf(c);
+    int const bp0 = axis_bin(a.ap, phi);
+    sure = sure && axis_bin(a.ap, phi - kAngleMargin) == bp0 && axis_bin(a.ap, phi + kAngleMargin) == bp0
+        && phi > kEdgeGuard && phi < a.ap.r_max - kEdgeGuard;
+    if (sure)
+    {
+        int const bt = axis_bin(a.at, theta), bp = axis_bin(a.ap, phi);
+        if (bt >= 0 && bp >= 0)
+        {
+            atomicAdd(&h[(uint32_t) bt * a.ap.bins + (uint32_t) bp], 1U);
+        }
+    }
+    else
+    {
+        uint32_t const slot = atomicAdd(a.deferred_count, 1U);
+        if (slot < a.deferred_cap)
+        {
+            a.deferred[slot] = make_uint4(i, j, __float_as_uint(vx), __float_as_uint(vy));
+            a.deferred_z[slot] = vz;
+        }
+    }
+}
+
+// ROWS = false: one thread per bond of a NeighborList; ROWS = true: a.group lanes per query row of the search's bag
+template<bool ROWS> __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
 {
     extern __shared__ uint32_t bo_hist[];
     uint32_t const n_bins = a.at.bins * a.ap.bins;
@@ -291,58 +347,26 @@ __global__ void __launch_bounds__(256) k_bond_order(BondOrderArgs a)
         __syncthreads();
     }
     uint32_t* const h = a.use_shared ? bo_hist : a.hist;
-    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
+    if (ROWS)
     {
-        uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
-        float const vx = a.vectors[3 * k], vy = a.vectors[3 * k + 1], vz = a.vectors[3 * k + 2];
-        float x = vx, y = vy, z = vz;
-        if (a.mode != FGPU_BOND_ORDER_BOD)
+        uint32_t const g = a.group, sub = threadIdx.x & (g - 1U);
+        uint32_t const groups = gridDim.x * blockDim.x / g;
+        for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / g; row < a.n_rows; row += groups)
         {
-            float4 const rq = a.orientations[ij.y];      // ref_q = orientations[point], BondOrder.cc:108
-            float4 const q = a.query_orientations[ij.x]; // q = query_orientations[query point], :110
-            if (a.mode == FGPU_BOND_ORDER_OOCD)
+            uint32_t const n = a.row_counts[row], start = a.row_bag_start[row];
+            for (uint32_t k = sub; k < n; k += g)
             {
-                x = 0.0f;
-                y = 0.0f;
-                z = 1.0f;
-                quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :127-130
-            }
-            quat_rotate(rq.x, -rq.y, -rq.z, -rq.w, x, y, z); // rotate(conj(ref_q), .), :116, :123, :133
-            if (a.mode == FGPU_BOND_ORDER_OBCD)
-            {
-                quat_rotate(q.x, q.y, q.z, q.w, x, y, z); // :117
+                float4 const r = a.bag[start + k];
+                bond_order_bond(a, row, __float_as_uint(r.w), r.x, r.y, r.z, h);
             }
         }
-        // theta: the chain of angle_bin with orientation - d replaced by d itself (t grows with d here)
-        float const d = atan2f(y, x);
-        float const theta = mod_two_pi(d);
-        int const bt0 = axis_bin(a.at, theta);
-        float const th_lo = mod_two_pi(d - kAngleMargin), th_hi = mod_two_pi(d + kAngleMargin);
-        bool sure = axis_bin(a.at, th_lo) == bt0 && axis_bin(a.at, th_hi) == bt0 && th_lo <= theta && theta <= th_hi
-            && theta > kEdgeGuard && theta < kTwoPi - kEdgeGuard;
-        // phi: the argument is float arithmetic (one division, one square root), acosf is libm's; the bin is a
-        // monotone function of phi
-        float const c = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
-        float const phi = acosf(c);
-        int const bp0 = axis_bin(a.ap, phi);
-        sure = sure && axis_bin(a.ap, phi - kAngleMargin) == bp0 && axis_bin(a.ap, phi + kAngleMargin) == bp0
-            && phi > kEdgeGuard && phi < a.ap.r_max - kEdgeGuard;
-        if (sure)
+    }
+    else
+    {
+        for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < a.n_bonds; k += (uint64_t) gridDim.x * blockDim.x)
         {
-            int const bt = axis_bin(a.at, theta), bp = axis_bin(a.ap, phi);
-            if (bt >= 0 && bp >= 0)
-            {
-                atomicAdd(&h[(uint32_t) bt * a.ap.bins + (uint32_t) bp], 1U);
-            }
-        }
-        else
-        {
-            uint32_t const slot = atomicAdd(a.deferred_count, 1U);
-            if (slot < a.deferred_cap)
-            {
-                a.deferred[slot] = make_uint4(ij.x, ij.y, __float_as_uint(vx), __float_as_uint(vy));
-                a.deferred_z[slot] = vz;
-            }
+            uint2 const ij = reinterpret_cast<const uint2*>(a.neighbors)[k];
+            bond_order_bond(a, ij.x, ij.y, a.vectors[3 * k], a.vectors[3 * k + 1], a.vectors[3 * k + 2], h);
         }
     }
     if (a.use_shared)
@@ -424,16 +448,25 @@ void launch_add_hist(fgpu_ctx* ctx, const uint32_t* frame, uint32_t n, uint32_t*
 
 void launch_bond_order(fgpu_ctx* ctx, BondOrderArgs a)
 {
-    if (a.n_bonds == 0)
+    bool const rows = a.bag != nullptr;
+    if (rows ? a.n_rows == 0 : a.n_bonds == 0)
     {
         return;
     }
     size_t const smem = (size_t) a.at.bins * a.ap.bins * sizeof(uint32_t);
     a.use_shared = smem <= 40 * 1024 ? 1 : 0;
-    unsigned const blocks = (unsigned) std::min<uint64_t>((a.n_bonds + 255) / 256, (uint64_t) ctx->sm_count * 8U);
+    uint64_t const want = rows ? ((uint64_t) a.n_rows * a.group + 255) / 256 : (a.n_bonds + 255) / 256;
+    unsigned const blocks = (unsigned) std::min<uint64_t>(want, (uint64_t) ctx->sm_count * 8U);
     {
-        KernelScope ks(ctx, "bond_order");
-        k_bond_order<<<blocks, 256, a.use_shared ? smem : 0, ctx->stream>>>(a);
+        KernelScope ks(ctx, rows ? "bond_order_rows" : "bond_order");
+        if (rows)
+        {
+            k_bond_order<true><<<blocks, 256, a.use_shared ? smem : 0, ctx->stream>>>(a);
+        }
+        else
+        {
+            k_bond_order<false><<<blocks, 256, a.use_shared ? smem : 0, ctx->stream>>>(a);
+        }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }

@@ -78,25 +78,42 @@ public:
                     const std::shared_ptr<locality::NeighborList>& nlist, locality::QueryArgs qargs)
     {
         m_box = neighbor_query->getBox();
-        std::shared_ptr<locality::NeighborList> list = nlist;
-        if (!list)
-        {
-            list = neighbor_query->query(query_points, n_query_points, qargs)->toNeighborList();
-        }
-        else
-        {
-            list->validate(n_query_points, neighbor_query->getNPoints());
-        }
         if (!m_dev)
         {
             fgpu_bondorder* h = nullptr;
             gpu::check(fgpu_bondorder_create(gpu::context(), (uint32_t) m_nt, (uint32_t) m_np, (int) m_mode, &h));
             m_dev = std::shared_ptr<fgpu_bondorder>(h, fgpu_bondorder_destroy);
         }
-        gpu::check(fgpu_bondorder_accumulate_nlist(m_dev.get(), list->device(gpu::context()),
-                                                   reinterpret_cast<const float*>(orientations),
-                                                   neighbor_query->getNPoints(),
-                                                   reinterpret_cast<const float*>(query_orientations)));
+        std::shared_ptr<locality::NeighborList> list = nlist;
+        if (!list)
+        {
+            auto query = neighbor_query->query(query_points, n_query_points, qargs); // validates, infers the mode
+            locality::QueryArgs const& args = query->getQueryArgs();
+            if (args.mode == locality::QueryType::ball)
+            {
+                // a ball query made for this diagram alone: the bonds are binned where the search left them
+                gpu::check(fgpu_bondorder_accumulate(m_dev.get(), neighbor_query->device(),
+                                                     locality::selfOrHost(*neighbor_query, query_points, n_query_points),
+                                                     n_query_points, neighbor_query->getFlavour(), args.r_max, args.r_min,
+                                                     args.exclude_ii ? 1 : 0, reinterpret_cast<const float*>(orientations),
+                                                     reinterpret_cast<const float*>(query_orientations)));
+            }
+            else
+            {
+                list = query->toNeighborList();
+            }
+        }
+        else
+        {
+            list->validate(n_query_points, neighbor_query->getNPoints());
+        }
+        if (list)
+        {
+            gpu::check(fgpu_bondorder_accumulate_nlist(m_dev.get(), list->device(gpu::context()),
+                                                       reinterpret_cast<const float*>(orientations),
+                                                       neighbor_query->getNPoints(),
+                                                       reinterpret_cast<const float*>(query_orientations)));
+        }
         m_frame_counter++;
         m_reduce = true;
     }

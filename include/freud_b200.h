@@ -87,7 +87,7 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
  * duration [ms] and launch count of the kernels whose name starts with `prefix` ("" = all) since the last
  * reset.  Names: cell_assign, cell_scatter, scan, search_nl, search_rdf, emit, segments, knn, knn_emit,
- * rdf_distances, local_density, local_density_rows, correlation, correlation_rows, pmft3, pmft3_rows, pmft_add_hist, bond_order, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
+ * rdf_distances, local_density, local_density_rows, correlation, correlation_rows, pmft3, pmft3_rows, pmft_add_hist, bond_order, bond_order_rows, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
 
@@ -270,6 +270,10 @@ void fgpu_bondorder_destroy(fgpu_bondorder* bo);
 int fgpu_bondorder_reset(fgpu_bondorder* bo);
 int fgpu_bondorder_accumulate_nlist(fgpu_bondorder* bo, const fgpu_nlist* nl, const float* orientations_host,
                                     uint32_t n_points, const float* query_orientations_host);
+/* the ball query and the histogram in one call, the bonds read from the search's hit bag (see fgpu_pmft_accumulate) */
+int fgpu_bondorder_accumulate(fgpu_bondorder* bo, fgpu_points* pts, const float* query_points_host, uint32_t n_query,
+                              int flavour, float r_max, float r_min, int exclude_ii, const float* orientations_host,
+                              const float* query_orientations_host);
 int fgpu_bondorder_read(fgpu_bondorder* bo, uint32_t* counts_host);
 int fgpu_bondorder_deferred(const fgpu_bondorder* bo, uint64_t* bonds);
 

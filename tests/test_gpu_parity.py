@@ -453,6 +453,42 @@ def test_pmft_query_and_histogram_in_one_call(ctx):
     assert np.array_equal(small.read(), port.pmft3(port.PMFT_XYT, tiny, 60, nl, ta, ta, (2.0, 2.0), (5, 5, 4))[0])
 
 
+def test_bond_order_query_and_histogram_in_one_call(ctx):
+    """fgpu_bondorder_accumulate: ball query and diagram without a NeighborList (bonds read from the search's bag) -- the
+    oracle's counts over the same bonds, bit for bit, in all four modes, for separate query points and a self query, two
+    accumulated frames; a perfect FCC lattice sends every bond to the host and the frame is repeated with a longer list."""
+    from freud_b200 import data
+    from freud_b200.box import Box
+    from tests.golden.make_golden import pmft3_quats
+
+    capi = _capi()
+    box = Box(12, 13, 14, 0.2, -0.1, 0.15)
+    pts, q = random_points(box, 800, 41), random_points(box, 300, 42)
+    o, qo = pmft3_quats(800, 1), pmft3_quats(300, 2)
+    dp = capi.DevicePoints(ctx, box, pts)
+    for flavour, pflav in ((IMAGE, port.IMAGE), (WRAP, port.WRAP)):
+        nl_q = port.ball_nlist(pflav, box, False, pts, q, 3.0)
+        nl_s = port.ball_nlist(pflav, box, False, pts, pts, 3.0, 0.0, True)
+        for mode in ("bod", "lbod", "obcd", "oocd"):
+            bo = capi.DeviceBondOrder(ctx, 12, 9, mode)
+            bo.accumulate(dp, q, flavour, 3.0, o, qo)
+            want = port.bond_order(mode, nl_q, o, qo, (12, 9))[0]
+            assert np.array_equal(bo.read(), want), mode
+            bo.accumulate(dp, q, flavour, 3.0, o, qo)
+            assert np.array_equal(bo.read(), 2 * want), mode
+            bo.reset()
+            bo.accumulate(dp, None, flavour, 3.0, o, o, exclude_ii=True)
+            assert np.array_equal(bo.read(), port.bond_order(mode, nl_s, o, o, (12, 9))[0]), mode
+    fbox, fpts = data.UnitCell.fcc().generate_system(8)
+    ident = np.tile(np.float32([1, 0, 0, 0]), (len(fpts), 1))
+    fcc = capi.DeviceBondOrder(ctx, 8, 4)
+    fcc.accumulate(capi.DevicePoints(ctx, fbox, fpts), None, IMAGE, 0.8, exclude_ii=True)  # the 12 nearest: a / sqrt 2
+    nl = port.ball_nlist(port.IMAGE, fbox, False, fpts, fpts, 0.8, 0.0, True)
+    assert len(nl.distances) == 12 * len(fpts)
+    assert np.array_equal(fcc.read(), port.bond_order("bod", nl, ident, ident, (8, 4))[0])
+    assert fcc.host_binned_bonds > len(nl.distances) // 16  # more than the first list held: the frame was repeated
+
+
 def test_local_density_and_correlation_in_one_call(ctx):
     """fgpu_local_density_query / fgpu_corr_accumulate: the ball query and the sums without a NeighborList in between (the
     bonds are read from the search's bag).  Correlation bin counts are identical to the list route's and the oracle's;
