@@ -472,25 +472,10 @@ def workload_hist_client(ctx, rank, n, name):
         accumulate(query(dp))
         return hist.read()
 
-    trace = []
-
     def step_e2e():
-        t0 = time.perf_counter()
         hist.reset()
-        d = _capi.DevicePoints(ctx, box, pin_pts)
-        t1 = time.perf_counter()
-        nl = query(d)
-        t2 = time.perf_counter()
-        accumulate(nl)
-        t3 = time.perf_counter()
-        out = hist.read()
-        del nl, d
-        t4 = time.perf_counter()
-        if os.environ.get("FGPU_BENCH_TRACE"):
-            trace.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
-            if len(trace) == 22:
-                print("e2e phases (points, query, accumulate, read+free) ms:", trace, file=sys.stderr)
-        return out
+        accumulate(query(_capi.DevicePoints(ctx, box, pin_pts)))
+        return hist.read()
 
     nb = int(np.prod(spec["bins"]))
     o_bytes = 0 if orient is None else orient.nbytes
