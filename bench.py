@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 
 RHO = 0.08
 WRAP, IMAGE = 0, 1
+TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload "
+                  "(profiles/ncu_r*_summary.md; the newest capture of the kernel named)")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -159,8 +161,8 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
                                     f"flavour={'wrap' if flavour == WRAP else 'image'}",
                         "bonds_per_step": n_bonds, "pair_evals_per_step": evals, "n_cells": n_cells},
                 # 24 B per bond cross PCIe (indices, distance, vector); the unit weights are written by the host
-                h2d=12 * n, d2h=24 * n_bonds + 8 * n, algo=algo, keep=keep, box=box, pts=pts, r_max=r_max,
-                secondary={"bonds": n_bonds})
+                h2d=12 * n, d2h=24 * n_bonds + 8 * n, algo=algo, keep=keep, box=box, pts=pts, r_max=r_max, dp=dp,
+                traffic_source=TRAFFIC_SOURCE, secondary={"bonds": n_bonds})
 
 
 def workload_rdf(ctx, rank, n, bins=100, r_max=5.0, flavour=IMAGE, tilt=None, is2d=False, density=RHO):
@@ -198,6 +200,7 @@ def workload_rdf(ctx, rank, n, bins=100, r_max=5.0, flavour=IMAGE, tilt=None, is
                                     f"flavour={'wrap' if flavour == WRAP else 'image'} fused (no NeighborList)",
                         "bonds_per_step": n_bonds, "pair_evals_per_step": evals},
                 h2d=12 * n, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max, rdf=rdf, dp=dp,
+                bins=bins, flavour=flavour, traffic_source=TRAFFIC_SOURCE,
                 # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v6_summary.md "full_rdf"): config 1 M / r=5 / image
                 traffic={"search_rdf": 16412672} if (n, r_max, flavour, bins, tilt, is2d) == (1_000_000, 5.0, IMAGE, 100, None, False)
                 else {},
@@ -238,6 +241,7 @@ def workload_q6(ctx, rank, n):
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
                 config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
                 h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={},
+                dp=dp, traffic_source=TRAFFIC_SOURCE,
                 # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v6_summary.md "full_q6")
                 traffic={"search_nl": 20075008 + 221451008, "knn_select": 366002432 + 323085568,
                          "steinhardt": 162739968 + 6141952} if n == 1_000_188 else {})
@@ -570,11 +574,12 @@ def cpu_reference_local_density(box, pts, r_max, diameter, budget_s=12.0, thread
 
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_nl(box, pts, r_max, budget_s=12.0, threads=None):
-    """The reference's own LinkCell (oracle/_ref, all host threads) on a bounded sample of query points.
+    """The reference's NeighborList query on this box's host cores, bounded samples of the query points.
 
-    The unmodified LinkCell deep-copies the whole cell list per visited cell, so only a few
-    thousand query points fit the budget at N = 1e6; its AABBQuery engine is timed beside it as the practical
-    CPU comparator."""
+    `value` is its practical engine, AABBQuery (what `(box, points)` systems get upstream): pair evaluations of the
+    27-cell scheme that the sampled query points stand for, per second, tree build excluded.  The engine BASELINE names,
+    LinkCell, is timed beside it as `linkcell_quadratic`: unmodified, it deep-copies the whole cell list per visited
+    cell, so it is a footnote, not a comparator."""
     from oracle import port, ref
 
     threads = threads or os.cpu_count()
@@ -588,34 +593,40 @@ def cpu_reference_nl(box, pts, r_max, budget_s=12.0, threads=None):
         out.update(value=ev / dt, unit="pair_evals/s", sample=f"oracle port, all {len(pts)} query points, {dt:.2f} s",
                    bonds_per_sec=len(nl) / dt)
         return out
+    # practical engine: AABBQuery on a sample sized to the budget
+    t0 = time.perf_counter()
+    qa = ref.Query("aabb", box, pts)
+    build_a = time.perf_counter() - t0
+    ma = min(len(pts), 20000)
+    t0 = time.perf_counter()
+    qa.nlist(pts[:ma], mode="ball", r_max=r_max, exclude_ii=True)
+    probe = time.perf_counter() - t0
+    ma2 = int(min(len(pts), max(ma, ma * 0.7 * budget_s / max(probe, 1e-6))))
+    t0 = time.perf_counter()
+    nla = qa.nlist(pts[:ma2], mode="ball", r_max=r_max, exclude_ii=True)
+    dta = time.perf_counter() - t0
+    eva = port.count_candidates(box, box.is2D, pts, pts[:ma2], r_max)
+    out.update(value=eva / dta, unit="pair_evals/s", bonds_per_sec=len(nla) / dta, engine="AABBQuery",
+               sample=f"reference AABBQuery.query(ball r_max={r_max:g}).toNeighborList() N={len(pts)}: first {ma2} query "
+                      f"points in {dta:.2f} s (+{build_a:.2f} s tree build, not counted); pair evals = the 27-cell "
+                      f"candidates those query points have")
+    del qa
+    # the engine the config names, a few thousand query points of it
     t0 = time.perf_counter()
     q = ref.Query("linkcell", box, pts, cell_width=r_max)
     build_s = time.perf_counter() - t0
     m = min(len(pts), 8 * threads)
     t0 = time.perf_counter()
-    q.nlist(pts[:m], r_max=r_max, exclude_ii=True)
+    q.nlist(pts[:m], mode="ball", r_max=r_max, exclude_ii=True)
     probe = time.perf_counter() - t0
-    m2 = int(min(len(pts), max(m, m * budget_s / max(probe, 1e-6))))
+    m2 = int(min(len(pts), max(m, m * 0.3 * budget_s / max(probe, 1e-6))))
     t0 = time.perf_counter()
-    nl = q.nlist(pts[:m2], r_max=r_max, exclude_ii=True)
+    nl = q.nlist(pts[:m2], mode="ball", r_max=r_max, exclude_ii=True)
     dt = time.perf_counter() - t0
     ev = port.count_candidates(box, box.is2D, pts, pts[:m2], r_max)
-    out.update(value=ev / dt, unit="pair_evals/s", bonds_per_sec=len(nl) / dt,
-               sample=f"reference LinkCell(cell_width={r_max:g}) N={len(pts)}: first {m2} query points in {dt:.2f} s "
-                      f"(+{build_s:.2f} s serial build, not counted)")
-    # practical engine: AABBQuery on a sample sized to the same budget
-    t0 = time.perf_counter()
-    qa = ref.Query("aabb", box, pts)
-    ma = min(len(pts), 20000)
-    qa.nlist(pts[:ma], r_max=r_max, exclude_ii=True)
-    probe = time.perf_counter() - t0
-    ma2 = int(min(len(pts), max(ma, ma * 0.5 * budget_s / max(probe, 1e-6))))
-    t0 = time.perf_counter()
-    nla = qa.nlist(pts[:ma2], r_max=r_max, exclude_ii=True)
-    dta = time.perf_counter() - t0
-    eva = port.count_candidates(box, box.is2D, pts, pts[:ma2], r_max)
-    out["aabb"] = {"value": eva / dta, "unit": "pair_evals/s (27-cell-equivalent)", "bonds_per_sec": len(nla) / dta,
-                   "sample": f"reference AABBQuery N={len(pts)}: first {ma2} query points in {dta:.2f} s"}
+    out["linkcell_quadratic"] = {"value": ev / dt, "unit": "pair_evals/s", "bonds_per_sec": len(nl) / dt,
+                                 "sample": f"reference LinkCell(cell_width={r_max:g}) N={len(pts)}: first {m2} query "
+                                           f"points in {dt:.2f} s (+{build_s:.2f} s serial build, not counted)"}
     return out
 
 
@@ -664,28 +675,149 @@ def cpu_reference_q6(box, pts, budget_s=12.0, threads=None):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# parity: the leg's result at its full size against the oracle, outside the timed regions (rank 0 only)
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def parity_nl(w, flavour):
+    """All five NeighborList arrays + segments / counts of the benchmark's own frame, bit for bit against the oracle's
+    restatement of LinkCell / AABBQuery (oracle/port.c: grid + exact per-pair arithmetic; pinned to the compiled
+    reference in tests/test_oracle_port.py)."""
+    from oracle import port
+
+    t0 = time.perf_counter()
+    got = w["dp"].ball_query(None, flavour, w["r_max"], 0.0, True).to_host()
+    want = port.ball_nlist(port.WRAP if flavour == WRAP else port.IMAGE, w["box"], w["box"].is2D, w["pts"], w["pts"],
+                           w["r_max"], 0.0, True)
+    same = {k: bool(np.array_equal(_bits(got[k]), _bits(getattr(want, k))))
+            for k in ("neighbors", "distances", "weights", "vectors", "segments", "counts")}
+    return {"oracle": "port (oracle/port.c fport_ball_nlist)", "n_bonds": int(len(want)), "n_bonds_gpu": int(len(got["distances"])),
+            "arrays": same, "bitwise_equal": all(same.values()), "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def parity_rdf_counts(got, w, bins, frames=None):
+    """Raw bin counts against the oracle (u32, bit-exact).  frames: list of (box, points) accumulated (default: the
+    leg's own frame)."""
+    from oracle import port
+
+    t0 = time.perf_counter()
+    want = np.zeros(bins, np.uint32)
+    for box, pts in (frames or [(w["box"], w["pts"])]):
+        want = port.rdf_accumulate(port.IMAGE if w.get("flavour", IMAGE) == IMAGE else port.WRAP, box, box.is2D, pts, pts,
+                                   bins, w["r_max"], 0.0, True, counts=want)
+    return {"oracle": "port (oracle/port.c fport_rdf_accumulate)", "n_bonds": int(want.astype(np.uint64).sum()),
+            "n_bonds_gpu": int(np.asarray(got).astype(np.uint64).sum()),
+            "bitwise_equal": bool(np.array_equal(np.asarray(got, dtype=np.uint32), want)),
+            "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def parity_q6(w):
+    """q_l of every particle against the reference's own Steinhardt on its own AABB kNN list (oracle/_ref), tolerance
+    1e-5 relative as north_star states; the kNN NeighborList itself bit for bit."""
+    from oracle import ref
+
+    if not ref.available():
+        return {"oracle": "unavailable (oracle/_ref missing)", "bitwise_equal": None}
+    t0 = time.perf_counter()
+    ref.set_num_threads(os.cpu_count())
+    dp = w["dp"]
+    nl = dp.knn_query(None, 12, exclude_ii=True)
+    got = dp.steinhardt(nl, [6], want_qlm=False)["ql"][:, 0]
+    got_nl = nl.to_host()
+    q = ref.Query("aabb", w["box"], w["pts"])
+    want_nl = q.nlist(w["pts"], mode="nearest", num_neighbors=12, exclude_ii=True)
+    want = ref.Steinhardt(6).compute(q, nlist=want_nl)["ql"][:, 0]
+    same = {k: bool(np.array_equal(_bits(got_nl[k]), _bits(getattr(want_nl, k))))
+            for k in ("neighbors", "distances", "vectors", "segments", "counts")}
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+    return {"oracle": "reference (oracle/_ref: AABBQuery kNN + Steinhardt::compute)", "n_particles": int(len(want)),
+            "ql_max_rel_diff": float(rel.max()), "ql_tolerance_rel": 1e-5, "ql_within_tolerance": bool(rel.max() <= 1e-5),
+            "knn_nlist_arrays": same, "bitwise_equal": all(same.values()),
+            "seconds": round(time.perf_counter() - t0, 2)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# e2e through the drop-in classes (freud_b200.locality / density / order): the call a freud user makes
+def api_step(name, w):
+    import freud_b200 as fr
+
+    box, pts = w["box"], w["pts"]
+    if name in ("nl", "nl_image"):
+        cls = fr.locality.LinkCell if name == "nl" else fr.locality.AABBQuery
+
+        def step():
+            nq = cls(box, pts, w["r_max"]) if name == "nl" else cls(box, pts)
+            nl = nq.query(pts, dict(r_max=w["r_max"], exclude_ii=True)).toNeighborList()
+            # touch every array the user can ask for (each is a D2H on first access)
+            return (nl.query_point_indices[-1], nl.point_indices[-1], nl.distances[-1], nl.weights[-1],
+                    nl.vectors[-1, 2], nl.segments[-1], nl.neighbor_counts[-1])
+        return step
+    if name in ("rdf", "rdf_wrap"):
+        rdf = fr.density.RDF(w["bins"], w["r_max"])
+
+        def step():
+            system = (box, pts) if name == "rdf" else fr.locality.LinkCell(box, pts, w["r_max"])
+            return rdf.compute(system).bin_counts[-1]
+        return step
+    if name == "q6":
+        st = fr.order.Steinhardt(6)
+
+        def step():
+            return st.compute((box, pts), neighbors=dict(num_neighbors=12)).particle_order[-1]
+        return step
+    return None
+
+
+def time_api(step, steps):
+    if step is None:
+        return None
+    for _ in range(2):
+        step()
+    marks = [time.perf_counter()]
+    for _ in range(steps):
+        step()
+        marks.append(time.perf_counter())
+    d = np.diff(marks) * 1e3
+    return {"ms_per_step": float(d.mean()), "ms_per_step_min_median_max": [round(float(x), 3) for x in (d.min(), np.median(d), d.max())]}
+
+
+# ---------------------------------------------------------------------------------------------------------
+WORKLOADS = ["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy",
+             "pmftxyz", "pmftxyt", "pmftr12", "bond_order"]
+N_DEFAULT = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
+             "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000,
+             "pmftxy": 1_000_000, "pmftxyz": 1_000_000, "pmftxyt": 1_000_000, "pmftr12": 1_000_000,
+             "bond_order": 1_000_188}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nl", choices=["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy", "pmftxyz", "pmftxyt", "pmftr12", "bond_order"])
+    ap.add_argument("--workload", default=None, choices=WORKLOADS,
+                    help="one workload only; default: the three legs of BASELINE.json's metric (nl, rdf, q6) on one GPU, "
+                         "the sharded 4 M-point RDF (+ 2-D trajectory, + NeighborList replicas) on several")
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_default = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
-                 "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000, "pmftxy": 1_000_000, "pmftxyz": 1_000_000, "pmftxyt": 1_000_000,
-                 "pmftr12": 1_000_000, "bond_order": 1_000_188}[args.workload]
-    n = args.n or n_default
+    if args.workload is not None:
+        legs = [args.workload]
+    elif world == 1:
+        legs = ["nl", "rdf", "q6"]        # BASELINE.json metric: pair evals/s + RDF frames/s @1M r_max=5 + Q6 particles/s
+    else:
+        legs = ["rdf4m", "traj2d", "nl"]  # configs[3] (strong scaling, the headline), configs[4], NeighborList replicas
 
     if args.impl == "reference":
-        return run_reference_arm(args, rank, world, n)
+        return run_reference_arm(args, rank, world, legs)
 
     import torch
     import torch.distributed as dist
@@ -696,43 +828,64 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     ctx = _capi.Context(local_rank)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-
-    comm = None
-    if world > 1 and args.workload in ("rdf4m", "traj2d"):
+    env = dict(torch=torch, dist=dist, ctx=ctx, rank=rank, world=world, local_rank=local_rank,
+               stream=torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank)),
+               flush=torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda"), comm=None)
+    if world > 1:
         from freud_b200 import parallel
 
-        comm = parallel.make_communicator(ctx)  # NCCL on the library's stream; id travels over torch.distributed
+        env["comm"] = parallel.make_communicator(ctx)  # NCCL on the library's stream; id travels over torch.distributed
 
-    if args.workload in ("nl", "nl_image"):
-        w = workload_nl(ctx, rank, n, WRAP if args.workload == "nl" else IMAGE)
+    lines = []
+    for k, name in enumerate(legs):
+        steps = args.steps if k == 0 or world == 1 else min(args.steps, 5)  # extras of a multi-GPU run stay short
+        lines.append(run_leg(name, args, env, steps, args.n or N_DEFAULT[name]))
+        ctx.trim()
+    if rank == 0:
+        line = lines[0]
+        if len(lines) > 1:
+            line["legs"] = {name: ln for name, ln in zip(legs[1:], lines[1:])}
+            for name, ln in zip(legs[1:], lines[1:]):
+                line[ln["metric"] if ln["metric"] != line["metric"] else f"{name}_{ln['metric']}"] = ln["value"]
+            line["parity_all_legs"] = all((ln.get("parity") or {}).get("bitwise_equal") is not False
+                                          and (ln.get("parity") or {}).get("ql_within_tolerance") is not False
+                                          for ln in lines)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_leg(name, args, env, steps, n):
+    torch, dist, ctx = env["torch"], env["dist"], env["ctx"]
+    rank, world, local_rank, stream, flush, comm = (env[k] for k in ("rank", "world", "local_rank", "stream", "flush", "comm"))
+    if name in ("nl", "nl_image"):
+        w = workload_nl(ctx, rank, n, WRAP if name == "nl" else IMAGE)
         scaling = "weak"
-    elif args.workload in ("rdf", "rdf_wrap"):
-        w = workload_rdf(ctx, rank, n, flavour=IMAGE if args.workload == "rdf" else WRAP)
+    elif name in ("rdf", "rdf_wrap"):
+        w = workload_rdf(ctx, rank, n, flavour=IMAGE if name == "rdf" else WRAP)
         scaling = "weak"
-    elif args.workload == "q6":
+    elif name == "q6":
         w = workload_q6(ctx, rank, n)
         scaling = "weak"
-    elif args.workload == "local_density":
+    elif name == "local_density":
         w = workload_local_density(ctx, rank, n)
         scaling = "weak"
-    elif args.workload == "correlation":
+    elif name == "correlation":
         w = workload_correlation(ctx, rank, n)
         scaling = "weak"
-    elif args.workload == "pmftxy":
+    elif name == "pmftxy":
         w = workload_pmftxy(ctx, rank, n)
         scaling = "weak"
-    elif args.workload in HIST_CLIENTS:
-        w = workload_hist_client(ctx, rank, n, args.workload)
+    elif name in HIST_CLIENTS:
+        w = workload_hist_client(ctx, rank, n, name)
         scaling = "weak"
-    elif args.workload == "rdf4m":
+    elif name == "rdf4m":
         w = workload_rdf4m(ctx, rank, world, n, comm)
         scaling = "strong"
     else:
         w = workload_traj2d(ctx, rank, world, n, comm)
         scaling = "weak"
-
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def barrier():
         if world > 1:
@@ -750,7 +903,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         barrier()
         t_wall0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             with torch.cuda.stream(stream):
                 flush.zero_()  # L2 flush between steps (outside the event pair)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -766,24 +919,24 @@ def main():
     ctx.profile(False)
     # dominant kernel over the timed region
     per_kernel = {}
-    names = ("cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
-             "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn",
-             "rdf_distances", "steinhardt", "local_density_rows", "local_density", "correlation_rows", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
-    raw = {name: ctx.kernel_time(name) for name in names}  # prefix match: subtract the longer names
-    for name in names:
-        ms, cnt = raw[name]
+    names = ("cell_prep", "cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
+             "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn_ylm", "knn",
+             "rdf_distances", "rdf_wait", "steinhardt", "local_density_rows", "local_density", "correlation_rows", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
+    raw = {nm: ctx.kernel_time(nm) for nm in names}  # prefix match: subtract the longer names
+    for nm in names:
+        ms, cnt = raw[nm]
         for other in names:
-            if other != name and other.startswith(name):
+            if other != nm and other.startswith(nm):
                 ms, cnt = ms - raw[other][0], cnt - raw[other][1]
         if cnt:
-            per_kernel[name] = (ms, cnt)
+            per_kernel[nm] = (ms, cnt)
     ctx.kernel_time(reset=True)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    ms_per_step = dev_ms_max / args.steps
-    value = w["units"] * world * args.steps / (dev_ms_max / 1e3)
+    ms_per_step = dev_ms_max / steps
+    value = w["units"] * world * steps / (dev_ms_max / 1e3)
 
     # ---- end-to-end leg ("e2e"): host buffers in, host result out, through the C ABI --------------------
     for _ in range(2):
@@ -791,7 +944,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e2e_marks = [t0]
-    for _ in range(args.steps):
+    for _ in range(steps):
         w["step_e2e"]()  # returns once the step's result is on the host
         e2e_marks.append(time.perf_counter())
     torch.cuda.synchronize()
@@ -801,46 +954,85 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e_value = w["units"] * world * args.steps / e2e_s
+    e2e_value = w["units"] * world * steps / e2e_s
+
+    # ---- the same through the drop-in classes (single GPU legs; pageable numpy in, numpy views out) ------
+    api = None
+    if world == 1:
+        api = time_api(api_step(name, w), max(3, min(steps, 10)))
+        if api is not None:
+            api["value"] = w["units"] / (api["ms_per_step"] * 1e-3)
+            api["unit"] = w["unit"]
+            api["vs_capi_e2e"] = round((e2e_s * 1e3 / steps) / api["ms_per_step"], 3)
+            api["call"] = {"nl": "LinkCell(box, pts, 3).query(pts, dict(r_max=3, exclude_ii=True)).toNeighborList() + every array",
+                           "nl_image": "AABBQuery(box, pts).query(...).toNeighborList() + every array",
+                           "rdf": "RDF(100, 5).compute((box, pts)).bin_counts", "rdf_wrap": "RDF(100, 5).compute(LinkCell(box, pts, 5)).bin_counts",
+                           "q6": "Steinhardt(6).compute((box, pts), neighbors=dict(num_neighbors=12)).particle_order"}.get(name)
+
+    # ---- parity at the benchmark's own size (outside every timed region) ---------------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            if name in ("nl", "nl_image") and rank == 0:
+                parity = parity_nl(w, WRAP if name == "nl" else IMAGE)
+            elif name in ("rdf", "rdf_wrap") and rank == 0:
+                w["rdf"].reset()
+                w["rdf"].accumulate(w["dp"], None, w["flavour"], w["r_max"], 0.0, True)
+                parity = parity_rdf_counts(w["rdf"].read(), w, w["bins"])
+            elif name == "q6" and rank == 0:
+                parity = parity_q6(w)
+            elif name == "rdf4m":
+                w["step_dev"]()  # every rank takes part in the reduction
+                got = w["read_global"]()
+                if rank == 0:
+                    parity = parity_rdf_counts(got, w, w["bins"])
+            elif name == "traj2d":
+                got = w["rank_counts"]()  # this rank's own frames, before any reduction
+                mine = parity_rdf_counts(got, w, w["bins"], frames=w["frames"])
+                flag = torch.tensor([1.0 if mine["bitwise_equal"] else 0.0], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                mine["bitwise_equal"] = bool(flag.item() == 1.0)
+                mine["scope"] = f"every rank checks the histogram of its own {len(w['frames'])} frames before the reduction; min over ranks"
+                parity = mine
+        except Exception as exc:  # a failed check is reported, never hidden
+            parity = {"bitwise_equal": False, "error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src = peaks()
     roofline = None
     if per_kernel:
-        name = max(per_kernel, key=lambda k: per_kernel[k][0])
-        ms, cnt = per_kernel[name]
+        kname = max(per_kernel, key=lambda k: per_kernel[k][0])
+        ms, cnt = per_kernel[kname]
         avg_ms = ms / cnt
-        algo = w["algo"].get(name)
+        algo = w["algo"].get(kname)
         if algo:
             # w["algo"] holds bytes per step; a kernel launched in several chunks per step moves its share per launch
-            algo = algo * args.steps / cnt if cnt > args.steps and w.get("algo_per_step") else algo
+            algo = algo * steps / cnt if cnt > steps and w.get("algo_per_step") else algo
             achieved = algo / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(name),
-                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                          "capture of this workload (profiles/ncu_r1_v6_summary.md, ncu_r1_v8_summary.md, ncu_r1_v9_summary.md)"
-                        if w.get("traffic", {}).get(name) else None,
+            roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(kname),
+                        "traffic_source": w.get("traffic_source") if w.get("traffic", {}).get(kname) else None,
                         "avg_launch_ms": round(avg_ms, 4),
                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
                         "share_of_step": round(ms / dev_ms, 3),
-                        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in per_kernel.items()}}
+                        "kernel_ms_per_step": {k: round(v[0] / steps, 4) for k, v in per_kernel.items()}}
     pipe = w["algo"]["pipeline"] / (ms_per_step * 1e-3) / 1e9
     line = {
-        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(w["config"], l2="256 MB memset between timed steps (outside the event pairs)",
                        timing="CUDA events on the library's stream, max over ranks"),
         "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(w["h2d"]),
-                "d2h_bytes_per_step": int(w["d2h"]), "ms_per_step": e2e_s * 1e3 / args.steps,
+                "d2h_bytes_per_step": int(w["d2h"]), "ms_per_step": e2e_s * 1e3 / steps,
                 "ms_per_step_min_median_max": [round(float(x), 3) for x in (e2e_steps_ms.min(), np.median(e2e_steps_ms),
                                                                             e2e_steps_ms.max())],
-                "host_buffers": "pinned"},
+                "host_buffers": "pinned", "through": "C ABI (ctypes)"},
+        "e2e_api": api,
+        "parity": parity,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roofline,
@@ -850,45 +1042,42 @@ def main():
         "wall_s": t_wall,
     }
     if "bonds" in w["secondary"]:
-        line["bonds_per_sec"] = w["secondary"]["bonds"] * world * args.steps / (dev_ms_max / 1e3)
+        line["bonds_per_sec"] = w["secondary"]["bonds"] * world * steps / (dev_ms_max / 1e3)
     if "pair_evals_per_sec_factor" in w["secondary"]:
-        line["pair_evals_per_sec"] = w["secondary"]["pair_evals_per_sec_factor"] * world * args.steps / (dev_ms_max / 1e3)
+        line["pair_evals_per_sec"] = w["secondary"]["pair_evals_per_sec_factor"] * world * steps / (dev_ms_max / 1e3)
     if world == 1 and not args.no_cpu_baseline:
         try:
-            if args.workload in ("nl", "nl_image"):
+            if name in ("nl", "nl_image"):
                 line["cpu_baseline"] = cpu_reference_nl(w["box"], w["pts"], w["r_max"])
-            elif args.workload in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
+            elif name in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
                 line["cpu_baseline"] = cpu_reference_rdf(w["box"], w["pts"], w["rdf"].bins, w["r_max"])
-            elif args.workload == "local_density":
+            elif name == "local_density":
                 line["cpu_baseline"] = cpu_reference_local_density(w["box"], w["pts"], w["r_max"], w["diameter"])
-            elif args.workload == "correlation":
+            elif name == "correlation":
                 line["cpu_baseline"] = cpu_reference_correlation(w["box"], w["pts"], w["values"], w["bins"], w["r_max"])
-            elif args.workload == "pmftxy":
+            elif name == "pmftxy":
                 line["cpu_baseline"] = cpu_reference_pmftxy(w["box"], w["pts"], w["angles"], w["x_max"], w["y_max"],
                                                             w["bins"])
-            elif args.workload in HIST_CLIENTS:
-                line["cpu_baseline"] = cpu_reference_hist_client(args.workload, w["box"], w["pts"], w["orient"], w["spec"])
+            elif name in HIST_CLIENTS:
+                line["cpu_baseline"] = cpu_reference_hist_client(name, w["box"], w["pts"], w["orient"], w["spec"])
             else:
                 line["cpu_baseline"] = cpu_reference_q6(w["box"], w["pts"])
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return line
 
 
 def workload_rdf4m(ctx, rank, world, n, comm):
-    """BASELINE.json configs[3]: one 4 M-point triclinic frame, query points sharded, one u32 allreduce."""
-    from freud_b200 import _capi, data
+    """BASELINE.json configs[3]: one 4 M-point triclinic frame, query points (home tiles) sharded over the ranks, the
+    histograms summed once per frame.  Strong scaling: value = frames/s of the ONE frame."""
+    from freud_b200 import _capi, data, parallel
 
     bins, r_max = 500, 5.0
     L = (n / RHO) ** (1.0 / 3.0)
     box, pts = data.make_random_system(L, n, seed=0, tilt=(0.3, 0.2, 0.1))
-    from freud_b200 import parallel
-
     dp = _capi.DevicePoints(ctx, box, pts)
     srdf = parallel.ShardedRDF(ctx, bins, r_max, comm=comm, rank=rank, world=world)
+    srdf.keep_shard = True
     rdf = srdf.rdf
     pin_pts, keep0 = pinned_empty((n, 3), np.float32)
     pin_pts[:] = pts
@@ -902,18 +1091,17 @@ def workload_rdf4m(ctx, rank, world, n, comm):
     def step_dev():
         srdf.reset()
         dp.build_cells(r_max)
-        srdf.accumulate_frame(dp, IMAGE, r_max, 0.0, True, query_shard=shard_arg)
-        if comm is not None:
-            rdf.allreduce(comm)
+        # search + exchange: every rank ends the step holding the frame's summed counts on the device
+        srdf.accumulate_frame(dp, IMAGE, r_max, 0.0, True, query_shard=shard_arg, reduce=True)
 
     def step_e2e():
         srdf.reset()
-        d = _capi.DevicePoints(ctx, box, pin_pts)
-        srdf.accumulate_frame(d, IMAGE, r_max, 0.0, True, query_shard=shard_arg)
-        return srdf.bin_counts()  # one ncclAllReduce(u32[500]) + D2H
+        d = parallel.replicated_points(ctx, box, pin_pts, comm, rank, world)  # each rank uploads 1/world, NVLink does the rest
+        srdf.accumulate_frame(d, IMAGE, r_max, 0.0, True, query_shard=shard_arg, reduce=True)
+        return srdf.bin_counts()  # D2H of the sum
 
     step_dev()
-    n_bonds = int(rdf.read().astype(np.uint64).sum())  # after the allreduce: the whole frame
+    n_bonds = int(srdf.bin_counts().astype(np.uint64).sum())  # the whole frame
     n_cells = int(np.prod(dp.build_cells(r_max)))
     nq = n // world
     algo = {"search_rdf": 16 * (n + nq) + 4 * n_cells + 4 * bins, "pipeline": 16 * (n + nq) + 4 * bins,
@@ -922,10 +1110,10 @@ def workload_rdf4m(ctx, rank, world, n, comm):
                 metric="rdf_frames_per_sec",
                 config={"workload": f"RDF bins=500 r_max=5 N={n} triclinic (xy=.3,xz=.2,yz=.1) L={L:.4f} query points "
                                     f"(home tiles) sharded over {world} GPU(s), points replicated, cell list built "
-                                    f"per slab, ncclAllReduce(u32[500])",
+                                    f"per slab, histograms summed over the ranks every frame ({srdf.reduce_kind()})",
                         "bonds_per_step": n_bonds},
-                h2d=12 * n, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max,
-                rdf=rdf, dp=dp, secondary={})
+                h2d=12 * n // world, d2h=4 * bins, algo=algo, keep=[keep0], box=box, pts=pts, r_max=r_max,
+                rdf=rdf, dp=dp, bins=bins, flavour=IMAGE, read_global=srdf.bin_counts, secondary={})
 
 
 def workload_traj2d(ctx, rank, world, n, comm, frames_per_rank=8):
@@ -962,6 +1150,12 @@ def workload_traj2d(ctx, rank, world, n, comm, frames_per_rank=8):
             rdf.allreduce(comm)
         return rdf.read()
 
+    def rank_counts():
+        rdf.reset()
+        for d in dps:
+            rdf.accumulate(d, None, IMAGE, r_max, 0.0, True)
+        return rdf.read()  # no reduction since the reset: this rank's own frames
+
     algo = {"search_rdf": 16 * 2 * n + 4 * bins, "pipeline": frames_per_rank * (16 * 2 * n + 4 * bins),
             "cell_assign": 20 * n, "cell_scatter": 36 * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=frames_per_rank, unit="frames/s",
@@ -969,34 +1163,32 @@ def workload_traj2d(ctx, rank, world, n, comm, frames_per_rank=8):
                 config={"workload": f"trajectory RDF bins=100 r_max=5 reset=False, {frames_per_rank} frames/GPU of N={n} "
                                     f"2-D square L={L:.4f}, frames sharded over {world} GPU(s), one allreduce at the end"},
                 h2d=12 * n * frames_per_rank, d2h=4 * bins, algo=algo, keep=keep, box=box, pts=frames[0][1],
-                r_max=r_max, rdf=rdf, dp=dps[0], secondary={})
+                r_max=r_max, rdf=rdf, dp=dps[0], bins=bins, flavour=IMAGE, frames=frames, rank_counts=rank_counts,
+                secondary={})
 
 
-def run_reference_arm(args, rank, world, n):
-    """--impl reference: the reference's own CPU implementation on this box's host cores (rank 0 only)."""
-    if rank != 0:
-        return
+def reference_leg(name, n, steps, budget, threads):
+    """One leg of --impl reference: the reference's own CPU implementation (oracle/_ref, every host thread) on a bounded
+    sample of the leg's workload; same metric / unit / config as the b200 arm's leg."""
     from freud_b200 import data
 
-    threads = os.cpu_count()
-    steps = max(1, min(args.steps, 3))
-    budget = 8.0
-    if args.workload in ("nl", "nl_image"):
+    if name in ("nl", "nl_image"):
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)
         runs = [cpu_reference_nl(box, pts, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "neighbour_pair_evals_per_sec", "pair_evals/s"
         config = {"workload": f"LinkCell NeighborList r_max=3 exclude_ii N={n} cubic L={L:.4f} rho=0.08 flavour=wrap"}
-    elif args.workload in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
-        is2d = args.workload == "traj2d"
+    elif name in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
+        is2d = name == "traj2d"
         L = (n / (0.5 if is2d else RHO)) ** (0.5 if is2d else 1.0 / 3.0)
-        tilt = (0.3, 0.2, 0.1) if args.workload == "rdf4m" else None
+        tilt = (0.3, 0.2, 0.1) if name == "rdf4m" else None
         box, pts = data.make_random_system(L, n, is2D=is2d, seed=0, tilt=tilt)
-        bins = 500 if args.workload == "rdf4m" else 100
+        bins = 500 if name == "rdf4m" else 100
         runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "rdf_frames_per_sec", "frames/s"
-        config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"}
-    elif args.workload == "pmftxy":
+        config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"
+                              + (" triclinic (xy=.3,xz=.2,yz=.1)" if tilt else "") + (" 2-D" if is2d else "")}
+    elif name == "pmftxy":
         L = (n / 0.5) ** 0.5
         box, pts = data.make_random_system(L, n, is2D=True, seed=0)
         rs = np.random.RandomState(29)
@@ -1005,13 +1197,13 @@ def run_reference_arm(args, rank, world, n):
                 for _ in range(steps)]
         metric, unit = "pmftxy_particles_per_sec", "particles/s"
         config = {"workload": f"PMFTXY x_max=4 y_max=3 bins=100x100 N={n} 2-D square L={L:.4f} areal density 0.5"}
-    elif args.workload in HIST_CLIENTS:
-        box, pts, orient, spec = hist_client_inputs(args.workload, n, 0)
-        runs = [cpu_reference_hist_client(args.workload, box, pts, orient, spec, budget_s=budget, threads=threads)
+    elif name in HIST_CLIENTS:
+        box, pts, orient, spec = hist_client_inputs(name, n, 0)
+        runs = [cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=budget, threads=threads)
                 for _ in range(steps)]
-        metric, unit = f"{args.workload}_particles_per_sec", "particles/s"
+        metric, unit = f"{name}_particles_per_sec", "particles/s"
         config = {"workload": spec["label"]}
-    elif args.workload == "correlation":
+    elif name == "correlation":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)
         rs = np.random.RandomState(17)
@@ -1019,7 +1211,7 @@ def run_reference_arm(args, rank, world, n):
         runs = [cpu_reference_correlation(box, pts, values, 100, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
         metric, unit = "correlation_function_particles_per_sec", "particles/s"
         config = {"workload": f"CorrelationFunction bins=100 r_max=3 complex values N={n} cubic L={L:.4f} rho=0.08"}
-    elif args.workload == "local_density":
+    elif name == "local_density":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)
         runs = [cpu_reference_local_density(box, pts, 2.5, 1.0, budget_s=budget, threads=threads) for _ in range(steps)]
@@ -1034,11 +1226,29 @@ def run_reference_arm(args, rank, world, n):
     vals = [r["value"] for r in runs if r.get("value")]
     value = float(np.median(vals)) if vals else None
     base = dict(runs[-1], value=value)
-    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps,
-            "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    return {"impl": "reference", "metric": metric, "value": value, "unit": unit, "steps": steps,
+            "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "strong" if name == "rdf4m" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+
+
+def run_reference_arm(args, rank, world, legs):
+    """--impl reference: the reference's own CPU implementation on this box's host cores (rank 0 only), for the same
+    legs the b200 arm runs at this world size (the first one is the line's headline)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    steps = max(1, min(args.steps, 3))
+    lines = []
+    for k, name in enumerate(legs):
+        lines.append(reference_leg(name, args.n or N_DEFAULT[name], steps if k == 0 else 1, 8.0 if k == 0 else 6.0, threads))
+    line = dict(lines[0], n_gpus=world)
+    if len(lines) > 1:
+        line["legs"] = {name: ln for name, ln in zip(legs[1:], lines[1:])}
+        for name, ln in zip(legs[1:], lines[1:]):
+            line[ln["metric"] if ln["metric"] != line["metric"] else f"{name}_{ln['metric']}"] = ln["value"]
     print(json.dumps(line))
 
 

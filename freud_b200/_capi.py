@@ -41,6 +41,7 @@ SIGNATURES = {
     "fgpu_ctx_kernel_time": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
     "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
+    "fgpu_points_create_replicated": (C.c_int, [_vp, _vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
     "fgpu_points_destroy": (None, [_vp]),
     "fgpu_points_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "fgpu_shard_plan": (C.c_int, [_up, C.c_uint32, C.c_int, C.c_int, _up]),
@@ -67,6 +68,9 @@ SIGNATURES = {
     "fgpu_rdf_accumulate_nlist": (C.c_int, [_vp, _vp]),
     "fgpu_rdf_read": (C.c_int, [_vp, _up]),
     "fgpu_rdf_allreduce": (C.c_int, [_vp, _vp]),
+    "fgpu_rdf_attach_comm": (C.c_int, [_vp, _vp]),
+    "fgpu_rdf_reduce_transport": (C.c_int, [_vp]),
+    "fgpu_rdf_accumulate_reduce": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int]),
     "fgpu_pmftxy_create": (C.c_int, [_vp, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _vpp]),
     "fgpu_pmftxy_destroy": (None, [_vp]),
     "fgpu_pmftxy_reset": (C.c_int, [_vp]),
@@ -99,6 +103,14 @@ SIGNATURES = {
                                            C.c_float, _fp, _fp]),
     "fgpu_steinhardt_compute": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _fp, _fp,
                                          _fp]),
+    "fgpu_steinhardt_compute_keep": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _vpp, _fp,
+                                              _fp]),
+    "fgpu_buffer_bytes": (C.c_uint64, [_vp]),
+    "fgpu_buffer_read": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
+    "fgpu_buffer_destroy": (None, [_vp]),
+    "fgpu_host_alloc": (C.c_int, [C.c_uint64, _vpp]),
+    "fgpu_host_free": (None, [_vp]),
+    "fgpu_host_trim": (C.c_int, []),
     "fgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "fgpu_comm_create": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, _vpp]),
     "fgpu_comm_destroy": (None, [_vp]),
@@ -298,13 +310,19 @@ class DevicePoints(_DeviceObject):
 
     _destroy = "fgpu_points_destroy"
 
-    def __init__(self, ctx, box, points):
+    def __init__(self, ctx, box, points, comm=None):
+        """comm: every rank holds the same host array; each uploads its block and NVLink replicates the rest
+        (``fgpu_points_create_replicated``, collective)."""
         self._adopt(ctx)
         self.box6, self.is2d = box6_of(box)
         pts = f32(points, 3)
         self.n = len(pts)
         self._h = _vp()
-        check(lib().fgpu_points_create(ctx._h, ptr(self.box6), int(self.is2d), ptr(pts), self.n, C.byref(self._h)))
+        if comm is None:
+            check(lib().fgpu_points_create(ctx._h, ptr(self.box6), int(self.is2d), ptr(pts), self.n, C.byref(self._h)))
+        else:
+            check(lib().fgpu_points_create_replicated(ctx._h, comm._h, ptr(self.box6), int(self.is2d), ptr(pts), self.n,
+                                                      C.byref(self._h)))
 
     def build_cells(self, r_search):
         dims = np.zeros(3, np.uint32)
@@ -415,6 +433,25 @@ class DeviceRDF(_DeviceObject):
 
     def allreduce(self, comm):
         check(lib().fgpu_rdf_allreduce(self._h, comm._h))
+
+    def attach_comm(self, comm):
+        """Collective: give this RDF a peer-memory mailbox on every rank of ``comm`` (NVLink red.add instead of an NCCL
+        launch for the sum).  True if attached, False if the ranks cannot map each other's memory (NCCL stays)."""
+        rc = lib().fgpu_rdf_attach_comm(self._h, comm._h)
+        if rc == 1:
+            return False
+        check(rc)
+        self._comm_ref = comm  # the communicator must outlive the mailbox
+        return True
+
+    @property
+    def reduce_transport(self):
+        return {1: "nccl", 2: "peer"}[lib().fgpu_rdf_reduce_transport(self._h)]
+
+    def accumulate_reduce(self, points, comm, flavour, r_max, r_min=0.0, exclude_ii=False):
+        """Self-query accumulation of (sharded) points and the sum over the ranks in one call."""
+        check(lib().fgpu_rdf_accumulate_reduce(self._h, points._h, comm._h, int(flavour), float(r_max), float(r_min),
+                                               int(bool(exclude_ii))))
 
 
 class DevicePMFTXY(_DeviceObject):

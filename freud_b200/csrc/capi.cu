@@ -10,7 +10,10 @@
 #include <complex>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <mutex>
 #include <thread>
 
@@ -328,6 +331,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     bool const self = q_host == nullptr && q_dev == nullptr;
     require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
     auto nl = new_nlist(ctx, n_query, pts->n);
+    nl->q_index_offset = self ? 0 : q_index_offset;
     if (n_query == 0)
     {
         alloc_bonds(nl.get(), 0);
@@ -529,8 +533,12 @@ bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int 
     return false;
 }
 
-void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query,
-                         uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii)
+// fuse_push: the caller ends the epoch right after this frame (fgpu_rdf_accumulate_reduce) and the RDF has a peer
+// mailbox -- where the frame is one launch of the warp-cooperative kernel with no fallback behind it (the sharded
+// path), that launch's last block sends the finished histogram to every rank.  Returns whether it did.
+bool rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, const float* q_dev, uint32_t n_query,
+                         uint32_t q_index_offset, int flavour, float q_r_max, float q_r_min, int exclude_ii,
+                         bool fuse_push = false)
 {
     require(rdf != nullptr && pts != nullptr, FGPU_EINVALID, "null argument");
     require(rdf->ctx == pts->ctx, FGPU_EINVALID, "rdf and points belong to different contexts");
@@ -541,8 +549,9 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
     if (n_query == 0)
     {
-        return;
+        return false;
     }
+    rdf->reduced_valid = false; // new counts: an earlier sum over the ranks no longer describes this histogram
     bool const sharded = pts->n_shards > 1;
     require(!sharded || self, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
     build_grid(pts, q_r_max);
@@ -571,12 +580,21 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
         // and fgpu_rdf_read reports it, so the frame needs no host round trip
         s2.fail = reinterpret_cast<int*>(rdf->hist.ptr + rdf->axis.bins);
         FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 5, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        bool pushed = false;
         if (s2.ticket_end > s2.ticket_begin)
         {
+            if (fuse_push && rdf->peer != nullptr)
+            {
+                s2.push = 1;
+                s2.done_counter = reinterpret_cast<unsigned int*>(ctx->d_scalars + 6) + 1; // zeroed just above
+                s2.peer = rdf->peer->box;
+                s2.peer.parity = (uint32_t) (rdf->peer->epoch & 1U);
+                pushed = true;
+            }
             launch_search2(ctx, flavour, S2_RDF, s2);
-            launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);
+            launch_count_evals(ctx, s2, n_query, nullptr, pts->n); // self query: no per-point cell table needed
         }
-        return;
+        return pushed;
     }
     SearchArgs a = base_search_args(pts, qv, n_query, q_index_offset, q_r_max, q_r_min, exclude_ii);
     a.axis = rdf->axis;
@@ -598,6 +616,7 @@ void rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     {
         sync(ctx); // the caller may reuse its host buffer / the staging buffer is context scratch
     }
+    return false;
 }
 
 // ---- NCCL, loaded lazily -----------------------------------------------------------------------------
@@ -609,6 +628,10 @@ struct NcclApi
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
         = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string why;
 };
@@ -637,7 +660,12 @@ NcclApi& nccl()
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
         api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString)
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+        api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.handle, "ncclBroadcast"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.handle, "ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.handle, "ncclGroupEnd"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString
+            || !api.AllGather || !api.Broadcast || !api.GroupStart || !api.GroupEnd)
         {
             api.why = "libnccl.so.2 lacks a required symbol";
             api.handle = nullptr;
@@ -912,7 +940,7 @@ int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint
 
 // ---- points ----------------------------------------------------------------------------------------
 static void points_create_impl(fgpu_ctx* ctx, const float* box6, int is2d, const float* host, const float* dev,
-                               uint32_t n, fgpu_points** out)
+                               uint32_t n, fgpu_points** out, fgpu_comm* comm = nullptr)
 {
     require(ctx != nullptr && box6 != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
     // NeighborQuery ctor, NeighborQuery.h:97-100
@@ -927,7 +955,31 @@ static void points_create_impl(fgpu_ctx* ctx, const float* box6, int is2d, const
     plane_distances(p->box, p->plane_dist);
     p->n = n;
     p->xyz.reserve((size_t) n * 3);
-    if (host != nullptr)
+    if (host != nullptr && comm != nullptr && comm->size > 1)
+    {
+        // Every rank holds the same host array: rank r sends only rows [r n / W, (r + 1) n / W) over its own PCIe
+        // link and the ranks hand each other their blocks over NVLink (one grouped ncclBroadcast per block), instead
+        // of W copies of the whole frame crossing PCIe (the e2e of configs[3] was upload-bound).
+        require(comm->ctx == ctx, FGPU_EINVALID, "comm belongs to a different context");
+        NcclApi& api = nccl_or_throw();
+        uint64_t const W = (uint64_t) comm->size;
+        auto lo_of = [&](uint64_t r) { return (uint64_t) n * r / W; };
+        uint64_t const lo = lo_of((uint64_t) comm->rank), hi = lo_of((uint64_t) comm->rank + 1);
+        h2d(ctx, p->xyz.ptr + 3 * lo, host + 3 * lo, (size_t) (hi - lo) * 3 * sizeof(float));
+        nccl_check(api.GroupStart(), "ncclGroupStart");
+        for (uint64_t r = 0; r < W; ++r)
+        {
+            uint64_t const a = lo_of(r), b = lo_of(r + 1);
+            if (b > a)
+            {
+                nccl_check(api.Broadcast(p->xyz.ptr + 3 * a, p->xyz.ptr + 3 * a, (size_t) (b - a) * 3, ncclFloat32, (int) r,
+                                         static_cast<ncclComm_t>(comm->nccl_comm), ctx->stream),
+                           "ncclBroadcast(points block)");
+            }
+        }
+        nccl_check(api.GroupEnd(), "ncclGroupEnd");
+    }
+    else if (host != nullptr)
     {
         h2d(ctx, p->xyz.ptr, host, (size_t) n * 3 * sizeof(float));
     }
@@ -964,6 +1016,15 @@ int fgpu_points_create_dev(fgpu_ctx* ctx, const float* box6, int is2d, const flo
                            fgpu_points** out)
 {
     return guarded([&] { points_create_impl(ctx, box6, is2d, nullptr, points_dev, n, out); });
+}
+
+int fgpu_points_create_replicated(fgpu_ctx* ctx, fgpu_comm* comm, const float* box6, int is2d, const float* points_host,
+                                  uint32_t n, fgpu_points** out)
+{
+    return guarded([&] {
+        require(comm != nullptr, FGPU_EINVALID, "null argument");
+        points_create_impl(ctx, box6, is2d, points_host, nullptr, n, out, comm);
+    });
 }
 
 void fgpu_points_destroy(fgpu_points* pts)
@@ -1096,6 +1157,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
         require(!self || n_query == pts->n, FGPU_EINVALID, "self query requires n_query == n_points");
         require(pts->n_shards == 1, FGPU_ERUNTIME, "sharded points serve self-query RDF accumulation only");
         auto nl = new_nlist(ctx, n_query, pts->n);
+        nl->q_index_offset = self ? 0 : q_index_offset;
         uint32_t const k = std::min<uint32_t>(num_neighbors, pts->n);
         if (n_query == 0 || k == 0)
         {
@@ -1520,6 +1582,19 @@ void fgpu_rdf_destroy(fgpu_rdf* rdf)
     if (rdf != nullptr)
     {
         bind_quiet(rdf->ctx);
+        if (rdf->peer != nullptr)
+        {
+            cudaStreamSynchronize(rdf->ctx->stream);
+            for (void* p : rdf->peer->opened)
+            {
+                if (p != nullptr)
+                {
+                    cudaIpcCloseMemHandle(p);
+                }
+            }
+            cudaFree(rdf->peer->mailbox);
+            delete rdf->peer;
+        }
         delete rdf;
     }
 }
@@ -1529,6 +1604,7 @@ int fgpu_rdf_reset(fgpu_rdf* rdf)
     return guarded([&] {
         require(rdf != nullptr, FGPU_EINVALID, "null argument");
         bind_device(rdf->ctx);
+        rdf->reduced_valid = false;
         FGPU_CUDA_CHECK(
             cudaMemsetAsync(rdf->hist.ptr, 0, ((size_t) rdf->axis.bins + 1) * sizeof(uint32_t), rdf->ctx->stream));
     });
@@ -1558,6 +1634,7 @@ int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl)
         require(rdf != nullptr && nl != nullptr, FGPU_EINVALID, "null argument");
         require(rdf->ctx == nl->ctx, FGPU_EINVALID, "rdf and nlist belong to different contexts");
         bind_device(rdf->ctx);
+        rdf->reduced_valid = false;
         launch_rdf_from_distances(rdf->ctx, nl->distances.ptr, nl->n_bonds, rdf->axis, rdf->hist.ptr);
     });
 }
@@ -1568,9 +1645,19 @@ int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host)
         require(rdf != nullptr && counts_host != nullptr, FGPU_EINVALID, "null argument");
         bind_device(rdf->ctx);
         fgpu_ctx* ctx = rdf->ctx;
-        d2h(ctx, counts_host, rdf->hist.ptr, (size_t) rdf->axis.bins * sizeof(uint32_t));
+        // after fgpu_rdf_allreduce: the sum over the ranks; the rank's own counts stay in hist, so accumulating
+        // further frames and reducing again never counts a frame twice
+        d2h(ctx, counts_host, rdf->reduced_valid ? rdf->reduced.ptr : rdf->hist.ptr,
+            (size_t) rdf->axis.bins * sizeof(uint32_t));
         d2h(ctx, ctx->h_scalars + 7, rdf->hist.ptr + rdf->axis.bins, sizeof(uint32_t));
+        bool const peer_sum = rdf->reduced_valid && rdf->peer != nullptr;
+        if (peer_sum)
+        {
+            d2h(ctx, ctx->h_scalars + 3, rdf->reduced.ptr + rdf->axis.bins, sizeof(uint32_t));
+        }
         sync(ctx);
+        require(!peer_sum || (ctx->h_scalars[3] & 0xffffffffULL) == 0, FGPU_ENCCL,
+                "histogram reduction over peer memory: a rank did not arrive within 10 s");
         // raised on the device by a sharded accumulation (fgpu_points_set_shard), which has no general-kernel
         // fallback and no host round trip of its own
         require((ctx->h_scalars[7] & 0xffffffffULL) == 0, FGPU_ERUNTIME,
@@ -1578,16 +1665,172 @@ int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host)
     });
 }
 
+namespace {
+
+// Ends the current epoch of a peer-attached RDF: sends this rank's counts unless a fused kernel already did, waits
+// (on the stream) for every rank's, leaves the sum in rdf->reduced.
+void peer_reduce(fgpu_rdf* rdf, bool already_pushed)
+{
+    fgpu_ctx* ctx = rdf->ctx;
+    fgpu_rdf_peer* pr = rdf->peer;
+    PeerBox pb = pr->box;
+    pb.parity = (uint32_t) (pr->epoch & 1U);
+    if (!already_pushed)
+    {
+        launch_rdf_push(ctx, pb, rdf->hist.ptr, rdf->axis.bins);
+    }
+    launch_rdf_wait(ctx, pb, rdf->axis.bins, rdf->reduced.ptr, reinterpret_cast<int*>(rdf->reduced.ptr + rdf->axis.bins));
+    pr->epoch += 1;
+    rdf->reduced_valid = true;
+}
+
+void nccl_reduce(fgpu_rdf* rdf, fgpu_comm* comm)
+{
+    NcclApi& api = nccl_or_throw();
+    // out of place: hist keeps this rank's counts (compute(..., reset=False) goes on adding to them)
+    rdf->reduced.reserve((size_t) rdf->axis.bins + 1);
+    nccl_check(api.AllReduce(rdf->hist.ptr, rdf->reduced.ptr, rdf->axis.bins, ncclUint32, ncclSum,
+                             static_cast<ncclComm_t>(comm->nccl_comm), rdf->ctx->stream),
+               "ncclAllReduce(u32 histogram)");
+    rdf->reduced_valid = true;
+}
+
+} // namespace
+
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm)
 {
     return guarded([&] {
         require(rdf != nullptr && comm != nullptr, FGPU_EINVALID, "null argument");
         require(rdf->ctx == comm->ctx, FGPU_EINVALID, "rdf and comm belong to different contexts");
         bind_device(rdf->ctx);
+        if (rdf->peer != nullptr && rdf->peer->comm == comm)
+        {
+            peer_reduce(rdf, false);
+        }
+        else
+        {
+            nccl_reduce(rdf, comm);
+        }
+    });
+}
+
+int fgpu_rdf_attach_comm(fgpu_rdf* rdf, fgpu_comm* comm)
+{
+    return guarded([&] {
+        require(rdf != nullptr && comm != nullptr, FGPU_EINVALID, "null argument");
+        require(rdf->ctx == comm->ctx, FGPU_EINVALID, "rdf and comm belong to different contexts");
+        require(rdf->peer == nullptr, FGPU_ERUNTIME, "this RDF already has a peer mailbox");
+        fgpu_ctx* ctx = rdf->ctx;
+        bind_device(ctx);
         NcclApi& api = nccl_or_throw();
-        nccl_check(api.AllReduce(rdf->hist.ptr, rdf->hist.ptr, rdf->axis.bins, ncclUint32, ncclSum,
-                                 static_cast<ncclComm_t>(comm->nccl_comm), rdf->ctx->stream),
-                   "ncclAllReduce(u32 histogram)");
+        int const world = comm->size;
+        // Collective, so every rank must reach the same verdict: each one reports whether it could allocate and
+        // export its mailbox, and later whether it could open every peer's; anything short of "all yes" leaves the
+        // RDF on the NCCL route (returns 1: not an error, a different transport).
+        uint32_t const bins_pad = (rdf->axis.bins + 31U) & ~31U;
+        size_t const words = 2 * (size_t) bins_pad + 32;
+        std::unique_ptr<fgpu_rdf_peer> pr(new fgpu_rdf_peer());
+        cudaIpcMemHandle_t mine;
+        std::memset(&mine, 0, sizeof(mine));
+        bool ok = world <= kMaxPeers;
+        if (ok)
+        {
+            ok = cudaMalloc(reinterpret_cast<void**>(&pr->mailbox), words * sizeof(uint32_t)) == cudaSuccess
+                && cudaMemset(pr->mailbox, 0, words * sizeof(uint32_t)) == cudaSuccess
+                && (world == 1 || cudaIpcGetMemHandle(&mine, pr->mailbox) == cudaSuccess);
+            cudaGetLastError();
+        }
+        // exchange {ok, handle} of every rank
+        constexpr size_t kRec = 128;
+        static_assert(sizeof(cudaIpcMemHandle_t) + 4 <= kRec, "ipc record");
+        std::vector<unsigned char> all((size_t) world * kRec, 0);
+        unsigned char rec[kRec] = {};
+        rec[0] = ok ? 1 : 0;
+        std::memcpy(rec + 4, &mine, sizeof(mine));
+        comm->stage.reserve((size_t) (world + 1) * kRec);
+        h2d(ctx, comm->stage.ptr + (size_t) world * kRec, rec, kRec);
+        nccl_check(api.AllGather(comm->stage.ptr + (size_t) world * kRec, comm->stage.ptr, kRec, ncclUint8,
+                                 static_cast<ncclComm_t>(comm->nccl_comm), ctx->stream),
+                   "ncclAllGather(ipc handles)");
+        d2h(ctx, all.data(), comm->stage.ptr, (size_t) world * kRec);
+        sync(ctx);
+        for (int r = 0; r < world; ++r)
+        {
+            ok = ok && all[(size_t) r * kRec] == 1;
+        }
+        if (ok)
+        {
+            for (int r = 0; r < world && ok; ++r)
+            {
+                if (r == comm->rank)
+                {
+                    pr->box.box[r] = pr->mailbox;
+                    continue;
+                }
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, all.data() + (size_t) r * kRec + 4, sizeof(h));
+                void* p = nullptr;
+                ok = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                cudaGetLastError();
+                pr->opened[r] = ok ? p : nullptr;
+                pr->box.box[r] = static_cast<uint32_t*>(p);
+            }
+        }
+        // second verdict: did everybody open everything?
+        uint32_t verdict = ok ? 1U : 0U;
+        h2d(ctx, comm->stage.ptr, &verdict, sizeof(verdict));
+        nccl_check(api.AllReduce(comm->stage.ptr, comm->stage.ptr, 1, ncclUint32, ncclMin,
+                                 static_cast<ncclComm_t>(comm->nccl_comm), ctx->stream),
+                   "ncclAllReduce(ipc verdict)");
+        d2h(ctx, &verdict, comm->stage.ptr, sizeof(verdict));
+        sync(ctx);
+        if (verdict == 0)
+        {
+            for (void* p : pr->opened)
+            {
+                if (p != nullptr)
+                {
+                    cudaIpcCloseMemHandle(p);
+                }
+            }
+            cudaFree(pr->mailbox);
+            set_last_error("peer mailbox unavailable (no CUDA IPC / peer access between the ranks): reductions use NCCL");
+            throw Error(1, "peer mailbox unavailable: reductions use NCCL");
+        }
+        pr->comm = comm;
+        pr->box.world = world;
+        pr->box.rank = comm->rank;
+        pr->box.bins_pad = bins_pad;
+        pr->box.parity = 0;
+        rdf->reduced.reserve((size_t) rdf->axis.bins + 1);
+        FGPU_CUDA_CHECK(cudaMemsetAsync(rdf->reduced.ptr, 0, ((size_t) rdf->axis.bins + 1) * sizeof(uint32_t), ctx->stream));
+        sync(ctx);
+        rdf->peer = pr.release();
+    });
+}
+
+int fgpu_rdf_reduce_transport(const fgpu_rdf* rdf)
+{
+    return rdf != nullptr && rdf->peer != nullptr ? 2 : 1;
+}
+
+int fgpu_rdf_accumulate_reduce(fgpu_rdf* rdf, fgpu_points* pts, fgpu_comm* comm, int flavour, float q_r_max,
+                               float q_r_min, int exclude_ii)
+{
+    return guarded([&] {
+        require(rdf != nullptr && pts != nullptr && comm != nullptr, FGPU_EINVALID, "null argument");
+        require(rdf->ctx == comm->ctx, FGPU_EINVALID, "rdf and comm belong to different contexts");
+        bool const peer = rdf->peer != nullptr && rdf->peer->comm == comm;
+        bool const pushed = rdf_accumulate_impl(rdf, pts, nullptr, nullptr, pts->n, 0, flavour, q_r_max, q_r_min,
+                                                exclude_ii, peer);
+        if (peer)
+        {
+            peer_reduce(rdf, pushed);
+        }
+        else
+        {
+            nccl_reduce(rdf, comm);
+        }
     });
 }
 
@@ -2517,15 +2760,16 @@ int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is
     });
 }
 
-int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
-                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
-                            float* sys_qlm_host, float* order_host)
+static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                                   uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
+                                   fgpu_buffer** qlm_keep, float* sys_qlm_host, float* order_host)
 {
     return guarded([&] {
         require(pts != nullptr && nl != nullptr && ls != nullptr && n_ls != 0, FGPU_EINVALID, "null argument");
         require(pts->ctx == nl->ctx, FGPU_EINVALID, "points and nlist belong to different contexts");
         require(nl->n_points == pts->n, FGPU_EINVALID, "NeighborList was built for a different number of points");
-        require(nl->n_query <= pts->n, FGPU_EINVALID, "NeighborList has more rows than there are points");
+        require((uint64_t) nl->n_query + nl->q_index_offset <= pts->n, FGPU_EINVALID,
+                "NeighborList has more rows than there are points");
         bool const weighted = (flags & FGPU_ST_WEIGHTED) != 0, average = (flags & FGPU_ST_AVERAGE) != 0;
         bool const wl = (flags & FGPU_ST_WL) != 0, wl_normalize = wl && (flags & FGPU_ST_WL_NORMALIZE) != 0;
         fgpu_ctx* ctx = pts->ctx;
@@ -2549,7 +2793,7 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         DevBuf<uint32_t> d_w3j_off;
         DevBuf<double> d_sys;
         d_ql.reserve((size_t) n * n_ls + 1);
-        bool const need_qlm = qlm_host != nullptr || average || wl;
+        bool const need_qlm = qlm_host != nullptr || qlm_keep != nullptr || average || wl;
         if (need_qlm)
         {
             d_qlm.reserve((size_t) n * tot_m * 2 + 2);
@@ -2570,6 +2814,7 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
         a.xyz = pts->xyz.ptr;
         a.xyz4 = pts->xyz4.ptr;
         a.n = n;
+        a.row_offset = nl->q_index_offset;
         a.neighbors = nl->neighbors.ptr;
         a.distances = nl->distances.ptr;
         a.weights = nl->weights.ptr;
@@ -2645,6 +2890,15 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
             d2h(ctx, qlm_host, d_qlm.ptr, (size_t) n * tot_m * 2 * sizeof(float));
         }
         sync(ctx);
+        if (qlm_keep != nullptr)
+        {
+            // the per-particle q_lm (104 MB at l = 6, N = 1e6) stay on the device until somebody asks for them
+            std::unique_ptr<fgpu_buffer> keep(new fgpu_buffer());
+            keep->ctx = ctx;
+            keep->bytes = (uint64_t) n * tot_m * 2 * sizeof(float);
+            keep->data.swap(d_qlm);
+            *qlm_keep = keep.release();
+        }
         // system q_lm = sum_i q_lm(i) / N ; derive m < 0 ; normalizeSystem (Steinhardt.cc:291-327)
         size_t off = 0;
         for (uint32_t r = 0; r < n_ls; ++r)
@@ -2707,6 +2961,194 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
             }
             off += 2 * (size_t) l + 1;
         }
+    });
+}
+
+int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                            uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
+                            float* sys_qlm_host, float* order_host)
+{
+    return steinhardt_compute_impl(pts, nl, ls, n_ls, flags, n_total, comm, ql_host, wl_host, qlm_host, nullptr,
+                                   sys_qlm_host, order_host);
+}
+
+int fgpu_steinhardt_compute_keep(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                                 uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host,
+                                 fgpu_buffer** qlm_dev_out, float* sys_qlm_host, float* order_host)
+{
+    if (qlm_dev_out == nullptr)
+    {
+        set_last_error("null argument");
+        return FGPU_EINVALID;
+    }
+    *qlm_dev_out = nullptr;
+    return steinhardt_compute_impl(pts, nl, ls, n_ls, flags, n_total, comm, ql_host, wl_host, nullptr, qlm_dev_out,
+                                   sys_qlm_host, order_host);
+}
+
+// ---- device buffers kept for a later read ----------------------------------------------------------------------
+uint64_t fgpu_buffer_bytes(const fgpu_buffer* buf)
+{
+    return buf != nullptr ? buf->bytes : 0;
+}
+
+int fgpu_buffer_read(fgpu_buffer* buf, void* host, uint64_t offset_bytes, uint64_t bytes)
+{
+    return guarded([&] {
+        require(buf != nullptr && (host != nullptr || bytes == 0), FGPU_EINVALID, "null argument");
+        require(offset_bytes <= buf->bytes && bytes <= buf->bytes - offset_bytes, FGPU_ERANGE, "read beyond the buffer");
+        bind_device(buf->ctx);
+        d2h(buf->ctx, host, reinterpret_cast<const unsigned char*>(buf->data.ptr) + offset_bytes, bytes);
+        sync(buf->ctx);
+    });
+}
+
+void fgpu_buffer_destroy(fgpu_buffer* buf)
+{
+    if (buf != nullptr)
+    {
+        bind_quiet(buf->ctx);
+        delete buf;
+    }
+}
+
+// ---- page-locked host memory, cached ---------------------------------------------------------------------------
+// The outputs of this path are large (225 MB of NeighborList arrays, 104 MB of q_lm per 1 M-point frame) and a
+// device -> pageable-host copy runs at a fraction of the link's rate, while page-locking memory costs about as much
+// as the copy it speeds up.  So the host classes take their arrays from here: blocks are page-locked once, handed
+// back on free and reused by the next frame's arrays of the same size class.  Without a CUDA device (host-only unit
+// tests of the container classes) the blocks are ordinary aligned memory.
+namespace {
+
+struct HostPool
+{
+    std::mutex mu;
+    std::unordered_map<void*, std::pair<size_t, bool>> live;   // block -> {size class, page-locked}
+    std::unordered_map<void*, std::pair<size_t, bool>> parked; // same for the cached blocks
+    std::multimap<size_t, void*> free_by_size;
+    size_t cached_bytes = 0;
+    int no_device = -1; // -1: unknown
+};
+
+HostPool& host_pool()
+{
+    static HostPool* p = new HostPool(); // never destroyed: blocks may outlive static destruction order
+    return *p;
+}
+
+size_t host_size_class(size_t bytes)
+{
+    size_t const unit = bytes <= (1U << 20) ? 4096 : (2U << 20);
+    return std::max<size_t>(unit, (bytes + unit - 1) / unit * unit);
+}
+
+constexpr size_t kHostCacheLimit = 6ULL << 30;
+
+} // namespace
+
+int fgpu_host_alloc(uint64_t bytes, void** out)
+{
+    return guarded([&] {
+        require(out != nullptr, FGPU_EINVALID, "null argument");
+        HostPool& hp = host_pool();
+        size_t const cls = host_size_class((size_t) bytes);
+        std::lock_guard<std::mutex> lock(hp.mu);
+        auto it = hp.free_by_size.lower_bound(cls);
+        if (it != hp.free_by_size.end() && it->first <= cls + cls / 4)
+        {
+            void* p = it->second;
+            hp.free_by_size.erase(it);
+            auto const rec = hp.parked[p];
+            hp.parked.erase(p);
+            hp.cached_bytes -= rec.first;
+            hp.live[p] = rec;
+            *out = p;
+            return;
+        }
+        void* p = nullptr;
+        bool pinned = false;
+        if (hp.no_device != 1)
+        {
+            cudaError_t const err = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
+            if (err == cudaSuccess)
+            {
+                pinned = true;
+                hp.no_device = 0;
+            }
+            else
+            {
+                cudaGetLastError();
+                p = nullptr;
+                if (err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver)
+                {
+                    hp.no_device = 1;
+                }
+            }
+        }
+        if (p == nullptr)
+        {
+            p = std::aligned_alloc(4096, cls);
+        }
+        if (p == nullptr)
+        {
+            throw Error(FGPU_ENOMEM, "out of host memory");
+        }
+        hp.live[p] = {cls, pinned};
+        *out = p;
+    });
+}
+
+void fgpu_host_free(void* p)
+{
+    if (p == nullptr)
+    {
+        return;
+    }
+    HostPool& hp = host_pool();
+    std::lock_guard<std::mutex> lock(hp.mu);
+    auto it = hp.live.find(p);
+    if (it == hp.live.end())
+    {
+        return; // not ours
+    }
+    auto const rec = it->second;
+    hp.live.erase(it);
+    if (hp.cached_bytes + rec.first <= kHostCacheLimit)
+    {
+        hp.parked[p] = rec;
+        hp.free_by_size.emplace(rec.first, p);
+        hp.cached_bytes += rec.first;
+        return;
+    }
+    if (rec.second)
+    {
+        cudaFreeHost(p);
+    }
+    else
+    {
+        std::free(p);
+    }
+}
+
+int fgpu_host_trim(void)
+{
+    return guarded([&] {
+        HostPool& hp = host_pool();
+        std::lock_guard<std::mutex> lock(hp.mu);
+        for (auto& kv : hp.parked)
+        {
+            if (kv.second.second)
+            {
+                cudaFreeHost(kv.first);
+            }
+            else
+            {
+                std::free(kv.first);
+            }
+        }
+        hp.parked.clear();
+        hp.free_by_size.clear();
+        hp.cached_bytes = 0;
     });
 }
 

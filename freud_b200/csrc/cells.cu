@@ -36,7 +36,7 @@ enum : unsigned long long
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restrict__ data, size_t n,
                                                                volatile unsigned long long* state,
-                                                               unsigned int* ticket)
+                                                               unsigned int* ticket, const uint32_t* init)
 {
     __shared__ uint32_t warp_sums[kScanThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
@@ -105,9 +105,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restr
         uint32_t prefix = 0;
         if (tile == 0)
         {
+            prefix = init != nullptr ? *init : 0U; // the scan continues another one (sharded build: second cell range)
             if (lane == 0)
             {
-                state[0] = kFlagPrefix | total;
+                state[0] = kFlagPrefix | (uint32_t) (prefix + total);
             }
         }
         else
@@ -218,6 +219,155 @@ __global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy,
     rank_in[i] = atomicAdd(&cell_count[c], 1U);
 }
 
+// K0: everything the build needs zeroed, in one launch instead of four memsets (launch gaps are a visible share of a
+// sharded step): the cell counters (two ranges: a sharded rank only zeroes, scans and reads the cells of its slab),
+// the scan's tile states + tickets, the out-of-box flag and the slab counter.
+__global__ void __launch_bounds__(256) k_cell_prep(uint32_t* __restrict__ cell_count, size_t a0, size_t a1, size_t b0,
+                                                   size_t b1, uint32_t* __restrict__ scan_words, uint32_t n_scan,
+                                                   int* __restrict__ any_shift, uint32_t* __restrict__ slab_count)
+{
+    size_t const stride = (size_t) gridDim.x * blockDim.x;
+    size_t const t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = a0 + t; i < a1; i += stride)
+    {
+        cell_count[i] = 0U;
+    }
+    for (size_t i = b0 + t; i < b1; i += stride)
+    {
+        cell_count[i] = 0U;
+    }
+    for (size_t i = t; i < n_scan; i += stride)
+    {
+        scan_words[i] = 0U;
+    }
+    if (t == 0)
+    {
+        *any_shift = 0;
+        if (slab_count != nullptr)
+        {
+            *slab_count = 0U;
+        }
+    }
+}
+
+// K1 for a sharded rank: one pass over ALL points (the input is replicated), but only the points of this rank's slab
+// leave a trace -- {x, y, z, index} + {cell, arrival rank} appended to a compact list, one global atomic per block --
+// so the scatter and everything after it touch the slab only (the build must not stay serial;
+// at 8 ranks the slab holds ~1/6 of the points).  Four points per thread as three 16-byte loads; the slab test needs
+// the z (2-D: y) fraction only, taken with a reciprocal, and a point within 1e-4 of a layer or box boundary is
+// settled by the exact arithmetic of cell_coords, which every accepted point goes through anyway.
+constexpr int kSlabThreads = 256;
+constexpr int kSlabPointsPerBlock = kSlabThreads * 4;
+
+__global__ void __launch_bounds__(kSlabThreads) k_cell_assign_slab(BoxDev box, int dx, int dy, int dz,
+                                                                   const float* __restrict__ xyz, uint32_t n,
+                                                                   uint32_t* __restrict__ cell_count,
+                                                                   int* __restrict__ any_shift, SlabDev slab,
+                                                                   float4* __restrict__ slab_pos,
+                                                                   uint2* __restrict__ slab_cr,
+                                                                   uint32_t* __restrict__ slab_count)
+{
+    __shared__ float4 s_pos[kSlabPointsPerBlock];
+    __shared__ uint2 s_cr[kSlabPointsPerBlock];
+    __shared__ uint32_t s_n, s_base;
+    if (threadIdx.x == 0)
+    {
+        s_n = 0;
+    }
+    __syncthreads();
+    uint32_t const i0 = (blockIdx.x * kSlabThreads + threadIdx.x) * 4U;
+    float v[12];
+    if (i0 + 4 <= n)
+    {
+        const float4* src = reinterpret_cast<const float4*>(xyz + 3 * (size_t) i0); // 48-byte aligned
+        float4 const a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        v[8] = c.x, v[9] = c.y, v[10] = c.z, v[11] = c.w;
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+        {
+            size_t const e = 3 * (size_t) i0 + k;
+            v[k] = e < 3 * (size_t) n ? xyz[e] : 0.0f;
+        }
+    }
+    int const d = slab.axis == 2 ? dz : dy;
+    float const rcp_lx = 1.0f / box.Lx, rcp_ly = 1.0f / box.Ly, rcp_lz = box.is2d ? 0.0f : 1.0f / box.Lz;
+    float const fd = (float) d;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        uint32_t const i = i0 + k;
+        if (i >= n)
+        {
+            break;
+        }
+        float const x = v[3 * k], y = v[3 * k + 1], z = v[3 * k + 2];
+        // approximate fractions (the arithmetic of fractional_for_cells with the divisions replaced)
+        float const gz = box.is2d ? 0.5f : (z - box.loz) * rcp_lz;
+        float const gy = ((y - box.loy) - box.yz * z) * rcp_ly;
+        float const gx = ((x - box.lox) - (box.t_xz * z + box.xy * y)) * rcp_lx;
+        bool const well_inside = gx > 1e-4f && gx < 0.9999f && gy > 1e-4f && gy < 0.9999f
+            && (box.is2d || (gz > 1e-4f && gz < 0.9999f));
+        float const gs = (slab.axis == 2 ? gz : gy) * fd; // layer coordinate
+        float const frac_layer = gs - floorf(gs);
+        bool decided = well_inside && frac_layer > 1e-2f && frac_layer < 0.99f;
+        bool mine = false;
+        if (decided)
+        {
+            int rel = (int) gs - slab.lo;
+            rel += rel < 0 ? d : 0;
+            mine = rel < slab.len;
+        }
+        if (!decided || mine)
+        {
+            int cx, cy, cz, nx, ny, nz;
+            cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+            if ((nx | ny | nz) != 0)
+            {
+                *any_shift = 1;
+            }
+            int rel = (slab.axis == 2 ? cz : cy) - slab.lo;
+            rel += rel < 0 ? d : 0;
+            if (rel < slab.len)
+            {
+                uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
+                uint32_t const pos = atomicAdd(&s_n, 1U);
+                s_pos[pos] = make_float4(x, y, z, __uint_as_float(i));
+                s_cr[pos] = make_uint2(c, atomicAdd(&cell_count[c], 1U));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n != 0)
+    {
+        s_base = atomicAdd(slab_count, s_n);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < s_n; k += blockDim.x)
+    {
+        slab_pos[s_base + k] = s_pos[k];
+        slab_cr[s_base + k] = s_cr[k];
+    }
+}
+
+// K3 for a sharded rank: the compact list only, read in order
+__global__ void __launch_bounds__(256) k_cell_scatter_slab(const float4* __restrict__ slab_pos,
+                                                           const uint2* __restrict__ slab_cr,
+                                                           const uint32_t* __restrict__ slab_count,
+                                                           const uint32_t* __restrict__ cell_start,
+                                                           float4* __restrict__ sorted)
+{
+    uint32_t const n = *slab_count;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    {
+        uint2 const cr = slab_cr[k];
+        sorted[__ldg(cell_start + cr.x) + cr.y] = slab_pos[k];
+    }
+}
+
 // K3: scatter to cell order -- 20 B read, 16 (+4) B written per point
 __global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
                                                       uint32_t n, const uint32_t* __restrict__ cell_of,
@@ -299,7 +449,14 @@ void choose_dims(const fgpu_points* pts, float r_search, bool force_single_cell,
 
 } // namespace
 
-void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n)
+size_t scan_scratch_words(size_t n)
+{
+    size_t const tiles = (n + kScanTile - 1) / kScanTile;
+    return 2 * tiles + 2; // one {flag, value} word per tile + the tile ticket
+}
+
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero, const uint32_t* init,
+                        size_t scratch_offset)
 {
     if (n == 0)
     {
@@ -310,14 +467,16 @@ void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n)
         throw Error(FGPU_ERUNTIME, "exclusive_scan_u32 needs a 16-byte aligned array");
     }
     size_t const tiles = (n + kScanTile - 1) / kScanTile;
-    // scratch: one {flag, value} word per tile + the tile ticket
-    ctx->scan_tmp.reserve(2 * tiles + 2);
-    FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->scan_tmp.ptr, 0, (2 * tiles + 2) * sizeof(uint32_t), ctx->stream));
-    auto* state = reinterpret_cast<unsigned long long*>(ctx->scan_tmp.ptr);
-    auto* ticket = reinterpret_cast<unsigned int*>(ctx->scan_tmp.ptr + 2 * tiles);
+    if (!scratch_is_zero)
+    {
+        ctx->scan_tmp.reserve(scan_scratch_words(n));
+        FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->scan_tmp.ptr, 0, scan_scratch_words(n) * sizeof(uint32_t), ctx->stream));
+    }
+    auto* state = reinterpret_cast<unsigned long long*>(ctx->scan_tmp.ptr + scratch_offset);
+    auto* ticket = reinterpret_cast<unsigned int*>(ctx->scan_tmp.ptr + scratch_offset + 2 * tiles);
     {
         KernelScope ks(ctx, "scan");
-        k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket);
+        k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket, init);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
@@ -412,29 +571,91 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
     }
     uint32_t const n = pts->n;
     uint32_t const n_cells = (uint32_t) dim[0] * dim[1] * dim[2];
-    g.cell_of.reserve(n);
-    g.rank_in.reserve(n);
-    g.cell_start.reserve((size_t) n_cells + 1);
+    bool const slab_only = slab.len >= 0;
+    g.cell_start.reserve((size_t) n_cells + 4);
     g.sorted.reserve(n);
-    FGPU_CUDA_CHECK(cudaMemsetAsync(g.cell_start.ptr, 0, ((size_t) n_cells + 1) * sizeof(uint32_t), ctx->stream));
     // out-of-box flag: set on the device by K1, read on the device by K3 and the search kernels, so the
     // build needs no host round trip; the shift array is only ever written when the flag is set
     g.shift.reserve(n);
-    g.any_shift_flag.reserve(1);
+    g.any_shift_flag.reserve(2); // [1]: points in this rank's slab (sharded build)
     int* d_flag = g.any_shift_flag.ptr;
-    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
-    unsigned const blocks = (n + 255) / 256;
+    uint32_t* d_slab_count = reinterpret_cast<uint32_t*>(d_flag + 1);
+    // The cells the build zeroes, scans and fills: all of them, or the one or two contiguous index ranges of the slab
+    // (layers of the slowest grid axis; a slab that wraps around the periodic boundary is two ranges, the second
+    // scan continuing the first).  Every range carries one extra element: cell_start[end] closes its last cell.
+    size_t ra0 = 0, ra1 = (size_t) n_cells + 1, rb0 = 0, rb1 = 0;
+    bool const ranged = slab_only && slab.axis == (dim[2] > 1 ? 2 : 1);
+    if (ranged)
     {
-        KernelScope ks(ctx, "cell_assign");
-        k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
-                                                       g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag, slab);
+        size_t const per_layer = slab.axis == 2 ? (size_t) dim[0] * dim[1] : (size_t) dim[0];
+        int const layers = slab.axis == 2 ? dim[2] : dim[1];
+        int const hi = slab.lo + slab.len;
+        ra0 = (size_t) slab.lo * per_layer;
+        ra1 = (size_t) std::min(hi, layers) * per_layer + 1;
+        if (hi > layers)
+        {
+            rb0 = 0;
+            rb1 = (size_t) (hi - layers) * per_layer + 1;
+        }
     }
-    exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1);
+    // 16-byte alignment of the scanned ranges (the scan reads uint4): grow them downwards
+    ra0 &= ~(size_t) 3;
+    size_t const words_a = scan_scratch_words(ra1 - ra0), words_b = rb1 > rb0 ? scan_scratch_words(rb1 - rb0) : 0;
+    ctx->scan_tmp.reserve(words_a + words_b);
     {
-        KernelScope ks(ctx, "cell_scatter");
-        k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
-                                                        g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
-                                                        g.shift.ptr, d_flag);
+        KernelScope ks(ctx, "cell_prep");
+        size_t const work = (ra1 - ra0) + (rb1 - rb0);
+        unsigned const pblocks = (unsigned) std::min<size_t>((work + 255) / 256, (size_t) ctx->sm_count * 8);
+        k_cell_prep<<<std::max(pblocks, 1U), 256, 0, ctx->stream>>>(g.cell_start.ptr, ra0, ra1, rb0, rb1, ctx->scan_tmp.ptr,
+                                                                   (uint32_t) (words_a + words_b), d_flag, d_slab_count);
+    }
+    unsigned const blocks = (n + 255) / 256;
+    if (slab_only)
+    {
+        // the list is sized for all n points (clustered systems); only its first *d_slab_count entries are touched
+        g.slab_pos.reserve(n);
+        g.cell_of.reserve((size_t) n * 2); // reused as the {cell, arrival rank} list
+        {
+            KernelScope ks(ctx, "cell_assign");
+            k_cell_assign_slab<<<(n + kSlabPointsPerBlock - 1) / kSlabPointsPerBlock, kSlabThreads, 0, ctx->stream>>>(
+                pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_start.ptr, d_flag, slab, g.slab_pos.ptr,
+                reinterpret_cast<uint2*>(g.cell_of.ptr), d_slab_count);
+        }
+        if (rb1 > rb0)
+        {
+            // wrapped slab: the low range first, the high range continues at its total
+            exclusive_scan_u32(ctx, g.cell_start.ptr + rb0, rb1 - rb0, true, nullptr, words_a);
+            exclusive_scan_u32(ctx, g.cell_start.ptr + ra0, ra1 - ra0, true, g.cell_start.ptr + rb1 - 1, 0);
+        }
+        else
+        {
+            exclusive_scan_u32(ctx, g.cell_start.ptr + ra0, ra1 - ra0, true, nullptr, 0);
+        }
+        {
+            KernelScope ks(ctx, "cell_scatter");
+            k_cell_scatter_slab<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+                g.slab_pos.ptr, reinterpret_cast<const uint2*>(g.cell_of.ptr), d_slab_count, g.cell_start.ptr,
+                g.sorted.ptr);
+        }
+        g.cell_of_valid = false;
+    }
+    else
+    {
+        g.cell_of.reserve(n);
+        g.rank_in.reserve(n);
+        {
+            KernelScope ks(ctx, "cell_assign");
+            k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
+                                                           g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag, slab);
+        }
+        exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1, true);
+        {
+            KernelScope ks(ctx, "cell_scatter");
+            k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
+                                                            g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
+                                                            g.shift.ptr, d_flag);
+        }
+        g.cell_of_valid = true;
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
     for (int d = 0; d < 3; ++d)

@@ -10,6 +10,7 @@
 
 #include "../../include/freud_b200.h"
 #include "pair_math.cuh"
+#include "peer.cuh"
 
 namespace fgpu {
 
@@ -189,10 +190,12 @@ struct fgpu_grid
     uint32_t n_cells = 0;
     int ambiguous[3] = {0, 0, 0}; // dim < 3 on a periodic axis: several images may map to one cell
     fgpu::DevBuf<int> any_shift_flag; // device flag: some point lies outside the box (image offset != 0)
-    fgpu::DevBuf<uint32_t> cell_of;    // per point
-    fgpu::DevBuf<uint32_t> rank_in;    // per point: arrival rank inside its cell
+    fgpu::DevBuf<uint32_t> cell_of;    // per point (sharded build: the compact {index, cell} list of the slab instead)
+    bool cell_of_valid = false;        // cell_of is indexed by point (k_count_evals reads it)
+    fgpu::DevBuf<uint32_t> rank_in;    // per point: arrival rank inside its cell (sharded build: per list entry)
     fgpu::DevBuf<uint32_t> cell_start; // n_cells + 1
     fgpu::DevBuf<float4> sorted;       // cell-ordered positions, w = bit pattern of the point index
+    fgpu::DevBuf<float4> slab_pos;     // sharded build: the slab's points {x, y, z, bits(index)} in arrival order
     fgpu::DevBuf<int> shift;           // cell-ordered packed integer image offsets (10 bits per axis, biased)
     int shard = 0, n_shards = 1;       // the slab this list was built for (fgpu_points_set_shard)
 };
@@ -217,13 +220,28 @@ struct fgpu_nlist : NlistStorage
     uint32_t n_query = 0;
     uint32_t n_points = 0;
     bool unit_weights = false; // built by a query: every weight is 1 (NeighborQuery.h:470-478)
+    uint32_t q_index_offset = 0; // built by a query of a contiguous shard of the points: row k is point k + offset
+};
+
+// Peer-memory reduction state of one RDF (fgpu_rdf_attach_comm, peer.cuh)
+struct fgpu_rdf_peer
+{
+    fgpu_comm* comm = nullptr;
+    uint32_t* mailbox = nullptr;           // this rank's mailbox (cudaMalloc: stream-ordered pool memory has no IPC handle)
+    void* opened[fgpu::kMaxPeers] = {};    // peers' mailboxes as opened here (nullptr for the own rank)
+    fgpu::PeerBox box;                     // parity is set per epoch
+    uint64_t epoch = 0;
+    bool pushed = false;                   // the counts of the current epoch are already on their way (fused push)
 };
 
 struct fgpu_rdf
 {
     fgpu_ctx* ctx = nullptr;
+    fgpu_rdf_peer* peer = nullptr;
     fgpu::AxisDev axis;
-    fgpu::DevBuf<uint32_t> hist;
+    fgpu::DevBuf<uint32_t> hist;    // this rank's counts (+ one sticky flag word), never touched by a reduction
+    fgpu::DevBuf<uint32_t> reduced; // sum over the ranks, valid from fgpu_rdf_allreduce until the next accumulate / reset
+    bool reduced_valid = false;
 };
 
 struct fgpu_pmft;
@@ -268,6 +286,13 @@ struct fgpu_corr
     fgpu::DevBuf<uint32_t> counts; // bins
     fgpu::DevBuf<double> sums;     // bins x (re, im)
     fgpu::DevBuf<double> values, query_values; // staged per call
+};
+
+struct fgpu_buffer
+{
+    fgpu_ctx* ctx = nullptr;
+    uint64_t bytes = 0;
+    fgpu::DevBuf<float> data;
 };
 
 struct fgpu_comm
@@ -324,7 +349,11 @@ struct SearchArgs
     const int* only_if;
 };
 
-void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n); // in place, n elements
+// in place, n elements; scratch_is_zero: ctx->scan_tmp (scan_scratch_words(n) words) was zeroed by the caller's kernel
+// init: device pointer to the value the scan starts from (nullptr: 0); scratch_offset: words into ctx->scan_tmp
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero = false, const uint32_t* init = nullptr,
+                        size_t scratch_offset = 0);
+size_t scan_scratch_words(size_t n);
 void build_grid(fgpu_points* pts, float r_search, bool force_single_cell = false);
 void launch_check_2d_z(fgpu_ctx* ctx, const float* xyz, uint32_t n, int* flag); // *flag = 1 if some |z| > 1e-6
 GridDev grid_dev(const fgpu_points* pts);
@@ -399,6 +428,10 @@ struct Search2Args
     // scheduling / instrumentation
     unsigned int* work_counter;
     unsigned long long* evals;      // may be nullptr
+    // RDF mode, multi-GPU: the last block to finish pushes the finished histogram into every rank's mailbox (peer.cuh)
+    int push;
+    unsigned int* done_counter;     // blocks that have merged their histogram (zeroed with work_counter)
+    PeerBox peer;
 };
 void search2_plan(Search2Args& a, uint32_t n_points); // sets span, spans_per_row, n_tickets
 
@@ -585,6 +618,7 @@ struct SteinhardtArgs
     const float* xyz;    // original order, n_points x 3
     const float4* xyz4;  // the same, padded to 16 bytes (fgpu_points::xyz4)
     uint32_t n;
+    uint32_t row_offset; // row k of the list is particle k + row_offset (a rank's shard of the rows)
     const uint32_t* neighbors;
     const float* distances;
     const float* weights;
@@ -625,6 +659,9 @@ struct SteinhardtWlArgs
 };
 void launch_steinhardt_wl(fgpu_ctx* ctx, const SteinhardtWlArgs& a, int n_ls);
 std::vector<float> wigner3j_table(uint32_t l);
+
+void launch_rdf_push(fgpu_ctx* ctx, const PeerBox& pb, const uint32_t* hist, uint32_t bins);
+void launch_rdf_wait(fgpu_ctx* ctx, const PeerBox& pb, uint32_t bins, uint32_t* reduced, int* timeout);
 
 // NCCL (loaded with dlopen)
 int nccl_available(std::string* why);

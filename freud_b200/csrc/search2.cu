@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
         {
             *a.fail = 1;
         }
+        if (MODE == S2_RDF && a.push && blockIdx.x == 0)
+        {
+            // the frame fails on this rank (and, the points being replicated, on every rank): still arrive, so that
+            // no peer's wait has to time out; fgpu_rdf_read raises on the sticky flag
+            peer_push_block(a.peer, a.hist, 0);
+        }
         return;
     }
     if (MODE == S2_RDF)
@@ -525,6 +531,24 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
                 atomicAdd(&a.hist[b], v); // u32 wraps like the reference's unsigned int counters
             }
         }
+        if (a.push)
+        {
+            // compute + collective in one kernel: the block that merges last owns the finished histogram and sends it
+            // to every rank over NVLink (peer.cuh); nobody waits here, the epoch's k_rdf_wait does
+            __shared__ unsigned int s_last;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                s_last = atomicAdd(a.done_counter, 1U) == gridDim.x - 1 ? 1U : 0U;
+            }
+            __syncthreads();
+            if (s_last != 0)
+            {
+                __threadfence();
+                peer_push_block(a.peer, a.hist, a.axis.bins);
+            }
+        }
     }
 }
 
@@ -562,7 +586,11 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
         if (a.exclude_ii)
         {
             uint32_t const j = __float_as_uint(q.w) + a.q_index_offset;
-            if (j < n_points)
+            if (j < n_points && cell_of_point == nullptr)
+            {
+                evals -= 1; // self query: the excluded point is the query itself, in its own cell
+            }
+            else if (j < n_points)
             {
                 uint32_t const c = cell_of_point[j];
                 if (c != 0xffffffffU) // else the point is outside this rank's slab: in none of the visited cells

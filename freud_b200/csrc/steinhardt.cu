@@ -163,9 +163,10 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
     float rx0 = 0.0f, ry0 = 0.0f, rz0 = 0.0f;
     if (active)
     {
-        rx0 = a.xyz[3 * (size_t) i];
-        ry0 = a.xyz[3 * (size_t) i + 1];
-        rz0 = a.xyz[3 * (size_t) i + 2];
+        size_t const pi = (size_t) i + a.row_offset;
+        rx0 = a.xyz[3 * pi];
+        ry0 = a.xyz[3 * pi + 1];
+        rz0 = a.xyz[3 * pi + 2];
     }
     for (uint32_t c0 = block_beg; c0 < block_end; c0 += kStageBonds)
     {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) k_steinhardt_generic(SteinhardtArgs 
     }
     float total_weight = 0.0f;
     uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
-    size_t const ii = active ? i : 0;
+    size_t const ii = active ? (size_t) i + a.row_offset : 0;
     float const rx0 = a.xyz[3 * ii], ry0 = a.xyz[3 * ii + 1], rz0 = a.xyz[3 * ii + 2];
     BondIn next = beg < end ? load_bond(a, beg) : BondIn {0, 0, 0, 0, 0};
     for (uint32_t b = beg; b < end; ++b)

@@ -79,24 +79,25 @@ public:
     unsigned int getNumQueryPoints() const { return m_num_query_points; }
     unsigned int getNumPoints() const { return m_num_points; }
 
+    // each getter brings over its own array only (a caller that reads the distances does not pay for the vectors)
     std::shared_ptr<const util::ManagedArray<unsigned int>> getNeighbors() const
     {
-        materialise();
+        materialise(kNeighbors);
         return m_neighbors;
     }
     std::shared_ptr<const util::ManagedArray<float>> getDistances() const
     {
-        materialise();
+        materialise(kDistances);
         return m_distances;
     }
     std::shared_ptr<const util::ManagedArray<float>> getWeights() const
     {
-        materialise();
+        materialise(kWeights);
         return m_weights;
     }
     std::shared_ptr<const util::ManagedArray<float>> getVectors() const
     {
-        materialise();
+        materialise(kVectors);
         return m_vectors;
     }
     std::shared_ptr<const util::ManagedArray<unsigned int>> getCounts() const
@@ -117,9 +118,10 @@ public:
         {
             return;
         }
-        m_counts = make<unsigned int>({m_num_query_points});
-        m_segments = make<unsigned int>({m_num_query_points});
-        if (m_dev && !m_host_valid)
+        bool const from_device = m_dev && !m_host_valid;
+        m_counts = from_device ? make_raw<unsigned int>({m_num_query_points}) : make<unsigned int>({m_num_query_points});
+        m_segments = from_device ? make_raw<unsigned int>({m_num_query_points}) : make<unsigned int>({m_num_query_points});
+        if (from_device)
         {
             gpu::check(fgpu_nlist_copy(m_dev.get(), nullptr, nullptr, nullptr, nullptr, m_segments->data(),
                                        m_counts->data()));
@@ -276,20 +278,54 @@ private:
         return std::make_shared<util::ManagedArray<T>>(std::move(shape));
     }
 
-    // D2H copy of the bond arrays, once
-    void materialise() const
+    enum : unsigned
+    {
+        kNeighbors = 1,
+        kDistances = 2,
+        kWeights = 4,
+        kVectors = 8,
+        kAll = 15
+    };
+    template<typename T> static std::shared_ptr<util::ManagedArray<T>> make_raw(std::vector<size_t> shape)
+    {
+        return std::make_shared<util::ManagedArray<T>>(std::move(shape), util::Uninitialized {});
+    }
+
+    // D2H copy of the bond arrays asked for, each at most once, straight into page-locked arrays that the copy
+    // overwrites entirely (no zero fill)
+    void materialise(unsigned want = kAll) const
     {
         if (m_host_valid)
         {
             return;
         }
-        m_neighbors = make<unsigned int>({m_num_bonds, 2});
-        m_distances = make<float>({m_num_bonds});
-        m_weights = make<float>({m_num_bonds});
-        m_vectors = make<float>({m_num_bonds, 3});
-        gpu::check(fgpu_nlist_copy(m_dev.get(), m_neighbors->data(), m_distances->data(), m_weights->data(),
-                                   m_vectors->data(), nullptr, nullptr));
-        m_host_valid = true;
+        want &= ~m_have;
+        if (want == 0)
+        {
+            return;
+        }
+        if (want & kNeighbors)
+        {
+            m_neighbors = make_raw<unsigned int>({m_num_bonds, 2});
+        }
+        if (want & kDistances)
+        {
+            m_distances = make_raw<float>({m_num_bonds});
+        }
+        if (want & kWeights)
+        {
+            m_weights = make_raw<float>({m_num_bonds});
+        }
+        if (want & kVectors)
+        {
+            m_vectors = make_raw<float>({m_num_bonds, 3});
+        }
+        gpu::check(fgpu_nlist_copy(m_dev.get(), (want & kNeighbors) ? m_neighbors->data() : nullptr,
+                                   (want & kDistances) ? m_distances->data() : nullptr,
+                                   (want & kWeights) ? m_weights->data() : nullptr,
+                                   (want & kVectors) ? m_vectors->data() : nullptr, nullptr, nullptr));
+        m_have |= want;
+        m_host_valid = m_have == kAll;
     }
 
     void reorder(const std::vector<unsigned int>& idx)
@@ -324,6 +360,7 @@ private:
     mutable std::shared_ptr<util::ManagedArray<float>> m_distances, m_weights, m_vectors;
     mutable std::shared_ptr<util::ManagedArray<unsigned int>> m_counts, m_segments;
     mutable bool m_host_valid {false}, m_segments_valid {false};
+    mutable unsigned m_have {0}; // bond arrays already on the host (device-built lists)
     mutable std::shared_ptr<fgpu_nlist> m_dev;
     mutable fgpu_ctx* m_ctx {nullptr};
 };

@@ -13,6 +13,9 @@
 // arithmetic ("flavour") whose results it reproduces bit for bit: LinkCell -> Box::wrap(p_j - q),
 // AABBQuery / RawPoints -> p_j - (q + image).
 #pragma once
+#include <atomic>
+#include <cstring>
+#include <thread>
 #include <cmath>
 #include <limits>
 #include <memory>
@@ -273,9 +276,61 @@ private:
 
 // The query points as the C ABI takes them: nullptr when they are the reference points themselves (no upload, no
 // second cell sort), else the packed floats.
+// Bitwise equality of two point arrays: a few probes first (different query sets fail at once), then the whole
+// array, on a few threads when it is large.
+inline bool samePoints(const vec3<float>* a, const vec3<float>* b, unsigned int n)
+{
+    if (a == b)
+    {
+        return true;
+    }
+    if (a == nullptr || b == nullptr)
+    {
+        return false;
+    }
+    size_t const bytes = (size_t) n * sizeof(vec3<float>);
+    for (unsigned int k = 0; k < 64 && n != 0; ++k)
+    {
+        size_t const i = (size_t) k * (n - 1) / 63;
+        if (std::memcmp(&a[i], &b[i], sizeof(vec3<float>)) != 0)
+        {
+            return false;
+        }
+    }
+    auto const* pa = reinterpret_cast<const unsigned char*>(a);
+    auto const* pb = reinterpret_cast<const unsigned char*>(b);
+    unsigned int const n_threads = bytes >= (2U << 20) ? 4 : 1;
+    if (n_threads == 1)
+    {
+        return std::memcmp(pa, pb, bytes) == 0;
+    }
+    std::atomic<bool> same {true};
+    std::vector<std::thread> pool;
+    size_t const chunk = (bytes + n_threads - 1) / n_threads;
+    for (unsigned int t = 0; t < n_threads; ++t)
+    {
+        size_t const lo = std::min(bytes, (size_t) t * chunk), hi = std::min(bytes, lo + chunk);
+        pool.emplace_back([=, &same] {
+            if (std::memcmp(pa + lo, pb + lo, hi - lo) != 0)
+            {
+                same = false;
+            }
+        });
+    }
+    for (auto& th : pool)
+    {
+        th.join();
+    }
+    return same;
+}
+
+// The query points as the C ABI takes them: nullptr when they are the reference points themselves (no upload, no
+// second cell sort), else the packed floats.  "Themselves" is decided by value, not by address: freud's Python layer
+// keeps a private copy of the points (freud/locality.py:867-868), so nq.query(points, ...) with the array the engine
+// was built from arrives here as a different pointer to the same numbers.
 inline const float* selfOrHost(const NeighborQuery& nq, const vec3<float>* query_points, unsigned int n_query_points)
 {
-    bool const self = query_points == nq.getPoints() && n_query_points == nq.getNPoints();
+    bool const self = n_query_points == nq.getNPoints() && samePoints(query_points, nq.getPoints(), n_query_points);
     return self ? nullptr : reinterpret_cast<const float*>(query_points);
 }
 

@@ -44,7 +44,33 @@ public:
     unsigned int getNP() const { return m_Np; }
     const std::shared_ptr<util::ManagedArray<float>>& getParticleOrder() const { return m_wl ? m_wli : m_qli; }
     const std::shared_ptr<util::ManagedArray<float>>& getQl() const { return m_qli; }
-    const std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>>& getQlm() const { return m_qlmi; }
+    // The per-particle q_lm stay on the device after compute() (104 MB at l = 6, N = 1e6) and cross the link the
+    // first time somebody asks for them: one copy into one page-locked block, the per-l arrays are slices of it.
+    const std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>>& getQlm() const
+    {
+        if (m_qlm_dev)
+        {
+            size_t tot_m = 0;
+            for (unsigned int l : m_ls)
+            {
+                tot_m += 2 * (size_t) l + 1;
+            }
+            size_t const bytes = (size_t) m_Np * tot_m * sizeof(std::complex<float>);
+            auto block = std::make_shared<util::HostBlock>(bytes);
+            gpu::check(fgpu_buffer_read(m_qlm_dev.get(), block->get(), 0, bytes));
+            auto* base = static_cast<std::complex<float>*>(block->get());
+            size_t off = 0;
+            for (size_t r = 0; r < m_ls.size(); ++r)
+            {
+                size_t const nm = 2 * (size_t) m_ls[r] + 1;
+                m_qlmi[r] = std::make_shared<util::ManagedArray<std::complex<float>>>(
+                    block, base + off, std::vector<size_t> {m_Np, nm});
+                off += (size_t) m_Np * nm;
+            }
+            m_qlm_dev.reset();
+        }
+        return m_qlmi;
+    }
     std::vector<float> getOrder() const { return m_norm; }
     bool isAverage() const { return m_average; }
     bool isWl() const { return m_wl; }
@@ -74,31 +100,25 @@ public:
         {
             tot_m += 2 * (size_t) l + 1;
         }
-        auto qli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()});
+        // every element of these is written by the copy that fills them
+        auto qli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()}, util::Uninitialized {});
         std::shared_ptr<util::ManagedArray<float>> wli;
         if (m_wl)
         {
-            wli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()});
+            wli = std::make_shared<util::ManagedArray<float>>(std::vector<size_t> {Np, m_ls.size()}, util::Uninitialized {});
         }
-        std::vector<float> qlm_flat((size_t) Np * tot_m * 2), sys(tot_m * 2);
+        std::vector<float> sys(tot_m * 2);
         std::vector<float> order(m_ls.size());
         int const flags = (m_weighted ? FGPU_ST_WEIGHTED : 0) | (m_average ? FGPU_ST_AVERAGE : 0)
             | (m_wl ? FGPU_ST_WL : 0) | (m_wl_normalize ? FGPU_ST_WL_NORMALIZE : 0);
-        gpu::check(fgpu_steinhardt_compute(points->device(), list->device(gpu::context()), m_ls.data(),
-                                           (uint32_t) m_ls.size(), flags, Np, nullptr, qli->data(),
-                                           wli ? wli->data() : nullptr, qlm_flat.data(), sys.data(), order.data()));
-        size_t off = 0;
-        for (size_t r = 0; r < m_ls.size(); ++r)
+        fgpu_buffer* keep = nullptr;
+        gpu::check(fgpu_steinhardt_compute_keep(points->device(), list->device(gpu::context()), m_ls.data(),
+                                                (uint32_t) m_ls.size(), flags, Np, nullptr, qli->data(),
+                                                wli ? wli->data() : nullptr, &keep, sys.data(), order.data()));
+        m_qlm_dev = std::shared_ptr<fgpu_buffer>(keep, fgpu_buffer_destroy);
+        for (auto& arr : m_qlmi)
         {
-            size_t const nm = 2 * (size_t) m_ls[r] + 1;
-            auto arr = std::make_shared<util::ManagedArray<std::complex<float>>>(std::vector<size_t> {Np, nm});
-            const float* src = qlm_flat.data() + off;
-            for (size_t k = 0; k < (size_t) Np * nm; ++k)
-            {
-                (*arr)[k] = std::complex<float>(src[2 * k], src[2 * k + 1]);
-            }
-            m_qlmi[r] = arr;
-            off += (size_t) Np * nm * 2;
+            arr.reset(); // views handed out earlier keep their own block alive
         }
         m_qli = qli;
         m_wli = wli;
@@ -111,7 +131,8 @@ private:
     bool m_average, m_wl, m_weighted, m_wl_normalize;
     std::shared_ptr<util::ManagedArray<float>> m_qli; // q_l, or the averaged q_l (what getQl() returns upstream)
     std::shared_ptr<util::ManagedArray<float>> m_wli; // w_l when wl is set
-    std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>> m_qlmi;
+    mutable std::vector<std::shared_ptr<util::ManagedArray<std::complex<float>>>> m_qlmi;
+    mutable std::shared_ptr<fgpu_buffer> m_qlm_dev; // q_lm of the last compute(), not yet read
     std::vector<float> m_norm;
 };
 

@@ -66,6 +66,21 @@ PYBIND11_MODULE(_freud_b200, m)
     m.doc() = "C++ host classes of freud_b200 (reference-compatible signatures on the sm_100a C ABI)";
     m.def("version", [] { return std::string(fgpu_version()); });
     m.def("device_count", [] { return fgpu_device_count(); });
+    // The private copy freud's Python layer keeps of the points (freud/locality.py:867-868), taken into a block of the
+    // page-locked host cache: the upload that follows runs at the link's rate instead of through the driver's bounce
+    // buffers.  Writable (N, 3) float32; the block returns to the cache when the array dies.
+    m.def("private_points", [](points_array a) {
+        unsigned int n = 0;
+        const vec3<float>* src = as_vec3(a, n);
+        auto* block = new std::shared_ptr<util::HostBlock>(std::make_shared<util::HostBlock>((size_t) n * 3 * sizeof(float)));
+        py::capsule owner(block, [](void* p) { delete static_cast<std::shared_ptr<util::HostBlock>*>(p); });
+        if (n != 0)
+        {
+            std::memcpy((*block)->get(), src, (size_t) n * 3 * sizeof(float));
+        }
+        return py::array_t<float>({(py::ssize_t) n, (py::ssize_t) 3}, static_cast<const float*>((*block)->get()), owner);
+    });
+    m.def("host_trim", [] { fgpu_host_trim(); });
 
     // ---- _box ------------------------------------------------------------------------------------------
     auto mbox = m.def_submodule("_box");

@@ -37,6 +37,12 @@ def _points(a, name="points"):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _private_points(a):
+    """The engine's own copy of the points (freud/locality.py:867-868), in page-locked memory from the library's host
+    cache so that the upload behind it runs at the link's rate."""
+    return _ext().private_points(_points(a))
+
+
 def _query_args(d):
     """dict -> C++ QueryArgs (freud/locality.py:39-175: unknown keys are an error, mode is a string)."""
     L = _ext()._locality
@@ -151,7 +157,14 @@ class NeighborQuery:
 
     @property
     def points(self):
-        return self._points
+        """Read-only view of the engine's private copy: the device copy is uploaded once, so an in-place edit through
+        this property would silently desynchronise the two (the reference reads the host array on every query)."""
+        ro = getattr(self, "_points_ro", None)
+        if ro is None:
+            ro = self._points.view()
+            ro.setflags(write=False)
+            self._points_ro = ro
+        return ro
 
     def query(self, query_points, query_args):
         return NeighborQueryResult(self, _points(query_points, "query_points"), _query_args(query_args))
@@ -162,7 +175,7 @@ class AABBQuery(NeighborQuery):
 
     def __init__(self, box, points):
         self._box = Box.from_box(box)
-        self._points = _points(points).copy()  # private copy, as upstream (:867-868)
+        self._points = _private_points(points)  # private copy, as upstream (:867-868)
         self._cpp_obj = _ext()._locality.AABBQuery(_cpp_box(self._box), self._points)
 
 
@@ -171,7 +184,7 @@ class CellQuery(NeighborQuery):
 
     def __init__(self, box, points):
         self._box = Box.from_box(box)
-        self._points = _points(points).copy()
+        self._points = _private_points(points)
         self._cpp_obj = _ext()._locality.CellQuery(_cpp_box(self._box), self._points)
 
 
@@ -180,7 +193,7 @@ class LinkCell(NeighborQuery):
 
     def __init__(self, box, points, cell_width=0):
         self._box = Box.from_box(box)
-        self._points = _points(points).copy()
+        self._points = _private_points(points)
         self._cpp_obj = _ext()._locality.LinkCell(_cpp_box(self._box), self._points, float(cell_width))
 
     @property
@@ -193,7 +206,7 @@ class _RawPoints(NeighborQuery):
 
     def __init__(self, box, points):
         self._box = Box.from_box(box)
-        self._points = _points(points).copy()
+        self._points = _private_points(points)
         self._cpp_obj = _ext()._locality.RawPoints(_cpp_box(self._box), self._points)
 
 

@@ -53,6 +53,7 @@ typedef struct fgpu_pmft fgpu_pmft;     /* device-resident PMFTXYZ / PMFTXYT / P
 typedef struct fgpu_bondorder fgpu_bondorder; /* device-resident BondOrder histogram              */
 typedef struct fgpu_corr fgpu_corr;     /* device-resident CorrelationFunction accumulators  */
 typedef struct fgpu_comm fgpu_comm;     /* NCCL communicator (one rank per process / GPU)     */
+typedef struct fgpu_buffer fgpu_buffer; /* a result array left on the device for a later read  */
 
 const char* fgpu_last_error(void);
 /* library + device description, e.g. "freud_b200 0.1 sm_100a NVIDIA B200 148 SMs"; safe without a GPU */
@@ -105,6 +106,12 @@ int fgpu_points_create(fgpu_ctx* ctx, const float* box6, int is2d, const float* 
 /* same, points already resident on the device (n x 3 float32) */
 int fgpu_points_create_dev(fgpu_ctx* ctx, const float* box6, int is2d, const float* points_dev, uint32_t n,
                            fgpu_points** out);
+/* same for a frame every rank of `comm` holds in host memory (one process per GPU, SURVEY.md section 8e: the points
+ * are replicated): rank r uploads rows [r n / W, (r + 1) n / W) only and the ranks exchange their blocks over NVLink
+ * (grouped ncclBroadcast on the context's stream), so the frame crosses PCIe once per node, not once per GPU.
+ * Collective: every rank calls it with the same box, n and point values. */
+int fgpu_points_create_replicated(fgpu_ctx* ctx, fgpu_comm* comm, const float* box6, int is2d, const float* points_host,
+                                  uint32_t n, fgpu_points** out);
 void fgpu_points_destroy(fgpu_points* pts);
 /* Force the cell-list build for search radius r (what the first query would do); exposed so the build can
  * be timed and tested on its own.  out_dims[3] receives the cell grid, may be NULL. */
@@ -197,8 +204,26 @@ int fgpu_rdf_accumulate_dev(fgpu_rdf* rdf, fgpu_points* pts, const float* query_
 int fgpu_rdf_accumulate_nlist(fgpu_rdf* rdf, const fgpu_nlist* nl);
 /* device -> host copy of the raw bin counts (BondHistogramCompute::getBinCounts :74-77) */
 int fgpu_rdf_read(fgpu_rdf* rdf, uint32_t* counts_host);
-/* sum the histograms of all ranks in place: one ncclAllReduce(u32[bins], sum) */
+/* Sum the histograms of all ranks: one ncclAllReduce(u32[bins], sum), OUT OF PLACE -- the
+ * rank's own counts stay as they are, fgpu_rdf_read returns the sum until the next accumulate / reset.  So
+ * accumulate -> allreduce -> read -> accumulate -> allreduce -> read (compute(..., reset=False) over a trajectory
+ * with intermediate reads) never counts a frame twice. */
 int fgpu_rdf_allreduce(fgpu_rdf* rdf, fgpu_comm* comm);
+/* Peer-memory transport for that sum (collective over `comm`, once per RDF; all ranks on one node, <= 8): every rank
+ * allocates a small mailbox, the CUDA IPC handles travel over NCCL, and from then on fgpu_rdf_allreduce /
+ * fgpu_rdf_accumulate_reduce add the rank's counts straight into every rank's mailbox with red.add over NVLink and
+ * wait on the stream until all ranks' counts are in (freud_b200/csrc/peer.cuh) -- no NCCL launch on the data path.
+ * Returns FGPU_OK when attached, 1 when peer access / CUDA IPC is unavailable (the RDF stays on the NCCL route; every
+ * rank gets the same answer).  Destroy the RDF before its communicator. */
+int fgpu_rdf_attach_comm(fgpu_rdf* rdf, fgpu_comm* comm);
+/* 1: reductions of this RDF go through ncclAllReduce, 2: through the peer mailbox */
+int fgpu_rdf_reduce_transport(const fgpu_rdf* rdf);
+/* BASELINE.json configs[3] in one call: self-query accumulation of (sharded, fgpu_points_set_shard) points AND the sum
+ * over the ranks.  With a peer mailbox the search kernel itself is the collective: the block that merges its
+ * histogram last pushes the finished counts to every rank (compute + exchange in one launch), and a one-block wait
+ * kernel closes the epoch.  Afterwards fgpu_rdf_read returns the sum; the rank's own counts are untouched. */
+int fgpu_rdf_accumulate_reduce(fgpu_rdf* rdf, fgpu_points* pts, fgpu_comm* comm, int flavour, float q_r_max,
+                               float q_r_min, int exclude_ii);
 
 /* ---- PMFTXY ----------------------------------------------------------------------------------------------
  * Device half of freud::pmft::PMFTXY (freud/pmft/PMFTXY.cc:25-87): a u32[n_x][n_y] histogram of the bond vectors
@@ -336,6 +361,27 @@ int fgpu_local_density_query(fgpu_points* pts, const float* query_points_host, u
 int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
                             uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
                             float* sys_qlm_host, float* order_host);
+
+/* The same, with the per-particle q_lm (the bulk of the output: 104 MB at l = 6, N = 1e6) left on the device:
+ * *qlm_dev_out owns them until fgpu_buffer_destroy; fgpu_buffer_read copies any byte range out (layout as qlm above).
+ * freud::order::Steinhardt::getQlm() (freud/order/Steinhardt.h:113-117) reads them on first access, so
+ * compute(...).particle_order does not pay for arrays nobody asked for. */
+int fgpu_steinhardt_compute_keep(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                                 uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host,
+                                 fgpu_buffer** qlm_dev_out, float* sys_qlm_host, float* order_host);
+uint64_t fgpu_buffer_bytes(const fgpu_buffer* buf);
+int fgpu_buffer_read(fgpu_buffer* buf, void* host, uint64_t offset_bytes, uint64_t bytes);
+void fgpu_buffer_destroy(fgpu_buffer* buf);
+
+/* ---- page-locked host memory ----------------------------------------------------------------------------
+ * Backing store of util::ManagedArray (freud/util/ManagedArray.h:37-333) in freud_b200/host: blocks are page-locked
+ * (cudaHostAlloc) once and cached by size class, so the arrays of every frame after the first cost no allocation and
+ * device -> host copies into them run at the link's rate.  Without a CUDA device the blocks are ordinary aligned
+ * memory (the container classes stay usable in host-only tests).  fgpu_host_free(NULL) is a no-op; fgpu_host_trim
+ * releases the cache. */
+int fgpu_host_alloc(uint64_t bytes, void** out);
+void fgpu_host_free(void* p);
+int fgpu_host_trim(void);
 
 /* ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
  * NCCL is loaded at run time (libnccl.so.2); unique_id is NCCL's 128-byte ncclUniqueId, produced on rank 0

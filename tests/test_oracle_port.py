@@ -389,6 +389,45 @@ def test_port_matches_compiled_reference(name):
 
 
 @needs_ref
+def test_port_matches_compiled_reference_large():
+    """SURVEY.md section 8c, plan (ii): before the grid-based port may stand in for the (quadratic) reference LinkCell at
+    N = 1e6 it is pinned to the compiled reference at the largest sizes the reference finishes in seconds: AABBQuery at
+    N = 1e5 (r = 3 and r = 5, RDF counts too) and the unmodified LinkCell at N = 2e4, bit for bit."""
+    ref.set_num_threads(0)
+    n = 100_000
+    box, pts = data.make_random_system((n / 0.08) ** (1 / 3), n, seed=3)
+    aq = ref.Query("aabb", box, pts)
+    for r in (3.0, 5.0):
+        a = aq.nlist(pts, mode="ball", r_max=r, exclude_ii=True)
+        b = port.ball_nlist(port.IMAGE, box, False, pts, pts, r, 0.0, True)
+        assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.distances), bits(b.distances))
+        assert np.array_equal(bits(a.vectors), bits(b.vectors))
+        assert np.array_equal(a.segments, b.segments) and np.array_equal(a.counts, b.counts)
+    R = ref.RDF(100, 5.0)
+    R.accumulate(ref.Query("raw", box, pts), pts, mode="ball", r_max=5.0, exclude_ii=True)
+    assert np.array_equal(R.results()["bin_counts"], port.rdf_accumulate(port.IMAGE, box, False, pts, pts, 100, 5.0, 0.0, True))
+    # triclinic at the same size (configs[3]'s tilts)
+    tbox, tpts = data.make_random_system((n / 0.08) ** (1 / 3), n, seed=4, tilt=(0.3, 0.2, 0.1))
+    a = ref.Query("aabb", tbox, tpts).nlist(tpts, mode="ball", r_max=5.0, exclude_ii=True)
+    b = port.ball_nlist(port.IMAGE, tbox, False, tpts, tpts, 5.0, 0.0, True)
+    assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.vectors), bits(b.vectors))
+    # the reference's own LinkCell (deep-copies its cell list per visited cell: N = 2e4 is what finishes in seconds)
+    n = 20_000
+    box, pts = data.make_random_system((n / 0.08) ** (1 / 3), n, seed=5)
+    a = ref.Query("linkcell", box, pts, cell_width=3.0).nlist(pts, mode="ball", r_max=3.0, exclude_ii=True)
+    b = port.ball_nlist(port.WRAP, box, False, pts, pts, 3.0, 0.0, True)
+    assert len(a) > 150_000
+    assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.distances), bits(b.distances))
+    assert np.array_equal(bits(a.vectors), bits(b.vectors)) and np.array_equal(a.segments, b.segments)
+    # 2-D at configs[4]'s density
+    n = 100_000
+    box, pts = data.make_random_system((n / 0.5) ** 0.5, n, is2D=True, seed=6)
+    a = ref.Query("aabb", box, pts, is2d=True).nlist(pts, mode="ball", r_max=5.0, exclude_ii=True)
+    b = port.ball_nlist(port.IMAGE, box, True, pts, pts, 5.0, 0.0, True)
+    assert np.array_equal(a.neighbors, b.neighbors) and np.array_equal(bits(a.vectors), bits(b.vectors))
+
+
+@needs_ref
 def test_reference_reproduces_its_own_constants():
     """The compiled reference itself: Q6 = 0.57452416, W6 = -0.00262604 (tests/test_order_steinhardt.py:17-18)."""
     box, pts = data.make_fcc_system(4)
