@@ -893,10 +893,15 @@ def run_leg(name, args, env, steps, n):
         torch.cuda.synchronize()
 
     # ---- device-resident leg ("value") ----------------------------------------------------------------
+    # The strong-scaling legs (configs[3], configs[4]) are timed WITHOUT the per-kernel event pairs: at 8 GPUs a step is
+    # ~0.17 ms of eight kernels, and two extra event records per kernel are a measurable share of that; their kernel
+    # breakdown comes from a separate short pass right after (same inputs, same stream).  Every other leg keeps the
+    # event pairs inside the timed region.
+    events_in_timed_region = name not in ("rdf4m", "traj2d")
     for _ in range(args.warmup):
         w["step_dev"]()
     barrier()
-    ctx.profile(True)
+    ctx.profile(events_in_timed_region)
     ctx.kernel_time(reset=True)
     launches0 = ctx.launch_count
     events = []
@@ -916,12 +921,29 @@ def run_leg(name, args, env, steps, n):
         t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
     launches = ctx.launch_count - launches0
+    breakdown_steps, breakdown_ms = steps, dev_ms
+    if not events_in_timed_region:
+        breakdown_steps = min(steps, 5)
+        ctx.profile(True)
+        ctx.kernel_time(reset=True)
+        barrier()
+        ev = []
+        for _ in range(breakdown_steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            w["step_dev"]()
+            e1.record(stream)
+            ev.append((e0, e1))
+        barrier()
+        breakdown_ms = sum(a.elapsed_time(b) for a, b in ev)
     ctx.profile(False)
     # dominant kernel over the timed region
     per_kernel = {}
     names = ("cell_prep", "cell_assign", "cell_scatter", "scan", "search_nl", "search_count", "search_fill", "search_rdf_general",
              "search_rdf", "emit_general", "emit", "segments", "knn_emit", "knn_rows", "knn_select", "knn_ylm", "knn",
-             "rdf_distances", "rdf_wait", "steinhardt", "local_density_rows", "local_density", "correlation_rows", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
+             "rdf_distances", "rdf_wait", "rdf_push", "steinhardt", "local_density_rows", "local_density", "correlation_rows", "correlation", "pmftxy", "pmft3_rows", "pmft3", "bond_order", "pmft_add_bins", "pmft_add_hist")
     raw = {nm: ctx.kernel_time(nm) for nm in names}  # prefix match: subtract the longer names
     for nm in names:
         ms, cnt = raw[nm]
@@ -1010,15 +1032,18 @@ def run_leg(name, args, env, steps, n):
         algo = w["algo"].get(kname)
         if algo:
             # w["algo"] holds bytes per step; a kernel launched in several chunks per step moves its share per launch
-            algo = algo * steps / cnt if cnt > steps and w.get("algo_per_step") else algo
+            algo = algo * breakdown_steps / cnt if cnt > breakdown_steps and w.get("algo_per_step") else algo
             achieved = algo / (avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": w.get("traffic", {}).get(kname),
                         "traffic_source": w.get("traffic_source") if w.get("traffic", {}).get(kname) else None,
                         "avg_launch_ms": round(avg_ms, 4),
                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src,
-                        "share_of_step": round(ms / dev_ms, 3),
-                        "kernel_ms_per_step": {k: round(v[0] / steps, 4) for k, v in per_kernel.items()}}
+                        "share_of_step": round(ms / breakdown_ms, 3),
+                        "kernel_ms_per_step": {k: round(v[0] / breakdown_steps, 4) for k, v in per_kernel.items()},
+                        "kernel_events": "inside the timed region" if events_in_timed_region
+                        else f"separate pass of {breakdown_steps} steps after the timed region (the timed steps carry no "
+                             f"per-kernel events)"}
     pipe = w["algo"]["pipeline"] / (ms_per_step * 1e-3) / 1e9
     line = {
         "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps,

@@ -10,6 +10,8 @@
 #include <complex>
 #include <cstring>
 #include <limits>
+#include <nvtx3/nvToolsExt.h>
+
 #include <map>
 #include <memory>
 #include <mutex>
@@ -38,8 +40,17 @@ cudaStream_t& current_stream()
 
 namespace {
 
-template<typename F> int guarded(F&& f)
+// NVTX range around every C-ABI entry point: nvtx3 is header-only and loads the tool's
+// injection library on demand, so the ranges cost nothing unless a profiler is attached.
+struct NvtxRange
 {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+template<typename F> int guarded_named(const char* name, F&& f)
+{
+    NvtxRange const range(name);
     try
     {
         f();
@@ -61,6 +72,8 @@ template<typename F> int guarded(F&& f)
         return FGPU_ERUNTIME;
     }
 }
+// the entry point's own name labels the range
+#define guarded(...) guarded_named(__func__, __VA_ARGS__)
 
 void require(bool cond, int code, const char* msg)
 {
@@ -829,6 +842,10 @@ void fgpu_ctx_destroy(fgpu_ctx* ctx)
         cudaEventDestroy(t.begin);
         cudaEventDestroy(t.end);
     }
+    for (cudaEvent_t e : ctx->event_pool)
+    {
+        cudaEventDestroy(e);
+    }
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_evals);
     cudaFreeHost(ctx->h_scalars);
@@ -930,8 +947,8 @@ int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint
         {
             for (auto& t : ctx->timers)
             {
-                cudaEventDestroy(t.begin);
-                cudaEventDestroy(t.end);
+                ctx->event_pool.push_back(t.begin);
+                ctx->event_pool.push_back(t.end);
             }
             ctx->timers.clear();
         }

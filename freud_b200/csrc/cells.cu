@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "bulk_copy.cuh"
 #include "internal.h"
 
 namespace fgpu {
@@ -34,9 +35,12 @@ enum : unsigned long long
     kFlagPrefix = 2ULL << 32
 };
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restrict__ data, size_t n,
+// The scanned array may be two physical pieces, `head` (split elements, a multiple of 8) followed by `data`: a slab of
+// cell layers that wraps around the periodic boundary is one logical run.
+__global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restrict__ data_in, size_t n,
                                                                volatile unsigned long long* state,
-                                                               unsigned int* ticket, const uint32_t* init)
+                                                               unsigned int* ticket, uint32_t* __restrict__ head,
+                                                               size_t split)
 {
     __shared__ uint32_t warp_sums[kScanThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
@@ -47,7 +51,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restr
     }
     __syncthreads();
     uint32_t const tile = s_tile;
-    size_t const base = (size_t) tile * kScanTile + (size_t) threadIdx.x * kScanItems;
+    // logical index of this thread's first item -> piece and local index (split is a multiple of kScanItems: a
+    // thread's items never straddle the pieces); from here on `n` is the length of that piece
+    size_t const logical = (size_t) tile * kScanTile + (size_t) threadIdx.x * kScanItems;
+    bool const in_head = logical < split;
+    uint32_t* const data = in_head ? head : data_in;
+    size_t const base = in_head ? logical : logical - split;
+    n = in_head ? split : n - split;
     uint32_t v[kScanItems];
     if (base + kScanItems <= n)
     {
@@ -105,10 +115,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restr
         uint32_t prefix = 0;
         if (tile == 0)
         {
-            prefix = init != nullptr ? *init : 0U; // the scan continues another one (sharded build: second cell range)
             if (lane == 0)
             {
-                state[0] = kFlagPrefix | (uint32_t) (prefix + total);
+                state[0] = kFlagPrefix | total;
             }
         }
         else
@@ -222,8 +231,9 @@ __global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy,
 // K0: everything the build needs zeroed, in one launch instead of four memsets (launch gaps are a visible share of a
 // sharded step): the cell counters (two ranges: a sharded rank only zeroes, scans and reads the cells of its slab),
 // the scan's tile states + tickets, the out-of-box flag and the slab counter.
-__global__ void __launch_bounds__(256) k_cell_prep(uint32_t* __restrict__ cell_count, size_t a0, size_t a1, size_t b0,
-                                                   size_t b1, uint32_t* __restrict__ scan_words, uint32_t n_scan,
+__global__ void __launch_bounds__(256) k_cell_prep(uint32_t* __restrict__ cell_count, uint32_t* __restrict__ cell_fill,
+                                                   size_t a0, size_t a1, size_t b0, size_t b1,
+                                                   uint32_t* __restrict__ scan_words, uint32_t n_scan,
                                                    int* __restrict__ any_shift, uint32_t* __restrict__ slab_count)
 {
     size_t const stride = (size_t) gridDim.x * blockDim.x;
@@ -231,10 +241,18 @@ __global__ void __launch_bounds__(256) k_cell_prep(uint32_t* __restrict__ cell_c
     for (size_t i = a0 + t; i < a1; i += stride)
     {
         cell_count[i] = 0U;
+        if (cell_fill != nullptr)
+        {
+            cell_fill[i] = 0U;
+        }
     }
     for (size_t i = b0 + t; i < b1; i += stride)
     {
         cell_count[i] = 0U;
+        if (cell_fill != nullptr)
+        {
+            cell_fill[i] = 0U;
+        }
     }
     for (size_t i = t; i < n_scan; i += stride)
     {
@@ -250,121 +268,161 @@ __global__ void __launch_bounds__(256) k_cell_prep(uint32_t* __restrict__ cell_c
     }
 }
 
-// K1 for a sharded rank: one pass over ALL points (the input is replicated), but only the points of this rank's slab
-// leave a trace -- {x, y, z, index} + {cell, arrival rank} appended to a compact list, one global atomic per block --
-// so the scatter and everything after it touch the slab only (the build must not stay serial;
-// at 8 ranks the slab holds ~1/6 of the points).  Four points per thread as three 16-byte loads; the slab test needs
-// the z (2-D: y) fraction only, taken with a reciprocal, and a point within 1e-4 of a layer or box boundary is
-// settled by the exact arithmetic of cell_coords, which every accepted point goes through anyway.
+// K1 for a sharded rank: one streaming pass over ALL points (the input is replicated), of which only the points of
+// this rank's slab leave a trace (the build must not stay serial; at 8 ranks the slab holds
+// ~1/6 of the points).  Persistent blocks; the points arrive in 12 KB chunks through cp.async.bulk into a two-stage
+// shared-memory ring (bulk_copy.cuh): the copy engine keeps a chunk per block in flight while the block works on the
+// previous one -- the first two versions of this kernel, load-then-process per block, were latency-bound at 1.5 TB/s
+// (32 us for 48 MB; profiles/launches_r2_shard.csv).  Per chunk: a cheap slab test on every point (the z fraction
+// -- 2-D: y -- through a reciprocal; anything within 1e-2 of a layer face or 1e-4 of a box face is left undecided),
+// survivors to a shared list, then the exact cell arithmetic of cell_coords (three IEEE divisions) on that list only,
+// on dense lanes.  Nothing here waits for a global atomic: the cell counters are bumped with RED, the list of
+// {position, cell} goes to a fixed window per chunk, and the arrival rank inside the cell is taken by the scatter.
 constexpr int kSlabThreads = 256;
-constexpr int kSlabPointsPerBlock = kSlabThreads * 4;
+constexpr int kSlabChunk = 1024; // points per chunk: 12288 bytes
 
 __global__ void __launch_bounds__(kSlabThreads) k_cell_assign_slab(BoxDev box, int dx, int dy, int dz,
                                                                    const float* __restrict__ xyz, uint32_t n,
                                                                    uint32_t* __restrict__ cell_count,
                                                                    int* __restrict__ any_shift, SlabDev slab,
-                                                                   float4* __restrict__ slab_pos,
-                                                                   uint2* __restrict__ slab_cr,
-                                                                   uint32_t* __restrict__ slab_count)
+                                                                   float4* __restrict__ list_pos,
+                                                                   uint32_t* __restrict__ list_cell,
+                                                                   uint32_t* __restrict__ chunk_count)
 {
-    __shared__ float4 s_pos[kSlabPointsPerBlock];
-    __shared__ uint2 s_cr[kSlabPointsPerBlock];
-    __shared__ uint32_t s_n, s_base;
+    __shared__ __align__(128) float s_raw[2][kSlabChunk * 3];
+    __shared__ float4 s_pos[kSlabChunk];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_maybe;
+    uint32_t const n_chunks = (n + kSlabChunk - 1) / kSlabChunk;
+    auto chunk_points = [&](uint32_t c) { return min((uint32_t) kSlabChunk, n - c * kSlabChunk); };
+    // only whole 16-byte multiples go through the copy engine (every chunk but possibly the last)
+    auto issue = [&](uint32_t c, int stage) {
+        uint32_t const bytes = chunk_points(c) * 12U;
+        if (bytes % 16U == 0)
+        {
+            bulk::mbar_arrive_expect_tx(&s_bar[stage], bytes);
+            bulk::copy_g2s(s_raw[stage], xyz + 3 * (size_t) c * kSlabChunk, bytes, &s_bar[stage]);
+        }
+    };
     if (threadIdx.x == 0)
     {
-        s_n = 0;
+        bulk::mbar_init(&s_bar[0], 1);
+        bulk::mbar_init(&s_bar[1], 1);
+        bulk::fence_barrier_init();
     }
     __syncthreads();
-    uint32_t const i0 = (blockIdx.x * kSlabThreads + threadIdx.x) * 4U;
-    float v[12];
-    if (i0 + 4 <= n)
+    if (threadIdx.x == 0 && blockIdx.x < n_chunks)
     {
-        const float4* src = reinterpret_cast<const float4*>(xyz + 3 * (size_t) i0); // 48-byte aligned
-        float4 const a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-        v[8] = c.x, v[9] = c.y, v[10] = c.z, v[11] = c.w;
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-        {
-            size_t const e = 3 * (size_t) i0 + k;
-            v[k] = e < 3 * (size_t) n ? xyz[e] : 0.0f;
-        }
+        issue(blockIdx.x, 0);
     }
     int const d = slab.axis == 2 ? dz : dy;
     float const rcp_lx = 1.0f / box.Lx, rcp_ly = 1.0f / box.Ly, rcp_lz = box.is2d ? 0.0f : 1.0f / box.Lz;
     float const fd = (float) d;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
+    uint32_t it = 0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it)
     {
-        uint32_t const i = i0 + k;
-        if (i >= n)
+        int const stage = (int) (it & 1U);
+        uint32_t const here = chunk_points(c);
+        if (threadIdx.x == 0)
         {
-            break;
+            s_maybe = 0;
+            uint32_t const next = c + gridDim.x;
+            if (next < n_chunks)
+            {
+                issue(next, stage ^ 1); // that buffer was released by the barrier that ended the previous iteration
+            }
         }
-        float const x = v[3 * k], y = v[3 * k + 1], z = v[3 * k + 2];
-        // approximate fractions (the arithmetic of fractional_for_cells with the divisions replaced)
-        float const gz = box.is2d ? 0.5f : (z - box.loz) * rcp_lz;
-        float const gy = ((y - box.loy) - box.yz * z) * rcp_ly;
-        float const gx = ((x - box.lox) - (box.t_xz * z + box.xy * y)) * rcp_lx;
-        bool const well_inside = gx > 1e-4f && gx < 0.9999f && gy > 1e-4f && gy < 0.9999f
-            && (box.is2d || (gz > 1e-4f && gz < 0.9999f));
-        float const gs = (slab.axis == 2 ? gz : gy) * fd; // layer coordinate
-        float const frac_layer = gs - floorf(gs);
-        bool decided = well_inside && frac_layer > 1e-2f && frac_layer < 0.99f;
-        bool mine = false;
-        if (decided)
+        if ((here * 12U) % 16U == 0)
         {
-            int rel = (int) gs - slab.lo;
-            rel += rel < 0 ? d : 0;
-            mine = rel < slab.len;
+            bulk::mbar_wait(&s_bar[stage], (it >> 1) & 1U);
         }
-        if (!decided || mine)
+        else
         {
+            for (uint32_t e = threadIdx.x; e < 3 * here; e += kSlabThreads)
+            {
+                s_raw[stage][e] = xyz[3 * (size_t) c * kSlabChunk + e];
+            }
+        }
+        __syncthreads();
+        const float* raw = s_raw[stage];
+        for (uint32_t k = threadIdx.x; k < here; k += kSlabThreads)
+        {
+            float const x = raw[3 * k], y = raw[3 * k + 1], z = raw[3 * k + 2];
+            // approximate fractions (the arithmetic of fractional_for_cells with the divisions replaced)
+            float const gz = box.is2d ? 0.5f : (z - box.loz) * rcp_lz;
+            float const gy = ((y - box.loy) - box.yz * z) * rcp_ly;
+            float const gx = ((x - box.lox) - (box.t_xz * z + box.xy * y)) * rcp_lx;
+            bool const well_inside = gx > 1e-4f && gx < 0.9999f && gy > 1e-4f && gy < 0.9999f
+                && (box.is2d || (gz > 1e-4f && gz < 0.9999f));
+            float const gs = (slab.axis == 2 ? gz : gy) * fd; // layer coordinate
+            float const frac_layer = gs - floorf(gs);
+            bool maybe = true; // near a box face or a layer face: the exact arithmetic decides
+            if (well_inside && frac_layer > 1e-2f && frac_layer < 0.99f)
+            {
+                int rel = (int) gs - slab.lo;
+                rel += rel < 0 ? d : 0;
+                maybe = rel < slab.len;
+            }
+            if (maybe)
+            {
+                s_pos[atomicAdd(&s_maybe, 1U)] = make_float4(x, y, z, __uint_as_float(c * kSlabChunk + k));
+            }
+        }
+        __syncthreads();
+        uint32_t const n_maybe = s_maybe;
+        size_t const window = (size_t) c * kSlabChunk;
+        for (uint32_t k = threadIdx.x; k < n_maybe; k += kSlabThreads)
+        {
+            float4 const p = s_pos[k];
             int cx, cy, cz, nx, ny, nz;
-            cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+            cell_coords(box, dx, dy, dz, p.x, p.y, p.z, cx, cy, cz, nx, ny, nz);
             if ((nx | ny | nz) != 0)
             {
                 *any_shift = 1;
             }
             int rel = (slab.axis == 2 ? cz : cy) - slab.lo;
             rel += rel < 0 ? d : 0;
+            uint32_t cell = 0xffffffffU;
             if (rel < slab.len)
             {
-                uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
-                uint32_t const pos = atomicAdd(&s_n, 1U);
-                s_pos[pos] = make_float4(x, y, z, __uint_as_float(i));
-                s_cr[pos] = make_uint2(c, atomicAdd(&cell_count[c], 1U));
+                cell = ((uint32_t) cz * dy + cy) * dx + cx;
+                atomicAdd(&cell_count[cell], 1U); // result unused: a RED, nobody waits for it
             }
+            list_pos[window + k] = p;
+            list_cell[window + k] = cell;
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_n != 0)
-    {
-        s_base = atomicAdd(slab_count, s_n);
-    }
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < s_n; k += blockDim.x)
-    {
-        slab_pos[s_base + k] = s_pos[k];
-        slab_cr[s_base + k] = s_cr[k];
+        if (threadIdx.x == 0)
+        {
+            chunk_count[c] = n_maybe;
+            bulk::fence_proxy_async(); // this block's reads of s_raw[stage] come before the engine's next write to it
+        }
+        __syncthreads();
     }
 }
 
-// K3 for a sharded rank: the compact list only, read in order
-__global__ void __launch_bounds__(256) k_cell_scatter_slab(const float4* __restrict__ slab_pos,
-                                                           const uint2* __restrict__ slab_cr,
-                                                           const uint32_t* __restrict__ slab_count,
+// K3 for a sharded rank: the chunk windows of the list; the arrival rank inside a cell is taken here, where every
+// thread is independent and the atomic's latency hides behind the other warps
+__global__ void __launch_bounds__(256) k_cell_scatter_slab(const float4* __restrict__ list_pos,
+                                                           const uint32_t* __restrict__ list_cell,
+                                                           const uint32_t* __restrict__ chunk_count, uint32_t n_chunks,
                                                            const uint32_t* __restrict__ cell_start,
-                                                           float4* __restrict__ sorted)
+                                                           uint32_t* __restrict__ cell_fill, float4* __restrict__ sorted)
 {
-    uint32_t const n = *slab_count;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    // a block per chunk: its entries are the first chunk_count[c] of the chunk's window, one per thread, so that all
+    // of a chunk's atomics are in flight at once (a warp walking its chunk serially was latency-bound: 17 us)
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
     {
-        uint2 const cr = slab_cr[k];
-        sorted[__ldg(cell_start + cr.x) + cr.y] = slab_pos[k];
+        uint32_t const cnt = __ldg(chunk_count + c);
+        size_t const window = (size_t) c * kSlabChunk;
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+        {
+            uint32_t const cell = list_cell[window + k];
+            if (cell != 0xffffffffU)
+            {
+                uint32_t const slot = __ldg(cell_start + cell) + atomicAdd(&cell_fill[cell], 1U);
+                sorted[slot] = list_pos[window + k];
+            }
+        }
     }
 }
 
@@ -455,8 +513,7 @@ size_t scan_scratch_words(size_t n)
     return 2 * tiles + 2; // one {flag, value} word per tile + the tile ticket
 }
 
-void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero, const uint32_t* init,
-                        size_t scratch_offset)
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero, uint32_t* head, size_t split)
 {
     if (n == 0)
     {
@@ -472,11 +529,15 @@ void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is
         ctx->scan_tmp.reserve(scan_scratch_words(n));
         FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->scan_tmp.ptr, 0, scan_scratch_words(n) * sizeof(uint32_t), ctx->stream));
     }
-    auto* state = reinterpret_cast<unsigned long long*>(ctx->scan_tmp.ptr + scratch_offset);
-    auto* ticket = reinterpret_cast<unsigned int*>(ctx->scan_tmp.ptr + scratch_offset + 2 * tiles);
+    if (split % kScanItems != 0 || (split != 0 && (reinterpret_cast<uintptr_t>(head) & 15U) != 0))
+    {
+        throw Error(FGPU_ERUNTIME, "exclusive_scan_u32: the head piece must be 16-byte aligned and a multiple of 8 long");
+    }
+    auto* state = reinterpret_cast<unsigned long long*>(ctx->scan_tmp.ptr);
+    auto* ticket = reinterpret_cast<unsigned int*>(ctx->scan_tmp.ptr + 2 * tiles);
     {
         KernelScope ks(ctx, "scan");
-        k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket, init);
+        k_scan_chained<<<(unsigned) tiles, kScanThreads, 0, ctx->stream>>>(data, n, state, ticket, head, split);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
@@ -598,44 +659,56 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
             rb1 = (size_t) (hi - layers) * per_layer + 1;
         }
     }
-    // 16-byte alignment of the scanned ranges (the scan reads uint4): grow them downwards
+    // 16-byte alignment of the scanned pieces (the scan reads uint4): the high range grows downwards, the low one
+    // (scanned first, as the head of one logical run) is padded to a multiple of 8 elements -- the extra cells belong
+    // to layers outside the slab, stay empty and are never read
     ra0 &= ~(size_t) 3;
-    size_t const words_a = scan_scratch_words(ra1 - ra0), words_b = rb1 > rb0 ? scan_scratch_words(rb1 - rb0) : 0;
-    ctx->scan_tmp.reserve(words_a + words_b);
+    if (rb1 > rb0)
+    {
+        rb1 = std::min<size_t>((rb1 + 7) & ~(size_t) 7, ra0);
+        if ((rb1 & 7) != 0)
+        {
+            throw Error(FGPU_ERUNTIME, "sharded cell list: the slab leaves no room between its two cell ranges");
+        }
+    }
+    size_t const scan_n = (ra1 - ra0) + (rb1 - rb0);
+    size_t const scan_words = scan_scratch_words(scan_n);
+    ctx->scan_tmp.reserve(scan_words);
     {
         KernelScope ks(ctx, "cell_prep");
-        size_t const work = (ra1 - ra0) + (rb1 - rb0);
-        unsigned const pblocks = (unsigned) std::min<size_t>((work + 255) / 256, (size_t) ctx->sm_count * 8);
-        k_cell_prep<<<std::max(pblocks, 1U), 256, 0, ctx->stream>>>(g.cell_start.ptr, ra0, ra1, rb0, rb1, ctx->scan_tmp.ptr,
-                                                                   (uint32_t) (words_a + words_b), d_flag, d_slab_count);
+        unsigned const pblocks = (unsigned) std::min<size_t>((scan_n + 255) / 256, (size_t) ctx->sm_count * 8);
+        if (slab_only)
+        {
+            g.rank_in.reserve((size_t) n_cells + 4); // sharded build: the per-cell fill cursor of the scatter
+        }
+        k_cell_prep<<<std::max(pblocks, 1U), 256, 0, ctx->stream>>>(g.cell_start.ptr, slab_only ? g.rank_in.ptr : nullptr,
+                                                                   ra0, ra1, rb0, rb1, ctx->scan_tmp.ptr,
+                                                                   (uint32_t) scan_words, d_flag, d_slab_count);
     }
     unsigned const blocks = (n + 255) / 256;
     if (slab_only)
     {
-        // the list is sized for all n points (clustered systems); only its first *d_slab_count entries are touched
-        g.slab_pos.reserve(n);
-        g.cell_of.reserve((size_t) n * 2); // reused as the {cell, arrival rank} list
+        // the list has a window of kSlabChunk entries per chunk of points (sized for clustered systems: every point of
+        // a chunk may belong to the slab); only the first chunk_count[c] entries of a window are ever touched
+        uint32_t const n_chunks = (n + kSlabChunk - 1) / kSlabChunk;
+        g.slab_pos.reserve((size_t) n_chunks * kSlabChunk);
+        g.cell_of.reserve((size_t) n_chunks * kSlabChunk + n_chunks); // {cell} per list entry, then the chunk counts
+        uint32_t* const chunk_count = g.cell_of.ptr + (size_t) n_chunks * kSlabChunk;
         {
             KernelScope ks(ctx, "cell_assign");
-            k_cell_assign_slab<<<(n + kSlabPointsPerBlock - 1) / kSlabPointsPerBlock, kSlabThreads, 0, ctx->stream>>>(
-                pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_start.ptr, d_flag, slab, g.slab_pos.ptr,
-                reinterpret_cast<uint2*>(g.cell_of.ptr), d_slab_count);
+            unsigned const ablocks = std::min<unsigned>(n_chunks, (unsigned) ctx->sm_count * 5U);
+            k_cell_assign_slab<<<ablocks, kSlabThreads, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
+                                                                         g.cell_start.ptr, d_flag, slab, g.slab_pos.ptr,
+                                                                         g.cell_of.ptr, chunk_count);
         }
-        if (rb1 > rb0)
-        {
-            // wrapped slab: the low range first, the high range continues at its total
-            exclusive_scan_u32(ctx, g.cell_start.ptr + rb0, rb1 - rb0, true, nullptr, words_a);
-            exclusive_scan_u32(ctx, g.cell_start.ptr + ra0, ra1 - ra0, true, g.cell_start.ptr + rb1 - 1, 0);
-        }
-        else
-        {
-            exclusive_scan_u32(ctx, g.cell_start.ptr + ra0, ra1 - ra0, true, nullptr, 0);
-        }
+        // one scan over the slab's cells: a wrapped slab is the low range followed by the high one
+        exclusive_scan_u32(ctx, g.cell_start.ptr + ra0, scan_n, true, g.cell_start.ptr + rb0, rb1 - rb0);
         {
             KernelScope ks(ctx, "cell_scatter");
-            k_cell_scatter_slab<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
-                g.slab_pos.ptr, reinterpret_cast<const uint2*>(g.cell_of.ptr), d_slab_count, g.cell_start.ptr,
-                g.sorted.ptr);
+            unsigned const sblocks = std::min<unsigned>(n_chunks, (unsigned) ctx->sm_count * 32U);
+            k_cell_scatter_slab<<<std::max(sblocks, 1U), 256, 0, ctx->stream>>>(g.slab_pos.ptr, g.cell_of.ptr, chunk_count,
+                                                                                n_chunks, g.cell_start.ptr, g.rank_in.ptr,
+                                                                                g.sorted.ptr);
         }
         g.cell_of_valid = false;
     }

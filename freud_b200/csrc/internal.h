@@ -153,6 +153,7 @@ struct fgpu_ctx
     };
     bool profile = false;
     std::vector<TimerRec> timers;
+    std::vector<cudaEvent_t> event_pool; // events of cleared timers, reused (cudaEventCreate costs more than a launch)
 };
 
 namespace fgpu {
@@ -167,8 +168,8 @@ struct KernelScope
         ctx->launches += 1;
         if (ctx->profile)
         {
-            cudaEventCreate(&begin);
-            cudaEventCreate(&end);
+            begin = take(ctx);
+            end = take(ctx);
             cudaEventRecord(begin, ctx->stream);
         }
     }
@@ -179,6 +180,20 @@ struct KernelScope
             cudaEventRecord(end, ctx->stream);
             ctx->timers.push_back({name, begin, end});
         }
+    }
+    static cudaEvent_t take(fgpu_ctx* c)
+    {
+        cudaEvent_t e = nullptr;
+        if (!c->event_pool.empty())
+        {
+            e = c->event_pool.back();
+            c->event_pool.pop_back();
+        }
+        else
+        {
+            cudaEventCreate(&e);
+        }
+        return e;
     }
 };
 } // namespace fgpu
@@ -350,9 +365,10 @@ struct SearchArgs
 };
 
 // in place, n elements; scratch_is_zero: ctx->scan_tmp (scan_scratch_words(n) words) was zeroed by the caller's kernel
-// init: device pointer to the value the scan starts from (nullptr: 0); scratch_offset: words into ctx->scan_tmp
-void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero = false, const uint32_t* init = nullptr,
-                        size_t scratch_offset = 0);
+// head / split: the n logical elements are `split` elements at `head` (16-byte aligned, a multiple of 8 long)
+// followed by n - split elements at `data`
+void exclusive_scan_u32(fgpu_ctx* ctx, uint32_t* data, size_t n, bool scratch_is_zero = false, uint32_t* head = nullptr,
+                        size_t split = 0);
 size_t scan_scratch_words(size_t n);
 void build_grid(fgpu_points* pts, float r_search, bool force_single_cell = false);
 void launch_check_2d_z(fgpu_ctx* ctx, const float* xyz, uint32_t n, int* flag); // *flag = 1 if some |z| > 1e-6

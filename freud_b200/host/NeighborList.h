@@ -118,7 +118,9 @@ public:
         {
             return;
         }
-        bool const from_device = m_dev && !m_host_valid;
+        // a list that came from a query still has its device twin (reorder() drops it): the kernels already wrote
+        // counts and segments, empty rows 0 as upstream
+        bool const from_device = (bool) m_dev;
         m_counts = from_device ? make_raw<unsigned int>({m_num_query_points}) : make<unsigned int>({m_num_query_points});
         m_segments = from_device ? make_raw<unsigned int>({m_num_query_points}) : make<unsigned int>({m_num_query_points});
         if (from_device)

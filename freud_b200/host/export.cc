@@ -8,6 +8,8 @@
 // base object keeps the owning ManagedArray alive, C++ exceptions surface as ValueError / RuntimeError /
 // IndexError.  Submodules are named after the reference's extension modules (_box, _locality, _density,
 // _order) so that freud's Python layer maps onto them one to one.
+#include <thread>
+
 #include <pybind11/complex.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -74,9 +76,30 @@ PYBIND11_MODULE(_freud_b200, m)
         const vec3<float>* src = as_vec3(a, n);
         auto* block = new std::shared_ptr<util::HostBlock>(std::make_shared<util::HostBlock>((size_t) n * 3 * sizeof(float)));
         py::capsule owner(block, [](void* p) { delete static_cast<std::shared_ptr<util::HostBlock>*>(p); });
-        if (n != 0)
+        size_t const bytes = (size_t) n * 3 * sizeof(float);
+        if (bytes >= (4U << 20))
         {
-            std::memcpy((*block)->get(), src, (size_t) n * 3 * sizeof(float));
+            // a 12 MB memcpy on one core costs more than the upload it precedes
+            py::gil_scoped_release release;
+            std::vector<std::thread> pool;
+            unsigned int const n_threads = 4;
+            size_t const chunk = (bytes / n_threads + 63) & ~(size_t) 63;
+            for (unsigned int t = 0; t < n_threads; ++t)
+            {
+                size_t const lo = std::min(bytes, (size_t) t * chunk), hi = t + 1 == n_threads ? bytes : std::min(bytes, lo + chunk);
+                pool.emplace_back([=] {
+                    std::memcpy(static_cast<unsigned char*>((*block)->get()) + lo,
+                                reinterpret_cast<const unsigned char*>(src) + lo, hi - lo);
+                });
+            }
+            for (auto& th : pool)
+            {
+                th.join();
+            }
+        }
+        else if (n != 0)
+        {
+            std::memcpy((*block)->get(), src, bytes);
         }
         return py::array_t<float>({(py::ssize_t) n, (py::ssize_t) 3}, static_cast<const float*>((*block)->get()), owner);
     });
