@@ -680,12 +680,25 @@ def _bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
+def oracle_threads(n=None):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the oracle's OpenMP loops (oracle/port.c) are the checker here,
+    not the thing measured, and get the host's cores back for the duration of a check."""
+    import ctypes
+
+    n = n or os.cpu_count() or 1
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def parity_nl(w, flavour):
     """All five NeighborList arrays + segments / counts of the benchmark's own frame, bit for bit against the oracle's
     restatement of LinkCell / AABBQuery (oracle/port.c: grid + exact per-pair arithmetic; pinned to the compiled
     reference in tests/test_oracle_port.py)."""
     from oracle import port
 
+    oracle_threads()
     t0 = time.perf_counter()
     got = w["dp"].ball_query(None, flavour, w["r_max"], 0.0, True).to_host()
     want = port.ball_nlist(port.WRAP if flavour == WRAP else port.IMAGE, w["box"], w["box"].is2D, w["pts"], w["pts"],
@@ -701,6 +714,7 @@ def parity_rdf_counts(got, w, bins, frames=None):
     leg's own frame)."""
     from oracle import port
 
+    oracle_threads()
     t0 = time.perf_counter()
     want = np.zeros(bins, np.uint32)
     for box, pts in (frames or [(w["box"], w["pts"])]):
@@ -1009,14 +1023,21 @@ def run_leg(name, args, env, steps, n):
                 if rank == 0:
                     parity = parity_rdf_counts(got, w, w["bins"])
             elif name == "traj2d":
-                got = w["rank_counts"]()  # this rank's own frames, before any reduction
-                mine = parity_rdf_counts(got, w, w["bins"], frames=w["frames"])
-                flag = torch.tensor([1.0 if mine["bitwise_equal"] else 0.0], dtype=torch.float64, device="cuda")
+                # (a) rank 0's own frames against the oracle (the host's cores go to one check, not to `world` of them);
+                # (b) the reduced histogram of the step against the sum of every rank's own histogram, all on the GPU
+                mine = w["rank_counts"]()  # this rank's own frames, before any reduction
+                t = torch.from_numpy(mine.astype(np.int64)).cuda()
                 if world > 1:
-                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                mine["bitwise_equal"] = bool(flag.item() == 1.0)
-                mine["scope"] = f"every rank checks the histogram of its own {len(w['frames'])} frames before the reduction; min over ranks"
-                parity = mine
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                w["step_dev"]()
+                reduced = w["rdf"].read()
+                sums_agree = bool(np.array_equal(reduced, (t.cpu().numpy() & 0xFFFFFFFF).astype(np.uint32)))
+                if rank == 0:
+                    parity = parity_rdf_counts(mine, w, w["bins"], frames=w["frames"])
+                    parity["reduced_equals_sum_of_rank_histograms"] = sums_agree
+                    parity["bitwise_equal"] = parity["bitwise_equal"] and sums_agree
+                    parity["scope"] = (f"rank 0's {len(w['frames'])} frames against the oracle; the step's reduced histogram "
+                                       f"against the sum of all {world} ranks' own histograms")
         except Exception as exc:  # a failed check is reported, never hidden
             parity = {"bitwise_equal": False, "error": f"{type(exc).__name__}: {exc}"}
 
