@@ -37,6 +37,7 @@ SIGNATURES = {
     "fgpu_ctx_count_pair_evals": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_pair_evals": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "fgpu_ctx_force_general_search": (C.c_int, [_vp, C.c_int]),
+    "fgpu_ctx_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "fgpu_ctx_profile": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_kernel_time": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
@@ -222,6 +223,10 @@ class Context:
 
     def force_general_search(self, enable=True):
         check(lib().fgpu_ctx_force_general_search(self._h, int(enable)))
+
+    def set_tuning(self, key, value):
+        """Experiment / test hook (``fgpu_ctx_set_tuning``): "span", "no_symmetry", "lanes_over_queries"."""
+        check(lib().fgpu_ctx_set_tuning(self._h, key.encode(), int(value)))
 
     def profile(self, enable=True):
         check(lib().fgpu_ctx_profile(self._h, int(enable)))

@@ -284,7 +284,7 @@ Search2Args base_search2_args(fgpu_points* pts, const QueryView& qv, uint32_t q_
     double const E = 16.0 * 5.9604644775390625e-08 * ext;
     double const r_hi = (double) r_max + 4.0 * E;
     a.r_hi_sq = std::nextafter((float) (r_hi * r_hi * (1.0 + 1.0e-6)), INFINITY);
-    search2_plan(a, pts->n);
+    search2_plan(a, pts->n, ctx->tune_span);
     a.out_cap = search2_out_cap((pts->box.is2d ? 3.0 : 9.0) * (a.span + 2) * (double) pts->n
                                 / (double) std::max(g.n_cells, 1U));
     a.fail = reinterpret_cast<int*>(ctx->d_scalars + 4);
@@ -292,6 +292,15 @@ Search2Args base_search2_args(fgpu_points* pts, const QueryView& qv, uint32_t q_
     a.work_counter = reinterpret_cast<unsigned int*>(ctx->d_scalars + 6);
     a.evals = ctx->count_evals ? ctx->d_evals : nullptr;
     return a;
+}
+
+// bonds a query point expects at the mean density: what sizes the hit buffers and picks the search's mapping
+double expected_hits_per_query(const fgpu_points* pts, float r_window)
+{
+    double const vol = box_volume(pts->box);
+    double const shell = pts->box.is2d ? M_PI * (double) r_window * r_window
+                                       : 4.0 / 3.0 * M_PI * (double) r_window * r_window * r_window;
+    return vol > 0 ? (double) pts->n / vol * shell : 0.0;
 }
 
 std::unique_ptr<fgpu_nlist> new_nlist(fgpu_ctx* ctx, uint32_t n_query, uint32_t n_points)
@@ -358,6 +367,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     // ---- production path: warp-cooperative single-pass search into a bag, then ranked emit ----------------
     bool fast_counted_evals = false;
     Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_max, r_min, exclude_ii);
+    search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_max), ctx->tune_lanes_over_queries);
     if (!ctx->force_general && search2_supported(s2, S2_NL))
     {
         // Capacities of the bag and of the output arrays: the previous query's bond count if there was one, else
@@ -498,6 +508,7 @@ bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int 
     build_grid(pts, r_max);
     QueryView const qv = prepare_queries(pts, q_host, nullptr, n_query);
     Search2Args s2 = base_search2_args(pts, qv, 0, r_max, r_min, exclude_ii);
+    search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_max), ctx->tune_lanes_over_queries);
     if (!search2_supported(s2, S2_NL))
     {
         return false;
@@ -574,7 +585,7 @@ bool rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
     // Queries are the points themselves and no image vector is involved in most pairs: r_ij and r_ji are exact
     // negatives there, so one test stands for both bonds (IMAGE arithmetic only: Box::wrap is not odd in floating
     // point).  The self pair (i, i) lies in the tile's own row, which is always walked in full.
-    s2.symmetric = self && q_index_offset == 0 && flavour == FGPU_FLAVOUR_IMAGE && std::getenv("FGPU_NO_SYMMETRY") == nullptr;
+    s2.symmetric = self && q_index_offset == 0 && flavour == FGPU_FLAVOUR_IMAGE && ctx->tune_no_symmetry == 0;
     bool const fast = !ctx->force_general && search2_supported(s2, S2_RDF);
     if (sharded)
     {
@@ -796,8 +807,6 @@ int fgpu_ctx_create(int device, fgpu_ctx** out)
         FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_evals, 0, sizeof(unsigned long long), ctx->stream));
         FGPU_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 8 * sizeof(unsigned long long)));
         FGPU_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        const char* env = std::getenv("FGPU_SEARCH");
-        ctx->force_general = env != nullptr && std::strcmp(env, "general") == 0;
         *out = ctx.release();
     });
 }
@@ -905,6 +914,30 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable)
     return guarded([&] {
         require(ctx != nullptr, FGPU_EINVALID, "null argument");
         ctx->force_general = enable != 0;
+    });
+}
+
+int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value)
+{
+    return guarded([&] {
+        require(ctx != nullptr && key != nullptr, FGPU_EINVALID, "null argument");
+        std::string const k(key);
+        if (k == "span")
+        {
+            ctx->tune_span = value;
+        }
+        else if (k == "no_symmetry")
+        {
+            ctx->tune_no_symmetry = value;
+        }
+        else if (k == "lanes_over_queries")
+        {
+            ctx->tune_lanes_over_queries = value;
+        }
+        else
+        {
+            throw Error(FGPU_EINVALID, "unknown tuning key: " + k);
+        }
     });
 }
 
@@ -1220,6 +1253,7 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
             // r_min: LinkCell compares squares (LinkCell.cc:619), AABBQuery the distance itself (AABBQuery.cc:213)
             Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, wrap ? r_min : 0.0f, exclude_ii);
             s2.knn_r_min = !wrap && r_min > 0.0f ? r_min : 0.0f;
+            search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_win), ctx->tune_lanes_over_queries);
             if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL) && pts->n < 0x7fffffffU)
             {
                 ctx->tmp_start.reserve((size_t) n_query + 1);
@@ -1316,6 +1350,8 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                     s2b.knn_r_min = s2.knn_r_min;
                     s2b.q_remap = ctx->knn_unresolved.ptr;
                     s2b.tmp_flag = kSecondBag;
+                    search2_choose_mapping(s2b, (uint32_t) n_short, expected_hits_per_query(pts, r_win2),
+                                           ctx->tune_lanes_over_queries);
                     if (!cover_all2 && search2_supported(s2b, S2_NL)
                         && run_window(s2b, ctx->bag4b, n_short, r_win2, ctx->knn_unresolved.ptr + n_query)
                             == WINDOW_DONE)

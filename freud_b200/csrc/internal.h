@@ -137,7 +137,11 @@ struct fgpu_ctx
     fgpu::DevBuf<float4> bag4b;           // kNN: bag of the second, wider search
     fgpu::DevBuf<int> q_outside_flag;     // device flag: a query point lies outside the box
     uint64_t bag_hint = 0;                // bonds of the previous query (sizes the next bag)
-    int force_general = 0;                // FGPU_SEARCH=general: always run the search.cu kernels (testing)
+    int force_general = 0;                // fgpu_ctx_force_general_search: always run the search.cu kernels (testing)
+    // fgpu_ctx_set_tuning: experiment / test hooks, never read from the environment
+    int tune_span = 0;                    // > 0: cells per home tile of the tile walk
+    int tune_no_symmetry = 0;             // 1: self-query IMAGE RDF without the symmetric walk
+    int tune_lanes_over_queries = -1;     // -1 automatic, 0 / 1: force the NeighborList search's mapping
     fgpu::DevBuf<double> st_partials;     // Steinhardt: per-block partial sums of the system q_lm
     fgpu::DevBuf<float> knn_d;            // kNN scratch, [k][n_query]
     fgpu::DevBuf<uint32_t> knn_s;         // kNN scratch, [k][n_query] (slot | image code)
@@ -407,6 +411,8 @@ struct Search2Args
     BoxDev box;
     int dx, dy, dz;
     uint32_t n_cells;
+    int lanes_over_queries;         // NeighborList mode: 32 cell-ordered queries per ticket, one per lane (sparse cells)
+    uint32_t n_query;               // queries in q_sorted (lanes-over-queries tickets)
     int span;                       // cells per home tile along x (search2_plan)
     uint32_t spans_per_row;
     uint32_t n_tickets;             // work items: one home tile each
@@ -449,7 +455,9 @@ struct Search2Args
     unsigned int* done_counter;     // blocks that have merged their histogram (zeroed with work_counter)
     PeerBox peer;
 };
-void search2_plan(Search2Args& a, uint32_t n_points); // sets span, spans_per_row, n_tickets
+void search2_plan(Search2Args& a, uint32_t n_points, int span_override = 0); // sets span, spans_per_row, n_tickets
+// NeighborList mode: tile walk or lanes over queries (force: -1 automatic, 0 / 1 fgpu_ctx_set_tuning); sets n_query
+void search2_choose_mapping(Search2Args& a, uint32_t n_query, double expected_hits_per_query, int force);
 
 // Share of one rank when the home tiles of a self query are dealt to n_shards ranks: a contiguous run of tickets,
 // the cells they cover, and the slab of cell layers (with one halo layer on each side) their candidates live in.

@@ -81,8 +81,14 @@ int fgpu_ctx_pair_evals(fgpu_ctx* ctx, uint64_t* out, int reset);
 /* Two kernel families implement the ball search: the warp-cooperative one (regular grids with >= 3 cells per
  * periodic axis and all points inside the box -- the normal case) and a general thread-per-query one that
  * also covers tiny boxes, points outside the box and rows longer than the warp buffer.  The choice is
- * automatic; enable != 0 forces the general family (parity tests compare the two; also FGPU_SEARCH=general). */
+ * automatic; enable != 0 forces the general family (the parity tests run every family against the oracle). */
 int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
+
+/* Experiment / test hooks (the library reads no environment variables).  Keys: "span" (> 0: cells per home tile of
+ * the tile-walk search, 0: automatic), "no_symmetry" (1: self-query IMAGE RDF without the symmetric walk),
+ * "lanes_over_queries" (NeighborList search mapping: -1 automatic, 0 tile walk, 1 one query per lane).  Results never
+ * depend on them; the parity tests run every mapping against the oracle. */
+int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value);
 
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).  While enabled,
  * every kernel launch is bracketed by an event pair; fgpu_ctx_kernel_time synchronises and returns the summed
