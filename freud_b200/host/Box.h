@@ -56,6 +56,72 @@ public:
         return vec3<float>(m_Lx / std::sqrt((float) a3), m_Ly / std::sqrt((float) c1), m_Lz);
     }
 
+    // Lattice vectors (Box.h:503-518); the third one vanishes in 2-D
+    vec3<float> getLatticeVector(unsigned int i) const
+    {
+        if (i == 0)
+        {
+            return vec3<float>(m_Lx, 0.0F, 0.0F);
+        }
+        if (i == 1)
+        {
+            volatile float bx = m_Ly * m_xy;
+            return vec3<float>(bx, m_Ly, 0.0F);
+        }
+        if (i == 2 && !m_2d)
+        {
+            volatile float cx = m_Lz * m_xz, cy = m_Lz * m_yz;
+            return vec3<float>(cx, cy, m_Lz);
+        }
+        throw std::out_of_range("Box lattice vector index requested does not exist.");
+    }
+
+    // Host restatement of the per-vector box arithmetic (Box.h:212-255, 307-329, freud/util/utils.h:29-32), one float32
+    // rounding per operation in the reference's order (this file is compiled with -ffp-contract=off; the volatile
+    // temporaries keep every intermediate in float).  The GPU kernels hold the production copy (csrc/pair_math.cuh);
+    // this one serves the host-only corners of the API: NeighborList's all-pairs constructor and CellQuery's grid
+    // introspection.
+    vec3<float> makeFractional(const vec3<float>& v) const
+    {
+        volatile float lox = -(m_Lx * 0.5F), loy = -(m_Ly * 0.5F), loz = -(m_Lz * 0.5F);
+        volatile float dx = v.x - lox, dy = v.y - loy, dz = v.z - loz;
+        volatile float t0 = m_yz * m_xy;
+        volatile float txz = m_xz - t0;
+        volatile float a = txz * v.z, b = m_xy * v.y;
+        volatile float ab = a + b;
+        dx = dx - ab;
+        volatile float c = m_yz * v.z;
+        dy = dy - c;
+        volatile float fx = dx / m_Lx, fy = dy / m_Ly, fz = m_2d ? 0.0F : dz / m_Lz;
+        return vec3<float>(fx, fy, fz);
+    }
+    vec3<float> makeAbsolute(const vec3<float>& f) const
+    {
+        volatile float lox = -(m_Lx * 0.5F), loy = -(m_Ly * 0.5F), loz = -(m_Lz * 0.5F);
+        volatile float px = f.x * m_Lx, py = f.y * m_Ly, pz = f.z * m_Lz;
+        volatile float x = lox + px, y = loy + py, z = loz + pz;
+        volatile float a = m_xy * y, b = m_xz * z;
+        volatile float ab = a + b;
+        x = x + ab;
+        volatile float c = m_yz * z;
+        y = y + c;
+        return vec3<float>(x, y, m_2d ? 0.0F : (float) z);
+    }
+    vec3<float> wrap(const vec3<float>& v) const
+    {
+        vec3<float> f = makeFractional(v);
+        auto mod1 = [](float a) {
+            volatile float t = std::fmod(a, 1.0F);
+            volatile float u = t + 1.0F;
+            volatile float w = std::fmod((float) u, 1.0F);
+            return (float) w;
+        };
+        f.x = mod1(f.x);
+        f.y = mod1(f.y);
+        f.z = m_2d ? 0.0F : mod1(f.z);
+        return makeAbsolute(f);
+    }
+
     bool operator==(const Box& o) const
     {
         return m_Lx == o.m_Lx && m_Ly == o.m_Ly && m_Lz == o.m_Lz && m_xy == o.m_xy && m_xz == o.m_xz

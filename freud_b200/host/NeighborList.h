@@ -13,6 +13,7 @@
 #include <numeric>
 #include <vector>
 
+#include "Box.h"
 #include "Context.h"
 #include "ManagedArray.h"
 #include "VectorMath.h"
@@ -66,6 +67,41 @@ public:
             volatile float s = xx + yy;
             volatile float d2 = s + zz;
             (*m_distances)[b] = std::sqrt((float) d2);
+        }
+    }
+
+    // all pairs (NeighborList.cc:84-128, NeighborList.all_pairs upstream): every (query point, point) bond, the vector
+    // being box.wrap(query_points[i] - points[j]) as upstream writes it; O(N Nq) on the host, for small systems
+    NeighborList(const vec3<float>* points, const vec3<float>* query_points, const box::Box& box, const bool exclude_ii,
+                 const unsigned int num_points, const unsigned int num_query_points)
+        : NeighborList(num_points * num_query_points - (exclude_ii ? std::min(num_points, num_query_points) : 0U))
+    {
+        m_num_points = num_points;
+        m_num_query_points = num_query_points;
+        size_t b = 0;
+        for (unsigned int i = 0; i < num_query_points; ++i)
+        {
+            for (unsigned int j = 0; j < num_points; ++j)
+            {
+                if (exclude_ii && i == j)
+                {
+                    continue;
+                }
+                volatile float dx = query_points[i].x - points[j].x, dy = query_points[i].y - points[j].y,
+                               dz = query_points[i].z - points[j].z;
+                vec3<float> const dr = box.wrap(vec3<float>(dx, dy, dz));
+                (*m_neighbors)[2 * b] = i;
+                (*m_neighbors)[2 * b + 1] = j;
+                (*m_weights)[b] = 1.0F;
+                volatile float xx = dr.x * dr.x, yy = dr.y * dr.y, zz = dr.z * dr.z;
+                volatile float s = xx + yy;
+                volatile float d2 = s + zz;
+                (*m_distances)[b] = std::sqrt((float) d2);
+                (*m_vectors)[3 * b] = dr.x;
+                (*m_vectors)[3 * b + 1] = dr.y;
+                (*m_vectors)[3 * b + 2] = dr.z;
+                ++b;
+            }
         }
     }
 

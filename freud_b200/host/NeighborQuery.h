@@ -20,6 +20,8 @@
 #include <limits>
 #include <memory>
 #include <stdexcept>
+#include <vector>
+#include <algorithm>
 
 #include "Box.h"
 #include "Context.h"
@@ -67,13 +69,37 @@ struct NeighborBond
         return query_point_idx == o.query_point_idx && point_idx == o.point_idx && distance == o.distance
             && weight == o.weight;
     }
+    bool operator!=(const NeighborBond& o) const { return !(*this == o); }
+    // accessors the binding layer exposes (freud/locality/NeighborBond.h:62-78, export-NeighborList.cc:90-96)
+    unsigned int getQueryPointIdx() const { return query_point_idx; }
+    unsigned int getPointIdx() const { return point_idx; }
+    float getDistance() const { return distance; }
+    float getWeight() const { return weight; }
+    const vec3<float>& getVector() const { return vector; }
 };
 inline NeighborBond iterator_terminator() // ITERATOR_TERMINATOR, NeighborQuery.h:51-52
 {
     return NeighborBond();
 }
 
+// freud/locality/NeighborPerPointIterator.h:38-58: the neighbours of one query point, one bond per next() until end()
+class NeighborPerPointIterator
+{
+public:
+    NeighborPerPointIterator() = default;
+    explicit NeighborPerPointIterator(unsigned int query_point_idx) : m_query_point_idx(query_point_idx) {}
+    virtual ~NeighborPerPointIterator() = default;
+    virtual bool end() const = 0;
+    virtual NeighborBond next() = 0;
+
+protected:
+    unsigned int m_query_point_idx {0};
+};
+
 class NeighborQueryIterator;
+class NeighborQueryPerPointIterator;
+class NeighborQuery;
+inline const float* selfOrHost(const NeighborQuery& nq, const vec3<float>* query_points, unsigned int n_query_points);
 
 class NeighborQuery
 {
@@ -102,6 +128,13 @@ public:
 
     std::shared_ptr<NeighborQueryIterator> query(const vec3<float>* query_points, unsigned int n_query_points,
                                                  QueryArgs query_args) const;
+
+    // The neighbours of ONE query point (NeighborQuery.h:144-154; what loopOverNeighborsIterator hands a compute that
+    // normalises per row, NeighborComputeFunctional.h:112-150): a one-row query on the device, its bonds served in
+    // (j) or, for nearest-neighbour mode, distance order.  query_point_idx is the row index the bonds carry and the
+    // point index exclude_ii compares against.
+    std::shared_ptr<NeighborQueryPerPointIterator> querySingle(const vec3<float> query_point, unsigned int query_point_idx,
+                                                               QueryArgs args) const;
 
     const box::Box& getBox() const { return m_box; }
     const vec3<float>* getPoints() const { return m_points; }
@@ -243,12 +276,8 @@ public:
     {
         fgpu_points* pts = m_nq->device();
         fgpu_nlist* out = nullptr;
-        // queries == the reference points themselves: skip the upload and the second cell sort
-        const float* q = reinterpret_cast<const float*>(m_query_points);
-        if (m_query_points == m_nq->getPoints() && m_n_query_points == m_nq->getNPoints())
-        {
-            q = nullptr;
-        }
+        // queries == the reference points themselves (by value): skip the upload and the second cell sort
+        const float* q = selfOrHost(*m_nq, m_query_points, m_n_query_points);
         if (m_qargs.mode == QueryType::ball)
         {
             gpu::check(fgpu_ball_query(pts, q, m_n_query_points, 0, m_nq->getFlavour(), m_qargs.r_max, m_qargs.r_min,
@@ -265,6 +294,17 @@ public:
 
     const QueryArgs& getQueryArgs() const { return m_qargs; }
 
+    // NeighborQuery.h:380-390, 392-419
+    bool end() const { return m_iter_list && m_cursor >= m_iter_list->getNumBonds(); }
+    std::shared_ptr<NeighborQueryPerPointIterator> query(unsigned int i)
+    {
+        if (i >= m_n_query_points)
+        {
+            throw std::out_of_range("query point index out of range");
+        }
+        return m_nq->querySingle(m_query_points[i], i, m_qargs);
+    }
+
 private:
     const NeighborQuery* m_nq;
     const vec3<float>* m_query_points;
@@ -276,6 +316,77 @@ private:
 
 // The query points as the C ABI takes them: nullptr when they are the reference points themselves (no upload, no
 // second cell sort), else the packed floats.
+// NeighborQuery.h:309-350.  One device query of a single row; next() walks its bonds.
+class NeighborQueryPerPointIterator : public NeighborPerPointIterator
+{
+public:
+    NeighborQueryPerPointIterator(const NeighborQuery* neighbor_query, const vec3<float>& query_point,
+                                  unsigned int query_point_idx, const QueryArgs& qargs)
+        : NeighborPerPointIterator(query_point_idx), m_neighbor_query(neighbor_query), m_query_point(query_point),
+          m_qargs(qargs)
+    {
+        if (qargs.r_max <= 0)
+        {
+            throw std::invalid_argument("NeighborQuery requires r_max to be positive.");
+        }
+        if (qargs.r_max <= qargs.r_min)
+        {
+            throw std::invalid_argument("NeighborQuery requires that r_max must be greater than r_min.");
+        }
+    }
+
+    bool end() const override { return m_list && m_cursor >= m_list->getNumBonds(); }
+
+    NeighborBond next() override
+    {
+        if (!m_list)
+        {
+            fgpu_nlist* out = nullptr;
+            const float* q = reinterpret_cast<const float*>(&m_query_point);
+            if (m_qargs.mode == QueryType::nearest)
+            {
+                gpu::check(fgpu_knn_query(m_neighbor_query->device(), q, 1, m_query_point_idx, m_neighbor_query->getFlavour(),
+                                          m_qargs.num_neighbors, m_qargs.r_max, m_qargs.r_min, m_qargs.exclude_ii ? 1 : 0,
+                                          1, &out));
+            }
+            else
+            {
+                gpu::check(fgpu_ball_query(m_neighbor_query->device(), q, 1, m_query_point_idx,
+                                           m_neighbor_query->getFlavour(), m_qargs.r_max, m_qargs.r_min,
+                                           m_qargs.exclude_ii ? 1 : 0, 0, &out));
+            }
+            m_list = std::make_shared<NeighborList>(out, gpu::context());
+        }
+        if (m_cursor >= m_list->getNumBonds())
+        {
+            return iterator_terminator();
+        }
+        size_t const b = m_cursor++;
+        NeighborBond nb;
+        nb.query_point_idx = m_query_point_idx;
+        nb.point_idx = (*m_list->getNeighbors())[2 * b + 1];
+        nb.distance = (*m_list->getDistances())[b];
+        nb.weight = (*m_list->getWeights())[b];
+        nb.vector = vec3<float>((*m_list->getVectors())[3 * b], (*m_list->getVectors())[3 * b + 1],
+                                (*m_list->getVectors())[3 * b + 2]);
+        return nb;
+    }
+
+protected:
+    const NeighborQuery* m_neighbor_query;
+    vec3<float> m_query_point;
+    QueryArgs m_qargs;
+    std::shared_ptr<NeighborList> m_list;
+    size_t m_cursor {0};
+};
+
+inline std::shared_ptr<NeighborQueryPerPointIterator>
+NeighborQuery::querySingle(const vec3<float> query_point, unsigned int query_point_idx, QueryArgs args) const
+{
+    this->validateQueryArgs(args);
+    return std::make_shared<NeighborQueryPerPointIterator>(this, query_point, query_point_idx, args);
+}
+
 // Bitwise equality of two point arrays: a few probes first (different query sets fail at once), then the whole
 // array, on a few threads when it is large.
 inline bool samePoints(const vec3<float>* a, const vec3<float>* b, unsigned int n)
@@ -409,6 +520,132 @@ public:
             throw std::runtime_error("The CellQuery r_max is too large for this box.");
         }
     }
+
+    // ---- grid introspection (CellQuery.h:84-171, CellQuery.cc:55-137) ------------------------------------------
+    // Upstream answers ball queries from a Cartesian grid of width r_cut over the box's bounding cuboid, with a
+    // ghost copy of every point that lies within r_cut of a periodic face; its binding layer exposes that grid
+    // (export-NeighborQuery.cc:96-111).  Queries here run on the GPU's own cell list (the grid only generates
+    // candidates), so these members describe the grid upstream WOULD build for r_cut --
+    // dimensions, origin, per-cell populations with and without ghosts, cell offsets -- computed on the host when
+    // asked, for callers that inspect it.
+    void setupGrid(const float r_cut) const
+    {
+        m_cell_inverse_length = 1.0F / r_cut;
+        float const lx = m_box.getLx(), ly = m_box.getLy(), lz = m_box.getLz();
+        float const xy = m_box.getTiltFactorXY(), xz = m_box.getTiltFactorXZ(), yz = m_box.getTiltFactorYZ();
+        // extent of the box along the Cartesian axes, and its lowest corner
+        volatile float wx = lx + ly * std::abs(xy) + lz * std::abs(xz);
+        volatile float wy = ly + lz * std::abs(yz);
+        m_nx = (unsigned int) (int) ((float) wx * m_cell_inverse_length) + 3U;
+        m_ny = (unsigned int) (int) ((float) wy * m_cell_inverse_length) + 3U;
+        m_nz = (unsigned int) (int) (lz * m_cell_inverse_length) + 3U;
+        volatile float min_x = ly * std::min(0.0F, xy) + lz * std::min(0.0F, xz);
+        volatile float min_y = lz * std::min(0.0F, yz);
+        vec3<float> const origin = m_box.makeAbsolute(vec3<float>(0.0F, 0.0F, 0.0F));
+        volatile float px = (float) min_x - r_cut, py = (float) min_y - r_cut, pz = -r_cut;
+        m_min_pos = vec3<float>((float) px + origin.x, (float) py + origin.y, (float) pz + origin.z);
+    }
+
+    void buildGrid(const float r_cut) const
+    {
+        if (r_cut <= 0)
+        {
+            throw std::runtime_error("CellQuery::buildGrid called with invalid r_cut (must be positive).");
+        }
+        setupGrid(r_cut);
+        size_t const n_cells = (size_t) m_nx * m_ny * m_nz;
+        m_counts.assign(n_cells, 0U);
+        m_counts_real.assign(n_cells, 0U);
+        m_cell_starts.assign(n_cells, 0U);
+        m_n_total = 0;
+        vec3<float> const pd = m_box.getNearestPlaneDistance();
+        vec3<float> const fr(r_cut / pd.x, r_cut / pd.y, r_cut / pd.z);
+        vec3<float> const a = m_box.getLatticeVector(0), b = m_box.getLatticeVector(1);
+        vec3<float> const c = m_box.is2D() ? vec3<float>(0.0F, 0.0F, 0.0F) : m_box.getLatticeVector(2);
+        auto cell_of = [&](const vec3<float>& p, size_t& idx) {
+            int const cx = (int) std::floor((p.x - m_min_pos.x) * m_cell_inverse_length);
+            int const cy = (int) std::floor((p.y - m_min_pos.y) * m_cell_inverse_length);
+            int const cz = (int) std::floor((p.z - m_min_pos.z) * m_cell_inverse_length);
+            if (cx < 0 || cy < 0 || cz < 0 || cx >= (int) m_nx || cy >= (int) m_ny || cz >= (int) m_nz)
+            {
+                return false;
+            }
+            idx = ((size_t) cz * m_ny + cy) * m_nx + cx;
+            return true;
+        };
+        for (unsigned int i = 0; i < m_n_points; ++i)
+        {
+            vec3<float> const p = m_points[i];
+            vec3<float> const f = m_box.makeFractional(p);
+            // +1: near the low face (its image appears beyond the high face), -1: near the high face
+            int const s[3] = {(int) (f.x <= fr.x) - (int) (f.x >= 1.0 - fr.x), (int) (f.y <= fr.y) - (int) (f.y >= 1.0 - fr.y),
+                              m_box.is2D() ? 0 : (int) (f.z <= fr.z) - (int) (f.z >= 1.0 - fr.z)};
+            // one ghost per non-empty subset of the faces the point is close to
+            for (int mask = 1; mask < 8; ++mask)
+            {
+                bool const ux = (mask & 1) != 0, uy = (mask & 2) != 0, uz = (mask & 4) != 0;
+                if ((ux && s[0] == 0) || (uy && s[1] == 0) || (uz && s[2] == 0))
+                {
+                    continue;
+                }
+                vec3<float> g = p;
+                vec3<float> shift(0.0F, 0.0F, 0.0F);
+                auto add = [&](const vec3<float>& v, int sign) {
+                    shift = vec3<float>(shift.x + (sign > 0 ? v.x : -v.x), shift.y + (sign > 0 ? v.y : -v.y),
+                                        shift.z + (sign > 0 ? v.z : -v.z));
+                };
+                if (ux)
+                {
+                    add(a, s[0]);
+                }
+                if (uy)
+                {
+                    add(b, s[1]);
+                }
+                if (uz)
+                {
+                    add(c, s[2]);
+                }
+                g = vec3<float>(p.x + shift.x, p.y + shift.y, p.z + shift.z);
+                size_t idx = 0;
+                if (cell_of(g, idx))
+                {
+                    m_counts[idx] += 1;
+                    m_n_total += 1;
+                }
+            }
+            size_t idx = 0;
+            if (cell_of(p, idx))
+            {
+                m_counts[idx] += 1;
+                m_counts_real[idx] += 1;
+                m_n_total += 1;
+            }
+        }
+        unsigned int acc = 0;
+        for (size_t k = 0; k < n_cells; ++k)
+        {
+            m_cell_starts[k] = acc;
+            acc += m_counts[k];
+        }
+    }
+
+    float getCellWidth() const { return 1.0F / m_cell_inverse_length; }
+    float getCellInverseWidth() const { return m_cell_inverse_length; }
+    const std::vector<unsigned int>& getCountsReal() const { return m_counts_real; }
+    const std::vector<unsigned int>& getCounts() const { return m_counts; }
+    const std::vector<unsigned int>& getCellStarts() const { return m_cell_starts; }
+    std::vector<float> getMinPos() const { return {m_min_pos.x, m_min_pos.y, m_min_pos.z}; }
+    unsigned int getNx() const { return m_nx; }
+    unsigned int getNy() const { return m_ny; }
+    unsigned int getNz() const { return m_nz; }
+    unsigned int getNTotal() const { return m_n_total; }
+
+private:
+    mutable float m_cell_inverse_length {0};
+    mutable vec3<float> m_min_pos;
+    mutable unsigned int m_nx {0}, m_ny {0}, m_nz {0}, m_n_total {0};
+    mutable std::vector<unsigned int> m_counts, m_counts_real, m_cell_starts;
 };
 
 // RawPoints (freud/locality/RawPoints.h:35-73): upstream builds an AABBQuery lazily on the first query.

@@ -1,0 +1,5 @@
+// freud::locality::RawPoints lives in NeighborQuery.h with the other engines; this header exists so that the reference's
+// binding layer, which includes "RawPoints.h" (freud/locality/export-NeighborQuery.cc:9-14), finds the replacement class and
+// not the stock one.
+#pragma once
+#include "NeighborQuery.h"

@@ -8,6 +8,7 @@
 // base object keeps the owning ManagedArray alive, C++ exceptions surface as ValueError / RuntimeError /
 // IndexError.  Submodules are named after the reference's extension modules (_box, _locality, _density,
 // _order) so that freud's Python layer maps onto them one to one.
+#include <array>
 #include <thread>
 
 #include <pybind11/complex.h>
@@ -176,6 +177,14 @@ PYBIND11_MODULE(_freud_b200, m)
              }),
              py::arg("query_point_indices"), py::arg("num_query_points"), py::arg("point_indices"),
              py::arg("num_points"), py::arg("vectors"), py::arg("weights") = py::none())
+        // all pairs (export-NeighborList.cc:41-51)
+        .def(py::init([](points_array points, points_array query_points, const box::Box& box, bool exclude_ii) {
+                 unsigned int np = 0, nq = 0;
+                 const vec3<float>* p = as_vec3(points, np);
+                 const vec3<float>* q = as_vec3(query_points, nq);
+                 return std::make_shared<locality::NeighborList>(p, q, box, exclude_ii, np, nq);
+             }),
+             py::arg("points"), py::arg("query_points"), py::arg("box"), py::arg("exclude_ii"))
         .def("getNumBonds", &locality::NeighborList::getNumBonds)
         .def("getNumQueryPoints", &locality::NeighborList::getNumQueryPoints)
         .def("getNumPoints", &locality::NeighborList::getNumPoints)
@@ -217,7 +226,19 @@ PYBIND11_MODULE(_freud_b200, m)
              },
              py::keep_alive<0, 1>(), py::keep_alive<0, 2>())
         .def("getBox", &locality::NeighborQuery::getBox)
-        .def("getNPoints", &locality::NeighborQuery::getNPoints);
+        .def("getNPoints", &locality::NeighborQuery::getNPoints)
+        // the bonds of one query point as a list of (i, j, distance, weight) (NeighborQuery::querySingle)
+        .def("querySingle",
+             [](std::shared_ptr<locality::NeighborQuery> nq, std::array<float, 3> q, unsigned int idx,
+                const locality::QueryArgs& qargs) {
+                 auto it = nq->querySingle(vec3<float>(q[0], q[1], q[2]), idx, qargs);
+                 py::list out;
+                 for (auto b = it->next(); !(b == locality::iterator_terminator()); b = it->next())
+                 {
+                     out.append(py::make_tuple(b.query_point_idx, b.point_idx, b.distance, b.weight));
+                 }
+                 return out;
+             });
     py::class_<locality::LinkCell, locality::NeighborQuery, std::shared_ptr<locality::LinkCell>>(mloc, "LinkCell")
         .def(py::init([](const box::Box& b, points_array pts, float cell_width) {
                  unsigned int n = 0;
@@ -239,7 +260,20 @@ PYBIND11_MODULE(_freud_b200, m)
                  const vec3<float>* p = as_vec3(pts, n);
                  return std::make_shared<locality::CellQuery>(b, p, n);
              }),
-             py::arg("box"), py::arg("points"), py::keep_alive<1, 3>());
+             py::arg("box"), py::arg("points"), py::keep_alive<1, 3>())
+        // grid introspection, as export-NeighborQuery.cc:96-111 binds it
+        .def("getCellWidth", &locality::CellQuery::getCellWidth)
+        .def("getCountsReal", &locality::CellQuery::getCountsReal)
+        .def("getCounts", &locality::CellQuery::getCounts)
+        .def("getMinPos", &locality::CellQuery::getMinPos)
+        .def("getCellInverseWidth", &locality::CellQuery::getCellInverseWidth)
+        .def("getNx", &locality::CellQuery::getNx)
+        .def("getNy", &locality::CellQuery::getNy)
+        .def("getNz", &locality::CellQuery::getNz)
+        .def("getNTotal", &locality::CellQuery::getNTotal)
+        .def("getCellStarts", &locality::CellQuery::getCellStarts)
+        .def("setupGrid", &locality::CellQuery::setupGrid)
+        .def("buildGrid", &locality::CellQuery::buildGrid);
     py::class_<locality::RawPoints, locality::NeighborQuery, std::shared_ptr<locality::RawPoints>>(mloc, "RawPoints")
         .def(py::init([](const box::Box& b, points_array pts) {
                  unsigned int n = 0;

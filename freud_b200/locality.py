@@ -232,6 +232,14 @@ class NeighborList:
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
         return cls._from_cpp(_ext()._locality.NeighborList(qi, int(num_query_points), pi, int(num_points), v, w))
 
+    @classmethod
+    def all_pairs(cls, system, query_points=None, exclude_ii=True):
+        """Every (query point, point) pair as a bond (freud/locality.py:558-600, NeighborList.cc:84-128); O(N^2), for small
+        systems.  Vectors are ``box.wrap(query_points[i] - points[j])`` as upstream writes them."""
+        nq = NeighborQuery.from_system(system)
+        qp = nq.points if query_points is None else _points(query_points, "query_points")
+        return cls._from_cpp(_ext()._locality.NeighborList(nq.points, qp, _cpp_box(nq.box), bool(exclude_ii)))
+
     def __len__(self):
         return self._cpp_obj.getNumBonds()
 

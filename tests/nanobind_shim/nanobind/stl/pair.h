@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY -- see nanobind.h in this directory.
+#pragma once

@@ -656,3 +656,29 @@ def test_steinhardt_nan_without_neighbours():
     pts = np.array([[0, 0, 0], [0.5, 0, 0], [4, 4, 4]], np.float32)
     ql = order.Steinhardt(6).compute((box, pts), neighbors=dict(r_max=1.0)).ql
     assert np.isfinite(ql[0]) and np.isfinite(ql[1]) and np.isnan(ql[2])
+
+
+@pytest.mark.gpu
+def test_query_single_matches_the_rows_of_the_full_query():
+    """NeighborQuery::querySingle / NeighborQueryPerPointIterator (NeighborQuery.h:144-154, 309-350): the per-point
+    iterator that loopOverNeighborsIterator hands a compute yields exactly row i of the full query, in both modes."""
+    from freud_b200 import data, locality
+
+    box, pts = data.make_random_system(12.0, 400, seed=9)
+    L = locality._ext()._locality
+    for cls in (locality.AABBQuery, locality.LinkCell):
+        nq = cls(box, pts)
+        qa = locality._query_args(dict(mode="ball", r_max=2.5, exclude_ii=True))
+        full = nq.query(pts, dict(mode="ball", r_max=2.5, exclude_ii=True)).toNeighborList()
+        for i in (0, 17, 399):
+            row = nq._cpp_obj.querySingle([float(v) for v in pts[i]], i, qa)
+            sel = full.query_point_indices == i
+            assert [b[1] for b in row] == list(full.point_indices[sel])
+            assert np.array_equal(np.float32([b[2] for b in row]), full.distances[sel])
+            assert all(b[0] == i for b in row)
+        qk = locality._query_args(dict(mode="nearest", num_neighbors=5, exclude_ii=True))
+        row = nq._cpp_obj.querySingle([float(v) for v in pts[3]], 3, qk)
+        fullk = nq.query(pts, dict(num_neighbors=5, exclude_ii=True)).toNeighborList(sort_by_distance=True)
+        sel = fullk.query_point_indices == 3
+        assert [b[1] for b in row] == list(fullk.point_indices[sel])
+    del L

@@ -269,3 +269,39 @@ def test_from_system_adapters():
     assert got.box.is2D and got.box.xy == 0.25
     with pytest.raises(ValueError):
         locality.NeighborQuery.from_system(42)
+
+
+def test_cellquery_grid_introspection_and_all_pairs():
+    """The host-only corners the reference's binding layer exposes (export-NeighborQuery.cc:96-111,
+    export-NeighborList.cc:41-51): CellQuery's grid description and NeighborList.all_pairs, the latter's vectors against
+    the compiled reference's Box::wrap bit for bit."""
+    import numpy as np
+
+    from freud_b200 import locality
+    from freud_b200.box import Box
+    from oracle import ref
+
+    box = Box(10, 12, 14, 0.2, -0.1, 0.3)
+    rs = np.random.RandomState(3)
+    pts = box.make_absolute(rs.random_sample((200, 3))).astype(np.float32)
+    cq = locality.CellQuery(box, pts)._cpp_obj
+    cq.buildGrid(2.0)
+    counts, real, starts = np.array(cq.getCounts()), np.array(cq.getCountsReal()), np.array(cq.getCellStarts())
+    assert cq.getNx() == int((10 + 12 * 0.2 + 14 * 0.1) / 2.0) + 3 and cq.getNz() == 14 // 2 + 3
+    assert len(counts) == cq.getNx() * cq.getNy() * cq.getNz()
+    assert real.sum() == 200 and counts.sum() == cq.getNTotal() > 200  # ghosts of the points near a face
+    assert np.array_equal(starts, np.concatenate([[0], np.cumsum(counts)[:-1]]))
+    assert abs(cq.getCellWidth() - 2.0) < 1e-6 and abs(cq.getCellInverseWidth() - 0.5) < 1e-7
+    with pytest.raises(RuntimeError):
+        cq.buildGrid(-1.0)
+
+    q = pts[:7] + np.float32(0.25)
+    nl = locality.NeighborList.all_pairs((box, pts[:50]), q, exclude_ii=True)
+    assert len(nl) == 50 * 7 - 7
+    i, j = nl.query_point_indices.astype(int), nl.point_indices.astype(int)
+    assert not np.any(i == j) and np.all(np.diff(i) >= 0)
+    if ref.available():
+        want = ref.box_apply(box, False, "wrap", q[i] - pts[:50][j])
+        assert np.array_equal(nl.vectors.view(np.uint32), want.view(np.uint32))
+    assert np.allclose(nl.distances, np.linalg.norm(nl.vectors, axis=1), rtol=1e-6)
+    assert np.all(nl.weights == 1)
