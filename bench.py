@@ -817,6 +817,8 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="experiment hook: fgpu_ctx_set_tuning(key, value), e.g. span=2 or lanes_over_queries=1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -842,6 +844,9 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     ctx = _capi.Context(local_rank)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        ctx.set_tuning(key, int(val))
     env = dict(torch=torch, dist=dist, ctx=ctx, rank=rank, world=world, local_rank=local_rank,
                stream=torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank)),
                flush=torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda"), comm=None)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "fgpu_nlist_num_query_points": (C.c_uint32, [_vp]),
     "fgpu_nlist_num_points": (C.c_uint32, [_vp]),
     "fgpu_nlist_copy": (C.c_int, [_vp, _up, _fp, _fp, _fp, _up, _up]),
+    "fgpu_nlist_copy_begin": (C.c_int, [_vp, _up, _fp, _fp, _fp]),
+    "fgpu_nlist_copy_wait": (C.c_int, [_vp, C.c_uint]),
     "fgpu_nlist_from_host": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, _up, _fp, _fp, _fp, _vpp]),
     "fgpu_nlist_destroy": (None, [_vp]),
     "fgpu_rdf_create": (C.c_int, [_vp, C.c_uint32, C.c_float, C.c_float, _vpp]),

@@ -395,11 +395,16 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
             s2.counts = nl->counts.ptr;
             s2.tmp_start = ctx->tmp_start.ptr;
             FGPU_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 4, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            // the search writes every row's count twice (counts and the array the row scan turns into offsets) and its
+            // first block clears the scan's scratch: no D2D copy and no memset between the two kernels
+            size_t const scan_words = scan_scratch_words((size_t) n_query + 1);
+            ctx->scan_tmp.reserve(scan_words);
+            s2.counts_copy = nl->row_start.ptr;
+            s2.zero_words = ctx->scan_tmp.ptr;
+            s2.zero_n = (uint32_t) scan_words;
+            s2.zero_tail = nl->row_start.ptr + n_query;
             launch_search2(ctx, flavour, S2_NL, s2);
-            FGPU_CUDA_CHECK(cudaMemcpyAsync(nl->row_start.ptr, nl->counts.ptr, (size_t) n_query * sizeof(uint32_t),
-                                            cudaMemcpyDeviceToDevice, ctx->stream));
-            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
-            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1, true);
             Emit2Args e;
             e.bag = ctx->bag4.ptr;
             e.tmp_start = ctx->tmp_start.ptr;
@@ -1475,6 +1480,26 @@ uint32_t fgpu_nlist_num_points(const fgpu_nlist* nl)
     return nl != nullptr ? nl->n_points : 0;
 }
 
+namespace {
+
+void fill_unit_weights(float* weights_host, size_t nb)
+{
+    unsigned const n_threads = nb >= (1U << 20) ? std::max(1U, std::min(4U, std::thread::hardware_concurrency())) : 1U;
+    auto fill = [&](size_t lo, size_t hi) { std::fill(weights_host + lo, weights_host + hi, 1.0f); };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; ++t)
+    {
+        pool.emplace_back(fill, nb * t / n_threads, nb * (t + 1) / n_threads);
+    }
+    fill(0, nb / n_threads);
+    for (auto& th : pool)
+    {
+        th.join();
+    }
+}
+
+} // namespace
+
 int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
                     float* vectors_host, uint32_t* segments_host, uint32_t* counts_host)
 {
@@ -1513,20 +1538,64 @@ int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* dista
             // A list built by a query carries weight 1 on every bond: write the ones here, on host threads, while
             // the other arrays cross PCIe (the copy of a frame's list is bound by that link) instead of sending a
             // seventh of the bytes for a constant.
-            unsigned const n_threads = nb >= (1U << 20) ? std::max(1U, std::min(4U, std::thread::hardware_concurrency())) : 1U;
-            auto fill = [&](size_t lo, size_t hi) { std::fill(weights_host + lo, weights_host + hi, 1.0f); };
-            std::vector<std::thread> pool;
-            for (unsigned t = 1; t < n_threads; ++t)
-            {
-                pool.emplace_back(fill, nb * t / n_threads, nb * (t + 1) / n_threads);
-            }
-            fill(0, nb / n_threads);
-            for (auto& th : pool)
-            {
-                th.join();
-            }
+            fill_unit_weights(weights_host, nb);
         }
         sync(ctx);
+    });
+}
+
+int fgpu_nlist_copy_begin(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
+                          float* vectors_host)
+{
+    return guarded([&] {
+        require(nl != nullptr, FGPU_EINVALID, "null argument");
+        fgpu_ctx* ctx = nl->ctx;
+        bind_device(ctx);
+        size_t const nb = nl->n_bonds;
+        void* const dst[4] = {neighbors_host, distances_host, weights_host, vectors_host};
+        const void* const src[4] = {nl->neighbors.ptr, nl->distances.ptr, nl->weights.ptr, nl->vectors.ptr};
+        size_t const bytes[4] = {nb * 2 * sizeof(uint32_t), nb * sizeof(float), nb * sizeof(float), nb * 3 * sizeof(float)};
+        for (int k = 0; k < 4; ++k)
+        {
+            if (dst[k] == nullptr)
+            {
+                continue;
+            }
+            if (nl->copy_done[k] == nullptr)
+            {
+                FGPU_CUDA_CHECK(cudaEventCreateWithFlags(&nl->copy_done[k], cudaEventDisableTiming));
+            }
+            if (k == 2 && nl->unit_weights)
+            {
+                nl->pending_unit_weights = weights_host; // a constant: written by the host when somebody waits for it
+            }
+            else
+            {
+                d2h(ctx, dst[k], src[k], bytes[k]);
+            }
+            FGPU_CUDA_CHECK(cudaEventRecord(nl->copy_done[k], ctx->stream));
+        }
+    });
+}
+
+int fgpu_nlist_copy_wait(const fgpu_nlist* nl, unsigned which)
+{
+    return guarded([&] {
+        require(nl != nullptr, FGPU_EINVALID, "null argument");
+        bind_device(nl->ctx);
+        for (int k = 0; k < 4; ++k)
+        {
+            if ((which & (1U << k)) == 0 || nl->copy_done[k] == nullptr)
+            {
+                continue;
+            }
+            if (k == 2 && nl->pending_unit_weights != nullptr)
+            {
+                fill_unit_weights(nl->pending_unit_weights, nl->n_bonds);
+                nl->pending_unit_weights = nullptr;
+            }
+            FGPU_CUDA_CHECK(cudaEventSynchronize(nl->copy_done[k]));
+        }
     });
 }
 
@@ -1593,6 +1662,15 @@ void fgpu_nlist_destroy(fgpu_nlist* nl)
     if (nl != nullptr)
     {
         bind_quiet(nl->ctx);
+        for (cudaEvent_t& e : nl->copy_done)
+        {
+            if (e != nullptr)
+            {
+                cudaEventSynchronize(e); // a copy begun by fgpu_nlist_copy_begin still owns its host destination
+                cudaEventDestroy(e);
+                e = nullptr;
+            }
+        }
         if (nl->bytes() > nl->ctx->spare_nlist.bytes())
         {
             nl->swap(nl->ctx->spare_nlist); // keep the larger set for the next list, free the smaller one

@@ -240,6 +240,9 @@ struct fgpu_nlist : NlistStorage
     uint32_t n_points = 0;
     bool unit_weights = false; // built by a query: every weight is 1 (NeighborQuery.h:470-478)
     uint32_t q_index_offset = 0; // built by a query of a contiguous shard of the points: row k is point k + offset
+    // fgpu_nlist_copy_begin / _wait: one event behind each array's copy, and the ones still to be written on the host
+    mutable cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    mutable float* pending_unit_weights = nullptr;
 };
 
 // Peer-memory reduction state of one RDF (fgpu_rdf_attach_comm, peer.cuh)
@@ -440,6 +443,10 @@ struct Search2Args
     uint32_t temp_cap;
     uint32_t out_cap;               // hit records a warp can buffer per batch (dynamic shared memory)
     uint32_t* counts;               // per query (original order)
+    uint32_t* counts_copy;          // not null: the same values again (the array the row scan runs on: no D2D copy)
+    uint32_t* zero_words;           // not null: block 0 clears zero_n words there (the row scan's scratch) and ...
+    uint32_t zero_n;
+    uint32_t* zero_tail;            // ... *zero_tail (the element closing the row scan), instead of three memsets
     uint32_t* tmp_start;            // per query: offset of its row in the bag
     unsigned long long* cursor;     // bag records reserved so far (== total bonds at the end)
     int* fail;                      // != 0: the result cannot be represented by this path (1: points outside the box,

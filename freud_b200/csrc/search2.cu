@@ -147,6 +147,19 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
     float* __restrict__ const o_z = o_y + a.out_cap;
     const BoxDev& box = a.box;
 
+    if (MODE == S2_NL && blockIdx.x == 0 && a.zero_words != nullptr)
+    {
+        // housekeeping for the row scan that follows this kernel on the stream (also when the kernel gives up below:
+        // the scan still runs, on counts nobody reads, and must find its scratch clean)
+        for (uint32_t i = threadIdx.x; i < a.zero_n; i += blockDim.x)
+        {
+            a.zero_words[i] = 0U;
+        }
+        if (threadIdx.x == 0)
+        {
+            *a.zero_tail = 0U;
+        }
+    }
     // points or queries outside the box: image offsets are not implied by the cell walk -> general kernel
     if (*a.flag_points_outside != 0 || *a.flag_queries_outside != 0)
     {
@@ -321,6 +334,10 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
         {
             uint32_t const qi = w.qid[lane];
             a.counts[qi] = cnt;
+            if (a.counts_copy != nullptr)
+            {
+                a.counts_copy[qi] = cnt;
+            }
             a.tmp_start[qi] = ((uint32_t) base + (incl - cnt)) | a.tmp_flag;
             w.row_pos[lane] = incl - cnt;
             w.row_cnt[lane] = 0; // ready for the next batch
@@ -800,6 +817,9 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
 }
 
 // ---- emit: blocks over output rows, threads over the bonds of those rows ------------------------------------
+// (A variant that staged a row-id table and the keys of the block's window in shared memory and ranked in a second
+// pass was measured slower -- 147 us against 115 us at configs[1]: the second read of the records and two more block
+// barriers cost more than the binary search and the L1 re-reads they replaced.)
 // Ranks every hit inside its row (NeighborBond::less_as_tuple / less_as_distance restricted to one row with
 // weight == 1, freud/locality/NeighborBond.h:80-112) and writes the five NeighborList arrays
 // (NeighborQuery.h:470-478).  A block owns kEmitRows consecutive OUTPUT rows, so its stores cover one contiguous

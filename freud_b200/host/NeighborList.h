@@ -329,39 +329,30 @@ private:
         return std::make_shared<util::ManagedArray<T>>(std::move(shape), util::Uninitialized {});
     }
 
-    // D2H copy of the bond arrays asked for, each at most once, straight into page-locked arrays that the copy
-    // overwrites entirely (no zero fill)
+    // Device -> host copy of the bond arrays: the first getter starts all four transfers (page-locked destinations the
+    // copies overwrite entirely: no zero fill) and every getter waits for its own array only.
     void materialise(unsigned want = kAll) const
     {
         if (m_host_valid)
         {
             return;
         }
+        if (!m_copy_started)
+        {
+            m_neighbors = make_raw<unsigned int>({m_num_bonds, 2});
+            m_distances = make_raw<float>({m_num_bonds});
+            m_weights = make_raw<float>({m_num_bonds});
+            m_vectors = make_raw<float>({m_num_bonds, 3});
+            gpu::check(fgpu_nlist_copy_begin(m_dev.get(), m_neighbors->data(), m_distances->data(), m_weights->data(),
+                                             m_vectors->data()));
+            m_copy_started = true;
+        }
         want &= ~m_have;
         if (want == 0)
         {
             return;
         }
-        if (want & kNeighbors)
-        {
-            m_neighbors = make_raw<unsigned int>({m_num_bonds, 2});
-        }
-        if (want & kDistances)
-        {
-            m_distances = make_raw<float>({m_num_bonds});
-        }
-        if (want & kWeights)
-        {
-            m_weights = make_raw<float>({m_num_bonds});
-        }
-        if (want & kVectors)
-        {
-            m_vectors = make_raw<float>({m_num_bonds, 3});
-        }
-        gpu::check(fgpu_nlist_copy(m_dev.get(), (want & kNeighbors) ? m_neighbors->data() : nullptr,
-                                   (want & kDistances) ? m_distances->data() : nullptr,
-                                   (want & kWeights) ? m_weights->data() : nullptr,
-                                   (want & kVectors) ? m_vectors->data() : nullptr, nullptr, nullptr));
+        gpu::check(fgpu_nlist_copy_wait(m_dev.get(), want));
         m_have |= want;
         m_host_valid = m_have == kAll;
     }
@@ -399,6 +390,7 @@ private:
     mutable std::shared_ptr<util::ManagedArray<unsigned int>> m_counts, m_segments;
     mutable bool m_host_valid {false}, m_segments_valid {false};
     mutable unsigned m_have {0}; // bond arrays already on the host (device-built lists)
+    mutable bool m_copy_started {false};
     mutable std::shared_ptr<fgpu_nlist> m_dev;
     mutable fgpu_ctx* m_ctx {nullptr};
 };

@@ -182,6 +182,16 @@ uint32_t fgpu_nlist_num_points(const fgpu_nlist* nl);
 /* device -> host copy of any subset (NULL pointers are skipped) */
 int fgpu_nlist_copy(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
                     float* vectors_host, uint32_t* segments_host, uint32_t* counts_host);
+/* The same copy of the four bond arrays, split in two: _begin enqueues the transfers on the context's stream and
+ * returns (truly asynchronous into page-locked memory, fgpu_host_alloc), _wait blocks until the arrays named in `which`
+ * (bit 0 neighbors, 1 distances, 2 weights, 3 vectors) have landed -- unit weights of a query-built list are written
+ * by host threads at that point instead of crossing the link.  The host class behind freud's NeighborList starts all
+ * four on the first getter and waits per array: `nlist.distances` costs one array's latency, touching everything costs
+ * one pass over the link with the ones filled meanwhile.  The destinations must stay valid until the list is destroyed
+ * or every array was waited for. */
+int fgpu_nlist_copy_begin(const fgpu_nlist* nl, uint32_t* neighbors_host, float* distances_host, float* weights_host,
+                          float* vectors_host);
+int fgpu_nlist_copy_wait(const fgpu_nlist* nl, unsigned which);
 /* upload a host NeighborList (already sorted by query index) so RDF / Steinhardt can consume it:
  * replaces passing a NeighborList* into accumulate/compute (NeighborComputeFunctional.h:180-193, 121-135) */
 int fgpu_nlist_from_host(fgpu_ctx* ctx, uint64_t n_bonds, uint32_t n_query, uint32_t n_points,
