@@ -108,6 +108,8 @@ SIGNATURES = {
                                          _fp]),
     "fgpu_steinhardt_compute_keep": (C.c_int, [_vp, _vp, _up, C.c_uint32, C.c_int, C.c_uint32, _vp, _fp, _fp, _vpp, _fp,
                                               _fp]),
+    "fgpu_steinhardt_knn": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_int, _up, C.c_uint32, C.c_int, _fp,
+                                     _fp, _vpp, _fp, _fp]),
     "fgpu_buffer_bytes": (C.c_uint64, [_vp]),
     "fgpu_buffer_read": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
     "fgpu_buffer_destroy": (None, [_vp]),
@@ -376,6 +378,34 @@ class DevicePoints(_DeviceObject):
         check(lib().fgpu_local_density_query(self._h, ptr(q), nq, int(flavour), float(q_r_max), float(q_r_min),
                                              int(bool(exclude_ii)), float(r_max), float(diameter), ptr(num), ptr(den)))
         return num, den
+
+    def steinhardt_knn(self, num_neighbors, ls, r_max=np.inf, r_min=0.0, exclude_ii=True, flavour=FLAVOUR_IMAGE,
+                       want_qlm=False, out=None):
+        """Steinhardt over the k nearest neighbours of every point, query and sums in one call, no NeighborList
+        (``fgpu_steinhardt_knn``).  Returns ``ql``, ``sys_qlm``, ``order`` and, with ``want_qlm``, ``qlm``."""
+        ls = np.atleast_1d(np.asarray(ls, dtype=np.uint32)).copy()
+        n = self.n
+        tot_m = int(sum(2 * int(l) + 1 for l in ls))
+        out = out or {}
+        ql = out["ql"] if "ql" in out else np.empty((n, len(ls)), np.float32)
+        sys_qlm = np.empty(tot_m * 2, np.float32)
+        order = np.empty(len(ls), np.float32)
+        keep = _vp()
+        check(lib().fgpu_steinhardt_knn(self._h, int(flavour), int(num_neighbors), float(r_max), float(r_min),
+                                        int(bool(exclude_ii)), ptr(ls, _up), len(ls), 0, ptr(ql), None,
+                                        C.byref(keep) if want_qlm else None, ptr(sys_qlm), ptr(order)))
+        res = {"ql": ql.reshape(n, len(ls)), "sys_qlm": sys_qlm, "order": order}
+        if want_qlm:
+            flat = out["qlm"] if "qlm" in out else np.empty(n * tot_m * 2, np.float32)
+            check(lib().fgpu_buffer_read(keep, flat.ctypes.data_as(_vp), 0, flat.nbytes))
+            lib().fgpu_buffer_destroy(keep)
+            qlm, off = [], 0
+            for l in ls:
+                nm = 2 * int(l) + 1
+                qlm.append(flat[off:off + n * nm * 2].view(np.complex64).reshape(n, nm))
+                off += n * nm * 2
+            res["qlm"] = qlm
+        return res
 
     def steinhardt(self, nlist, ls, weighted=False, want_qlm=True, comm=None, n_total=0, out=None, average=False,
                    wl=False, wl_normalize=False):

@@ -12,6 +12,7 @@
 #include <limits>
 #include <nvtx3/nvToolsExt.h>
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1190,11 +1191,16 @@ int fgpu_ball_query_dev(fgpu_points* pts, const float* query_points_dev, uint32_
 // ---- kNN ---------------------------------------------------------------------------------------------
 static constexpr double kKnnWindowFill = 1.5;
 
-int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
-                   int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
-                   int sort_by_distance, fgpu_nlist** out)
+// bag_consumer: a compute that only needs the k nearest bond vectors of every row (Steinhardt without a NeighborList)
+// takes the window search's bag as it is -- rows grouped, unsorted -- instead of the selected, sorted list; it is
+// called once, when the warp-cooperative search has resolved every row, and *out then stays null.  When the frame
+// goes through the general kernels instead it is not called and *out is the list, as always.
+static void knn_query_body(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                           int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                           int sort_by_distance, fgpu_nlist** out,
+                           const std::function<void(const KnnSelectArgs&)>* bag_consumer)
 {
-    return guarded([&] {
+    {
         require(pts != nullptr && out != nullptr, FGPU_EINVALID, "null argument");
         // CellQuery::validateQueryArgs, CellQuery.h:180-184
         require(flavour != FGPU_FLAVOUR_GHOST, FGPU_ERUNTIME,
@@ -1378,6 +1384,20 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
                         continue;
                     }
                     uint64_t const n_bonds = ctx->h_scalars[3];
+                    if (bag_consumer != nullptr)
+                    {
+                        KnnSelectArgs sa;
+                        std::memset(&sa, 0, sizeof(sa));
+                        sa.bag = ctx->bag4.ptr;
+                        sa.bag2 = second_bag ? ctx->bag4b.ptr : nullptr;
+                        sa.tmp_start = ctx->tmp_start.ptr;
+                        sa.hits = ctx->knn_hits.ptr;
+                        sa.n_query = n_query;
+                        sa.k = k;
+                        (*bag_consumer)(sa);
+                        *out = nullptr;
+                        return;
+                    }
                     alloc_bonds(nl.get(), n_bonds);
                     if (n_bonds != 0)
                     {
@@ -1461,6 +1481,16 @@ int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_
         launch_segments(ctx, nl->row_start.ptr, nl->counts.ptr, nl->segments.ptr, n_query);
         sync(ctx);
         *out = nl.release();
+    }
+}
+
+int fgpu_knn_query(fgpu_points* pts, const float* query_points_host, uint32_t n_query, uint32_t q_index_offset,
+                   int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                   int sort_by_distance, fgpu_nlist** out)
+{
+    return guarded([&] {
+        knn_query_body(pts, query_points_host, n_query, q_index_offset, flavour, num_neighbors, r_max, r_min, exclude_ii,
+                       sort_by_distance, out, nullptr);
     });
 }
 
@@ -2891,15 +2921,20 @@ int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is
     });
 }
 
-static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
-                                   uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
-                                   fgpu_buffer** qlm_keep, float* sys_qlm_host, float* order_host)
+// fused: the neighbours are not a list but the bag of a k-nearest-neighbour window search over the points themselves
+// (nl == nullptr then): q_l / q_lm come out of k_knn_ylm, everything behind the kernels is shared.
+static void steinhardt_compute_body(fgpu_points* pts, const fgpu_nlist* nl, const KnnSelectArgs* fused,
+                                    const uint32_t* ls, uint32_t n_ls, int flags, uint32_t n_total, fgpu_comm* comm,
+                                    float* ql_host, float* wl_host, float* qlm_host, fgpu_buffer** qlm_keep,
+                                    float* sys_qlm_host, float* order_host, bool* fused_too_long)
 {
-    return guarded([&] {
-        require(pts != nullptr && nl != nullptr && ls != nullptr && n_ls != 0, FGPU_EINVALID, "null argument");
-        require(pts->ctx == nl->ctx, FGPU_EINVALID, "points and nlist belong to different contexts");
-        require(nl->n_points == pts->n, FGPU_EINVALID, "NeighborList was built for a different number of points");
-        require((uint64_t) nl->n_query + nl->q_index_offset <= pts->n, FGPU_EINVALID,
+    {
+        require(pts != nullptr && (nl != nullptr || fused != nullptr) && ls != nullptr && n_ls != 0, FGPU_EINVALID,
+                "null argument");
+        require(nl == nullptr || pts->ctx == nl->ctx, FGPU_EINVALID, "points and nlist belong to different contexts");
+        require(nl == nullptr || nl->n_points == pts->n, FGPU_EINVALID,
+                "NeighborList was built for a different number of points");
+        require(nl == nullptr || (uint64_t) nl->n_query + nl->q_index_offset <= pts->n, FGPU_EINVALID,
                 "NeighborList has more rows than there are points");
         bool const weighted = (flags & FGPU_ST_WEIGHTED) != 0, average = (flags & FGPU_ST_AVERAGE) != 0;
         bool const wl = (flags & FGPU_ST_WL) != 0, wl_normalize = wl && (flags & FGPU_ST_WL_NORMALIZE) != 0;
@@ -2913,7 +2948,7 @@ static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const
             // getWigner3j, freud/order/Wigner3j.cc: std::out_of_range beyond the tabulated range
             require(!wl || l <= 20, FGPU_ERANGE, "Wigner 3j coefficients are implemented for l <= 20.");
         }
-        uint32_t const n = nl->n_query; // rows held by this rank (== pts->n on a single GPU)
+        uint32_t const n = nl != nullptr ? nl->n_query : pts->n; // rows held by this rank (== pts->n on a single GPU)
         require(!average || n == pts->n, FGPU_ERUNTIME,
                 "Steinhardt average needs the q_lm of every neighbour: all rows must be on this rank");
         if (n_total == 0)
@@ -2945,18 +2980,35 @@ static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const
         a.xyz = pts->xyz.ptr;
         a.xyz4 = pts->xyz4.ptr;
         a.n = n;
-        a.row_offset = nl->q_index_offset;
-        a.neighbors = nl->neighbors.ptr;
-        a.distances = nl->distances.ptr;
-        a.weights = nl->weights.ptr;
-        a.row_start = nl->row_start.ptr;
+        a.row_offset = nl != nullptr ? nl->q_index_offset : 0;
+        a.neighbors = nl != nullptr ? nl->neighbors.ptr : nullptr;
+        a.distances = nl != nullptr ? nl->distances.ptr : nullptr;
+        a.weights = nl != nullptr ? nl->weights.ptr : nullptr;
+        a.row_start = nl != nullptr ? nl->row_start.ptr : nullptr;
         a.weighted = weighted;
         a.n_total = n_total;
         a.ql = d_ql.ptr;
         a.qlm = need_qlm ? d_qlm.ptr : nullptr;
         a.sys_qlm = average ? nullptr : d_sys.ptr; // the system sums come from the averaged q_lm then
         a.sys_partials = nullptr;
-        launch_steinhardt(ctx, a, lv);
+        if (fused != nullptr)
+        {
+            require(!average && knn_ylm_supported(lv, fused->k), FGPU_ERUNTIME, "fused kNN -> Ylm: unsupported options");
+            int* const flag = reinterpret_cast<int*>(ctx->d_scalars + 1);
+            FGPU_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), ctx->stream));
+            launch_knn_ylm(ctx, a, lv[0], *fused, flag);
+            d2h(ctx, ctx->h_scalars + 1, ctx->d_scalars + 1, sizeof(unsigned long long));
+            sync(ctx);
+            if ((ctx->h_scalars[1] & 0xffffffffULL) != 0)
+            {
+                *fused_too_long = true; // a row beyond the kernel's staging: the caller takes the NeighborList route
+                return;
+            }
+        }
+        else
+        {
+            launch_steinhardt(ctx, a, lv);
+        }
         if (average)
         {
             d_ql_ave.reserve((size_t) n * n_ls + 1);
@@ -3092,6 +3144,18 @@ static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const
             }
             off += 2 * (size_t) l + 1;
         }
+    }
+}
+
+static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
+                                   uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host, float* qlm_host,
+                                   fgpu_buffer** qlm_keep, float* sys_qlm_host, float* order_host)
+{
+    return guarded([&] {
+        require(nl != nullptr, FGPU_EINVALID, "null argument");
+        bool unused = false;
+        steinhardt_compute_body(pts, nl, nullptr, ls, n_ls, flags, n_total, comm, ql_host, wl_host, qlm_host, qlm_keep,
+                                sys_qlm_host, order_host, &unused);
     });
 }
 
@@ -3115,6 +3179,46 @@ int fgpu_steinhardt_compute_keep(fgpu_points* pts, const fgpu_nlist* nl, const u
     *qlm_dev_out = nullptr;
     return steinhardt_compute_impl(pts, nl, ls, n_ls, flags, n_total, comm, ql_host, wl_host, nullptr, qlm_dev_out,
                                    sys_qlm_host, order_host);
+}
+
+int fgpu_steinhardt_knn(fgpu_points* pts, int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                        const uint32_t* ls, uint32_t n_ls, int flags, float* ql_host, float* wl_host,
+                        fgpu_buffer** qlm_dev_out, float* sys_qlm_host, float* order_host)
+{
+    return guarded([&] {
+        require(pts != nullptr && ls != nullptr && n_ls != 0, FGPU_EINVALID, "null argument");
+        if (qlm_dev_out != nullptr)
+        {
+            *qlm_dev_out = nullptr;
+        }
+        std::vector<uint32_t> const lv(ls, ls + n_ls);
+        bool const fusable = (flags & (FGPU_ST_AVERAGE | FGPU_ST_WL)) == 0
+            && knn_ylm_supported(lv, std::min<uint32_t>(num_neighbors, pts->n));
+        bool done = false, too_long = false;
+        std::function<void(const KnnSelectArgs&)> const consumer = [&](const KnnSelectArgs& sa) {
+            steinhardt_compute_body(pts, nullptr, &sa, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
+                                    qlm_dev_out, sys_qlm_host, order_host, &too_long);
+            done = !too_long;
+        };
+        fgpu_nlist* nl = nullptr;
+        knn_query_body(pts, nullptr, pts->n, 0, flavour, num_neighbors, r_max, r_min, exclude_ii, 0, &nl,
+                       fusable ? &consumer : nullptr);
+        if (done)
+        {
+            return;
+        }
+        std::unique_ptr<fgpu_nlist, void (*)(fgpu_nlist*)> guard(nl, fgpu_nlist_destroy);
+        if (nl == nullptr)
+        {
+            // the fused kernel declined the frame (a row beyond its staging): the same query again, as a list
+            fgpu_nlist* again = nullptr;
+            knn_query_body(pts, nullptr, pts->n, 0, flavour, num_neighbors, r_max, r_min, exclude_ii, 0, &again, nullptr);
+            guard.reset(again);
+        }
+        bool unused = false;
+        steinhardt_compute_body(pts, guard.get(), nullptr, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
+                                qlm_dev_out, sys_qlm_host, order_host, &unused);
+    });
 }
 
 // ---- device buffers kept for a later read ----------------------------------------------------------------------

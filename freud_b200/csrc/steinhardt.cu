@@ -86,12 +86,20 @@ __device__ __forceinline__ BondIn load_bond(const SteinhardtArgs& a, uint32_t b)
     return in;
 }
 
+__device__ __forceinline__ Angles vector_angles(float dx, float dy, float dz, float dist);
+
 __device__ __forceinline__ Angles bond_angles(const SteinhardtArgs& args, float rx0, float ry0, float rz0, float px,
                                               float py, float pz, float dist)
 {
     float dx, dy, dz;
     wrap_quick(args.box, args.rcp_lx, args.rcp_ly, args.rcp_lz, __fsub_rn(px, rx0), __fsub_rn(py, ry0), __fsub_rn(pz, rz0), dx, dy,
                dz);
+    return vector_angles(dx, dy, dz, dist);
+}
+
+// sines and cosines of the two angles of a bond vector of length dist
+__device__ __forceinline__ Angles vector_angles(float dx, float dy, float dz, float dist)
+{
     // The reference takes phi = atan2(y, x) and theta = acos(clamp(z / d)) (Steinhardt.cc:161-174) and the
     // evaluator immediately goes back to sin/cos of both (spherical_harmonics.hpp:239-244, :272-281).  Here the
     // sines and cosines come straight from the components -- cos(theta) = clamp(z / d), sin(theta) =
@@ -139,109 +147,45 @@ __device__ __forceinline__ void block_sum_to(double v, double* dst)
     __syncthreads();
 }
 
-// ---- single l, everything unrolled into registers ---------------------------------------------------
-template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(SteinhardtArgs a)
+// One bond's Y_lm, m = 0..L, added to the particle's accumulators (the loop body of Steinhardt::baseCompute,
+// Steinhardt.cc:141-193, with fsph's evaluator unrolled into registers)
+template<int L> __device__ __forceinline__ void accumulate_ylm(const Angles& ang, float w, float* re, float* im)
 {
-    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    float re[L + 1], im[L + 1];
+    float sinpow = 1.0f;
+    float c = 1.0f, s = 0.0f; // exp(i m phi) by rotation, m = 0
 #pragma unroll
     for (int m = 0; m <= L; ++m)
     {
-        re[m] = 0.0f;
-        im[m] = 0.0f;
-    }
-    float total_weight = 0.0f;
-    bool const active = i < a.n;
-    // The bonds of the block's particles are one contiguous range of the list.  The block stages them chunk by
-    // chunk in shared memory -- coalesced reads of the index and distance arrays, one independent gather of the
-    // neighbour's position per thread -- and only then walks its rows: the per-row loop is a chain of dependent
-    // loads otherwise (index -> position), twelve deep, with nothing to overlap it.
-    __shared__ float s_px[kStageBonds], s_py[kStageBonds], s_pz[kStageBonds], s_dist[kStageBonds], s_w[kStageBonds];
-    uint32_t const i0 = blockIdx.x * blockDim.x, i1 = min(i0 + blockDim.x, a.n);
-    uint32_t const block_beg = a.row_start[i0], block_end = a.row_start[i1];
-    uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
-    float rx0 = 0.0f, ry0 = 0.0f, rz0 = 0.0f;
-    if (active)
-    {
-        size_t const pi = (size_t) i + a.row_offset;
-        rx0 = a.xyz[3 * pi];
-        ry0 = a.xyz[3 * pi + 1];
-        rz0 = a.xyz[3 * pi + 2];
-    }
-    for (uint32_t c0 = block_beg; c0 < block_end; c0 += kStageBonds)
-    {
-        uint32_t const c1 = min(c0 + (uint32_t) kStageBonds, block_end);
-        __syncthreads();
-        // seven bonds per thread at a time: all indices first, then all gathers (16-byte padded positions, one
-        // sector each), then the stores -- the hardware issues in order, so a gather that is consumed right
-        // away would leave one chain in flight per warp
+        // Jacobi recurrence in l' = l - m up to L - m (spherical_harmonics.hpp:246-270)
+        float j_prev = 0.0f, j_cur = c_jac0[m];
 #pragma unroll
-        for (int h = 0; h < kStageBonds / kThreads / kStageBatch; ++h)
+        for (int lp = 1; lp <= L - m; ++lp)
         {
-            uint32_t jj[kStageBatch];
-            float4 pp[kStageBatch];
-#pragma unroll
-            for (int k = 0; k < kStageBatch; ++k)
+            float next = ang.cphi * c_pref[L * m + (lp - 1)] * j_cur;
+            if (lp >= 2)
             {
-                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
-                jj[k] = b < c1 ? a.neighbors[2 * (size_t) b + 1] : 0U;
+                next += c_pref[L * (L + 1) + L * m + (lp - 1)] * j_prev;
             }
-#pragma unroll
-            for (int k = 0; k < kStageBatch; ++k)
-            {
-                pp[k] = __ldg(a.xyz4 + jj[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < kStageBatch; ++k)
-            {
-                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
-                if (b < c1)
-                {
-                    s_px[b - c0] = pp[k].x;
-                    s_py[b - c0] = pp[k].y;
-                    s_pz[b - c0] = pp[k].z;
-                    s_dist[b - c0] = a.distances[b];
-                    s_w[b - c0] = a.weighted ? a.weights[b] : 1.0f;
-                }
-            }
+            j_prev = j_cur;
+            j_cur = next;
         }
-        __syncthreads();
-        uint32_t const lo = max(beg, c0), hi = min(end, c1);
-        for (uint32_t b = lo; b < hi; ++b)
-        {
-            float const w = s_w[b - c0];
-            Angles const ang = bond_angles(a, rx0, ry0, rz0, s_px[b - c0], s_py[b - c0], s_pz[b - c0], s_dist[b - c0]);
-            float sinpow = 1.0f;
-            float c = 1.0f, s = 0.0f; // exp(i m phi) by rotation, m = 0
-#pragma unroll
-            for (int m = 0; m <= L; ++m)
-            {
-                // Jacobi recurrence in l' = l - m up to L - m (spherical_harmonics.hpp:246-270)
-                float j_prev = 0.0f, j_cur = c_jac0[m];
-#pragma unroll
-                for (int lp = 1; lp <= L - m; ++lp)
-                {
-                    float next = ang.cphi * c_pref[L * m + (lp - 1)] * j_cur;
-                    if (lp >= 2)
-                    {
-                        next += c_pref[L * (L + 1) + L * m + (lp - 1)] * j_prev;
-                    }
-                    j_prev = j_cur;
-                    j_cur = next;
-                }
-                float const legendre = sinpow * j_cur;                      // :272-281
-                float const amp = legendre; // / sqrt(2 pi) is folded into c_jac0
-                float const phase = (m & 1) ? -1.0f : 1.0f; // Steinhardt.cc:47-49
-                re[m] += w * (phase * (amp * c));           // exp(i m theta), :239-244
-                im[m] += w * (phase * (amp * s));
-                sinpow *= ang.sphi;
-                float const cn = c * ang.caz - s * ang.saz;
-                s = s * ang.caz + c * ang.saz;
-                c = cn;
-            }
-            total_weight += w;
-        }
+        float const legendre = sinpow * j_cur;                      // :272-281
+        float const amp = legendre; // / sqrt(2 pi) is folded into c_jac0
+        float const phase = (m & 1) ? -1.0f : 1.0f; // Steinhardt.cc:47-49
+        re[m] += w * (phase * (amp * c));           // exp(i m theta), :239-244
+        im[m] += w * (phase * (amp * s));
+        sinpow *= ang.sphi;
+        float const cn = c * ang.caz - s * ang.saz;
+        s = s * ang.caz + c * ang.saz;
+        c = cn;
     }
+}
+
+// normalise, q_l, outputs and the block's partial sums of the system q_lm; every thread of the block must call it
+template<int L>
+__device__ __forceinline__ void finish_particle(const SteinhardtArgs& a, uint32_t i, bool active, float* re, float* im,
+                                                float total_weight)
+{
     // normalise, q_l, outputs (Steinhardt.cc:195-220)
     float const nf = (float) (4.0 * 3.14159265358979323846 / (2 * L + 1));
     float sum = 0.0f;
@@ -319,6 +263,232 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
             a.sys_partials[(size_t) blockIdx.x * (2 * (L + 1)) + threadIdx.x] = v;
         }
     }
+}
+
+// ---- single l, everything unrolled into registers ---------------------------------------------------
+template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(SteinhardtArgs a)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    float re[L + 1], im[L + 1];
+#pragma unroll
+    for (int m = 0; m <= L; ++m)
+    {
+        re[m] = 0.0f;
+        im[m] = 0.0f;
+    }
+    float total_weight = 0.0f;
+    bool const active = i < a.n;
+    // The bonds of the block's particles are one contiguous range of the list.  The block stages them chunk by
+    // chunk in shared memory -- coalesced reads of the index and distance arrays, one independent gather of the
+    // neighbour's position per thread -- and only then walks its rows: the per-row loop is a chain of dependent
+    // loads otherwise (index -> position), twelve deep, with nothing to overlap it.
+    __shared__ float s_px[kStageBonds], s_py[kStageBonds], s_pz[kStageBonds], s_dist[kStageBonds], s_w[kStageBonds];
+    uint32_t const i0 = blockIdx.x * blockDim.x, i1 = min(i0 + blockDim.x, a.n);
+    uint32_t const block_beg = a.row_start[i0], block_end = a.row_start[i1];
+    uint32_t const beg = active ? a.row_start[i] : 0U, end = active ? a.row_start[i + 1] : 0U;
+    float rx0 = 0.0f, ry0 = 0.0f, rz0 = 0.0f;
+    if (active)
+    {
+        size_t const pi = (size_t) i + a.row_offset;
+        rx0 = a.xyz[3 * pi];
+        ry0 = a.xyz[3 * pi + 1];
+        rz0 = a.xyz[3 * pi + 2];
+    }
+    for (uint32_t c0 = block_beg; c0 < block_end; c0 += kStageBonds)
+    {
+        uint32_t const c1 = min(c0 + (uint32_t) kStageBonds, block_end);
+        __syncthreads();
+        // seven bonds per thread at a time: all indices first, then all gathers (16-byte padded positions, one
+        // sector each), then the stores -- the hardware issues in order, so a gather that is consumed right
+        // away would leave one chain in flight per warp
+#pragma unroll
+        for (int h = 0; h < kStageBonds / kThreads / kStageBatch; ++h)
+        {
+            uint32_t jj[kStageBatch];
+            float4 pp[kStageBatch];
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
+            {
+                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
+                jj[k] = b < c1 ? a.neighbors[2 * (size_t) b + 1] : 0U;
+            }
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
+            {
+                pp[k] = __ldg(a.xyz4 + jj[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < kStageBatch; ++k)
+            {
+                uint32_t const b = c0 + (uint32_t) (h * kStageBatch + k) * kThreads + threadIdx.x;
+                if (b < c1)
+                {
+                    s_px[b - c0] = pp[k].x;
+                    s_py[b - c0] = pp[k].y;
+                    s_pz[b - c0] = pp[k].z;
+                    s_dist[b - c0] = a.distances[b];
+                    s_w[b - c0] = a.weighted ? a.weights[b] : 1.0f;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t const lo = max(beg, c0), hi = min(end, c1);
+        for (uint32_t b = lo; b < hi; ++b)
+        {
+            float const w = s_w[b - c0];
+            Angles const ang = bond_angles(a, rx0, ry0, rz0, s_px[b - c0], s_py[b - c0], s_pz[b - c0], s_dist[b - c0]);
+            accumulate_ylm<L>(ang, w, re, im);
+            total_weight += w;
+        }
+    }
+    finish_particle<L>(a, i, active, re, im, total_weight);
+}
+
+// ---- k nearest neighbours -> Y_lm in one kernel (BASELINE.json configs[2]) ------------------------------------------
+// Steinhardt(l).compute(system, neighbors = {num_neighbors: k}) needs no NeighborList: the window search has left
+// every row's hits in the bag (16-byte records {bond vector, point index}, knn2.cu), and all this compute wants from
+// them is the k nearest bond vectors.  Phase A, a warp per row (lane = hit): squared lengths, rank of every hit among
+// the row's (ties at the k-th place by point index, as k_knn_select and the oracle resolve them), the kept vectors to
+// shared memory, transposed so that phase B reads them without bank conflicts.  Phase B, a thread per row: the Y_lm
+// recurrence over its <= k vectors in registers, q_l, q_lm and the block's share of the system sums -- the epilogue of
+// k_steinhardt_single.  Gone: the 28 B/bond NeighborList written by k_knn_select (336 MB at 1 M particles) and read
+// back with a gather per bond by k_steinhardt_single, and the row-offset scan between them.
+// Rows longer than kFusedStage hits (never at uniform density: the window holds 1.5 (k + 1) points on average) raise
+// *too_long and the host takes the two-kernel route for the frame.
+constexpr int kFusedRows = kThreads;  // rows per block
+constexpr int kFusedMaxK = 16;        // vectors kept per row
+constexpr uint32_t kFusedStage = 96;  // hits of a row a warp can rank
+
+struct KnnYlmArgs
+{
+    const float4* bag;
+    const float4* bag2;        // rows searched again with a wider window (top bit of tmp_start)
+    const uint32_t* tmp_start; // per row: offset of its hits in the bag
+    const uint32_t* hits;      // per row: number of hits in the window
+    uint32_t k;
+    int* too_long;
+};
+
+template<int L> __global__ void __launch_bounds__(kThreads) k_knn_ylm(SteinhardtArgs a, KnnYlmArgs s)
+{
+    __shared__ float4 s_bond[kFusedMaxK][kFusedRows]; // {x, y, z, distance}, [slot][row]: 32 KB
+    __shared__ uint32_t s_cnt[kFusedRows];
+    __shared__ __align__(16) float s_rsq[kThreads / 32][kFusedStage];
+    __shared__ __align__(16) uint32_t s_j[kThreads / 32][kFusedStage];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t const lt_mask = (1U << lane) - 1U;
+    float const inf = __int_as_float(0x7f800000);
+    uint32_t const i0 = blockIdx.x * kFusedRows;
+    float* const rsq = s_rsq[warp];
+    uint32_t* const js = s_j[warp];
+    // ---- phase A: warp w selects for rows i0 + w * 32 + r ------------------------------------------------------
+    for (int r = 0; r < 32; ++r)
+    {
+        uint32_t const local = (uint32_t) warp * 32U + (uint32_t) r;
+        uint32_t const row = i0 + local;
+        if (row >= a.n)
+        {
+            break; // uniform per warp
+        }
+        uint32_t const n = __ldg(s.hits + row);
+        uint32_t const ts = __ldg(s.tmp_start + row);
+        const float4* __restrict__ const bag = (ts & kSecondBag) != 0 ? s.bag2 + (ts & ~kSecondBag) : s.bag + ts;
+        uint32_t const kept = min(n, s.k);
+        if (lane == 0)
+        {
+            s_cnt[local] = n <= kFusedStage ? kept : 0U;
+        }
+        if (n > kFusedStage)
+        {
+            if (lane == 0)
+            {
+                *s.too_long = 1;
+            }
+            continue;
+        }
+        __syncwarp();
+        for (uint32_t h = lane; h < ((n + 3U) & ~3U); h += 32)
+        {
+            float4 const v = h < n ? bag[h] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0x7fffffffU));
+            rsq[h] = h < n ? dot_exact(v.x, v.y, v.z) : inf;
+            js[h] = __float_as_uint(v.w);
+        }
+        __syncwarp();
+        // Pass 1: hits closer than this one.  r_sq >= +0, so bit patterns order like values and (a - b) >> 31 is
+        // [a < b] in two instructions (the keys are padded with +inf to a multiple of four).  Hits whose count is
+        // below `kept` are the answer unless a group of equal r_sq straddles the k-th place; only then the slow
+        // pass with the point index as tie-break runs.
+        uint32_t const n4 = (n + 3U) & ~3U;
+        uint32_t n_seen = 0;
+        for (int pass = 0; pass < 2; ++pass)
+        {
+            n_seen = 0;
+            uint32_t n_keep = 0;
+            for (uint32_t h0 = 0; h0 < n; h0 += 32)
+            {
+                uint32_t const h = h0 + lane;
+                bool const act = h < n;
+                float const my_rsq = act ? rsq[h] : inf;
+                uint32_t before = 0;
+                if (pass == 0)
+                {
+                    uint32_t const mine = __float_as_uint(my_rsq);
+                    for (uint32_t i = 0; i < n4; i += 4)
+                    {
+                        uint4 const v = *reinterpret_cast<const uint4*>(rsq + i);
+                        before += (v.x - mine) >> 31;
+                        before += (v.y - mine) >> 31;
+                        before += (v.z - mine) >> 31;
+                        before += (v.w - mine) >> 31;
+                    }
+                }
+                else
+                {
+                    uint32_t const my_j = act ? js[h] : 0x7fffffffU;
+                    for (uint32_t i = 0; i < n; ++i)
+                    {
+                        float const v = rsq[i];
+                        before += (v < my_rsq || (v == my_rsq && js[i] < my_j)) ? 1U : 0U;
+                    }
+                }
+                bool const keep = act && before < kept;
+                unsigned const mk = __ballot_sync(0xffffffffU, keep);
+                n_keep += __popc(mk);
+                uint32_t const slot = n_seen + __popc(mk & lt_mask);
+                if (keep && slot < (uint32_t) kFusedMaxK)
+                {
+                    float4 const v = bag[h];
+                    s_bond[slot][local] = make_float4(v.x, v.y, v.z, __fsqrt_rn(my_rsq));
+                }
+                n_seen += __popc(mk);
+            }
+            if (n_keep == kept)
+            {
+                break; // no tie at the k-th place (the usual case): pass 0 was exact
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase B: thread t accumulates row i0 + t -------------------------------------------------------------
+    uint32_t const i = i0 + threadIdx.x;
+    bool const active = i < a.n;
+    float re[L + 1], im[L + 1];
+#pragma unroll
+    for (int m = 0; m <= L; ++m)
+    {
+        re[m] = 0.0f;
+        im[m] = 0.0f;
+    }
+    float total_weight = 0.0f;
+    uint32_t const cnt = active ? s_cnt[threadIdx.x] : 0U;
+    for (uint32_t b = 0; b < cnt; ++b)
+    {
+        float4 const v = s_bond[b][threadIdx.x];
+        Angles const ang = vector_angles(v.x, v.y, v.z, v.w);
+        accumulate_ylm<L>(ang, 1.0f, re, im);
+        total_weight += 1.0f;
+    }
+    finish_particle<L>(a, i, active, re, im, total_weight);
 }
 
 // Column sums of the per-block partials: one block per column, fixed summation order (bitwise reproducible).
@@ -657,7 +827,75 @@ template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a_in)
     }
 }
 
+template<int L> void launch_fused(fgpu_ctx* ctx, SteinhardtArgs a, const KnnYlmArgs& s)
+{
+    unsigned const blocks = (a.n + kFusedRows - 1) / kFusedRows;
+    uint32_t const width = 2 * (L + 1);
+    if (a.sys_qlm != nullptr)
+    {
+        ctx->st_partials.reserve((size_t) blocks * width);
+        a.sys_partials = ctx->st_partials.ptr;
+    }
+    k_knn_ylm<L><<<blocks, kThreads, 0, ctx->stream>>>(a, s);
+    if (a.sys_qlm != nullptr)
+    {
+        k_sum_partials<<<width, 256, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
+    }
+}
+
 } // namespace
+
+void ensure_steinhardt_tables(fgpu_ctx* ctx, const std::vector<uint32_t>& ls, int lmax)
+{
+    // the tables live in __constant__ memory, one copy per device: upload only when the l list changes
+    static std::mutex mtx;
+    static std::map<int, std::vector<uint32_t>> resident;
+    std::lock_guard<std::mutex> lock(mtx);
+    auto it = resident.find(ctx->device);
+    if (it == resident.end() || it->second != ls)
+    {
+        upload_tables(ctx, lmax, ls);
+        resident[ctx->device] = ls;
+    }
+}
+
+bool knn_ylm_supported(const std::vector<uint32_t>& ls, uint32_t k)
+{
+    if (ls.size() != 1 || k == 0 || k > (uint32_t) kFusedMaxK)
+    {
+        return false;
+    }
+    uint32_t const l = ls[0];
+    return l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12;
+}
+
+void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const KnnSelectArgs& src, int* too_long)
+{
+    ensure_steinhardt_tables(ctx, std::vector<uint32_t> {l}, (int) l);
+    if (a.n == 0)
+    {
+        return;
+    }
+    KnnYlmArgs s;
+    s.bag = src.bag;
+    s.bag2 = src.bag2;
+    s.tmp_start = src.tmp_start;
+    s.hits = src.hits;
+    s.k = src.k;
+    s.too_long = too_long;
+    KernelScope ks(ctx, "knn_ylm");
+    switch (l)
+    {
+    case 2: launch_fused<2>(ctx, a, s); break;
+    case 4: launch_fused<4>(ctx, a, s); break;
+    case 6: launch_fused<6>(ctx, a, s); break;
+    case 8: launch_fused<8>(ctx, a, s); break;
+    case 10: launch_fused<10>(ctx, a, s); break;
+    case 12: launch_fused<12>(ctx, a, s); break;
+    default: throw Error(FGPU_EINVALID, "knn_ylm: unsupported l");
+    }
+    FGPU_CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector<uint32_t>& ls)
 {
@@ -676,18 +914,7 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
     {
         throw Error(FGPU_EINVALID, "Steinhardt: unsupported list of l values");
     }
-    {
-        // the tables live in __constant__ memory, one copy per device: upload only when the l list changes
-        static std::mutex mtx;
-        static std::map<int, std::vector<uint32_t>> resident;
-        std::lock_guard<std::mutex> lock(mtx);
-        auto it = resident.find(ctx->device);
-        if (it == resident.end() || it->second != ls)
-        {
-            upload_tables(ctx, lmax, ls);
-            resident[ctx->device] = ls;
-        }
-    }
+    ensure_steinhardt_tables(ctx, ls, lmax);
     if (a.n == 0)
     {
         return;

@@ -82,12 +82,26 @@ public:
                  const std::shared_ptr<locality::NeighborQuery>& points, const locality::QueryArgs& qargs)
     {
         unsigned int const Np = points->getNPoints();
-        // neighbours: the list handed in, or the default query over the points themselves
-        // (loopOverNeighborsIterator, NeighborComputeFunctional.h:112-150)
+        // Neighbours: the list handed in, or the default query over the points themselves
+        // (loopOverNeighborsIterator, NeighborComputeFunctional.h:112-150).  A nearest-neighbour query made for this
+        // compute alone never becomes a list: fgpu_steinhardt_knn searches and accumulates in one call.
         std::shared_ptr<locality::NeighborList> list = nlist;
+        locality::QueryArgs knn_args = qargs;
+        bool fused = false;
         if (!list)
         {
-            list = points->query(points->getPoints(), Np, qargs)->toNeighborList();
+            points->validateQueryArgs(knn_args); // infers the mode, fills the defaults, raises like query() would
+            vec3<bool> const periodic = points->getBox().getPeriodic();
+            if (!(periodic.x && periodic.y && periodic.z))
+            {
+                throw std::domain_error("Pair queries in a non-periodic box are not implemented.");
+            }
+            fused = knn_args.mode == locality::QueryType::nearest && !m_average && !m_wl
+                && points->getFlavour() != FGPU_FLAVOUR_GHOST;
+            if (!fused)
+            {
+                list = points->query(points->getPoints(), Np, qargs)->toNeighborList();
+            }
         }
         else
         {
@@ -112,9 +126,18 @@ public:
         int const flags = (m_weighted ? FGPU_ST_WEIGHTED : 0) | (m_average ? FGPU_ST_AVERAGE : 0)
             | (m_wl ? FGPU_ST_WL : 0) | (m_wl_normalize ? FGPU_ST_WL_NORMALIZE : 0);
         fgpu_buffer* keep = nullptr;
-        gpu::check(fgpu_steinhardt_compute_keep(points->device(), list->device(gpu::context()), m_ls.data(),
-                                                (uint32_t) m_ls.size(), flags, Np, nullptr, qli->data(),
-                                                wli ? wli->data() : nullptr, &keep, sys.data(), order.data()));
+        if (fused)
+        {
+            gpu::check(fgpu_steinhardt_knn(points->device(), points->getFlavour(), knn_args.num_neighbors, knn_args.r_max,
+                                           knn_args.r_min, knn_args.exclude_ii ? 1 : 0, m_ls.data(), (uint32_t) m_ls.size(),
+                                           flags, qli->data(), nullptr, &keep, sys.data(), order.data()));
+        }
+        else
+        {
+            gpu::check(fgpu_steinhardt_compute_keep(points->device(), list->device(gpu::context()), m_ls.data(),
+                                                    (uint32_t) m_ls.size(), flags, Np, nullptr, qli->data(),
+                                                    wli ? wli->data() : nullptr, &keep, sys.data(), order.data()));
+        }
         m_qlm_dev = std::shared_ptr<fgpu_buffer>(keep, fgpu_buffer_destroy);
         for (auto& arr : m_qlmi)
         {

@@ -385,6 +385,17 @@ int fgpu_steinhardt_compute(fgpu_points* pts, const fgpu_nlist* nl, const uint32
 int fgpu_steinhardt_compute_keep(fgpu_points* pts, const fgpu_nlist* nl, const uint32_t* ls, uint32_t n_ls, int flags,
                                  uint32_t n_total, fgpu_comm* comm, float* ql_host, float* wl_host,
                                  fgpu_buffer** qlm_dev_out, float* sys_qlm_host, float* order_host);
+/* Steinhardt::compute(nlist = nullptr, points, {mode nearest, num_neighbors}) in one call (BASELINE.json configs[2];
+ * loopOverNeighborsIterator's query-on-the-fly branch, NeighborComputeFunctional.h:137-178): the k-nearest-neighbour
+ * search of the points themselves and the Y_lm sums over its result, with no NeighborList in between -- the window
+ * search leaves every row's hits in device memory and one kernel picks the k nearest bond vectors of a row and
+ * accumulates q_lm over them (freud_b200/csrc/steinhardt.cu k_knn_ylm).  A single l in {2, 4, ..., 12}, k <= 16 and
+ * flags without FGPU_ST_AVERAGE / FGPU_ST_WL take that route; everything else (and frames the warp-cooperative search
+ * does not take) builds the list and calls the kernels of fgpu_steinhardt_compute_keep: same results either way
+ * (q_l to float summation order).  Outputs as fgpu_steinhardt_compute_keep; qlm_dev_out may be NULL. */
+int fgpu_steinhardt_knn(fgpu_points* pts, int flavour, uint32_t num_neighbors, float r_max, float r_min, int exclude_ii,
+                        const uint32_t* ls, uint32_t n_ls, int flags, float* ql_host, float* wl_host,
+                        fgpu_buffer** qlm_dev_out, float* sys_qlm_host, float* order_host);
 uint64_t fgpu_buffer_bytes(const fgpu_buffer* buf);
 int fgpu_buffer_read(fgpu_buffer* buf, void* host, uint64_t offset_bytes, uint64_t bytes);
 void fgpu_buffer_destroy(fgpu_buffer* buf);

@@ -823,3 +823,39 @@ def test_medium_system_properties(ctx, flavour):
     rdf = capi.DeviceRDF(ctx, 100, 3.0)
     rdf.accumulate(dp, None, flavour, 3.0, 0.0, True)
     assert np.array_equal(rdf.read(), port.rdf_accumulate_distances(got["distances"], 100, 3.0))
+
+
+@pytest.mark.parametrize("flavour", [IMAGE, WRAP])
+def test_steinhardt_knn_fused_matches_list_route(ctx, flavour):
+    """fgpu_steinhardt_knn: the k nearest of every row picked out of the window search's bag and their Y_lm sums in
+    one kernel must give what the NeighborList route gives (q_l to summation order: the list is sorted by j, the bag is
+    not) and what the oracle gives (1e-5); ties, short rows (k > neighbours in r_max) and k = n - 1 included."""
+    from freud_b200 import data
+
+    capi = _capi()
+    box, pts = data.make_fcc_system(7, sigma_noise=0.05, seed=4)
+    dp = capi.DevicePoints(ctx, box, pts)
+    for l, k in ((6, 12), (4, 6), (12, 16)):
+        fused = dp.steinhardt_knn(k, [l], exclude_ii=True, flavour=flavour, want_qlm=True)
+        nl = dp.knn_query(None, k, exclude_ii=True, flavour=flavour)
+        listed = dp.steinhardt(nl, [l])
+        assert np.allclose(fused["ql"], listed["ql"], rtol=2e-6, atol=1e-7), (l, k)
+        assert np.allclose(fused["qlm"][0], listed["qlm"][0], atol=2e-6)
+        assert np.allclose(fused["order"], listed["order"], rtol=1e-5)
+    pnl = port.knn_nlist(box, False, pts, pts, 12, exclude_ii=True, flavour=port.IMAGE if flavour == IMAGE else port.WRAP)
+    want = port.steinhardt(box, False, pts, pnl, [6])["ql"]
+    assert np.allclose(dp.steinhardt_knn(12, [6], exclude_ii=True, flavour=flavour)["ql"], want, rtol=1e-5, atol=1e-6)
+    # a perfect lattice: twelve exactly tied nearest neighbours, then a gap -- k = 8 cuts through the tie group
+    lbox, lpts = data.make_fcc_system(5)
+    dl = capi.DevicePoints(ctx, lbox, lpts)
+    f8 = dl.steinhardt_knn(8, [6], exclude_ii=True, flavour=flavour)["ql"]
+    l8 = dl.steinhardt(dl.knn_query(None, 8, exclude_ii=True, flavour=flavour), [6])["ql"]
+    assert np.allclose(f8, l8, rtol=2e-6, atol=1e-7)
+    # r_max so small that most rows hold fewer than k neighbours; unsupported l / k fall back to the list inside the call
+    short = dp.steinhardt_knn(12, [6], r_max=0.72, exclude_ii=True, flavour=flavour)["ql"]
+    short_l = dp.steinhardt(dp.knn_query(None, 12, r_max=0.72, exclude_ii=True, flavour=flavour), [6])["ql"]
+    assert np.array_equal(np.isnan(short), np.isnan(short_l))
+    assert np.allclose(short[~np.isnan(short)], short_l[~np.isnan(short_l)], rtol=2e-6, atol=1e-7)
+    odd = dp.steinhardt_knn(20, [5, 7], exclude_ii=True, flavour=flavour)["ql"]
+    odd_l = dp.steinhardt(dp.knn_query(None, 20, exclude_ii=True, flavour=flavour), [5, 7])["ql"]
+    assert np.allclose(odd, odd_l, rtol=2e-6, atol=1e-7)
