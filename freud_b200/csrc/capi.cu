@@ -2923,7 +2923,7 @@ int fgpu_local_density(const fgpu_nlist* nl, float r_max, float diameter, int is
 
 // fused: the neighbours are not a list but the bag of a k-nearest-neighbour window search over the points themselves
 // (nl == nullptr then): q_l / q_lm come out of k_knn_ylm, everything behind the kernels is shared.
-static void steinhardt_compute_body(fgpu_points* pts, const fgpu_nlist* nl, const KnnSelectArgs* fused,
+static void steinhardt_compute_body(fgpu_points* pts, const fgpu_nlist* nl, const KnnSelectArgs* fused, int fused_flavour,
                                     const uint32_t* ls, uint32_t n_ls, int flags, uint32_t n_total, fgpu_comm* comm,
                                     float* ql_host, float* wl_host, float* qlm_host, fgpu_buffer** qlm_keep,
                                     float* sys_qlm_host, float* order_host, bool* fused_too_long)
@@ -2994,16 +2994,7 @@ static void steinhardt_compute_body(fgpu_points* pts, const fgpu_nlist* nl, cons
         if (fused != nullptr)
         {
             require(!average && knn_ylm_supported(lv, fused->k), FGPU_ERUNTIME, "fused kNN -> Ylm: unsupported options");
-            int* const flag = reinterpret_cast<int*>(ctx->d_scalars + 1);
-            FGPU_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), ctx->stream));
-            launch_knn_ylm(ctx, a, lv[0], *fused, flag);
-            d2h(ctx, ctx->h_scalars + 1, ctx->d_scalars + 1, sizeof(unsigned long long));
-            sync(ctx);
-            if ((ctx->h_scalars[1] & 0xffffffffULL) != 0)
-            {
-                *fused_too_long = true; // a row beyond the kernel's staging: the caller takes the NeighborList route
-                return;
-            }
+            launch_knn_ylm(ctx, a, lv[0], *fused);
         }
         else
         {
@@ -3154,7 +3145,7 @@ static int steinhardt_compute_impl(fgpu_points* pts, const fgpu_nlist* nl, const
     return guarded([&] {
         require(nl != nullptr, FGPU_EINVALID, "null argument");
         bool unused = false;
-        steinhardt_compute_body(pts, nl, nullptr, ls, n_ls, flags, n_total, comm, ql_host, wl_host, qlm_host, qlm_keep,
+        steinhardt_compute_body(pts, nl, nullptr, 0, ls, n_ls, flags, n_total, comm, ql_host, wl_host, qlm_host, qlm_keep,
                                 sys_qlm_host, order_host, &unused);
     });
 }
@@ -3196,7 +3187,7 @@ int fgpu_steinhardt_knn(fgpu_points* pts, int flavour, uint32_t num_neighbors, f
             && knn_ylm_supported(lv, std::min<uint32_t>(num_neighbors, pts->n));
         bool done = false, too_long = false;
         std::function<void(const KnnSelectArgs&)> const consumer = [&](const KnnSelectArgs& sa) {
-            steinhardt_compute_body(pts, nullptr, &sa, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
+            steinhardt_compute_body(pts, nullptr, &sa, flavour, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
                                     qlm_dev_out, sys_qlm_host, order_host, &too_long);
             done = !too_long;
         };
@@ -3216,7 +3207,7 @@ int fgpu_steinhardt_knn(fgpu_points* pts, int flavour, uint32_t num_neighbors, f
             guard.reset(again);
         }
         bool unused = false;
-        steinhardt_compute_body(pts, guard.get(), nullptr, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
+        steinhardt_compute_body(pts, guard.get(), nullptr, 0, ls, n_ls, flags, pts->n, nullptr, ql_host, wl_host, nullptr,
                                 qlm_dev_out, sys_qlm_host, order_host, &unused);
     });
 }

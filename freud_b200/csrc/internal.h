@@ -665,7 +665,7 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& args, const std::vec
 void launch_pad_positions(fgpu_ctx* ctx, const float* xyz, uint32_t n, float4* out);
 // k nearest of every bag row -> Y_lm, one kernel (steinhardt.cu k_knn_ylm); single l in {2, 4, .., 12}, k <= 16
 bool knn_ylm_supported(const std::vector<uint32_t>& ls, uint32_t k);
-void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const KnnSelectArgs& src, int* too_long);
+void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const KnnSelectArgs& src);
 
 // follow-up kernels over the per-particle q_lm array (the l tables of launch_steinhardt must be resident)
 struct SteinhardtAveArgs

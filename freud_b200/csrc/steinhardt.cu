@@ -347,17 +347,18 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_steinhardt_single(
 // ---- k nearest neighbours -> Y_lm in one kernel (BASELINE.json configs[2]) ------------------------------------------
 // Steinhardt(l).compute(system, neighbors = {num_neighbors: k}) needs no NeighborList: the window search has left
 // every row's hits in the bag (16-byte records {bond vector, point index}, knn2.cu), and all this compute wants from
-// them is the k nearest bond vectors.  Phase A, a warp per row (lane = hit): squared lengths, rank of every hit among
-// the row's (ties at the k-th place by point index, as k_knn_select and the oracle resolve them), the kept vectors to
-// shared memory, transposed so that phase B reads them without bank conflicts.  Phase B, a thread per row: the Y_lm
-// recurrence over its <= k vectors in registers, q_l, q_lm and the block's share of the system sums -- the epilogue of
-// k_steinhardt_single.  Gone: the 28 B/bond NeighborList written by k_knn_select (336 MB at 1 M particles) and read
-// back with a gather per bond by k_steinhardt_single, and the row-offset scan between them.
-// Rows longer than kFusedStage hits (never at uniform density: the window holds 1.5 (k + 1) points on average) raise
-// *too_long and the host takes the two-kernel route for the frame.
-constexpr int kFusedRows = kThreads;  // rows per block
-constexpr int kFusedMaxK = 16;        // vectors kept per row
-constexpr uint32_t kFusedStage = 96;  // hits of a row a warp can rank
+// them is WHICH k points are nearest.  One thread per row: it streams its row of the bag, keeps the k smallest keys
+// (bits(r_sq) << 32 | point index -- r_sq >= +0, so the bit pattern orders like the value, and ties at the k-th place
+// fall to the point index as in k_knn_select and the oracle) in a sorted array that lives in registers (branch-free
+// insertion: K'[i] = min(K[i], max(x, K[i-1]))), then gathers the k positions and runs the Y_lm recurrence over
+// Box::wrap(p_j - p_i) exactly as k_steinhardt_single does -- the reference evaluates Y_lm on the wrapped difference
+// (Steinhardt.cc:155), whose float32 round trip moves a component by a few 1e-6, so the bag's own (IMAGE-arithmetic)
+// vector would drift from the reference by more than the 1e-5 this path promises.
+// Gone: k_knn_select (a warp per row ranking, ordering and writing a 28 B/bond NeighborList: 336 MB at 1 M particles),
+// the row-offset scan, and k_steinhardt_single's staging of that list.  A first fused version kept the warp-per-row
+// selection and handed the vectors to a thread per row through shared memory: 437 us against 337 + 180 us for the two
+// kernels it replaced -- the selection leaves a third of the lanes idle and pays ~150 instructions per row.
+constexpr int kFusedMaxK = 16; // neighbours per row this route serves
 
 struct KnnYlmArgs
 {
@@ -366,112 +367,35 @@ struct KnnYlmArgs
     const uint32_t* tmp_start; // per row: offset of its hits in the bag
     const uint32_t* hits;      // per row: number of hits in the window
     uint32_t k;
-    int* too_long;
 };
 
-template<int L> __global__ void __launch_bounds__(kThreads) k_knn_ylm(SteinhardtArgs a, KnnYlmArgs s)
+template<int L, int KMAX> __global__ void __launch_bounds__(kThreads) k_knn_ylm(SteinhardtArgs a, KnnYlmArgs s)
 {
-    __shared__ float4 s_bond[kFusedMaxK][kFusedRows]; // {x, y, z, distance}, [slot][row]: 32 KB
-    __shared__ uint32_t s_cnt[kFusedRows];
-    __shared__ __align__(16) float s_rsq[kThreads / 32][kFusedStage];
-    __shared__ __align__(16) uint32_t s_j[kThreads / 32][kFusedStage];
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t const lt_mask = (1U << lane) - 1U;
-    float const inf = __int_as_float(0x7f800000);
-    uint32_t const i0 = blockIdx.x * kFusedRows;
-    float* const rsq = s_rsq[warp];
-    uint32_t* const js = s_j[warp];
-    // ---- phase A: warp w selects for rows i0 + w * 32 + r ------------------------------------------------------
-    for (int r = 0; r < 32; ++r)
-    {
-        uint32_t const local = (uint32_t) warp * 32U + (uint32_t) r;
-        uint32_t const row = i0 + local;
-        if (row >= a.n)
-        {
-            break; // uniform per warp
-        }
-        uint32_t const n = __ldg(s.hits + row);
-        uint32_t const ts = __ldg(s.tmp_start + row);
-        const float4* __restrict__ const bag = (ts & kSecondBag) != 0 ? s.bag2 + (ts & ~kSecondBag) : s.bag + ts;
-        uint32_t const kept = min(n, s.k);
-        if (lane == 0)
-        {
-            s_cnt[local] = n <= kFusedStage ? kept : 0U;
-        }
-        if (n > kFusedStage)
-        {
-            if (lane == 0)
-            {
-                *s.too_long = 1;
-            }
-            continue;
-        }
-        __syncwarp();
-        for (uint32_t h = lane; h < ((n + 3U) & ~3U); h += 32)
-        {
-            float4 const v = h < n ? bag[h] : make_float4(inf, 0.0f, 0.0f, __uint_as_float(0x7fffffffU));
-            rsq[h] = h < n ? dot_exact(v.x, v.y, v.z) : inf;
-            js[h] = __float_as_uint(v.w);
-        }
-        __syncwarp();
-        // Pass 1: hits closer than this one.  r_sq >= +0, so bit patterns order like values and (a - b) >> 31 is
-        // [a < b] in two instructions (the keys are padded with +inf to a multiple of four).  Hits whose count is
-        // below `kept` are the answer unless a group of equal r_sq straddles the k-th place; only then the slow
-        // pass with the point index as tie-break runs.
-        uint32_t const n4 = (n + 3U) & ~3U;
-        uint32_t n_seen = 0;
-        for (int pass = 0; pass < 2; ++pass)
-        {
-            n_seen = 0;
-            uint32_t n_keep = 0;
-            for (uint32_t h0 = 0; h0 < n; h0 += 32)
-            {
-                uint32_t const h = h0 + lane;
-                bool const act = h < n;
-                float const my_rsq = act ? rsq[h] : inf;
-                uint32_t before = 0;
-                if (pass == 0)
-                {
-                    uint32_t const mine = __float_as_uint(my_rsq);
-                    for (uint32_t i = 0; i < n4; i += 4)
-                    {
-                        uint4 const v = *reinterpret_cast<const uint4*>(rsq + i);
-                        before += (v.x - mine) >> 31;
-                        before += (v.y - mine) >> 31;
-                        before += (v.z - mine) >> 31;
-                        before += (v.w - mine) >> 31;
-                    }
-                }
-                else
-                {
-                    uint32_t const my_j = act ? js[h] : 0x7fffffffU;
-                    for (uint32_t i = 0; i < n; ++i)
-                    {
-                        float const v = rsq[i];
-                        before += (v < my_rsq || (v == my_rsq && js[i] < my_j)) ? 1U : 0U;
-                    }
-                }
-                bool const keep = act && before < kept;
-                unsigned const mk = __ballot_sync(0xffffffffU, keep);
-                n_keep += __popc(mk);
-                uint32_t const slot = n_seen + __popc(mk & lt_mask);
-                if (keep && slot < (uint32_t) kFusedMaxK)
-                {
-                    float4 const v = bag[h];
-                    s_bond[slot][local] = make_float4(v.x, v.y, v.z, __fsqrt_rn(my_rsq));
-                }
-                n_seen += __popc(mk);
-            }
-            if (n_keep == kept)
-            {
-                break; // no tie at the k-th place (the usual case): pass 0 was exact
-            }
-        }
-    }
-    __syncthreads();
-    // ---- phase B: thread t accumulates row i0 + t -------------------------------------------------------------
-    uint32_t const i = i0 + threadIdx.x;
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     bool const active = i < a.n;
+    uint32_t const n = active ? __ldg(s.hits + i) : 0U;
+    uint32_t const ts = active ? __ldg(s.tmp_start + i) : 0U;
+    const float4* __restrict__ const bag = (ts & kSecondBag) != 0 ? s.bag2 + (ts & ~kSecondBag) : s.bag + ts;
+    unsigned long long key[KMAX];
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q)
+    {
+        key[q] = ~0ULL;
+    }
+    for (uint32_t h = 0; h < n; ++h)
+    {
+        float4 const v = bag[h];
+        unsigned long long const x
+            = ((unsigned long long) __float_as_uint(dot_exact(v.x, v.y, v.z)) << 32) | __float_as_uint(v.w);
+#pragma unroll
+        for (int q = KMAX - 1; q >= 1; --q)
+        {
+            unsigned long long const up = key[q - 1] > x ? key[q - 1] : x;
+            key[q] = key[q] < up ? key[q] : up;
+        }
+        key[0] = key[0] < x ? key[0] : x;
+    }
+    uint32_t const kept = min(min(n, s.k), (uint32_t) KMAX);
     float re[L + 1], im[L + 1];
 #pragma unroll
     for (int m = 0; m <= L; ++m)
@@ -480,13 +404,35 @@ template<int L> __global__ void __launch_bounds__(kThreads) k_knn_ylm(Steinhardt
         im[m] = 0.0f;
     }
     float total_weight = 0.0f;
-    uint32_t const cnt = active ? s_cnt[threadIdx.x] : 0U;
-    for (uint32_t b = 0; b < cnt; ++b)
+    float rx0 = 0.0f, ry0 = 0.0f, rz0 = 0.0f;
+    if (active)
     {
-        float4 const v = s_bond[b][threadIdx.x];
-        Angles const ang = vector_angles(v.x, v.y, v.z, v.w);
-        accumulate_ylm<L>(ang, 1.0f, re, im);
-        total_weight += 1.0f;
+        rx0 = a.xyz[3 * (size_t) i];
+        ry0 = a.xyz[3 * (size_t) i + 1];
+        rz0 = a.xyz[3 * (size_t) i + 2];
+    }
+    // the kept points' positions, four gathers in flight, then their Y_lm
+#pragma unroll
+    for (int q0 = 0; q0 < KMAX; q0 += 4)
+    {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            bool const live = (uint32_t) (q0 + u) < kept;
+            p[u] = live ? __ldg(a.xyz4 + (uint32_t) (key[q0 + u] & 0xffffffffULL)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            if ((uint32_t) (q0 + u) < kept)
+            {
+                float const dist = __fsqrt_rn(__uint_as_float((uint32_t) (key[q0 + u] >> 32))); // NeighborBond.h:41-44
+                Angles const ang = bond_angles(a, rx0, ry0, rz0, p[u].x, p[u].y, p[u].z, dist);
+                accumulate_ylm<L>(ang, 1.0f, re, im);
+                total_weight += 1.0f;
+            }
+        }
     }
     finish_particle<L>(a, i, active, re, im, total_weight);
 }
@@ -829,14 +775,21 @@ template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a_in)
 
 template<int L> void launch_fused(fgpu_ctx* ctx, SteinhardtArgs a, const KnnYlmArgs& s)
 {
-    unsigned const blocks = (a.n + kFusedRows - 1) / kFusedRows;
+    unsigned const blocks = (a.n + kThreads - 1) / kThreads;
     uint32_t const width = 2 * (L + 1);
     if (a.sys_qlm != nullptr)
     {
         ctx->st_partials.reserve((size_t) blocks * width);
         a.sys_partials = ctx->st_partials.ptr;
     }
-    k_knn_ylm<L><<<blocks, kThreads, 0, ctx->stream>>>(a, s);
+    if (s.k <= 12)
+    {
+        k_knn_ylm<L, 12><<<blocks, kThreads, 0, ctx->stream>>>(a, s);
+    }
+    else
+    {
+        k_knn_ylm<L, kFusedMaxK><<<blocks, kThreads, 0, ctx->stream>>>(a, s);
+    }
     if (a.sys_qlm != nullptr)
     {
         k_sum_partials<<<width, 256, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
@@ -869,7 +822,7 @@ bool knn_ylm_supported(const std::vector<uint32_t>& ls, uint32_t k)
     return l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12;
 }
 
-void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const KnnSelectArgs& src, int* too_long)
+void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const KnnSelectArgs& src)
 {
     ensure_steinhardt_tables(ctx, std::vector<uint32_t> {l}, (int) l);
     if (a.n == 0)
@@ -882,7 +835,6 @@ void launch_knn_ylm(fgpu_ctx* ctx, const SteinhardtArgs& a, uint32_t l, const Kn
     s.tmp_start = src.tmp_start;
     s.hits = src.hits;
     s.k = src.k;
-    s.too_long = too_long;
     KernelScope ks(ctx, "knn_ylm");
     switch (l)
     {
