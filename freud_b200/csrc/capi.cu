@@ -618,7 +618,6 @@ bool rdf_accumulate_impl(fgpu_rdf* rdf, fgpu_points* pts, const float* q_host, c
                 s2.push = 1;
                 s2.done_counter = reinterpret_cast<unsigned int*>(ctx->d_scalars + 6) + 1; // zeroed just above
                 s2.peer = rdf->peer->box;
-                s2.peer.parity = (uint32_t) (rdf->peer->epoch & 1U);
                 pushed = true;
             }
             launch_search2(ctx, flavour, S2_RDF, s2);
@@ -1834,8 +1833,7 @@ void peer_reduce(fgpu_rdf* rdf, bool already_pushed)
 {
     fgpu_ctx* ctx = rdf->ctx;
     fgpu_rdf_peer* pr = rdf->peer;
-    PeerBox pb = pr->box;
-    pb.parity = (uint32_t) (pr->epoch & 1U);
+    PeerBox const pb = pr->box; // the epoch's parity lives in the mailbox: nothing here changes from call to call
     if (!already_pushed)
     {
         launch_rdf_push(ctx, pb, rdf->hist.ptr, rdf->axis.bins);
@@ -1962,7 +1960,6 @@ int fgpu_rdf_attach_comm(fgpu_rdf* rdf, fgpu_comm* comm)
         pr->box.world = world;
         pr->box.rank = comm->rank;
         pr->box.bins_pad = bins_pad;
-        pr->box.parity = 0;
         rdf->reduced.reserve((size_t) rdf->axis.bins + 1);
         FGPU_CUDA_CHECK(cudaMemsetAsync(rdf->reduced.ptr, 0, ((size_t) rdf->axis.bins + 1) * sizeof(uint32_t), ctx->stream));
         sync(ctx);

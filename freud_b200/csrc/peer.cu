@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) k_rdf_wait(PeerBox pb, uint32_t bins, uin
 {
     __shared__ int s_ok;
     uint32_t* const mine = pb.box[pb.rank];
-    uint32_t* const arrived = mine + 2 * (size_t) pb.bins_pad + pb.parity;
+    uint32_t const parity = peer_parity(pb);
+    uint32_t* const arrived = mine + 2 * (size_t) pb.bins_pad + parity;
     if (threadIdx.x == 0)
     {
         long long const t0 = clock64();
@@ -45,15 +46,17 @@ __global__ void __launch_bounds__(256) k_rdf_wait(PeerBox pb, uint32_t bins, uin
         }
         return;
     }
-    uint32_t* const h = mine + (size_t) pb.parity * pb.bins_pad;
+    uint32_t* const h = mine + (size_t) parity * pb.bins_pad;
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
     {
         reduced[b] = __ldcg(h + b);
         h[b] = 0U;
     }
+    __syncthreads(); // every thread has read the parity
     if (threadIdx.x == 0)
     {
         *arrived = 0U;
+        mine[2 * (size_t) pb.bins_pad + 2] += 1U; // this rank's next epoch
     }
 }
 

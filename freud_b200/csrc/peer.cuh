@@ -8,7 +8,9 @@
 // mailbox then holds the sum over all ranks once `world` arrivals are in; k_rdf_wait (peer.cu) waits for that on the
 // stream, copies the sum out and clears the mailbox for the epoch after next.
 //
-// Mailbox of one rank (u32 words): hist[2][bins_pad] -- one histogram per epoch parity -- then arrived[2].
+// Mailbox of one rank (u32 words): hist[2][bins_pad] -- one histogram per epoch parity -- then arrived[2], then the
+// rank's own epoch counter (written by its k_rdf_wait only: the kernels read the parity from the device, so a step
+// captured in a CUDA graph replays through the epochs without a changing launch argument).
 // Why two parities suffice: an epoch ends, on every rank, with the wait for all `world` arrivals.  A peer can only
 // start epoch e + 1 after it saw my arrival of epoch e, and my clearing of parity e happens (in stream order) before
 // my arrival of epoch e + 1, which every peer waits for before it can touch parity e again in epoch e + 2.
@@ -25,8 +27,13 @@ struct PeerBox
     int world;
     int rank;
     uint32_t bins_pad; // words between the two parities' histograms
-    uint32_t parity;   // epoch & 1
 };
+
+// parity of the epoch this rank is in (its own counter; every rank ends an epoch with exactly one k_rdf_wait)
+__device__ __forceinline__ uint32_t peer_parity(const PeerBox& pb)
+{
+    return *(pb.box[pb.rank] + 2 * (size_t) pb.bins_pad + 2) & 1U;
+}
 
 __device__ __forceinline__ void red_add_sys(uint32_t* addr, uint32_t v)
 {
@@ -44,6 +51,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr)
 // non-zero counters into every rank's mailbox and announces the arrival.  Ends with a block barrier.
 __device__ __forceinline__ void peer_push_block(const PeerBox& pb, const uint32_t* hist, uint32_t bins)
 {
+    uint32_t const parity = peer_parity(pb);
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
     {
         uint32_t const v = __ldcg(hist + b);
@@ -51,7 +59,7 @@ __device__ __forceinline__ void peer_push_block(const PeerBox& pb, const uint32_
         {
             for (int p = 0; p < pb.world; ++p)
             {
-                red_add_sys(pb.box[p] + (size_t) pb.parity * pb.bins_pad + b, v);
+                red_add_sys(pb.box[p] + (size_t) parity * pb.bins_pad + b, v);
             }
         }
     }
@@ -59,7 +67,7 @@ __device__ __forceinline__ void peer_push_block(const PeerBox& pb, const uint32_
     __syncthreads();
     if (threadIdx.x < (unsigned) pb.world)
     {
-        red_add_sys(pb.box[threadIdx.x] + 2 * (size_t) pb.bins_pad + pb.parity, 1U);
+        red_add_sys(pb.box[threadIdx.x] + 2 * (size_t) pb.bins_pad + parity, 1U);
     }
 }
 
