@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chained(uint32_t* __restr
     }
 }
 
-// K1: cell index + arrival rank (one atomic per point) -- 12 B read, 8 B written per point
 // A slab restricts the list to the cell layers [lo, lo + len) (cyclic) of one axis: a rank that only searches
 // its share of the home tiles needs nothing else (the build must not stay serial).
 struct SlabDev
@@ -195,37 +194,147 @@ struct SlabDev
     int len;  // < 0: no restriction
 };
 
-__global__ void __launch_bounds__(256) k_cell_assign(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
-                                                     uint32_t n, uint32_t* __restrict__ cell_of,
-                                                     uint32_t* __restrict__ rank_in, uint32_t* __restrict__ cell_count,
-                                                     int* __restrict__ any_shift, SlabDev slab)
+// Cell of a point, the value cell_coords gives, for a fraction of its cost: the fractional coordinates through
+// reciprocals (three multiplies instead of three IEEE divisions) settle the cell whenever frac * dim is farther than
+// 1e-3 from an integer and the point is farther than 1e-4 (in box units) from a face; the reciprocal arithmetic is
+// off by a few 1e-7 there, so both routes name the same cell.  Everything else -- about 1 % of uniform points, and
+// every point outside the box -- takes cell_coords itself.  Returns false if the point lies outside the box.
+struct CellRecip
+{
+    float rx, ry, rz, fdx, fdy, fdz;
+};
+
+__device__ __forceinline__ bool cell_of_point(const BoxDev& box, const CellRecip& r, int dx, int dy, int dz, float x, float y,
+                                              float z, uint32_t& cell)
+{
+    float const gz = box.is2d ? 0.0f : (z - box.loz) * r.rz;
+    float const gy = ((y - box.loy) - box.yz * z) * r.ry;
+    float const gx = ((x - box.lox) - (box.t_xz * z + box.xy * y)) * r.rx;
+    float const sx = gx * r.fdx, sy = gy * r.fdy, sz = gz * r.fdz;
+    float const fx = sx - floorf(sx), fy = sy - floorf(sy), fz = sz - floorf(sz);
+    bool const inside = gx > 1e-4f && gx < 0.9999f && gy > 1e-4f && gy < 0.9999f && (box.is2d || (gz > 1e-4f && gz < 0.9999f));
+    bool const clear = fx > 1e-3f && fx < 0.999f && fy > 1e-3f && fy < 0.999f && (box.is2d || (fz > 1e-3f && fz < 0.999f));
+    if (inside && clear)
+    {
+        cell = ((uint32_t) (box.is2d ? 0 : (int) sz) * dy + (uint32_t) (int) sy) * dx + (uint32_t) (int) sx;
+        return true;
+    }
+    int cx, cy, cz, nx, ny, nz;
+    cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+    cell = ((uint32_t) cz * dy + cy) * dx + cx;
+    return (nx | ny | nz) == 0;
+}
+
+// K1: cell index + arrival rank of every point, cell populations -- 12 B read, 8 B written per point, one atomic.
+// Persistent blocks stream the points through a two-stage cp.async.bulk ring (bulk_copy.cuh); the cell comes from
+// cell_of_point (reciprocals, the IEEE route only next to a face).  45 -> 36 us at 4 M points; what is left is the L2's
+// atomic rate (4 M atomics on 389 k counters).  Taking the arrival rank in the scatter instead (RED here, a returning
+// atomic on a per-cell cursor there) was measured: assign 36 us, scatter 82 -> 92 us -- the scatter is bound by its
+// 16-byte random writes and had no room for the atomic, so the rank stays here.
+constexpr int kAssignThreads = 256;
+constexpr int kAssignChunk = 1024; // points per chunk: 12288 bytes
+
+__global__ void __launch_bounds__(kAssignThreads) k_cell_assign_stream(BoxDev box, int dx, int dy, int dz,
+                                                                       const float* __restrict__ xyz, uint32_t n,
+                                                                       uint32_t* __restrict__ cell_of,
+                                                                       uint32_t* __restrict__ rank_in,
+                                                                       uint32_t* __restrict__ cell_count,
+                                                                       int* __restrict__ any_shift)
+{
+    __shared__ __align__(128) float s_raw[2][kAssignChunk * 3];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    uint32_t const n_chunks = (n + kAssignChunk - 1) / kAssignChunk;
+    auto chunk_points = [&](uint32_t c) { return min((uint32_t) kAssignChunk, n - c * kAssignChunk); };
+    bool const aligned = (reinterpret_cast<uintptr_t>(xyz) & 15U) == 0; // caller-owned arrays may sit anywhere
+    auto bulk_ok = [&](uint32_t c) { return aligned && (chunk_points(c) * 12U) % 16U == 0; };
+    auto issue = [&](uint32_t c, int stage) {
+        if (bulk_ok(c))
+        {
+            uint32_t const bytes = chunk_points(c) * 12U;
+            bulk::mbar_arrive_expect_tx(&s_bar[stage], bytes);
+            bulk::copy_g2s(s_raw[stage], xyz + 3 * (size_t) c * kAssignChunk, bytes, &s_bar[stage]);
+        }
+    };
+    if (threadIdx.x == 0)
+    {
+        bulk::mbar_init(&s_bar[0], 1);
+        bulk::mbar_init(&s_bar[1], 1);
+        bulk::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < n_chunks)
+    {
+        issue(blockIdx.x, 0);
+    }
+    CellRecip const rc {1.0f / box.Lx, 1.0f / box.Ly, box.is2d ? 0.0f : 1.0f / box.Lz, (float) dx, (float) dy, (float) dz};
+    uint32_t it = 0, waits[2] = {0, 0};
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it)
+    {
+        int const stage = (int) (it & 1U);
+        uint32_t const here = chunk_points(c);
+        if (threadIdx.x == 0)
+        {
+            uint32_t const next = c + gridDim.x;
+            if (next < n_chunks)
+            {
+                issue(next, stage ^ 1); // that buffer was released by the barrier that ended the previous iteration
+            }
+        }
+        if (bulk_ok(c))
+        {
+            bulk::mbar_wait(&s_bar[stage], waits[stage] & 1U);
+            waits[stage] += 1;
+        }
+        else
+        {
+            for (uint32_t e = threadIdx.x; e < 3 * here; e += kAssignThreads)
+            {
+                s_raw[stage][e] = xyz[3 * (size_t) c * kAssignChunk + e];
+            }
+            __syncthreads();
+        }
+        const float* raw = s_raw[stage];
+        for (uint32_t k = threadIdx.x; k < here; k += kAssignThreads)
+        {
+            uint32_t cell;
+            if (!cell_of_point(box, rc, dx, dy, dz, raw[3 * k], raw[3 * k + 1], raw[3 * k + 2], cell))
+            {
+                *any_shift = 1;
+            }
+            cell_of[(size_t) c * kAssignChunk + k] = cell;
+            rank_in[(size_t) c * kAssignChunk + k] = atomicAdd(&cell_count[cell], 1U);
+        }
+        if (threadIdx.x == 0)
+        {
+            bulk::fence_proxy_async();
+        }
+        __syncthreads();
+    }
+}
+
+// K3: scatter to cell order -- 20 B read, 16 (+4) B written per point
+__global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
+                                                      uint32_t n, const uint32_t* __restrict__ cell_of,
+                                                      const uint32_t* __restrict__ rank_in,
+                                                      const uint32_t* __restrict__ cell_start,
+                                                      float4* __restrict__ sorted, int* __restrict__ shift,
+                                                      const int* __restrict__ any_shift)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
     {
         return;
     }
+    uint32_t const cell = cell_of[i];
     float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
-    int cx, cy, cz, nx, ny, nz;
-    cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
-    if ((nx | ny | nz) != 0)
+    uint32_t const slot = __ldg(cell_start + cell) + rank_in[i];
+    sorted[slot] = make_float4(x, y, z, __uint_as_float(i));
+    if (shift != nullptr && *any_shift != 0)
     {
-        *any_shift = 1;
+        int cx, cy, cz, nx, ny, nz;
+        cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
+        shift[slot] = pack_shift(nx, ny, nz);
     }
-    if (slab.len >= 0)
-    {
-        int const d = slab.axis == 2 ? dz : dy, c = slab.axis == 2 ? cz : cy;
-        int rel = c - slab.lo;
-        rel += rel < 0 ? d : 0;
-        if (rel >= slab.len)
-        {
-            cell_of[i] = 0xffffffffU; // not in this rank's slab: left out of the list
-            return;
-        }
-    }
-    uint32_t const c = ((uint32_t) cz * dy + cy) * dx + cx;
-    cell_of[i] = c;
-    rank_in[i] = atomicAdd(&cell_count[c], 1U);
 }
 
 // K0: everything the build needs zeroed, in one launch instead of four memsets (launch gaps are a visible share of a
@@ -426,35 +535,6 @@ __global__ void __launch_bounds__(256) k_cell_scatter_slab(const float4* __restr
     }
 }
 
-// K3: scatter to cell order -- 20 B read, 16 (+4) B written per point
-__global__ void __launch_bounds__(256) k_cell_scatter(BoxDev box, int dx, int dy, int dz, const float* __restrict__ xyz,
-                                                      uint32_t n, const uint32_t* __restrict__ cell_of,
-                                                      const uint32_t* __restrict__ rank_in,
-                                                      const uint32_t* __restrict__ cell_start,
-                                                      float4* __restrict__ sorted, int* __restrict__ shift,
-                                                      const int* __restrict__ any_shift)
-{
-    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-    {
-        return;
-    }
-    uint32_t const cell = cell_of[i];
-    if (cell == 0xffffffffU)
-    {
-        return; // outside the slab of this rank
-    }
-    float const x = xyz[3 * (size_t) i], y = xyz[3 * (size_t) i + 1], z = xyz[3 * (size_t) i + 2];
-    uint32_t const slot = cell_start[cell] + rank_in[i];
-    sorted[slot] = make_float4(x, y, z, __uint_as_float(i));
-    if (shift != nullptr && *any_shift != 0)
-    {
-        int cx, cy, cz, nx, ny, nz;
-        cell_coords(box, dx, dy, dz, x, y, z, cx, cy, cz, nx, ny, nz);
-        shift[slot] = pack_shift(nx, ny, nz);
-    }
-}
-
 // NeighborQuery.h:103-112: a 2-D box takes no point with |z| > 1e-6.  Checked on the device after the upload (a host
 // pass over the array costs more than the whole RDF frame it precedes).
 __global__ void __launch_bounds__(256) k_check_2d_z(const float* __restrict__ xyz, uint32_t n, int* __restrict__ flag)
@@ -584,8 +664,41 @@ ShardPlan shard_plan(const int dim[3], uint32_t n_points, int shard, int n_shard
     a.n_cells = (uint32_t) dim[0] * dim[1] * dim[2];
     search2_plan(a, n_points);
     ShardPlan p;
-    p.ticket_begin = (uint32_t) ((uint64_t) a.n_tickets * (uint64_t) shard / (uint64_t) n_shards);
-    p.ticket_end = (uint32_t) ((uint64_t) a.n_tickets * (uint64_t) (shard + 1) / (uint64_t) n_shards);
+    // Equal COST, not equal count: the home tiles of the two cell layers at the periodic boundary of the slowest axis
+    // see a third of their candidate rows across that boundary, where the symmetric walk cannot halve the pair tests
+    // (tile_walk.cuh) -- measured 1.5x the time of an interior tile (one GPU playing ranks 0 and 7 of 8:
+    // profiles/ncu_r2_summary.md).  Tickets are ordered layer by layer, so the cumulative cost is piecewise linear.
+    {
+        int const layers = dim[2] > 1 ? dim[2] : dim[1];
+        uint64_t const per_layer = (uint64_t) a.n_tickets / (uint64_t) layers; // tickets of one layer of the slow axis
+        double const w_edge = layers >= 3 ? 1.5 : 1.0;
+        double const total = (double) a.n_tickets + (w_edge - 1.0) * 2.0 * (double) per_layer;
+        auto ticket_at = [&](double cost) {
+            double const first = w_edge * (double) per_layer;                       // cost of the first layer
+            double const middle = (double) (a.n_tickets - 2 * per_layer);           // ... of the interior layers
+            double t;
+            if (cost <= first)
+            {
+                t = cost / w_edge;
+            }
+            else if (cost <= first + middle)
+            {
+                t = (double) per_layer + (cost - first);
+            }
+            else
+            {
+                t = (double) (a.n_tickets - per_layer) + (cost - first - middle) / w_edge;
+            }
+            return (uint32_t) std::min<double>(std::max(t, 0.0), (double) a.n_tickets);
+        };
+        p.ticket_begin = shard == 0 ? 0U : ticket_at(total * (double) shard / (double) n_shards);
+        p.ticket_end = shard + 1 == n_shards ? a.n_tickets : ticket_at(total * (double) (shard + 1) / (double) n_shards);
+        if (n_shards == 1)
+        {
+            p.ticket_begin = 0;
+            p.ticket_end = a.n_tickets;
+        }
+    }
     p.slab_axis = dim[2] > 1 ? 2 : 1;
     int const layers = p.slab_axis == 2 ? dim[2] : dim[1];
     p.slab_lo = 0;
@@ -715,18 +828,21 @@ void build_grid(fgpu_points* pts, float r_search, bool force_single_cell)
     else
     {
         g.cell_of.reserve(n);
-        g.rank_in.reserve(n);
+        g.rank_in.reserve(std::max<size_t>(n, (size_t) n_cells + 4));
         {
             KernelScope ks(ctx, "cell_assign");
-            k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
-                                                           g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, d_flag, slab);
+            unsigned const n_chunks = (n + kAssignChunk - 1) / kAssignChunk;
+            unsigned const ablocks = std::min<unsigned>(n_chunks, (unsigned) ctx->sm_count * 8U);
+            k_cell_assign_stream<<<ablocks, kAssignThreads, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr,
+                                                                             n, g.cell_of.ptr, g.rank_in.ptr,
+                                                                             g.cell_start.ptr, d_flag);
         }
         exclusive_scan_u32(ctx, g.cell_start.ptr, (size_t) n_cells + 1, true);
         {
             KernelScope ks(ctx, "cell_scatter");
-            k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n,
-                                                            g.cell_of.ptr, g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr,
-                                                            g.shift.ptr, d_flag);
+            k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, dim[0], dim[1], dim[2], pts->xyz.ptr, n, g.cell_of.ptr,
+                                                            g.rank_in.ptr, g.cell_start.ptr, g.sorted.ptr, g.shift.ptr,
+                                                            d_flag);
         }
         g.cell_of_valid = true;
     }
@@ -748,26 +864,34 @@ void sort_queries(fgpu_points* pts, const float* q_dev, uint32_t n_query)
     const fgpu_grid& g = pts->grid;
     ctx->q_cell.reserve(n_query);
     ctx->q_rank.reserve(n_query);
-    ctx->q_cell_start.reserve((size_t) g.n_cells + 1);
+    ctx->q_cell_start.reserve((size_t) g.n_cells + 4);
     ctx->q_sorted.reserve(n_query);
-    FGPU_CUDA_CHECK(
-        cudaMemsetAsync(ctx->q_cell_start.ptr, 0, ((size_t) g.n_cells + 1) * sizeof(uint32_t), ctx->stream));
-    ctx->q_outside_flag.reserve(1);
+    ctx->q_outside_flag.reserve(2);
     int* d_flag = ctx->q_outside_flag.ptr; // read on the device by the warp-cooperative search
-    FGPU_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    size_t const scan_words = scan_scratch_words((size_t) g.n_cells + 1);
+    ctx->scan_tmp.reserve(scan_words);
+    {
+        KernelScope ks(ctx, "cell_prep");
+        unsigned const pblocks = (unsigned) std::min<size_t>(((size_t) g.n_cells + 256) / 256, (size_t) ctx->sm_count * 8);
+        k_cell_prep<<<std::max(pblocks, 1U), 256, 0, ctx->stream>>>(ctx->q_cell_start.ptr, nullptr, 0,
+                                                                   (size_t) g.n_cells + 1, 0, 0, ctx->scan_tmp.ptr,
+                                                                   (uint32_t) scan_words, d_flag, nullptr);
+    }
     unsigned const blocks = (n_query + 255) / 256;
     {
         KernelScope ks(ctx, "cell_assign");
-        k_cell_assign<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
-                                                       ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
-                                                       d_flag, SlabDev {2, 0, -1});
+        unsigned const n_chunks = (n_query + kAssignChunk - 1) / kAssignChunk;
+        unsigned const ablocks = std::max(1U, std::min<unsigned>(n_chunks, (unsigned) ctx->sm_count * 8U));
+        k_cell_assign_stream<<<ablocks, kAssignThreads, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev,
+                                                                         n_query, ctx->q_cell.ptr, ctx->q_rank.ptr,
+                                                                         ctx->q_cell_start.ptr, d_flag);
     }
-    exclusive_scan_u32(ctx, ctx->q_cell_start.ptr, (size_t) g.n_cells + 1);
+    exclusive_scan_u32(ctx, ctx->q_cell_start.ptr, (size_t) g.n_cells + 1, true);
     {
         KernelScope ks(ctx, "cell_scatter");
-        k_cell_scatter<<<blocks, 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
-                                                        ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
-                                                        ctx->q_sorted.ptr, nullptr, nullptr);
+        k_cell_scatter<<<std::max(blocks, 1U), 256, 0, ctx->stream>>>(pts->box, g.dim[0], g.dim[1], g.dim[2], q_dev, n_query,
+                                                                     ctx->q_cell.ptr, ctx->q_rank.ptr, ctx->q_cell_start.ptr,
+                                                                     ctx->q_sorted.ptr, nullptr, nullptr);
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
