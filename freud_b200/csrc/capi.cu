@@ -304,6 +304,20 @@ double expected_hits_per_query(const fgpu_points* pts, float r_window)
     return vol > 0 ? (double) pts->n / vol * shell : 0.0;
 }
 
+// First guess of a query's bond count, which sizes the bag and the output arrays (the search reports the exact count
+// and the host repeats with it when the guess was short): the previous query's count when this context has one --
+// a trajectory's frames resemble each other -- but never more than four times what the mean density predicts for THIS
+// query, nor more than every pair: one large query must not make every small query after it allocate gigabytes.
+uint64_t bag_capacity(uint64_t hint, uint32_t n_query, uint32_t n_points, double volume, double shell)
+{
+    double const ideal = (double) n_query * (double) n_points / volume * shell;
+    uint64_t const estimate = (uint64_t) (1.25 * ideal) + 4096;
+    uint64_t cap = hint != 0 ? hint + hint / 16 + 1024 : estimate;
+    cap = std::min<uint64_t>(cap, 4 * estimate);
+    cap = std::min<uint64_t>(cap, (uint64_t) n_query * (uint64_t) n_points + 1024);
+    return cap;
+}
+
 std::unique_ptr<fgpu_nlist> new_nlist(fgpu_ctx* ctx, uint32_t n_query, uint32_t n_points)
 {
     std::unique_ptr<fgpu_nlist> nl(new fgpu_nlist());
@@ -378,9 +392,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
         double const vol = box_volume(pts->box);
         double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max
                                            : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
-        uint64_t cap = ctx->bag_hint != 0
-            ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
-            : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
+        uint64_t cap = bag_capacity(ctx->bag_hint, n_query, pts->n, vol, shell);
         ctx->tmp_start.reserve((size_t) n_query + 1);
         bool done = false, general = false;
         uint64_t n_bonds = 0;
@@ -521,8 +533,7 @@ bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int 
     }
     double const vol = box_volume(pts->box);
     double const shell = pts->box.is2d ? M_PI * (double) r_max * r_max : 4.0 / 3.0 * M_PI * (double) r_max * r_max * r_max;
-    uint64_t cap = ctx->bag_hint != 0 ? ctx->bag_hint + ctx->bag_hint / 16 + 1024
-                                      : (uint64_t) (1.25 * (double) n_query * (double) pts->n / vol * shell) + 4096;
+    uint64_t cap = bag_capacity(ctx->bag_hint, n_query, pts->n, vol, shell);
     ctx->tmp_start.reserve((size_t) n_query + 1);
     ctx->row_counts.reserve((size_t) n_query + 1);
     launch_count_evals(ctx, s2, n_query, pts->grid.cell_of.ptr, pts->n);

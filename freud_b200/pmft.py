@@ -7,12 +7,28 @@ from .density import _box_of
 from .locality import _computed, _ext, _PairCompute
 
 
+def _quat_to_z_angle(orientations, num_points):
+    """freud/pmft.py:58-84: a last dimension of length 4 means quaternions -- unless there are exactly four points and the
+    array is 1-D, which is four angles.  Quaternions must be rotations about +z (or all be the identity); they become
+    their rotation angle as ``rowan.to_axis_angle`` defines it: angle = 2 atan2(|v|, w), axis = v / sin(angle / 2)."""
+    is_quat = (orientations.ndim == 1 and orientations.shape[0] == 4 and num_points != 4) or (
+        orientations.ndim == 2 and orientations.shape[1] == 4)
+    if not is_quat:
+        return orientations
+    q = np.asarray(orientations, dtype=np.float64)
+    angles = 2.0 * np.atleast_1d(np.arctan2(np.linalg.norm(q[..., 1:], axis=-1), q[..., 0]))
+    sines = np.sin(angles / 2.0)
+    sines[sines == 0] = 1.0
+    axes = np.where(angles[..., np.newaxis] != 0, np.atleast_2d(q)[..., 1:] / sines[..., np.newaxis], 0.0)
+    axes, angles = axes.squeeze(), angles.squeeze()
+    if not (np.allclose(angles, 0) or np.allclose(axes, [0, 0, 1])):
+        raise ValueError("Orientations provided as quaternions must represent rotations about the z-axis.")
+    return angles
+
+
 def _angles(orientations, n):
-    """Angles in radians, one per query point; (N, 4) quaternions are reduced to their rotation about z
-    (``freud/pmft.py:60-94``)."""
-    a = np.asarray(orientations, dtype=np.float64).squeeze()
-    if a.ndim == 2 and a.shape[1] == 4:
-        a = 2.0 * np.arctan2(a[:, 3], a[:, 0])
+    """Angles in radians, one per (query) point (``_gen_angle_array``, freud/pmft.py:87-94)."""
+    a = _quat_to_z_angle(np.asarray(orientations).squeeze(), n)
     a = np.ascontiguousarray(np.atleast_1d(a), dtype=np.float32)
     if a.shape != (n,):
         raise ValueError(f"orientations must have shape ({n},) or ({n}, 4)")

@@ -305,3 +305,23 @@ def test_cellquery_grid_introspection_and_all_pairs():
         assert np.array_equal(nl.vectors.view(np.uint32), want.view(np.uint32))
     assert np.allclose(nl.distances, np.linalg.norm(nl.vectors, axis=1), rtol=1e-6)
     assert np.all(nl.weights == 1)
+
+
+def test_pmft_quaternion_orientations_must_rotate_about_z():
+    """freud/pmft.py:58-84 (`_quat_to_z_angle`): quaternions are accepted only as rotations about +z, a 1-D length-4
+    input is a quaternion unless there are exactly four points, and the angle is rowan's 2 atan2(|v|, w)."""
+    import numpy as np
+
+    from freud_b200.pmft import _angles
+
+    half = np.pi / 6
+    qz = np.tile([np.cos(half), 0, 0, np.sin(half)], (5, 1))
+    assert np.allclose(_angles(qz, 5), 2 * half)
+    assert np.allclose(_angles(np.tile([1.0, 0, 0, 0], (5, 1)), 5), 0)  # identities are fine
+    with pytest.raises(ValueError):
+        _angles(np.tile([np.cos(half), np.sin(half), 0, 0], (5, 1)), 5)  # about x
+    with pytest.raises(ValueError):
+        _angles(np.tile([np.cos(half), 0, 0, -np.sin(half)], (5, 1)), 5)  # about -z: rejected upstream too
+    assert np.allclose(_angles([0.1, 0.2, 0.3, 0.4], 4), [0.1, 0.2, 0.3, 0.4])  # four points: four angles
+    assert np.allclose(_angles(np.array([np.cos(half), 0, 0, np.sin(half)]), 1), 2 * half)  # one point, one quaternion
+    assert np.allclose(_angles(np.arange(5) * 0.1, 5), np.arange(5) * 0.1)
