@@ -382,7 +382,8 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
     // ---- production path: warp-cooperative single-pass search into a bag, then ranked emit ----------------
     bool fast_counted_evals = false;
     Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_max, r_min, exclude_ii);
-    search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_max), ctx->tune_lanes_over_queries);
+    search2_choose_mapping(s2, flavour, n_query, pts->n, expected_hits_per_query(pts, r_max),
+                           ctx->tune_lanes_over_queries);
     if (!ctx->force_general && search2_supported(s2, S2_NL))
     {
         // Capacities of the bag and of the output arrays: the previous query's bond count if there was one, else
@@ -435,10 +436,18 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
             e.vectors = nl->vectors.ptr;
             launch_emit2(ctx, sort_by_distance, e);
             d2h(ctx, ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(unsigned long long));
+            // the bond count is the total of the row scan: the bag cursor may run a few records ahead of it (the
+            // lanes-over-queries search reserves a record per filter survivor, search_lq.cu)
+            ctx->h_scalars[1] = 0;
+            d2h(ctx, ctx->h_scalars + 1, nl->row_start.ptr + n_query, sizeof(uint32_t));
             sync(ctx);
             int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
             uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
-            if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
+            if (search2_lq_fallback(s2, fail))
+            {
+                // rows beyond the buffers of the lanes-over-queries search: the tile walk takes the frame
+            }
+            else if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
             {
                 // a tile denser than the uniform estimate (clustered system): same kernels, a hit buffer that holds
                 // it -- fewer resident warps, still far ahead of the thread-per-query family
@@ -451,7 +460,7 @@ void ball_query_impl(fgpu_points* pts, const float* q_host, const float* q_dev, 
             }
             else if (ctx->h_scalars[5] <= cap)
             {
-                n_bonds = ctx->h_scalars[5];
+                n_bonds = ctx->h_scalars[1];
                 done = true;
             }
             else
@@ -526,7 +535,8 @@ bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int 
     build_grid(pts, r_max);
     QueryView const qv = prepare_queries(pts, q_host, nullptr, n_query);
     Search2Args s2 = base_search2_args(pts, qv, 0, r_max, r_min, exclude_ii);
-    search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_max), ctx->tune_lanes_over_queries);
+    search2_choose_mapping(s2, flavour, n_query, pts->n, expected_hits_per_query(pts, r_max),
+                           ctx->tune_lanes_over_queries);
     if (!search2_supported(s2, S2_NL))
     {
         return false;
@@ -552,7 +562,11 @@ bool search_to_bag(fgpu_points* pts, const float* q_host, uint32_t n_query, int 
         sync(ctx);
         int const fail = (int) (ctx->h_scalars[4] & 0xffffffffULL);
         uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
-        if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
+        if (search2_lq_fallback(s2, fail))
+        {
+            // rows beyond the buffers of the lanes-over-queries search: the tile walk takes the frame
+        }
+        else if (fail == 2 && densest <= search2_max_out_cap() && s2.out_cap < search2_max_out_cap())
         {
             s2.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
         }
@@ -950,6 +964,10 @@ int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value)
         {
             ctx->tune_lanes_over_queries = value;
         }
+        else if (k == "lq_blocks")
+        {
+            ctx->tune_lq_blocks = value;
+        }
         else
         {
             throw Error(FGPU_EINVALID, "unknown tuning key: " + k);
@@ -1274,7 +1292,8 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
             // r_min: LinkCell compares squares (LinkCell.cc:619), AABBQuery the distance itself (AABBQuery.cc:213)
             Search2Args s2 = base_search2_args(pts, qv, q_index_offset, r_win, wrap ? r_min : 0.0f, exclude_ii);
             s2.knn_r_min = !wrap && r_min > 0.0f ? r_min : 0.0f;
-            search2_choose_mapping(s2, n_query, expected_hits_per_query(pts, r_win), ctx->tune_lanes_over_queries);
+            search2_choose_mapping(s2, flavour, n_query, pts->n, expected_hits_per_query(pts, r_win),
+                                   ctx->tune_lanes_over_queries);
             if (!ctx->force_general && !cover_all && search2_supported(s2, S2_NL) && pts->n < 0x7fffffffU)
             {
                 ctx->tmp_start.reserve((size_t) n_query + 1);
@@ -1325,6 +1344,10 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
                         sync(ctx);
                         int const failed = (int) (ctx->h_scalars[4] & 0xffffffffULL);
                         uint32_t const densest = (uint32_t) (ctx->h_scalars[4] >> 32);
+                        if (search2_lq_fallback(args, failed))
+                        {
+                            continue; // rows beyond the buffers of the lanes-over-queries search: the tile walk
+                        }
                         if (failed == 2 && densest <= search2_max_out_cap() && args.out_cap < search2_max_out_cap())
                         {
                             args.out_cap = std::min(search2_max_out_cap(), (densest + densest / 8 + 31U) & ~31U);
@@ -1371,7 +1394,7 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
                     s2b.knn_r_min = s2.knn_r_min;
                     s2b.q_remap = ctx->knn_unresolved.ptr;
                     s2b.tmp_flag = kSecondBag;
-                    search2_choose_mapping(s2b, (uint32_t) n_short, expected_hits_per_query(pts, r_win2),
+                    search2_choose_mapping(s2b, flavour, (uint32_t) n_short, pts->n, expected_hits_per_query(pts, r_win2),
                                            ctx->tune_lanes_over_queries);
                     if (!cover_all2 && search2_supported(s2b, S2_NL)
                         && run_window(s2b, ctx->bag4b, n_short, r_win2, ctx->knn_unresolved.ptr + n_query)

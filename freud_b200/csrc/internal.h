@@ -142,6 +142,8 @@ struct fgpu_ctx
     int tune_span = 0;                    // > 0: cells per home tile of the tile walk
     int tune_no_symmetry = 0;             // 1: self-query IMAGE RDF without the symmetric walk
     int tune_lanes_over_queries = -1;     // -1 automatic, 0 / 1: force the NeighborList search's mapping
+    int tune_lq_blocks = 0;               // > 0: resident blocks per SM of the lanes-over-queries search (the rest of
+                                          // the SM's 256 KB stays L1)
     fgpu::DevBuf<double> st_partials;     // Steinhardt: per-block partial sums of the system q_lm
     fgpu::DevBuf<float> knn_d;            // kNN scratch, [k][n_query]
     fgpu::DevBuf<uint32_t> knn_s;         // kNN scratch, [k][n_query] (slot | image code)
@@ -414,8 +416,10 @@ struct Search2Args
     BoxDev box;
     int dx, dy, dz;
     uint32_t n_cells;
-    int lanes_over_queries;         // NeighborList mode: 32 cell-ordered queries per ticket, one per lane (sparse cells)
-    uint32_t n_query;               // queries in q_sorted (lanes-over-queries tickets)
+    int lanes_over_queries;         // NeighborList mode: 32 cell-ordered queries per ticket, one per lane (search_lq.cu)
+    uint32_t n_query;               // queries in q_sorted
+    uint32_t lq_tickets;            // lanes over queries: ceil(n_query / 32)
+    uint32_t lq_c, lq_f;            // ... filter survivors a lane / a warp can hold (dynamic shared memory)
     int span;                       // cells per home tile along x (search2_plan)
     uint32_t spans_per_row;
     uint32_t n_tickets;             // work items: one home tile each
@@ -464,7 +468,11 @@ struct Search2Args
 };
 void search2_plan(Search2Args& a, uint32_t n_points, int span_override = 0); // sets span, spans_per_row, n_tickets
 // NeighborList mode: tile walk or lanes over queries (force: -1 automatic, 0 / 1 fgpu_ctx_set_tuning); sets n_query
-void search2_choose_mapping(Search2Args& a, uint32_t n_query, double expected_hits_per_query, int force);
+void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint32_t n_points,
+                            double expected_hits_per_query, int force);
+// the lanes-over-queries launch gave up (fail == 2: a row or a warp's rows beyond its buffers): back to the tile walk
+bool search2_lq_fallback(Search2Args& a, int fail);
+void launch_search_lq(fgpu_ctx* ctx, int flavour, const Search2Args& a);
 
 // Share of one rank when the home tiles of a self query are dealt to n_shards ranks: a contiguous run of tickets,
 // the cells they cover, and the slab of cell layers (with one halo layer on each side) their candidates live in.

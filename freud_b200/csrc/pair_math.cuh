@@ -100,6 +100,51 @@ __device__ __forceinline__ void wrap_quick(const BoxDev& b, float ylx, float yly
     rz = b.is2d ? 0.0f : z;
 }
 
+__device__ __forceinline__ bool in_window2(float r_sq, float r_max_sq, float r_min_sq)
+{
+    return r_sq < r_max_sq && r_sq >= r_min_sq; // LinkCell.cc:525, AABBQuery.cc:129
+}
+
+// Division by a box length: div_by_const (pair_math.cuh) replaces __fdiv_rn (x86 divss upstream, Box.h:248-250).
+// Exact here because stage 1 bounds |a| / L away from 0 (no underflow in the residuals).
+// modulus_positive_one_small (pair_math.cuh): util::modulusPositive(f, 1) (freud/util/utils.h:29-32) for f in (-1, 2).
+// Box::wrap(v) (freud/box/Box.h:307-329) for displacements whose fractional coordinates are within
+// (-1/2 - 0.35, 1/2 + 0.35) + {-1, 0, 1}; bit-identical to wrap_exact on that domain.
+template<bool TRI>
+__device__ __forceinline__ void wrap_fast(const BoxDev& b, float ylx, float yly, float ylz, float vx, float vy,
+                                          float vz, float& rx, float& ry, float& rz)
+{
+    float dx = __fsub_rn(vx, b.lox);
+    float dy = __fsub_rn(vy, b.loy);
+    float const dz = __fsub_rn(vz, b.loz);
+    if (TRI)
+    {
+        dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(b.t_xz, vz), __fmul_rn(b.xy, vy)));
+        dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
+    }
+    float fx = div_by_const(dx, b.Lx, ylx);
+    float fy = div_by_const(dy, b.Ly, yly);
+    float fz = b.is2d ? 0.0f : div_by_const(dz, b.Lz, ylz);
+    fx = modulus_positive_one_small(fx);
+    fy = modulus_positive_one_small(fy);
+    fz = modulus_positive_one_small(fz);
+    float x = __fadd_rn(b.lox, __fmul_rn(fx, b.Lx));
+    float y = __fadd_rn(b.loy, __fmul_rn(fy, b.Ly));
+    float z = __fadd_rn(b.loz, __fmul_rn(fz, b.Lz));
+    if (TRI)
+    {
+        x = __fadd_rn(x, __fadd_rn(__fmul_rn(b.xy, y), __fmul_rn(b.xz, z)));
+        y = __fadd_rn(y, __fmul_rn(b.yz, z));
+    }
+    if (b.is2d)
+    {
+        z = 0.0f;
+    }
+    rx = x;
+    ry = y;
+    rz = z;
+}
+
 // r = Box::wrap(v), all axes periodic.
 __device__ __forceinline__ void wrap_exact(const BoxDev& b, float vx, float vy, float vz, float& rx, float& ry,
                                            float& rz)

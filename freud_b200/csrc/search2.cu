@@ -48,51 +48,6 @@ constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
 constexpr int kQueueCap = 96;   // stage-2 stack: < 32 left over + two pushes of <= 32
 
-__device__ __forceinline__ bool in_window2(float r_sq, float r_max_sq, float r_min_sq)
-{
-    return r_sq < r_max_sq && r_sq >= r_min_sq; // LinkCell.cc:525, AABBQuery.cc:129
-}
-
-// Division by a box length: div_by_const (pair_math.cuh) replaces __fdiv_rn (x86 divss upstream, Box.h:248-250).
-// Exact here because stage 1 bounds |a| / L away from 0 (no underflow in the residuals).
-// modulus_positive_one_small (pair_math.cuh): util::modulusPositive(f, 1) (freud/util/utils.h:29-32) for f in (-1, 2).
-// Box::wrap(v) (freud/box/Box.h:307-329) for displacements whose fractional coordinates are within
-// (-1/2 - 0.35, 1/2 + 0.35) + {-1, 0, 1}; bit-identical to wrap_exact on that domain.
-template<bool TRI>
-__device__ __forceinline__ void wrap_fast(const BoxDev& b, float ylx, float yly, float ylz, float vx, float vy,
-                                          float vz, float& rx, float& ry, float& rz)
-{
-    float dx = __fsub_rn(vx, b.lox);
-    float dy = __fsub_rn(vy, b.loy);
-    float const dz = __fsub_rn(vz, b.loz);
-    if (TRI)
-    {
-        dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(b.t_xz, vz), __fmul_rn(b.xy, vy)));
-        dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
-    }
-    float fx = div_by_const(dx, b.Lx, ylx);
-    float fy = div_by_const(dy, b.Ly, yly);
-    float fz = b.is2d ? 0.0f : div_by_const(dz, b.Lz, ylz);
-    fx = modulus_positive_one_small(fx);
-    fy = modulus_positive_one_small(fy);
-    fz = modulus_positive_one_small(fz);
-    float x = __fadd_rn(b.lox, __fmul_rn(fx, b.Lx));
-    float y = __fadd_rn(b.loy, __fmul_rn(fy, b.Ly));
-    float z = __fadd_rn(b.loz, __fmul_rn(fz, b.Lz));
-    if (TRI)
-    {
-        x = __fadd_rn(x, __fadd_rn(__fmul_rn(b.xy, y), __fmul_rn(b.xz, z)));
-        y = __fadd_rn(y, __fmul_rn(b.yz, z));
-    }
-    if (b.is2d)
-    {
-        z = 0.0f;
-    }
-    rx = x;
-    ry = y;
-    rz = z;
-}
-
 // Per-warp shared memory.  The stage-2 queue is a stack (push on top, pop the top 32): the order in which
 // pairs reach stage 2 is irrelevant, rows are regrouped when a batch is flushed.
 struct WarpMemBase
@@ -123,12 +78,10 @@ __host__ __device__ inline size_t warp_mem_bytes(int mode, uint32_t out_cap)
     return mode == S2_NL ? sizeof(WarpMemNL) + (size_t) out_cap * 5 * sizeof(uint32_t) : sizeof(WarpMemBase);
 }
 
-// LQ ("lanes over queries", NeighborList mode): see the second work loop below.
-template<int FLAVOUR, int MODE, bool TRI, bool SYM = false, bool LQ = false>
+template<int FLAVOUR, int MODE, bool TRI, bool SYM = false>
 __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
 {
     static_assert(!SYM || (FLAVOUR == FGPU_FLAVOUR_IMAGE && MODE == S2_RDF), "symmetric walk: fused IMAGE RDF only");
-    static_assert(!LQ || MODE == S2_NL, "lanes over queries: NeighborList mode only");
     using WarpMem = typename WarpMemOf<MODE>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -414,184 +367,6 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
             }
         }
     };
-
-    // ---- lanes over queries (LQ): 32 consecutive cell-ordered queries per ticket, one per lane -------------------
-    // At sparse cells (cell width ~ r_max at liquid density: ~2 points per cell) a home tile holds a handful of
-    // queries, and the tile walk below pays its setup, candidate flattening and flush for each of them -- 60 % of
-    // the instructions of a 1 M-point frame at r_max = 3 (profiles/ncu_r1_v6_summary.md) -- while every query is
-    // tested against the candidates of the whole tile (117 for the 58 of its own 27 cells).  Here every lane owns a
-    // query and walks ITS 27 cells as nine runs of the cell-ordered array (x is the fastest cell index: the three x
-    // neighbours of a row are contiguous), loading its own candidate each iteration (neighbouring lanes sit in
-    // neighbouring cells, so the loads of a warp fall into a few L1 lines); the loop of a run is warp-uniform over
-    // the longest lane.  Filter, stack, dense exact stage 2 and the row-grouped flush are the ones of the tile walk.
-    if (LQ)
-    {
-        uint32_t q_per_chunk = 32; // halved when the hits of a chunk overflow the buffer, reset per ticket
-        for (;;)
-        {
-            uint32_t ticket = 0;
-            if (lane == 0)
-            {
-                ticket = atomicAdd(a.work_counter, 1U);
-            }
-            ticket = __shfl_sync(FULL, ticket, 0);
-            if (ticket >= a.n_tickets)
-            {
-                break;
-            }
-            uint32_t const t0 = ticket * 32U, t1 = min(t0 + 32U, a.n_query);
-            q_per_chunk = 32;
-            for (uint32_t qb0 = t0; qb0 < t1;)
-            {
-                uint32_t const nqc = min(q_per_chunk, t1 - qb0);
-                bool const mine = (uint32_t) lane < nqc;
-                __syncwarp();
-                float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (mine)
-                {
-                    q = __ldg(a.q_sorted + qb0 + lane);
-                    uint32_t qi = __float_as_uint(q.w);
-                    if (a.q_remap != nullptr)
-                    {
-                        qi = __ldg(a.q_remap + qi); // a subset of the rows is searched again (kNN, knn2.cu)
-                    }
-                    reinterpret_cast<WarpMemNL&>(wm).qid[lane] = qi;
-                    if (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d)
-                    {
-                        q.z = 0.0f; // AABBQuery.cc:84-87
-                    }
-                    q.w = __uint_as_float(a.exclude_ii ? qi + a.q_index_offset : 0xffffffffU);
-                    sq[lane] = q;
-                }
-                __syncwarp();
-                batch_n = nqc;
-                uint32_t const q_excl = __float_as_uint(q.w);
-                // the lane's cell (the arithmetic that sorted it there) and its nine runs, all offsets fetched up front
-                int cx = 0, cy = 0, cz = 0;
-                {
-                    int nx, ny, nz;
-                    cell_coords(box, dx, dy, dz, q.x, q.y, q.z, cx, cy, cz, nx, ny, nz);
-                }
-                int const x0 = max(cx - 1, 0), x1 = min(cx + 1, dx - 1);
-                int const r_first = dz == 1 ? 3 : 0, r_last = dz == 1 ? 6 : 9; // 2-D: the three rows of the plane
-                // run r of the lane: rows (oy, oz) = (r % 3 - 1, r / 3 - 1) of its cell, cells [x0, x1]
-                auto run_of = [&](int r, uint32_t& b, uint32_t& n, int& wy, int& wz, uint32_t& rowbase) {
-                    int const oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
-                    int y = cy + oy, z = cz + oz;
-                    wy = y < 0 ? -1 : (y >= dy ? 1 : 0);
-                    wz = z < 0 ? -1 : (z >= dz ? 1 : 0);
-                    y -= wy * dy;
-                    z -= wz * dz;
-                    rowbase = ((uint32_t) z * dy + y) * dx;
-                    b = mine ? __ldg(a.cell_start + rowbase + x0) : 0U;
-                    n = mine ? __ldg(a.cell_start + rowbase + x1 + 1) - b : 0U;
-                };
-                // One filter loop over a run: candidate = sorted[b + it], query shifted by the run's boundary crossings.
-                // Lanes past the end of their run test slot 0 and drop the answer, so nothing in the loop is
-                // predicated; the next candidate is on its way while the current one is tested; two candidates per
-                // trip share the loop overhead and the stack check (96 slots hold 31 left over + 2 x 32 new).
-                auto walk = [&](uint32_t b, uint32_t n_mine, float qx, float qy, float qz, uint32_t code) {
-                    uint32_t const n_max = __reduce_max_sync(FULL, n_mine);
-                    uint32_t const tag = (uint32_t) lane | (code << 8);
-                    auto slot_of = [&](uint32_t it) { return it < n_mine ? b + it : 0U; };
-                    auto test = [&](uint32_t it, uint32_t slot, float4 const& p) {
-                        float const pz = (FLAVOUR == FGPU_FLAVOUR_IMAGE && box.is2d) ? 0.0f : p.z;
-                        float const ddx = p.x - qx, ddy = p.y - qy, ddz = pz - qz;
-                        float const r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-                        bool const ok = r2 <= r_hi_sq && __float_as_uint(p.w) != q_excl && it < n_mine;
-                        unsigned const m = __ballot_sync(FULL, ok);
-                        if (ok)
-                        {
-                            queue[q_len + __popc(m & lt_mask)] = make_uint2(slot, tag);
-                        }
-                        q_len += __popc(m);
-                    };
-                    uint32_t s0 = slot_of(0), s1 = slot_of(1);
-                    float4 p0 = __ldg(a.sorted + s0), p1 = __ldg(a.sorted + s1);
-                    for (uint32_t it = 0; it < n_max; it += 2)
-                    {
-                        uint32_t const t0s = s0, t1s = s1;
-                        float4 const c0 = p0, c1 = p1;
-                        s0 = slot_of(it + 2);
-                        s1 = slot_of(it + 3);
-                        p0 = __ldg(a.sorted + s0);
-                        p1 = __ldg(a.sorted + s1);
-                        test(it, t0s, c0);
-                        test(it + 1, t1s, c1);
-                        if (q_len >= 32)
-                        {
-                            stage2_round(32);
-                            if (q_len >= 32)
-                            {
-                                stage2_round(32);
-                            }
-                        }
-                    }
-                };
-                uint32_t nb = 0, nn = 0, nrow = 0;
-                int nwy = 0, nwz = 0;
-                run_of(r_first, nb, nn, nwy, nwz, nrow);
-                for (int r = r_first; r < r_last; ++r)
-                {
-                    uint32_t const b = nb, n_mine = nn, rowbase = nrow;
-                    int const wy = nwy, wz = nwz;
-                    if (r + 1 < r_last)
-                    {
-                        run_of(r + 1, nb, nn, nwy, nwz, nrow); // the next row's offsets travel while this row is walked
-                    }
-                    // the candidates of a run reached across boundaries (wy, wz) are images shifted by wy b + wz c:
-                    // move the query the other way instead (fused arithmetic, filter only)
-                    float const fy = (float) wy, fz = (float) wz;
-                    float const qx = q.x - (fy * box.bx + fz * box.cx), qy = q.y - (fy * box.by + fz * box.cy),
-                                qz = q.z - fz * box.cz;
-                    uint32_t const code = 1U | ((uint32_t) (wy + 1) << 2) | ((uint32_t) (wz + 1) << 4);
-                    walk(b, n_mine, qx, qy, qz, code);
-                    // the x neighbour across the periodic boundary is a run of its own (one cell)
-                    bool const edge = mine && (cx == 0 || cx == dx - 1);
-                    if (__any_sync(FULL, edge))
-                    {
-                        int const wx = cx == 0 ? -1 : 1;
-                        uint32_t const cell = rowbase + (uint32_t) (cx == 0 ? dx - 1 : 0);
-                        uint32_t const b2 = edge ? __ldg(a.cell_start + cell) : 0U;
-                        uint32_t const n2 = edge ? __ldg(a.cell_start + cell + 1) - b2 : 0U;
-                        float const fx = (float) wx;
-                        walk(b2, n2, qx - fx * box.ax, qy, qz,
-                             (uint32_t) (wx + 1) | ((uint32_t) (wy + 1) << 2) | ((uint32_t) (wz + 1) << 4));
-                    }
-                }
-                if (q_len != 0)
-                {
-                    stage2_round(q_len); // rows must be complete before they are published
-                }
-                if (overflow)
-                {
-                    __syncwarp();
-                    reinterpret_cast<WarpMemNL&>(wm).row_cnt[lane] = 0;
-                    o_len = 0;
-                    q_len = 0;
-                    overflow = false;
-                    if (nqc == 1)
-                    {
-                        // one row alone exceeds the buffer: the host retries with a larger one (or the general kernels)
-                        if (lane == 0)
-                        {
-                            *a.fail = 2;
-                            atomicMax(reinterpret_cast<unsigned int*>(a.fail) + 1, 2U * a.out_cap);
-                        }
-                        qb0 += 1;
-                    }
-                    else
-                    {
-                        q_per_chunk = max(1U, nqc / 2); // same qb0, smaller chunk
-                    }
-                    continue;
-                }
-                flush_batch();
-                qb0 += nqc;
-            }
-        }
-        return;
-    }
 
     // ---- work loop: one home tile (a span of a.span cells of one grid row) per ticket ---------------------
     for (;;)
@@ -900,12 +675,12 @@ template<bool BY_DISTANCE> __global__ void __launch_bounds__(256) k_emit2(Emit2A
     }
 }
 
-template<int FLAVOUR, int MODE, bool TRI, bool SYM = false, bool LQ = false>
+template<int FLAVOUR, int MODE, bool TRI, bool SYM = false>
 void launch_one(fgpu_ctx* ctx, const Search2Args& a, const char* name)
 {
     size_t const hist_bytes = MODE == S2_RDF ? ((a.axis.bins * sizeof(uint32_t) + 15) / 16) * 16 : 0;
     size_t const smem = hist_bytes + (size_t) kWarps * warp_mem_bytes(MODE, a.out_cap);
-    auto kern = k_search2<FLAVOUR, MODE, TRI, SYM, LQ>;
+    auto kern = k_search2<FLAVOUR, MODE, TRI, SYM>;
     static bool configured = false; // per instantiation
     if (!configured)
     {
@@ -918,7 +693,7 @@ void launch_one(fgpu_ctx* ctx, const Search2Args& a, const char* name)
     {
         throw Error(FGPU_ERUNTIME, "search kernel does not fit the shared memory of this device");
     }
-    uint64_t const n_tickets = LQ ? a.n_tickets : a.ticket_end - a.ticket_begin;
+    uint64_t const n_tickets = a.ticket_end - a.ticket_begin;
     unsigned const blocks
         = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, (n_tickets + kWarps - 1) / kWarps);
     KernelScope ks(ctx, name);
@@ -982,28 +757,6 @@ uint32_t search2_out_cap(double expected_candidates_per_tile)
     return std::max(cap, 128U);
 }
 
-// Mapping of the NeighborList search.  The tile walk is the default everywhere: measured on B200 at configs[1]
-// (1 M points, r_max = 3, 2.2 points per cell) lanes over queries needs 203 M warp instructions for the tile walk's
-// 224 M but issues them at 59 % against 77 % (20 resident warps, a dependent load per trip) -- 318 us against 271 us,
-// and 631 us against 451 us as the kNN window search of configs[2] (profiles/ncu_r2_summary.md).  It stays as an
-// alternative that the parity tests run against the oracle (fgpu_ctx_set_tuning(ctx, "lanes_over_queries", 1)).
-void search2_choose_mapping(Search2Args& a, uint32_t n_query, double expected_hits_per_query, int force)
-{
-    a.n_query = n_query;
-    a.lanes_over_queries = 0;
-    double const mu = std::max(expected_hits_per_query, 0.25) * 32.0;
-    double const want = mu + 7.0 * std::sqrt(mu) + 32.0;
-    if (force <= 0 || n_query == 0)
-    {
-        return;
-    }
-    a.lanes_over_queries = 1;
-    a.n_tickets = (n_query + 31U) / 32U;
-    a.ticket_begin = 0;
-    a.ticket_end = a.n_tickets;
-    a.out_cap = std::max(128U, ((uint32_t) std::min(want, 2048.0) + 31U) & ~31U);
-}
-
 void launch_count_evals(fgpu_ctx* ctx, const Search2Args& a, uint32_t n_query, const uint32_t* cell_of_point,
                         uint32_t n_points)
 {
@@ -1030,22 +783,9 @@ void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a)
         else                                                                                                     \
             launch_one<FL, MD, false>(ctx, a, name);                                                             \
     } while (0)
-#define FGPU_S2_LQ(FL)                                                                                           \
-    do                                                                                                           \
-    {                                                                                                            \
-        if (tri)                                                                                                 \
-            launch_one<FL, S2_NL, true, false, true>(ctx, a, name);                                              \
-        else                                                                                                     \
-            launch_one<FL, S2_NL, false, false, true>(ctx, a, name);                                             \
-    } while (0)
     if (mode == S2_NL && a.lanes_over_queries)
     {
-        if (flavour == FGPU_FLAVOUR_WRAP)
-            FGPU_S2_LQ(FGPU_FLAVOUR_WRAP);
-        else if (flavour == FGPU_FLAVOUR_GHOST)
-            launch_one<FGPU_FLAVOUR_GHOST, S2_NL, false, false, true>(ctx, a, name);
-        else
-            FGPU_S2_LQ(FGPU_FLAVOUR_IMAGE);
+        launch_search_lq(ctx, flavour, a); // search_lq.cu
     }
     else if (flavour == FGPU_FLAVOUR_WRAP)
     {
@@ -1071,7 +811,6 @@ void launch_search2(fgpu_ctx* ctx, int flavour, int mode, const Search2Args& a)
             launch_one<FGPU_FLAVOUR_IMAGE, S2_RDF, false, false>(ctx, a, name);
     }
 #undef FGPU_S2
-#undef FGPU_S2_LQ
     FGPU_CUDA_CHECK(cudaGetLastError());
 }
 

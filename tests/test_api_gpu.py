@@ -216,10 +216,14 @@ def test_pmftxy_api():
     pm.compute((box, pts), th_p)
     assert np.array_equal(pm.bin_counts, gold["tilt2d_self_counts"])
     assert np.array_equal(bits(pm._pcf), bits(gold["tilt2d_self_pcf"])) and pm.box == box
-    # quaternions about z are reduced to their angle
-    quats = np.stack([np.cos(th_p / 2), np.zeros_like(th_p), np.zeros_like(th_p), np.sin(th_p / 2)], axis=1)
+    # quaternions about +z are reduced to their angle (freud/pmft.py:58-84: rowan's axis-angle, so the angle is taken
+    # in [0, 2 pi) -- a quaternion with a negative z component is a rotation about -z and is refused, as upstream)
+    th_pos = np.mod(th_p.astype(np.float64), 2 * np.pi)
+    quats = np.stack([np.cos(th_pos / 2), np.zeros_like(th_pos), np.zeros_like(th_pos), np.sin(th_pos / 2)], axis=1)
     counts_q = pmft.PMFTXY(3.0, 2.5, (30, 24)).compute((box, pts), quats).bin_counts
     assert abs(int(counts_q.sum()) - int(gold["tilt2d_self_counts"].sum())) < 50  # angles differ by rounding only
+    with pytest.raises(ValueError):
+        pmft.PMFTXY(3.0, 2.5, (30, 24)).compute((box, pts), quats * np.array([1.0, 1.0, 1.0, -1.0]))
     with pytest.raises(ValueError):
         pmft.PMFTXY(3.0, 2.5, 10).compute((Box.cube(10), random_points(Box.cube(10), 100, 1)), np.zeros(100))
     with pytest.raises(ValueError):
