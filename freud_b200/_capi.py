@@ -40,6 +40,7 @@ SIGNATURES = {
     "fgpu_ctx_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "fgpu_ctx_profile": (C.c_int, [_vp, C.c_int]),
     "fgpu_ctx_kernel_time": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    "fgpu_ctx_kernel_timeline": (C.c_int, [_vp, C.c_char_p, C.c_uint64]),
     "fgpu_points_create": (C.c_int, [_vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
     "fgpu_points_create_dev": (C.c_int, [_vp, _fp, C.c_int, _vp, C.c_uint32, _vpp]),
     "fgpu_points_create_replicated": (C.c_int, [_vp, _vp, _fp, C.c_int, _fp, C.c_uint32, _vpp]),
@@ -240,6 +241,13 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         check(lib().fgpu_ctx_kernel_time(self._h, prefix.encode(), C.byref(ms), C.byref(n), int(reset)))
         return ms.value, int(n.value)
+
+    def kernel_timeline(self):
+        """[(name, begin_us, end_us)] of the profiled launches since the last reset (``fgpu_ctx_kernel_timeline``)."""
+        buf = C.create_string_buffer(1 << 20)
+        check(lib().fgpu_ctx_kernel_timeline(self._h, buf, len(buf)))
+        rows = [ln.split() for ln in buf.value.decode().splitlines()]
+        return [(r[0], float(r[1]), float(r[2])) for r in rows]
 
     def trim(self):
         """Release the context's grow-only scratch and the arrays kept from the last NeighborList (``fgpu_ctx_trim``)."""

@@ -975,6 +975,28 @@ int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value)
     });
 }
 
+int fgpu_ctx_kernel_timeline(fgpu_ctx* ctx, char* out, uint64_t cap)
+{
+    return guarded([&] {
+        require(ctx != nullptr && out != nullptr && cap != 0, FGPU_EINVALID, "null argument");
+        bind_device(ctx);
+        sync(ctx);
+        std::string text;
+        for (const auto& t : ctx->timers)
+        {
+            float b = 0.0f, e = 0.0f;
+            FGPU_CUDA_CHECK(cudaEventElapsedTime(&b, ctx->timers.front().begin, t.begin));
+            FGPU_CUDA_CHECK(cudaEventElapsedTime(&e, ctx->timers.front().begin, t.end));
+            char line[160];
+            std::snprintf(line, sizeof(line), "%s %.3f %.3f\n", t.name, (double) b * 1e3, (double) e * 1e3);
+            text += line;
+        }
+        size_t const n = std::min<size_t>(text.size(), (size_t) cap - 1);
+        std::memcpy(out, text.data(), n);
+        out[n] = '\0';
+    });
+}
+
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable)
 {
     return guarded([&] {

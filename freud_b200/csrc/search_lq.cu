@@ -371,9 +371,9 @@ template<int FLAVOUR, bool TRI> void launch_lq(fgpu_ctx* ctx, const Search2Args&
 
 // Mapping of the NeighborList search.  Lanes over queries pays per candidate of a query's own 27 cells and needs a
 // stack per row sized for the row's bonds; the tile walk pays per candidate of a tile and per tile, and its buffers
-// adapt to dense tiles.  Automatic choice: lanes over queries while a row's stack stays within 48 entries (rows of up
-// to ~13 bonds: configs[1]); the kNN window search of configs[2] (~20 bonds per row) and everything denser stays on
-// the tile walk.
+// adapt to dense tiles.  Automatic choice: lanes over queries while a row's stack stays within 72 entries (rows of up
+// to ~25 bonds: configs[1] at 9 bonds per row, 272 -> 176 us, and the kNN window search of configs[2] at ~20 per row,
+// 452 -> 299 us); everything denser stays on the tile walk.
 void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint32_t n_points,
                             double expected_hits_per_query, int force)
 {
@@ -388,7 +388,7 @@ void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint3
     // a stack entry of the IMAGE / GHOST flavours shares its word with the boundary crossings (6 bits)
     bool const fits_word = flavour == FGPU_FLAVOUR_WRAP || n_points <= (1U << 26);
     bool const possible = n_query != 0 && fits_word && lq_warp_bytes(a.lq_c) * kLqWarps <= 160 * 1024;
-    bool const automatic = a.lq_c <= 48;
+    bool const automatic = a.lq_c <= 72;
     if (possible && (force > 0 || (force < 0 && automatic)))
     {
         a.lanes_over_queries = 1;

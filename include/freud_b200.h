@@ -86,8 +86,9 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
 
 /* Experiment / test hooks (the library reads no environment variables).  Keys: "span" (> 0: cells per home tile of
  * the tile-walk search, 0: automatic), "no_symmetry" (1: self-query IMAGE RDF without the symmetric walk),
- * "lanes_over_queries" (NeighborList search mapping: -1 automatic, 0 tile walk, 1 one query per lane).  Results never
- * depend on them; the parity tests run every mapping against the oracle. */
+ * "lanes_over_queries" (NeighborList search mapping: -1 automatic, 0 tile walk, 1 one query per lane), "lq_blocks"
+ * (> 0: resident blocks per SM of that mapping).  Results never depend on them; the parity tests run every mapping
+ * against the oracle. */
 int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value);
 
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).  While enabled,
@@ -97,6 +98,10 @@ int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value);
  * rdf_distances, local_density, local_density_rows, correlation, correlation_rows, pmft3, pmft3_rows, pmft_add_hist, bond_order, bond_order_rows, pmft_add_bins, steinhardt, steinhardt_average, steinhardt_wl, knn_rows, knn_select (general family: search_count, search_fill, search_rdf_general, emit_general). */
 int fgpu_ctx_profile(fgpu_ctx* ctx, int enable);
 int fgpu_ctx_kernel_time(fgpu_ctx* ctx, const char* prefix, double* ms_out, uint64_t* launches_out, int reset);
+/* The same records as a timeline: one line "name begin_us end_us" per profiled launch since the last reset, times
+ * relative to the first launch's begin (device clock), into `out` (NUL-terminated, truncated to `cap` bytes).  What
+ * the idle time between dependent launches of a step is read from (tools/timeline.py). */
+int fgpu_ctx_kernel_timeline(fgpu_ctx* ctx, char* out, uint64_t cap);
 
 /* ---- points + periodic cell list -------------------------------------------------------------------
  * Replaces the constructors LinkCell(box, points, n, cell_width) freud/locality/LinkCell.cc:222-260,
