@@ -53,7 +53,7 @@ __host__ __device__ inline size_t lq_warp_bytes(uint32_t c)
     return kLqHead + (size_t) 32 * c * sizeof(uint32_t);
 }
 
-template<int FLAVOUR, bool TRI> __global__ void __launch_bounds__(kLqThreads) k_search_lq(Search2Args a)
+template<int FLAVOUR, bool TRI> __global__ void __launch_bounds__(kLqThreads, 10) k_search_lq(Search2Args a)
 {
     constexpr bool CODED = FLAVOUR != FGPU_FLAVOUR_WRAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -382,7 +382,7 @@ void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint3
     a.lq_tickets = (n_query + 31U) / 32U;
     // survivors of the filter: the bonds, a few in a thousand more, and nothing for the excluded pair
     double const mu = std::max(expected_hits_per_query * 1.01, 0.5);
-    double const per_lane = mu + 7.0 * std::sqrt(mu) + 10.0;
+    double const per_lane = mu + 7.0 * std::sqrt(mu) + 4.0;
     a.lq_c = ((uint32_t) std::min(per_lane, 1024.0) + 3U) & ~3U;
     a.lq_f = 0;
     // a stack entry of the IMAGE / GHOST flavours shares its word with the boundary crossings (6 bits)
