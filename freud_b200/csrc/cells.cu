@@ -20,7 +20,7 @@ namespace fgpu {
 
 namespace {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024; // 8192 elements per tile: the look-back of the last tile is a few rounds, not fifteen
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 

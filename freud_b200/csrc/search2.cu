@@ -594,10 +594,14 @@ __global__ void __launch_bounds__(256) k_count_evals(Search2Args a, uint32_t n_q
 // ---- emit: blocks over output rows, threads over the bonds of those rows ------------------------------------
 // (A variant that staged a row-id table and the keys of the block's window in shared memory and ranked in a second
 // pass was measured slower -- 147 us against 115 us at configs[1]: the second read of the records and two more block
-// barriers cost more than the binary search and the L1 re-reads they replaced.  So was a warp-per-whole-rows variant
-// -- chunks of complete rows on the 32 lanes, the row found with five shuffles, ranks by one shuffle per row member,
-// a third of the instructions: 120 us.  The kernel is bound by its gather, not by its instructions: the rows of a
-// block's window lie scattered over the 145 MB bag in 144-byte pieces, DRAM delivers 1.4 bytes per byte used.)
+// barriers cost more than the binary search and the L1 re-reads they replaced.  Round 2 measured four more, all with
+// identical output and none faster: a warp per chunk of whole rows (row by five shuffles, ranks by one shuffle per
+// row member) 120 us; a 4-byte bag of point indices with the vector re-derived from the two points, which halves the
+// DRAM reads (231 -> 116 MB) but costs 109 M instructions for 80 M: 136 us; a shared-memory row table instead of the
+// binary search: 115 us; the record of the thread's next slot requested one iteration ahead: 125 us; and the offsets
+// scan folded into this kernel by look-back over its blocks: 145 us, for the 15 us of the scan kernel it replaces.
+// At 107 us under ncu the kernel runs DRAM at 50 %, issue slots at 72 % and L1 at 65 % with 85 % of the warps
+// resident -- no single limiter to remove.)
 // Ranks every hit inside its row (NeighborBond::less_as_tuple / less_as_distance restricted to one row with
 // weight == 1, freud/locality/NeighborBond.h:80-112) and writes the five NeighborList arrays
 // (NeighborQuery.h:470-478).  A block owns kEmitRows consecutive OUTPUT rows, so its stores cover one contiguous
