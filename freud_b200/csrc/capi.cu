@@ -968,6 +968,10 @@ int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value)
         {
             ctx->tune_lq_blocks = value;
         }
+        else if (k == "pmft_cluster")
+        {
+            ctx->tune_pmft_cluster = value;
+        }
         else
         {
             throw Error(FGPU_EINVALID, "unknown tuning key: " + k);

@@ -142,6 +142,7 @@ struct fgpu_ctx
     int tune_span = 0;                    // > 0: cells per home tile of the tile walk
     int tune_no_symmetry = 0;             // 1: self-query IMAGE RDF without the symmetric walk
     int tune_lanes_over_queries = -1;     // -1 automatic, 0 / 1: force the NeighborList search's mapping
+    int tune_pmft_cluster = 0;            // 1: PMFT histograms beyond one block's shared memory count in cluster DSMEM (slower, pmft.cu)
     int tune_lq_blocks = 0;               // > 0: resident blocks per SM of the lanes-over-queries search (the rest of
                                           // the SM's 256 KB stays L1)
     fgpu::DevBuf<double> st_partials;     // Steinhardt: per-block partial sums of the system q_lm
@@ -611,7 +612,8 @@ struct Pmft3Args
     float* deferred_dist;
     uint32_t deferred_cap;
     uint32_t* deferred_count;
-    int use_shared;
+    int use_shared;            // 0: global atomics, 1: the block's shared memory, 2: slices over a cluster (pmft.cu)
+    uint32_t slice;            // bins per CTA of the cluster
 };
 void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a);
 void launch_add_bins(fgpu_ctx* ctx, const uint32_t* bins, uint32_t n, uint32_t* hist);

@@ -22,6 +22,9 @@
 // sincosf, and the rotated coordinate must land in the same bin when moved by what a few last places of (cos, sin)
 // can move it -- the host evaluates libm only for the bonds that do not (it used to for every particle).  (Double
 // precision atan2 / sincos were tried first: 390 instructions per bond, the kernel issue-bound at 0.59 ms per frame.)
+#include <algorithm>
+#include <cstring>
+
 #include "internal.h"
 #include "pair_math.cuh"
 
@@ -204,25 +207,74 @@ __device__ __forceinline__ void pmft3_bond(const Pmft3Args& a, uint32_t i, uint3
     }
 }
 
+// DSMEM helpers (sm_90+ thread-block clusters): the shared-memory window of CTA `rank` of this cluster, and a
+// fire-and-forget add into it.
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_cluster(const uint32_t* local_word, uint32_t rank, uint32_t value)
+{
+    uint32_t const local = (uint32_t) __cvta_generic_to_shared(local_word);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"(value) : "memory");
+}
+
 // ROWS = false: one thread per bond of a NeighborList.  ROWS = true: the bonds are still in the search's bag (no
 // NeighborList was built): a group of lanes per query row, over the row's records {bond vector, bits(point index)}.
-template<int KIND, bool ROWS> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
+// Where the histogram lives (a.use_shared): 1 = in the block's shared memory (up to 10 k bins); 0 = global memory,
+// one L2 atomic per bond (the 65-90 k bin histograms of PMFTXYT / PMFTR12 / PMFTXYZ: 39 M atomics per frame at half
+// of L2's atomic throughput, profiles/ncu_r1_v9_summary.md); 2 = CLUSTER: spread over the shared memories of a
+// thread-block cluster -- CTA c of the cluster owns bins [c, c + 1) * a.slice and every CTA adds into the owner's
+// slice through distributed shared memory (red.shared::cluster), flushed once per CTA at the end.  Measured on B200
+// (8 CTAs x 45 KB, 4 clusters' worth of CTAs per SM): PMFTXYT 1.39 ms against 0.60 ms with global atomics, PMFTR12
+// 1.78 against 0.73, PMFTXYZ 0.20 against 0.16 -- seven of eight adds cross the cluster at DSMEM latency and L2's
+// atomic units outrun them.  Global atomics stay the default; the cluster path is an alternative the tests keep honest
+// (fgpu_ctx_set_tuning "pmft_cluster").
+template<int KIND, bool ROWS, bool CLUSTER = false> __global__ void __launch_bounds__(256) k_pmft3(Pmft3Args a)
 {
     extern __shared__ uint32_t p3_hist[];
     uint32_t const n_bins = a.a0.bins * a.a1.bins * a.a2.bins;
-    if (a.use_shared)
+    // CLUSTER: this CTA's slice
+    uint32_t const my_first = CLUSTER ? cluster_rank() * a.slice : 0U;
+    uint32_t const my_bins = CLUSTER ? (my_first < n_bins ? min(a.slice, n_bins - my_first) : 0U) : n_bins;
+    if (CLUSTER || a.use_shared)
     {
-        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+        for (uint32_t b = threadIdx.x; b < my_bins; b += blockDim.x)
         {
             p3_hist[b] = 0;
         }
-        __syncthreads();
+        if (CLUSTER)
+        {
+            cluster_barrier(); // every slice is clear before anybody adds into it
+        }
+        else
+        {
+            __syncthreads();
+        }
     }
     uint32_t* const h = a.use_shared ? p3_hist : a.hist;
     auto count = [&](int b0, int b1, int b2) {
         if (b0 >= 0 && b1 >= 0 && b2 >= 0)
         {
-            atomicAdd(&h[((uint32_t) b0 * a.a1.bins + (uint32_t) b1) * a.a2.bins + (uint32_t) b2], 1U);
+            uint32_t const bin = ((uint32_t) b0 * a.a1.bins + (uint32_t) b1) * a.a2.bins + (uint32_t) b2;
+            if (CLUSTER)
+            {
+                uint32_t const owner = bin / a.slice;
+                red_add_cluster(p3_hist + (bin - owner * a.slice), owner, 1U);
+            }
+            else
+            {
+                atomicAdd(&h[bin], 1U);
+            }
         }
     };
     if (ROWS)
@@ -251,7 +303,18 @@ template<int KIND, bool ROWS> __global__ void __launch_bounds__(256) k_pmft3(Pmf
             pmft3_bond<KIND>(a, ij.x, ij.y, a.vectors[3 * k], a.vectors[3 * k + 1], vz, dist, count);
         }
     }
-    if (a.use_shared)
+    if (CLUSTER)
+    {
+        cluster_barrier(); // every add of every CTA of the cluster has landed; from here on a CTA reads only its own slice
+        for (uint32_t b = threadIdx.x; b < my_bins; b += blockDim.x)
+        {
+            if (p3_hist[b] != 0)
+            {
+                atomicAdd(&a.hist[my_first + b], p3_hist[b]);
+            }
+        }
+    }
+    else if (a.use_shared)
     {
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
@@ -394,6 +457,29 @@ __global__ void __launch_bounds__(256) k_add_bins(const uint32_t* __restrict__ b
 
 } // namespace
 
+template<int KIND, bool ROWS> void launch_pmft3_cluster(fgpu_ctx* ctx, const Pmft3Args& a, unsigned blocks, int cluster, size_t dyn)
+{
+    auto kern = k_pmft3<KIND, ROWS, true>;
+    if (dyn > 48 * 1024)
+    {
+        FGPU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned) cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    FGPU_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+}
+
 void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
 {
     bool const rows = a.bag != nullptr;
@@ -401,15 +487,50 @@ void launch_pmft3(fgpu_ctx* ctx, int kind, Pmft3Args a)
     {
         return;
     }
-    size_t const smem = (size_t) a.a0.bins * a.a1.bins * a.a2.bins * sizeof(uint32_t);
+    uint32_t const n_bins = a.a0.bins * a.a1.bins * a.a2.bins;
+    size_t const smem = (size_t) n_bins * sizeof(uint32_t);
     a.use_shared = smem <= 40 * 1024 ? 1 : 0;
-    size_t const dyn = a.use_shared ? smem : 0;
+    a.slice = n_bins;
+    // beyond one block's shared memory: a cluster of 2, 4 or 8 CTAs holds the histogram in slices of at most 48 KB
+    // where that is possible (several clusters per SM), else of up to 200 KB
+    int cluster = 0;
+    if (!a.use_shared && ctx->tune_pmft_cluster != 0)
+    {
+        for (int c = 2; c <= 8 && cluster == 0; c *= 2)
+        {
+            if ((smem + c - 1) / c <= 48 * 1024)
+            {
+                cluster = c;
+            }
+        }
+        if (cluster == 0 && (smem + 7) / 8 <= 200 * 1024)
+        {
+            cluster = 8;
+        }
+    }
+    size_t dyn = a.use_shared ? smem : 0;
     uint64_t const want = rows ? ((uint64_t) a.n_rows * a.group + 255) / 256 : (a.n_bonds + 255) / 256;
-    unsigned const blocks = (unsigned) std::min<uint64_t>(want, (uint64_t) ctx->sm_count * 8U);
+    unsigned blocks = (unsigned) std::min<uint64_t>(want, (uint64_t) ctx->sm_count * 8U);
+    if (cluster != 0)
+    {
+        a.slice = (n_bins + (uint32_t) cluster - 1U) / (uint32_t) cluster;
+        dyn = (size_t) a.slice * sizeof(uint32_t);
+        a.use_shared = 2;
+        unsigned const per_sm = (unsigned) std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (dyn + 1024)));
+        blocks = (unsigned) std::min<uint64_t>(want, (uint64_t) ctx->sm_count * per_sm);
+        blocks = std::max(1U, (blocks + (unsigned) cluster - 1U) / (unsigned) cluster) * (unsigned) cluster;
+    }
     {
         KernelScope ks(ctx, rows ? "pmft3_rows" : "pmft3");
 #define FGPU_PMFT3_LAUNCH(KIND)                                                                                  \
-    if (rows)                                                                                                    \
+    if (cluster != 0)                                                                                            \
+    {                                                                                                            \
+        if (rows)                                                                                                \
+            launch_pmft3_cluster<KIND, true>(ctx, a, blocks, cluster, dyn);                                      \
+        else                                                                                                     \
+            launch_pmft3_cluster<KIND, false>(ctx, a, blocks, cluster, dyn);                                     \
+    }                                                                                                            \
+    else if (rows)                                                                                               \
     {                                                                                                            \
         k_pmft3<KIND, true><<<blocks, 256, dyn, ctx->stream>>>(a);                                               \
     }                                                                                                            \

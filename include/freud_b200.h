@@ -87,8 +87,10 @@ int fgpu_ctx_force_general_search(fgpu_ctx* ctx, int enable);
 /* Experiment / test hooks (the library reads no environment variables).  Keys: "span" (> 0: cells per home tile of
  * the tile-walk search, 0: automatic), "no_symmetry" (1: self-query IMAGE RDF without the symmetric walk),
  * "lanes_over_queries" (NeighborList search mapping: -1 automatic, 0 tile walk, 1 one query per lane), "lq_blocks"
- * (> 0: resident blocks per SM of that mapping).  Results never depend on them; the parity tests run every mapping
- * against the oracle. */
+ * (> 0: resident blocks per SM of that mapping), "pmft_cluster" (1: PMFT histograms too large for one block's shared
+ * memory count in the distributed shared memory of a thread-block cluster instead of with global atomics -- measured
+ * 2.3x slower on B200, kept as a tested alternative).  Results never depend on them; the parity tests run every
+ * mapping against the oracle. */
 int fgpu_ctx_set_tuning(fgpu_ctx* ctx, const char* key, int value);
 
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).  While enabled,

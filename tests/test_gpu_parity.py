@@ -376,7 +376,21 @@ def test_pmft3_over_a_neighbor_list(ctx):
     big = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (20, 36, 36))  # 104 KB of counters: global atomics
     big.accumulate_nlist(dp.ball_query(None, IMAGE, 4.0, 0.0, True), th_p, th_p)
     nl = port.ball_nlist(port.IMAGE, box, True, pts, pts, 4.0, 0.0, True)
-    assert np.array_equal(big.read(), port.pmft3(port.PMFT_R12, box, 3000, nl, th_p, th_p, (4.0,), (20, 36, 36))[0])
+    want_big = port.pmft3(port.PMFT_R12, box, 3000, nl, th_p, th_p, (4.0,), (20, 36, 36))[0]
+    assert np.array_equal(big.read(), want_big)
+    # the same histogram in slices over the shared memories of a thread-block cluster (the alternative to global
+    # atomics, pmft.cu), through a NeighborList and straight from the search's bag
+    ctx.set_tuning("pmft_cluster", 1)
+    try:
+        for route in ("nlist", "bag"):
+            big = capi.DevicePMFT(ctx, capi.PMFT_R12, (4.0,), (20, 36, 36))
+            if route == "nlist":
+                big.accumulate_nlist(dp.ball_query(None, IMAGE, 4.0, 0.0, True), th_p, th_p)
+            else:
+                big.accumulate(dp, None, IMAGE, 4.0, th_p, th_p, exclude_ii=True)
+            assert np.array_equal(big.read(), want_big), route
+    finally:
+        ctx.set_tuning("pmft_cluster", 0)
     box, pts, th = pmft3_lattice()
     dp = capi.DevicePoints(ctx, box, pts)
     xyt = capi.DevicePMFT(ctx, capi.PMFT_XYT, (3.0, 3.0), (6, 6, 8))
