@@ -411,28 +411,34 @@ template<int L, int KMAX> __global__ void __launch_bounds__(kThreads) k_knn_ylm(
         ry0 = a.xyz[3 * (size_t) i + 1];
         rz0 = a.xyz[3 * (size_t) i + 2];
     }
-    // the kept points' positions, four gathers in flight, then their Y_lm
+    // The kept points' Y_lm in a ROLLED loop: unrolled over the KMAX slots the kernel was 76 KB of code (l = 6, k = 12)
+    // and its warps, each at its own place, waited for instruction fetches more than for anything else (ncu:
+    // stalled_no_instruction 5.1 per issue).  The sorted keys go to the thread's column of a shared-memory table so
+    // that the loop can index them; the next point's position is requested while the current one is evaluated.
+    __shared__ unsigned long long s_key[KMAX][kThreads];
 #pragma unroll
-    for (int q0 = 0; q0 < KMAX; q0 += 4)
+    for (int q = 0; q < KMAX; ++q)
     {
-        float4 p[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
+        s_key[q][threadIdx.x] = key[q];
+    }
+    float4 p_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (kept != 0)
+    {
+        p_next = __ldg(a.xyz4 + (uint32_t) (key[0] & 0xffffffffULL));
+    }
+#pragma unroll 1
+    for (uint32_t q = 0; q < kept; ++q)
+    {
+        unsigned long long const kq = s_key[q][threadIdx.x];
+        float4 const p = p_next;
+        if (q + 1 < kept)
         {
-            bool const live = (uint32_t) (q0 + u) < kept;
-            p[u] = live ? __ldg(a.xyz4 + (uint32_t) (key[q0 + u] & 0xffffffffULL)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            p_next = __ldg(a.xyz4 + (uint32_t) (s_key[q + 1][threadIdx.x] & 0xffffffffULL));
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            if ((uint32_t) (q0 + u) < kept)
-            {
-                float const dist = __fsqrt_rn(__uint_as_float((uint32_t) (key[q0 + u] >> 32))); // NeighborBond.h:41-44
-                Angles const ang = bond_angles(a, rx0, ry0, rz0, p[u].x, p[u].y, p[u].z, dist);
-                accumulate_ylm<L>(ang, 1.0f, re, im);
-                total_weight += 1.0f;
-            }
-        }
+        float const dist = __fsqrt_rn(__uint_as_float((uint32_t) (kq >> 32))); // NeighborBond.h:41-44
+        Angles const ang = bond_angles(a, rx0, ry0, rz0, p.x, p.y, p.z, dist);
+        accumulate_ylm<L>(ang, 1.0f, re, im);
+        total_weight += 1.0f;
     }
     finish_particle<L>(a, i, active, re, im, total_weight);
 }
