@@ -153,8 +153,8 @@ def workload_nl(ctx, rank, n, flavour=WRAP, r_max=3.0):
         "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
         "pipeline": 16 * (n + n) + 28 * n_bonds + 8 * n,  # SURVEY.md section 8d "NL emit"
     }
-    # measured DRAM bytes per launch (ncu, profiles/ncu_r1_v6_summary.md): only for the configuration it was taken on
-    traffic = {"search_nl": 22736384 + 99777536, "emit": 225808896 + 208339968} if n == 1_000_000 and r_max == 3.0 else {}
+    # measured DRAM bytes per launch (ncu, profiles/ncu_r2_summary.md section 3): only for the configuration it was taken on
+    traffic = {"search_nl": 24105216 + 105016832, "emit": 230652928 + 208475136} if n == 1_000_000 and r_max == 3.0 else {}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=evals, unit="pair_evals/s", traffic=traffic,
                 metric="neighbour_pair_evals_per_sec",
                 config={"workload": f"LinkCell NeighborList r_max={r_max:g} exclude_ii N={n} cubic L={L:.4f} rho=0.08 "
@@ -242,9 +242,8 @@ def workload_q6(ctx, rank, n):
                 config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05"},
                 h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={},
                 dp=dp, traffic_source=TRAFFIC_SOURCE,
-                # measured DRAM bytes of one launch (ncu, profiles/ncu_r1_v6_summary.md "full_q6")
-                traffic={"search_nl": 20075008 + 221451008, "knn_select": 366002432 + 323085568,
-                         "steinhardt": 162739968 + 6141952} if n == 1_000_188 else {})
+                # measured DRAM bytes of one launch (ncu, profiles/ncu_r2_summary.md section 3)
+                traffic={"search_nl": 19511808 + 218465280, "knn_ylm": 406877952 + 7923968} if n == 1_000_188 else {})
 
 
 def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
