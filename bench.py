@@ -1250,10 +1250,20 @@ def reference_leg(name, n, steps, budget, threads):
     sample of the leg's workload; same metric / unit / config as the b200 arm's leg."""
     from freud_b200 import data
 
+    def rep(fn):
+        """`steps` bounded samples, each with the wall time it took (the line's ms_per_step)"""
+        out = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            r = fn()
+            r["wall_s"] = time.perf_counter() - t0
+            out.append(r)
+        return out
+
     if name in ("nl", "nl_image"):
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)
-        runs = [cpu_reference_nl(box, pts, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_nl(box, pts, 3.0, budget_s=budget, threads=threads))
         metric, unit = "neighbour_pair_evals_per_sec", "pair_evals/s"
         config = {"workload": f"LinkCell NeighborList r_max=3 exclude_ii N={n} cubic L={L:.4f} rho=0.08 flavour=wrap"}
     elif name in ("rdf", "rdf_wrap", "rdf4m", "traj2d"):
@@ -1262,7 +1272,7 @@ def reference_leg(name, n, steps, budget, threads):
         tilt = (0.3, 0.2, 0.1) if name == "rdf4m" else None
         box, pts = data.make_random_system(L, n, is2D=is2d, seed=0, tilt=tilt)
         bins = 500 if name == "rdf4m" else 100
-        runs = [cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_rdf(box, pts, bins, 5.0, budget_s=budget, threads=threads))
         metric, unit = "rdf_frames_per_sec", "frames/s"
         config = {"workload": f"RDF bins={bins} r_max=5 N={n} L={L:.4f}"
                               + (" triclinic (xy=.3,xz=.2,yz=.1)" if tilt else "") + (" 2-D" if is2d else "")}
@@ -1271,14 +1281,12 @@ def reference_leg(name, n, steps, budget, threads):
         box, pts = data.make_random_system(L, n, is2D=True, seed=0)
         rs = np.random.RandomState(29)
         angles = (rs.random_sample(n) * 2 * np.pi - np.pi).astype(np.float32)
-        runs = [cpu_reference_pmftxy(box, pts, angles, 4.0, 3.0, (100, 100), budget_s=budget, threads=threads)
-                for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_pmftxy(box, pts, angles, 4.0, 3.0, (100, 100), budget_s=budget, threads=threads))
         metric, unit = "pmftxy_particles_per_sec", "particles/s"
         config = {"workload": f"PMFTXY x_max=4 y_max=3 bins=100x100 N={n} 2-D square L={L:.4f} areal density 0.5"}
     elif name in HIST_CLIENTS:
         box, pts, orient, spec = hist_client_inputs(name, n, 0)
-        runs = [cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=budget, threads=threads)
-                for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_hist_client(name, box, pts, orient, spec, budget_s=budget, threads=threads))
         metric, unit = f"{name}_particles_per_sec", "particles/s"
         config = {"workload": spec["label"]}
     elif name == "correlation":
@@ -1286,26 +1294,26 @@ def reference_leg(name, n, steps, budget, threads):
         box, pts = data.make_random_system(L, n, seed=0)
         rs = np.random.RandomState(17)
         values = rs.standard_normal(n) + 1j * rs.standard_normal(n)
-        runs = [cpu_reference_correlation(box, pts, values, 100, 3.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_correlation(box, pts, values, 100, 3.0, budget_s=budget, threads=threads))
         metric, unit = "correlation_function_particles_per_sec", "particles/s"
         config = {"workload": f"CorrelationFunction bins=100 r_max=3 complex values N={n} cubic L={L:.4f} rho=0.08"}
     elif name == "local_density":
         L = (n / RHO) ** (1.0 / 3.0)
         box, pts = data.make_random_system(L, n, seed=0)
-        runs = [cpu_reference_local_density(box, pts, 2.5, 1.0, budget_s=budget, threads=threads) for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_local_density(box, pts, 2.5, 1.0, budget_s=budget, threads=threads))
         metric, unit = "local_density_particles_per_sec", "particles/s"
         config = {"workload": f"LocalDensity r_max=2.5 diameter=1 N={n} cubic L={L:.4f} rho=0.08"}
     else:
         m = max(2, round((n / 4) ** (1.0 / 3.0)))
         box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=0)
-        runs = [cpu_reference_q6(box, pts, threads=threads) for _ in range(steps)]
+        runs = rep(lambda: cpu_reference_q6(box, pts, threads=threads))
         metric, unit = "q6_particles_per_sec", "particles/s"
         config = {"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={len(pts)} sigma=0.05"}
     vals = [r["value"] for r in runs if r.get("value")]
     value = float(np.median(vals)) if vals else None
     base = dict(runs[-1], value=value)
     return {"impl": "reference", "metric": metric, "value": value, "unit": unit, "steps": steps,
-            "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+            "warmup": 0, "ms_per_step": float(np.median([r["wall_s"] for r in runs])) * 1e3, "higher_is_better": True,
             "scaling": "strong" if name == "rdf4m" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
