@@ -371,9 +371,15 @@ template<int FLAVOUR, bool TRI> void launch_lq(fgpu_ctx* ctx, const Search2Args&
 
 // Mapping of the NeighborList search.  Lanes over queries pays per candidate of a query's own 27 cells and needs a
 // stack per row sized for the row's bonds; the tile walk pays per candidate of a tile and per tile, and its buffers
-// adapt to dense tiles.  Automatic choice: lanes over queries while a row's stack stays within 72 entries (rows of up
-// to ~25 bonds: configs[1] at 9 bonds per row, 272 -> 176 us, and the kNN window search of configs[2] at ~20 per row,
-// 452 -> 299 us); everything denser stays on the tile walk.
+// adapt to dense tiles.  Automatic choice: lanes over queries while a row's stack stays within 96 entries (rows of up
+// to ~40 bonds).  Measured against the tile walk: configs[1] at 9 bonds per row 272 -> 171 us, the kNN window search
+// of configs[2] at ~20 per row 452 -> 278 us, the 2-D ball query of the PMFT benches at 39 per row 553 -> 466 us;
+// everything denser stays on the tile walk.
+//
+// The fused RDF was tried in this mapping too (IMAGE arithmetic, r_sq of a bond on the lane's stack, every lane
+// binning its own stack): 314 us against the tile walk's 237 us at 1 M points, r_max = 5 -- the exact test costs the
+// same 16 instructions per pair in both, the tile walk runs it on dense lanes (lanes over candidates) where this
+// mapping walks to the longest of 32 runs (65 % of the lanes busy): 270 M instructions against 227 M.  Not in the tree.
 void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint32_t n_points,
                             double expected_hits_per_query, int force)
 {
@@ -388,7 +394,7 @@ void search2_choose_mapping(Search2Args& a, int flavour, uint32_t n_query, uint3
     // a stack entry of the IMAGE / GHOST flavours shares its word with the boundary crossings (6 bits)
     bool const fits_word = flavour == FGPU_FLAVOUR_WRAP || n_points <= (1U << 26);
     bool const possible = n_query != 0 && fits_word && lq_warp_bytes(a.lq_c) * kLqWarps <= 160 * 1024;
-    bool const automatic = a.lq_c <= 72;
+    bool const automatic = a.lq_c <= 96;
     if (possible && (force > 0 || (force < 0 && automatic)))
     {
         a.lanes_over_queries = 1;

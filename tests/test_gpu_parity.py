@@ -873,3 +873,36 @@ def test_steinhardt_knn_fused_matches_list_route(ctx, flavour):
     odd = dp.steinhardt_knn(20, [5, 7], exclude_ii=True, flavour=flavour)["ql"]
     odd_l = dp.steinhardt(dp.knn_query(None, 20, exclude_ii=True, flavour=flavour), [5, 7])["ql"]
     assert np.allclose(odd, odd_l, rtol=2e-6, atol=1e-7)
+
+
+def test_kernel_timeline_of_a_frame():
+    """fgpu_ctx_profile + fgpu_ctx_kernel_time / fgpu_ctx_kernel_timeline (tracing): every launch
+    of a NeighborList frame is named and bracketed on the device clock, in stream order, and the summed durations of
+    the two views agree."""
+    from freud_b200.box import Box
+
+    capi = _capi()
+    c = capi.Context(0)
+    try:
+        box = Box.cube(40.0)
+        pts = random_points(box, 20000, 5)
+        dp = capi.DevicePoints(c, box, pts)
+        dp.ball_query(None, WRAP, 3.0, 0.0, True)  # warm: allocations, kernel attributes
+        c.profile(True)
+        c.kernel_time("", reset=True)
+        dp.build_cells(3.0)
+        nl = dp.ball_query(None, WRAP, 3.0, 0.0, True)
+        tl = c.kernel_timeline()
+        total_ms, launches = c.kernel_time("", reset=True)
+        names = [t[0] for t in tl]
+        assert launches == len(tl) >= 6
+        for must in ("cell_assign", "scan", "cell_scatter", "search_nl", "emit"):
+            assert must in names, names
+        assert names.index("cell_assign") < names.index("search_nl") < names.index("emit")
+        assert tl[0][1] == 0.0 and all(e >= b for _, b, e in tl)
+        assert all(tl[k + 1][1] >= tl[k][2] - 1e-3 for k in range(len(tl) - 1))  # one stream: no overlap
+        assert abs(sum(e - b for _, b, e in tl) - total_ms * 1e3) < 1.0  # microseconds
+        assert nl.num_bonds > 0
+        c.profile(False)
+    finally:
+        c.close()
