@@ -214,11 +214,12 @@ def test_cell_list_is_a_partition(ctx):
     cell_start, order = dp.read_cells(dims)
     assert cell_start[0] == 0 and cell_start[-1] == n and np.all(np.diff(cell_start.astype(np.int64)) >= 0)
     assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
-    # cell thickness covers r along every axis
-    pd = box.nearest_plane_distance()
+    # cell thickness covers r along every axis; plane distances and fractional coordinates from the ORACLE's Box
+    # (Box::getNearestPlaneDistance, Box::makeFractional: freud/box/Box.h:243-255, 468-487), not from this package's own
+    _, pd = port.box_info(box, False)
     assert np.all(pd / dims > r)
     # membership: fractional coordinate of every point lies inside its cell (up to float rounding)
-    frac = box.make_fractional(pts[order]).astype(np.float64)
+    frac = port.box_apply(box, False, "fractional", pts[order]).astype(np.float64)
     cell_of_slot = np.searchsorted(cell_start, np.arange(n), side="right") - 1
     cx = cell_of_slot % dims[0]
     cy = (cell_of_slot // dims[0]) % dims[1]
