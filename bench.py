@@ -399,6 +399,7 @@ def cpu_reference_pmftxy(box, pts, angles, x_max, y_max, bins, budget_s=12.0, th
 
 
 HIST_CLIENTS = ("pmftxyz", "pmftxyt", "pmftr12", "bond_order")
+FCC_SIGMA = 0.05  # noise on the FCC lattice of the bond_order workload (--sigma 0: the perfect lattice, every bond on a bin edge)
 
 
 def hist_client_inputs(name, n, seed):
@@ -430,10 +431,10 @@ def hist_client_inputs(name, n, seed):
                           f"image flavour) N={n} cubic L={L:.4f} rho=0.08")
     else:
         m = max(2, round((n / 4) ** (1.0 / 3.0)))
-        box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=seed)
+        box, pts = data.make_fcc_system(m, sigma_noise=FCC_SIGMA, seed=seed)
         orient = None
         spec = dict(kind=None, bins=(72, 36), k=12,
-                    label=f"BondOrder bins=72x36 mode=bod num_neighbors=12 FCC {m}^3x4={len(pts)} sigma=0.05")
+                    label=f"BondOrder bins=72x36 mode=bod num_neighbors=12 FCC {m}^3x4={len(pts)} sigma={FCC_SIGMA:g}")
     return box, pts, orient, spec
 
 
@@ -480,13 +481,16 @@ def workload_hist_client(ctx, rank, n, name):
         accumulate(query(_capi.DevicePoints(ctx, box, pin_pts)))
         return hist.read()
 
+    step_dev()
+    host_binned = int(hist.host_binned_bonds)  # bonds next to a bin edge, binned by the host's libm
     nb = int(np.prod(spec["bins"]))
     o_bytes = 0 if orient is None else orient.nbytes
     algo = {kernel: 20 * n_bonds + 2 * o_bytes + 4 * nb, "pipeline": 16 * (n + n) + 2 * o_bytes + 4 * nb,
             "search_nl": 16 * (n + n) + 16 * n_bonds + 8 * n, "emit": 16 * n_bonds + 16 * n + 12 * n + 4 * n + 28 * n_bonds,
             "knn_select": (16 * 26 + 12 + 28 * 12) * n}
     return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric=f"{name}_particles_per_sec",
-                config={"workload": spec["label"], "bonds_per_step": n_bonds}, h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
+                config={"workload": spec["label"], "bonds_per_step": n_bonds, "host_binned_bonds_per_step": host_binned},
+                h2d=12 * n + o_bytes, d2h=4 * nb, algo=algo,
                 keep=keep, box=box, pts=pts, orient=orient, spec=spec, hist=hist, secondary={"bonds": n_bonds},
                 algo_per_step=True,
                 # measured DRAM bytes of one launch of the client's kernel (ncu, profiles/ncu_r1_v8_summary.md)
@@ -820,10 +824,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="rdf4m: launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--sigma", type=float, default=None,
+                    help="bond_order: noise on the FCC lattice (0 = the perfect lattice: every bond sits on a bin edge and is "
+                         "binned by the host -- the cliff DESIGN.md section 8 names)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="experiment hook: fgpu_ctx_set_tuning(key, value), e.g. span=2 or lanes_over_queries=1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.sigma is not None:
+        global FCC_SIGMA
+        FCC_SIGMA = args.sigma
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

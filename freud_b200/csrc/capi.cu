@@ -1364,8 +1364,12 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
                         ra.total = ctx->d_scalars + 3;
                         ra.unresolved_rows = unresolved_rows;
                         launch_knn_rows(ctx, ra);
-                        FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
-                        exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+                        if (bag_consumer == nullptr)
+                        {
+                            // offsets of the NeighborList's rows; a compute that reads the bag itself has no use for them
+                            FGPU_CUDA_CHECK(cudaMemsetAsync(nl->row_start.ptr + n_query, 0, sizeof(uint32_t), ctx->stream));
+                            exclusive_scan_u32(ctx, nl->row_start.ptr, (size_t) n_query + 1);
+                        }
                         d2h(ctx, ctx->h_scalars + 2, ctx->d_scalars + 2, 4 * sizeof(unsigned long long));
                         sync(ctx);
                         int const failed = (int) (ctx->h_scalars[4] & 0xffffffffULL);
@@ -2304,7 +2308,7 @@ bool run_pmft_pass(fgpu_pmft* pmft, Pmft3Args& a, uint64_t cap, const PmftHostIn
                                                 : kNone;
     }
     };
-    unsigned const n_threads = n_def >= 4096 ? std::max(1U, std::min(8U, std::thread::hardware_concurrency())) : 1U;
+    unsigned const n_threads = n_def >= 4096 ? std::max(1U, std::min(32U, std::thread::hardware_concurrency())) : 1U;
     {
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < n_threads; ++t)
@@ -2621,39 +2625,64 @@ bool run_bond_order_pass(fgpu_bondorder* bo, BondOrderArgs& a, uint64_t cap, con
     d2h(ctx, rec.data(), bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
     d2h(ctx, rec_z.data(), bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
     sync(ctx);
+    // two libm calls per bond: a perfect lattice leaves every bond here (each sits on a bin edge), so the loop runs on
+    // every host thread (one thread took 0.5 s for the 12 M bonds of a million-particle FCC frame)
+    std::vector<uint32_t> slot(n_def);
+    uint32_t const kNone = 0xffffffffU;
+    auto bin_range = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t r = lo; r < hi; ++r)
+        {
+            uint32_t const i = rec[r].x, j = rec[r].y;
+            float x, y, z = rec_z[r];
+            std::memcpy(&x, &rec[r].z, sizeof(float));
+            std::memcpy(&y, &rec[r].w, sizeof(float));
+            if (mode != FGPU_BOND_ORDER_BOD) // BondOrder.cc:108-134
+            {
+                const float* rq = orientations_host + 4 * (size_t) j;
+                const float* q = query_orientations_host + 4 * (size_t) i;
+                if (mode == FGPU_BOND_ORDER_OOCD)
+                {
+                    x = 0.0f;
+                    y = 0.0f;
+                    z = 1.0f;
+                    host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+                }
+                host_quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], x, y, z);
+                if (mode == FGPU_BOND_ORDER_OBCD)
+                {
+                    host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
+                }
+            }
+            float const theta = host_mod_two_pi(std::atan2(y, x)); // BondOrder.cc:140-141
+            float const xx = x * x, yy = y * y, zz = z * z;
+            float const dot = (xx + yy) + zz;
+            float const arg = z / std::sqrt(dot);
+            float const phi = std::acos(arg); // :144
+            int const bt = host_axis_bin(a.at, theta), bp = host_axis_bin(a.ap, phi);
+            slot[r] = bt >= 0 && bp >= 0 ? (uint32_t) bt * a.ap.bins + (uint32_t) bp : kNone;
+        }
+    };
+    unsigned const n_threads = n_def >= 4096 ? std::max(1U, std::min(32U, std::thread::hardware_concurrency())) : 1U;
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_threads; ++t)
+        {
+            pool.emplace_back(bin_range, (uint32_t) ((uint64_t) n_def * t / n_threads),
+                              (uint32_t) ((uint64_t) n_def * (t + 1) / n_threads));
+        }
+        bin_range(0, (uint32_t) ((uint64_t) n_def / n_threads));
+        for (auto& th : pool)
+        {
+            th.join();
+        }
+    }
     std::vector<uint32_t> bins;
+    bins.reserve(n_def);
     for (uint32_t r = 0; r < n_def; ++r)
     {
-        uint32_t const i = rec[r].x, j = rec[r].y;
-        float x, y, z = rec_z[r];
-        std::memcpy(&x, &rec[r].z, sizeof(float));
-        std::memcpy(&y, &rec[r].w, sizeof(float));
-        if (mode != FGPU_BOND_ORDER_BOD) // BondOrder.cc:108-134
+        if (slot[r] != kNone)
         {
-            const float* rq = orientations_host + 4 * (size_t) j;
-            const float* q = query_orientations_host + 4 * (size_t) i;
-            if (mode == FGPU_BOND_ORDER_OOCD)
-            {
-                x = 0.0f;
-                y = 0.0f;
-                z = 1.0f;
-                host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
-            }
-            host_quat_rotate(rq[0], -rq[1], -rq[2], -rq[3], x, y, z);
-            if (mode == FGPU_BOND_ORDER_OBCD)
-            {
-                host_quat_rotate(q[0], q[1], q[2], q[3], x, y, z);
-            }
-        }
-        float const theta = host_mod_two_pi(std::atan2(y, x)); // BondOrder.cc:140-141
-        float const xx = x * x, yy = y * y, zz = z * z;
-        float const dot = (xx + yy) + zz;
-        float const arg = z / std::sqrt(dot);
-        float const phi = std::acos(arg); // :144
-        int const bt = host_axis_bin(a.at, theta), bp = host_axis_bin(a.ap, phi);
-        if (bt >= 0 && bp >= 0)
-        {
-            bins.push_back((uint32_t) bt * a.ap.bins + (uint32_t) bp);
+            bins.push_back(slot[r]);
         }
     }
     bo->deferred_total += n_def;

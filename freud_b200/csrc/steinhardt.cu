@@ -443,11 +443,14 @@ template<int L, int KMAX> __global__ void __launch_bounds__(kThreads) k_knn_ylm(
     finish_particle<L>(a, i, active, re, im, total_weight);
 }
 
-// Column sums of the per-block partials: one block per column, fixed summation order (bitwise reproducible).
-__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, uint32_t n_rows, uint32_t width,
-                                                      double* __restrict__ out)
+// Column sums of the per-block partials: one block per column, fixed summation order (bitwise reproducible).  1024
+// threads: a column of 7 814 partials (C3) is eight independent loads per thread, all in flight at once -- with 256
+// threads the kernel was thirty dependent rounds of DRAM latency on fourteen SMs (18 us).
+constexpr int kSumThreads = 1024;
+__global__ void __launch_bounds__(kSumThreads) k_sum_partials(const double* __restrict__ partials, uint32_t n_rows,
+                                                              uint32_t width, double* __restrict__ out)
 {
-    __shared__ double s_sum[256];
+    __shared__ double s_sum[kSumThreads];
     uint32_t const col = blockIdx.x;
     double v = 0.0;
     for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x)
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__
     }
     s_sum[threadIdx.x] = v;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1)
+    for (int o = kSumThreads / 2; o > 0; o >>= 1)
     {
         if ((int) threadIdx.x < o)
         {
@@ -775,7 +778,7 @@ template<int L> void launch_single(fgpu_ctx* ctx, const SteinhardtArgs& a_in)
     k_steinhardt_single<L><<<blocks, kThreads, 0, ctx->stream>>>(a);
     if (a.sys_qlm != nullptr)
     {
-        k_sum_partials<<<width, 256, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
+        k_sum_partials<<<width, kSumThreads, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
     }
 }
 
@@ -798,7 +801,7 @@ template<int L> void launch_fused(fgpu_ctx* ctx, SteinhardtArgs a, const KnnYlmA
     }
     if (a.sys_qlm != nullptr)
     {
-        k_sum_partials<<<width, 256, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
+        k_sum_partials<<<width, kSumThreads, 0, ctx->stream>>>(a.sys_partials, blocks, width, a.sys_qlm);
     }
 }
 
@@ -906,7 +909,7 @@ void launch_steinhardt(fgpu_ctx* ctx, const SteinhardtArgs& a, const std::vector
         k_steinhardt_generic<<<blocks, kThreads, 0, ctx->stream>>>(g, lmax, (int) ls.size(), n_acc, tot_m);
         if (a.sys_qlm != nullptr)
         {
-            k_sum_partials<<<width, 256, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
+            k_sum_partials<<<width, kSumThreads, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
         }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
@@ -945,7 +948,7 @@ void launch_steinhardt_average(fgpu_ctx* ctx, const SteinhardtAveArgs& a, int n_
         k_steinhardt_average<<<blocks, kThreads, 0, ctx->stream>>>(g, n_ls);
         if (a.sys_qlm != nullptr)
         {
-            k_sum_partials<<<width, 256, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
+            k_sum_partials<<<width, kSumThreads, 0, ctx->stream>>>(g.sys_partials, blocks, width, a.sys_qlm);
         }
     }
     FGPU_CUDA_CHECK(cudaGetLastError());
