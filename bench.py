@@ -841,7 +841,9 @@ def main():
     if args.workload is not None:
         legs = [args.workload]
     elif world == 1:
-        legs = ["nl", "rdf", "q6"]        # BASELINE.json metric: pair evals/s + RDF frames/s @1M r_max=5 + Q6 particles/s
+        # BASELINE.json metric: pair evals/s + RDF frames/s @1M r_max=5 + Q6 particles/s; and configs[3] on this one GPU,
+        # the N = 1 point of the strong-scaling curve whose N > 1 points are the headline of the multi-GPU runs
+        legs = ["nl", "rdf", "q6", "rdf4m"]
     else:
         legs = ["rdf4m", "traj2d", "nl"]  # configs[3] (strong scaling, the headline), configs[4], NeighborList replicas
 
@@ -878,7 +880,8 @@ def main():
         if len(lines) > 1:
             line["legs"] = {name: ln for name, ln in zip(legs[1:], lines[1:])}
             for name, ln in zip(legs[1:], lines[1:]):
-                line[ln["metric"] if ln["metric"] != line["metric"] else f"{name}_{ln['metric']}"] = ln["value"]
+                key = ln["metric"] if ln["metric"] != line["metric"] and ln["metric"] not in line else f"{name}_{ln['metric']}"
+                line[key] = ln["value"]
             line["parity_all_legs"] = all((ln.get("parity") or {}).get("bitwise_equal") is not False
                                           and (ln.get("parity") or {}).get("ql_within_tolerance") is not False
                                           for ln in lines)
@@ -1344,7 +1347,8 @@ def run_reference_arm(args, rank, world, legs):
     if len(lines) > 1:
         line["legs"] = {name: ln for name, ln in zip(legs[1:], lines[1:])}
         for name, ln in zip(legs[1:], lines[1:]):
-            line[ln["metric"] if ln["metric"] != line["metric"] else f"{name}_{ln['metric']}"] = ln["value"]
+            key = ln["metric"] if ln["metric"] != line["metric"] and ln["metric"] not in line else f"{name}_{ln['metric']}"
+            line[key] = ln["value"]
     print(json.dumps(line))
 
 
