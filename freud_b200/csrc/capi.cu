@@ -2185,6 +2185,26 @@ int fgpu_pmft_reset(fgpu_pmft* pmft)
 
 namespace {
 
+// Page-locked scratch from the library's host cache (fgpu_host_alloc): the bonds left to the host come back at the
+// link's rate and without a zero-fill (a perfect lattice leaves all of them: 240 MB per million-particle frame).
+struct HostScratch
+{
+    void* p = nullptr;
+    explicit HostScratch(size_t bytes)
+    {
+        if (fgpu_host_alloc(bytes, &p) != FGPU_OK)
+        {
+            throw Error(FGPU_ENOMEM, fgpu_last_error());
+        }
+    }
+    HostScratch(const HostScratch&) = delete;
+    HostScratch& operator=(const HostScratch&) = delete;
+    ~HostScratch()
+    {
+        fgpu_host_free(p);
+    }
+};
+
 struct PmftHostInputs
 {
     const float* orientations;
@@ -2263,17 +2283,18 @@ bool run_pmft_pass(fgpu_pmft* pmft, Pmft3Args& a, uint64_t cap, const PmftHostIn
         return true;
     }
     // the bonds whose coordinate or angle sits within a few ulps of a bin edge: the reference's own libm decides
-    std::vector<uint4> rec(n_def);
-    std::vector<float> rec_dist;
-    d2h(ctx, rec.data(), pmft->deferred.ptr, (size_t) n_def * sizeof(uint4));
+    HostScratch rec_mem((size_t) n_def * sizeof(uint4)), dist_mem(kind == FGPU_PMFT_R12 ? (size_t) n_def * sizeof(float) : 16);
+    const uint4* const rec = static_cast<uint4*>(rec_mem.p);
+    const float* const rec_dist = static_cast<float*>(dist_mem.p);
+    d2h(ctx, rec_mem.p, pmft->deferred.ptr, (size_t) n_def * sizeof(uint4));
     if (kind == FGPU_PMFT_R12)
     {
-        rec_dist.resize(n_def);
-        d2h(ctx, rec_dist.data(), pmft->deferred_dist.ptr, (size_t) n_def * sizeof(float));
+        d2h(ctx, dist_mem.p, pmft->deferred_dist.ptr, (size_t) n_def * sizeof(float));
     }
     sync(ctx);
-    // a few libm calls per bond: tens of thousands of bonds per frame are worth a handful of host threads
-    std::vector<uint32_t> slot(n_def);
+    // a few libm calls per bond: tens of thousands of bonds per frame (all of them on a lattice) are worth the host's threads
+    HostScratch slot_mem((size_t) n_def * sizeof(uint32_t));
+    uint32_t* const slot = static_cast<uint32_t*>(slot_mem.p);
     uint32_t const kNone = 0xffffffffU;
     auto bin_range = [&](uint32_t lo, uint32_t hi) {
     for (uint32_t r = lo; r < hi; ++r)
@@ -2322,22 +2343,13 @@ bool run_pmft_pass(fgpu_pmft* pmft, Pmft3Args& a, uint64_t cap, const PmftHostIn
             th.join();
         }
     }
-    std::vector<uint32_t> bins;
-    bins.reserve(n_def);
-    for (uint32_t r = 0; r < n_def; ++r)
-    {
-        if (slot[r] != kNone)
-        {
-            bins.push_back(slot[r]);
-        }
-    }
     pmft->deferred_total += n_def;
-    if (!bins.empty())
     {
-        pmft->host_bins.reserve(bins.size());
-        h2d(ctx, pmft->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
-        launch_add_bins(ctx, pmft->host_bins.ptr, (uint32_t) bins.size(), a.hist);
-        sync(ctx); // `bins` goes out of scope
+        // every slot goes up; the kernel skips the bonds that fell outside the axes
+        pmft->host_bins.reserve(n_def);
+        h2d(ctx, pmft->host_bins.ptr, slot, (size_t) n_def * sizeof(uint32_t));
+        launch_add_bins(ctx, pmft->host_bins.ptr, n_def, a.hist);
+        sync(ctx); // the scratch goes back to the cache
     }
     return true;
 }
@@ -2620,14 +2632,16 @@ bool run_bond_order_pass(fgpu_bondorder* bo, BondOrderArgs& a, uint64_t cap, con
     {
         return true;
     }
-    std::vector<uint4> rec(n_def);
-    std::vector<float> rec_z(n_def);
-    d2h(ctx, rec.data(), bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
-    d2h(ctx, rec_z.data(), bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
+    HostScratch rec_mem((size_t) n_def * sizeof(uint4)), z_mem((size_t) n_def * sizeof(float));
+    const uint4* const rec = static_cast<uint4*>(rec_mem.p);
+    const float* const rec_z = static_cast<float*>(z_mem.p);
+    d2h(ctx, rec_mem.p, bo->deferred.ptr, (size_t) n_def * sizeof(uint4));
+    d2h(ctx, z_mem.p, bo->deferred_z.ptr, (size_t) n_def * sizeof(float));
     sync(ctx);
     // two libm calls per bond: a perfect lattice leaves every bond here (each sits on a bin edge), so the loop runs on
     // every host thread (one thread took 0.5 s for the 12 M bonds of a million-particle FCC frame)
-    std::vector<uint32_t> slot(n_def);
+    HostScratch slot_mem((size_t) n_def * sizeof(uint32_t));
+    uint32_t* const slot = static_cast<uint32_t*>(slot_mem.p);
     uint32_t const kNone = 0xffffffffU;
     auto bin_range = [&](uint32_t lo, uint32_t hi) {
         for (uint32_t r = lo; r < hi; ++r)
@@ -2676,23 +2690,11 @@ bool run_bond_order_pass(fgpu_bondorder* bo, BondOrderArgs& a, uint64_t cap, con
             th.join();
         }
     }
-    std::vector<uint32_t> bins;
-    bins.reserve(n_def);
-    for (uint32_t r = 0; r < n_def; ++r)
-    {
-        if (slot[r] != kNone)
-        {
-            bins.push_back(slot[r]);
-        }
-    }
     bo->deferred_total += n_def;
-    if (!bins.empty())
-    {
-        bo->host_bins.reserve(bins.size());
-        h2d(ctx, bo->host_bins.ptr, bins.data(), bins.size() * sizeof(uint32_t));
-        launch_add_bins(ctx, bo->host_bins.ptr, (uint32_t) bins.size(), a.hist);
-        sync(ctx);
-    }
+    bo->host_bins.reserve(n_def);
+    h2d(ctx, bo->host_bins.ptr, slot, (size_t) n_def * sizeof(uint32_t)); // the kernel skips the bonds outside the axes
+    launch_add_bins(ctx, bo->host_bins.ptr, n_def, a.hist);
+    sync(ctx);
     return true;
 }
 

@@ -445,13 +445,17 @@ template<bool ROWS> __global__ void __launch_bounds__(256) k_bond_order(BondOrde
     }
 }
 
-// the host's share: one count per listed bin
+// the host's share: one count per listed bin (0xffffffff: the bond fell outside the axes)
 __global__ void __launch_bounds__(256) k_add_bins(const uint32_t* __restrict__ bins, uint32_t n, uint32_t* __restrict__ hist)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
     {
-        atomicAdd(&hist[bins[i]], 1U);
+        uint32_t const b = bins[i];
+        if (b != 0xffffffffU)
+        {
+            atomicAdd(&hist[b], 1U);
+        }
     }
 }
 
