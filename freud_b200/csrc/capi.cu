@@ -792,7 +792,7 @@ const char* fgpu_version(void)
             cudaDeviceProp prop;
             if (cudaGetDeviceProperties(&prop, 0) == cudaSuccess)
             {
-                char buf[256];
+                char buf[320];
                 std::snprintf(buf, sizeof(buf), " on %s, %d SMs, cc %d.%d", prop.name, prop.multiProcessorCount,
                               prop.major, prop.minor);
                 text += buf;
@@ -1300,7 +1300,6 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
         double r_search = pts->box.is2d ? std::sqrt(kKnnWindowFill * (k + 1) / (M_PI * density))
                                         : std::cbrt(3.0 * kKnnWindowFill * (k + 1) / (4.0 * M_PI * density));
         QueryView qv;
-        uint64_t total = 0;
         bool evals_counted = false; // by the count kernel of the warp-cooperative path
         float r_grid_done = 0.0f;   // grid radius the last warp-cooperative search ran at
         for (int attempt = 0;; ++attempt)
@@ -1511,15 +1510,13 @@ static void knn_query_body(fgpu_points* pts, const float* query_points_host, uin
             sync(ctx);
             if (ctx->h_scalars[2] == 0 || cover_all)
             {
-                total = ctx->h_scalars[3];
-                break;
+                break; // the total (d_scalars[3]) is read back by finish_counts below
             }
             r_search = (double) r_grid * 1.5;
         }
         FGPU_CUDA_CHECK(cudaMemcpyAsync(ctx->d_scalars, ctx->d_scalars + 3, sizeof(unsigned long long),
                                         cudaMemcpyDeviceToDevice, ctx->stream));
         uint64_t const n_bonds = finish_counts(ctx, nl.get(), ctx->row_counts.ptr, ctx->d_scalars);
-        (void) total;
         alloc_bonds(nl.get(), n_bonds);
         if (n_bonds != 0)
         {

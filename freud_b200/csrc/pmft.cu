@@ -468,8 +468,7 @@ template<int KIND, bool ROWS> void launch_pmft3_cluster(fgpu_ctx* ctx, const Pmf
     {
         FGPU_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
     }
-    cudaLaunchConfig_t cfg;
-    std::memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
     cfg.dynamicSmemBytes = dyn;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) k_search2(Search2Args a)
     using WarpMem = typename WarpMemOf<MODE>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t const lt_mask = (1U << lane) - 1U, le_mask = (2U << lane) - 1U;
+    uint32_t const lt_mask = (1U << lane) - 1U;
     size_t const hist_bytes = MODE == S2_RDF ? ((a.axis.bins * sizeof(uint32_t) + 15) / 16) * 16 : 0;
     uint32_t* const sh_hist = reinterpret_cast<uint32_t*>(smem_raw);
     unsigned char* const wbase = smem_raw + hist_bytes + (size_t) warp * warp_mem_bytes(MODE, a.out_cap);
