@@ -246,6 +246,48 @@ def workload_q6(ctx, rank, n):
                 traffic={"search_nl": 19511808 + 218465280, "knn_ylm": 406877952 + 7923968} if n == 1_000_188 else {})
 
 
+def workload_q6_sharded(ctx, rank, world, n, comm):
+    """configs[2] with the ROWS dealt to the ranks (north_star: "per-GPU ... Ql partials are reduced with a single NCCL
+    allreduce"): every rank holds the frame, queries the 12 nearest neighbours of its block of particles
+    (q_index_offset = first index of the block), accumulates their q_lm, and the fp64 system sums are reduced with one
+    ncclAllReduce inside fgpu_steinhardt_compute(comm).  Strong scaling: the value is particles of the ONE frame per
+    second."""
+    from freud_b200 import _capi, data, parallel
+
+    m = max(2, round((n / 4) ** (1.0 / 3.0)))
+    box, pts = data.make_fcc_system(m, sigma_noise=0.05, seed=0)  # the same frame on every rank
+    n = len(pts)
+    lo, hi = parallel.shard_bounds(n, rank, world)
+    dp = _capi.DevicePoints(ctx, box, pts)
+    pin_pts, keep0 = pinned_empty((n, 3), np.float32)
+    pin_pts[:] = pts
+    pin_q, keep1 = pinned_empty((hi - lo, 3), np.float32)
+    pin_q[:] = pts[lo:hi]
+    pin_ql, keep2 = pinned_empty((hi - lo, 1), np.float32)
+    r_window = float(np.cbrt(3.0 * 1.5 * 13.0 / (4.0 * np.pi * (n / float(box.volume)))))
+
+    def rows(d):
+        nl = d.knn_query(pin_q, 12, exclude_ii=True, q_index_offset=lo)
+        return d.steinhardt(nl, [6], want_qlm=False, comm=comm, n_total=n, out={"ql": pin_ql})
+
+    def step_dev():
+        dp.build_cells(r_window)
+        return rows(dp)
+
+    def step_e2e():
+        return rows(_capi.DevicePoints(ctx, box, pin_pts))["ql"]
+
+    block = hi - lo
+    algo = {"search_nl": 16 * (n + block) + 16 * 26 * block + 8 * block, "knn_select": (16 * 26 + 12 + 28 * 12) * block,
+            "steinhardt": 588 * block, "pipeline": 124 * n}
+    return dict(step_dev=step_dev, step_e2e=step_e2e, units=n, unit="particles/s", metric="q6_particles_per_sec",
+                config={"workload": f"Steinhardt Q6 num_neighbors=12 FCC {m}^3x4={n} sigma=0.05, rows (query particles) "
+                                    f"sharded over {world} GPU(s), points replicated, fp64 system q_lm summed with one "
+                                    f"ncclAllReduce"},
+                h2d=12 * n, d2h=4 * block, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={}, dp=dp,
+                rows=rows, block=(lo, hi))
+
+
 def workload_local_density(ctx, rank, n, r_max=2.5, diameter=1.0):
     """SURVEY.md section 8f rank 3, first client: freud.density.LocalDensity(r_max, diameter).compute((box, points)) on
     the C2 system -- ball query of r_max + diameter / 2 = 3 (IMAGE arithmetic), then the fractional count per row."""
@@ -757,6 +799,29 @@ def parity_q6(w):
             "seconds": round(time.perf_counter() - t0, 2)}
 
 
+def parity_q6_rows(w, got):
+    """Sharded Q6: rank 0's rows of q_l and the all-reduced system order parameter against the reference's Steinhardt
+    over the whole frame (oracle/_ref), tolerance 1e-5 relative."""
+    from oracle import ref
+
+    if not ref.available():
+        return {"oracle": "unavailable (oracle/_ref missing)", "bitwise_equal": None}
+    t0 = time.perf_counter()
+    ref.set_num_threads(os.cpu_count())
+    q = ref.Query("aabb", w["box"], w["pts"])
+    want_nl = q.nlist(w["pts"], mode="nearest", num_neighbors=12, exclude_ii=True)
+    res = ref.Steinhardt(6).compute(q, nlist=want_nl)
+    lo, hi = w["block"]
+    want = res["ql"][lo:hi, 0]
+    rel = np.abs(got["ql"][:, 0] - want) / np.maximum(np.abs(want), 1e-30)
+    order_rel = abs(float(got["order"][0]) - float(res["order"][0])) / max(abs(float(res["order"][0])), 1e-30)
+    ok = bool(rel.max() <= 1e-5 and order_rel <= 1e-5)
+    return {"oracle": "reference (oracle/_ref: AABBQuery kNN + Steinhardt::compute over the whole frame)",
+            "rows_checked": [int(lo), int(hi)], "ql_max_rel_diff": float(rel.max()),
+            "system_order_rel_diff_after_allreduce": order_rel, "ql_tolerance_rel": 1e-5, "ql_within_tolerance": ok,
+            "bitwise_equal": None, "seconds": round(time.perf_counter() - t0, 2)}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # e2e through the drop-in classes (freud_b200.locality / density / order): the call a freud user makes
 def api_step(name, w):
@@ -803,9 +868,9 @@ def time_api(step, steps):
 
 
 # ---------------------------------------------------------------------------------------------------------
-WORKLOADS = ["nl", "nl_image", "rdf", "rdf_wrap", "q6", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy",
+WORKLOADS = ["nl", "nl_image", "rdf", "rdf_wrap", "q6", "q6s", "rdf4m", "traj2d", "local_density", "correlation", "pmftxy",
              "pmftxyz", "pmftxyt", "pmftr12", "bond_order"]
-N_DEFAULT = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188,
+N_DEFAULT = {"nl": 1_000_000, "nl_image": 1_000_000, "rdf": 1_000_000, "rdf_wrap": 1_000_000, "q6": 1_000_188, "q6s": 1_000_188,
              "rdf4m": 4_000_000, "traj2d": 1_000_000, "local_density": 1_000_000, "correlation": 1_000_000,
              "pmftxy": 1_000_000, "pmftxyz": 1_000_000, "pmftxyt": 1_000_000, "pmftr12": 1_000_000,
              "bond_order": 1_000_188}
@@ -845,7 +910,8 @@ def main():
         # the N = 1 point of the strong-scaling curve whose N > 1 points are the headline of the multi-GPU runs
         legs = ["nl", "rdf", "q6", "rdf4m"]
     else:
-        legs = ["rdf4m", "traj2d", "nl"]  # configs[3] (strong scaling, the headline), configs[4], NeighborList replicas
+        # configs[3] (strong scaling, the headline), configs[4], NeighborList replicas, configs[2] with its rows sharded
+        legs = ["rdf4m", "traj2d", "nl", "q6s"]
 
     if args.impl == "reference":
         return run_reference_arm(args, rank, world, legs)
@@ -903,6 +969,9 @@ def run_leg(name, args, env, steps, n):
     elif name == "q6":
         w = workload_q6(ctx, rank, n)
         scaling = "weak"
+    elif name == "q6s":
+        w = workload_q6_sharded(ctx, rank, world, n, comm)
+        scaling = "strong"
     elif name == "local_density":
         w = workload_local_density(ctx, rank, n)
         scaling = "weak"
@@ -1061,6 +1130,10 @@ def run_leg(name, args, env, steps, n):
                 parity = parity_rdf_counts(w["rdf"].read(), w, w["bins"])
             elif name == "q6" and rank == 0:
                 parity = parity_q6(w)
+            elif name == "q6s":
+                got = w["rows"](w["dp"])  # collective: every rank takes part in the allreduce
+                if rank == 0:
+                    parity = parity_q6_rows(w, got)
             elif name == "rdf4m":
                 w["step_dev"]()  # every rank takes part in the reduction
                 got = w["read_global"]()
