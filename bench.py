@@ -243,7 +243,7 @@ def workload_q6(ctx, rank, n):
                 h2d=12 * n, d2h=4 * n + 104 * n, algo=algo, keep=[keep0, keep1, keep2], box=box, pts=pts, secondary={},
                 dp=dp, traffic_source=TRAFFIC_SOURCE,
                 # measured DRAM bytes of one launch (ncu, profiles/ncu_r2_summary.md section 3)
-                traffic={"search_nl": 19511808 + 218465280, "knn_ylm": 406877952 + 7923968} if n == 1_000_188 else {})
+                traffic={"search_nl": 19511808 + 218465280, "knn_ylm": 407950592 + 10454016} if n == 1_000_188 else {})
 
 
 def workload_q6_sharded(ctx, rank, world, n, comm):
